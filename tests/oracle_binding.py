@@ -1,0 +1,210 @@
+"""ctypes binding of the TEST ORACLE (oracle/libsr_oracle.so).  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libsr_oracle.so")
+
+import softrender_b200 as sr  # noqa: E402  (shim at the repo root; scene types only)
+from softrender_b200.scenes import Uniforms, Viewport  # noqa: E402
+
+u32p = ctypes.POINTER(ctypes.c_uint32)
+u64p = ctypes.POINTER(ctypes.c_uint64)
+f32p = ctypes.POINTER(ctypes.c_float)
+u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class SoFramebuffer(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("color", f32p), ("depth", f32p),
+                ("stencil", u8p), ("winner", u32p)]
+
+
+class SoTexture(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("rgba", u8p)]
+
+
+class SoRasterState(ctypes.Structure):
+    _fields_ = [("cull_faces", ctypes.c_uint32), ("blend", ctypes.c_uint32), ("antialiased_lines", ctypes.c_uint32),
+                ("tile_width", ctypes.c_uint32), ("tile_height", ctypes.c_uint32),
+                ("stencil_test", ctypes.c_uint32), ("stencil_op", ctypes.c_uint32)]
+
+
+def build_oracle() -> str:
+    src = os.path.join(ORACLE_DIR, "sr_oracle.cpp")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build_oracle())
+        L.so_draw_create.restype = ctypes.c_void_p
+        L.so_draw_create.argtypes = [ctypes.c_int, u32p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32]
+        L.so_draw_destroy.argtypes = [ctypes.c_void_p]
+        L.so_draw_vertex_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Uniforms), f32p, ctypes.c_uint64,
+                                         ctypes.c_uint32, ctypes.c_int]
+        L.so_draw_vertex_run_to_fragment.argtypes = [ctypes.c_void_p, ctypes.POINTER(Viewport), ctypes.c_int,
+                                                     ctypes.POINTER(Uniforms), f32p, ctypes.c_uint64, ctypes.c_uint32,
+                                                     ctypes.c_int]
+        L.so_draw_set_vertices.argtypes = [ctypes.c_void_p, f32p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
+        L.so_draw_set_generated.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, ctypes.c_uint64, ctypes.c_uint32]
+        L.so_draw_geometry_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Uniforms), ctypes.c_int]
+        L.so_draw_finish.argtypes = [ctypes.c_void_p, ctypes.POINTER(Viewport), ctypes.c_int]
+        L.so_draw_fragment_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(SoFramebuffer), ctypes.POINTER(SoRasterState),
+                                           ctypes.c_int, ctypes.POINTER(Uniforms), ctypes.POINTER(SoTexture), ctypes.c_int]
+        L.so_draw_count.restype = ctypes.c_uint64
+        L.so_draw_count.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.so_draw_data.restype = f32p
+        L.so_draw_data.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.so_draw_nk.restype = ctypes.c_uint32
+        L.so_draw_nk.argtypes = [ctypes.c_void_p]
+        L.so_tiles.restype = ctypes.c_uint64
+        L.so_tiles.argtypes = [ctypes.c_uint32] * 4 + [u32p, ctypes.c_uint64]
+        L.so_draw_bins.restype = ctypes.c_uint64
+        L.so_draw_bins.argtypes = [ctypes.c_void_p] + [ctypes.c_uint32] * 5 + [u64p, u32p]
+        L.so_coordinate_index.restype = ctypes.c_uint64
+        L.so_coordinate_index.argtypes = [ctypes.c_uint32] * 3
+        L.so_stencil_test.restype = ctypes.c_int
+        L.so_stencil_test.argtypes = [ctypes.c_uint32, ctypes.c_uint8, ctypes.c_uint8]
+        L.so_stencil_op.restype = ctypes.c_uint8
+        L.so_stencil_op.argtypes = [ctypes.c_uint32, ctypes.c_uint8, ctypes.c_uint8]
+        L.so_depth_far.restype = ctypes.c_float
+        L.so_framebuffer_clear.argtypes = [ctypes.POINTER(SoFramebuffer), f32p]
+        _lib = L
+    return _lib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(f32p)
+
+
+@dataclass
+class OracleFramebuffer:
+    """RenderBuffer<ColorDepth[Stencil]Attachments<RGBAf32Color, f32[, u8]>> held in numpy planes."""
+    width: int
+    height: int
+    stencil_bits: int = 0
+    color: np.ndarray = field(init=False)
+    depth: np.ndarray = field(init=False)
+    stencil: np.ndarray | None = field(init=False)
+    winner: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        n = self.width * self.height
+        self.color = np.zeros((n, 4), np.float32)
+        self.depth = np.full(n, lib().so_depth_far(), np.float32)
+        self.stencil = np.zeros(n, np.uint8) if self.stencil_bits else None
+        self.winner = np.zeros(n, np.uint32)
+
+    def struct(self) -> SoFramebuffer:
+        return SoFramebuffer(self.width, self.height, _fp(self.color), _fp(self.depth),
+                             self.stencil.ctypes.data_as(u8p) if self.stencil is not None else None,
+                             self.winner.ctypes.data_as(u32p))
+
+    def clear(self, color):
+        c = np.asarray(color, np.float32)
+        s = self.struct()
+        lib().so_framebuffer_clear(ctypes.byref(s), _fp(c))
+
+
+class OracleDraw:
+    """The reference's VertexShader -> GeometryShader -> FragmentShader chain for one render_mesh call."""
+
+    def __init__(self, primitive: int, indices: np.ndarray, stencil_value=None):
+        self.indices = np.ascontiguousarray(indices, np.uint32)
+        self.h = lib().so_draw_create(primitive, self.indices.ctypes.data_as(u32p), len(self.indices),
+                                      0 if stencil_value is None else 1, 0 if stencil_value is None else stencil_value)
+        if not self.h:
+            raise ValueError("render_mesh: indices.len() % num_vertices != 0")
+        self.cull = sr.CULL_NONE
+        self.blend = sr.BLEND_REPLACE
+        self.aa = False
+        self.tile = None  # None -> one frame-sized tile (canonical); (128,128) is the reference default
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().so_draw_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _ck(rc):
+        if rc != 0:
+            raise RuntimeError(f"oracle status {rc}")
+
+    def vertex_run(self, vs, uniforms, vertices: np.ndarray, nthreads=1):
+        v = np.ascontiguousarray(vertices, np.float32)
+        self._ck(lib().so_draw_vertex_run(self.h, vs, ctypes.byref(uniforms), _fp(v), v.shape[0], v.shape[1], nthreads))
+        return self
+
+    def vertex_run_to_fragment(self, viewport, vs, uniforms, vertices: np.ndarray, nthreads=1):
+        v = np.ascontiguousarray(vertices, np.float32)
+        self._ck(lib().so_draw_vertex_run_to_fragment(self.h, ctypes.byref(viewport), vs, ctypes.byref(uniforms), _fp(v),
+                                                      v.shape[0], v.shape[1], nthreads))
+        return self
+
+    def set_vertices(self, verts: np.ndarray, space: int):
+        v = np.ascontiguousarray(verts, np.float32)
+        self._ck(lib().so_draw_set_vertices(self.h, _fp(v), v.shape[0], v.shape[1] - 4, space))
+        return self
+
+    def set_generated(self, which: int, verts: np.ndarray):
+        v = np.ascontiguousarray(verts, np.float32)
+        self._ck(lib().so_draw_set_generated(self.h, which, _fp(v), v.shape[0], v.shape[1] - 4))
+        return self
+
+    def geometry_run(self, gs, uniforms=None, nthreads=1):
+        self._ck(lib().so_draw_geometry_run(self.h, gs, ctypes.byref(uniforms) if uniforms is not None else None, nthreads))
+        return self
+
+    def clip_primitives(self, nthreads=1):
+        return self.geometry_run(sr.GS_CLIP, None, nthreads)
+
+    def finish(self, viewport, nthreads=1):
+        self._ck(lib().so_draw_finish(self.h, ctypes.byref(viewport), nthreads))
+        return self
+
+    def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1):
+        tw, th = self.tile if self.tile else (max(fb.width, 1), max(fb.height, 1))
+        st = SoRasterState(self.cull, self.blend, 1 if self.aa else 0, tw, th, stencil_test, stencil_op)
+        s = fb.struct()
+        tex = None
+        if texture is not None:
+            t = np.ascontiguousarray(texture, np.uint8)
+            tex = SoTexture(t.shape[1], t.shape[0], t.ctypes.data_as(u8p))
+        self._ck(lib().so_draw_fragment_run(self.h, ctypes.byref(s), ctypes.byref(st), fs, ctypes.byref(uniforms),
+                                            ctypes.byref(tex) if tex is not None else None, nthreads))
+        return self
+
+    def data(self, which: int) -> np.ndarray:
+        n = lib().so_draw_count(self.h, which)
+        S = 4 + lib().so_draw_nk(self.h)
+        if n == 0:
+            return np.zeros((0, S), np.float32)
+        return np.ctypeslib.as_array(lib().so_draw_data(self.h, which), shape=(n, S)).copy()
+
+    def bins(self, width, height, tw, th, cull=0):
+        ntiles = ((width + tw - 1) // tw) * ((height + th - 1) // th)
+        offsets = np.zeros(ntiles + 1, np.uint64)
+        total = lib().so_draw_bins(self.h, width, height, tw, th, cull, offsets.ctypes.data_as(u64p), None)
+        ids = np.zeros(max(total, 1), np.uint32)
+        lib().so_draw_bins(self.h, width, height, tw, th, cull, offsets.ctypes.data_as(u64p), ids.ctypes.data_as(u32p))
+        return offsets, ids[:total]
+
+
+def tiles(width, height, tw=128, th=128) -> np.ndarray:
+    n = lib().so_tiles(width, height, tw, th, None, 0)
+    out = np.zeros((max(n, 1), 4), np.uint32)
+    lib().so_tiles(width, height, tw, th, out.ctypes.data_as(u32p), n)
+    return out[:n]
