@@ -1,0 +1,170 @@
+/*
+ * softrender_b200.h -- C ABI of libsoftrender_b200.so, the B200-native (sm_100a CUDA)
+ * implementation of the draw hot path of novacrazy/rust-softrender.
+ *
+ * The reference has no FFI/plugin interface: its "operator API" is the typed Rust
+ * builder (Pipeline -> VertexShader -> GeometryShader -> FragmentShader).  Each entry
+ * point below is what a Rust `-sys` crate would bind so that the body of the cited
+ * builder method becomes one call into this library (INTEGRATION.md shows the binding).
+ * Paths are relative to the reference repository root.
+ *
+ * Conventions
+ *  - every function returns an sr_status (0 = SR_OK); sr_last_error() gives the text of the
+ *    last failure on the calling thread.  Nothing aborts or throws across the boundary
+ *    (the reference panics on contract violations).
+ *  - handles are opaque, freed by the matching *_destroy.  Buffers passed in are copied
+ *    before the call returns; downloads write into caller memory.
+ *  - a context is externally synchronised (one caller thread at a time), matching the
+ *    reference's `&mut Pipeline`.
+ *  - draw calls are enqueued on the context's CUDA stream; the framebuffer contents are
+ *    defined for every later call on the same context (downloads synchronise), which is
+ *    the observable behaviour of the reference's `pool.scoped` joins.
+ *  - there is NO CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef SOFTRENDER_B200_H
+#define SOFTRENDER_B200_H
+
+#include "softrender_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sr_context sr_context;
+typedef struct sr_framebuffer sr_framebuffer;
+typedef struct sr_mesh sr_mesh;
+typedef struct sr_texture sr_texture;
+typedef struct sr_pipeline sr_pipeline;
+typedef struct sr_draw sr_draw;
+
+/* ---- library ----------------------------------------------------------------------- */
+const char *sr_last_error(void);
+int sr_version(void);
+/* internal GPU tile (pixels).  Results do not depend on it. */
+int sr_tile_size(uint32_t *width, uint32_t *height);
+
+/* ---- context: owns the device, stream and scratch memory.  Replaces the thread pool
+ *      Pipeline::new creates (src/pipeline/mod.rs:110-117). ---------------------------- */
+int sr_context_create(int device_ordinal, sr_context **out);
+int sr_context_destroy(sr_context *);
+int sr_context_synchronize(sr_context *);
+/* the context's cudaStream_t (for CUDA-event timing on the launching stream) */
+void *sr_context_stream(sr_context *);
+/* sort-first tile sharding: this context rasterises only the GPU tiles with
+ * tile_index % world == rank (geometry stages still run for the whole mesh). */
+int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
+/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+int sr_context_launch_count(sr_context *, uint64_t *out);
+
+/* ---- framebuffer: RenderBuffer<ColorDepth[Stencil]Attachments<RGBAf32Color,f32[,u8]>>
+ *      (src/framebuffer/renderbuffer/mod.rs:34-133) ------------------------------------ */
+/* RenderBuffer::with_dimensions (renderbuffer/mod.rs:58-63): colour = Color::empty() (zeros),
+ * depth = Depth::far() = f32::MIN, stencil = 0. */
+int sr_framebuffer_create(sr_context *, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out);
+int sr_framebuffer_destroy(sr_framebuffer *);
+/* RenderBuffer::clear (renderbuffer/mod.rs:126-133) */
+int sr_framebuffer_clear(sr_framebuffer *, const float color[4]);
+/* HasDimensions::dimensions (src/geometry/dimension.rs:29) */
+int sr_framebuffer_dimensions(const sr_framebuffer *, uint32_t *width, uint32_t *height);
+/* read-back of the RenderBuffer's Vec<{color,depth}>: row-major, index = x + y*width
+ * (src/geometry/coordinate.rs:47-51), 20 B/pixel {r,g,b,a,depth}. nbytes must be width*height*20. */
+int sr_framebuffer_download(sr_framebuffer *, void *dst, size_t nbytes);
+/* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL */
+int sr_framebuffer_download_planes(sr_framebuffer *, float *color, float *depth, uint8_t *stencil);
+int sr_framebuffer_upload_planes(sr_framebuffer *, const float *color, const float *depth, const uint8_t *stencil);
+/* checked accessor: PixelRead::pixel_ref / FramebufferAccessor (src/pixels/mod.rs:56-63,
+ * src/framebuffer/accessor.rs:4-18); out-of-range -> SR_ERR_INVALID_PIXEL_COORDINATE */
+int sr_framebuffer_get_pixel(sr_framebuffer *, uint32_t x, uint32_t y, float rgba[4], float *depth, uint8_t *stencil);
+/* parity introspection: per pixel, 1 + canonical index of the last primitive of the most recent
+ * draw that wrote it (0 = untouched by that draw).  Enable before drawing. */
+int sr_framebuffer_enable_winner(sr_framebuffer *, int enable);
+int sr_framebuffer_download_winner(sr_framebuffer *, uint32_t *dst);
+/* device address of the AoS pixel store (for zero-copy consumers / collectives) */
+void *sr_framebuffer_device_ptr(sr_framebuffer *);
+
+/* ---- multi-GPU composite over NVLink peer memory -------------------------------------
+ * One process per GPU.  Rank 0 exports its framebuffer; the other ranks open it and make it
+ * their write-back target, so the tile rasteriser stores finished tiles straight into rank
+ * 0's HBM (no staging buffer, no separate collective). */
+int sr_framebuffer_ipc_export(sr_framebuffer *, void *handle64 /* 64 bytes */);
+int sr_framebuffer_ipc_open(sr_context *, const void *handle64, uint32_t width, uint32_t height, uint32_t format,
+                            sr_framebuffer **out);
+
+/* ---- mesh: Arc<Mesh<V>> (src/mesh.rs:12-20,61-63) ----------------------------------------
+ * vertices: AoS, `vin_floats` f32 per vertex, position.xyz first (SimpleVertex{position,data});
+ * indices: u32 (index_bytes 4) or usize/u64 (index_bytes 8).  Converted to SoA planes in HBM. */
+int sr_mesh_create(sr_context *, const float *vertices, uint64_t nverts, uint32_t vin_floats,
+                   const void *indices, uint64_t nindices, uint32_t index_bytes, sr_mesh **out);
+int sr_mesh_destroy(sr_mesh *);
+
+/* ---- texture: RGBA8 image sampled by the textured fragment shader
+ *      (full_example/src/texture.rs:25-84) ----------------------------------------------- */
+int sr_texture_create(sr_context *, const uint8_t *rgba, uint32_t width, uint32_t height, sr_texture **out);
+int sr_texture_destroy(sr_texture *);
+
+/* ---- pipeline: Pipeline<U, F, S> (src/pipeline/mod.rs:60-140) ------------------------------ */
+/* Pipeline::from_framebuffer (mod.rs:120); errors if width or height is 0 (asserts mod.rs:129-130) */
+int sr_pipeline_create(sr_context *, sr_framebuffer *, const sr_uniforms *, sr_pipeline **out);
+int sr_pipeline_destroy(sr_pipeline *);
+/* PipelineObject::uniforms_mut (mod.rs:45) */
+int sr_pipeline_set_uniforms(sr_pipeline *, const sr_uniforms *);
+/* Pipeline::with_framebuffer (mod.rs:126-140): also RESETS the stencil config to default */
+int sr_pipeline_set_framebuffer(sr_pipeline *, sr_framebuffer *);
+/* PipelineObject::stencil_config_mut with GenericStencilConfig{op,test} (src/stencil.rs:177-199) */
+int sr_pipeline_set_stencil_config(sr_pipeline *, uint32_t test, uint32_t op);
+int sr_pipeline_bind_texture(sr_pipeline *, sr_texture *);
+
+/* ---- draw: the VertexShader -> GeometryShader -> FragmentShader chain ---------------------- */
+/* Pipeline::render_mesh (mod.rs:146-157); errors if nindices % num_vertices(primitive) != 0 (assert mod.rs:148).
+ * has_stencil_value=0 is `None` (value defaults to 0). */
+int sr_render_mesh(sr_pipeline *, sr_mesh *, uint32_t primitive, int has_stencil_value, uint32_t stencil_value,
+                   sr_draw **out);
+/* VertexShader::run (src/pipeline/stages/vertex.rs:87-120) */
+int sr_vertex_run(sr_draw *, uint32_t vertex_shader);
+/* VertexShader::run_to_fragment (vertex.rs:123-160) */
+int sr_vertex_run_to_fragment(sr_draw *, const sr_viewport *, uint32_t vertex_shader);
+/* GeometryShader::run (src/pipeline/stages/geometry.rs:132-258) with a registered shader */
+int sr_geometry_run(sr_draw *, uint32_t geometry_shader);
+/* GeometryShader::clip_primitives (geometry.rs:261-336) */
+int sr_geometry_clip_primitives(sr_draw *);
+/* GeometryShader::finish (geometry.rs:60-129) */
+int sr_geometry_finish(sr_draw *, const sr_viewport *);
+/* {Vertex,Geometry,Fragment}Shader::duplicate (vertex.rs:44, geometry.rs:43, fragment.rs:122) */
+int sr_draw_duplicate(sr_draw *, sr_draw **out);
+/* FragmentShader::cull_faces / set_cull_faces (src/pipeline/stages/fragment.rs:82-90) */
+int sr_fragment_set_cull_faces(sr_draw *, uint32_t winding);
+/* FragmentShader::antialiased_lines (fragment.rs:96-104) */
+int sr_fragment_set_antialiased_lines(sr_draw *, int enable);
+/* FragmentShader::tile_size (fragment.rs:107-116).  Accepted for API parity; the GPU tiles pixels
+ * disjointly, which equals the reference with one frame-sized tile (DESIGN.md "canonical semantics"). */
+int sr_fragment_set_tile_size(sr_draw *, uint32_t width, uint32_t height);
+/* FragmentShader::with_blend / with_default_blend (fragment.rs:140-160) with a registered blend */
+int sr_fragment_set_blend(sr_draw *, uint32_t blend);
+/* FragmentShader::run (fragment.rs:168-319) */
+int sr_fragment_run(sr_draw *, uint32_t fragment_shader);
+int sr_draw_destroy(sr_draw *);
+
+/* ---- parity-test injection and introspection ------------------------------------------------ */
+/* start a draw from already-shaded vertices (records of 4+nk floats) in clip (space=0) or screen
+ * (space=1) space; the state VertexShader::run / GeometryShader::finish would have produced. */
+int sr_draw_from_vertices(sr_pipeline *, uint32_t primitive, const float *verts, uint64_t nverts, uint32_t nk,
+                          int space, const uint32_t *indices, uint64_t nindices, int has_stencil_value,
+                          uint32_t stencil_value, sr_draw **out);
+/* replace one generated-primitive stream (which: 1 points, 2 lines, 3 triangles) */
+int sr_draw_set_generated(sr_draw *, int which, const float *verts, uint64_t nverts, uint32_t nk);
+/* which: 0 indexed vertices, 1 points, 2 lines, 3 triangles (vertex counts; records of 4+nk floats) */
+int sr_draw_count(sr_draw *, int which, uint64_t *nverts, uint32_t *nk);
+int sr_draw_download(sr_draw *, int which, float *dst, uint64_t capacity_floats);
+/* for generated triangles: position of each kept triangle in the reference's literal output
+ * sequence (the clipper's zero-area triangles may be dropped) */
+int sr_draw_download_sequence(sr_draw *, uint32_t *dst, uint64_t capacity);
+/* per-GPU-tile triangle lists of a finished (screen-space) draw: CSR offsets[ntiles+1] + ids
+ * (canonical triangle index, ascending per tile).  ids may be NULL to query *total. */
+int sr_draw_bins(sr_draw *, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total);
+/* device time of the stages of the most recent fragment_run of this context */
+int sr_context_stage_times(sr_context *, sr_stage_times *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTRENDER_B200_H */

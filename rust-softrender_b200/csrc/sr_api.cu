@@ -1,0 +1,1165 @@
+// sr_api.cu -- host side of libsoftrender_b200.so: handle objects, stage orchestration, the C ABI
+// declared in include/softrender_b200.h.  No CPU fallback exists: every entry point drives CUDA.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "sr_common.cuh"
+#include "sr_shaders.cuh"
+#include "sr_stages.cuh"
+#include "sr_raster.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int sr_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define SR_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) return sr_fail(SR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define SR_TRY(expr)               \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != SR_OK) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    sr_context *ctx = nullptr;
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    ~DevBuf();
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+using Buf = std::shared_ptr<DevBuf>;
+
+struct sr_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::multimap<size_t, void *> free_list;  // stream-ordered reuse of scratch allocations
+    uint32_t shard_rank = 0, shard_world = 1;
+    uint64_t launches = 0;
+    cudaEvent_t ev[6] = {};  // vertex begin/end, geometry end, bin end, raster end, spare
+    bool ev_valid[6] = {};
+    sr_stage_times times = {};
+    int alloc(size_t bytes, Buf *out);
+    void release(void *p, size_t bytes) { free_list.emplace(bytes, p); }
+};
+
+DevBuf::~DevBuf() {
+    if (ptr && ctx) ctx->release(ptr, bytes);
+}
+
+int sr_context::alloc(size_t bytes, Buf *out) {
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 511) & ~(size_t)511;
+    void *p = nullptr;
+    auto it = free_list.lower_bound(bytes);
+    if (it != free_list.end() && it->first <= bytes + bytes / 4 + 4096) {
+        p = it->second;
+        bytes = it->first;
+        free_list.erase(it);
+    } else {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            // drop the cache and retry once
+            for (auto &kv : free_list) cudaFree(kv.second);
+            free_list.clear();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) return sr_fail(SR_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    auto b = std::make_shared<DevBuf>();
+    b->ctx = this;
+    b->ptr = p;
+    b->bytes = bytes;
+    *out = b;
+    return SR_OK;
+}
+
+#define SR_LAUNCH(ctx, kernel, grid, block, smem, ...)                                                    \
+    do {                                                                                                  \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                  \
+        (ctx)->launches++;                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                             \
+        if (e__ != cudaSuccess) return sr_fail(SR_ERR_CUDA, "launch %s failed: %s", #kernel, cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+struct sr_framebuffer {
+    sr_context *ctx;
+    uint32_t width, height, format;
+    uint32_t ntx, nty;
+    Buf aos_buf, stencil_buf, winner_buf;
+    float *aos = nullptr;       // device (possibly peer) pointer
+    bool is_peer = false;       // opened through cudaIpcOpenMemHandle
+    bool pending_clear = false;
+    float clear[4] = {0, 0, 0, 0};
+    bool winner_enabled = false;
+    SrFbView view() const {
+        SrFbView v;
+        v.aos = aos;
+        v.stencil = stencil_buf ? stencil_buf->as<uint8_t>() : nullptr;
+        v.winner = (winner_enabled && winner_buf) ? winner_buf->as<uint32_t>() : nullptr;
+        v.width = width; v.height = height; v.ntx = ntx; v.nty = nty;
+        v.pending_clear = pending_clear ? 1u : 0u;
+        for (int i = 0; i < 4; ++i) v.clear[i] = clear[i];
+        return v;
+    }
+};
+
+struct sr_mesh {
+    sr_context *ctx;
+    Buf planes, indices;
+    uint64_t nverts = 0, pstride = 0, nindices = 0;
+    uint32_t vin = 0;
+};
+
+struct sr_texture {
+    sr_context *ctx;
+    Buf rgba;
+    uint32_t width, height;
+};
+
+struct sr_pipeline {
+    sr_context *ctx;
+    sr_framebuffer *fb;
+    sr_uniforms uniforms;
+    uint32_t stencil_test = SR_STENCIL_ALWAYS, stencil_op = SR_STENCIL_KEEP;
+    sr_texture *texture = nullptr;
+};
+
+struct VertexStream {  // one flat Vec of vertices in HBM: position plane + attribute planes
+    Buf pos, attr;
+    uint64_t n = 0, stride = 0;
+    SrVertexSet set() const {
+        SrVertexSet s;
+        s.pos = pos ? pos->as<float4>() : nullptr;
+        s.attr = attr ? attr->as<float4>() : nullptr;
+        s.stride = stride;
+        return s;
+    }
+};
+
+enum DrawStage { STAGE_VERTEX = 0, STAGE_GEOMETRY = 1, STAGE_FRAGMENT = 2 };
+
+struct sr_draw {
+    sr_pipeline *pipeline;
+    uint32_t primitive;
+    bool has_stencil_value = false;
+    uint32_t stencil_value = 0;
+    // the mesh (Arc<Mesh<V>>): input planes for the vertex stage, indices for every stage
+    Buf mesh_planes, indices;
+    uint64_t mesh_nverts = 0, mesh_pstride = 0, nindices = 0;
+    uint32_t vin = 0;
+    DrawStage stage = STAGE_VERTEX;
+    uint32_t nk = 0;
+    bool have_indexed = false;  // indexed_vertices: Option<Vec<..>>
+    VertexStream indexed;
+    VertexStream gen[3];        // generated points, lines, tris
+    Buf tri_seq;                // literal sequence number of each generated triangle (null = identity)
+    uint32_t tri_literal_total = 0;
+    // FragmentShader builder state (fragment.rs:45-56)
+    uint32_t cull = SR_CULL_NONE, blend = SR_BLEND_REPLACE, aa_lines = 0;
+    uint32_t tile_w = 128, tile_h = 128;  // DEFAULT_TILE_SIZE (fragment.rs:29); accepted, not used
+};
+
+static uint32_t nplanes_of(uint32_t nk) { return (nk + 3) / 4; }
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+static void record(sr_context *c, int i) {
+    if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
+    cudaEventRecord(c->ev[i], c->stream);
+    c->ev_valid[i] = true;
+}
+
+static int alloc_stream(sr_context *c, uint64_t n, uint32_t nk, VertexStream *out) {
+    out->n = n;
+    out->stride = (n + 3) & ~(uint64_t)3;
+    if (out->stride == 0) out->stride = 4;
+    SR_TRY(c->alloc(out->stride * sizeof(float4), &out->pos));
+    SR_TRY(c->alloc(out->stride * sizeof(float4) * std::max(1u, nplanes_of(nk)), &out->attr));
+    return SR_OK;
+}
+
+static void fill_vs_const(const sr_pipeline *p, const sr_viewport *vp, SrVsConst *c) {
+    memset(c, 0, sizeof(*c));
+    c->u = p->uniforms;
+    sr_mat_mat(p->uniforms.projection, p->uniforms.view, c->pv);  // projection * view
+    sr_mat_mat(c->pv, p->uniforms.model, c->pvm);                 // (projection * view) * model
+    c->normalize = vp ? 1 : 0;
+    if (vp) {
+        // viewport matrix of ClipVertex::normalize (clipvertex.rs:104-112), column-major
+        const float left = vp->x, bottom = vp->y;
+        const float right = left + vp->width, top = bottom + vp->height;
+        c->vpm[0 * 4 + 0] = (right - left) / 2.0f;
+        c->vpm[3 * 4 + 0] = (right + left) / 2.0f;
+        c->vpm[1 * 4 + 1] = (top - bottom) / -2.0f;
+        c->vpm[3 * 4 + 1] = (top + bottom) / 2.0f;
+        c->vpm[2 * 4 + 2] = (vp->far_ - vp->near_) / -2.0f;
+        c->vpm[3 * 4 + 2] = (vp->far_ + vp->near_) / -2.0f;
+        c->vpm[3 * 4 + 3] = 1.0f;
+    }
+}
+
+static int exclusive_scan(sr_context *c, const uint32_t *in, uint64_t n, uint32_t *out, uint32_t *total_host) {
+    const uint32_t nblocks = std::max(1u, ceil_div(n, SR_SCAN_BLOCK));
+    Buf sums, total;
+    SR_TRY(c->alloc((size_t)nblocks * 4, &sums));
+    SR_TRY(c->alloc(4, &total));
+    SR_LAUNCH(c, k_scan_reduce, nblocks, SR_SCAN_THREADS, 0, in, n, sums->as<uint32_t>());
+    SR_LAUNCH(c, k_scan_sums, 1, SR_SCAN_THREADS, 0, sums->as<uint32_t>(), nblocks, total->as<uint32_t>());
+    SR_LAUNCH(c, k_scan_apply, nblocks, SR_SCAN_THREADS, 0, in, n, sums->as<uint32_t>(), out);
+    SR_CUDA(cudaMemcpyAsync(total_host, total->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+
+static int materialize_clear(sr_framebuffer *fb) {
+    if (!fb->pending_clear) return SR_OK;
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    SrFbView v = fb->view();
+    if (fb->winner_buf) v.winner = fb->winner_buf->as<uint32_t>();
+    SR_LAUNCH(fb->ctx, k_fb_fill, ceil_div(n, 256), 256, 0, v);
+    fb->pending_clear = false;
+    return SR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bins
+// ---------------------------------------------------------------------------------------------------------
+struct Bins {
+    Buf rects, off, list;
+    uint32_t total = 0;
+};
+
+static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
+    SR_CUDA(cudaMemsetAsync(b->off->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
+    SR_TRY(c->alloc(4, &b->rects));
+    SR_TRY(c->alloc(4, &b->list));
+    b->total = 0;
+    return SR_OK;
+}
+
+template <int NV>
+static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSource &src, uint32_t nprims, uint32_t cull, Bins *b) {
+    const uint32_t ntiles = fb->ntx * fb->nty;
+    if (nprims == 0) return zero_offsets(c, ntiles, b);
+    Buf count;
+    SR_TRY(c->alloc((size_t)nprims * 4, &b->rects));
+    SR_TRY(c->alloc((size_t)ntiles * 4, &count));
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
+    SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)ntiles * 4, c->stream));
+    SrBinParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = src;
+    p.nprims = nprims;
+    p.cull = cull;
+    p.width = fb->width; p.height = fb->height; p.ntx = fb->ntx; p.nty = fb->nty;
+    p.shard_rank = c->shard_rank; p.shard_world = c->shard_world;
+    p.rects = b->rects->as<uint32_t>();
+    p.tile_count = count->as<uint32_t>();
+    const uint32_t grid = ceil_div(nprims, 256);
+    SR_LAUNCH(c, k_bin_setup<NV>, grid, 256, 0, p);
+    SR_LAUNCH(c, k_tile_offsets, 1, 256, 0, count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), count->as<uint32_t>());
+    SR_CUDA(cudaMemcpyAsync(&b->total, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    SR_TRY(c->alloc((size_t)std::max(b->total, 1u) * 4, &b->list));
+    p.tile_off = b->off->as<uint32_t>();
+    p.list = b->list->as<uint32_t>();
+    SR_LAUNCH(c, k_bin_fill, grid, 256, 0, p);
+    return SR_OK;
+}
+
+static SrPrimSource prim_source(const sr_draw *d, uint32_t kind /*1 point,2 line,3 tri*/) {
+    SrPrimSource s;
+    memset(&s, 0, sizeof(s));
+    s.nk = d->nk;
+    s.nplanes = nplanes_of(d->nk);
+    if (d->have_indexed && d->primitive == kind) {
+        s.indices = d->indices->as<uint32_t>();
+        s.vs0 = d->indexed.set();
+        s.n0 = (uint32_t)(d->nindices / kind);
+    }
+    const VertexStream &g = d->gen[kind - 1];
+    s.vs1 = g.set();
+    s.n1 = (uint32_t)(g.n / kind);
+    s.seq1 = (kind == 3 && d->tri_seq) ? d->tri_seq->as<uint32_t>() : nullptr;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel dispatch by registered shader id
+// ---------------------------------------------------------------------------------------------------------
+template <int FS>
+static int launch_tiles(sr_context *c, bool ordered, uint32_t ntiles_owned, const SrTileParams &p) {
+    if (ordered) {
+        SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
+        SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
+    } else {
+        const size_t smem = (size_t)SR_TILE_PIXELS * 8;
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_RASTER_THREADS, smem, p);
+    }
+    return SR_OK;
+}
+static int launch_tiles_fs(sr_context *c, uint32_t fs, bool ordered, uint32_t ntiles_owned, const SrTileParams &p) {
+    switch (fs) {
+        case SR_FS_FLAT: return launch_tiles<SR_FS_FLAT>(c, ordered, ntiles_owned, p);
+        case SR_FS_SUZANNE: return launch_tiles<SR_FS_SUZANNE>(c, ordered, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE: return launch_tiles<SR_FS_FULL_EXAMPLE>(c, ordered, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_tiles<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ordered, ntiles_owned, p);
+        case SR_FS_GREEN: return launch_tiles<SR_FS_GREEN>(c, ordered, ntiles_owned, p);
+        case SR_FS_DISCARD_CHECKER: return launch_tiles<SR_FS_DISCARD_CHECKER>(c, ordered, ntiles_owned, p);
+    }
+    return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown fragment shader %u", fs);
+}
+static int fs_nk(uint32_t fs) {
+    switch (fs) {
+        case SR_FS_FLAT: return SrFsInfo<SR_FS_FLAT>::NK;
+        case SR_FS_SUZANNE: return SrFsInfo<SR_FS_SUZANNE>::NK;
+        case SR_FS_FULL_EXAMPLE: return SrFsInfo<SR_FS_FULL_EXAMPLE>::NK;
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED>::NK;
+        case SR_FS_GREEN: return SrFsInfo<SR_FS_GREEN>::NK;
+        case SR_FS_DISCARD_CHECKER: return SrFsInfo<SR_FS_DISCARD_CHECKER>::NK;
+    }
+    return -1;
+}
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+const char *sr_last_error(void) { return g_last_error.c_str(); }
+int sr_version(void) { return 100; }
+int sr_tile_size(uint32_t *w, uint32_t *h) {
+    if (w) *w = SR_TILE_W;
+    if (h) *h = SR_TILE_H;
+    return SR_OK;
+}
+
+// ---- context ---------------------------------------------------------------------------------------------
+int sr_context_create(int device, sr_context **out) {
+    if (!out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "out is null");
+    int count = 0;
+    SR_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return sr_fail(SR_ERR_INVALID_ARGUMENT, "device %d of %d", device, count);
+    SR_CUDA(cudaSetDevice(device));
+    auto *c = new sr_context();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return sr_fail(SR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return SR_OK;
+}
+int sr_context_destroy(sr_context *c) {
+    if (!c) return SR_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->free_list) cudaFree(kv.second);
+    c->free_list.clear();
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return SR_OK;
+}
+int sr_context_synchronize(sr_context *c) {
+    if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null context");
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+void *sr_context_stream(sr_context *c) { return c ? (void *)c->stream : nullptr; }
+int sr_context_set_tile_shard(sr_context *c, uint32_t rank, uint32_t world) {
+    if (!c || world == 0 || rank >= world) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad shard %u/%u", rank, world);
+    c->shard_rank = rank;
+    c->shard_world = world;
+    return SR_OK;
+}
+int sr_context_launch_count(sr_context *c, uint64_t *out) {
+    if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    *out = c->launches;
+    return SR_OK;
+}
+int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
+    if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    sr_stage_times t = {};
+    auto span = [&](int a, int b, float *dst) {
+        if (c->ev_valid[a] && c->ev_valid[b]) cudaEventElapsedTime(dst, c->ev[a], c->ev[b]);
+    };
+    span(0, 1, &t.vertex_ms);
+    span(1, 2, &t.geometry_ms);
+    span(3, 4, &t.bin_ms);
+    span(4, 5, &t.raster_ms);
+    t.total_ms = t.vertex_ms + t.geometry_ms + t.bin_ms + t.raster_ms;
+    *out = t;
+    return SR_OK;
+}
+
+// ---- framebuffer -----------------------------------------------------------------------------------------
+int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out) {
+    if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (format > SR_FB_RGBAF32_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
+    if (width > 256u * SR_TILE_W || height > 256u * SR_TILE_H || width > 65535u || height > 65535u)
+        return sr_fail(SR_ERR_UNSUPPORTED, "framebuffer %ux%u exceeds %ux%u", width, height, 256u * SR_TILE_W, 256u * SR_TILE_H);
+    SR_CUDA(cudaSetDevice(c->device));
+    auto fb = std::make_unique<sr_framebuffer>();
+    fb->ctx = c;
+    fb->width = width; fb->height = height; fb->format = format;
+    fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
+    const uint64_t n = (uint64_t)width * height;
+    SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * 20, &fb->aos_buf));
+    fb->aos = fb->aos_buf->as<float>();
+    if (format == SR_FB_RGBAF32_DF32_S8) SR_TRY(c->alloc(std::max<uint64_t>(n, 1), &fb->stencil_buf));
+    // RenderBuffer::with_dimensions: Color::empty() (zeros), Depth::far(), stencil default -- recorded lazily
+    fb->pending_clear = true;
+    *out = fb.release();
+    return SR_OK;
+}
+int sr_framebuffer_destroy(sr_framebuffer *fb) {
+    if (!fb) return SR_OK;
+    if (fb->is_peer && fb->aos) cudaIpcCloseMemHandle(fb->aos);
+    delete fb;
+    return SR_OK;
+}
+int sr_framebuffer_clear(sr_framebuffer *fb, const float color[4]) {
+    if (!fb || !color) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    for (int i = 0; i < 4; ++i) fb->clear[i] = color[i];
+    fb->pending_clear = true;  // produced on chip by the next draw (or materialised before a read-back)
+    return SR_OK;
+}
+int sr_framebuffer_dimensions(const sr_framebuffer *fb, uint32_t *w, uint32_t *h) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (w) *w = fb->width;
+    if (h) *h = fb->height;
+    return SR_OK;
+}
+int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
+    if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    const size_t need = (size_t)fb->width * fb->height * 20;
+    if (nbytes != need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, need);
+    SR_CUDA(cudaSetDevice(fb->ctx->device));
+    SR_TRY(materialize_clear(fb));
+    SR_CUDA(cudaMemcpyAsync(dst, fb->aos, need, cudaMemcpyDeviceToHost, fb->ctx->stream));
+    SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
+    return SR_OK;
+}
+int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *depth, uint8_t *stencil) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    Buf dc, dd;
+    if (color) SR_TRY(c->alloc(n * 16, &dc));
+    if (depth) SR_TRY(c->alloc(n * 4, &dd));
+    if (color || depth)
+        SR_LAUNCH(c, k_fb_split, ceil_div(n, 256), 256, 0, fb->aos, n, color ? dc->as<float>() : nullptr, depth ? dd->as<float>() : nullptr);
+    if (color) SR_CUDA(cudaMemcpyAsync(color, dc->ptr, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (depth) SR_CUDA(cudaMemcpyAsync(depth, dd->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (stencil) {
+        if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
+        SR_CUDA(cudaMemcpyAsync(stencil, fb->stencil_buf->ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const float *depth, const uint8_t *stencil) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    Buf dc, dd;
+    if (color) {
+        SR_TRY(c->alloc(n * 16, &dc));
+        SR_CUDA(cudaMemcpyAsync(dc->ptr, color, n * 16, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (depth) {
+        SR_TRY(c->alloc(n * 4, &dd));
+        SR_CUDA(cudaMemcpyAsync(dd->ptr, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (color || depth)
+        SR_LAUNCH(c, k_fb_merge, ceil_div(n, 256), 256, 0, fb->aos, n, color ? dc->as<float>() : nullptr, depth ? dd->as<float>() : nullptr);
+    if (stencil) {
+        if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
+        SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->ptr, stencil, n, cudaMemcpyHostToDevice, c->stream));
+    }
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float rgba[4], float *depth, uint8_t *stencil) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (x >= fb->width || y >= fb->height)
+        return sr_fail(SR_ERR_INVALID_PIXEL_COORDINATE, "pixel (%u,%u) outside %ux%u", x, y, fb->width, fb->height);
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    float px[5];
+    const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
+    SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
+    uint8_t s = 0;
+    if (stencil && fb->stencil_buf) SR_CUDA(cudaMemcpyAsync(&s, fb->stencil_buf->as<uint8_t>() + idx, 1, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    if (rgba) memcpy(rgba, px, 16);
+    if (depth) *depth = px[4];
+    if (stencil) *stencil = s;
+    return SR_OK;
+}
+int sr_framebuffer_enable_winner(sr_framebuffer *fb, int enable) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (enable && !fb->winner_buf) {
+        const uint64_t n = (uint64_t)fb->width * fb->height;
+        SR_TRY(fb->ctx->alloc(std::max<uint64_t>(n, 1) * 4, &fb->winner_buf));
+        SR_CUDA(cudaMemsetAsync(fb->winner_buf->ptr, 0, std::max<uint64_t>(n, 1) * 4, fb->ctx->stream));
+    }
+    fb->winner_enabled = enable != 0;
+    return SR_OK;
+}
+int sr_framebuffer_download_winner(sr_framebuffer *fb, uint32_t *dst) {
+    if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (!fb->winner_buf) return sr_fail(SR_ERR_INVALID_STATE, "winner plane not enabled");
+    SR_TRY(materialize_clear(fb));
+    SR_CUDA(cudaMemcpyAsync(dst, fb->winner_buf->ptr, (size_t)fb->width * fb->height * 4, cudaMemcpyDeviceToHost, fb->ctx->stream));
+    SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
+    return SR_OK;
+}
+void *sr_framebuffer_device_ptr(sr_framebuffer *fb) { return fb ? (void *)fb->aos : nullptr; }
+
+int sr_framebuffer_ipc_export(sr_framebuffer *fb, void *handle64) {
+    if (!fb || !handle64) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    SR_CUDA(cudaSetDevice(fb->ctx->device));
+    SR_TRY(materialize_clear(fb));
+    SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
+    cudaIpcMemHandle_t h;
+    SR_CUDA(cudaIpcGetMemHandle(&h, fb->aos));
+    memcpy(handle64, &h, 64);
+    return SR_OK;
+}
+int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width, uint32_t height, uint32_t format,
+                            sr_framebuffer **out) {
+    if (!c || !handle64 || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (format != SR_FB_RGBAF32_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "peer framebuffers carry colour+depth only");
+    SR_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    SR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    auto *fb = new sr_framebuffer();
+    fb->ctx = c;
+    fb->width = width; fb->height = height; fb->format = format;
+    fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
+    fb->aos = reinterpret_cast<float *>(p);
+    fb->is_peer = true;
+    fb->pending_clear = false;
+    *out = fb;
+    return SR_OK;
+}
+
+// ---- mesh ------------------------------------------------------------------------------------------------
+int sr_mesh_create(sr_context *c, const float *vertices, uint64_t nverts, uint32_t vin_floats, const void *indices,
+                   uint64_t nindices, uint32_t index_bytes, sr_mesh **out) {
+    if (!c || !out || (!vertices && nverts) || (!indices && nindices)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (vin_floats < 3 || vin_floats > 4 + SR_MAX_NK) return sr_fail(SR_ERR_INVALID_ARGUMENT, "vin_floats %u", vin_floats);
+    if (index_bytes != 4 && index_bytes != 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "index_bytes %u", index_bytes);
+    if (nverts > 0xFFFFFFF0ull || nindices > 0xFFFFFFF0ull * 3) return sr_fail(SR_ERR_UNSUPPORTED, "mesh too large for 32-bit ids");
+    SR_CUDA(cudaSetDevice(c->device));
+    auto m = std::make_unique<sr_mesh>();
+    m->ctx = c;
+    m->nverts = nverts;
+    m->vin = vin_floats;
+    m->nindices = nindices;
+    m->pstride = std::max<uint64_t>((nverts + 3) & ~(uint64_t)3, 4);
+    SR_TRY(c->alloc(m->pstride * vin_floats * 4, &m->planes));
+    SR_TRY(c->alloc(std::max<uint64_t>(nindices, 1) * 4, &m->indices));
+    if (nverts) {
+        Buf tmp;
+        SR_TRY(c->alloc(nverts * vin_floats * 4, &tmp));
+        SR_CUDA(cudaMemsetAsync(m->planes->ptr, 0, m->pstride * vin_floats * 4, c->stream));
+        SR_CUDA(cudaMemcpyAsync(tmp->ptr, vertices, nverts * vin_floats * 4, cudaMemcpyHostToDevice, c->stream));
+        SR_LAUNCH(c, k_aos_to_planes, ceil_div(nverts * vin_floats, 256), 256, 0, tmp->as<float>(), nverts, vin_floats,
+                  m->planes->as<float>(), m->pstride);
+    }
+    if (nindices) {
+        if (index_bytes == 4) {
+            SR_CUDA(cudaMemcpyAsync(m->indices->ptr, indices, nindices * 4, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            Buf tmp;
+            SR_TRY(c->alloc(nindices * 8, &tmp));
+            SR_CUDA(cudaMemcpyAsync(tmp->ptr, indices, nindices * 8, cudaMemcpyHostToDevice, c->stream));
+            SR_LAUNCH(c, k_narrow_indices, ceil_div(nindices, 256), 256, 0, tmp->as<uint64_t>(), nindices, m->indices->as<uint32_t>());
+        }
+    }
+    // "buffers passed in are copied before return"
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    // bounds-check the indices once on upload (the reference would panic on an out-of-range index)
+    if (nindices) {
+        uint64_t maxidx = 0;
+        if (index_bytes == 4) {
+            const uint32_t *ix = (const uint32_t *)indices;
+            for (uint64_t i = 0; i < nindices; ++i) maxidx = std::max<uint64_t>(maxidx, ix[i]);
+        } else {
+            const uint64_t *ix = (const uint64_t *)indices;
+            for (uint64_t i = 0; i < nindices; ++i) maxidx = std::max<uint64_t>(maxidx, ix[i]);
+        }
+        if (maxidx >= nverts) return sr_fail(SR_ERR_INVALID_ARGUMENT, "index %llu out of range (%llu vertices)", (unsigned long long)maxidx, (unsigned long long)nverts);
+    }
+    *out = m.release();
+    return SR_OK;
+}
+int sr_mesh_destroy(sr_mesh *m) {
+    delete m;
+    return SR_OK;
+}
+
+// ---- texture ---------------------------------------------------------------------------------------------
+int sr_texture_create(sr_context *c, const uint8_t *rgba, uint32_t width, uint32_t height, sr_texture **out) {
+    if (!c || !rgba || !out || !width || !height) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null or empty texture");
+    SR_CUDA(cudaSetDevice(c->device));
+    auto t = std::make_unique<sr_texture>();
+    t->ctx = c;
+    t->width = width; t->height = height;
+    SR_TRY(c->alloc((size_t)width * height * 4, &t->rgba));
+    SR_CUDA(cudaMemcpyAsync(t->rgba->ptr, rgba, (size_t)width * height * 4, cudaMemcpyHostToDevice, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    *out = t.release();
+    return SR_OK;
+}
+int sr_texture_destroy(sr_texture *t) {
+    delete t;
+    return SR_OK;
+}
+
+// ---- pipeline --------------------------------------------------------------------------------------------
+int sr_pipeline_create(sr_context *c, sr_framebuffer *fb, const sr_uniforms *u, sr_pipeline **out) {
+    if (!c || !fb || !u || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (fb->width == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero width");
+    if (fb->height == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero height");
+    auto *p = new sr_pipeline();
+    p->ctx = c;
+    p->fb = fb;
+    p->uniforms = *u;
+    *out = p;
+    return SR_OK;
+}
+int sr_pipeline_destroy(sr_pipeline *p) {
+    delete p;
+    return SR_OK;
+}
+int sr_pipeline_set_uniforms(sr_pipeline *p, const sr_uniforms *u) {
+    if (!p || !u) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    p->uniforms = *u;
+    return SR_OK;
+}
+int sr_pipeline_set_framebuffer(sr_pipeline *p, sr_framebuffer *fb) {
+    if (!p || !fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (fb->width == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero width");
+    if (fb->height == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero height");
+    p->fb = fb;
+    p->stencil_test = SR_STENCIL_ALWAYS;  // with_framebuffer: stencil_config: Default::default() (mod.rs:137)
+    p->stencil_op = SR_STENCIL_KEEP;
+    return SR_OK;
+}
+int sr_pipeline_set_stencil_config(sr_pipeline *p, uint32_t test, uint32_t op) {
+    if (!p || test > SR_STENCIL_NOT_EQUAL || op > SR_STENCIL_DECREMENT_SAT) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad stencil config");
+    p->stencil_test = test;
+    p->stencil_op = op;
+    return SR_OK;
+}
+int sr_pipeline_bind_texture(sr_pipeline *p, sr_texture *t) {
+    if (!p) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    p->texture = t;
+    return SR_OK;
+}
+
+// ---- draw ------------------------------------------------------------------------------------------------
+int sr_render_mesh(sr_pipeline *p, sr_mesh *m, uint32_t primitive, int has_sv, uint32_t sv, sr_draw **out) {
+    if (!p || !m || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (primitive < SR_POINT || primitive > SR_TRIANGLE) return sr_fail(SR_ERR_INVALID_ARGUMENT, "primitive %u", primitive);
+    if (m->nindices % primitive != 0)
+        return sr_fail(SR_ERR_INVALID_ARGUMENT, "assertion failed: mesh.indices.len() %% T::num_vertices() == 0 (%llu %% %u)",
+                       (unsigned long long)m->nindices, primitive);
+    auto *d = new sr_draw();
+    d->pipeline = p;
+    d->primitive = primitive;
+    d->has_stencil_value = has_sv != 0;
+    d->stencil_value = has_sv ? sv : 0;  // stencil.unwrap_or_default()
+    d->mesh_planes = m->planes;
+    d->indices = m->indices;
+    d->mesh_nverts = m->nverts;
+    d->mesh_pstride = m->pstride;
+    d->nindices = m->nindices;
+    d->vin = m->vin;
+    *out = d;
+    return SR_OK;
+}
+
+static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
+    if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (d->stage != STAGE_VERTEX || !d->mesh_planes) return sr_fail(SR_ERR_INVALID_STATE, "vertex stage already consumed");
+    sr_pipeline *p = d->pipeline;
+    sr_context *c = p->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    uint32_t nk;
+    switch (vs) {
+        case SR_VS_PASSTHROUGH:
+            if (d->vin < 4) return sr_fail(SR_ERR_INVALID_ARGUMENT, "passthrough needs >= 4 input floats");
+            nk = d->vin - 4;
+            break;
+        case SR_VS_SUZANNE:
+            if (d->vin != 6) return sr_fail(SR_ERR_INVALID_ARGUMENT, "suzanne vertex shader needs pos3+normal3");
+            nk = 8;
+            break;
+        case SR_VS_FULL_EXAMPLE:
+            if (d->vin != 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "full_example vertex shader needs pos3+normal3+uv2");
+            nk = 10;
+            break;
+        default: return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown vertex shader %u", vs);
+    }
+    d->nk = nk;
+    SR_TRY(alloc_stream(c, d->mesh_nverts, nk, &d->indexed));
+    SrVsConst vc;
+    fill_vs_const(p, vp, &vc);
+    SrMeshView mv;
+    mv.planes = d->mesh_planes->as<float>();
+    mv.pstride = d->mesh_pstride;
+    mv.nverts = d->mesh_nverts;
+    mv.vin = d->vin;
+    record(c, 0);
+    if (d->mesh_nverts) {
+        float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
+        const uint32_t grid4 = ceil_div(ceil_div(d->mesh_nverts, 4), 128);
+        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid4, 128, 0, vc, mv, pos, attr, d->indexed.stride);
+        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid4, 128, 0, vc, mv, pos, attr, d->indexed.stride);
+        else SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, pos, attr, d->indexed.stride);
+    }
+    record(c, 1);
+    record(c, 2);
+    d->have_indexed = true;
+    d->stage = vp ? STAGE_FRAGMENT : STAGE_GEOMETRY;
+    return SR_OK;
+}
+int sr_vertex_run(sr_draw *d, uint32_t vs) { return vertex_stage(d, nullptr, vs); }
+int sr_vertex_run_to_fragment(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
+    if (!vp) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null viewport");
+    return vertex_stage(d, vp, vs);
+}
+
+}  // extern "C"
+// count -> scan -> emit for the 0/1-output clippers
+template <int NV>
+static int clip_small(sr_context *c, const SrGeoIn &in, uint32_t nk, VertexStream *out) {
+    const uint32_t n = in.ngen + in.nidx;
+    if (n == 0) return alloc_stream(c, 0, nk, out);
+    Buf cnt, off;
+    SR_TRY(c->alloc((size_t)n * 4, &cnt));
+    SR_TRY(c->alloc((size_t)n * 4, &off));
+    SrGeoOut none = {};
+    const uint32_t grid = ceil_div(n, 128);
+    if (NV == 2) SR_LAUNCH(c, k_clip_line<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);
+    else SR_LAUNCH(c, k_clip_point<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);
+    uint32_t total = 0;
+    SR_TRY(exclusive_scan(c, cnt->as<uint32_t>(), n, off->as<uint32_t>(), &total));
+    SR_TRY(alloc_stream(c, (uint64_t)total * NV, nk, out));
+    SrGeoOut o = {out->pos->as<float4>(), out->attr->as<float4>(), out->stride};
+    if (NV == 2) SR_LAUNCH(c, k_clip_line<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
+    else SR_LAUNCH(c, k_clip_point<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
+    return SR_OK;
+}
+extern "C" {
+
+int sr_geometry_run(sr_draw *d, uint32_t gs) {
+    if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (d->stage != STAGE_GEOMETRY) return sr_fail(SR_ERR_INVALID_STATE, "geometry stage needs clip-space vertices");
+    if (gs > SR_GS_VERTEX_NORMALS) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown geometry shader %u", gs);
+    if (gs != SR_GS_CLIP && d->nk < 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "normal visualisation needs K = {position4, normal4, ..}");
+    sr_pipeline *p = d->pipeline;
+    sr_context *c = p->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    const uint32_t np = nplanes_of(d->nk);
+    auto geo_in = [&](uint32_t kind, bool with_gen, bool with_idx) {
+        SrGeoIn in;
+        memset(&in, 0, sizeof(in));
+        in.nplanes = np;
+        if (with_gen) {
+            in.gen = d->gen[kind - 1].set();
+            in.ngen = (uint32_t)(d->gen[kind - 1].n / kind);
+        }
+        if (with_idx && d->have_indexed && d->primitive == kind) {
+            in.idx = d->indexed.set();
+            in.indices = d->indices->as<uint32_t>();
+            in.nidx = (uint32_t)(d->nindices / kind);
+        }
+        return in;
+    };
+    VertexStream npoints, nlines, ntris;
+    Buf nseq;
+    uint32_t literal_total = 0;
+    if (gs == SR_GS_CLIP) {
+        SR_TRY(clip_small<1>(c, geo_in(1, true, true), d->nk, &npoints));
+        SR_TRY(clip_small<2>(c, geo_in(2, true, true), d->nk, &nlines));
+        const SrGeoIn tin = geo_in(3, true, true);
+        const uint32_t n = tin.ngen + tin.nidx;
+        if (n == 0) {
+            SR_TRY(alloc_stream(c, 0, d->nk, &ntris));
+        } else {
+            // zero-area outputs of the literal clipper are dropped unless a stencil op could observe them
+            const bool stencil_active = p->fb->stencil_buf && p->stencil_op != SR_STENCIL_KEEP;
+            const uint32_t drop = stencil_active ? 0u : 1u;
+            Buf kept, lit, kept_off, lit_off;
+            SR_TRY(c->alloc((size_t)n * 4, &kept));
+            SR_TRY(c->alloc((size_t)n * 4, &lit));
+            SR_TRY(c->alloc((size_t)n * 4, &kept_off));
+            SR_TRY(c->alloc((size_t)n * 4, &lit_off));
+            const uint32_t grid = ceil_div(n, 128);
+            SR_LAUNCH(c, k_clip_tri_count, grid, 128, 0, tin, drop, kept->as<uint32_t>(), lit->as<uint32_t>());
+            uint32_t kept_total = 0;
+            SR_TRY(exclusive_scan(c, kept->as<uint32_t>(), n, kept_off->as<uint32_t>(), &kept_total));
+            SR_TRY(exclusive_scan(c, lit->as<uint32_t>(), n, lit_off->as<uint32_t>(), &literal_total));
+            SR_TRY(alloc_stream(c, (uint64_t)kept_total * 3, d->nk, &ntris));
+            SR_TRY(c->alloc((size_t)std::max(kept_total, 1u) * 4, &nseq));
+            SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.stride};
+            SR_LAUNCH(c, k_clip_tri_emit, grid, 128, 0, tin, drop, kept_off->as<uint32_t>(), lit_off->as<uint32_t>(), o, nseq->as<uint32_t>());
+        }
+    } else {
+        SrVsConst vc;
+        fill_vs_const(p, nullptr, &vc);
+        // points: re-emitted
+        {
+            const SrGeoIn in = geo_in(1, true, true);
+            const uint32_t n = in.ngen + in.nidx;
+            SR_TRY(alloc_stream(c, n, d->nk, &npoints));
+            SrGeoOut o = {npoints.pos->as<float4>(), npoints.attr->as<float4>(), npoints.stride};
+            if (n) SR_LAUNCH(c, k_geo_reemit<1>, ceil_div(n, 128), 128, 0, in, o, (uint64_t)0);
+        }
+        // lines: [generated lines re-emitted | normals of generated triangles | indexed lines re-emitted or normals of indexed triangles]
+        {
+            const SrGeoIn gl = geo_in(2, true, false), gt = geo_in(3, true, false);
+            const SrGeoIn il = geo_in(2, false, true), it = geo_in(3, false, true);
+            const uint32_t per_tri = gs == SR_GS_FACE_NORMALS ? 1u : 3u;
+            const uint64_t total_lines = (uint64_t)gl.ngen + (uint64_t)gt.ngen * per_tri + il.nidx + (uint64_t)it.nidx * per_tri;
+            SR_TRY(alloc_stream(c, total_lines * 2, d->nk, &nlines));
+            SrGeoOut o = {nlines.pos->as<float4>(), nlines.attr->as<float4>(), nlines.stride};
+            uint64_t base = 0;
+            if (gl.ngen) SR_LAUNCH(c, k_geo_reemit<2>, ceil_div(gl.ngen, 128), 128, 0, gl, o, base);
+            base += (uint64_t)gl.ngen * 2;
+            auto normals = [&](const SrGeoIn &in, uint64_t at) -> int {
+                const uint32_t n = in.ngen + in.nidx;
+                if (!n) return SR_OK;
+                if (gs == SR_GS_FACE_NORMALS) SR_LAUNCH(c, k_geo_normals<SR_GS_FACE_NORMALS>, ceil_div(n, 128), 128, 0, in, vc, o, at);
+                else SR_LAUNCH(c, k_geo_normals<SR_GS_VERTEX_NORMALS>, ceil_div(n, 128), 128, 0, in, vc, o, at);
+                return SR_OK;
+            };
+            SR_TRY(normals(gt, base));
+            base += (uint64_t)gt.ngen * per_tri * 2;
+            if (il.nidx) SR_LAUNCH(c, k_geo_reemit<2>, ceil_div(il.nidx, 128), 128, 0, il, o, base);
+            base += (uint64_t)il.nidx * 2;
+            SR_TRY(normals(it, base));
+        }
+        SR_TRY(alloc_stream(c, 0, d->nk, &ntris));
+    }
+    d->gen[0] = npoints;
+    d->gen[1] = nlines;
+    d->gen[2] = ntris;
+    d->tri_seq = nseq;
+    d->tri_literal_total = literal_total;
+    d->have_indexed = false;  // indexed_vertices: None (geometry.rs:250-257)
+    d->indexed = VertexStream();
+    record(c, 2);
+    return SR_OK;
+}
+int sr_geometry_clip_primitives(sr_draw *d) { return sr_geometry_run(d, SR_GS_CLIP); }
+
+int sr_geometry_finish(sr_draw *d, const sr_viewport *vp) {
+    if (!d || !vp) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (d->stage != STAGE_GEOMETRY) return sr_fail(SR_ERR_INVALID_STATE, "finish needs clip-space vertices");
+    sr_pipeline *p = d->pipeline;
+    sr_context *c = p->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SrVsConst vc;
+    fill_vs_const(p, vp, &vc);
+    auto norm = [&](VertexStream &s) -> int {
+        if (!s.pos || s.n == 0) return SR_OK;
+        if (s.pos.use_count() > 1) {  // shared with a duplicate(): copy on write (geometry.rs:43 deep-copies)
+            Buf np_;
+            SR_TRY(c->alloc(s.stride * sizeof(float4), &np_));
+            SR_CUDA(cudaMemcpyAsync(np_->ptr, s.pos->ptr, s.stride * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            s.pos = np_;
+        }
+        SR_LAUNCH(c, k_normalize, ceil_div(s.n, 256), 256, 0, s.pos->as<float4>(), s.n, vc);
+        return SR_OK;
+    };
+    SR_TRY(norm(d->gen[0]));
+    SR_TRY(norm(d->gen[1]));
+    SR_TRY(norm(d->gen[2]));
+    if (d->have_indexed) SR_TRY(norm(d->indexed));
+    record(c, 2);
+    d->stage = STAGE_FRAGMENT;
+    return SR_OK;
+}
+
+int sr_draw_duplicate(sr_draw *d, sr_draw **out) {
+    if (!d || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    *out = new sr_draw(*d);  // device buffers are shared and immutable (finish copies on write)
+    return SR_OK;
+}
+int sr_fragment_set_cull_faces(sr_draw *d, uint32_t winding) {
+    if (!d || winding > SR_COUNTER_CLOCKWISE) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad winding");
+    d->cull = winding;
+    return SR_OK;
+}
+int sr_fragment_set_antialiased_lines(sr_draw *d, int enable) {
+    if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    d->aa_lines = enable ? 1 : 0;
+    return SR_OK;
+}
+int sr_fragment_set_tile_size(sr_draw *d, uint32_t w, uint32_t h) {
+    if (!d || !w || !h) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad tile size");
+    d->tile_w = w;
+    d->tile_h = h;
+    return SR_OK;
+}
+int sr_fragment_set_blend(sr_draw *d, uint32_t blend) {
+    if (!d || blend > SR_BLEND_ALPHA_OVER) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad blend");
+    d->blend = blend;
+    return SR_OK;
+}
+
+int sr_fragment_run(sr_draw *d, uint32_t fs) {
+    if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (d->stage != STAGE_FRAGMENT) return sr_fail(SR_ERR_INVALID_STATE, "fragment stage needs screen-space vertices (finish / run_to_fragment)");
+    const int need = fs_nk(fs);
+    if (need < 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown fragment shader %u", fs);
+    if ((int)d->nk < need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u reads %d interpolated floats, draw carries %u", fs, need, d->nk);
+    sr_pipeline *p = d->pipeline;
+    sr_context *c = p->ctx;
+    sr_framebuffer *fb = p->fb;
+    SR_CUDA(cudaSetDevice(c->device));
+    if (fb->width < 2 || fb->height < 2) return SR_OK;  // fragment.rs:188-216: a 1-pixel-wide frame has no tiles, nothing is drawn
+    if (fs == SR_FS_FULL_EXAMPLE_TEXTURED && !p->texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
+
+    SrTileParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.tris = prim_source(d, 3);
+    tp.lines = prim_source(d, 2);
+    tp.points = prim_source(d, 1);
+    tp.ntris = tp.tris.n0 + tp.tris.n1;
+    tp.nlines = tp.lines.n0 + tp.lines.n1;
+    tp.npoints = tp.points.n0 + tp.points.n1;
+    const uint32_t tri_canonical = tp.tris.n0 + (tp.tris.seq1 ? d->tri_literal_total : tp.tris.n1);
+    tp.line_base = tri_canonical;
+    tp.point_base = tri_canonical + tp.nlines;
+    tp.shard_rank = c->shard_rank; tp.shard_world = c->shard_world;
+    tp.blend = d->blend;
+    tp.stencil_test = p->stencil_test; tp.stencil_op = p->stencil_op; tp.stencil_value = d->stencil_value;
+    tp.aa_lines = d->aa_lines;
+    tp.fs.u = p->uniforms;
+    if (p->texture) {
+        tp.fs.tex = p->texture->rgba->as<uint8_t>();
+        tp.fs.tex_w = p->texture->width;
+        tp.fs.tex_h = p->texture->height;
+    }
+
+    if (fb->winner_enabled && fb->winner_buf)  // winner plane reports the primitives of THIS draw
+        SR_CUDA(cudaMemsetAsync(fb->winner_buf->ptr, 0, (size_t)fb->width * fb->height * 4, c->stream));
+    record(c, 3);
+    Bins bt, bl, bp;
+    SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt));
+    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl));
+    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp));
+    record(c, 4);
+    tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>();
+    tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>();
+    tp.point_rects = bp.rects->as<uint32_t>(); tp.point_off = bp.off->as<uint32_t>(); tp.point_list = bp.list->as<uint32_t>();
+
+    const uint32_t ntiles = fb->ntx * fb->nty;
+    const uint32_t owned = ntiles > c->shard_rank ? (ntiles - c->shard_rank + c->shard_world - 1) / c->shard_world : 0;
+    const bool stencil_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
+    const bool opaque_ok = d->blend == SR_BLEND_REPLACE && !stencil_active && fs != SR_FS_DISCARD_CHECKER;
+    if (owned) {
+        if (opaque_ok) {
+            // triangles through the order-independent resolve; lines/points (always after all triangles,
+            // fragment.rs:268-311) through the ordered kernel
+            if (tp.ntris || fb->pending_clear) {
+                tp.fb = fb->view();
+                SR_TRY(launch_tiles_fs(c, fs, false, owned, tp));
+                fb->pending_clear = false;
+            }
+            if (tp.nlines + tp.npoints) {
+                Bins none;
+                SR_TRY(zero_offsets(c, ntiles, &none));
+                SrTileParams t2 = tp;
+                t2.ntris = 0;
+                t2.tri_off = none.off->as<uint32_t>();
+                t2.fb = fb->view();
+                SR_TRY(launch_tiles_fs(c, fs, true, owned, t2));
+            }
+        } else {
+            tp.fb = fb->view();
+            SR_TRY(launch_tiles_fs(c, fs, true, owned, tp));
+            fb->pending_clear = false;
+        }
+    }
+    record(c, 5);
+    return SR_OK;
+}
+
+int sr_draw_destroy(sr_draw *d) {
+    delete d;
+    return SR_OK;
+}
+
+// ---- injection / introspection ---------------------------------------------------------------------------
+static int upload_records(sr_context *c, const float *verts, uint64_t n, uint32_t nk, VertexStream *out) {
+    SR_TRY(alloc_stream(c, n, nk, out));
+    if (n == 0) return SR_OK;
+    Buf tmp;
+    SR_TRY(c->alloc(n * (4 + nk) * 4, &tmp));
+    SR_CUDA(cudaMemcpyAsync(tmp->ptr, verts, n * (4 + nk) * 4, cudaMemcpyHostToDevice, c->stream));
+    SR_LAUNCH(c, k_records_to_planes, ceil_div(n, 256), 256, 0, tmp->as<float>(), n, nk, out->pos->as<float4>(), out->attr->as<float4>(), out->stride);
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+
+int sr_draw_from_vertices(sr_pipeline *p, uint32_t primitive, const float *verts, uint64_t nverts, uint32_t nk, int space,
+                          const uint32_t *indices, uint64_t nindices, int has_sv, uint32_t sv, sr_draw **out) {
+    if (!p || !out || (!verts && nverts) || (!indices && nindices)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (primitive < SR_POINT || primitive > SR_TRIANGLE) return sr_fail(SR_ERR_INVALID_ARGUMENT, "primitive %u", primitive);
+    if (nindices % primitive != 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "indices.len() %% num_vertices != 0");
+    if (nk > SR_MAX_NK) return sr_fail(SR_ERR_UNSUPPORTED, "nk %u > %u", nk, SR_MAX_NK);
+    for (uint64_t i = 0; i < nindices; ++i)
+        if (indices[i] >= nverts) return sr_fail(SR_ERR_INVALID_ARGUMENT, "index out of range");
+    sr_context *c = p->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    auto d = std::make_unique<sr_draw>();
+    d->pipeline = p;
+    d->primitive = primitive;
+    d->has_stencil_value = has_sv != 0;
+    d->stencil_value = has_sv ? sv : 0;
+    d->nk = nk;
+    d->nindices = nindices;
+    SR_TRY(c->alloc(std::max<uint64_t>(nindices, 1) * 4, &d->indices));
+    if (nindices) SR_CUDA(cudaMemcpyAsync(d->indices->ptr, indices, nindices * 4, cudaMemcpyHostToDevice, c->stream));
+    SR_TRY(upload_records(c, verts, nverts, nk, &d->indexed));
+    d->have_indexed = true;
+    d->stage = space ? STAGE_FRAGMENT : STAGE_GEOMETRY;
+    *out = d.release();
+    return SR_OK;
+}
+int sr_draw_set_generated(sr_draw *d, int which, const float *verts, uint64_t nverts, uint32_t nk) {
+    if (!d || which < 1 || which > 3 || (!verts && nverts)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (nverts % (uint64_t)which != 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "vertex count not a multiple of the primitive size");
+    if (nk != d->nk) return sr_fail(SR_ERR_INVALID_ARGUMENT, "nk mismatch");
+    if (d->stage == STAGE_VERTEX) return sr_fail(SR_ERR_INVALID_STATE, "run the vertex stage first");
+    SR_TRY(upload_records(d->pipeline->ctx, verts, nverts, nk, &d->gen[which - 1]));
+    if (which == 3) { d->tri_seq.reset(); d->tri_literal_total = 0; }
+    return SR_OK;
+}
+int sr_draw_count(sr_draw *d, int which, uint64_t *nverts, uint32_t *nk) {
+    if (!d || which < 0 || which > 3) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (nverts) *nverts = which == 0 ? (d->have_indexed ? d->indexed.n : 0) : d->gen[which - 1].n;
+    if (nk) *nk = d->nk;
+    return SR_OK;
+}
+int sr_draw_download(sr_draw *d, int which, float *dst, uint64_t capacity_floats) {
+    if (!d || which < 0 || which > 3 || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad arguments");
+    const VertexStream &s = which == 0 ? d->indexed : d->gen[which - 1];
+    const uint64_t n = which == 0 ? (d->have_indexed ? s.n : 0) : s.n;
+    if (n == 0) return SR_OK;
+    if (capacity_floats < n * (4 + d->nk)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "capacity too small");
+    sr_context *c = d->pipeline->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    Buf tmp;
+    SR_TRY(c->alloc(n * (4 + d->nk) * 4, &tmp));
+    SR_LAUNCH(c, k_planes_to_records, ceil_div(n, 256), 256, 0, s.pos->as<float4>(), s.attr->as<float4>(), s.stride, n, d->nk, tmp->as<float>());
+    SR_CUDA(cudaMemcpyAsync(dst, tmp->ptr, n * (4 + d->nk) * 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
+int sr_draw_download_sequence(sr_draw *d, uint32_t *dst, uint64_t capacity) {
+    if (!d || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    const uint64_t n = d->gen[2].n / 3;
+    if (capacity < n) return sr_fail(SR_ERR_INVALID_ARGUMENT, "capacity too small");
+    if (n == 0) return SR_OK;
+    sr_context *c = d->pipeline->ctx;
+    if (d->tri_seq) {
+        SR_CUDA(cudaMemcpyAsync(dst, d->tri_seq->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        for (uint64_t i = 0; i < n; ++i) dst[i] = (uint32_t)i;
+    }
+    return SR_OK;
+}
+
+int sr_draw_bins(sr_draw *d, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total) {
+    if (!d || !total) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (d->stage != STAGE_FRAGMENT) return sr_fail(SR_ERR_INVALID_STATE, "bins need screen-space vertices");
+    sr_pipeline *p = d->pipeline;
+    sr_context *c = p->ctx;
+    sr_framebuffer *fb = p->fb;
+    SR_CUDA(cudaSetDevice(c->device));
+    const SrPrimSource src = prim_source(d, 3);
+    const uint32_t ntris = src.n0 + src.n1, ntiles = fb->ntx * fb->nty;
+    Bins b;
+    SR_TRY(build_bins<3>(c, fb, src, ntris, d->cull, &b));
+    std::vector<uint32_t> rects(std::max(ntris, 1u)), off(ntiles + 1), list(std::max(b.total, 1u)), seq;
+    if (ntris) SR_CUDA(cudaMemcpyAsync(rects.data(), b.rects->ptr, (size_t)ntris * 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaMemcpyAsync(off.data(), b.off->ptr, (size_t)(ntiles + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (b.total) SR_CUDA(cudaMemcpyAsync(list.data(), b.list->ptr, (size_t)b.total * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (src.seq1 && src.n1) {
+        seq.resize(src.n1);
+        SR_CUDA(cudaMemcpyAsync(seq.data(), src.seq1, (size_t)src.n1 * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    // expand the per-tile group lists into exact per-tile triangle lists, exactly as the tile kernels do
+    uint64_t n = 0;
+    for (uint32_t tile = 0; tile < ntiles; ++tile) {
+        if (offsets) offsets[tile] = n;
+        std::vector<uint32_t> groups(list.begin() + off[tile], list.begin() + off[tile + 1]);
+        std::sort(groups.begin(), groups.end());
+        const uint32_t tx = tile % fb->ntx, ty = tile / fb->ntx;
+        for (uint32_t g : groups)
+            for (uint32_t j = 0; j < SR_GROUP; ++j) {
+                const uint32_t t = g * SR_GROUP + j;
+                if (t >= ntris) break;
+                const uint32_t r = rects[t];
+                if (r == SR_RECT_INVALID) continue;
+                const uint32_t tx0 = r & 255u, ty0 = (r >> 8) & 255u, tx1 = (r >> 16) & 255u, ty1 = r >> 24;
+                if (!(tx0 <= tx && tx <= tx1 && ty0 <= ty && ty <= ty1)) continue;
+                if (ids && n < ids_capacity) ids[n] = (t < src.n0 || seq.empty()) ? t : src.n0 + seq[t - src.n0];
+                ++n;
+            }
+    }
+    if (offsets) offsets[ntiles] = n;
+    *total = n;
+    return SR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,765 @@
+// sr_raster.cuh -- primitive setup + screen-tile binning, and the tile rasterisers
+// (FragmentShader::run, src/pipeline/stages/fragment.rs:168-319; rasterize_triangle / _line / _point,
+// src/pipeline/stages/rasterization/{triangle,line,point}.rs).
+//
+// Canonical semantics: the reference with ONE frame-sized tile (tile_size >= dimensions), i.e. every
+// primitive visits the pixels of its integer bounding box clamped to the frame exactly once, in
+// submission order.  The GPU partitions the frame into disjoint SR_TILE_W x SR_TILE_H tiles; the union
+// over tiles of (clamped bbox intersected with the tile) is that same pixel set, so results do not depend
+// on the GPU tile size.
+#pragma once
+
+#include "sr_shaders.cuh"
+
+#define SR_RASTER_THREADS 256
+#define SR_RASTER_WARPS (SR_RASTER_THREADS / 32)
+#define SR_SMALL_AREA 16          // bbox pixels a single lane rasterises itself; larger boxes go warp-wide
+#define SR_DEPTH_FAR_BITS 0xFF7FFFFFu  // f32::MIN, Depth::far() (src/framebuffer/attachments/depth.rs:31)
+
+struct SrBinParams {
+    SrPrimSource src;
+    uint32_t nprims;
+    uint32_t cull;
+    uint32_t width, height, ntx, nty;
+    uint32_t shard_rank, shard_world;
+    uint32_t expand;       // lines: widen the box by one pixel (rounding of the clipped end-points, Wu neighbours)
+    uint32_t *rects;       // per primitive: packed tile rectangle or SR_RECT_INVALID
+    uint32_t *tile_count;  // count pass: entries per tile; fill pass: running cursor per tile
+    const uint32_t *tile_off;
+    uint32_t *list;        // fill pass: group ids per tile
+};
+
+// ---- per-primitive tile rectangle ------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ uint32_t sr_prim_rect(const SrBinParams &p, uint32_t t) {
+    const SrVertexSet *vs;
+    uint32_t vi[NV];
+    sr_prim_vertices<NV>(p.src, t, vs, vi);
+    float x[NV], y[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float4 v = __ldg(vs->pos + vi[k]);
+        x[k] = v.x;
+        y[k] = v.y;
+    }
+    bool nan = false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) nan = nan || isnan(x[k]) || isnan(y[k]);
+    if (nan) return SR_RECT_INVALID;  // the reference panics on NaN (cast(..).unwrap()); defined here as "skipped"
+    uint32_t minx, miny, maxx, maxy;
+    if (NV == 3) {
+        if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
+            const float area = x[0] * y[1] + x[1] * y[2] + x[2] * y[0] - x[1] * y[0] - x[2] * y[1] - x[0] * y[2];
+            const uint32_t winding = signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE;
+            if (winding == p.cull) return SR_RECT_INVALID;
+        }
+        // triangle.rs:74-78 with tile = the whole frame
+        minx = sr_clamp_as_int(fminf(fminf(x[0], x[1]), x[2]), 0, p.width - 1);
+        miny = sr_clamp_as_int(fminf(fminf(y[0], y[1]), y[2]), 0, p.height - 1);
+        maxx = sr_clamp_as_int(fmaxf(fmaxf(x[0], x[1]), x[2]), 0, p.width - 1);
+        maxy = sr_clamp_as_int(fmaxf(fmaxf(y[0], y[1]), y[2]), 0, p.height - 1);
+    } else if (NV == 2) {
+        // conservative: every pixel rasterize_line can plot lies in the end-point box (+1 pixel)
+        minx = sr_clamp_as_int(fminf(x[0], x[NV - 1]), 0, p.width - 1);
+        miny = sr_clamp_as_int(fminf(y[0], y[NV - 1]), 0, p.height - 1);
+        maxx = sr_clamp_as_int(fmaxf(x[0], x[NV - 1]), 0, p.width - 1);
+        maxy = sr_clamp_as_int(fmaxf(y[0], y[NV - 1]), 0, p.height - 1);
+        minx = minx > 0 ? minx - 1 : 0;
+        miny = miny > 0 ? miny - 1 : 0;
+        maxx = maxx + 1 < p.width ? maxx + 1 : p.width - 1;
+        maxy = maxy + 1 < p.height ? maxy + 1 : p.height - 1;
+    } else {
+        // point.rs:46: bounds.0 <= x < bounds.1 with bounds = (0,0)..(w-1,h-1)
+        if (!(0.0f <= x[0] && x[0] < (float)(p.width - 1) && 0.0f <= y[0] && y[0] < (float)(p.height - 1))) return SR_RECT_INVALID;
+        minx = maxx = __float2uint_rz(x[0]);
+        miny = maxy = __float2uint_rz(y[0]);
+    }
+    return sr_pack_rect(minx / SR_TILE_W, miny / SR_TILE_H, maxx / SR_TILE_W, maxy / SR_TILE_H);
+}
+
+// Warp = one group of 32 consecutive primitives.  For every tile touched by at least one primitive of
+// the group: FILL ? append the group id to the tile's list : count it.
+template <bool FILL>
+__device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect, uint32_t group) {
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = rect != SR_RECT_INVALID;
+    uint32_t gx0 = valid ? (rect & 255u) : 255u, gy0 = valid ? ((rect >> 8) & 255u) : 255u;
+    uint32_t gx1 = valid ? ((rect >> 16) & 255u) : 0u, gy1 = valid ? (rect >> 24) : 0u;
+    gx0 = __reduce_min_sync(0xffffffffu, gx0);
+    gy0 = __reduce_min_sync(0xffffffffu, gy0);
+    gx1 = __reduce_max_sync(0xffffffffu, gx1);
+    gy1 = __reduce_max_sync(0xffffffffu, gy1);
+    if (!__any_sync(0xffffffffu, valid)) return;
+    for (uint32_t ty = gy0; ty <= gy1; ++ty)
+        for (uint32_t tx = gx0; tx <= gx1; ++tx) {
+            const bool hit = valid && sr_rect_hits(rect, tx, ty);
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            const uint32_t tile = ty * p.ntx + tx;
+            if (tile % p.shard_world != p.shard_rank) continue;
+            if (lane == 0) {
+                const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
+                if (FILL) p.list[p.tile_off[tile] + at] = group;
+            }
+        }
+}
+
+// pass 1: primitive setup (rect per primitive) + per-tile entry counts
+template <int NV>
+__global__ void __launch_bounds__(256) k_bin_setup(const SrBinParams p) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // grid covers whole warps
+    uint32_t rect = SR_RECT_INVALID;
+    if (t < p.nprims) {
+        rect = sr_prim_rect<NV>(p, t);
+        p.rects[t] = rect;
+    }
+    sr_bin_group<false>(p, rect, t >> 5);
+}
+// pass 2: fill the per-tile group lists (order inside a list is arbitrary; consumers that need
+// submission order sort the list, which is tiny because entries are groups of 32 primitives)
+__global__ void __launch_bounds__(256) k_bin_fill(const SrBinParams p) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rect = t < p.nprims ? __ldg(p.rects + t) : SR_RECT_INVALID;
+    sr_bin_group<true>(p, rect, t >> 5);
+}
+
+// exclusive scan of the per-tile counts (a few thousand tiles: one block), total to off[ntiles]
+__global__ void __launch_bounds__(256) k_tile_offsets(const uint32_t *count, uint32_t ntiles, uint32_t *off, uint32_t *cursor) {
+    __shared__ uint32_t ws[32];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? count[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = sr_block_exclusive_scan(v, &tot, ws);
+        if (i < ntiles) {
+            off[i] = carry + ex;
+            cursor[i] = 0;
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) off[ntiles] = carry;
+}
+
+// =====================================================================================================
+// shared per-triangle arithmetic (rasterization/triangle.rs:64,104-115)
+// =====================================================================================================
+struct SrTri {
+    float x3, y3;
+    float a, b, c, d;  // (y2-y3), (x3-x2), (y3-y1), (x1-x3)
+    float det;
+    bool det_ok;       // det finite-ish and non-zero: the exact sign shortcut below is valid
+};
+__device__ __forceinline__ SrTri sr_tri_setup(float x1, float y1, float x2, float y2, float x3, float y3) {
+    SrTri t;
+    t.x3 = x3; t.y3 = y3;
+    t.a = y2 - y3; t.b = x3 - x2; t.c = y3 - y1; t.d = x1 - x3;
+    t.det = t.a * (x1 - x3) + t.b * (y1 - y3);
+    t.det_ok = fabsf(t.det) > 0.0f && fabsf(t.det) <= 1e30f;
+    return t;
+}
+// Barycentrics of pixel (px,py) exactly as triangle.rs:104-113.  Returns false when the pixel is outside.
+// The early-outs are exact: for finite non-zero det and |n| >= 1e-7 the quotient n/det is a non-zero
+// normal/denormal float whose sign is sign(n)*sign(det), so `n/det < 0` iff the signs differ.
+__device__ __forceinline__ bool sr_tri_bary(const SrTri &t, uint32_t px, uint32_t py, float &u, float &v, float &w) {
+    const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+    const float dx = x - t.x3, dy = y - t.y3;
+    const float nu = t.a * dx + t.b * dy;
+    const float nv = t.c * dx + t.d * dy;
+    if (t.det_ok) {
+        const bool dneg = t.det < 0.0f;
+        if (fabsf(nu) >= 1e-7f && ((nu < 0.0f) != dneg)) return false;
+        if (fabsf(nv) >= 1e-7f && ((nv < 0.0f) != dneg)) return false;
+    }
+    u = nu / t.det;
+    v = nv / t.det;
+    w = 1.0f - u - v;
+    return !(u < 0.0f || v < 0.0f || w < 0.0f);
+}
+
+struct SrTileParams {
+    SrPrimSource tris, lines, points;
+    uint32_t ntris, nlines, npoints;
+    const uint32_t *tri_rects, *line_rects, *point_rects;
+    const uint32_t *tri_off, *line_off, *point_off;  // per-tile CSR offsets (ntiles+1) into the group lists
+    uint32_t *tri_list, *line_list, *point_list;
+    SrFbView fb;
+    uint32_t shard_rank, shard_world;
+    uint32_t blend, stencil_test, stencil_op, stencil_value, aa_lines;
+    uint32_t line_base, point_base;  // canonical index of the first line / point (after all triangles / lines)
+    SrFsConst fs;
+};
+
+__device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, uint32_t py) {
+    return fb.aos + ((uint64_t)py * fb.width + px) * 5;
+}
+
+// =====================================================================================================
+// Opaque tile rasteriser: Blend = (), stencil test Always / op Keep, shader never discards.
+// In that state the reference's in-order result at a pixel is the covering fragment with z<0 that
+// maximises (z, submission index) among those with z >= the depth already stored (`d >= dt`, later
+// primitives win ties, triangle.rs:120-126).  That is order-independent, so the tile keeps one 64-bit
+// key (order-preserving depth bits << 32 | primitive+1) per pixel in shared memory, resolves it with
+// atomicMax, then shades each pixel ONCE and writes the tile back to HBM once.
+// =====================================================================================================
+template <int FS>
+__global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_opaque(const __grid_constant__ SrTileParams p) {
+    extern __shared__ __align__(16) unsigned char sr_smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
+
+    const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
+    const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
+    const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
+    const uint32_t lbeg = p.tri_off[tile], L = p.tri_off[tile + 1] - lbeg;
+    if (L == 0 && !p.fb.pending_clear) return;  // nothing to draw, contents already in HBM
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t W = p.fb.width, H = p.fb.height;
+
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+        uint32_t dk = sr_depth_key(__uint_as_float(SR_DEPTH_FAR_BITS));
+        if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_pixel(p.fb, px, py)[4]);
+        keys[i] = (unsigned long long)dk << 32;
+    }
+    __syncthreads();
+
+    const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;  // last pixel of the tile in the frame
+
+    auto raster_pixel = [&](const SrTri &tr, float z1, float z2, float z3, uint32_t px, uint32_t py, uint32_t id) {
+        float u, v, w;
+        if (!sr_tri_bary(tr, px, py, u, v, w)) return;
+        const float z = (z1 * u + z2 * v) + z3 * w;
+        if (!(z < 0.0f)) return;  // triangle.rs:120
+        const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u);
+        unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
+        if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
+    };
+
+    for (uint32_t gi = warp; gi < L; gi += SR_RASTER_WARPS) {
+        const uint32_t g = __ldg(p.tri_list + lbeg + gi);
+        const uint32_t t = g * SR_GROUP + lane;
+        const uint32_t rect = t < p.ntris ? __ldg(p.tri_rects + t) : SR_RECT_INVALID;
+        const bool hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
+        SrTri tr;
+        float z1 = 0, z2 = 0, z3 = 0;
+        uint32_t minx = 1, maxx = 0, miny = 1, maxy = 0;
+        if (hit) {
+            const SrVertexSet *vs;
+            uint32_t vi[3];
+            sr_prim_vertices<3>(p.tris, t, vs, vi);
+            const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+            tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+            z1 = A.z; z2 = B.z; z3 = C.z;
+            minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
+            miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
+            maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
+            maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
+        }
+        const bool nonempty = hit && minx <= maxx && miny <= maxy;
+        const uint32_t bw = nonempty ? maxx - minx + 1 : 0, bh = nonempty ? maxy - miny + 1 : 0;
+        const bool small = nonempty && bw * bh <= SR_SMALL_AREA;
+        if (small) {
+            for (uint32_t py = miny; py <= maxy; ++py)
+                for (uint32_t px = minx; px <= maxx; ++px) raster_pixel(tr, z1, z2, z3, px, py, t);
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, nonempty && !small);
+        while (big) {  // warp-cooperative sweep of one large box at a time
+            const int l = __ffs(big) - 1;
+            big &= big - 1;
+            SrTri s;
+            s.x3 = __shfl_sync(0xffffffffu, tr.x3, l); s.y3 = __shfl_sync(0xffffffffu, tr.y3, l);
+            s.a = __shfl_sync(0xffffffffu, tr.a, l); s.b = __shfl_sync(0xffffffffu, tr.b, l);
+            s.c = __shfl_sync(0xffffffffu, tr.c, l); s.d = __shfl_sync(0xffffffffu, tr.d, l);
+            s.det = __shfl_sync(0xffffffffu, tr.det, l);
+            s.det_ok = fabsf(s.det) > 0.0f && fabsf(s.det) <= 1e30f;
+            const float sz1 = __shfl_sync(0xffffffffu, z1, l), sz2 = __shfl_sync(0xffffffffu, z2, l), sz3 = __shfl_sync(0xffffffffu, z3, l);
+            const uint32_t sminx = __shfl_sync(0xffffffffu, minx, l), sminy = __shfl_sync(0xffffffffu, miny, l);
+            const uint32_t sbw = __shfl_sync(0xffffffffu, bw, l), sbh = __shfl_sync(0xffffffffu, bh, l);
+            const uint32_t st = g * SR_GROUP + l;
+            for (uint32_t i = lane; i < sbw * sbh; i += 32) raster_pixel(s, sz1, sz2, sz3, sminx + i % sbw, sminy + i / sbw, st);
+        }
+    }
+    __syncthreads();
+
+    // resolve: shade every pixel once, write colour + depth (+winner) to HBM once
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+        if (px >= W || py >= H) continue;
+        const unsigned long long key = keys[i];
+        const uint32_t id = (uint32_t)key;
+        float *dst = sr_fb_pixel(p.fb, px, py);
+        if (id == 0) {
+            if (p.fb.pending_clear) {
+                dst[0] = p.fb.clear[0]; dst[1] = p.fb.clear[1]; dst[2] = p.fb.clear[2]; dst[3] = p.fb.clear[3];
+                dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+            }
+            if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = 0;
+            continue;
+        }
+        const uint32_t t = id - 1;
+        const SrVertexSet *vs;
+        uint32_t vi[3];
+        sr_prim_vertices<3>(p.tris, t, vs, vi);
+        const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+        float u, v, w;
+        sr_tri_bary(tr, px, py, u, v, w);  // same arithmetic as the coverage pass: identical u,v,w
+        float sv[4 + NP * 4 + 1];
+        sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
+        sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
+        sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+        sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+            const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
+            const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
+            const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
+            sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+            sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+            sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+            sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+        }
+        float col[4];
+        sr_fragment_shader<FS>(p.fs, sv, col);
+        dst[0] = col[0]; dst[1] = col[1]; dst[2] = col[2]; dst[3] = col[3];
+        dst[4] = sv[2];
+        if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = sr_prim_canonical(p.tris, t, 0) + 1;
+    }
+}
+
+// =====================================================================================================
+// Ordered tile rasteriser: any blend, stencil, discarding shaders, lines and points.  Strictly in
+// submission order per pixel.  Tile colour, depth, stencil (and winner) live in shared memory; each
+// warp owns a band of tile rows, so all operations on a pixel are issued by one warp in program order.
+// =====================================================================================================
+struct SrOrdSetup {
+    float x1, y1, x2, y2, x3, y3;
+    uint32_t bx, by;  // minx | maxx<<16, miny | maxy<<16 (frame-clamped bbox intersected with the tile)
+    uint32_t t;
+};
+#define SR_ORD_LIST_CAP 8192  // group ids sorted in shared memory; longer lists are sorted in place in HBM
+#define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4)
+
+struct SrOrdCtx {
+    float4 *color;
+    float *depth;
+    uint32_t *winner;
+    uint8_t *stencil;
+    const SrTileParams *p;
+    uint32_t x0, y0, xe, ye;  // tile pixel rectangle inside the frame (inclusive)
+    bool has_stencil;
+    uint8_t mesh_stencil;
+};
+
+// stencil step (triangle.rs:91-99, line.rs:58-66, point.rs:52-60)
+__device__ __forceinline__ bool sr_ord_stencil_step(const SrOrdCtx &c, uint32_t li) {
+    if (!c.has_stencil) return true;  // stencil type (): Always / Keep
+    const uint8_t sval = c.stencil[li];
+    if (!sr_stencil_test_fn(c.p->stencil_test, sval, c.mesh_stencil)) return false;
+    c.stencil[li] = sr_stencil_op_fn(c.p->stencil_op, sval, c.mesh_stencil);
+    return true;
+}
+// everything after the stencil step of one fragment (triangle.rs:117-143, line.rs:81-106, point.rs:62-82)
+template <int FS>
+__device__ __forceinline__ void sr_ord_shade_write(const SrOrdCtx &c, uint32_t li, const float *sv, bool use_alpha, float alpha,
+                                                   uint32_t canonical) {
+    const float z = sv[2];
+    if (!(z < 0.0f)) return;
+    if (!(z >= c.depth[li])) return;
+    float col[4];
+    if (!sr_fragment_shader<FS>(c.p->fs, sv, col)) return;  // Fragment::Discard
+    if (use_alpha) col[3] = col[3] * alpha;                 // Color::mul_alpha (src/color/predefined.rs:82-86)
+    const float4 old = c.color[li];
+    const float dstc[4] = {old.x, old.y, old.z, old.w};
+    float outc[4];
+    sr_blend(c.p->blend, col, dstc, outc);
+    c.color[li] = make_float4(outc[0], outc[1], outc[2], outc[3]);
+    c.depth[li] = z;
+    c.winner[li] = canonical + 1;
+}
+
+// direction-free bitonic sort (ascending); elements at index >= n are virtual +inf, so n need not be a power of two
+__device__ __forceinline__ void sr_block_sort(uint32_t *a, uint32_t n) {
+    uint32_t n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+            const uint32_t h = k >> 1, blk = i / h, wi = i % h;
+            const uint32_t lo = blk * k + wi, hi = blk * k + k - 1 - wi;
+            if (hi < n) {
+                const uint32_t va = a[lo], vb = a[hi];
+                if (va > vb) { a[lo] = vb; a[hi] = va; }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+                const uint32_t lo = (i / j) * 2 * j + i % j, hi = lo + j;
+                if (hi < n) {
+                    const uint32_t va = a[lo], vb = a[hi];
+                    if (va > vb) { a[lo] = vb; a[hi] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// liang_barsky_iterative (src/geometry/line.rs:6-54)
+__device__ __forceinline__ bool sr_liang_barsky(float x1, float y1, float x2, float y2, float xmin, float ymin, float xmax,
+                                                float ymax, float *o) {
+    float t0 = 0.0f, t1 = 1.0f;
+    const float dx = x2 - x1, dy = y2 - y1;
+    for (int edge = 0; edge < 4; ++edge) {
+        float pp, q;
+        switch (edge) {
+            case 0: pp = -dx; q = x1 - xmin; break;
+            case 1: pp = dx; q = xmax - x1; break;
+            case 2: pp = -dy; q = y1 - ymin; break;
+            default: pp = dy; q = ymax - y1; break;
+        }
+        if (pp == 0.0f && q < 0.0f) return false;
+        const float r = q / pp;
+        if (pp < 0.0f) {
+            if (r > t1) return false;
+            else if (r > t0) t0 = r;
+        } else if (pp > 0.0f) {
+            if (r < t0) return false;
+            else if (r < t1) t1 = r;
+        }
+    }
+    o[0] = x1 + t0 * dx; o[1] = y1 + t0 * dy; o[2] = x1 + t1 * dx; o[3] = y1 + t1 * dy;
+    return true;
+}
+
+struct SrLineCtx {
+    float x1, y1, d;       // clipped start point and clipped length (line.rs:51-52)
+    float4 ps, pe;         // unclipped end-point positions: interpolation runs over these (line.rs:75-77)
+    const SrVertexSet *vs;
+    uint32_t vi[2];
+    uint32_t canonical;
+};
+
+// the rasterize_fragment closure of rasterize_line (line.rs:54-109); one non-inlined copy per shader
+template <int FS>
+__device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx &L, long long x, long long y, double alpha) {
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    if (x < 0 || y < 0) return;
+    // only this tile's pixels (the frame test also covers Wu's +1 neighbour past the last row/column,
+    // where the reference would index out of bounds)
+    if (x < (long long)c.x0 || x > (long long)c.xe || y < (long long)c.y0 || y > (long long)c.ye) return;
+    const uint32_t li = ((uint32_t)y - c.y0) * SR_TILE_W + ((uint32_t)x - c.x0);
+    if (!sr_ord_stencil_step(c, li)) return;
+    const float xf = (float)x + 0.5f, yf = (float)y + 0.5f;
+    const float t = sr_hypot32(L.x1 - xf, L.y1 - yf) / L.d;
+    float sv[4 + NP * 4 + 1];
+    sv[0] = sr_lerp(t, L.ps.x, L.pe.x);
+    sv[1] = sr_lerp(t, L.ps.y, L.pe.y);
+    sv[2] = sr_lerp(t, L.ps.z, L.pe.z);
+    sv[3] = sr_lerp(t, L.ps.w, L.pe.w);
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) {
+        const float4 ka = __ldg(L.vs->attr + (uint64_t)pl * L.vs->stride + L.vi[0]);
+        const float4 kb = __ldg(L.vs->attr + (uint64_t)pl * L.vs->stride + L.vi[1]);
+        sv[4 + pl * 4 + 0] = sr_lerp(t, ka.x, kb.x);
+        sv[4 + pl * 4 + 1] = sr_lerp(t, ka.y, kb.y);
+        sv[4 + pl * 4 + 2] = sr_lerp(t, ka.z, kb.z);
+        sv[4 + pl * 4 + 3] = sr_lerp(t, ka.w, kb.w);
+    }
+    sr_ord_shade_write<FS>(c, li, sv, true, (float)alpha, L.canonical);
+}
+
+__device__ __forceinline__ double sr_fract64(double x) { return x - trunc(x); }
+
+// rasterize_line (src/pipeline/stages/rasterization/line.rs:22-119) for one line, executed by one thread
+template <int FS>
+__device__ void sr_ord_line(const SrOrdCtx &c, uint32_t t) {
+    const SrTileParams &p = *c.p;
+    SrLineCtx L;
+    sr_prim_vertices<2>(p.lines, t, L.vs, L.vi);
+    L.ps = __ldg(L.vs->pos + L.vi[0]);
+    L.pe = __ldg(L.vs->pos + L.vi[1]);
+    L.canonical = p.line_base + sr_prim_canonical(p.lines, t, 0);
+    float cl[4];
+    // bounds = the one frame-sized tile ((0,0),(w-1,h-1)) cast to float (fragment.rs:255-258)
+    if (!sr_liang_barsky(L.ps.x, L.ps.y, L.pe.x, L.pe.y, 0.0f, 0.0f, (float)(p.fb.width - 1), (float)(p.fb.height - 1), cl)) return;
+    if (!isfinite(cl[0]) || !isfinite(cl[1]) || !isfinite(cl[2]) || !isfinite(cl[3])) return;  // reference would panic
+    L.x1 = cl[0]; L.y1 = cl[1];
+    L.d = sr_hypot32(cl[0] - cl[2], cl[1] - cl[3]);
+    if (!p.aa_lines) {
+        // draw_line_bresenham (line.rs:125-151)
+        long long bx0 = (long long)cl[0], by0 = (long long)cl[1];
+        const long long bx1 = (long long)cl[2], by1 = (long long)cl[3];
+        const long long dx = llabs(bx1 - bx0), dy = -llabs(by1 - by0);
+        const long long sx = bx0 < bx1 ? 1 : -1, sy = by0 < by1 ? 1 : -1;
+        long long err = dx + dy;
+        while (true) {
+            sr_ord_plot_line<FS>(c, L, bx0, by0, 1.0);
+            if (bx0 == bx1 && by0 == by1) break;
+            const long long e2 = 2 * err;
+            if (e2 >= dy) { err += dy; bx0 += sx; }
+            if (e2 <= dx) { err += dx; by0 += sy; }
+        }
+    } else {
+        // draw_line_xiaolin_wu (line.rs:159-239), f64 throughout
+        double wx0 = (double)cl[0], wy0 = (double)cl[1], wx1 = (double)cl[2], wy1 = (double)cl[3];
+        const bool steep = fabs(wy1 - wy0) > fabs(wx1 - wx0);
+        if (steep) { double tmp = wx0; wx0 = wy0; wy0 = tmp; tmp = wx1; wx1 = wy1; wy1 = tmp; }
+        if (wx0 > wx1) { double tmp = wx0; wx0 = wx1; wx1 = tmp; tmp = wy0; wy0 = wy1; wy1 = tmp; }
+        const double dx = wx1 - wx0, dy = wy1 - wy0;
+        const double gradient = dx < 0.0001 ? 1.0 : dy / dx;
+        auto plot_float = [&](double a, double b, double opacity) {
+            if (steep) sr_ord_plot_line<FS>(c, L, (long long)b, (long long)a, opacity);
+            else sr_ord_plot_line<FS>(c, L, (long long)a, (long long)b, opacity);
+        };
+        // both arms of the reference's `if steep` plot (x, y) / (y, x); plot_float takes (x_major, y_minor)
+        double xend = round(wx0);
+        double yend = wy0 + gradient * (xend - wx0);
+        double xgap = 1.0 - sr_fract64(wx0 + 0.5);
+        const double xpxl1 = xend, ypxl1 = trunc(yend);
+        plot_float(xpxl1, ypxl1, (1.0 - sr_fract64(yend)) * xgap);
+        plot_float(xpxl1, ypxl1 + 1.0, sr_fract64(yend) * xgap);
+        double intery = yend + gradient;
+        xend = round(wx1);
+        yend = wy1 + gradient * (xend - wx1);
+        xgap = sr_fract64(wx1 + 0.5);
+        const double xpxl2 = xend, ypxl2 = trunc(yend);
+        plot_float(xpxl2, ypxl2, (1.0 - sr_fract64(yend)) * xgap);
+        plot_float(xpxl2, ypxl2 + 1.0, sr_fract64(yend) * xgap);
+        for (double x = xpxl1 + 1.0; x <= (xpxl2 - 1.0); x += 1.0) {
+            const double y = trunc(intery);
+            plot_float(x, y, 1.0 - sr_fract64(intery));
+            plot_float(x, y + 1.0, sr_fract64(intery));
+            intery += gradient;
+        }
+    }
+}
+
+// rasterize_point (src/pipeline/stages/rasterization/point.rs:21-86); membership in this tile was decided by the rect
+template <int FS>
+__device__ __noinline__ void sr_ord_point(const SrOrdCtx &c, uint32_t t) {
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    const SrTileParams &p = *c.p;
+    const SrVertexSet *vs;
+    uint32_t vi[1];
+    sr_prim_vertices<1>(p.points, t, vs, vi);
+    const float4 P = __ldg(vs->pos + vi[0]);
+    const uint32_t px = __float2uint_rz(P.x), py = __float2uint_rz(P.y);
+    if (px < c.x0 || px > c.xe || py < c.y0 || py > c.ye) return;
+    const uint32_t li = (py - c.y0) * SR_TILE_W + (px - c.x0);
+    if (!sr_ord_stencil_step(c, li)) return;
+    float sv[4 + NP * 4 + 1];
+    sv[0] = P.x; sv[1] = P.y; sv[2] = P.z; sv[3] = P.w;
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) {
+        const float4 k = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
+        sv[4 + pl * 4 + 0] = k.x; sv[4 + pl * 4 + 1] = k.y; sv[4 + pl * 4 + 2] = k.z; sv[4 + pl * 4 + 3] = k.w;
+    }
+    sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, p.point_base + sr_prim_canonical(p.points, t, 0));
+}
+
+template <int FS>
+__global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid_constant__ SrTileParams p) {
+    extern __shared__ __align__(16) unsigned char sr_smem[];
+    float4 *s_color = reinterpret_cast<float4 *>(sr_smem);
+    float *s_depth = reinterpret_cast<float *>(s_color + SR_TILE_PIXELS);
+    uint32_t *s_winner = reinterpret_cast<uint32_t *>(s_depth + SR_TILE_PIXELS);
+    SrOrdSetup *s_setup = reinterpret_cast<SrOrdSetup *>(s_winner + SR_TILE_PIXELS);
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(s_setup + SR_RASTER_THREADS);
+    uint8_t *s_stencil = reinterpret_cast<uint8_t *>(s_list + SR_ORD_LIST_CAP);
+    __shared__ uint32_t s_wcount[SR_RASTER_WARPS];
+
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    constexpr uint32_t RH = SR_TILE_H / SR_RASTER_WARPS;  // tile rows owned by each warp
+    static_assert(SR_TILE_H % SR_RASTER_WARPS == 0, "tile height must split evenly over the warps");
+
+    const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
+    const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
+    const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
+    const uint32_t tbeg = p.tri_off[tile], LT = p.tri_off[tile + 1] - tbeg;
+    const uint32_t lbeg = p.line_off[tile], LL = p.line_off[tile + 1] - lbeg;
+    const uint32_t pbeg = p.point_off[tile], LP = p.point_off[tile + 1] - pbeg;
+    if (LT + LL + LP == 0 && !p.fb.pending_clear) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t W = p.fb.width, H = p.fb.height;
+
+    SrOrdCtx c;
+    c.color = s_color; c.depth = s_depth; c.winner = s_winner; c.stencil = s_stencil; c.p = &p;
+    c.x0 = x0; c.y0 = y0;
+    c.xe = min(x0 + SR_TILE_W, W) - 1; c.ye = min(y0 + SR_TILE_H, H) - 1;
+    c.has_stencil = p.fb.stencil != nullptr;
+    c.mesh_stencil = (uint8_t)p.stencil_value;
+
+    // load the tile (or generate the pending clear on chip)
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+        float4 col = make_float4(p.fb.clear[0], p.fb.clear[1], p.fb.clear[2], p.fb.clear[3]);
+        float d = __uint_as_float(SR_DEPTH_FAR_BITS);
+        uint8_t s = 0;
+        if (!p.fb.pending_clear && px < W && py < H) {
+            const float *src = sr_fb_pixel(p.fb, px, py);
+            col = make_float4(src[0], src[1], src[2], src[3]);
+            d = src[4];
+            if (c.has_stencil) s = p.fb.stencil[(uint64_t)py * W + px];
+        }
+        s_color[i] = col;
+        s_depth[i] = d;
+        s_stencil[i] = s;
+        s_winner[i] = 0;
+    }
+    __syncthreads();
+
+    // ---------------- triangles ----------------
+    if (LT > 0) {
+        uint32_t *lst = p.tri_list + tbeg;
+        if (LT <= SR_ORD_LIST_CAP) {
+            for (uint32_t i = tid; i < LT; i += SR_RASTER_THREADS) s_list[i] = lst[i];
+            __syncthreads();
+            lst = s_list;
+        }
+        sr_block_sort(lst, LT);
+        __syncthreads();
+        for (uint32_t gb = 0; gb < LT; gb += SR_RASTER_WARPS) {
+            const uint32_t gi = gb + warp;
+            bool hit = false;
+            SrOrdSetup su;
+            if (gi < LT) {
+                const uint32_t t = lst[gi] * SR_GROUP + lane;
+                const uint32_t rect = t < p.ntris ? __ldg(p.tri_rects + t) : SR_RECT_INVALID;
+                hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
+                if (hit) {
+                    const SrVertexSet *vs;
+                    uint32_t vi[3];
+                    sr_prim_vertices<3>(p.tris, t, vs, vi);
+                    const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+                    const uint32_t minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
+                    const uint32_t miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
+                    const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), c.xe);
+                    const uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), c.ye);
+                    hit = minx <= maxx && miny <= maxy;
+                    su.x1 = A.x; su.y1 = A.y; su.x2 = B.x; su.y2 = B.y; su.x3 = C.x; su.y3 = C.y;
+                    su.bx = minx | (maxx << 16);
+                    su.by = miny | (maxy << 16);
+                    su.t = t;
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcount[warp] = __popc(mask);
+            __syncthreads();
+            uint32_t base = 0, total = 0;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) {
+                const uint32_t cnt = s_wcount[w2];
+                if (w2 < warp) base += cnt;
+                total += cnt;
+            }
+            if (hit) s_setup[base + __popc(mask & ((1u << lane) - 1u))] = su;
+            __syncthreads();
+            const uint32_t ry_lo = y0 + warp * RH, ry_hi = ry_lo + RH - 1;
+            for (uint32_t s = 0; s < total; ++s) {
+                const SrOrdSetup q = s_setup[s];
+                const uint32_t minx = q.bx & 0xffffu, maxx = q.bx >> 16;
+                const uint32_t r0 = max(q.by & 0xffffu, ry_lo), r1 = min(q.by >> 16, ry_hi);
+                if (r0 > r1) continue;
+                const SrTri tr = sr_tri_setup(q.x1, q.y1, q.x2, q.y2, q.x3, q.y3);
+                const uint32_t bw = maxx - minx + 1, npix = bw * (r1 - r0 + 1);
+                const SrVertexSet *vs;
+                uint32_t vi[3];
+                sr_prim_vertices<3>(p.tris, q.t, vs, vi);
+                const uint32_t canonical = sr_prim_canonical(p.tris, q.t, 0);
+                for (uint32_t i = lane; i < npix; i += 32) {
+                    const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                    const uint32_t li = (py - y0) * SR_TILE_W + (px - x0);
+                    if (!sr_ord_stencil_step(c, li)) continue;
+                    float u, v, w;
+                    if (!sr_tri_bary(tr, px, py, u, v, w)) continue;
+                    const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+                    float sv[4 + NP * 4 + 1];
+                    sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
+                    sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
+                    sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+                    sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+                    if (!(sv[2] < 0.0f) || !(sv[2] >= s_depth[li])) continue;
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
+                        const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
+                        const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
+                        sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+                        sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                        sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+                        sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                    }
+                    sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, canonical);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- lines, then points (fragment.rs:284-311): one thread walks them in order ----------------
+    for (int kind = 2; kind >= 1; --kind) {
+        const uint32_t Ln = kind == 2 ? LL : LP;
+        if (Ln == 0) continue;
+        uint32_t *lst = kind == 2 ? p.line_list + lbeg : p.point_list + pbeg;
+        if (Ln <= SR_ORD_LIST_CAP) {
+            for (uint32_t i = tid; i < Ln; i += SR_RASTER_THREADS) s_list[i] = lst[i];
+            __syncthreads();
+            lst = s_list;
+        }
+        sr_block_sort(lst, Ln);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t nprim = kind == 2 ? p.nlines : p.npoints;
+            const uint32_t *rects = kind == 2 ? p.line_rects : p.point_rects;
+            for (uint32_t gi = 0; gi < Ln; ++gi) {
+                const uint32_t g = lst[gi];
+                for (uint32_t j = 0; j < SR_GROUP; ++j) {
+                    const uint32_t t = g * SR_GROUP + j;
+                    if (t >= nprim) break;
+                    const uint32_t rect = __ldg(rects + t);
+                    if (rect == SR_RECT_INVALID || !sr_rect_hits(rect, tx, ty)) continue;
+                    if (kind == 2) sr_ord_line<FS>(c, t);
+                    else sr_ord_point<FS>(c, t);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // write the tile back once
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+        if (px >= W || py >= H) continue;
+        float *dst = sr_fb_pixel(p.fb, px, py);
+        const float4 col = s_color[i];
+        dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; dst[3] = col.w;
+        dst[4] = s_depth[i];
+        if (c.has_stencil) p.fb.stencil[(uint64_t)py * W + px] = s_stencil[i];
+        if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];
+    }
+}
+
+// materialise a pending clear (RenderBuffer::clear, renderbuffer/mod.rs:126-133) when no draw did it
+__global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)fb.width * fb.height) return;
+    float *dst = fb.aos + i * 5;
+    dst[0] = fb.clear[0]; dst[1] = fb.clear[1]; dst[2] = fb.clear[2]; dst[3] = fb.clear[3];
+    dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+    if (fb.stencil) fb.stencil[i] = 0;
+    if (fb.winner) fb.winner[i] = 0;
+}
+__global__ void __launch_bounds__(256) k_fb_split(const float *aos, uint64_t n, float *color, float *depth) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (color) { color[i * 4] = aos[i * 5]; color[i * 4 + 1] = aos[i * 5 + 1]; color[i * 4 + 2] = aos[i * 5 + 2]; color[i * 4 + 3] = aos[i * 5 + 3]; }
+    if (depth) depth[i] = aos[i * 5 + 4];
+}
+__global__ void __launch_bounds__(256) k_fb_merge(float *aos, uint64_t n, const float *color, const float *depth) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (color) { aos[i * 5] = color[i * 4]; aos[i * 5 + 1] = color[i * 4 + 1]; aos[i * 5 + 2] = color[i * 4 + 2]; aos[i * 5 + 3] = color[i * 4 + 3]; }
+    if (depth) aos[i * 5 + 4] = depth[i];
+}

@@ -1,0 +1,238 @@
+// sr_shaders.cuh -- the registered set of device-function shaders that replaces the reference's
+// Rust shader closures.  Each mirrors one closure the reference ships.
+#pragma once
+
+#include "sr_common.cuh"
+
+// ---- vertex stage constants: uniforms + products that are identical for every vertex -------------
+// `projection * view * world` is left-associative in Rust, so the reference recomputes the 4x4
+// product per vertex (examples/suzanne.rs:134, full_example/src/shaders.rs:20); it is the same
+// value every time, so it is computed once on the host with the same f32 operation order.
+struct SrVsConst {
+    sr_uniforms u;
+    float pv[16];   // projection * view
+    float pvm[16];  // (projection * view) * model
+    float vpm[16];  // viewport matrix of ClipVertex::normalize (clipvertex.rs:107-112)
+    int normalize;  // run_to_fragment: apply ClipVertex::normalize after the shader
+};
+
+struct SrFsConst {
+    sr_uniforms u;
+    const uint8_t *tex;  // RGBA8
+    uint32_t tex_w, tex_h;
+};
+
+template <int VS> struct SrVsInfo;  // VIN = input floats (0 = runtime), NK = interpolated floats (0 = runtime)
+template <> struct SrVsInfo<SR_VS_PASSTHROUGH> { static constexpr int VIN = 0, NK = 0; };
+template <> struct SrVsInfo<SR_VS_SUZANNE> { static constexpr int VIN = 6, NK = 8; };
+template <> struct SrVsInfo<SR_VS_FULL_EXAMPLE> { static constexpr int VIN = 8, NK = 10; };
+
+// ClipVertex::normalize (src/geometry/clipvertex.rs:89-127)
+__device__ __forceinline__ void sr_normalize_vertex(const float *vpm, float *p) {
+    const float w = p[3];
+    float ndc[4] = {p[0] / w, p[1] / w, p[2] / w, 1.0f};
+    float screen[4];
+    sr_mat_vec(vpm, ndc, screen);
+    p[0] = screen[0];
+    p[1] = screen[1];
+    p[2] = screen[2];
+    p[3] = 1.0f / w;
+}
+
+// examples/suzanne.rs:123-141 and full_example/src/shaders.rs:8-31; `in` = {pos3, normal3[, uv2]},
+// `out` = {clip4, world4, normal4[, uv2]}
+template <int VS>
+__device__ __forceinline__ void sr_vertex_shader(const SrVsConst &c, const float *in, float *out) {
+    float pos_h[4] = {in[0], in[1], in[2], 1.0f};  // Point3::to_homogeneous
+    float nrm_h[4] = {in[3], in[4], in[5], 0.0f};  // Vector3::to_homogeneous
+    float n[4];
+    sr_mat_vec(c.u.model, pos_h, out + 4);          // world_position = model * position
+    sr_mat_vec(c.u.mit, nrm_h, n);
+    sr_normalize4(n, out + 8);                      // (mit * normal).normalize()
+    if (VS == SR_VS_SUZANNE) {
+        sr_mat_vec(c.pv, out + 4, out);             // (projection * view) * world_position
+    } else {
+        sr_mat_vec(c.pvm, pos_h, out);              // mvp * position
+        out[12] = in[6];
+        out[13] = in[7];
+    }
+}
+
+// ---- fragment shaders ---------------------------------------------------------------------------------
+template <int FS> struct SrFsInfo;  // NK = interpolated floats the shader reads; DISCARDS = may return Fragment::Discard
+template <> struct SrFsInfo<SR_FS_FLAT> { static constexpr int NK = 4; static constexpr bool DISCARDS = false; };
+template <> struct SrFsInfo<SR_FS_SUZANNE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false; };
+template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false; };
+template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int NK = 10; static constexpr bool DISCARDS = false; };
+template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false; };
+template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true; };
+
+__device__ __forceinline__ float sr_saturate(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+__device__ __forceinline__ float sr_fresnel_schlick(float cos_theta, float ior) {
+    const float f0 = sr_powi2((1.0f - ior) / (1.0f + ior));
+    return f0 + (1.0f - f0) * sr_powi5(1.0f - cos_theta);
+}
+
+// full_example/src/texture.rs:47-84 (Bilinear, Clamp); the x+1 / y+1 neighbour is clamped to the
+// last texel where the reference would index out of bounds (documented deviation).
+__device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, float u, float v, float *out) {
+    u = fmaxf(fminf(u, 1.0f), 0.0f);
+    v = fmaxf(fminf(v, 1.0f), 0.0f);
+    const float uu = (u * (float)(c.tex_w - 1)) + 0.5f;
+    const float vv = (v * (float)(c.tex_h - 1)) + 0.5f;
+    const uint32_t x = (uint32_t)floorf(uu), y = (uint32_t)floorf(vv);
+    const float u_ratio = uu - (float)x, v_ratio = vv - (float)y;
+    const float u_opp = 1.0f - u_ratio, v_opp = 1.0f - v_ratio;
+    const uint32_t x0 = x < c.tex_w ? x : c.tex_w - 1, y0 = y < c.tex_h ? y : c.tex_h - 1;
+    const uint32_t x1 = x + 1 < c.tex_w ? x + 1 : c.tex_w - 1, y1 = y + 1 < c.tex_h ? y + 1 : c.tex_h - 1;
+    const uchar4 t00 = __ldg((const uchar4 *)c.tex + (size_t)y0 * c.tex_w + x0);
+    const uchar4 t10 = __ldg((const uchar4 *)c.tex + (size_t)y0 * c.tex_w + x1);
+    const uchar4 t01 = __ldg((const uchar4 *)c.tex + (size_t)y1 * c.tex_w + x0);
+    const uchar4 t11 = __ldg((const uchar4 *)c.tex + (size_t)y1 * c.tex_w + x1);
+    const float a00[4] = {(float)t00.x / 255.0f, (float)t00.y / 255.0f, (float)t00.z / 255.0f, (float)t00.w / 255.0f};
+    const float a10[4] = {(float)t10.x / 255.0f, (float)t10.y / 255.0f, (float)t10.z / 255.0f, (float)t10.w / 255.0f};
+    const float a01[4] = {(float)t01.x / 255.0f, (float)t01.y / 255.0f, (float)t01.z / 255.0f, (float)t01.w / 255.0f};
+    const float a11[4] = {(float)t11.x / 255.0f, (float)t11.y / 255.0f, (float)t11.z / 255.0f, (float)t11.w / 255.0f};
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const float val = (a00[ch] * u_opp + a10[ch] * u_ratio) * v_opp + (a01[ch] * u_opp + a11[ch] * u_ratio) * v_ratio;
+        out[ch] = ch < 3 ? powf(val, 2.2f) : val;  // decode_gamma (full_example/src/color.rs:48-55)
+    }
+}
+
+// `sv` = interpolated ScreenVertex: position[4] then K.  Returns false for Fragment::Discard.
+template <int FS>
+__device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const float *sv, float *out) {
+    const float *K = sv + 4;
+    if (FS == SR_FS_FLAT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = K[i];
+        return true;
+    } else if (FS == SR_FS_GREEN) {  // full_example/src/shaders.rs:102
+        out[0] = 0.0f; out[1] = 1.0f; out[2] = 0.0f; out[3] = 1.0f;
+        return true;
+    } else if (FS == SR_FS_DISCARD_CHECKER) {
+        const int xi = (int)floorf(sv[0]), yi = (int)floorf(sv[1]);
+        if ((xi + yi) & 1) return false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = K[i];
+        return true;
+    } else if (FS == SR_FS_SUZANNE) {
+        // examples/suzanne.rs:147-183
+        const float *position = K, *normal = K + 4;
+        float d[4], view_dir[4], light_dir[4], h[4], halfway[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = c.u.camera[i] - position[i];
+        sr_normalize4(d, view_dir);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = c.u.sz_light[i] - position[i];
+        sr_normalize4(d, light_dir);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
+        sr_normalize4(h, halfway);
+        const float NdotL = fmaxf(fminf(sr_dot4(light_dir, normal), 1.0f), 0.0f);
+        const float NdotH = fmaxf(fminf(sr_dot4(normal, halfway), 1.0f), 0.0f);
+        const float VdotH = fmaxf(fminf(sr_dot4(view_dir, halfway), 1.0f), 0.0f);
+        const float f = sr_fresnel_schlick(VdotH, 1.45f);
+        const float diffuse = NdotL * (1.0f - f);
+        const float specular = f * powf(NdotH, 32.0f * 2.0f);
+        const float inv_gamma = 1.0f / 2.2f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = powf(c.u.sz_intensity * (specular + (diffuse * c.u.sz_color[i])), inv_gamma);
+        out[3] = 1.0f;
+        return true;
+    } else {
+        // full_example/src/shaders.rs:108-162
+        const float *position = K, *normal = K + 4;
+        float d[4], view_dir[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = c.u.camera[i] - position[i];
+        sr_normalize4(d, view_dir);
+        const float m = powf(0.25f, 2.2f);
+        float material[3] = {m, m, m};
+        if (FS == SR_FS_FULL_EXAMPLE_TEXTURED) {
+            if (c.tex != nullptr) {
+                float t[4];
+                sr_texture_bilinear_clamp(c, K[8], K[9], t);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) material[i] = material[i] * t[i];
+            }
+        }
+        const float albedo = 0.7f;
+        float color[3] = {0.0f, 0.0f, 0.0f};
+        const uint32_t nl = c.u.nlights < SR_MAX_LIGHTS ? c.u.nlights : SR_MAX_LIGHTS;
+        for (uint32_t l = 0; l < nl; ++l) {
+            const sr_light &light = c.u.lights[l];
+            const float lp[4] = {light.position[0], light.position[1], light.position[2], 1.0f};
+            float ld[4], light_dir[4], h[4], halfway[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ld[i] = lp[i] - position[i];
+            const float light_distance = sr_norm4(ld);
+            sr_normalize4(ld, light_dir);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
+            sr_normalize4(h, halfway);
+            const float intensity = light.intensity / sr_powi2(light_distance);
+            const float NdotL = sr_saturate(sr_dot4(light_dir, normal));
+            const float NdotH = sr_saturate(sr_dot4(normal, halfway));
+            const float VdotH = sr_saturate(sr_dot4(view_dir, halfway));
+            const float f = sr_fresnel_schlick(VdotH, 1.45f);
+            const float diffuse = (1.0f - f) * NdotL;
+            const float specular = f * sr_powi64(NdotH);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                color[i] = color[i] + intensity * light.color[i] * (specular + (diffuse * albedo * material[i]));
+        }
+        const float inv_gamma = 1.0f / 2.2f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float x = color[i];  // aces_filmic_tonemap_component (full_example/src/color.rs:20-28)
+            const float tm = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
+            out[i] = powf(tm, inv_gamma);
+        }
+        out[3] = 1.0f;
+        return true;
+    }
+}
+
+// Blend (src/color/blend.rs:28-31 for `()`; full_example/src/color.rs:5-17 for alpha-over)
+__device__ __forceinline__ void sr_blend(uint32_t mode, const float *a, const float *b, float *out) {
+    if (mode == SR_BLEND_ALPHA_OVER) {
+        const float a1 = 1.0f - a[3];
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = (a[i] * a[3] + b[i] * b[3] * a1) / (a[3] + b[3] * a1);
+        r[3] = a[3] + b[3] * (1.0f - a[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = r[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = a[i];
+    }
+}
+
+// StencilTest::test / StencilOp::op (src/stencil.rs:112-123,147-158) on u8
+__device__ __forceinline__ bool sr_stencil_test_fn(uint32_t test, uint8_t value, uint8_t mask) {
+    switch (test) {
+        case SR_STENCIL_ALWAYS: return true;
+        case SR_STENCIL_NEVER: return false;
+        case SR_STENCIL_LESS_THAN: return mask < value;
+        case SR_STENCIL_LESS_THAN_EQ: return mask <= value;
+        case SR_STENCIL_GREATER_THAN: return mask > value;
+        case SR_STENCIL_GREATER_THAN_EQ: return mask >= value;
+        case SR_STENCIL_EQUAL: return mask == value;
+        default: return mask != value;
+    }
+}
+__device__ __forceinline__ uint8_t sr_stencil_op_fn(uint32_t op, uint8_t value, uint8_t mask) {
+    switch (op) {
+        case SR_STENCIL_KEEP: return value;
+        case SR_STENCIL_INVERT: return (uint8_t)~value;
+        case SR_STENCIL_ZERO: return 0;
+        case SR_STENCIL_REPLACE: return mask;
+        case SR_STENCIL_INCREMENT_WRAP: return (uint8_t)(value + 1);
+        case SR_STENCIL_DECREMENT_WRAP: return (uint8_t)(value - 1);
+        case SR_STENCIL_INCREMENT_SAT: return value == 255 ? (uint8_t)255 : (uint8_t)(value + 1);
+        default: return value == 0 ? (uint8_t)0 : (uint8_t)(value - 1);
+    }
+}

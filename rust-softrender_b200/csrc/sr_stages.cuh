@@ -1,0 +1,442 @@
+// sr_stages.cuh -- vertex stage, geometry stage (clipper + registered geometry shaders), finish.
+#pragma once
+
+#include "sr_shaders.cuh"
+
+// =====================================================================================================
+// exclusive scan of u32 (three small kernels; inputs here are <= a few hundred MB)
+// =====================================================================================================
+#define SR_SCAN_THREADS 256
+#define SR_SCAN_ITEMS 8
+#define SR_SCAN_BLOCK (SR_SCAN_THREADS * SR_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t sr_block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *warp_sums) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t nw = blockDim.x >> 5;
+        uint32_t s = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += n;
+        }
+        if (lane < nw) warp_sums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t warp_base = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return warp_base + inc - v;
+}
+
+__global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_reduce(const uint32_t *in, uint64_t n, uint32_t *block_sums) {
+    __shared__ uint32_t ws[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SR_SCAN_BLOCK + (uint64_t)threadIdx.x * SR_SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SR_SCAN_ITEMS; ++i)
+        if (base + i < n) s += in[base + i];
+    uint32_t total;
+    sr_block_exclusive_scan(s, &total, ws);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of block_sums in place, grand total to *total
+__global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_sums(uint32_t *block_sums, uint32_t nblocks, uint32_t *total) {
+    __shared__ uint32_t ws[32];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblocks; base += SR_SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_sums[i] : 0;
+        uint32_t t;
+        const uint32_t ex = sr_block_exclusive_scan(v, &t, ws);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += t;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_apply(const uint32_t *in, uint64_t n, const uint32_t *block_sums,
+                                                                uint32_t *out) {
+    __shared__ uint32_t ws[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SR_SCAN_BLOCK + (uint64_t)threadIdx.x * SR_SCAN_ITEMS;
+    uint32_t v[SR_SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SR_SCAN_ITEMS; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t ex = sr_block_exclusive_scan(s, nullptr, ws) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SR_SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+}
+
+// =====================================================================================================
+// a2: vertex stage (VertexShader::run / run_to_fragment, src/pipeline/stages/vertex.rs:87-160)
+// One thread shades four consecutive vertices: each SoA input plane is read with one float4 load,
+// outputs are float4 stores (position plane + ceil(nk/4) attribute planes).
+// =====================================================================================================
+struct SrMeshView {
+    const float *planes;  // plane c starts at planes + c*pstride; pstride is a multiple of 4
+    uint64_t pstride;
+    uint64_t nverts;
+    uint32_t vin;
+};
+
+template <int VS>
+__global__ void __launch_bounds__(128) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
+                                                float4 *attr, const uint64_t ostride) {
+    constexpr int VIN = SrVsInfo<VS>::VIN, NK = SrVsInfo<VS>::NK, NP = (NK + 3) / 4;
+    const uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (base >= m.nverts) return;
+    float in[4][VIN];
+#pragma unroll
+    for (int ch = 0; ch < VIN; ++ch) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(m.planes + (uint64_t)ch * m.pstride + base));
+        in[0][ch] = v.x; in[1][ch] = v.y; in[2][ch] = v.z; in[3][ch] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j >= m.nverts) break;
+        float out[4 + NP * 4];
+#pragma unroll
+        for (int i = 4 + NK; i < 4 + NP * 4; ++i) out[i] = 0.0f;
+        sr_vertex_shader<VS>(c, in[j], out);
+        if (c.normalize) sr_normalize_vertex(c.vpm, out);
+        pos[base + j] = make_float4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            attr[(uint64_t)p * ostride + base + j] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
+    }
+}
+
+// SR_VS_PASSTHROUGH (test shader): Vin = {x,y,z,w,k...}, any nk <= SR_MAX_NK; one vertex per thread.
+__global__ void __launch_bounds__(128) k_vertex_passthrough(const __grid_constant__ SrVsConst c, const SrMeshView m,
+                                                            float4 *pos, float4 *attr, const uint64_t ostride) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.nverts) return;
+    float p[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) p[ch] = m.planes[(uint64_t)ch * m.pstride + i];
+    if (c.normalize) sr_normalize_vertex(c.vpm, p);
+    pos[i] = make_float4(p[0], p[1], p[2], p[3]);
+    const uint32_t nk = m.vin - 4, np = (nk + 3) / 4;
+    for (uint32_t pl = 0; pl < np; ++pl) {
+        float k[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t ch = 4 + pl * 4 + j;
+            k[j] = ch < m.vin ? m.planes[(uint64_t)ch * m.pstride + i] : 0.0f;
+        }
+        attr[(uint64_t)pl * ostride + i] = make_float4(k[0], k[1], k[2], k[3]);
+    }
+}
+
+// a3: GeometryShader::finish (src/pipeline/stages/geometry.rs:60-129): normalize every position in place
+__global__ void __launch_bounds__(256) k_normalize(float4 *pos, uint64_t n, const __grid_constant__ SrVsConst c) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = pos[i];
+    float p[4] = {v.x, v.y, v.z, v.w};
+    sr_normalize_vertex(c.vpm, p);
+    pos[i] = make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// AoS -> SoA plane transpose used by mesh upload and vertex injection
+__global__ void __launch_bounds__(256) k_aos_to_planes(const float *aos, uint64_t n, uint32_t nfloats, float *planes,
+                                                       uint64_t pstride) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * nfloats) return;
+    const uint64_t v = i / nfloats;
+    const uint32_t ch = (uint32_t)(i % nfloats);
+    planes[(uint64_t)ch * pstride + v] = aos[i];
+}
+// records {pos4, k[nk]} (AoS) -> pos plane + attribute planes
+__global__ void __launch_bounds__(256) k_records_to_planes(const float *rec, uint64_t n, uint32_t nk, float4 *pos, float4 *attr,
+                                                           uint64_t ostride) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r = rec + i * (4 + nk);
+    pos[i] = make_float4(r[0], r[1], r[2], r[3]);
+    const uint32_t np = (nk + 3) / 4;
+    for (uint32_t p = 0; p < np; ++p) {
+        float k[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) k[j] = (p * 4 + j) < nk ? r[4 + p * 4 + j] : 0.0f;
+        attr[(uint64_t)p * ostride + i] = make_float4(k[0], k[1], k[2], k[3]);
+    }
+}
+__global__ void __launch_bounds__(256) k_planes_to_records(const float4 *pos, const float4 *attr, uint64_t stride, uint64_t n,
+                                                           uint32_t nk, float *rec) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *r = rec + i * (4 + nk);
+    const float4 p = pos[i];
+    r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
+    const uint32_t np = (nk + 3) / 4;
+    for (uint32_t pl = 0; pl < np; ++pl) {
+        const float4 a = attr[(uint64_t)pl * stride + i];
+        const float k[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (pl * 4 + j < nk) r[4 + pl * 4 + j] = k[j];
+    }
+}
+// usize (u64) indices -> u32
+__global__ void __launch_bounds__(256) k_narrow_indices(const uint64_t *in, uint64_t n, uint32_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+
+// =====================================================================================================
+// a4: geometry stage (GeometryShader::run / clip_primitives, src/pipeline/stages/geometry.rs:132-336)
+// Input primitives of one kind in the reference's visit order: generated first, then the indexed mesh.
+// =====================================================================================================
+struct SrGeoIn {
+    SrVertexSet gen;
+    uint32_t ngen;  // primitives
+    SrVertexSet idx;
+    const uint32_t *indices;
+    uint32_t nidx;  // primitives
+    uint32_t nplanes;
+};
+struct SrGeoOut {
+    float4 *pos;
+    float4 *attr;
+    uint64_t stride;
+};
+
+template <int NV>
+__device__ __forceinline__ void sr_geo_load(const SrGeoIn &in, uint32_t prim, float rec[NV][4 + SR_MAX_NK]) {
+    const SrVertexSet &vs = prim < in.ngen ? in.gen : in.idx;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const uint32_t vi = prim < in.ngen ? prim * NV + k : __ldg(in.indices + (uint64_t)(prim - in.ngen) * NV + k);
+        const float4 p = vs.pos[vi];
+        rec[k][0] = p.x; rec[k][1] = p.y; rec[k][2] = p.z; rec[k][3] = p.w;
+        for (uint32_t pl = 0; pl < in.nplanes; ++pl) {
+            const float4 a = vs.attr[(uint64_t)pl * vs.stride + vi];
+            rec[k][4 + pl * 4] = a.x; rec[k][5 + pl * 4] = a.y; rec[k][6 + pl * 4] = a.z; rec[k][7 + pl * 4] = a.w;
+        }
+    }
+}
+__device__ __forceinline__ void sr_geo_store(const SrGeoOut &out, uint64_t at, const float *rec, uint32_t nplanes) {
+    out.pos[at] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+    for (uint32_t pl = 0; pl < nplanes; ++pl)
+        out.attr[(uint64_t)pl * out.stride + at] = make_float4(rec[4 + pl * 4], rec[5 + pl * 4], rec[6 + pl * 4], rec[7 + pl * 4]);
+}
+
+// ClippingPlane::has_inside / intersect (src/geometry/clip.rs:33-63)
+__device__ __forceinline__ bool sr_has_inside(int plane, const float *v) {
+    const float x = v[0], y = v[1], z = v[2], w = v[3];
+    switch (plane) {
+        case 0: return x >= -w;
+        case 1: return x <= w;
+        case 2: return y >= -w;
+        case 3: return y <= w;
+        case 4: return z >= 0.0f;
+        default: return z <= w;
+    }
+}
+__device__ __forceinline__ void sr_intersect(int plane, const float *v1, const float *v2, uint32_t nfloats, float *out) {
+    float a, b;
+    switch (plane) {
+        case 0: a = v1[3] + v1[0]; b = v2[3] + v2[0]; break;
+        case 1: a = v1[3] - v1[0]; b = v2[3] - v2[0]; break;
+        case 2: a = v1[3] + v1[1]; b = v2[3] + v2[1]; break;
+        case 3: a = v1[3] - v1[1]; b = v2[3] - v2[1]; break;
+        case 4: a = v1[2]; b = v2[2]; break;
+        default: a = v1[3] - v1[2]; b = v2[3] - v2[2]; break;
+    }
+    const float t = a / (a - b);
+    for (uint32_t i = 0; i < nfloats; ++i) out[i] = sr_lerp(t, v1[i], v2[i]);
+}
+
+// The triangle clipper, literally (geometry.rs:265-298), but symbolic: polygon entries are ids
+// 0..2 = the input vertices a,b,c and 3 + edge*6 + plane = intersect(plane, edge.s, edge.p).
+// Two entries with the same id are bit-identical vertices.
+__device__ __forceinline__ int sr_clip_polygon(const float rec[3][4 + SR_MAX_NK], uint8_t *poly) {
+    int n = 0;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int s = e, p = e == 2 ? 0 : e + 1;
+#pragma unroll
+        for (int plane = 0; plane < 6; ++plane) {
+            const bool s_in = sr_has_inside(plane, rec[s]);
+            const bool p_in = sr_has_inside(plane, rec[p]);
+            if (s_in != p_in) poly[n++] = (uint8_t)(3 + e * 6 + plane);
+            if (p_in) poly[n++] = (uint8_t)p;
+        }
+    }
+    return n;
+}
+__device__ __forceinline__ int sr_clip_tri_count(int n) { return n == 3 ? 1 : (n > 3 ? n - 2 : 0); }
+__device__ __forceinline__ void sr_clip_tri_ids(const uint8_t *poly, int n, int i, uint8_t ids[3]) {
+    if (n == 3) { ids[0] = poly[0]; ids[1] = poly[1]; ids[2] = poly[2]; }
+    else { ids[0] = poly[n - 1]; ids[1] = poly[i]; ids[2] = poly[i + 1]; }
+}
+// A triangle with two bit-identical vertices has det == +-0 exactly and can never produce a
+// fragment (triangle.rs:64,108-113,120); with stencil op Keep it has no observable effect at all.
+__device__ __forceinline__ bool sr_clip_tri_degenerate(const uint8_t ids[3]) {
+    return ids[0] == ids[1] || ids[0] == ids[2] || ids[1] == ids[2];
+}
+
+// pass 1: per input triangle, number of kept and of literal output triangles
+__global__ void __launch_bounds__(128) k_clip_tri_count(const SrGeoIn in, uint32_t drop_degenerate, uint32_t *kept,
+                                                        uint32_t *literal) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[3][4 + SR_MAX_NK];
+    sr_geo_load<3>(in, t, rec);
+    uint8_t poly[36];
+    const int n = sr_clip_polygon(rec, poly);
+    const int nt = sr_clip_tri_count(n);
+    int k = 0;
+    for (int i = 0; i < nt; ++i) {
+        uint8_t ids[3];
+        sr_clip_tri_ids(poly, n, i, ids);
+        if (!(drop_degenerate && sr_clip_tri_degenerate(ids))) ++k;
+    }
+    kept[t] = (uint32_t)k;
+    literal[t] = (uint32_t)nt;
+}
+// pass 2: materialise the kept triangles at their scanned offsets (order-preserving compaction)
+__global__ void __launch_bounds__(128) k_clip_tri_emit(const SrGeoIn in, uint32_t drop_degenerate, const uint32_t *kept_off,
+                                                       const uint32_t *literal_off, SrGeoOut out, uint32_t *seq) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[3][4 + SR_MAX_NK];
+    sr_geo_load<3>(in, t, rec);
+    uint8_t poly[36];
+    const int n = sr_clip_polygon(rec, poly);
+    const int nt = sr_clip_tri_count(n);
+    const uint32_t nfloats = 4 + in.nplanes * 4;
+    uint32_t o = kept_off[t];
+    const uint32_t lbase = literal_off[t];
+    float tmp[4 + SR_MAX_NK];
+    for (int i = 0; i < nt; ++i) {
+        uint8_t ids[3];
+        sr_clip_tri_ids(poly, n, i, ids);
+        if (drop_degenerate && sr_clip_tri_degenerate(ids)) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int id = ids[k];
+            if (id < 3) {
+                sr_geo_store(out, (uint64_t)o * 3 + k, rec[id], in.nplanes);
+            } else {
+                const int e = (id - 3) / 6, plane = (id - 3) % 6;
+                sr_intersect(plane, rec[e], rec[e == 2 ? 0 : e + 1], nfloats, tmp);
+                sr_geo_store(out, (uint64_t)o * 3 + k, tmp, in.nplanes);
+            }
+        }
+        seq[o] = lbase + (uint32_t)i;
+        ++o;
+    }
+}
+
+// line clipper (geometry.rs:300-327): MODE 0 = count, 1 = emit
+template <int MODE>
+__global__ void __launch_bounds__(128) k_clip_line(const SrGeoIn in, uint32_t *count, const uint32_t *off, SrGeoOut out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[2][4 + SR_MAX_NK];
+    sr_geo_load<2>(in, t, rec);
+    const uint32_t nfloats = 4 + in.nplanes * 4;
+    float tmp[4 + SR_MAX_NK];
+    int intersections = 0;
+    bool emit = true;
+    for (int plane = 0; plane < 6; ++plane) {
+        const bool s_in = sr_has_inside(plane, rec[0]);
+        const bool p_in = sr_has_inside(plane, rec[1]);
+        if (s_in != p_in) {
+            sr_intersect(plane, rec[0], rec[1], nfloats, tmp);
+            float *dst = s_in ? rec[1] : rec[0];  // `if s_in { end = .. } else if p_in { start = .. }`
+            for (uint32_t i = 0; i < nfloats; ++i) dst[i] = tmp[i];
+            intersections += 1;
+        } else if (!s_in) {
+            emit = false;
+            break;
+        }
+        if (intersections > 2) break;
+    }
+    if (MODE == 0) {
+        count[t] = emit ? 1u : 0u;
+    } else if (emit) {
+        const uint32_t o = off[t];
+        sr_geo_store(out, (uint64_t)o * 2, rec[0], in.nplanes);
+        sr_geo_store(out, (uint64_t)o * 2 + 1, rec[1], in.nplanes);
+    }
+}
+// point clipper (geometry.rs:329-333)
+template <int MODE>
+__global__ void __launch_bounds__(128) k_clip_point(const SrGeoIn in, uint32_t *count, const uint32_t *off, SrGeoOut out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[1][4 + SR_MAX_NK];
+    sr_geo_load<1>(in, t, rec);
+    bool inside = true;
+#pragma unroll
+    for (int plane = 0; plane < 6; ++plane) inside = inside && sr_has_inside(plane, rec[0]);
+    if (MODE == 0) count[t] = inside ? 1u : 0u;
+    else if (inside) sr_geo_store(out, off[t], rec[0], in.nplanes);
+}
+
+// `_ => storage.re_emit(primitive)`: copy a primitive stream through unchanged
+template <int NV>
+__global__ void __launch_bounds__(128) k_geo_reemit(const SrGeoIn in, SrGeoOut out, uint64_t out_base) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[NV][4 + SR_MAX_NK];
+    sr_geo_load<NV>(in, t, rec);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sr_geo_store(out, out_base + (uint64_t)t * NV + k, rec[k], in.nplanes);
+}
+
+// geometry_shader_visualize_{face,vertex}_normals (full_example/src/shaders.rs:35-89): triangle -> lines
+#define SR_NORMAL_LENGTH 0.05f
+template <int GS>
+__global__ void __launch_bounds__(128) k_geo_normals(const SrGeoIn in, const __grid_constant__ SrVsConst c, SrGeoOut out,
+                                                     uint64_t out_base) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[3][4 + SR_MAX_NK];
+    sr_geo_load<3>(in, t, rec);
+    const uint32_t nk = in.nplanes * 4;
+    float o[4 + SR_MAX_NK];
+    if (GS == SR_GS_FACE_NORMALS) {
+        const float third = 1.0f / 3.0f;
+        float center[SR_MAX_NK];
+        for (uint32_t i = 0; i < nk; ++i) center[i] = sr_bary(third, rec[0][4 + i], third, rec[1][4 + i], third, rec[2][4 + i]);
+        float nn[4], tip[4];
+        sr_normalize4(center + 4, nn);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tip[i] = center[i] + nn[i] * SR_NORMAL_LENGTH;
+        for (uint32_t i = 0; i < nk; ++i) o[4 + i] = center[i];
+        sr_mat_vec(c.pv, center, o);
+        sr_geo_store(out, out_base + (uint64_t)t * 2, o, in.nplanes);
+        sr_mat_vec(c.pv, tip, o);
+        sr_geo_store(out, out_base + (uint64_t)t * 2 + 1, o, in.nplanes);
+    } else {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            float tip[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tip[i] = rec[v][4 + i] + rec[v][8 + i] * SR_NORMAL_LENGTH;
+            for (uint32_t i = 0; i < nk; ++i) o[4 + i] = rec[v][4 + i];
+            sr_mat_vec(c.pv, rec[v] + 4, o);
+            sr_geo_store(out, out_base + (uint64_t)t * 6 + v * 2, o, in.nplanes);
+            sr_mat_vec(c.pv, tip, o);
+            sr_geo_store(out, out_base + (uint64_t)t * 6 + v * 2 + 1, o, in.nplanes);
+        }
+    }
+}

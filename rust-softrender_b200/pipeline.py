@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's builder API over the C ABI.
+
+Same verbs, argument meaning and error behaviour as the Rust types (panics become SoftrenderError):
+
+    Pipeline.from_framebuffer(fb, uniforms)              src/pipeline/mod.rs:120
+      .render_mesh(TRIANGLE, mesh, stencil=None)         src/pipeline/mod.rs:146            -> VertexShader
+         .run(VS_*)                                      src/pipeline/stages/vertex.rs:87   -> GeometryShader
+            .run(GS_*) / .clip_primitives()              src/pipeline/stages/geometry.rs:132,261
+            .finish(viewport)                            src/pipeline/stages/geometry.rs:60 -> FragmentShader
+         .run_to_fragment(viewport, VS_*)                src/pipeline/stages/vertex.rs:123  -> FragmentShader
+               .with_blend / cull_faces / tile_size ...  src/pipeline/stages/fragment.rs:82-160
+               .run(FS_*)                                src/pipeline/stages/fragment.rs:168
+
+Shaders are ids of the registered CUDA device functions (softrender_b200.constants) instead of closures.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from ._abi import check, lib
+from .constants import *  # noqa: F401,F403
+from .scenes import MeshData, Uniforms, Viewport
+
+
+def _vp(p=None):
+    return ctypes.c_void_p(p)
+
+
+class Context:
+    """Owns the device, the CUDA stream and scratch memory (replaces the thread pool of Pipeline::new)."""
+
+    def __init__(self, device: int = 0):
+        h = ctypes.c_void_p()
+        check(lib.sr_context_create(device, ctypes.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib.sr_context_destroy(self.h)
+            self.h = None
+
+    def synchronize(self):
+        check(lib.sr_context_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return lib.sr_context_stream(self.h) or 0
+
+    def set_tile_shard(self, rank: int, world: int):
+        check(lib.sr_context_set_tile_shard(self.h, rank, world))
+
+    def launch_count(self) -> int:
+        n = ctypes.c_uint64()
+        check(lib.sr_context_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    def stage_times(self) -> dict:
+        t = _abi.StageTimes()
+        check(lib.sr_context_stage_times(self.h, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+
+def tile_size():
+    w, h = ctypes.c_uint32(), ctypes.c_uint32()
+    check(lib.sr_tile_size(ctypes.byref(w), ctypes.byref(h)))
+    return w.value, h.value
+
+
+class RenderBuffer:
+    """RenderBuffer<ColorDepth[Stencil]Attachments<RGBAf32Color, f32[, u8]>> (src/framebuffer/renderbuffer/mod.rs)."""
+
+    def __init__(self, ctx: Context, handle, width, height, fmt):
+        self.ctx, self.h, self.width, self.height, self.format = ctx, handle, width, height, fmt
+
+    @staticmethod
+    def with_dimensions(ctx: Context, width: int, height: int, stencil: bool = False) -> "RenderBuffer":
+        fmt = FB_RGBAF32_DF32_S8 if stencil else FB_RGBAF32_DF32
+        h = ctypes.c_void_p()
+        check(lib.sr_framebuffer_create(ctx.h, width, height, fmt, ctypes.byref(h)))
+        return RenderBuffer(ctx, h, width, height, fmt)
+
+    def destroy(self):
+        if self.h:
+            lib.sr_framebuffer_destroy(self.h)
+            self.h = None
+
+    def dimensions(self):
+        return self.width, self.height
+
+    def clear(self, color):
+        c = (ctypes.c_float * 4)(*[float(x) for x in color])
+        check(lib.sr_framebuffer_clear(self.h, c))
+
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """AoS read-back: float32 [height*width, 5] = {r,g,b,a,depth}, index = x + y*width."""
+        n = self.width * self.height
+        if out is None:
+            out = np.empty((n, 5), np.float32)
+        check(lib.sr_framebuffer_download(self.h, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def download_planes(self, stencil: bool = False):
+        n = self.width * self.height
+        color, depth = np.empty((n, 4), np.float32), np.empty(n, np.float32)
+        st = np.empty(n, np.uint8) if stencil else None
+        check(lib.sr_framebuffer_download_planes(self.h, color.ctypes.data_as(_abi.f32p), depth.ctypes.data_as(_abi.f32p),
+                                                 st.ctypes.data_as(_abi.u8p) if st is not None else None))
+        return color, depth, st
+
+    def upload_planes(self, color=None, depth=None, stencil=None):
+        c = np.ascontiguousarray(color, np.float32) if color is not None else None
+        d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
+        s = np.ascontiguousarray(stencil, np.uint8) if stencil is not None else None
+        check(lib.sr_framebuffer_upload_planes(self.h, c.ctypes.data_as(_abi.f32p) if c is not None else None,
+                                               d.ctypes.data_as(_abi.f32p) if d is not None else None,
+                                               s.ctypes.data_as(_abi.u8p) if s is not None else None))
+
+    def pixel(self, x: int, y: int):
+        """Checked accessor (PixelRead::pixel_ref): raises SoftrenderError(ERR_INVALID_PIXEL_COORDINATE) out of range."""
+        rgba = (ctypes.c_float * 4)()
+        d, s = ctypes.c_float(), ctypes.c_uint8()
+        check(lib.sr_framebuffer_get_pixel(self.h, x, y, rgba, ctypes.byref(d), ctypes.byref(s)))
+        return tuple(rgba), d.value, s.value
+
+    def enable_winner(self, enable: bool = True):
+        check(lib.sr_framebuffer_enable_winner(self.h, 1 if enable else 0))
+
+    def download_winner(self) -> np.ndarray:
+        w = np.empty(self.width * self.height, np.uint32)
+        check(lib.sr_framebuffer_download_winner(self.h, w.ctypes.data_as(_abi.u32p)))
+        return w
+
+    def device_ptr(self) -> int:
+        return lib.sr_framebuffer_device_ptr(self.h) or 0
+
+    def ipc_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        check(lib.sr_framebuffer_ipc_export(self.h, buf))
+        return buf.raw
+
+    @staticmethod
+    def ipc_open(ctx: Context, handle: bytes, width: int, height: int) -> "RenderBuffer":
+        h = ctypes.c_void_p()
+        check(lib.sr_framebuffer_ipc_open(ctx.h, ctypes.create_string_buffer(handle, 64), width, height, FB_RGBAF32_DF32, ctypes.byref(h)))
+        return RenderBuffer(ctx, h, width, height, FB_RGBAF32_DF32)
+
+
+class Mesh:
+    """Arc<Mesh<V>> resident in HBM (src/mesh.rs:12-20)."""
+
+    def __init__(self, ctx: Context, data: MeshData = None, vertices=None, indices=None):
+        if data is not None:
+            vertices, indices = data.vertices, data.indices
+        v = np.ascontiguousarray(vertices, np.float32)
+        ix = np.ascontiguousarray(indices)
+        if ix.dtype not in (np.uint32, np.uint64):
+            ix = ix.astype(np.uint32)
+        h = ctypes.c_void_p()
+        check(lib.sr_mesh_create(ctx.h, v.ctypes.data_as(ctypes.c_void_p), v.shape[0], v.shape[1] if v.ndim == 2 else 0,
+                                 ix.ctypes.data_as(ctypes.c_void_p), ix.size, ix.dtype.itemsize, ctypes.byref(h)))
+        self.h, self.nverts, self.nindices = h, v.shape[0], ix.size
+
+    def destroy(self):
+        if self.h:
+            lib.sr_mesh_destroy(self.h)
+            self.h = None
+
+
+class Texture:
+    def __init__(self, ctx: Context, rgba: np.ndarray):
+        t = np.ascontiguousarray(rgba, np.uint8)
+        h = ctypes.c_void_p()
+        check(lib.sr_texture_create(ctx.h, t.ctypes.data_as(_abi.u8p), t.shape[1], t.shape[0], ctypes.byref(h)))
+        self.h = h
+
+    def destroy(self):
+        if self.h:
+            lib.sr_texture_destroy(self.h)
+            self.h = None
+
+
+class _Stage:
+    def __init__(self, pipeline: "Pipeline", handle):
+        self.pipeline, self.h = pipeline, handle
+
+    def _take(self):
+        h, self.h = self.h, None
+        if h is None:
+            raise _abi.SoftrenderError(ERR_INVALID_STATE, "stage object already consumed (stage transitions take `self`)")
+        return h
+
+    def destroy(self):
+        if self.h:
+            lib.sr_draw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # parity-test introspection
+    def download(self, which: int) -> np.ndarray:
+        n, nk = ctypes.c_uint64(), ctypes.c_uint32()
+        check(lib.sr_draw_count(self.h, which, ctypes.byref(n), ctypes.byref(nk)))
+        out = np.zeros((n.value, 4 + nk.value), np.float32)
+        if n.value:
+            check(lib.sr_draw_download(self.h, which, out.ctypes.data_as(_abi.f32p), out.size))
+        return out
+
+    def download_sequence(self) -> np.ndarray:
+        n, nk = ctypes.c_uint64(), ctypes.c_uint32()
+        check(lib.sr_draw_count(self.h, 3, ctypes.byref(n), ctypes.byref(nk)))
+        out = np.zeros(n.value // 3, np.uint32)
+        if out.size:
+            check(lib.sr_draw_download_sequence(self.h, out.ctypes.data_as(_abi.u32p), out.size))
+        return out
+
+    def set_generated(self, which: int, verts: np.ndarray):
+        v = np.ascontiguousarray(verts, np.float32)
+        check(lib.sr_draw_set_generated(self.h, which, v.ctypes.data_as(_abi.f32p), v.shape[0], v.shape[1] - 4))
+        return self
+
+
+class VertexShader(_Stage):
+    def duplicate(self) -> "VertexShader":
+        h = ctypes.c_void_p()
+        check(lib.sr_draw_duplicate(self.h, ctypes.byref(h)))
+        return VertexShader(self.pipeline, h)
+
+    def run(self, vertex_shader: int) -> "GeometryShader":
+        check(lib.sr_vertex_run(self.h, vertex_shader))
+        return GeometryShader(self.pipeline, self._take())
+
+    def run_to_fragment(self, viewport: Viewport, vertex_shader: int) -> "FragmentShader":
+        check(lib.sr_vertex_run_to_fragment(self.h, ctypes.byref(viewport), vertex_shader))
+        return FragmentShader(self.pipeline, self._take())
+
+
+class GeometryShader(_Stage):
+    def duplicate(self) -> "GeometryShader":
+        h = ctypes.c_void_p()
+        check(lib.sr_draw_duplicate(self.h, ctypes.byref(h)))
+        return GeometryShader(self.pipeline, h)
+
+    def run(self, geometry_shader: int) -> "GeometryShader":
+        check(lib.sr_geometry_run(self.h, geometry_shader))
+        return GeometryShader(self.pipeline, self._take())
+
+    def clip_primitives(self) -> "GeometryShader":
+        check(lib.sr_geometry_clip_primitives(self.h))
+        return GeometryShader(self.pipeline, self._take())
+
+    def finish(self, viewport: Viewport) -> "FragmentShader":
+        check(lib.sr_geometry_finish(self.h, ctypes.byref(viewport)))
+        return FragmentShader(self.pipeline, self._take())
+
+
+class FragmentShader(_Stage):
+    def duplicate(self) -> "FragmentShader":
+        h = ctypes.c_void_p()
+        check(lib.sr_draw_duplicate(self.h, ctypes.byref(h)))
+        return FragmentShader(self.pipeline, h)
+
+    def cull_faces(self, winding: Optional[int]) -> "FragmentShader":
+        check(lib.sr_fragment_set_cull_faces(self.h, CULL_NONE if winding is None else winding))
+        return self
+
+    def antialiased_lines(self, enable: bool) -> "FragmentShader":
+        check(lib.sr_fragment_set_antialiased_lines(self.h, 1 if enable else 0))
+        return self
+
+    def tile_size(self, width: int, height: int) -> "FragmentShader":
+        check(lib.sr_fragment_set_tile_size(self.h, width, height))
+        return self
+
+    def with_blend(self, blend: int) -> "FragmentShader":
+        check(lib.sr_fragment_set_blend(self.h, blend))
+        return self
+
+    def bins(self):
+        ntx = (self.pipeline.fb.width + tile_size()[0] - 1) // tile_size()[0]
+        nty = (self.pipeline.fb.height + tile_size()[1] - 1) // tile_size()[1]
+        offsets = np.zeros(ntx * nty + 1, np.uint64)
+        total = ctypes.c_uint64()
+        check(lib.sr_draw_bins(self.h, offsets.ctypes.data_as(_abi.u64p), None, 0, ctypes.byref(total)))
+        ids = np.zeros(max(total.value, 1), np.uint32)
+        check(lib.sr_draw_bins(self.h, offsets.ctypes.data_as(_abi.u64p), ids.ctypes.data_as(_abi.u32p), ids.size, ctypes.byref(total)))
+        return offsets, ids[:total.value]
+
+    def run(self, fragment_shader: int) -> None:
+        """Draws (consumes the stage, like `FragmentShader::run(self, ..)`)."""
+        check(lib.sr_fragment_run(self.h, fragment_shader))
+        self.destroy()
+
+    def run_keep(self, fragment_shader: int) -> "FragmentShader":
+        """Draw without consuming (what `duplicate().run(..)` does in the reference)."""
+        check(lib.sr_fragment_run(self.h, fragment_shader))
+        return self
+
+
+class Pipeline:
+    """Pipeline<U, F, S> (src/pipeline/mod.rs:60-157)."""
+
+    def __init__(self, ctx: Context, fb: RenderBuffer, uniforms: Uniforms):
+        h = ctypes.c_void_p()
+        check(lib.sr_pipeline_create(ctx.h, fb.h, ctypes.byref(uniforms), ctypes.byref(h)))
+        self.ctx, self.fb, self.h = ctx, fb, h
+        self._uniforms = uniforms.copy()
+
+    @staticmethod
+    def from_framebuffer(fb: RenderBuffer, uniforms: Uniforms) -> "Pipeline":
+        return Pipeline(fb.ctx, fb, uniforms)
+
+    def destroy(self):
+        if self.h:
+            lib.sr_pipeline_destroy(self.h)
+            self.h = None
+
+    def framebuffer(self) -> RenderBuffer:
+        return self.fb
+
+    def with_framebuffer(self, fb: RenderBuffer) -> "Pipeline":
+        check(lib.sr_pipeline_set_framebuffer(self.h, fb.h))
+        self.fb = fb
+        return self
+
+    def uniforms(self) -> Uniforms:
+        return self._uniforms
+
+    def set_uniforms(self, uniforms: Uniforms):
+        """`*pipeline.uniforms_mut() = uniforms`."""
+        check(lib.sr_pipeline_set_uniforms(self.h, ctypes.byref(uniforms)))
+        self._uniforms = uniforms.copy()
+
+    def set_stencil_config(self, test: int, op: int):
+        check(lib.sr_pipeline_set_stencil_config(self.h, test, op))
+
+    def bind_texture(self, tex: Optional[Texture]):
+        check(lib.sr_pipeline_bind_texture(self.h, tex.h if tex else None))
+
+    def render_mesh(self, primitive: int, mesh: Mesh, stencil: Optional[int] = None) -> VertexShader:
+        h = ctypes.c_void_p()
+        check(lib.sr_render_mesh(self.h, mesh.h, primitive, 0 if stencil is None else 1, stencil or 0, ctypes.byref(h)))
+        return VertexShader(self, h)
+
+    # parity-test injection: the state a vertex/geometry stage would have produced
+    def draw_from_vertices(self, primitive: int, verts: np.ndarray, indices: np.ndarray, space: int,
+                           stencil: Optional[int] = None):
+        v = np.ascontiguousarray(verts, np.float32)
+        ix = np.ascontiguousarray(indices, np.uint32)
+        h = ctypes.c_void_p()
+        check(lib.sr_draw_from_vertices(self.h, primitive, v.ctypes.data_as(_abi.f32p), v.shape[0], v.shape[1] - 4, space,
+                                        ix.ctypes.data_as(_abi.u32p), ix.size, 0 if stencil is None else 1, stencil or 0,
+                                        ctypes.byref(h)))
+        return (FragmentShader if space else GeometryShader)(self, h)

@@ -178,6 +178,7 @@ class OracleDraw:
     def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1):
         tw, th = self.tile if self.tile else (max(fb.width, 1), max(fb.height, 1))
         st = SoRasterState(self.cull, self.blend, 1 if self.aa else 0, tw, th, stencil_test, stencil_op)
+        fb.winner[:] = 0  # winner plane = primitives of THIS draw
         s = fb.struct()
         tex = None
         if texture is not None:

@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares
+(no compute calls here -- those need a GPU), and fails loudly instead of falling back to a CPU path."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+
+
+def test_header_symbols_are_exported():
+    _ensure_built()
+    from softrender_b200 import _abi
+    header = open(os.path.join(ROOT, "include", "softrender_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # declarations only, not prose
+    declared = set(re.findall(r"\b(sr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    missing = [s for s in sorted(declared) if not hasattr(_abi.lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert declared == set(_abi.SYMBOLS), f"binding/header mismatch: {declared ^ set(_abi.SYMBOLS)}"
+
+
+def test_enum_values_match_header():
+    import softrender_b200 as sr
+    types = open(os.path.join(ROOT, "include", "softrender_b200_types.h")).read()
+    for name, value in re.findall(r"\bSR_([A-Z0-9_]+)\s*=\s*(\d+)", types):
+        if hasattr(sr, name):
+            assert getattr(sr, name) == int(value), name
+
+
+def test_uniforms_struct_layout():
+    import ctypes
+    from softrender_b200.scenes import Light, Uniforms, Viewport
+    assert ctypes.sizeof(Light) == 32 and ctypes.sizeof(Viewport) == 24
+    assert ctypes.sizeof(Uniforms) == 4 * (4 + 64 + 4 + 4 + 1 + 3) + 8 * 32
+    assert Uniforms.lights.offset == 320
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device every entry point must fail loudly (status != 0), never compute on the CPU."""
+    _ensure_built()
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from softrender_b200 import pipeline
+    from softrender_b200._abi import SoftrenderError
+    with pytest.raises(SoftrenderError) as e:
+        pipeline.Context(0)
+    assert e.value.status == 3  # SR_ERR_CUDA
+
+
+def test_product_sources_do_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "rust-softrender_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "sr_oracle" not in text and "oracle_binding" not in text and "libsr_oracle" not in text, f

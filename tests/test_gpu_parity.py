@@ -1,0 +1,534 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): tile bins, pixel coverage and depth-test outcomes bit-exact; depth
+bit-exact (tolerance stated: 1e-6 relative, expected and asserted: 0); colour within 1/255 per channel
+(shaders call powf, libm vs CUDA differ in the last ulps) and bit-exact for the power-free test shaders.
+"""
+import numpy as np
+import pytest
+
+import softrender_b200 as sr
+from softrender_b200 import scenes
+
+import helpers as H
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+COLOR_TOL = 1.0 / 255.0
+
+
+@pytest.fixture(scope="module")
+def P():
+    from softrender_b200 import pipeline
+    return pipeline
+
+
+def make_fb(P, ctx, w, h, stencil=False, winner=True):
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h, stencil=stencil)
+    if winner:
+        fb.enable_winner(True)
+    fb.clear(H.CLEAR)
+    return fb
+
+
+def oracle_fb(w, h, stencil=False):
+    fb = ob.OracleFramebuffer(w, h, 8 if stencil else 0)
+    fb.clear(H.CLEAR)
+    return fb
+
+
+# ------------------------------------------------------------------------------------------------------
+# stage by stage on the Suzanne scene (config 1)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [256, 1024])
+def test_suzanne_stages_and_frame(P, ctx, size):
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+
+    od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    od.vertex_run(sr.VS_SUZANNE, u, mesh.vertices)
+    o_clip_verts = od.data(0)
+
+    fb = make_fb(P, ctx, size, size)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    gs = pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE)
+    H.assert_bits_equal(gs.download(0), o_clip_verts, "vertex stage")
+
+    # clipper: the kept triangles are the oracle's literal sequence at the reported positions;
+    # everything dropped is a triangle with two bit-identical vertices
+    od.clip_primitives()
+    o_tris = od.data(3).reshape(-1, 3, o_clip_verts.shape[1])
+    gs = gs.clip_primitives()
+    g_tris = gs.download(3).reshape(-1, 3, o_clip_verts.shape[1])
+    seq = gs.download_sequence()
+    assert len(o_tris) == 16 * mesh.ntris  # fully inside: 18-vertex polygon -> 16 triangles each
+    assert len(g_tris) == len(seq) and np.all(np.diff(seq.astype(np.int64)) > 0)
+    H.assert_bits_equal(g_tris, o_tris[seq], "clipped triangles")
+    dropped = np.ones(len(o_tris), bool)
+    dropped[seq] = False
+    d = o_tris[dropped]
+    same = (np.all(H.bits(d[:, 0]) == H.bits(d[:, 1]), axis=1) | np.all(H.bits(d[:, 0]) == H.bits(d[:, 2]), axis=1)
+            | np.all(H.bits(d[:, 1]) == H.bits(d[:, 2]), axis=1))
+    assert same.all()
+
+    od.finish(vp)
+    fs = gs.finish(vp)
+    H.assert_bits_equal(fs.download(3).reshape(-1, 3, o_clip_verts.shape[1]), od.data(3).reshape(o_tris.shape)[seq], "finish")
+
+    ofb = oracle_fb(size, size)
+    od.fragment_run(ofb, sr.FS_SUZANNE, u)
+    fs.run(sr.FS_SUZANNE)
+    H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what=f"suzanne {size}")
+    assert np.array_equal(fb.download_winner(), ofb.winner), "coverage / winning primitive"
+
+    # the no-clip path gives the identical image (mesh fully inside the frustum)
+    fb2 = make_fb(P, ctx, size, size)
+    pipe2 = P.Pipeline.from_framebuffer(fb2, u)
+    pipe2.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    a, b = fb.download(), fb2.download()
+    H.assert_bits_equal(a, b, "clip vs run_to_fragment")
+    for x in (pipe, pipe2, gmesh, fb, fb2):
+        x.destroy()
+
+
+def test_suzanne_matches_reference_golden_image(P, ctx):
+    """Loose visual golden: examples/suzanne.png, box-downsampled 4x."""
+    size = 2000
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    fb = make_fb(P, ctx, size, size, winner=False)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+    img = np.clip(fb.download()[:, :3].reshape(size, size, 3), 0, 1)
+    img = img.reshape(500, 4, 500, 4, 3).mean(axis=(1, 3))
+    gold = np.load(H.GOLDEN + "/suzanne_gold_500.npz")["rgb"].astype(np.float32) / 255.0
+    lit_o = np.abs(img - 0.01).max(-1) > 0.02
+    lit_g = np.abs(gold - 0.01).max(-1) > 0.02
+
+    def bbox(m):
+        ys, xs = np.nonzero(m)
+        return np.array([xs.min(), xs.max(), ys.min(), ys.max()])
+
+    assert np.abs(bbox(lit_o) - bbox(lit_g)).max() <= 1
+    assert np.abs(bbox(lit_g) - np.array([88, 477, 78, 440])).max() <= 1
+    iou = (lit_o & lit_g).sum() / (lit_o | lit_g).sum()
+    assert iou >= 0.94
+    both = lit_o & lit_g
+    assert np.median(np.abs(img - gold)[both]) * 255 <= 2.0
+    for x in (pipe, gmesh, fb):
+        x.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# rasteriser on injected screen-space triangles (bit-exact colour with the flat shader)
+# ------------------------------------------------------------------------------------------------------
+def run_both_screen(P, ctx, w, h, verts, indices, *, prim=sr.TRIANGLE, fs=sr.FS_FLAT, cull=None, blend=sr.BLEND_REPLACE,
+                    stencil=False, stencil_cfg=None, stencil_value=None, aa=False, gen=None, draws=1, oracle_tile=None,
+                    init=None):
+    u = scenes.suzanne_uniforms(w, h)
+    ofb = oracle_fb(w, h, stencil)
+    fb = make_fb(P, ctx, w, h, stencil=stencil)
+    if init is not None:
+        col, dep, st = init
+        ofb.color[:] = col
+        ofb.depth[:] = dep
+        if stencil:
+            ofb.stencil[:] = st
+        fb.upload_planes(col, dep, st if stencil else None)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    if stencil_cfg:
+        pipe.set_stencil_config(*stencil_cfg)
+    for _ in range(draws):
+        od = ob.OracleDraw(prim, indices, stencil_value)
+        od.set_vertices(verts, 1)
+        od.cull = sr.CULL_NONE if cull is None else cull
+        od.blend, od.aa, od.tile = blend, aa, oracle_tile
+        fsd = pipe.draw_from_vertices(prim, verts, indices, 1, stencil_value)
+        if gen:
+            for which, gv in gen.items():
+                od.set_generated(which, gv)
+                fsd.set_generated(which, gv)
+        od.fragment_run(ofb, fs, u, *(stencil_cfg or (0, 0)))
+        fsd.cull_faces(cull).with_blend(blend).antialiased_lines(aa).run(fs)
+    out = fb.download()
+    win = fb.download_winner()
+    st = fb.download_planes(stencil=True)[2] if stencil else None
+    pipe.destroy()
+    fb.destroy()
+    return out, win, st, ofb
+
+
+@pytest.mark.parametrize("w,h,n,seed", [(64, 64, 40, 1), (200, 150, 300, 2), (333, 257, 2000, 3), (1000, 700, 5000, 4)])
+def test_random_triangles_opaque(P, ctx, w, h, n, seed):
+    rng = np.random.default_rng(seed)
+    verts = H.random_screen_triangles(rng, n, w, h)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="random opaque")
+
+
+def test_depth_ties_later_primitive_wins(P, ctx):
+    """`d >= dt`: equal depth goes to the later primitive (triangle.rs:126); shuffled submission order."""
+    rng = np.random.default_rng(7)
+    w, h, n = 96, 80, 150
+    verts = H.random_screen_triangles(rng, n, w, h, integer_depth=True)
+    idx = rng.permutation(n).astype(np.uint32)[:, None] * 3 + np.arange(3, dtype=np.uint32)[None, :]
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx.reshape(-1))
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="depth ties")
+    # and the reference's default overlapping 128x128 tiling gives the same image (idempotent state)
+    _, _, _, ofb128 = run_both_screen(P, ctx, w, h, verts, idx.reshape(-1), oracle_tile=(16, 16))
+    H.assert_bits_equal(ofb128.color, ofb.color, "tiling independence")
+
+
+def test_tiny_and_subpixel_triangles(P, ctx):
+    rng = np.random.default_rng(11)
+    w, h, n = 256, 192, 20000
+    verts = H.random_screen_triangles(rng, n, w, h, max_size=1.5, margin=0.02)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="tiny triangles")
+
+
+def test_inclusive_edges_half_integer_vertices(P, ctx):
+    """Pixel centres exactly on an edge are covered; two triangles sharing an edge both cover them and the
+    later one wins at equal depth."""
+    w = h = 32
+    z = -1.0
+
+    def v(x, y, c):
+        return [x, y, z, 1.0] + c
+
+    red, green = [1, 0, 0, 1], [0, 1, 0, 1]
+    verts = np.array([v(4.5, 4.5, red), v(20.5, 4.5, red), v(4.5, 20.5, red),
+                      v(20.5, 4.5, green), v(20.5, 20.5, green), v(4.5, 20.5, green)], np.float32)
+    idx = np.arange(6, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="inclusive edges")
+    W = win.reshape(h, w)
+    assert W[4, 4] == 1 and W[4, 20] == 2 and W[20, 4] == 2  # corners: shared-edge end points go to the later triangle
+    for k in range(5, 20):
+        assert W[k, 24 - k] == 2  # the shared diagonal x + y = 24 (pixel centres on it) belongs to triangle 2
+
+
+@pytest.mark.parametrize("cull", [sr.CLOCKWISE, sr.COUNTER_CLOCKWISE])
+def test_cull_faces(P, ctx, cull):
+    rng = np.random.default_rng(5)
+    w, h, n = 128, 128, 400
+    verts = H.random_screen_triangles(rng, n, w, h)
+    # a zero-area triangle whose shoelace sum is -0.0 counts as clockwise
+    verts[:3, :2] = [[3.0, 3.0], [3.0, 3.0], [3.0, 3.0]]
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, cull=cull)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="cull")
+
+
+def test_degenerate_offscreen_and_nonfinite(P, ctx):
+    w, h = 64, 48
+    rng = np.random.default_rng(9)
+    verts = H.random_screen_triangles(rng, 60, w, h)
+    t = verts.reshape(-1, 3, 8)
+    t[0, :, :2] = [[10, 10], [20, 20], [30, 30]]       # det == 0
+    t[1, :, 2] = 0.5                                    # z >= 0: covered but rejected
+    t[2, :, 0] += 1e4                                   # entirely off screen (clamp artefact column)
+    t[3, 0, 0] = np.inf                                 # +inf clamps to the last pixel
+    t[4, 1, 1] = -np.inf
+    t[5, 0, 0] = np.nan                                 # NaN: primitive skipped (reference would panic)
+    t[6, :, 2] = [-1.0, np.nan, -2.0]                   # NaN depth: z < 0 is false
+    idx = np.arange(len(verts), dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="degenerate")
+
+
+def test_second_draw_uses_existing_depth(P, ctx):
+    rng = np.random.default_rng(21)
+    w, h, n = 160, 120, 500
+    verts = H.random_screen_triangles(rng, n, w, h, integer_depth=True)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, draws=2)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="two draws")
+
+
+def test_one_pixel_frames_draw_nothing(P, ctx):
+    """1xN framebuffers have no tiles (fragment.rs:188-216): nothing is ever drawn."""
+    verts = np.array([[-5, -5, -1, 1, 1, 0, 0, 1], [9, -5, -1, 1, 1, 0, 0, 1], [0, 9, -1, 1, 1, 0, 0, 1]], np.float32)
+    out, win, _, ofb = run_both_screen(P, ctx, 1, 1, verts, np.arange(3, dtype=np.uint32))
+    H.compare_framebuffers(out, ofb, exact_color=True, what="1x1")
+    assert win.max() == 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# bins
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cull", [sr.CULL_NONE, sr.CLOCKWISE])
+def test_tile_bins_match_oracle(P, ctx, cull):
+    rng = np.random.default_rng(31)
+    w, h, n = 700, 450, 3000
+    verts = H.random_screen_triangles(rng, n, w, h, max_size=90)
+    verts.reshape(-1, 3, 8)[7, 0, 0] = np.nan
+    idx = rng.permutation(3 * n).astype(np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    fsd = pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).cull_faces(None if cull == 0 else cull)
+    g_off, g_ids = fsd.bins()
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 1)
+    tw, th = P.tile_size()
+    o_off, o_ids = od.bins(w, h, tw, th, cull)
+    assert np.array_equal(g_off, o_off)
+    assert np.array_equal(g_ids, o_ids)
+    pipe.destroy()
+    fb.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# ordered path: blend, stencil, discard, lines, points
+# ------------------------------------------------------------------------------------------------------
+def test_alpha_over_blend_in_order(P, ctx):
+    rng = np.random.default_rng(41)
+    w, h, n = 150, 110, 400
+    verts = H.random_screen_triangles(rng, n, w, h)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, blend=sr.BLEND_ALPHA_OVER)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="alpha over")
+
+
+def test_discarding_shader(P, ctx):
+    rng = np.random.default_rng(43)
+    w, h, n = 130, 90, 300
+    verts = H.random_screen_triangles(rng, n, w, h)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, fs=sr.FS_DISCARD_CHECKER)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="discard")
+
+
+@pytest.mark.parametrize("test,op", [(sr.STENCIL_ALWAYS, sr.STENCIL_INCREMENT_WRAP), (sr.STENCIL_EQUAL, sr.STENCIL_KEEP),
+                                     (sr.STENCIL_GREATER_THAN, sr.STENCIL_REPLACE), (sr.STENCIL_NOT_EQUAL, sr.STENCIL_INVERT),
+                                     (sr.STENCIL_LESS_THAN_EQ, sr.STENCIL_DECREMENT_SAT), (sr.STENCIL_NEVER, sr.STENCIL_ZERO),
+                                     (sr.STENCIL_ALWAYS, sr.STENCIL_INCREMENT_SAT), (sr.STENCIL_ALWAYS, sr.STENCIL_DECREMENT_WRAP)])
+def test_stencil(P, ctx, test, op):
+    """Stencil test+op run for every pixel of the clamped bbox BEFORE the coverage test, also
+    for zero-area triangles."""
+    rng = np.random.default_rng(47)
+    w, h, n = 100, 84, 120
+    verts = H.random_screen_triangles(rng, n, w, h)
+    verts.reshape(-1, 3, 8)[0, :, :2] = [[10, 10], [20, 20], [30, 30]]
+    idx = np.arange(3 * n, dtype=np.uint32)
+    init = (np.tile(np.float32(H.CLEAR), (w * h, 1)), np.full(w * h, np.float32(-3.4028235e38)),
+            rng.integers(0, 4, w * h).astype(np.uint8))
+    out, win, st, ofb = run_both_screen(P, ctx, w, h, verts, idx, stencil=True, stencil_cfg=(test, op), stencil_value=2, init=init)
+    assert np.array_equal(st, ofb.stencil)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="stencil")
+
+
+@pytest.mark.parametrize("aa", [False, True])
+def test_lines(P, ctx, aa):
+    rng = np.random.default_rng(53)
+    w, h, n = 140, 100, 200
+    v = np.zeros((2 * n, 8), np.float32)
+    v[:, 0] = rng.uniform(-20, w + 20, 2 * n)
+    v[:, 1] = rng.uniform(-20, h + 20, 2 * n)
+    v[:, 2] = -rng.uniform(0.5, 5, 2 * n)
+    v[:, 3] = 1
+    v[:, 4:] = rng.uniform(0, 1, (2 * n, 4))
+    v[0, :2], v[1, :2] = (5.5, 7.5), (5.5, 60.2)     # vertical
+    v[2, :2], v[3, :2] = (3.2, 9.5), (120.7, 9.5)    # horizontal
+    v[4, :2], v[5, :2] = (30.0, 30.0), (30.0, 30.0)  # zero length
+    idx = np.arange(2 * n, dtype=np.uint32)
+    blend = sr.BLEND_ALPHA_OVER if aa else sr.BLEND_REPLACE
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, v, idx, prim=sr.LINE, aa=aa, blend=blend)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="lines")
+
+
+def test_points_half_open_bounds(P, ctx):
+    rng = np.random.default_rng(59)
+    w, h, n = 90, 70, 3000
+    v = np.zeros((n, 8), np.float32)
+    v[:, 0] = rng.uniform(-3, w + 3, n)
+    v[:, 1] = rng.uniform(-3, h + 3, n)
+    v[:, 2] = -rng.uniform(0.5, 5, n)
+    v[:, 3] = 1
+    v[:, 4:] = rng.uniform(0, 1, (n, 4))
+    v[0, :2] = (w - 1 + 0.5, 10.5)  # last column: never drawn (point.rs:46)
+    v[1, :2] = (10.5, h - 1 + 0.5)  # last row: never drawn
+    idx = np.arange(n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, v, idx, prim=sr.POINT)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="points")
+    W = win.reshape(h, w)
+    assert W[:, w - 1].max() == 0 and W[h - 1, :].max() == 0
+
+
+def test_mixed_generated_primitives_order(P, ctx):
+    """Triangles, then lines, then points (fragment.rs:268-311), indexed before generated."""
+    rng = np.random.default_rng(61)
+    w, h = 120, 96
+    tri = H.random_screen_triangles(rng, 80, w, h)
+    gen_tri = H.random_screen_triangles(rng, 50, w, h)
+    lines = H.random_screen_triangles(rng, 40, w, h)[:80]
+    pts = H.random_screen_triangles(rng, 100, w, h)[:300]
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, tri, np.arange(len(tri), dtype=np.uint32),
+                                       gen={3: gen_tri, 2: lines, 1: pts})
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="mixed")
+
+
+# ------------------------------------------------------------------------------------------------------
+# geometry stage
+# ------------------------------------------------------------------------------------------------------
+def _clip_space_triangles(rng, n, nk=8):
+    v = np.zeros((3 * n, 4 + nk), np.float32)
+    v[:, 3] = rng.uniform(0.2, 3.0, 3 * n)
+    v[:, 0] = rng.uniform(-1.8, 1.8, 3 * n) * v[:, 3]
+    v[:, 1] = rng.uniform(-1.8, 1.8, 3 * n) * v[:, 3]
+    v[:, 2] = rng.uniform(-0.6, 1.6, 3 * n) * v[:, 3]
+    neg = rng.uniform(0, 1, 3 * n) < 0.05
+    v[neg, 3] *= -1  # behind the eye
+    v[:, 4:] = rng.uniform(-1, 1, (3 * n, nk))
+    return v
+
+
+@pytest.mark.parametrize("prim", [sr.TRIANGLE, sr.LINE, sr.POINT])
+def test_clip_primitives_random(P, ctx, prim):
+    rng = np.random.default_rng(71)
+    n = 600
+    verts = _clip_space_triangles(rng, n)
+    idx = rng.integers(0, len(verts), prim * 500).astype(np.uint32)
+    u = scenes.suzanne_uniforms(64, 64)
+    fb = make_fb(P, ctx, 64, 64)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    od = ob.OracleDraw(prim, idx)
+    od.set_vertices(verts, 0).clip_primitives()
+    gs = pipe.draw_from_vertices(prim, verts, idx, 0).clip_primitives()
+    S = verts.shape[1]
+    if prim == sr.TRIANGLE:
+        o = od.data(3).reshape(-1, 3, S)
+        g = gs.download(3).reshape(-1, 3, S)
+        seq = gs.download_sequence()
+        H.assert_bits_equal(g, o[seq], "clipped triangles")
+        dropped = np.ones(len(o), bool)
+        dropped[seq] = False
+        d = o[dropped]
+        same = (np.all(H.bits(d[:, 0]) == H.bits(d[:, 1]), axis=1) | np.all(H.bits(d[:, 0]) == H.bits(d[:, 2]), axis=1)
+                | np.all(H.bits(d[:, 1]) == H.bits(d[:, 2]), axis=1))
+        assert same.all()
+    else:
+        H.assert_bits_equal(gs.download(prim), od.data(prim), "clipped")
+    pipe.destroy()
+    fb.destroy()
+
+
+@pytest.mark.parametrize("gs_id", [sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS])
+def test_normal_visualisation_geometry_shaders(P, ctx, gs_id):
+    size = 200
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    fb = make_fb(P, ctx, size, size)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    od.vertex_run(sr.VS_SUZANNE, u, mesh.vertices).geometry_run(gs_id, u)
+    gs = pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE).run(gs_id)
+    H.assert_bits_equal(gs.download(2), od.data(2), "normal lines")
+    ofb = oracle_fb(size, size)
+    od.finish(vp).fragment_run(ofb, sr.FS_GREEN, u)
+    gs.finish(vp).run(sr.FS_GREEN)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="normal lines frame")
+    for x in (pipe, gmesh, fb):
+        x.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# full_example scene parts (config 2) and the synthetic grid (configs 3/4, reduced)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("textured,camera_distance", [(False, 2.0), (True, 2.0), (True, 0.9)])
+def test_full_example_scene(P, ctx, textured, camera_distance):
+    w, h = 480, 270
+    mesh = H.suzanne_mesh(with_uv=True)
+    tex = scenes.checker_texture(64, 8)
+    vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
+    fb = make_fb(P, ctx, w, h)
+    ofb = oracle_fb(w, h)
+    gmesh = P.Mesh(ctx, mesh)
+    gtex = P.Texture(ctx, tex)
+    fs = sr.FS_FULL_EXAMPLE_TEXTURED if textured else sr.FS_FULL_EXAMPLE
+    pipe = None
+    for k, (rot, off) in enumerate([(45.0, -1.6), (165.0, 0.0), (285.0, 1.6)]):
+        u = scenes.full_example_uniforms(w / h, np.deg2rad(75.0), camera_distance, np.deg2rad(rot), np.deg2rad(65.0), off)
+        if pipe is None:
+            pipe = P.Pipeline.from_framebuffer(fb, u)
+            pipe.bind_texture(gtex)
+        else:
+            pipe.set_uniforms(u)
+        od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        od.blend = sr.BLEND_ALPHA_OVER
+        od.vertex_run(sr.VS_FULL_EXAMPLE, u, mesh.vertices)
+        gs = pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_FULL_EXAMPLE)
+        H.assert_bits_equal(gs.download(0), od.data(0), "full_example vertex stage")
+        if camera_distance < 1.0:
+            od.clip_primitives()
+            gs = gs.clip_primitives()
+        od.finish(vp).fragment_run(ofb, fs, u, texture=tex)
+        gs.finish(vp).with_blend(sr.BLEND_ALPHA_OVER).run(fs)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="full_example")
+    for x in (pipe, gmesh, gtex, fb):
+        x.destroy()
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_grid_scene_reduced(P, ctx, reverse):
+    """Config 3's generator at 1/100 of the triangle count on a 960x540 frame (same px^2 per triangle)."""
+    w, h = 960, 540
+    mesh = scenes.make_grid(125, 100, 4, seed=0x5EED0003, reverse=reverse)
+    u = scenes.grid_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.1, 100.0)
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    pipe.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    ofb = oracle_fb(w, h)
+    od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    od.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices).fragment_run(ofb, sr.FS_SUZANNE, u)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="grid")
+    for x in (pipe, gmesh, fb):
+        x.destroy()
+
+
+def test_error_behaviour(P, ctx):
+    from softrender_b200._abi import SoftrenderError
+    u = scenes.suzanne_uniforms(8, 8)
+    fb0 = P.RenderBuffer.with_dimensions(ctx, 0, 4)
+    with pytest.raises(SoftrenderError):  # assert!(width > 0) (src/pipeline/mod.rs:129)
+        P.Pipeline.from_framebuffer(fb0, u)
+    fb = make_fb(P, ctx, 8, 8)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    mesh = P.Mesh(ctx, vertices=np.zeros((4, 6), np.float32), indices=np.array([0, 1, 2, 3], np.uint32))
+    with pytest.raises(SoftrenderError):  # assert_eq!(indices.len() % num_vertices, 0) (mod.rs:148)
+        pipe.render_mesh(sr.TRIANGLE, mesh)
+    with pytest.raises(SoftrenderError) as e:  # RenderError::InvalidPixelCoordinate (src/error.rs:9)
+        fb.pixel(8, 0)
+    assert e.value.status == sr.ERR_INVALID_PIXEL_COORDINATE
+    rgba, depth, _ = fb.pixel(7, 7)
+    assert np.float32(depth).view(np.uint32) == sr.DEPTH_FAR_BITS and np.allclose(rgba, H.CLEAR)
+    for x in (pipe, mesh, fb, fb0):
+        x.destroy()

@@ -1,0 +1,237 @@
+"""CPU tests: pin the oracle against the reference's own test (pixel index layout) and the known-answer
+vectors derived line by line from the reference source, and against the reference's
+golden image examples/suzanne.png (committed as a 4x box-downsampled fixture)."""
+import numpy as np
+import pytest
+
+import softrender_b200 as sr
+from softrender_b200 import scenes
+
+import helpers as H
+import oracle_binding as ob
+
+L = ob.lib()
+
+
+def test_coordinate_index_reference_test():
+    """src/geometry/coordinate.rs:71-85 (`coordinate_index`): row-major x + y*width on a 10x20 frame."""
+    for y in range(20):
+        for x in range(10):
+            assert L.so_coordinate_index(x, y, 10) == x + 10 * y
+
+
+def test_depth_far_is_f32_min():
+    assert np.float32(L.so_depth_far()).view(np.uint32) == 0xFF7FFFFF  # depth.rs:31
+
+
+@pytest.mark.parametrize("w,h,count,last", [(1024, 1024, 64, (896, 896, 1023, 1023)), (2000, 2000, 256, None),
+                                            (1920, 1080, 135, None), (3840, 2160, 510, (3712, 2048, 3839, 2159)),
+                                            (7680, 4320, 2040, None), (800, 600, 35, None), (129, 129, 1, (0, 0, 128, 128)),
+                                            (1, 1, 0, None)])
+def test_tile_lists(w, h, count, last):
+    """fragment.rs:188-216 at the default 128x128 tile size."""
+    t = ob.tiles(w, h)
+    assert len(t) == count
+    if last:
+        assert tuple(t[-1]) == last
+    if count:
+        covered = np.zeros((h, w), bool)
+        for x0, y0, x1, y1 in t:
+            covered[y0:y1 + 1, x0:x1 + 1] = True
+        assert covered.all()
+
+
+def test_stencil_truth_table():
+    """src/stencil.rs:112-123 (test compares MESH value `mask` against BUFFER value) and :147-158."""
+    for value in (0, 1, 2, 254, 255):
+        for mask in (0, 1, 2, 255):
+            exp = {sr.STENCIL_ALWAYS: True, sr.STENCIL_NEVER: False, sr.STENCIL_LESS_THAN: mask < value,
+                   sr.STENCIL_LESS_THAN_EQ: mask <= value, sr.STENCIL_GREATER_THAN: mask > value,
+                   sr.STENCIL_GREATER_THAN_EQ: mask >= value, sr.STENCIL_EQUAL: mask == value,
+                   sr.STENCIL_NOT_EQUAL: mask != value}
+            for t, e in exp.items():
+                assert bool(L.so_stencil_test(t, value, mask)) == e
+            ops = {sr.STENCIL_KEEP: value, sr.STENCIL_INVERT: (~value) & 255, sr.STENCIL_ZERO: 0, sr.STENCIL_REPLACE: mask,
+                   sr.STENCIL_INCREMENT_WRAP: (value + 1) & 255, sr.STENCIL_DECREMENT_WRAP: (value - 1) & 255,
+                   sr.STENCIL_INCREMENT_SAT: min(value + 1, 255), sr.STENCIL_DECREMENT_SAT: max(value - 1, 0)}
+            for o, e in ops.items():
+                assert L.so_stencil_op(o, value, mask) == e
+
+
+def _clip(a, b, c):
+    v = np.zeros((3, 8), np.float32)
+    v[0, :4], v[1, :4], v[2, :4] = a, b, c
+    v[:, 4:] = np.arange(12, dtype=np.float32).reshape(3, 4)
+    d = ob.OracleDraw(sr.TRIANGLE, np.arange(3, dtype=np.uint32))
+    d.set_vertices(v, 0).clip_primitives()
+    t = d.data(3).reshape(-1, 3, 8)
+
+    def nondeg(tri):
+        b_ = [x.tobytes() for x in tri]
+        return len(set(b_)) == 3
+    return v, t, [i for i in range(len(t)) if nondeg(t[i])]
+
+
+def test_clipper_known_answers():
+    """geometry.rs:261-299 literally: the clipper amplifies instead of clipping."""
+    A, B, C = (-0.5, -0.5, 0.5, 1.0), (0.5, -0.5, 0.5, 1.0), (0.0, 0.5, 0.5, 1.0)
+    v, t, nd = _clip(A, B, C)  # fully inside: polygon of 18 -> 16 triangles, one real = (a,b,c) at fan index 5
+    assert len(t) == 16 and nd == [5]
+    assert np.array_equal(t[5], v)
+    v, t, nd = _clip((-2.0, -0.5, 0.5, 1.0), B, C)  # a outside Left only: 19 -> 17, three non-degenerate
+    assert len(t) == 17 and len(nd) == 3
+    assert any(np.array_equal(t[i], v) for i in nd)  # the unclipped (a,b,c) survives
+    assert all(np.array_equal(t[i][0], v[0]) for i in nd)  # fan pivot is the OUTSIDE vertex a
+    _, t, _ = _clip((-2.0, -0.5, 0.5, 1.0), (-3.0, 0.2, 0.5, 1.0), C)  # a,b outside Left: 18 -> 16
+    assert len(t) == 16
+    v, t, nd = _clip((-2.0, -0.5, 0.5, 1.0), (-3.0, 0.2, 0.5, 1.0), (-2.5, 0.5, 0.5, 1.0))  # all outside Left: 15 -> 13
+    assert len(t) == 13 and any(np.array_equal(t[i], v) for i in nd)
+    _, t, nd = _clip((-2.0, -2.0, 0.5, 1.0), B, C)  # a outside Left+Top: 20 -> 18, five non-degenerate
+    assert len(t) == 18 and len(nd) == 5
+    _, t, nd = _clip((0.1, 0.1, -0.5, -1.0), B, C)  # a with w<0 (outside all six planes): 24 -> 22, seventeen non-degenerate
+    assert len(t) == 22 and len(nd) >= 16  # the non-degenerate count depends on coincident intersections of the chosen vertex
+
+
+def _raster(verts, idx, w=32, h=32, prim=sr.TRIANGLE, **kw):
+    fb = ob.OracleFramebuffer(w, h, 8 if kw.get("stencil") else 0)
+    fb.clear(H.CLEAR)
+    d = ob.OracleDraw(prim, np.asarray(idx, np.uint32), kw.get("stencil_value"))
+    d.set_vertices(np.asarray(verts, np.float32), 1)
+    d.cull = kw.get("cull", 0)
+    d.tile = kw.get("tile")
+    d.fragment_run(fb, sr.FS_FLAT, scenes.suzanne_uniforms(w, h), kw.get("stencil_test", 0), kw.get("stencil_op", 0))
+    return fb
+
+
+def test_inclusive_edges_and_tie_break():
+    z = -1.0
+    red, green = [1, 0, 0, 1], [0, 1, 0, 1]
+    tri = lambda pts, c: [[x, y, z, 1.0] + c for x, y in pts]  # noqa: E731
+    verts = tri([(4.5, 4.5), (20.5, 4.5), (4.5, 20.5)], red) + tri([(20.5, 4.5), (20.5, 20.5), (4.5, 20.5)], green)
+    fb = _raster(verts, range(6))
+    W = fb.winner.reshape(32, 32)
+    assert W[4, 4] == 1 and W[4, 19] == 1  # centres on triangle 1's own edges are covered
+    assert all(W[k, 24 - k] == 2 for k in range(4, 21))  # shared diagonal: both cover, later wins at equal depth
+    assert W[3, 4] == 0 and W[21, 21] == 0
+    # single triangle: edge pixels covered on all three sides
+    fb1 = _raster(verts[:3], range(3))
+    W1 = fb1.winner.reshape(32, 32)
+    assert all(W1[k, 24 - k] == 1 for k in range(4, 21)) and W1[4, 4:21].all() and W1[4:21, 4].all()
+
+
+def test_cull_negative_zero_is_clockwise():
+    p = [3.0, 3.0, -1.0, 1.0, 1, 1, 1, 1]
+    big = [[2.5, 2.5, -1, 1, 1, 0, 0, 1], [12.5, 2.5, -1, 1, 1, 0, 0, 1], [2.5, 12.5, -1, 1, 1, 0, 0, 1]]
+    # shoelace of identical points: 9+9+9-9-9-9 = +0.0 -> CounterClockwise; flipping the sign bit needs a real -0.0
+    x1, y1, x2, y2, x3, y3 = -1.0, 0.0, 0.0, 0.0, 1.0, 0.0
+    a = np.float32(x1 * y2 + x2 * y3 + x3 * y1 - x2 * y1 - x3 * y2 - x1 * y3)
+    assert not np.signbit(a)
+    fb = _raster(big, range(3), cull=sr.COUNTER_CLOCKWISE)
+    ccw_drawn = fb.winner.max()
+    fb = _raster(big, range(3), cull=sr.CLOCKWISE)
+    cw_drawn = fb.winner.max()
+    assert {int(ccw_drawn), int(cw_drawn)} == {0, 1}  # culled under exactly one winding
+    del p
+
+
+def test_det_zero_draws_nothing_but_applies_stencil():
+    verts = [[10, 10, -1, 1, 1, 1, 1, 1], [20, 20, -1, 1, 1, 1, 1, 1], [30, 30, -1, 1, 1, 1, 1, 1]]
+    fb = _raster(verts, range(3), w=40, h=40, stencil=True, stencil_value=1, stencil_test=sr.STENCIL_ALWAYS,
+                 stencil_op=sr.STENCIL_INCREMENT_WRAP)
+    assert fb.winner.max() == 0
+    S = fb.stencil.reshape(40, 40)
+    assert S[10:31, 10:31].min() == 1 and S.sum() == 21 * 21
+
+
+def test_nonnegative_z_rejected_and_points_last_row_column():
+    verts = [[2.5, 2.5, 0.0, 1, 1, 1, 1, 1], [12.5, 2.5, 0.0, 1, 1, 1, 1, 1], [2.5, 12.5, 0.0, 1, 1, 1, 1, 1]]
+    assert _raster(verts, range(3)).winner.max() == 0
+    pts = [[31.5, 5.5, -1, 1, 1, 1, 1, 1], [5.5, 31.5, -1, 1, 1, 1, 1, 1], [30.9, 30.9, -1, 1, 1, 1, 1, 1]]
+    W = _raster(pts, range(3), prim=sr.POINT).winner.reshape(32, 32)
+    assert W[5, 31] == 0 and W[31, 5] == 0 and W[30, 30] == 3
+    assert _raster(verts, range(3), w=1, h=1).winner.max() == 0  # 1x1: no tiles at all
+
+
+def test_reference_tiling_equals_one_tile_and_literal_equals_binned():
+    """(i) overlapping 16x16 tiles == one frame tile for idempotent state; (ii) shuffled order with
+    exact depth ties; (iii) bins derived from the clamped bbox cover every pixel that was drawn."""
+    rng = np.random.default_rng(3)
+    w, h, n = 64, 64, 120
+    verts = H.random_screen_triangles(rng, n, w, h, integer_depth=True)
+    idx = (rng.permutation(n).astype(np.uint32)[:, None] * 3 + np.arange(3, dtype=np.uint32)).reshape(-1)
+    one = _raster(verts, idx, w, h)
+    tiled = _raster(verts, idx, w, h, tile=(16, 16))
+    assert np.array_equal(one.winner, tiled.winner)
+    H.assert_bits_equal(one.color, tiled.color)
+    H.assert_bits_equal(one.depth, tiled.depth)
+    d = ob.OracleDraw(sr.TRIANGLE, idx)
+    d.set_vertices(verts, 1)
+    off, ids = d.bins(w, h, 16, 16)
+    for tile in range(16):
+        tx, ty = tile % 4, tile // 4
+        winners = set(np.unique(one.winner.reshape(h, w)[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16])) - {0}
+        assert {x - 1 for x in winners} <= set(ids[off[tile]:off[tile + 1]].tolist())
+        assert np.all(np.diff(ids[off[tile]:off[tile + 1]].astype(np.int64)) > 0)
+
+
+def test_threaded_reference_structure_matches_canonical():
+    """The timing mode (thread pool + atomic cursors + 128x128 tiles) renders the same image."""
+    size = 192
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    frames = []
+    for nthreads, tile in ((1, None), (4, (128, 128))):
+        fb = ob.OracleFramebuffer(size, size)
+        fb.clear(H.CLEAR)
+        d = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        d.tile = tile
+        d.vertex_run(sr.VS_SUZANNE, u, mesh.vertices, nthreads).clip_primitives(1).finish(vp, nthreads)
+        d.fragment_run(fb, sr.FS_SUZANNE, u, nthreads=nthreads)
+        frames.append(fb)
+    H.assert_bits_equal(frames[0].color, frames[1].color)
+    H.assert_bits_equal(frames[0].depth, frames[1].depth)
+
+
+def test_suzanne_golden_image():
+    """examples/suzanne.png (reference golden, older revision): silhouette bbox equal after 4x box downsample
+    (x 88..477, y 78..440 at 500^2), lit-coverage IoU >= 0.94, median colour error <= 2/255."""
+    size = 500
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    fb = ob.OracleFramebuffer(size, size)
+    fb.clear(H.CLEAR)
+    d = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    d.vertex_run(sr.VS_SUZANNE, u, mesh.vertices, 4).clip_primitives().finish(vp)
+    assert len(d.data(3)) == 3 * 16 * 968
+    d.tile = (128, 128)
+    d.fragment_run(fb, sr.FS_SUZANNE, u, nthreads=8)
+    img = np.clip(fb.color[:, :3].reshape(size, size, 3), 0, 1)
+    gold = np.load(H.GOLDEN + "/suzanne_gold_500.npz")["rgb"].astype(np.float32) / 255.0
+    lit_o = np.abs(img - 0.01).max(-1) > 0.02
+    lit_g = np.abs(gold - 0.01).max(-1) > 0.02
+
+    def bbox(m):
+        ys, xs = np.nonzero(m)
+        return np.array([xs.min(), xs.max(), ys.min(), ys.max()])
+
+    assert np.abs(bbox(lit_g) - np.array([88, 477, 78, 440])).max() == 0
+    assert np.abs(bbox(lit_o) - bbox(lit_g)).max() <= 1  # the golden is anti-aliased by the downsample
+    assert (lit_o & lit_g).sum() / (lit_o | lit_g).sum() >= 0.94
+    assert np.median(np.abs(img - gold)[lit_o & lit_g]) * 255 <= 2.0
+
+
+def test_mesh_fixture_matches_tobj_indexing():
+    m = H.suzanne_mesh()
+    assert m.vertices.shape == (1966, 6) and m.ntris == 968
+
+
+def test_grid_generator_counts():
+    g = scenes.make_grid(10, 8, 4)
+    assert g.ntris == 2 * 10 * 8 * 4 and len(g.vertices) == 4 * 11 * 9
+    r = scenes.make_grid(10, 8, 4, reverse=True)
+    assert np.array_equal(np.sort(g.indices.reshape(-1, 3), axis=0), np.sort(r.indices.reshape(-1, 3), axis=0))
+    # config 3 / 4 sizes without building them
+    assert 4 * 2 * 1250 * 1000 == 10_000_000 and 4 * 1251 * 1001 == 5_009_004
+    assert 4 * 2 * 5000 * 2500 == 100_000_000 and 4 * 5001 * 2501 == 50_030_004
