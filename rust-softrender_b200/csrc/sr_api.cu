@@ -617,20 +617,19 @@ int sr_mesh_create(sr_context *c, const float *vertices, uint64_t nverts, uint32
             SR_LAUNCH(c, k_narrow_indices, ceil_div(nindices, 256), 256, 0, tmp->as<uint64_t>(), nindices, m->indices->as<uint32_t>());
         }
     }
+    // range-check the indices on the device (the reference would panic on an out-of-range index)
+    uint32_t maxidx = 0;
+    if (nindices) {
+        Buf mx;
+        SR_TRY(c->alloc(4, &mx));
+        SR_CUDA(cudaMemsetAsync(mx->ptr, 0, 4, c->stream));
+        SR_LAUNCH(c, k_index_max, std::min<uint32_t>(ceil_div(nindices, 256), 1184u), 256, 0, m->indices->as<uint32_t>(), nindices, mx->as<uint32_t>());
+        SR_CUDA(cudaMemcpyAsync(&maxidx, mx->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     // "buffers passed in are copied before return"
     SR_CUDA(cudaStreamSynchronize(c->stream));
-    // bounds-check the indices once on upload (the reference would panic on an out-of-range index)
-    if (nindices) {
-        uint64_t maxidx = 0;
-        if (index_bytes == 4) {
-            const uint32_t *ix = (const uint32_t *)indices;
-            for (uint64_t i = 0; i < nindices; ++i) maxidx = std::max<uint64_t>(maxidx, ix[i]);
-        } else {
-            const uint64_t *ix = (const uint64_t *)indices;
-            for (uint64_t i = 0; i < nindices; ++i) maxidx = std::max<uint64_t>(maxidx, ix[i]);
-        }
-        if (maxidx >= nverts) return sr_fail(SR_ERR_INVALID_ARGUMENT, "index %llu out of range (%llu vertices)", (unsigned long long)maxidx, (unsigned long long)nverts);
-    }
+    if (nindices && maxidx >= nverts)
+        return sr_fail(SR_ERR_INVALID_ARGUMENT, "index %u out of range (%llu vertices)", maxidx, (unsigned long long)nverts);
     *out = m.release();
     return SR_OK;
 }

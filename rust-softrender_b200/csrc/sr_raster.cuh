@@ -293,7 +293,6 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_opaque(const __grid_
                 dst[0] = p.fb.clear[0]; dst[1] = p.fb.clear[1]; dst[2] = p.fb.clear[2]; dst[3] = p.fb.clear[3];
                 dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
             }
-            if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = 0;
             continue;
         }
         const uint32_t t = id - 1;
@@ -737,7 +736,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; dst[3] = col.w;
         dst[4] = s_depth[i];
         if (c.has_stencil) p.fb.stencil[(uint64_t)py * W + px] = s_stencil[i];
-        if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];
+        if (p.fb.winner && s_winner[i]) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];  // plane is zeroed per draw
     }
 }
 

@@ -192,10 +192,17 @@ __global__ void __launch_bounds__(256) k_planes_to_records(const float4 *pos, co
             if (pl * 4 + j < nk) r[4 + pl * 4 + j] = k[j];
     }
 }
+// largest index of an index buffer (range check on upload; the reference would panic on a bad index)
+__global__ void __launch_bounds__(256) k_index_max(const uint32_t *idx, uint64_t n, uint32_t *out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, __ldg(idx + i));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
 // usize (u64) indices -> u32
 __global__ void __launch_bounds__(256) k_narrow_indices(const uint64_t *in, uint64_t n, uint32_t *out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)in[i];
+    if (i < n) out[i] = in[i] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)in[i];
 }
 
 // =====================================================================================================
