@@ -161,6 +161,9 @@ int sr_draw_download_sequence(sr_draw *, uint32_t *dst, uint64_t capacity);
 /* per-GPU-tile triangle lists of a finished (screen-space) draw: CSR offsets[ntiles+1] + ids
  * (canonical triangle index, ascending per tile).  ids may be NULL to query *total. */
 int sr_draw_bins(sr_draw *, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total);
+/* self-test: compares the rasteriser's exact-division shortcut with IEEE division on `count` random operand
+ * pairs over its whole validity range; *mismatches must come back 0 */
+int sr_selftest_division(sr_context *, uint64_t seed, uint64_t count, uint64_t *mismatches);
 /* device time of the stages of the most recent fragment_run of this context */
 int sr_context_stage_times(sr_context *, sr_stage_times *out);
 

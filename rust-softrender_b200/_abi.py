@@ -9,7 +9,7 @@ import os
 from .scenes import Uniforms, Viewport
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsoftrender_b200.so")
+LIB_PATH = os.environ.get("SOFTRENDER_B200_LIB") or os.path.join(_HERE, "csrc", "libsoftrender_b200.so")  # env override: tuning builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -85,6 +85,7 @@ SYMBOLS = {
     "sr_draw_download": (c_int, [c_void_p, c_int, f32p, c_u64]),
     "sr_draw_download_sequence": (c_int, [c_void_p, u32p, c_u64]),
     "sr_draw_bins": (c_int, [c_void_p, u64p, u32p, c_u64, u64p]),
+    "sr_selftest_division": (c_int, [c_void_p, c_u64, c_u64, u64p]),
 }
 
 for _name, (_res, _args) in SYMBOLS.items():

@@ -267,7 +267,7 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     const uint32_t ntiles = fb->ntx * fb->nty;
     if (nprims == 0) return zero_offsets(c, ntiles, b);
     Buf count;
-    SR_TRY(c->alloc((size_t)nprims * 4, &b->rects));
+    SR_TRY(c->alloc(((size_t)nprims + 64) * 4, &b->rects));
     SR_TRY(c->alloc((size_t)ntiles * 4, &count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
     SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)ntiles * 4, c->stream));
@@ -318,9 +318,10 @@ static int launch_tiles(sr_context *c, bool ordered, uint32_t ntiles_owned, cons
         SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
         SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
     } else {
-        const size_t smem = (size_t)SR_TILE_PIXELS * 8;
+        const size_t smem = SR_OPQ_SMEM_BYTES;
         SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_RASTER_THREADS, smem, p);
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_OPQ_THREADS, smem, p);
     }
     return SR_OK;
 }
@@ -598,7 +599,7 @@ int sr_mesh_create(sr_context *c, const float *vertices, uint64_t nverts, uint32
     m->nindices = nindices;
     m->pstride = std::max<uint64_t>((nverts + 3) & ~(uint64_t)3, 4);
     SR_TRY(c->alloc(m->pstride * vin_floats * 4, &m->planes));
-    SR_TRY(c->alloc(std::max<uint64_t>(nindices, 1) * 4, &m->indices));
+    SR_TRY(c->alloc((nindices + 128) * 4, &m->indices));  // padded: the tile kernel bulk-copies whole groups (96 indices)
     if (nverts) {
         Buf tmp;
         SR_TRY(c->alloc(nverts * vin_floats * 4, &tmp));
@@ -1064,7 +1065,7 @@ int sr_draw_from_vertices(sr_pipeline *p, uint32_t primitive, const float *verts
     d->stencil_value = has_sv ? sv : 0;
     d->nk = nk;
     d->nindices = nindices;
-    SR_TRY(c->alloc(std::max<uint64_t>(nindices, 1) * 4, &d->indices));
+    SR_TRY(c->alloc((nindices + 128) * 4, &d->indices));
     if (nindices) SR_CUDA(cudaMemcpyAsync(d->indices->ptr, indices, nindices * 4, cudaMemcpyHostToDevice, c->stream));
     SR_TRY(upload_records(c, verts, nverts, nk, &d->indexed));
     d->have_indexed = true;
@@ -1114,6 +1115,19 @@ int sr_draw_download_sequence(sr_draw *d, uint32_t *dst, uint64_t capacity) {
     } else {
         for (uint64_t i = 0; i < n; ++i) dst[i] = (uint32_t)i;
     }
+    return SR_OK;
+}
+
+int sr_selftest_division(sr_context *c, uint64_t seed, uint64_t count, uint64_t *mismatches) {
+    if (!c || !mismatches) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_CUDA(cudaSetDevice(c->device));
+    Buf bad;
+    SR_TRY(c->alloc(8, &bad));
+    SR_CUDA(cudaMemsetAsync(bad->ptr, 0, 8, c->stream));
+    const uint32_t threads = 148 * 8 * 256;
+    SR_LAUNCH(c, k_selftest_division, 148 * 8, 256, 0, seed, (count + threads - 1) / threads, bad->as<unsigned long long>());
+    SR_CUDA(cudaMemcpyAsync(mismatches, bad->ptr, 8, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
 

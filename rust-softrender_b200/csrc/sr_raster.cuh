@@ -11,7 +11,9 @@
 
 #include "sr_shaders.cuh"
 
+#ifndef SR_RASTER_THREADS
 #define SR_RASTER_THREADS 256
+#endif
 #define SR_RASTER_WARPS (SR_RASTER_THREADS / 32)
 #define SR_SMALL_AREA 16          // bbox pixels a single lane rasterises itself; larger boxes go warp-wide
 #define SR_DEPTH_FAR_BITS 0xFF7FFFFFu  // f32::MIN, Depth::far() (src/framebuffer/attachments/depth.rs:31)
@@ -79,9 +81,17 @@ __device__ __forceinline__ uint32_t sr_prim_rect(const SrBinParams &p, uint32_t 
 
 // Warp = one group of 32 consecutive primitives.  For every tile touched by at least one primitive of
 // the group: FILL ? append the group id to the tile's list : count it.
+// Consecutive groups of a coherent mesh land in the same one or two tiles, so per-group global atomics
+// would all hit the same few addresses.  Each warp therefore posts up to SR_BIN_SLOTS (tile) entries to
+// shared memory and warp 0 merges equal tiles of the whole CTA with __match_any_sync: one atomic per
+// distinct tile per CTA.  Groups spanning more tiles (large primitives) use direct atomics.
+#define SR_BIN_THREADS 256
+#define SR_BIN_WARPS (SR_BIN_THREADS / 32)
+#define SR_BIN_SLOTS 4
 template <bool FILL>
 __device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect, uint32_t group) {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t s_tile[SR_BIN_WARPS * SR_BIN_SLOTS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = rect != SR_RECT_INVALID;
     uint32_t gx0 = valid ? (rect & 255u) : 255u, gy0 = valid ? ((rect >> 8) & 255u) : 255u;
     uint32_t gx1 = valid ? ((rect >> 16) & 255u) : 0u, gy1 = valid ? (rect >> 24) : 0u;
@@ -89,34 +99,55 @@ __device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect
     gy0 = __reduce_min_sync(0xffffffffu, gy0);
     gx1 = __reduce_max_sync(0xffffffffu, gx1);
     gy1 = __reduce_max_sync(0xffffffffu, gy1);
-    if (!__any_sync(0xffffffffu, valid)) return;
-    for (uint32_t ty = gy0; ty <= gy1; ++ty)
-        for (uint32_t tx = gx0; tx <= gx1; ++tx) {
-            const bool hit = valid && sr_rect_hits(rect, tx, ty);
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            const uint32_t tile = ty * p.ntx + tx;
-            if (tile % p.shard_world != p.shard_rank) continue;
-            if (lane == 0) {
-                const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
-                if (FILL) p.list[p.tile_off[tile] + at] = group;
+    const bool any_valid = __any_sync(0xffffffffu, valid);
+    const bool compact = any_valid && (gx1 - gx0 + 1) * (gy1 - gy0 + 1) <= SR_BIN_SLOTS;
+    uint32_t nslots = 0;
+    if (any_valid) {
+        for (uint32_t ty = gy0; ty <= gy1; ++ty)
+            for (uint32_t tx = gx0; tx <= gx1; ++tx) {
+                const bool hit = valid && sr_rect_hits(rect, tx, ty);
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                const uint32_t tile = ty * p.ntx + tx;
+                if (tile % p.shard_world != p.shard_rank) continue;
+                if (compact) {
+                    if (lane == 0) s_tile[warp * SR_BIN_SLOTS + nslots] = tile;
+                    ++nslots;
+                } else if (lane == 0) {
+                    const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
+                    if (FILL) p.list[p.tile_off[tile] + at] = group;
+                }
             }
+    }
+    if (lane == 0)
+        for (uint32_t k = nslots; k < SR_BIN_SLOTS; ++k) s_tile[warp * SR_BIN_SLOTS + k] = 0xFFFFFFFFu;
+    __syncthreads();
+    if (warp == 0) {
+        static_assert(SR_BIN_WARPS * SR_BIN_SLOTS == 32, "one slot per lane of warp 0");
+        const uint32_t tile = s_tile[lane];
+        const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (tile != 0xFFFFFFFFu && (int)lane == leader) base = atomicAdd(p.tile_count + tile, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (FILL && tile != 0xFFFFFFFFu) {
+            const uint32_t first_group = group - warp;  // this lane is in warp 0: group of warp w is first_group + w
+            p.list[p.tile_off[tile] + base + __popc(peers & ((1u << lane) - 1u))] = first_group + lane / SR_BIN_SLOTS;
         }
+    }
 }
 
 // pass 1: primitive setup (rect per primitive) + per-tile entry counts
 template <int NV>
-__global__ void __launch_bounds__(256) k_bin_setup(const SrBinParams p) {
+__global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_setup(const SrBinParams p) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // grid covers whole warps
     uint32_t rect = SR_RECT_INVALID;
-    if (t < p.nprims) {
-        rect = sr_prim_rect<NV>(p, t);
-        p.rects[t] = rect;
-    }
+    if (t < p.nprims) rect = sr_prim_rect<NV>(p, t);
+    if (t < ((p.nprims + 31u) & ~31u)) p.rects[t] = rect;  // the rect array is padded to whole groups (bulk-copied per group)
     sr_bin_group<false>(p, rect, t >> 5);
 }
 // pass 2: fill the per-tile group lists (order inside a list is arbitrary; consumers that need
 // submission order sort the list, which is tiny because entries are groups of 32 primitives)
-__global__ void __launch_bounds__(256) k_bin_fill(const SrBinParams p) {
+__global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_fill(const SrBinParams p) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t rect = t < p.nprims ? __ldg(p.rects + t) : SR_RECT_INVALID;
     sr_bin_group<true>(p, rect, t >> 5);
@@ -147,33 +178,117 @@ struct SrTri {
     float x3, y3;
     float a, b, c, d;  // (y2-y3), (x3-x2), (y3-y1), (x1-x3)
     float det;
-    bool det_ok;       // det finite-ish and non-zero: the exact sign shortcut below is valid
+    float rdet;        // correctly rounded 1/det (valid when `fast`)
+    uint32_t dsign;    // sign bit of det
+    bool fast;         // |det| in [2^-40, 2^40]: the exact shortcuts below are valid
 };
 __device__ __forceinline__ SrTri sr_tri_setup(float x1, float y1, float x2, float y2, float x3, float y3) {
     SrTri t;
     t.x3 = x3; t.y3 = y3;
     t.a = y2 - y3; t.b = x3 - x2; t.c = y3 - y1; t.d = x1 - x3;
     t.det = t.a * (x1 - x3) + t.b * (y1 - y3);
-    t.det_ok = fabsf(t.det) > 0.0f && fabsf(t.det) <= 1e30f;
+    const uint32_t db = __float_as_uint(t.det);
+    t.dsign = db & 0x80000000u;
+    t.fast = ((db & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+    t.rdet = __frcp_rn(t.det);
     return t;
 }
-// Barycentrics of pixel (px,py) exactly as triangle.rs:104-113.  Returns false when the pixel is outside.
-// The early-outs are exact: for finite non-zero det and |n| >= 1e-7 the quotient n/det is a non-zero
-// normal/denormal float whose sign is sign(n)*sign(det), so `n/det < 0` iff the signs differ.
-__device__ __forceinline__ bool sr_tri_bary(const SrTri &t, uint32_t px, uint32_t py, float &u, float &v, float &w) {
-    const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+// Correctly rounded n/det without the generic division sequence.  r = RN(1/det); after one
+// Newton correction q is within one ulp of n/det, the residual n - q*det is then exact in an FMA, and
+// q' = RN(q + rem*r) is the correctly rounded quotient (Markstein's theorem).  Valid for |det| in
+// [2^-40, 2^40] and |n| in [2^-60, 2^60] (no over/underflow anywhere); checked against __fdiv_rn on the GPU
+// by tests/test_gpu_parity.py::test_exact_division_shortcut.
+__device__ __forceinline__ float sr_div_exact(float n, float det, float rdet) {
+    float q = n * rdet;
+    float rem = fmaf(-q, det, n);
+    q = fmaf(rem, rdet, q);
+    rem = fmaf(-q, det, n);
+    return fmaf(rem, rdet, q);
+}
+// numerators of u and v at pixel centre (x,y) (triangle.rs:108-109)
+__device__ __forceinline__ void sr_tri_numerators(const SrTri &t, float x, float y, float &nu, float &nv) {
     const float dx = x - t.x3, dy = y - t.y3;
-    const float nu = t.a * dx + t.b * dy;
-    const float nv = t.c * dx + t.d * dy;
-    if (t.det_ok) {
-        const bool dneg = t.det < 0.0f;
-        if (fabsf(nu) >= 1e-7f && ((nu < 0.0f) != dneg)) return false;
-        if (fabsf(nv) >= 1e-7f && ((nv < 0.0f) != dneg)) return false;
+    nu = t.a * dx + t.b * dy;
+    nv = t.c * dx + t.d * dy;
+}
+// u = nu/det, v = nv/det, w = 1-u-v and the inside test, bit-exact with triangle.rs:108-113.
+// Exact early-out: for |det| in the fast range and finite |n| >= 2^-60 the quotient n/det is a non-zero float
+// whose sign is sign(n)*sign(det), so `n/det < 0` iff the sign bits differ.
+__device__ __forceinline__ bool sr_tri_inside(const SrTri &t, float nu, float nv, float &u, float &v, float &w) {
+    const uint32_t bu = __float_as_uint(nu), bv = __float_as_uint(nv);
+    if (t.fast) {
+        if (((bu ^ t.dsign) - 0xA1800000u) < 0x5E000000u) return false;  // negative quotient, magnitude in [2^-60, inf)
+        if (((bv ^ t.dsign) - 0xA1800000u) < 0x5E000000u) return false;
+        const bool fu = ((bu & 0x7FFFFFFFu) - 0x21800000u) < (0x5D800000u - 0x21800000u);
+        const bool fv = ((bv & 0x7FFFFFFFu) - 0x21800000u) < (0x5D800000u - 0x21800000u);
+        if (fu && fv) {
+            u = sr_div_exact(nu, t.det, t.rdet);
+            v = sr_div_exact(nv, t.det, t.rdet);
+        } else {
+            u = nu / t.det;
+            v = nv / t.det;
+        }
+    } else {
+        u = nu / t.det;
+        v = nv / t.det;
     }
-    u = nu / t.det;
-    v = nv / t.det;
     w = 1.0f - u - v;
     return !(u < 0.0f || v < 0.0f || w < 0.0f);
+}
+// Barycentrics of pixel (px,py) exactly as triangle.rs:104-113.  Returns false when the pixel is outside.
+__device__ __forceinline__ bool sr_tri_bary(const SrTri &t, uint32_t px, uint32_t py, float &u, float &v, float &w) {
+    float nu, nv;
+    sr_tri_numerators(t, (float)px + 0.5f, (float)py + 0.5f, nu, nv);
+    return sr_tri_inside(t, nu, nv, u, v, w);
+}
+
+
+// =====================================================================================================
+// sm_100a async-copy plumbing: mbarrier, cp.async.bulk (TMA bulk copy, SASS UBLKCP) and cp.async (LDGSTS)
+// =====================================================================================================
+__device__ __forceinline__ uint32_t sr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sr_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sr_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sr_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void sr_mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sr_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sr_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SR_DONE_%=;\n\t"
+        "bra SR_WAIT_%=;\n\t"
+        "SR_DONE_%=:\n\t"
+        "}" ::"r"(sr_smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void sr_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sr_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sr_smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (tile write-back), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void sr_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sr_smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sr_bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void sr_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sr_cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sr_smem_u32(dst)), "l"(src) : "memory");
+}
+// makes `bar` receive one (pre-counted) arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void sr_cp_async_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sr_smem_u32(bar)) : "memory");
 }
 
 struct SrTileParams {
@@ -201,10 +316,38 @@ __device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, u
 // key (order-preserving depth bits << 32 | primitive+1) per pixel in shared memory, resolves it with
 // atomicMax, then shades each pixel ONCE and writes the tile back to HBM once.
 // =====================================================================================================
+#ifndef SR_OPQ_CONSUMERS
+#define SR_OPQ_CONSUMERS 16   // consumer (rasterising) warps per tile CTA; one more warp is the producer
+#endif
+#ifndef SR_OPQ_STAGES
+#define SR_OPQ_STAGES 32      // ring of group stages in shared memory
+#endif
+#ifndef SR_OPQ_LAG
+#define SR_OPQ_LAG 12         // groups between the bulk copy of rects/indices and the vertex gather
+#endif
+#ifndef SR_OPQ_MIN_CTAS
+#define SR_OPQ_MIN_CTAS 2
+#endif
+#define SR_OPQ_THREADS ((SR_OPQ_CONSUMERS + 1) * 32)
+static_assert(SR_OPQ_LAG < SR_OPQ_STAGES, "the gather must trail the bulk copy by less than the ring size");
+
+// one group of 32 triangles staged for the consumer warps
+struct __align__(16) SrStage {
+    float4 pos[3][32];   // screen-space positions of vertex k of triangle `lane` (gathered with cp.async)
+    uint32_t idx[96];    // the group's 32x3 vertex indices   (cp.async.bulk)
+    uint32_t rect[32];   // the group's 32 packed tile rects  (cp.async.bulk)
+};
+#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_STAGES * (sizeof(SrStage) + 3 * 8 + 4))
+
 template <int FS>
-__global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_opaque(const __grid_constant__ SrTileParams p) {
+__global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrTileParams p) {
     extern __shared__ __align__(16) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
+    SrStage *stage = reinterpret_cast<SrStage *>(keys + SR_TILE_PIXELS);
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(stage + SR_OPQ_STAGES);  // rects + indices landed
+    uint64_t *full_b = full_a + SR_OPQ_STAGES;                               // positions landed
+    uint64_t *empty = full_b + SR_OPQ_STAGES;                                // consumer is done with the stage
+    uint32_t *s_group = reinterpret_cast<uint32_t *>(empty + SR_OPQ_STAGES);
 
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
@@ -214,7 +357,13 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_opaque(const __grid_
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = p.fb.width, H = p.fb.height;
 
-    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+    if (tid < SR_OPQ_STAGES) {
+        sr_mbar_init(full_a + tid, 1);    // producer lane 0: arrive.expect_tx
+        sr_mbar_init(full_b + tid, 32);   // every producer lane: cp.async arrive (noinc)
+        sr_mbar_init(empty + tid, 1);     // consumer lane 0
+    }
+    sr_mbar_init_fence();
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         uint32_t dk = sr_depth_key(__uint_as_float(SR_DEPTH_FAR_BITS));
         if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_pixel(p.fb, px, py)[4]);
@@ -224,65 +373,139 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_opaque(const __grid_
 
     const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;  // last pixel of the tile in the frame
 
-    auto raster_pixel = [&](const SrTri &tr, float z1, float z2, float z3, uint32_t px, uint32_t py, uint32_t id) {
-        float u, v, w;
-        if (!sr_tri_bary(tr, px, py, u, v, w)) return;
-        const float z = (z1 * u + z2 * v) + z3 * w;
-        if (!(z < 0.0f)) return;  // triangle.rs:120
-        const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u);
-        unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
-        if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
-    };
+    if (warp == SR_OPQ_CONSUMERS) {
+        // ---------------- producer warp: keeps the ring of stages full ----------------
+        const uint32_t n0 = p.tris.n0;
+        uint32_t my_g = 0;
+        for (uint32_t step = 0; step < L + SR_OPQ_LAG; ++step) {
+            if (step < L) {  // A: TMA bulk copies of the group's rects and indices
+                if ((step & 31u) == 0) my_g = step + lane < L ? __ldg(p.tri_list + lbeg + step + lane) : 0u;
+                const uint32_t g = __shfl_sync(0xffffffffu, my_g, step & 31u);
+                const uint32_t st = step % SR_OPQ_STAGES, use = step / SR_OPQ_STAGES;
+                if (lane == 0) {
+                    sr_mbar_wait(empty + st, (use & 1u) ^ 1u);
+                    s_group[st] = g;
+                    const bool has_idx = g * SR_GROUP < n0;  // the group holds at least one indexed triangle
+                    sr_mbar_arrive_expect_tx(full_a + st, 128u + (has_idx ? 384u : 0u));
+                    sr_bulk_g2s(stage[st].rect, p.tri_rects + (size_t)g * SR_GROUP, 128u, full_a + st);
+                    if (has_idx) sr_bulk_g2s(stage[st].idx, p.tris.indices + (size_t)g * SR_GROUP * 3, 384u, full_a + st);
+                }
+                __syncwarp();
+            }
+            if (step >= SR_OPQ_LAG) {  // B: gather the positions of the triangles that touch this tile
+                const uint32_t gi = step - SR_OPQ_LAG;
+                const uint32_t st = gi % SR_OPQ_STAGES, use = gi / SR_OPQ_STAGES;
+                sr_mbar_wait(full_a + st, use & 1u);
+                const uint32_t t = s_group[st] * SR_GROUP + lane;
+                const uint32_t rect = stage[st].rect[lane];
+                if (t < p.ntris && rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty)) {
+                    const float4 *src;
+                    uint32_t vi[3];
+                    if (t < n0) {
+                        src = p.tris.vs0.pos;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) vi[k] = stage[st].idx[lane * 3 + k];
+                    } else {
+                        src = p.tris.vs1.pos;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) vi[k] = (t - n0) * 3 + k;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sr_cp_async16(&stage[st].pos[k][lane], src + vi[k]);
+                }
+                sr_cp_async_arrive_noinc(full_b + st);
+            }
+        }
+    } else {
+        // ---------------- consumer warps: setup + coverage + depth resolve, everything from shared memory ----------------
+        // one covered-pixel candidate: exact inside test, depth, 64-bit max
+        auto raster_test = [&](const SrTri &tr, float z1, float z2, float z3, float nu, float nv, uint32_t slot_index, uint32_t id) {
+            float u, v, w;
+            if (!sr_tri_inside(tr, nu, nv, u, v, w)) return;
+            const float z = (z1 * u + z2 * v) + z3 * w;
+            if (!(z < 0.0f)) return;  // triangle.rs:120
+            const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u);
+            unsigned long long *slot = keys + slot_index;
+            if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
+        };
 
-    for (uint32_t gi = warp; gi < L; gi += SR_RASTER_WARPS) {
-        const uint32_t g = __ldg(p.tri_list + lbeg + gi);
-        const uint32_t t = g * SR_GROUP + lane;
-        const uint32_t rect = t < p.ntris ? __ldg(p.tri_rects + t) : SR_RECT_INVALID;
-        const bool hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
-        SrTri tr;
-        float z1 = 0, z2 = 0, z3 = 0;
-        uint32_t minx = 1, maxx = 0, miny = 1, maxy = 0;
-        if (hit) {
-            const SrVertexSet *vs;
-            uint32_t vi[3];
-            sr_prim_vertices<3>(p.tris, t, vs, vi);
-            const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
-            tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
-            z1 = A.z; z2 = B.z; z3 = C.z;
-            minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
-            miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
-            maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
-            maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
-        }
-        const bool nonempty = hit && minx <= maxx && miny <= maxy;
-        const uint32_t bw = nonempty ? maxx - minx + 1 : 0, bh = nonempty ? maxy - miny + 1 : 0;
-        const bool small = nonempty && bw * bh <= SR_SMALL_AREA;
-        if (small) {
-            for (uint32_t py = miny; py <= maxy; ++py)
-                for (uint32_t px = minx; px <= maxx; ++px) raster_pixel(tr, z1, z2, z3, px, py, t);
-        }
-        uint32_t big = __ballot_sync(0xffffffffu, nonempty && !small);
-        while (big) {  // warp-cooperative sweep of one large box at a time
-            const int l = __ffs(big) - 1;
-            big &= big - 1;
-            SrTri s;
-            s.x3 = __shfl_sync(0xffffffffu, tr.x3, l); s.y3 = __shfl_sync(0xffffffffu, tr.y3, l);
-            s.a = __shfl_sync(0xffffffffu, tr.a, l); s.b = __shfl_sync(0xffffffffu, tr.b, l);
-            s.c = __shfl_sync(0xffffffffu, tr.c, l); s.d = __shfl_sync(0xffffffffu, tr.d, l);
-            s.det = __shfl_sync(0xffffffffu, tr.det, l);
-            s.det_ok = fabsf(s.det) > 0.0f && fabsf(s.det) <= 1e30f;
-            const float sz1 = __shfl_sync(0xffffffffu, z1, l), sz2 = __shfl_sync(0xffffffffu, z2, l), sz3 = __shfl_sync(0xffffffffu, z3, l);
-            const uint32_t sminx = __shfl_sync(0xffffffffu, minx, l), sminy = __shfl_sync(0xffffffffu, miny, l);
-            const uint32_t sbw = __shfl_sync(0xffffffffu, bw, l), sbh = __shfl_sync(0xffffffffu, bh, l);
-            const uint32_t st = g * SR_GROUP + l;
-            for (uint32_t i = lane; i < sbw * sbh; i += 32) raster_pixel(s, sz1, sz2, sz3, sminx + i % sbw, sminy + i / sbw, st);
+        for (uint32_t gi = warp; gi < L; gi += SR_OPQ_CONSUMERS) {
+            const uint32_t st = gi % SR_OPQ_STAGES, use = gi / SR_OPQ_STAGES;
+            sr_mbar_wait(full_b + st, use & 1u);
+            const uint32_t g = s_group[st];
+            const uint32_t t = g * SR_GROUP + lane;
+            const uint32_t rect = stage[st].rect[lane];
+            const bool hit = t < p.ntris && rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
+            float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
+            if (hit) {
+                A = stage[st].pos[0][lane];
+                B = stage[st].pos[1][lane];
+                C = stage[st].pos[2][lane];
+            }
+            __syncwarp();
+            if (lane == 0) sr_mbar_arrive(empty + st);  // the stage may be refilled
+            SrTri tr;
+            float z1 = 0, z2 = 0, z3 = 0;
+            uint32_t minx = 1, maxx = 0, miny = 1, maxy = 0;
+            if (hit) {
+                tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+                z1 = A.z; z2 = B.z; z3 = C.z;
+                minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
+                miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
+                maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
+                maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
+            }
+            const bool nonempty = hit && minx <= maxx && miny <= maxy;
+            const uint32_t bw = nonempty ? maxx - minx + 1 : 0, bh = nonempty ? maxy - miny + 1 : 0;
+            const bool small = nonempty && bw * bh <= SR_SMALL_AREA;
+            if (small) {
+                // one lane walks its own small box.  Pixel centres are generated incrementally: (float)px + 0.5f is
+                // exact and so is adding 1.0f to it, so xf/yf carry exactly the values triangle.rs:104-105 computes;
+                // the row terms b*dy and d*dy are hoisted (same roundings, evaluated once per row).
+                const float xf0 = (float)minx + 0.5f;
+                float xf = xf0, yf = (float)miny + 0.5f;
+                float dy = yf - tr.y3, bdy = tr.b * dy, ddy = tr.d * dy;
+                uint32_t px = minx, slot_index = (miny - y0) * SR_TILE_W + (minx - x0);
+                const uint32_t n = bw * bh;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const float dx = xf - tr.x3;
+                    raster_test(tr, z1, z2, z3, tr.a * dx + bdy, tr.c * dx + ddy, slot_index, t);
+                    ++px; ++slot_index; xf += 1.0f;
+                    if (px > maxx) {
+                        px = minx; xf = xf0; slot_index += SR_TILE_W - bw;
+                        yf += 1.0f; dy = yf - tr.y3; bdy = tr.b * dy; ddy = tr.d * dy;
+                    }
+                }
+            }
+            uint32_t big = __ballot_sync(0xffffffffu, nonempty && !small);
+            while (big) {  // warp-cooperative sweep of one large box at a time
+                const int l = __ffs(big) - 1;
+                big &= big - 1;
+                SrTri s;
+                s.x3 = __shfl_sync(0xffffffffu, tr.x3, l); s.y3 = __shfl_sync(0xffffffffu, tr.y3, l);
+                s.a = __shfl_sync(0xffffffffu, tr.a, l); s.b = __shfl_sync(0xffffffffu, tr.b, l);
+                s.c = __shfl_sync(0xffffffffu, tr.c, l); s.d = __shfl_sync(0xffffffffu, tr.d, l);
+                s.det = __shfl_sync(0xffffffffu, tr.det, l); s.rdet = __shfl_sync(0xffffffffu, tr.rdet, l);
+                s.dsign = __float_as_uint(s.det) & 0x80000000u;
+                s.fast = ((__float_as_uint(s.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                const float sz1 = __shfl_sync(0xffffffffu, z1, l), sz2 = __shfl_sync(0xffffffffu, z2, l), sz3 = __shfl_sync(0xffffffffu, z3, l);
+                const uint32_t sminx = __shfl_sync(0xffffffffu, minx, l), sminy = __shfl_sync(0xffffffffu, miny, l);
+                const uint32_t sbw = __shfl_sync(0xffffffffu, bw, l), sbh = __shfl_sync(0xffffffffu, bh, l);
+                const uint32_t st_id = g * SR_GROUP + l;
+                for (uint32_t i = lane; i < sbw * sbh; i += 32) {
+                    const uint32_t px = sminx + i % sbw, py = sminy + i / sbw;
+                    float nu, nv;
+                    sr_tri_numerators(s, (float)px + 0.5f, (float)py + 0.5f, nu, nv);
+                    raster_test(s, sz1, sz2, sz3, nu, nv, (py - y0) * SR_TILE_W + (px - x0), st_id);
+                }
+            }
         }
     }
     __syncthreads();
 
     // resolve: shade every pixel once, write colour + depth (+winner) to HBM once
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
-    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
+    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         if (px >= W || py >= H) continue;
         const unsigned long long key = keys[i];
@@ -738,6 +961,38 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         if (c.has_stencil) p.fb.stencil[(uint64_t)py * W + px] = s_stencil[i];
         if (p.fb.winner && s_winner[i]) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];  // plane is zeroed per draw
     }
+}
+
+// self-test of sr_div_exact against the IEEE division it replaces (parity evidence for the coverage shortcut):
+// random sign/exponent/mantissa patterns over the whole validity range, plus all-ones / sparse mantissas.
+__global__ void __launch_bounds__(256) k_selftest_division(uint64_t seed, uint64_t per_thread, unsigned long long *mismatches) {
+    uint64_t state = seed + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    auto next = [&]() {
+        state += 0x9E3779B97F4A7C15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto make = [&](uint64_t r, uint32_t elo, uint32_t ehi) {
+        uint32_t mant = (uint32_t)(r >> 8) & 0x7FFFFFu;
+        const uint32_t mode = (uint32_t)(r >> 40) & 15u;
+        if (mode == 0) mant = 0x7FFFFFu;
+        else if (mode == 1) mant = 0;
+        else if (mode == 2) mant &= 0x7FF000u;
+        else if (mode == 3) mant |= 0x7FF000u;
+        else if (mode == 4) mant = 1u << ((r >> 44) % 23);
+        const uint32_t e = elo + (uint32_t)((r >> 48) % (ehi - elo));
+        return __uint_as_float(((uint32_t)(r & 1) << 31) | (e << 23) | mant);
+    };
+    unsigned long long bad = 0;
+    for (uint64_t i = 0; i < per_thread; ++i) {
+        const float det = make(next(), 87, 167);  // |det| in [2^-40, 2^40)
+        const float n = make(next(), 67, 187);    // |n| in [2^-60, 2^60)
+        const float q = sr_div_exact(n, det, __frcp_rn(det));
+        if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(n, det))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // materialise a pending clear (RenderBuffer::clear, renderbuffer/mod.rs:126-133) when no draw did it

@@ -67,6 +67,21 @@ template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int 
 template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false; };
 template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true; };
 
+// Fragment-shader arithmetic is NOT on the bit-exact path (colour parity is 1/255 per channel, and the reference's
+// powf is libm's): normalisation uses rsqrtf and powers use exp2(y*log2(x)) on the SFU unless SR_FS_EXACT is set.
+#ifdef SR_FS_EXACT
+__device__ __forceinline__ float sr_fs_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ void sr_fs_normalize4(const float *a, float *out) { sr_normalize4(a, out); }
+__device__ __forceinline__ float sr_fs_div(float a, float b) { return a / b; }
+#else
+__device__ __forceinline__ float sr_fs_pow(float x, float y) { return __powf(x, y); }
+__device__ __forceinline__ void sr_fs_normalize4(const float *a, float *out) {
+    const float inv = rsqrtf(sr_dot4(a, a));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = a[i] * inv;
+}
+__device__ __forceinline__ float sr_fs_div(float a, float b) { return __fdividef(a, b); }
+#endif
 __device__ __forceinline__ float sr_saturate(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 __device__ __forceinline__ float sr_fresnel_schlick(float cos_theta, float ior) {
     const float f0 = sr_powi2((1.0f - ior) / (1.0f + ior));
@@ -96,7 +111,7 @@ __device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, fl
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         const float val = (a00[ch] * u_opp + a10[ch] * u_ratio) * v_opp + (a01[ch] * u_opp + a11[ch] * u_ratio) * v_ratio;
-        out[ch] = ch < 3 ? powf(val, 2.2f) : val;  // decode_gamma (full_example/src/color.rs:48-55)
+        out[ch] = ch < 3 ? sr_fs_pow(val, 2.2f) : val;  // decode_gamma (full_example/src/color.rs:48-55)
     }
 }
 
@@ -123,22 +138,22 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
         float d[4], view_dir[4], light_dir[4], h[4], halfway[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = c.u.camera[i] - position[i];
-        sr_normalize4(d, view_dir);
+        sr_fs_normalize4(d, view_dir);
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = c.u.sz_light[i] - position[i];
-        sr_normalize4(d, light_dir);
+        sr_fs_normalize4(d, light_dir);
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
-        sr_normalize4(h, halfway);
+        sr_fs_normalize4(h, halfway);
         const float NdotL = fmaxf(fminf(sr_dot4(light_dir, normal), 1.0f), 0.0f);
         const float NdotH = fmaxf(fminf(sr_dot4(normal, halfway), 1.0f), 0.0f);
         const float VdotH = fmaxf(fminf(sr_dot4(view_dir, halfway), 1.0f), 0.0f);
         const float f = sr_fresnel_schlick(VdotH, 1.45f);
         const float diffuse = NdotL * (1.0f - f);
-        const float specular = f * powf(NdotH, 32.0f * 2.0f);
+        const float specular = f * sr_fs_pow(NdotH, 32.0f * 2.0f);
         const float inv_gamma = 1.0f / 2.2f;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) out[i] = powf(c.u.sz_intensity * (specular + (diffuse * c.u.sz_color[i])), inv_gamma);
+        for (int i = 0; i < 3; ++i) out[i] = sr_fs_pow(c.u.sz_intensity * (specular + (diffuse * c.u.sz_color[i])), inv_gamma);
         out[3] = 1.0f;
         return true;
     } else {
@@ -147,8 +162,8 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
         float d[4], view_dir[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = c.u.camera[i] - position[i];
-        sr_normalize4(d, view_dir);
-        const float m = powf(0.25f, 2.2f);
+        sr_fs_normalize4(d, view_dir);
+        const float m = sr_fs_pow(0.25f, 2.2f);
         float material[3] = {m, m, m};
         if (FS == SR_FS_FULL_EXAMPLE_TEXTURED) {
             if (c.tex != nullptr) {
@@ -168,11 +183,11 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
 #pragma unroll
             for (int i = 0; i < 4; ++i) ld[i] = lp[i] - position[i];
             const float light_distance = sr_norm4(ld);
-            sr_normalize4(ld, light_dir);
+            sr_fs_normalize4(ld, light_dir);
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
-            sr_normalize4(h, halfway);
-            const float intensity = light.intensity / sr_powi2(light_distance);
+            sr_fs_normalize4(h, halfway);
+            const float intensity = sr_fs_div(light.intensity, sr_powi2(light_distance));
             const float NdotL = sr_saturate(sr_dot4(light_dir, normal));
             const float NdotH = sr_saturate(sr_dot4(normal, halfway));
             const float VdotH = sr_saturate(sr_dot4(view_dir, halfway));
@@ -187,8 +202,8 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float x = color[i];  // aces_filmic_tonemap_component (full_example/src/color.rs:20-28)
-            const float tm = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
-            out[i] = powf(tm, inv_gamma);
+            const float tm = sr_fs_div(x * (2.51f * x + 0.03f), x * (2.43f * x + 0.59f) + 0.14f);
+            out[i] = sr_fs_pow(tm, inv_gamma);
         }
         out[3] = 1.0f;
         return true;

@@ -59,6 +59,11 @@ class Context:
         check(lib.sr_context_launch_count(self.h, ctypes.byref(n)))
         return n.value
 
+    def selftest_division(self, seed: int, count: int) -> int:
+        bad = ctypes.c_uint64()
+        check(lib.sr_selftest_division(self.h, seed, count, ctypes.byref(bad)))
+        return bad.value
+
     def stage_times(self) -> dict:
         t = _abi.StageTimes()
         check(lib.sr_context_stage_times(self.h, ctypes.byref(t)))

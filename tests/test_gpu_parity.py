@@ -514,6 +514,13 @@ def test_grid_scene_reduced(P, ctx, reverse):
         x.destroy()
 
 
+def test_exact_division_shortcut(P, ctx):
+    """The coverage path replaces `n / det` by a reciprocal + two FMA corrections; it must be the IEEE quotient,
+    bit for bit, over its whole validity range (4e9 random operand pairs incl. all-ones/sparse mantissas)."""
+    for seed in (1, 0xDEADBEEF):
+        assert ctx.selftest_division(seed, 2_000_000_000) == 0
+
+
 def test_error_behaviour(P, ctx):
     from softrender_b200._abi import SoftrenderError
     u = scenes.suzanne_uniforms(8, 8)
