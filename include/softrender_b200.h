@@ -53,6 +53,11 @@ void *sr_context_stream(sr_context *);
 /* sort-first tile sharding: this context rasterises only the GPU tiles with
  * tile_index % world == rank (geometry stages still run for the whole mesh). */
 int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
+/* tuning of the opaque triangle path: triangles whose frame-clamped bounding box holds at most
+ * `area` pixels are rasterised per-triangle into the visibility buffer, the rest through per-tile lists.
+ * area = 0 sends every triangle through the tile lists.  Draws onto existing (not freshly cleared) contents
+ * use the visibility buffer only from `min_triangles` on.  Results never depend on these values. */
+int sr_context_set_micro(sr_context *, uint32_t area, uint32_t min_triangles, uint32_t precheck);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int sr_context_launch_count(sr_context *, uint64_t *out);
 

@@ -144,8 +144,9 @@ typedef struct sr_uniforms {
 typedef struct sr_stage_times {
     float vertex_ms;
     float geometry_ms;
-    float bin_ms;
-    float raster_ms;
+    float bin_ms;     /* per-tile lists of the ordered path (triangles with blend/stencil/discard, lines, points) */
+    float micro_ms;   /* opaque path: visibility-buffer init + per-triangle setup / small-triangle rasterisation */
+    float raster_ms;  /* tile kernels: large triangles, resolve (shading) and the single write-back */
     float total_ms;
 } sr_stage_times;
 

@@ -28,7 +28,7 @@ pp = ctypes.POINTER(c_void_p)
 
 class StageTimes(ctypes.Structure):
     _fields_ = [("vertex_ms", ctypes.c_float), ("geometry_ms", ctypes.c_float), ("bin_ms", ctypes.c_float),
-                ("raster_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
+                ("micro_ms", ctypes.c_float), ("raster_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
 
 
 # every symbol include/softrender_b200.h declares: name -> (restype, argtypes)
@@ -41,6 +41,7 @@ SYMBOLS = {
     "sr_context_synchronize": (c_int, [c_void_p]),
     "sr_context_stream": (c_void_p, [c_void_p]),
     "sr_context_set_tile_shard": (c_int, [c_void_p, c_u32, c_u32]),
+    "sr_context_set_micro": (c_int, [c_void_p, c_u32, c_u32, c_u32]),
     "sr_context_launch_count": (c_int, [c_void_p, u64p]),
     "sr_context_stage_times": (c_int, [c_void_p, ctypes.POINTER(StageTimes)]),
     "sr_framebuffer_create": (c_int, [c_void_p, c_u32, c_u32, c_u32, pp]),

@@ -56,8 +56,12 @@ struct sr_context {
     std::multimap<size_t, void *> free_list;  // stream-ordered reuse of scratch allocations
     uint32_t shard_rank = 0, shard_world = 1;
     uint64_t launches = 0;
-    cudaEvent_t ev[6] = {};  // vertex begin/end, geometry end, bin end, raster end, spare
-    bool ev_valid[6] = {};
+    cudaEvent_t ev[8] = {};  // vertex begin/end, geometry end, fragment begin, bins end, micro end, raster end
+    bool ev_valid[8] = {};
+    uint32_t micro_area = SR_MICRO_AREA_DEFAULT;  // bbox pixels up to which k_micro rasterises a triangle itself (0: off)
+    uint32_t micro_min_tris = 65536;              // draws onto existing contents use the visibility buffer from this size on
+    uint32_t micro_precheck = 1;
+    uint32_t *pinned = nullptr;                   // pinned host words for device->host counters
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);
     void release(void *p, size_t bytes) { free_list.emplace(bytes, p); }
@@ -109,6 +113,7 @@ struct sr_framebuffer {
     uint32_t width, height, format;
     uint32_t ntx, nty;
     Buf aos_buf, stencil_buf, winner_buf;
+    Buf vis_buf;                // tiled visibility buffer of the opaque path (allocated on first use)
     float *aos = nullptr;       // device (possibly peer) pointer
     bool is_peer = false;       // opened through cudaIpcOpenMemHandle
     bool pending_clear = false;
@@ -313,28 +318,104 @@ static SrPrimSource prim_source(const sr_draw *d, uint32_t kind /*1 point,2 line
 // kernel dispatch by registered shader id
 // ---------------------------------------------------------------------------------------------------------
 template <int FS>
-static int launch_tiles(sr_context *c, bool ordered, uint32_t ntiles_owned, const SrTileParams &p) {
-    if (ordered) {
-        SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
-        SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
-    } else {
-        const size_t smem = SR_OPQ_SMEM_BYTES;
-        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_OPQ_THREADS, smem, p);
-    }
+static int launch_tiles(sr_context *c, uint32_t ntiles_owned, const SrTileParams &p) {
+    SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
+    SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
     return SR_OK;
 }
-static int launch_tiles_fs(sr_context *c, uint32_t fs, bool ordered, uint32_t ntiles_owned, const SrTileParams &p) {
+static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrTileParams &p) {
     switch (fs) {
-        case SR_FS_FLAT: return launch_tiles<SR_FS_FLAT>(c, ordered, ntiles_owned, p);
-        case SR_FS_SUZANNE: return launch_tiles<SR_FS_SUZANNE>(c, ordered, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE: return launch_tiles<SR_FS_FULL_EXAMPLE>(c, ordered, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_tiles<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ordered, ntiles_owned, p);
-        case SR_FS_GREEN: return launch_tiles<SR_FS_GREEN>(c, ordered, ntiles_owned, p);
-        case SR_FS_DISCARD_CHECKER: return launch_tiles<SR_FS_DISCARD_CHECKER>(c, ordered, ntiles_owned, p);
+        case SR_FS_FLAT: return launch_tiles<SR_FS_FLAT>(c, ntiles_owned, p);
+        case SR_FS_SUZANNE: return launch_tiles<SR_FS_SUZANNE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE: return launch_tiles<SR_FS_FULL_EXAMPLE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_tiles<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
+        case SR_FS_GREEN: return launch_tiles<SR_FS_GREEN>(c, ntiles_owned, p);
+        case SR_FS_DISCARD_CHECKER: return launch_tiles<SR_FS_DISCARD_CHECKER>(c, ntiles_owned, p);
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown fragment shader %u", fs);
+}
+template <int FS>
+static int launch_opaque(sr_context *c, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+    SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
+    SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
+    return SR_OK;
+}
+static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+    switch (fs) {
+        case SR_FS_FLAT: return launch_opaque<SR_FS_FLAT>(c, ntiles_owned, p);
+        case SR_FS_SUZANNE: return launch_opaque<SR_FS_SUZANNE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE: return launch_opaque<SR_FS_FULL_EXAMPLE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
+        case SR_FS_GREEN: return launch_opaque<SR_FS_GREEN>(c, ntiles_owned, p);
+    }
+    return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
+}
+
+// The opaque triangle path (sr_raster.cuh): visibility-buffer init, k_micro (per-triangle setup + direct
+// rasterisation of small triangles + compaction/counting of the large ones), per-tile lists of the large
+// triangles, then the tile kernel (large triangles + resolve + single write-back).
+static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned) {
+    const uint32_t ntiles = fb->ntx * fb->nty;
+    const bool use_micro = c->micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
+    if (use_micro) {
+        if (!fb->vis_buf) SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
+        SR_LAUNCH(c, k_vis_init, owned, 256, 0, fb->vis_buf->as<unsigned long long>(), fb->view(), c->shard_rank, c->shard_world);
+    }
+    Buf count, off, lcount, lids, lrects, list;
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
+    SR_TRY(c->alloc(4, &lcount));
+    SR_TRY(c->alloc((size_t)std::max(tp.ntris, 1u) * 4, &lids));
+    SR_TRY(c->alloc((size_t)std::max(tp.ntris, 1u) * 4, &lrects));
+    SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
+    SR_CUDA(cudaMemsetAsync(lcount->ptr, 0, 4, c->stream));
+    uint32_t nlarge = 0, total = 0;
+    if (tp.ntris) {
+        SrMicroParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.src = tp.tris;
+        mp.ntris = tp.ntris;
+        mp.cull = cull;
+        mp.width = fb->width; mp.height = fb->height; mp.ntx = fb->ntx; mp.nty = fb->nty;
+        mp.shard_rank = c->shard_rank; mp.shard_world = c->shard_world;
+        mp.micro_area = use_micro ? c->micro_area : 0u;
+        mp.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
+        mp.large_count = lcount->as<uint32_t>();
+        mp.large_ids = lids->as<uint32_t>();
+        mp.large_rects = lrects->as<uint32_t>();
+        mp.tile_count = count->as<uint32_t>();
+        const uint32_t grid = ceil_div(tp.ntris, SR_MICRO_THREADS);
+        if (c->micro_precheck) SR_LAUNCH(c, k_micro<true>, grid, SR_MICRO_THREADS, 0, mp);
+        else SR_LAUNCH(c, k_micro<false>, grid, SR_MICRO_THREADS, 0, mp);
+        record(c, 5);
+        SR_LAUNCH(c, k_tile_offsets, 1, 256, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
+        if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+        SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaMemcpyAsync(&c->pinned[1], lcount->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaStreamSynchronize(c->stream));
+        total = c->pinned[0];
+        nlarge = c->pinned[1];
+    } else {
+        SR_CUDA(cudaMemsetAsync(off->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
+        record(c, 5);
+    }
+    SR_TRY(c->alloc((size_t)std::max(total, 1u) * 4, &list));
+    if (nlarge)
+        SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(nlarge, 256), 148u * 8u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
+                  lrects->as<uint32_t>(), fb->ntx, c->shard_rank, c->shard_world, off->as<uint32_t>(), count->as<uint32_t>(), list->as<uint32_t>());
+    SrOpaqueParams op;
+    memset(&op, 0, sizeof(op));
+    op.tris = tp.tris;
+    op.ntris = tp.ntris;
+    op.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
+    op.tile_off = off->as<uint32_t>();
+    op.list = list->as<uint32_t>();
+    op.fb = fb->view();
+    op.shard_rank = c->shard_rank; op.shard_world = c->shard_world;
+    op.fs = tp.fs;
+    SR_TRY(launch_opaque_fs(c, fs, owned, op));
+    fb->pending_clear = false;
+    return SR_OK;
 }
 static int fs_nk(uint32_t fs) {
     switch (fs) {
@@ -387,6 +468,7 @@ int sr_context_destroy(sr_context *c) {
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
     return SR_OK;
 }
@@ -400,6 +482,14 @@ int sr_context_set_tile_shard(sr_context *c, uint32_t rank, uint32_t world) {
     if (!c || world == 0 || rank >= world) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad shard %u/%u", rank, world);
     c->shard_rank = rank;
     c->shard_world = world;
+    return SR_OK;
+}
+int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, uint32_t precheck) {
+    if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null context");
+    if (area > SR_MICRO_AREA_MAX) return sr_fail(SR_ERR_INVALID_ARGUMENT, "micro area %u > %u", area, SR_MICRO_AREA_MAX);
+    c->micro_area = area;
+    c->micro_min_tris = min_triangles;
+    c->micro_precheck = precheck ? 1u : 0u;
     return SR_OK;
 }
 int sr_context_launch_count(sr_context *c, uint64_t *out) {
@@ -417,8 +507,9 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
     span(0, 1, &t.vertex_ms);
     span(1, 2, &t.geometry_ms);
     span(3, 4, &t.bin_ms);
-    span(4, 5, &t.raster_ms);
-    t.total_ms = t.vertex_ms + t.geometry_ms + t.bin_ms + t.raster_ms;
+    span(4, 5, &t.micro_ms);
+    span(5, 6, &t.raster_ms);
+    t.total_ms = t.vertex_ms + t.geometry_ms + t.bin_ms + t.micro_ms + t.raster_ms;
     *out = t;
     return SR_OK;
 }
@@ -990,44 +1081,39 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     if (fb->winner_enabled && fb->winner_buf)  // winner plane reports the primitives of THIS draw
         SR_CUDA(cudaMemsetAsync(fb->winner_buf->ptr, 0, (size_t)fb->width * fb->height * 4, c->stream));
     record(c, 3);
-    Bins bt, bl, bp;
-    SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt));
-    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl));
-    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp));
-    record(c, 4);
-    tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>();
-    tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>();
-    tp.point_rects = bp.rects->as<uint32_t>(); tp.point_off = bp.off->as<uint32_t>(); tp.point_list = bp.list->as<uint32_t>();
-
     const uint32_t ntiles = fb->ntx * fb->nty;
     const uint32_t owned = ntiles > c->shard_rank ? (ntiles - c->shard_rank + c->shard_world - 1) / c->shard_world : 0;
     const bool stencil_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
     const bool opaque_ok = d->blend == SR_BLEND_REPLACE && !stencil_active && fs != SR_FS_DISCARD_CHECKER;
+    Bins bt, bl, bp;
+    if (opaque_ok) SR_TRY(zero_offsets(c, ntiles, &bt));  // triangles go through opaque_triangles below
+    else SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt));
+    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl));
+    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp));
+    record(c, 4);
+    record(c, 5);
+    tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>();
+    tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>();
+    tp.point_rects = bp.rects->as<uint32_t>(); tp.point_off = bp.off->as<uint32_t>(); tp.point_list = bp.list->as<uint32_t>();
+
     if (owned) {
         if (opaque_ok) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,
             // fragment.rs:268-311) through the ordered kernel
-            if (tp.ntris || fb->pending_clear) {
-                tp.fb = fb->view();
-                SR_TRY(launch_tiles_fs(c, fs, false, owned, tp));
-                fb->pending_clear = false;
-            }
+            if (tp.ntris || fb->pending_clear) SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned));
             if (tp.nlines + tp.npoints) {
-                Bins none;
-                SR_TRY(zero_offsets(c, ntiles, &none));
                 SrTileParams t2 = tp;
                 t2.ntris = 0;
-                t2.tri_off = none.off->as<uint32_t>();
                 t2.fb = fb->view();
-                SR_TRY(launch_tiles_fs(c, fs, true, owned, t2));
+                SR_TRY(launch_tiles_fs(c, fs, owned, t2));
             }
         } else {
             tp.fb = fb->view();
-            SR_TRY(launch_tiles_fs(c, fs, true, owned, tp));
+            SR_TRY(launch_tiles_fs(c, fs, owned, tp));
             fb->pending_clear = false;
         }
     }
-    record(c, 5);
+    record(c, 6);
     return SR_OK;
 }
 

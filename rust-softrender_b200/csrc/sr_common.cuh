@@ -18,7 +18,7 @@
 #define SR_TILE_W 64
 #endif
 #ifndef SR_TILE_H
-#define SR_TILE_H 64
+#define SR_TILE_H 32
 #endif
 #define SR_TILE_PIXELS (SR_TILE_W * SR_TILE_H)
 #define SR_GROUP 32          // primitives per bin entry (one warp's worth of consecutive primitives)

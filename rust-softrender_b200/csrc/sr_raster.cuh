@@ -16,6 +16,8 @@
 #endif
 #define SR_RASTER_WARPS (SR_RASTER_THREADS / 32)
 #define SR_SMALL_AREA 16          // bbox pixels a single lane rasterises itself; larger boxes go warp-wide
+#define SR_MICRO_AREA_DEFAULT 16   // bbox pixels up to which k_micro rasterises a triangle itself
+#define SR_MICRO_AREA_MAX 4096
 #define SR_DEPTH_FAR_BITS 0xFF7FFFFFu  // f32::MIN, Depth::far() (src/framebuffer/attachments/depth.rs:31)
 
 struct SrBinParams {
@@ -309,145 +311,263 @@ __device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, u
 }
 
 // =====================================================================================================
-// Opaque tile rasteriser: Blend = (), stencil test Always / op Keep, shader never discards.
+// Opaque path: Blend = (), stencil test Always / op Keep, shader never discards.
 // In that state the reference's in-order result at a pixel is the covering fragment with z<0 that
 // maximises (z, submission index) among those with z >= the depth already stored (`d >= dt`, later
-// primitives win ties, triangle.rs:120-126).  That is order-independent, so the tile keeps one 64-bit
-// key (order-preserving depth bits << 32 | primitive+1) per pixel in shared memory, resolves it with
-// atomicMax, then shades each pixel ONCE and writes the tile back to HBM once.
+// primitives win ties, triangle.rs:120-126).  That is order-independent, so every fragment is reduced
+// into one 64-bit key per pixel, (order-preserving depth bits << 32 | primitive+1), with atomicMax; each
+// pixel is then shaded ONCE and the tile is written back to HBM once.
+//
+// Two producers feed the keys:
+//  * k_micro: one thread per triangle, in submission order.  A triangle whose frame-clamped bounding box
+//    holds at most `micro_area` pixels is rasterised on the spot into the frame's visibility buffer (keys in
+//    HBM/L2, tiled so each GPU tile is one contiguous 16 KB block) -- no bin lists, no second visit.
+//    Larger triangles are appended to a compact list and counted per tile.
+//  * k_tile_opaque: one CTA per tile.  Pulls the tile's keys into shared memory with one TMA bulk copy,
+//    sweeps the tile's (large) triangle list warp-cooperatively against them, then resolves.
 // =====================================================================================================
-#ifndef SR_OPQ_CONSUMERS
-#define SR_OPQ_CONSUMERS 16   // consumer (rasterising) warps per tile CTA; one more warp is the producer
-#endif
-#ifndef SR_OPQ_STAGES
-#define SR_OPQ_STAGES 32      // ring of group stages in shared memory
-#endif
-#ifndef SR_OPQ_LAG
-#define SR_OPQ_LAG 12         // groups between the bulk copy of rects/indices and the vertex gather
+#define SR_VIS_FAR_KEY ((unsigned long long)(~SR_DEPTH_FAR_BITS) << 32)  // sr_depth_key(f32::MIN) << 32, primitive 0
+static_assert((SR_DEPTH_FAR_BITS & 0x80000000u) != 0, "far depth is negative");
+
+__device__ __forceinline__ uint64_t sr_vis_index(uint32_t px, uint32_t py, uint32_t ntx) {
+    const uint32_t tile = (py / SR_TILE_H) * ntx + (px / SR_TILE_W);
+    return (uint64_t)tile * SR_TILE_PIXELS + (py % SR_TILE_H) * SR_TILE_W + (px % SR_TILE_W);
+}
+
+struct SrMicroParams {
+    SrPrimSource src;
+    uint32_t ntris, cull;
+    uint32_t width, height, ntx, nty;
+    uint32_t shard_rank, shard_world;
+    uint32_t micro_area;          // bbox pixels up to which a triangle is rasterised by k_micro (0: none)
+    unsigned long long *vis;      // tiled visibility buffer (ntiles * SR_TILE_PIXELS keys)
+    uint32_t *large_count;        // number of entries in large_ids
+    uint32_t *large_ids;          // triangles left to the tile kernel ...
+    uint32_t *large_rects;        // ... and their packed tile rectangles
+    uint32_t *tile_count;         // per tile: number of large triangles touching it
+};
+
+// keys of the tiles this rank owns := far (pending clear) or the depth already in the framebuffer
+__global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const SrFbView fb, uint32_t shard_rank, uint32_t shard_world) {
+    const uint32_t tile = shard_rank + blockIdx.x * shard_world;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(vis + (uint64_t)tile * SR_TILE_PIXELS);
+    if (fb.pending_clear) {
+        const ulonglong2 k = make_ulonglong2(SR_VIS_FAR_KEY, SR_VIS_FAR_KEY);
+        for (uint32_t i = threadIdx.x; i < SR_TILE_PIXELS / 2; i += 256) dst[i] = k;
+        return;
+    }
+    const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
+    for (uint32_t i = threadIdx.x; i < SR_TILE_PIXELS; i += 256) {
+        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+        uint32_t dk = ~SR_DEPTH_FAR_BITS;
+        if (px < fb.width && py < fb.height) dk = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px) * 5 + 4]);
+        vis[(uint64_t)tile * SR_TILE_PIXELS + i] = (unsigned long long)dk << 32;
+    }
+}
+
+// One lane walks a small pixel box [minx, minx+bw) x [miny, miny+bh) of its triangle and calls
+// emit(px, py, key) for every fragment that passes coverage and z<0 (triangle.rs:104-120).
+// Pixel centres are generated incrementally: (float)px + 0.5f is exact and so is adding 1.0f to it, so xf/yf carry
+// exactly the values triangle.rs:104-105 computes; the row terms b*dy and d*dy are hoisted (same roundings).
+template <class Emit>
+__device__ __forceinline__ void sr_raster_box(const SrTri &tr, float z1, float z2, float z3, uint32_t minx, uint32_t miny,
+                                              uint32_t bw, uint32_t bh, uint32_t id, Emit emit) {
+    const float xf0 = (float)minx + 0.5f;
+    float xf = xf0, yf = (float)miny + 0.5f;
+    float dy = yf - tr.y3, bdy = tr.b * dy, ddy = tr.d * dy;
+    uint32_t px = minx, py = miny;
+    const uint32_t n = bw * bh, maxx = minx + bw - 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float dx = xf - tr.x3;
+        float u, v, w;
+        if (sr_tri_inside(tr, tr.a * dx + bdy, tr.c * dx + ddy, u, v, w)) {
+            const float z = (z1 * u + z2 * v) + z3 * w;
+            if (z < 0.0f)  // triangle.rs:120
+                emit(px, py, ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u));
+        }
+        ++px; xf += 1.0f;
+        if (px > maxx) {
+            px = minx; xf = xf0; ++py;
+            yf += 1.0f; dy = yf - tr.y3; bdy = tr.b * dy; ddy = tr.d * dy;
+        }
+    }
+}
+
+__device__ __forceinline__ void sr_red_max_u64(unsigned long long *addr, unsigned long long key) {
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(addr), "l"(key) : "memory");
+}
+__device__ __forceinline__ unsigned long long sr_ld_relaxed_u64(const unsigned long long *addr) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+
+#define SR_MICRO_THREADS 256
+template <bool PRECHECK>
+__global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constant__ SrMicroParams p) {
+    const uint32_t t = blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    bool large = false;
+    uint32_t rect = SR_RECT_INVALID;
+    if (t < p.ntris) {
+        const SrVertexSet *vs;
+        uint32_t vi[3];
+        sr_prim_vertices<3>(p.src, t, vs, vi);
+        const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+        // the reference panics on NaN coordinates (cast(..).unwrap()); defined here as "skipped"
+        bool ok = !(isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y));
+        if (ok && p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
+            const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
+            ok = (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) != p.cull;
+        }
+        if (ok) {
+            // triangle.rs:74-78 with tile = the whole frame
+            const uint32_t minx = sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, p.width - 1);
+            const uint32_t miny = sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, p.height - 1);
+            const uint32_t maxx = sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, p.width - 1);
+            const uint32_t maxy = sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, p.height - 1);
+            if (minx <= maxx && miny <= maxy) {
+                const uint32_t bw = maxx - minx + 1, bh = maxy - miny + 1;
+                const uint32_t tx0 = minx / SR_TILE_W, ty0 = miny / SR_TILE_H, tx1 = maxx / SR_TILE_W, ty1 = maxy / SR_TILE_H;
+                if (bw * bh <= p.micro_area) {
+                    const bool one_tile = tx0 == tx1 && ty0 == ty1;
+                    const bool sharded = p.shard_world > 1;
+                    if (!(sharded && one_tile && (ty0 * p.ntx + tx0) % p.shard_world != p.shard_rank)) {
+                        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+                        const bool per_pixel_owner = sharded && !one_tile;
+                        sr_raster_box(tr, A.z, B.z, C.z, minx, miny, bw, bh, t, [&](uint32_t px, uint32_t py, unsigned long long key) {
+                            if (per_pixel_owner && ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world != p.shard_rank) return;
+                            unsigned long long *slot = p.vis + sr_vis_index(px, py, p.ntx);
+                            if (PRECHECK && !(key > sr_ld_relaxed_u64(slot))) return;
+                            sr_red_max_u64(slot, key);
+                        });
+                    }
+                } else {
+                    rect = sr_pack_rect(tx0, ty0, tx1, ty1);
+                    if (p.shard_world == 1) {
+                        large = true;
+                    } else {
+                        for (uint32_t ty = ty0; ty <= ty1 && !large; ++ty)
+                            for (uint32_t tx = tx0; tx <= tx1; ++tx)
+                                if ((ty * p.ntx + tx) % p.shard_world == p.shard_rank) { large = true; break; }
+                    }
+                }
+            }
+        }
+    }
+    // large triangles: order-preserving (within the warp) append to the compact list + per-tile counts
+    const uint32_t m = __ballot_sync(0xffffffffu, large);
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(p.large_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (large) {
+        const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+        p.large_ids[slot] = t;
+        p.large_rects[slot] = rect;
+        const uint32_t tx0 = rect & 255u, ty0 = (rect >> 8) & 255u, tx1 = (rect >> 16) & 255u, ty1 = rect >> 24;
+        for (uint32_t ty = ty0; ty <= ty1; ++ty)
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                const uint32_t tile = ty * p.ntx + tx;
+                if (tile % p.shard_world == p.shard_rank) atomicAdd(p.tile_count + tile, 1u);
+            }
+    }
+}
+
+// second pass over the large triangles only: write their ids into the per-tile lists
+__global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count, const uint32_t *large_ids, const uint32_t *large_rects,
+                                                    uint32_t ntx, uint32_t shard_rank, uint32_t shard_world, const uint32_t *tile_off,
+                                                    uint32_t *tile_cursor, uint32_t *list) {
+    const uint32_t n = *large_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t t = large_ids[i], rect = large_rects[i];
+        const uint32_t tx0 = rect & 255u, ty0 = (rect >> 8) & 255u, tx1 = (rect >> 16) & 255u, ty1 = rect >> 24;
+        for (uint32_t ty = ty0; ty <= ty1; ++ty)
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                const uint32_t tile = ty * ntx + tx;
+                if (tile % shard_world != shard_rank) continue;
+                list[tile_off[tile] + atomicAdd(tile_cursor + tile, 1u)] = t;
+            }
+    }
+}
+
+#ifndef SR_OPQ_THREADS
+#define SR_OPQ_THREADS 256
 #endif
 #ifndef SR_OPQ_MIN_CTAS
-#define SR_OPQ_MIN_CTAS 2
+#define SR_OPQ_MIN_CTAS 3
 #endif
-#define SR_OPQ_THREADS ((SR_OPQ_CONSUMERS + 1) * 32)
-static_assert(SR_OPQ_LAG < SR_OPQ_STAGES, "the gather must trail the bulk copy by less than the ring size");
+#define SR_OPQ_WARPS (SR_OPQ_THREADS / 32)
+#define SR_OPQ_STAGE_FLOATS (32 * 5)  // one warp's 32 finished pixels, AoS {r,g,b,a,depth}
+#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4 + 16)
+static_assert(SR_TILE_W % 32 == 0, "a warp resolves 32 consecutive pixels of one tile row");
 
-// one group of 32 triangles staged for the consumer warps
-struct __align__(16) SrStage {
-    float4 pos[3][32];   // screen-space positions of vertex k of triangle `lane` (gathered with cp.async)
-    uint32_t idx[96];    // the group's 32x3 vertex indices   (cp.async.bulk)
-    uint32_t rect[32];   // the group's 32 packed tile rects  (cp.async.bulk)
+struct SrOpaqueParams {
+    SrPrimSource tris;
+    uint32_t ntris;
+    const unsigned long long *vis;  // null: keys start from the framebuffer depth / the pending clear
+    const uint32_t *tile_off;       // per-tile CSR offsets into `list` (large triangles)
+    const uint32_t *list;
+    SrFbView fb;
+    uint32_t shard_rank, shard_world;
+    SrFsConst fs;
 };
-#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_STAGES * (sizeof(SrStage) + 3 * 8 + 4))
 
 template <int FS>
-__global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrTileParams p) {
-    extern __shared__ __align__(16) unsigned char sr_smem[];
+__global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrOpaqueParams p) {
+    extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
-    SrStage *stage = reinterpret_cast<SrStage *>(keys + SR_TILE_PIXELS);
-    uint64_t *full_a = reinterpret_cast<uint64_t *>(stage + SR_OPQ_STAGES);  // rects + indices landed
-    uint64_t *full_b = full_a + SR_OPQ_STAGES;                               // positions landed
-    uint64_t *empty = full_b + SR_OPQ_STAGES;                                // consumer is done with the stage
-    uint32_t *s_group = reinterpret_cast<uint32_t *>(empty + SR_OPQ_STAGES);
+    float *stage_all = reinterpret_cast<float *>(keys + SR_TILE_PIXELS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage_all + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS);
 
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
-    const uint32_t lbeg = p.tri_off[tile], L = p.tri_off[tile + 1] - lbeg;
-    if (L == 0 && !p.fb.pending_clear) return;  // nothing to draw, contents already in HBM
+    const uint32_t lbeg = p.tile_off[tile], L = p.tile_off[tile + 1] - lbeg;
+    if (L == 0 && !p.fb.pending_clear && p.vis == nullptr) return;  // nothing to draw, contents already in HBM
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = p.fb.width, H = p.fb.height;
 
-    if (tid < SR_OPQ_STAGES) {
-        sr_mbar_init(full_a + tid, 1);    // producer lane 0: arrive.expect_tx
-        sr_mbar_init(full_b + tid, 32);   // every producer lane: cp.async arrive (noinc)
-        sr_mbar_init(empty + tid, 1);     // consumer lane 0
+    if (p.vis != nullptr) {
+        // the tile's keys are one contiguous block of the visibility buffer: one TMA bulk copy
+        if (tid == 0) {
+            sr_mbar_init(bar, 1);
+            sr_mbar_init_fence();
+            sr_mbar_arrive_expect_tx(bar, SR_TILE_PIXELS * 8);
+            sr_bulk_g2s(keys, p.vis + (uint64_t)tile * SR_TILE_PIXELS, SR_TILE_PIXELS * 8, bar);
+        }
+        __syncthreads();
+        sr_mbar_wait(bar, 0);
+    } else {
+        for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
+            const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
+            uint32_t dk = ~SR_DEPTH_FAR_BITS;
+            if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_pixel(p.fb, px, py)[4]);
+            keys[i] = (unsigned long long)dk << 32;
+        }
+        __syncthreads();
     }
-    sr_mbar_init_fence();
-    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
-        const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
-        uint32_t dk = sr_depth_key(__uint_as_float(SR_DEPTH_FAR_BITS));
-        if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_pixel(p.fb, px, py)[4]);
-        keys[i] = (unsigned long long)dk << 32;
-    }
-    __syncthreads();
 
     const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;  // last pixel of the tile in the frame
 
-    if (warp == SR_OPQ_CONSUMERS) {
-        // ---------------- producer warp: keeps the ring of stages full ----------------
-        const uint32_t n0 = p.tris.n0;
-        uint32_t my_g = 0;
-        for (uint32_t step = 0; step < L + SR_OPQ_LAG; ++step) {
-            if (step < L) {  // A: TMA bulk copies of the group's rects and indices
-                if ((step & 31u) == 0) my_g = step + lane < L ? __ldg(p.tri_list + lbeg + step + lane) : 0u;
-                const uint32_t g = __shfl_sync(0xffffffffu, my_g, step & 31u);
-                const uint32_t st = step % SR_OPQ_STAGES, use = step / SR_OPQ_STAGES;
-                if (lane == 0) {
-                    sr_mbar_wait(empty + st, (use & 1u) ^ 1u);
-                    s_group[st] = g;
-                    const bool has_idx = g * SR_GROUP < n0;  // the group holds at least one indexed triangle
-                    sr_mbar_arrive_expect_tx(full_a + st, 128u + (has_idx ? 384u : 0u));
-                    sr_bulk_g2s(stage[st].rect, p.tri_rects + (size_t)g * SR_GROUP, 128u, full_a + st);
-                    if (has_idx) sr_bulk_g2s(stage[st].idx, p.tris.indices + (size_t)g * SR_GROUP * 3, 384u, full_a + st);
-                }
-                __syncwarp();
-            }
-            if (step >= SR_OPQ_LAG) {  // B: gather the positions of the triangles that touch this tile
-                const uint32_t gi = step - SR_OPQ_LAG;
-                const uint32_t st = gi % SR_OPQ_STAGES, use = gi / SR_OPQ_STAGES;
-                sr_mbar_wait(full_a + st, use & 1u);
-                const uint32_t t = s_group[st] * SR_GROUP + lane;
-                const uint32_t rect = stage[st].rect[lane];
-                if (t < p.ntris && rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty)) {
-                    const float4 *src;
-                    uint32_t vi[3];
-                    if (t < n0) {
-                        src = p.tris.vs0.pos;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) vi[k] = stage[st].idx[lane * 3 + k];
-                    } else {
-                        src = p.tris.vs1.pos;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) vi[k] = (t - n0) * 3 + k;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) sr_cp_async16(&stage[st].pos[k][lane], src + vi[k]);
-                }
-                sr_cp_async_arrive_noinc(full_b + st);
-            }
-        }
-    } else {
-        // ---------------- consumer warps: setup + coverage + depth resolve, everything from shared memory ----------------
-        // one covered-pixel candidate: exact inside test, depth, 64-bit max
-        auto raster_test = [&](const SrTri &tr, float z1, float z2, float z3, float nu, float nv, uint32_t slot_index, uint32_t id) {
-            float u, v, w;
-            if (!sr_tri_inside(tr, nu, nv, u, v, w)) return;
-            const float z = (z1 * u + z2 * v) + z3 * w;
-            if (!(z < 0.0f)) return;  // triangle.rs:120
-            const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u);
-            unsigned long long *slot = keys + slot_index;
+    // ---------------- the tile's triangle list: 32 triangles per warp step, setup per lane ----------------
+    if (L > 0) {
+        auto emit = [&](uint32_t px, uint32_t py, unsigned long long key) {
+            unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
             if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
         };
-
-        for (uint32_t gi = warp; gi < L; gi += SR_OPQ_CONSUMERS) {
-            const uint32_t st = gi % SR_OPQ_STAGES, use = gi / SR_OPQ_STAGES;
-            sr_mbar_wait(full_b + st, use & 1u);
-            const uint32_t g = s_group[st];
-            const uint32_t t = g * SR_GROUP + lane;
-            const uint32_t rect = stage[st].rect[lane];
-            const bool hit = t < p.ntris && rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
-            float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
-            if (hit) {
-                A = stage[st].pos[0][lane];
-                B = stage[st].pos[1][lane];
-                C = stage[st].pos[2][lane];
-            }
-            __syncwarp();
-            if (lane == 0) sr_mbar_arrive(empty + st);  // the stage may be refilled
+        for (uint32_t gb = warp * 32; gb < L; gb += SR_OPQ_WARPS * 32) {
+            const bool have = gb + lane < L;
+            uint32_t t = 0;
             SrTri tr;
             float z1 = 0, z2 = 0, z3 = 0;
             uint32_t minx = 1, maxx = 0, miny = 1, maxy = 0;
-            if (hit) {
+            if (have) {
+                t = __ldg(p.list + lbeg + gb + lane);
+                const SrVertexSet *vs;
+                uint32_t vi[3];
+                sr_prim_vertices<3>(p.tris, t, vs, vi);
+                const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
                 tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
                 z1 = A.z; z2 = B.z; z3 = C.z;
                 minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
@@ -455,28 +575,10 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
                 maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
             }
-            const bool nonempty = hit && minx <= maxx && miny <= maxy;
+            const bool nonempty = have && minx <= maxx && miny <= maxy;
             const uint32_t bw = nonempty ? maxx - minx + 1 : 0, bh = nonempty ? maxy - miny + 1 : 0;
             const bool small = nonempty && bw * bh <= SR_SMALL_AREA;
-            if (small) {
-                // one lane walks its own small box.  Pixel centres are generated incrementally: (float)px + 0.5f is
-                // exact and so is adding 1.0f to it, so xf/yf carry exactly the values triangle.rs:104-105 computes;
-                // the row terms b*dy and d*dy are hoisted (same roundings, evaluated once per row).
-                const float xf0 = (float)minx + 0.5f;
-                float xf = xf0, yf = (float)miny + 0.5f;
-                float dy = yf - tr.y3, bdy = tr.b * dy, ddy = tr.d * dy;
-                uint32_t px = minx, slot_index = (miny - y0) * SR_TILE_W + (minx - x0);
-                const uint32_t n = bw * bh;
-                for (uint32_t i = 0; i < n; ++i) {
-                    const float dx = xf - tr.x3;
-                    raster_test(tr, z1, z2, z3, tr.a * dx + bdy, tr.c * dx + ddy, slot_index, t);
-                    ++px; ++slot_index; xf += 1.0f;
-                    if (px > maxx) {
-                        px = minx; xf = xf0; slot_index += SR_TILE_W - bw;
-                        yf += 1.0f; dy = yf - tr.y3; bdy = tr.b * dy; ddy = tr.d * dy;
-                    }
-                }
-            }
+            if (small) sr_raster_box(tr, z1, z2, z3, minx, miny, bw, bh, t, emit);
             uint32_t big = __ballot_sync(0xffffffffu, nonempty && !small);
             while (big) {  // warp-cooperative sweep of one large box at a time
                 const int l = __ffs(big) - 1;
@@ -491,62 +593,97 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 const float sz1 = __shfl_sync(0xffffffffu, z1, l), sz2 = __shfl_sync(0xffffffffu, z2, l), sz3 = __shfl_sync(0xffffffffu, z3, l);
                 const uint32_t sminx = __shfl_sync(0xffffffffu, minx, l), sminy = __shfl_sync(0xffffffffu, miny, l);
                 const uint32_t sbw = __shfl_sync(0xffffffffu, bw, l), sbh = __shfl_sync(0xffffffffu, bh, l);
-                const uint32_t st_id = g * SR_GROUP + l;
+                const uint32_t st = __shfl_sync(0xffffffffu, t, l);
                 for (uint32_t i = lane; i < sbw * sbh; i += 32) {
                     const uint32_t px = sminx + i % sbw, py = sminy + i / sbw;
-                    float nu, nv;
+                    float nu, nv, u, v, w;
                     sr_tri_numerators(s, (float)px + 0.5f, (float)py + 0.5f, nu, nv);
-                    raster_test(s, sz1, sz2, sz3, nu, nv, (py - y0) * SR_TILE_W + (px - x0), st_id);
+                    if (!sr_tri_inside(s, nu, nv, u, v, w)) continue;
+                    const float z = (sz1 * u + sz2 * v) + sz3 * w;
+                    if (!(z < 0.0f)) continue;  // triangle.rs:120
+                    emit(px, py, ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(st + 1u));
                 }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // resolve: shade every pixel once, write colour + depth (+winner) to HBM once
+    // ---------------- resolve: shade every pixel once, write colour + depth (+winner) to HBM once ----------------
+    // A warp finishes 32 consecutive pixels of a tile row at a time.  When the whole frame is being (re)written
+    // (pending clear) the 640 B of AoS pixels are staged in shared memory and leave with one TMA bulk store.
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
-    for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
+    float *stage = stage_all + warp * 2 * SR_OPQ_STAGE_FLOATS;
+    const bool row_aligned = (W % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
+    uint32_t nbulk = 0;
+    for (uint32_t chunk = warp; chunk < SR_TILE_PIXELS / 32; chunk += SR_OPQ_WARPS) {
+        const uint32_t i = chunk * 32 + lane;
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
-        if (px >= W || py >= H) continue;
+        const uint32_t cx0 = x0 + (chunk * 32) % SR_TILE_W;  // first pixel of the chunk (warp-uniform)
+        if (cx0 >= W || py >= H) continue;
+        const bool bulk = p.fb.pending_clear && row_aligned && cx0 + 32 <= W;
+        const bool in_frame = px < W;
         const unsigned long long key = keys[i];
         const uint32_t id = (uint32_t)key;
-        float *dst = sr_fb_pixel(p.fb, px, py);
-        if (id == 0) {
-            if (p.fb.pending_clear) {
-                dst[0] = p.fb.clear[0]; dst[1] = p.fb.clear[1]; dst[2] = p.fb.clear[2]; dst[3] = p.fb.clear[3];
-                dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
-            }
-            continue;
-        }
-        const uint32_t t = id - 1;
-        const SrVertexSet *vs;
-        uint32_t vi[3];
-        sr_prim_vertices<3>(p.tris, t, vs, vi);
-        const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
-        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
-        float u, v, w;
-        sr_tri_bary(tr, px, py, u, v, w);  // same arithmetic as the coverage pass: identical u,v,w
-        float sv[4 + NP * 4 + 1];
-        sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
-        sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
-        sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
-        sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+        float o[5];
+        bool write = false;
+        if (in_frame) {
+            if (id == 0) {
+                if (p.fb.pending_clear) {
+                    o[0] = p.fb.clear[0]; o[1] = p.fb.clear[1]; o[2] = p.fb.clear[2]; o[3] = p.fb.clear[3];
+                    o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+                    write = true;
+                }
+            } else {
+                const uint32_t t = id - 1;
+                const SrVertexSet *vs;
+                uint32_t vi[3];
+                sr_prim_vertices<3>(p.tris, t, vs, vi);
+                const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+                const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+                float u, v, w;
+                sr_tri_bary(tr, px, py, u, v, w);  // same arithmetic as the coverage pass: identical u,v,w
+                float sv[4 + NP * 4 + 1];
+                sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
+                sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
+                sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+                sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
 #pragma unroll
-        for (int pl = 0; pl < NP; ++pl) {
-            const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
-            const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
-            const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
-            sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
-            sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
-            sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
-            sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                for (int pl = 0; pl < NP; ++pl) {
+                    const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
+                    const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
+                    const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
+                    sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+                    sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                    sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+                    sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                }
+                sr_fragment_shader<FS>(p.fs, sv, o);
+                o[4] = sv[2];
+                write = true;
+                if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = sr_prim_canonical(p.tris, t, 0) + 1;
+            }
         }
-        float col[4];
-        sr_fragment_shader<FS>(p.fs, sv, col);
-        dst[0] = col[0]; dst[1] = col[1]; dst[2] = col[2]; dst[3] = col[3];
-        dst[4] = sv[2];
-        if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = sr_prim_canonical(p.tris, t, 0) + 1;
+        if (bulk) {
+            float *sb = stage + (nbulk & 1u) * SR_OPQ_STAGE_FLOATS;
+            if (nbulk >= 2) {  // the bulk store that last read this buffer must have finished reading it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sb[lane * 5 + k] = o[k];
+            sr_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                sr_bulk_s2g(sr_fb_pixel(p.fb, cx0, py), sb, 32 * 20);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nbulk;
+        } else if (write) {
+            float *dst = sr_fb_pixel(p.fb, px, py);
+            dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; dst[4] = o[4];
+        }
     }
+    if (nbulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // =====================================================================================================

@@ -54,6 +54,10 @@ class Context:
     def set_tile_shard(self, rank: int, world: int):
         check(lib.sr_context_set_tile_shard(self.h, rank, world))
 
+    def set_micro(self, area: int = 16, min_triangles: int = 65536, precheck: bool = True):
+        """Tuning of the opaque triangle path (results never depend on it): see sr_context_set_micro."""
+        check(lib.sr_context_set_micro(self.h, area, min_triangles, 1 if precheck else 0))
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         check(lib.sr_context_launch_count(self.h, ctypes.byref(n)))

@@ -260,6 +260,57 @@ def test_second_draw_uses_existing_depth(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="two draws")
 
 
+@pytest.mark.parametrize("area,min_tris,precheck", [(0, 65536, True), (16, 0, True), (64, 0, False), (4096, 0, True), (1, 0, True)])
+def test_opaque_path_split_is_invisible(P, ctx, area, min_tris, precheck):
+    """The opaque path sends small triangles through the visibility buffer (k_micro) and the rest through per-tile
+    lists; where the split lies (and whether a second draw re-initialises the keys from the stored depth) must not
+    change a single bit.  Mixture of sub-pixel, small and large triangles with exact depth ties, drawn twice."""
+    rng = np.random.default_rng(77)
+    w, h = 333, 190
+    tiny = H.random_screen_triangles(rng, 6000, w, h, max_size=2.5, margin=0.02, integer_depth=True)
+    mid = H.random_screen_triangles(rng, 800, w, h, max_size=9.0, integer_depth=True)
+    big = H.random_screen_triangles(rng, 60, w, h, integer_depth=True)
+    verts = np.concatenate([tiny, mid, big])
+    n = len(verts) // 3
+    idx = (rng.permutation(n).astype(np.uint32)[:, None] * 3 + np.arange(3, dtype=np.uint32)[None, :]).reshape(-1)
+    ctx.set_micro(area, min_tris, precheck)
+    try:
+        out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, draws=2)
+    finally:
+        ctx.set_micro()
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what=f"micro area {area}")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_sharding_is_invisible(P, ctx, world):
+    """Sort-first sharding: `world` contexts each rasterise the tiles with index % world == rank into ONE shared
+    framebuffer; the union must be bit-identical to the unsharded frame."""
+    rng = np.random.default_rng(78)
+    w, h = 300, 200
+    verts = np.concatenate([H.random_screen_triangles(rng, 5000, w, h, max_size=3.0, integer_depth=True),
+                            H.random_screen_triangles(rng, 300, w, h, integer_depth=True)])
+    n = len(verts) // 3
+    idx = np.arange(3 * n, dtype=np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    out1, win1, _, ofb = run_both_screen(P, ctx, w, h, verts, idx)
+    # rank 0 owns the framebuffer, the other ranks open it through CUDA IPC-free aliasing (same device): every rank
+    # draws with its own shard setting into the same pixels
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    try:
+        for rank in range(world):
+            ctx.set_tile_shard(rank, world)
+            fb.clear(H.CLEAR)  # lazy clear: every rank produces the clear colour of ITS tiles on chip
+            pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_FLAT)
+    finally:
+        ctx.set_tile_shard(0, 1)
+    out = fb.download()
+    H.assert_bits_equal(out, out1, "sharded frame")
+    pipe.destroy()
+    fb.destroy()
+
+
 def test_one_pixel_frames_draw_nothing(P, ctx):
     """1xN framebuffers have no tiles (fragment.rs:188-216): nothing is ever drawn."""
     verts = np.array([[-5, -5, -1, 1, 1, 0, 0, 1], [9, -5, -1, 1, 1, 0, 0, 1], [0, 9, -1, 1, 1, 0, 0, 1]], np.float32)
