@@ -365,10 +365,37 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
     }
 }
 
+// ---- candidate pixels of a small triangle -----------------------------------------------------------------
+// The reference tests every pixel of the integer bounding box [trunc(min), trunc(max)] (triangle.rs:74-85).
+// For a small, well-conditioned triangle most of those pixels are provably rejected by the reference's own f32
+// inside test, so they need not be visited (DESIGN.md "candidate tightening" carries the proof):
+//   let hx = xmax-xmin < 5, hy = ymax-ymin < 5 and |det| >= 1.  A pixel centre c = px+0.5 with c <= xmin - m
+//   (m = 1/16 - rounding slack) has an exact barycentric weight lambda_k <= -m/(2 hx) (the centre is a convex
+//   combination of the vertices only if it lies in their bounding box).  The f32 values u, v and w = (1-u)-v differ
+//   from the exact weights by at most 2(E + L*Ed)/|det| + 3 eps (1 + 2L) with E <= 4.0001 eps (2 hx hy + (hx+hy)/2),
+//   Ed <= 8.0002 eps hx hy, L = |lambda| <= 55/|det|: below 1.4e-3 < m/(2 hx) = 6.2e-3.  So the most negative of
+//   u, v, w IS negative in f32 and the reference rejects the pixel.  Same on the other three sides.
+// Pixels inside the kept range run the reference's exact test; results are bit-identical either way.
+__device__ __forceinline__ void sr_tighten_candidates(float xmin, float xmax, float ymin, float ymax, float det, uint32_t &minx,
+                                                      uint32_t &miny, uint32_t &maxx, uint32_t &maxy) {
+    if (!(xmax - xmin < 4.99f && ymax - ymin < 4.99f && fabsf(det) >= 1.0f)) return;  // NaN-safe: any NaN skips the tightening
+    // keep px iff xmin - 1/16 < px + 0.5 < xmax + 1/16 (subtraction rounding <= 2^-8 for |x| < 2^16 is inside the slack)
+    const int lx = max((int)minx, __float2int_ru(xmin - 0.5625f)), hx = min((int)maxx, __float2int_rd(xmax - 0.4375f));
+    const int ly = max((int)miny, __float2int_ru(ymin - 0.5625f)), hy = min((int)maxy, __float2int_rd(ymax - 0.4375f));
+    if (lx > hx || ly > hy) {
+        minx = 1; maxx = 0;  // no pixel centre can be inside
+        return;
+    }
+    minx = (uint32_t)lx; maxx = (uint32_t)hx; miny = (uint32_t)ly; maxy = (uint32_t)hy;
+}
+
 // One lane walks a small pixel box [minx, minx+bw) x [miny, miny+bh) of its triangle and calls
 // emit(px, py, key) for every fragment that passes coverage and z<0 (triangle.rs:104-120).
 // Pixel centres are generated incrementally: (float)px + 0.5f is exact and so is adding 1.0f to it, so xf/yf carry
 // exactly the values triangle.rs:104-105 computes; the row terms b*dy and d*dy are hoisted (same roundings).
+// The body is written for SIMT: lanes of a warp sit on different triangles, so the warp executes the union of all
+// paths anyway -- u and v are therefore always computed (exact-division shortcut when valid) instead of branching
+// on the sign of the numerators first.
 template <class Emit>
 __device__ __forceinline__ void sr_raster_box(const SrTri &tr, float z1, float z2, float z3, uint32_t minx, uint32_t miny,
                                               uint32_t bw, uint32_t bh, uint32_t id, Emit emit) {
@@ -379,11 +406,21 @@ __device__ __forceinline__ void sr_raster_box(const SrTri &tr, float z1, float z
     const uint32_t n = bw * bh, maxx = minx + bw - 1;
     for (uint32_t i = 0; i < n; ++i) {
         const float dx = xf - tr.x3;
-        float u, v, w;
-        if (sr_tri_inside(tr, tr.a * dx + bdy, tr.c * dx + ddy, u, v, w)) {
+        const float nu = tr.a * dx + bdy, nv = tr.c * dx + ddy;
+        float u, v;
+        const float au = fabsf(nu), av = fabsf(nv);
+        if (tr.fast && au >= 0x1p-60f && au < 0x1p60f && av >= 0x1p-60f && av < 0x1p60f) {
+            u = sr_div_exact(nu, tr.det, tr.rdet);
+            v = sr_div_exact(nv, tr.det, tr.rdet);
+        } else {
+            u = nu / tr.det;
+            v = nv / tr.det;
+        }
+        const float w = 1.0f - u - v;
+        if (!(u < 0.0f || v < 0.0f || w < 0.0f)) {
             const float z = (z1 * u + z2 * v) + z3 * w;
-            if (z < 0.0f)  // triangle.rs:120
-                emit(px, py, ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(id + 1u));
+            if (z < 0.0f)  // triangle.rs:120; for negative z the order-preserving key is ~bits
+                emit(px, py, ((unsigned long long)(~__float_as_uint(z)) << 32) | (unsigned long long)(id + 1u));
         }
         ++px; xf += 1.0f;
         if (px > maxx) {
@@ -422,10 +459,10 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
         }
         if (ok) {
             // triangle.rs:74-78 with tile = the whole frame
-            const uint32_t minx = sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, p.width - 1);
-            const uint32_t miny = sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, p.height - 1);
-            const uint32_t maxx = sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, p.width - 1);
-            const uint32_t maxy = sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, p.height - 1);
+            const float xmin = fminf(fminf(A.x, B.x), C.x), xmax = fmaxf(fmaxf(A.x, B.x), C.x);
+            const float ymin = fminf(fminf(A.y, B.y), C.y), ymax = fmaxf(fmaxf(A.y, B.y), C.y);
+            const uint32_t minx = sr_clamp_as_int(xmin, 0, p.width - 1), maxx = sr_clamp_as_int(xmax, 0, p.width - 1);
+            const uint32_t miny = sr_clamp_as_int(ymin, 0, p.height - 1), maxy = sr_clamp_as_int(ymax, 0, p.height - 1);
             if (minx <= maxx && miny <= maxy) {
                 const uint32_t bw = maxx - minx + 1, bh = maxy - miny + 1;
                 const uint32_t tx0 = minx / SR_TILE_W, ty0 = miny / SR_TILE_H, tx1 = maxx / SR_TILE_W, ty1 = maxy / SR_TILE_H;
@@ -435,7 +472,10 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
                     if (!(sharded && one_tile && (ty0 * p.ntx + tx0) % p.shard_world != p.shard_rank)) {
                         const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
                         const bool per_pixel_owner = sharded && !one_tile;
-                        sr_raster_box(tr, A.z, B.z, C.z, minx, miny, bw, bh, t, [&](uint32_t px, uint32_t py, unsigned long long key) {
+                        uint32_t cx0 = minx, cy0 = miny, cx1 = maxx, cy1 = maxy;
+                        sr_tighten_candidates(xmin, xmax, ymin, ymax, tr.det, cx0, cy0, cx1, cy1);
+                        const uint32_t cw = cx0 <= cx1 ? cx1 - cx0 + 1 : 0, ch = cy1 - cy0 + 1;
+                        sr_raster_box(tr, A.z, B.z, C.z, cx0, cy0, cw, ch, t, [&](uint32_t px, uint32_t py, unsigned long long key) {
                             if (per_pixel_owner && ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world != p.shard_rank) return;
                             unsigned long long *slot = p.vis + sr_vis_index(px, py, p.ntx);
                             if (PRECHECK && !(key > sr_ld_relaxed_u64(slot))) return;
