@@ -163,6 +163,9 @@ def run_ours(args):
     w, h, mesh, u, vp = build_scene(args.config)
     ntris, nverts = mesh.ntris, len(mesh.vertices)
     ctx = P.Context(local_rank)
+    if os.environ.get("SR_MICRO"):  # tuning experiments only: "area,min_triangles,precheck"
+        a, m, pc = (int(x) for x in os.environ["SR_MICRO"].split(","))
+        ctx.set_micro(a, m, bool(pc))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     # framebuffer: rank 0 owns it; other ranks map it through CUDA IPC and store their tiles into it over NVLink

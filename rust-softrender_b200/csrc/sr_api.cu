@@ -60,7 +60,7 @@ struct sr_context {
     bool ev_valid[8] = {};
     uint32_t micro_area = SR_MICRO_AREA_DEFAULT;  // bbox pixels up to which k_micro rasterises a triangle itself (0: off)
     uint32_t micro_min_tris = 65536;              // draws onto existing contents use the visibility buffer from this size on
-    uint32_t micro_precheck = 1;
+    uint32_t micro_precheck = 0;  // read the key before the atomic: measured slower (load latency inside the per-lane loop)
     uint32_t *pinned = nullptr;                   // pinned host words for device->host counters
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);

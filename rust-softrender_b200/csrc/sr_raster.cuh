@@ -9,6 +9,8 @@
 // on the GPU tile size.
 #pragma once
 
+#include <type_traits>
+
 #include "sr_shaders.cuh"
 
 #ifndef SR_RASTER_THREADS
@@ -321,18 +323,16 @@ __device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, u
 // Two producers feed the keys:
 //  * k_micro: one thread per triangle, in submission order.  A triangle whose frame-clamped bounding box
 //    holds at most `micro_area` pixels is rasterised on the spot into the frame's visibility buffer (keys in
-//    HBM/L2, tiled so each GPU tile is one contiguous 16 KB block) -- no bin lists, no second visit.
+//    HBM/L2, row-major with the pitch padded to whole tiles) -- no bin lists, no second visit.
 //    Larger triangles are appended to a compact list and counted per tile.
-//  * k_tile_opaque: one CTA per tile.  Pulls the tile's keys into shared memory with one TMA bulk copy,
-//    sweeps the tile's (large) triangle list warp-cooperatively against them, then resolves.
+//  * k_tile_opaque: one CTA per tile.  Pulls the tile's keys into shared memory with TMA bulk copies (one 512 B
+//    row each), sweeps the tile's (large) triangle list warp-cooperatively against them, then resolves.
 // =====================================================================================================
 #define SR_VIS_FAR_KEY ((unsigned long long)(~SR_DEPTH_FAR_BITS) << 32)  // sr_depth_key(f32::MIN) << 32, primitive 0
 static_assert((SR_DEPTH_FAR_BITS & 0x80000000u) != 0, "far depth is negative");
 
-__device__ __forceinline__ uint64_t sr_vis_index(uint32_t px, uint32_t py, uint32_t ntx) {
-    const uint32_t tile = (py / SR_TILE_H) * ntx + (px / SR_TILE_W);
-    return (uint64_t)tile * SR_TILE_PIXELS + (py % SR_TILE_H) * SR_TILE_W + (px % SR_TILE_W);
-}
+// visibility buffer: (nty * SR_TILE_H) rows of pitch = ntx * SR_TILE_W keys, so every tile row is a full 512 B run
+__device__ __forceinline__ uint32_t sr_vis_index(uint32_t px, uint32_t py, uint32_t ntx) { return py * (ntx * SR_TILE_W) + px; }
 
 struct SrMicroParams {
     SrPrimSource src;
@@ -340,7 +340,7 @@ struct SrMicroParams {
     uint32_t width, height, ntx, nty;
     uint32_t shard_rank, shard_world;
     uint32_t micro_area;          // bbox pixels up to which a triangle is rasterised by k_micro (0: none)
-    unsigned long long *vis;      // tiled visibility buffer (ntiles * SR_TILE_PIXELS keys)
+    unsigned long long *vis;      // visibility buffer (ntiles * SR_TILE_PIXELS keys, see sr_vis_index)
     uint32_t *large_count;        // number of entries in large_ids
     uint32_t *large_ids;          // triangles left to the tile kernel ...
     uint32_t *large_rects;        // ... and their packed tile rectangles
@@ -350,18 +350,16 @@ struct SrMicroParams {
 // keys of the tiles this rank owns := far (pending clear) or the depth already in the framebuffer
 __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const SrFbView fb, uint32_t shard_rank, uint32_t shard_world) {
     const uint32_t tile = shard_rank + blockIdx.x * shard_world;
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(vis + (uint64_t)tile * SR_TILE_PIXELS);
-    if (fb.pending_clear) {
-        const ulonglong2 k = make_ulonglong2(SR_VIS_FAR_KEY, SR_VIS_FAR_KEY);
-        for (uint32_t i = threadIdx.x; i < SR_TILE_PIXELS / 2; i += 256) dst[i] = k;
-        return;
-    }
     const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
-    for (uint32_t i = threadIdx.x; i < SR_TILE_PIXELS; i += 256) {
+    for (uint32_t i = threadIdx.x * 2; i < SR_TILE_PIXELS; i += 512) {  // two keys (16 B) per thread and step
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
-        uint32_t dk = ~SR_DEPTH_FAR_BITS;
-        if (px < fb.width && py < fb.height) dk = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px) * 5 + 4]);
-        vis[(uint64_t)tile * SR_TILE_PIXELS + i] = (unsigned long long)dk << 32;
+        uint32_t dk0 = ~SR_DEPTH_FAR_BITS, dk1 = ~SR_DEPTH_FAR_BITS;
+        if (!fb.pending_clear && py < fb.height) {
+            if (px < fb.width) dk0 = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px) * 5 + 4]);
+            if (px + 1 < fb.width) dk1 = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px + 1) * 5 + 4]);
+        }
+        *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(px, py, fb.ntx)) =
+            make_ulonglong2((unsigned long long)dk0 << 32, (unsigned long long)dk1 << 32);
     }
 }
 
@@ -376,18 +374,12 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
 //   Ed <= 8.0002 eps hx hy, L = |lambda| <= 55/|det|: below 1.4e-3 < m/(2 hx) = 6.2e-3.  So the most negative of
 //   u, v, w IS negative in f32 and the reference rejects the pixel.  Same on the other three sides.
 // Pixels inside the kept range run the reference's exact test; results are bit-identical either way.
-__device__ __forceinline__ void sr_tighten_candidates(float xmin, float xmax, float ymin, float ymax, float det, uint32_t &minx,
-                                                      uint32_t &miny, uint32_t &maxx, uint32_t &maxy) {
-    if (!(xmax - xmin < 4.99f && ymax - ymin < 4.99f && fabsf(det) >= 1.0f)) return;  // NaN-safe: any NaN skips the tightening
-    // keep px iff xmin - 1/16 < px + 0.5 < xmax + 1/16 (subtraction rounding <= 2^-8 for |x| < 2^16 is inside the slack)
-    const int lx = max((int)minx, __float2int_ru(xmin - 0.5625f)), hx = min((int)maxx, __float2int_rd(xmax - 0.4375f));
-    const int ly = max((int)miny, __float2int_ru(ymin - 0.5625f)), hy = min((int)maxy, __float2int_rd(ymax - 0.4375f));
-    if (lx > hx || ly > hy) {
-        minx = 1; maxx = 0;  // no pixel centre can be inside
-        return;
-    }
-    minx = (uint32_t)lx; maxx = (uint32_t)hx; miny = (uint32_t)ly; maxy = (uint32_t)hy;
+__device__ __forceinline__ bool sr_tightening_applies(float xmin, float xmax, float ymin, float ymax, float det) {
+    return xmax - xmin < 4.99f && ymax - ymin < 4.99f && fabsf(det) >= 1.0f;  // NaN-safe: any NaN coordinate gives a NaN det -> false
 }
+// keep px iff xmin - 1/16 < px + 0.5 < xmax + 1/16 (the rounding of the subtraction, <= 2^-8 for |x| < 2^16, is inside the slack)
+__device__ __forceinline__ int sr_tight_lo(float vmin) { return __float2int_ru(vmin - 0.5625f); }
+__device__ __forceinline__ int sr_tight_hi(float vmax) { return __float2int_rd(vmax - 0.4375f); }
 
 // One lane walks a small pixel box [minx, minx+bw) x [miny, miny+bh) of its triangle and calls
 // emit(px, py, key) for every fragment that passes coverage and z<0 (triangle.rs:104-120).
@@ -396,7 +388,9 @@ __device__ __forceinline__ void sr_tighten_candidates(float xmin, float xmax, fl
 // The body is written for SIMT: lanes of a warp sit on different triangles, so the warp executes the union of all
 // paths anyway -- u and v are therefore always computed (exact-division shortcut when valid) instead of branching
 // on the sign of the numerators first.
-template <class Emit>
+// BOUNDED: the caller guarantees |det| in [1, 2^40] and numerators below 2^60 (k_micro's tightened path: extents
+// below 5 pixels), so only the lower validity bound of the exact-division shortcut has to be checked per pixel.
+template <bool BOUNDED, class Emit>
 __device__ __forceinline__ void sr_raster_box(const SrTri &tr, float z1, float z2, float z3, uint32_t minx, uint32_t miny,
                                               uint32_t bw, uint32_t bh, uint32_t id, Emit emit) {
     const float xf0 = (float)minx + 0.5f;
@@ -404,12 +398,15 @@ __device__ __forceinline__ void sr_raster_box(const SrTri &tr, float z1, float z
     float dy = yf - tr.y3, bdy = tr.b * dy, ddy = tr.d * dy;
     uint32_t px = minx, py = miny;
     const uint32_t n = bw * bh, maxx = minx + bw - 1;
+    // validity range of sr_div_exact folded into two constants (an invalid det makes the range empty)
+    const float lo = (BOUNDED || tr.fast) ? 0x1p-60f : __int_as_float(0x7f800000), hi = 0x1p60f;
+#pragma unroll 1
     for (uint32_t i = 0; i < n; ++i) {
         const float dx = xf - tr.x3;
         const float nu = tr.a * dx + bdy, nv = tr.c * dx + ddy;
         float u, v;
         const float au = fabsf(nu), av = fabsf(nv);
-        if (tr.fast && au >= 0x1p-60f && au < 0x1p60f && av >= 0x1p-60f && av < 0x1p60f) {
+        if (BOUNDED ? (au >= lo && av >= lo) : (au >= lo && au < hi && av >= lo && av < hi)) {
             u = sr_div_exact(nu, tr.det, tr.rdet);
             v = sr_div_exact(nv, tr.det, tr.rdet);
         } else {
@@ -451,45 +448,58 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
         uint32_t vi[3];
         sr_prim_vertices<3>(p.src, t, vs, vi);
         const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
-        // the reference panics on NaN coordinates (cast(..).unwrap()); defined here as "skipped"
-        bool ok = !(isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y));
-        if (ok && p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
+        bool culled = false;
+        if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61 (a NaN area is "not negative", like is_sign_negative of the reference's NaN)
             const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
-            ok = (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) != p.cull;
+            culled = (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) == p.cull;
         }
-        if (ok) {
-            // triangle.rs:74-78 with tile = the whole frame
+        if (!culled) {
+            const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
             const float xmin = fminf(fminf(A.x, B.x), C.x), xmax = fmaxf(fmaxf(A.x, B.x), C.x);
             const float ymin = fminf(fminf(A.y, B.y), C.y), ymax = fmaxf(fmaxf(A.y, B.y), C.y);
-            const uint32_t minx = sr_clamp_as_int(xmin, 0, p.width - 1), maxx = sr_clamp_as_int(xmax, 0, p.width - 1);
-            const uint32_t miny = sr_clamp_as_int(ymin, 0, p.height - 1), maxy = sr_clamp_as_int(ymax, 0, p.height - 1);
-            if (minx <= maxx && miny <= maxy) {
-                const uint32_t bw = maxx - minx + 1, bh = maxy - miny + 1;
-                const uint32_t tx0 = minx / SR_TILE_W, ty0 = miny / SR_TILE_H, tx1 = maxx / SR_TILE_W, ty1 = maxy / SR_TILE_H;
-                if (bw * bh <= p.micro_area) {
-                    const bool one_tile = tx0 == tx1 && ty0 == ty1;
-                    const bool sharded = p.shard_world > 1;
-                    if (!(sharded && one_tile && (ty0 * p.ntx + tx0) % p.shard_world != p.shard_rank)) {
-                        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
-                        const bool per_pixel_owner = sharded && !one_tile;
-                        uint32_t cx0 = minx, cy0 = miny, cx1 = maxx, cy1 = maxy;
-                        sr_tighten_candidates(xmin, xmax, ymin, ymax, tr.det, cx0, cy0, cx1, cy1);
-                        const uint32_t cw = cx0 <= cx1 ? cx1 - cx0 + 1 : 0, ch = cy1 - cy0 + 1;
-                        sr_raster_box(tr, A.z, B.z, C.z, cx0, cy0, cw, ch, t, [&](uint32_t px, uint32_t py, unsigned long long key) {
-                            if (per_pixel_owner && ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world != p.shard_rank) return;
-                            unsigned long long *slot = p.vis + sr_vis_index(px, py, p.ntx);
-                            if (PRECHECK && !(key > sr_ld_relaxed_u64(slot))) return;
-                            sr_red_max_u64(slot, key);
-                        });
-                    }
-                } else {
-                    rect = sr_pack_rect(tx0, ty0, tx1, ty1);
-                    if (p.shard_world == 1) {
-                        large = true;
+            const bool sharded = p.shard_world > 1;
+            // walks the candidate box, reducing every fragment into the visibility buffer (tiles of other ranks are skipped
+            // when sharded); `bounded` marks the tightened path
+            auto raster = [&](auto bounded, int lx, int ly, int hx, int hy) {
+                if (lx > hx || ly > hy) return;
+                const uint32_t tx0 = (uint32_t)lx / SR_TILE_W, ty0 = (uint32_t)ly / SR_TILE_H;
+                const bool one_tile = tx0 == (uint32_t)hx / SR_TILE_W && ty0 == (uint32_t)hy / SR_TILE_H;
+                if (sharded && one_tile && (ty0 * p.ntx + tx0) % p.shard_world != p.shard_rank) return;
+                const bool per_pixel_owner = sharded && !one_tile;
+                sr_raster_box<decltype(bounded)::value>(
+                    tr, A.z, B.z, C.z, (uint32_t)lx, (uint32_t)ly, (uint32_t)(hx - lx + 1), (uint32_t)(hy - ly + 1), t,
+                    [&](uint32_t px, uint32_t py, unsigned long long key) {
+                        if (per_pixel_owner && ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world != p.shard_rank) return;
+                        unsigned long long *slot = p.vis + sr_vis_index(px, py, p.ntx);
+                        if (PRECHECK && !(key > sr_ld_relaxed_u64(slot))) return;
+                        sr_red_max_u64(slot, key);
+                    });
+            };
+            if (p.micro_area != 0 && sr_tightening_applies(xmin, xmax, ymin, ymax, tr.det)) {
+                // small and well conditioned (this also implies six finite coordinates): the candidate pixels are the
+                // reference's clamped bounding box intersected with the tightened range (rule above;
+                // for x >= 0 trunc(xmin) <= ceil(xmin - 0.5625) and floor(xmax - 0.4375) <= trunc(xmax), so the
+                // intersection is just the tightened range clamped to the frame)
+                raster(std::true_type(), max(0, sr_tight_lo(xmin)), max(0, sr_tight_lo(ymin)), min((int)p.width - 1, sr_tight_hi(xmax)),
+                       min((int)p.height - 1, sr_tight_hi(ymax)));
+            } else if (!(isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y))) {
+                // (the reference panics on NaN coordinates, cast(..).unwrap(); defined here as "skipped")
+                // triangle.rs:74-78 with tile = the whole frame
+                const uint32_t minx = sr_clamp_as_int(xmin, 0, p.width - 1), maxx = sr_clamp_as_int(xmax, 0, p.width - 1);
+                const uint32_t miny = sr_clamp_as_int(ymin, 0, p.height - 1), maxy = sr_clamp_as_int(ymax, 0, p.height - 1);
+                if (minx <= maxx && miny <= maxy) {
+                    if ((maxx - minx + 1) * (maxy - miny + 1) <= p.micro_area) {
+                        raster(std::false_type(), (int)minx, (int)miny, (int)maxx, (int)maxy);
                     } else {
-                        for (uint32_t ty = ty0; ty <= ty1 && !large; ++ty)
-                            for (uint32_t tx = tx0; tx <= tx1; ++tx)
-                                if ((ty * p.ntx + tx) % p.shard_world == p.shard_rank) { large = true; break; }
+                        const uint32_t tx0 = minx / SR_TILE_W, ty0 = miny / SR_TILE_H, tx1 = maxx / SR_TILE_W, ty1 = maxy / SR_TILE_H;
+                        rect = sr_pack_rect(tx0, ty0, tx1, ty1);
+                        if (!sharded) {
+                            large = true;
+                        } else {
+                            for (uint32_t ty = ty0; ty <= ty1 && !large; ++ty)
+                                for (uint32_t tx = tx0; tx <= tx1; ++tx)
+                                    if ((ty * p.ntx + tx) % p.shard_world == p.shard_rank) { large = true; break; }
+                        }
                     }
                 }
             }
@@ -569,14 +579,14 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     const uint32_t W = p.fb.width, H = p.fb.height;
 
     if (p.vis != nullptr) {
-        // the tile's keys are one contiguous block of the visibility buffer: one TMA bulk copy
+        // the tile's keys: SR_TILE_H rows of 512 B in the visibility buffer, one TMA bulk copy per row
         if (tid == 0) {
             sr_mbar_init(bar, 1);
             sr_mbar_init_fence();
             sr_mbar_arrive_expect_tx(bar, SR_TILE_PIXELS * 8);
-            sr_bulk_g2s(keys, p.vis + (uint64_t)tile * SR_TILE_PIXELS, SR_TILE_PIXELS * 8, bar);
         }
         __syncthreads();
+        if (tid < SR_TILE_H) sr_bulk_g2s(keys + tid * SR_TILE_W, p.vis + sr_vis_index(x0, y0 + tid, p.fb.ntx), SR_TILE_W * 8, bar);
         sr_mbar_wait(bar, 0);
     } else {
         for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
             const bool nonempty = have && minx <= maxx && miny <= maxy;
             const uint32_t bw = nonempty ? maxx - minx + 1 : 0, bh = nonempty ? maxy - miny + 1 : 0;
             const bool small = nonempty && bw * bh <= SR_SMALL_AREA;
-            if (small) sr_raster_box(tr, z1, z2, z3, minx, miny, bw, bh, t, emit);
+            if (small) sr_raster_box<false>(tr, z1, z2, z3, minx, miny, bw, bh, t, emit);
             uint32_t big = __ballot_sync(0xffffffffu, nonempty && !small);
             while (big) {  // warp-cooperative sweep of one large box at a time
                 const int l = __ffs(big) - 1;
@@ -959,7 +969,7 @@ __device__ __noinline__ void sr_ord_point(const SrOrdCtx &c, uint32_t t) {
 
 template <int FS>
 __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid_constant__ SrTileParams p) {
-    extern __shared__ __align__(16) unsigned char sr_smem[];
+    extern __shared__ __align__(128) unsigned char sr_smem[];
     float4 *s_color = reinterpret_cast<float4 *>(sr_smem);
     float *s_depth = reinterpret_cast<float *>(s_color + SR_TILE_PIXELS);
     uint32_t *s_winner = reinterpret_cast<uint32_t *>(s_depth + SR_TILE_PIXELS);

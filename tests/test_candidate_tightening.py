@@ -1,5 +1,5 @@
 """CPU check of the rasteriser's "candidate tightening" rule (rust-softrender_b200/csrc/sr_raster.cuh,
-sr_tighten_candidates; proof in DESIGN.md).
+sr_tightening_applies / sr_tight_lo / sr_tight_hi; proof in DESIGN.md).
 
 The reference tests every pixel of a triangle's integer bounding box with its f32 inside test
 (src/pipeline/stages/rasterization/triangle.rs:74-113).  The CUDA path skips pixels whose centre lies more than 1/16
@@ -27,7 +27,7 @@ def reference_inside(x, y, px, py):
 
 
 def tightened_range(lo_f, hi_f, lo_i, hi_i):
-    """sr_tighten_candidates for one axis: keep p iff ceil(lo - 0.5625) <= p <= floor(hi - 0.4375)."""
+    """sr_tight_lo / sr_tight_hi for one axis: keep p iff ceil(lo - 0.5625) <= p <= floor(hi - 0.4375)."""
     a = np.maximum(lo_i, np.ceil(lo_f - F(0.5625)).astype(np.int64))
     b = np.minimum(hi_i, np.floor(hi_f - F(0.4375)).astype(np.int64))
     return a, b
