@@ -846,9 +846,9 @@ static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
     record(c, 0);
     if (d->mesh_nverts) {
         float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
-        const uint32_t grid4 = ceil_div(ceil_div(d->mesh_nverts, 4), 128);
-        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid4, 128, 0, vc, mv, pos, attr, d->indexed.stride);
-        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid4, 128, 0, vc, mv, pos, attr, d->indexed.stride);
+        const uint32_t grid1 = ceil_div(d->mesh_nverts, 256);
+        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.stride);
+        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.stride);
         else SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, pos, attr, d->indexed.stride);
     }
     record(c, 1);

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
 #define SR_OPQ_THREADS 256
 #endif
 #ifndef SR_OPQ_MIN_CTAS
-#define SR_OPQ_MIN_CTAS 3
+#define SR_OPQ_MIN_CTAS 4
 #endif
 #define SR_OPQ_WARPS (SR_OPQ_THREADS / 32)
 #define SR_OPQ_STAGE_FLOATS (32 * 5)  // one warp's 32 finished pixels, AoS {r,g,b,a,depth}
@@ -665,30 +665,49 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     float *stage = stage_all + warp * 2 * SR_OPQ_STAGE_FLOATS;
     const bool row_aligned = (W % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
     uint32_t nbulk = 0;
+    // The winner's vertex indices are fetched one chunk ahead, so the two dependent gathers (indices, then vertices) of
+    // consecutive chunks overlap instead of adding up.
+    const uint32_t n0 = p.tris.n0;
+    auto fetch = [&](uint32_t chunk, uint32_t &id, uint32_t (&vi)[3]) {
+        id = 0;
+        if (chunk >= SR_TILE_PIXELS / 32) return;
+        const uint32_t i = chunk * 32 + lane;
+        if (x0 + i % SR_TILE_W >= W || y0 + i / SR_TILE_W >= H) return;
+        id = (uint32_t)keys[i];
+        if (id == 0) return;
+        const uint32_t t = id - 1;
+        if (t < n0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vi[k] = __ldg(p.tris.indices + (uint64_t)t * 3 + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vi[k] = (t - n0) * 3 + k;
+        }
+    };
+    uint32_t id = 0, vi[3] = {0, 0, 0};
+    fetch(warp, id, vi);
     for (uint32_t chunk = warp; chunk < SR_TILE_PIXELS / 32; chunk += SR_OPQ_WARPS) {
+        const uint32_t id_cur = id, vi0 = vi[0], vi1 = vi[1], vi2 = vi[2];
+        fetch(chunk + SR_OPQ_WARPS, id, vi);
         const uint32_t i = chunk * 32 + lane;
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         const uint32_t cx0 = x0 + (chunk * 32) % SR_TILE_W;  // first pixel of the chunk (warp-uniform)
         if (cx0 >= W || py >= H) continue;
         const bool bulk = p.fb.pending_clear && row_aligned && cx0 + 32 <= W;
         const bool in_frame = px < W;
-        const unsigned long long key = keys[i];
-        const uint32_t id = (uint32_t)key;
         float o[5];
         bool write = false;
         if (in_frame) {
-            if (id == 0) {
+            if (id_cur == 0) {
                 if (p.fb.pending_clear) {
                     o[0] = p.fb.clear[0]; o[1] = p.fb.clear[1]; o[2] = p.fb.clear[2]; o[3] = p.fb.clear[3];
                     o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
                     write = true;
                 }
             } else {
-                const uint32_t t = id - 1;
-                const SrVertexSet *vs;
-                uint32_t vi[3];
-                sr_prim_vertices<3>(p.tris, t, vs, vi);
-                const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+                const uint32_t t = id_cur - 1;
+                const SrVertexSet *vs = t < n0 ? &p.tris.vs0 : &p.tris.vs1;
+                const float4 A = __ldg(vs->pos + vi0), B = __ldg(vs->pos + vi1), C = __ldg(vs->pos + vi2);
                 const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
                 float u, v, w;
                 sr_tri_bary(tr, px, py, u, v, w);  // same arithmetic as the coverage pass: identical u,v,w
@@ -699,9 +718,9 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl) {
-                    const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
-                    const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
-                    const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
+                    const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi0);
+                    const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi1);
+                    const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi2);
                     sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
                     sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
                     sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);

@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_apply(const uint32_t *
 
 // =====================================================================================================
 // a2: vertex stage (VertexShader::run / run_to_fragment, src/pipeline/stages/vertex.rs:87-160)
-// One thread shades four consecutive vertices: each SoA input plane is read with one float4 load,
-// outputs are float4 stores (position plane + ceil(nk/4) attribute planes).
+// One thread shades one vertex (see k_vertex).
 // =====================================================================================================
 struct SrMeshView {
     const float *planes;  // plane c starts at planes + c*pstride; pstride is a multiple of 4
@@ -94,30 +93,25 @@ struct SrMeshView {
 };
 
 template <int VS>
-__global__ void __launch_bounds__(128) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
+__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
                                                 float4 *attr, const uint64_t ostride) {
     constexpr int VIN = SrVsInfo<VS>::VIN, NK = SrVsInfo<VS>::NK, NP = (NK + 3) / 4;
-    const uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (base >= m.nverts) return;
-    float in[4][VIN];
+    // One vertex per thread: a warp reads 128 contiguous bytes of every SoA input plane and writes 512 contiguous
+    // bytes (32 float4) of every output plane, so every sector that moves is fully used in both directions.
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= m.nverts) return;
+    float in[VIN];
 #pragma unroll
-    for (int ch = 0; ch < VIN; ++ch) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(m.planes + (uint64_t)ch * m.pstride + base));
-        in[0][ch] = v.x; in[1][ch] = v.y; in[2][ch] = v.z; in[3][ch] = v.w;
-    }
+    for (int ch = 0; ch < VIN; ++ch) in[ch] = __ldg(m.planes + (uint64_t)ch * m.pstride + v);
+    float out[4 + NP * 4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (base + j >= m.nverts) break;
-        float out[4 + NP * 4];
+    for (int i = 4 + NK; i < 4 + NP * 4; ++i) out[i] = 0.0f;
+    sr_vertex_shader<VS>(c, in, out);
+    if (c.normalize) sr_normalize_vertex(c.vpm, out);
+    pos[v] = make_float4(out[0], out[1], out[2], out[3]);
 #pragma unroll
-        for (int i = 4 + NK; i < 4 + NP * 4; ++i) out[i] = 0.0f;
-        sr_vertex_shader<VS>(c, in[j], out);
-        if (c.normalize) sr_normalize_vertex(c.vpm, out);
-        pos[base + j] = make_float4(out[0], out[1], out[2], out[3]);
-#pragma unroll
-        for (int p = 0; p < NP; ++p)
-            attr[(uint64_t)p * ostride + base + j] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
-    }
+    for (int p = 0; p < NP; ++p)
+        attr[(uint64_t)p * ostride + v] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
 }
 
 // SR_VS_PASSTHROUGH (test shader): Vin = {x,y,z,w,k...}, any nk <= SR_MAX_NK; one vertex per thread.
