@@ -143,6 +143,15 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
+def kernel_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -160,6 +169,13 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     w, h, mesh, u, vp = build_scene(args.config)
     ntris, nverts = mesh.ntris, len(mesh.vertices)
     ctx = P.Context(local_rank)
@@ -168,67 +184,87 @@ def run_ours(args):
         ctx.set_micro(a, m, bool(pc))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
-    # framebuffer: rank 0 owns it; other ranks map it through CUDA IPC and store their tiles into it over NVLink
-    if rank == 0:
-        fb = P.RenderBuffer.with_dimensions(ctx, w, h)
-        fb.clear(CLEAR)
-        handle = [fb.ipc_export()] if world > 1 else [None]
-    else:
-        handle = [None]
-    if world > 1:
-        dist.broadcast_object_list(handle, src=0)
-        ctx.set_tile_shard(rank, world)
-        if rank != 0:
-            fb = P.RenderBuffer.ipc_open(ctx, handle[0], w, h)
+    # every rank owns a framebuffer and the whole mesh (geometry replicated)
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)
     pipe = P.Pipeline.from_framebuffer(fb, u)
     gmesh = P.Mesh(ctx, mesh)
 
-    def frame():
-        fb.clear(CLEAR)
-        pipe.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    def frame(pipeline=pipe, target=fb):
+        target.clear(CLEAR)
+        pipeline.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
 
-    for _ in range(args.warmup):
-        frame()
-    ctx.synchronize()
-    barrier()
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        ctx.synchronize()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / steps
+
+    # ---- headline: whole frames per GPU (N=1: the frame; N>1: frame batching, one independent frame stream per rank) ----
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        frame()
-    ev1.record(stream)
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
-    stage = ctx.stage_times()  # CUDA events of the last timed step, on the launching stream
+    ms_per_step = timed(frame, args.steps, args.warmup)
+    launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # per-stage device times (CUDA events recorded by the library on its stream), averaged over a few more frames
+    stage_acc, nstage = {}, 5
+    for _ in range(nstage):
+        frame()
+        for k, v in ctx.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / nstage
+
+    # ---- N>1: sort-first tile sharding of ONE frame, peer-store composite into rank 0's framebuffer over NVLink ----
+    sharded = None
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+        handle = [fb.ipc_export() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        ctx.set_tile_shard(rank, world)
+        sfb = fb if rank == 0 else P.RenderBuffer.ipc_open(ctx, handle[0], w, h)
+        spipe = pipe if rank == 0 else P.Pipeline.from_framebuffer(sfb, u)
+
+        def sharded_frame():
+            frame(spipe, sfb)
+            ctx.synchronize()
+            barrier()  # the frame is complete when every rank's tiles have landed in rank 0's HBM
+
+        for _ in range(3):
+            sharded_frame()
+        t0 = time.perf_counter()
+        n_sh = max(3, min(args.steps, 10))
+        for _ in range(n_sh):
+            sharded_frame()
+        sh_ms = max_over_ranks((time.perf_counter() - t0) / n_sh * 1e3)
+        sharded = {"ms_per_frame": sh_ms, "Mtris_per_s": ntris / (sh_ms * 1e-3) / 1e6, "frames_per_s": 1e3 / sh_ms,
+                   "timing": "host clock around draw + stream sync + barrier, max over ranks",
+                   "composite": "tile rasteriser stores finished tiles into rank 0's framebuffer (CUDA IPC peer pointer, NVLink)"}
+        ctx.set_tile_shard(0, 1)
+        if rank != 0:
+            spipe.destroy()
+        barrier()
 
     # ---- end to end through the C ABI with HOST buffers: mesh upload + draw + framebuffer read-back each step ----
-    e2e = None
     host_v = torch.from_numpy(mesh.vertices).pin_memory().numpy()
     host_i = torch.from_numpy(mesh.indices.astype(np.uint32)).pin_memory().numpy()
-    host_fb = torch.empty((w * h, 5), dtype=torch.float32).pin_memory().numpy() if rank == 0 else None
+    host_fb = torch.empty((w * h, 5), dtype=torch.float32).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_frame():
         m = P.Mesh(ctx, vertices=host_v, indices=host_i)  # H2D of this step's inputs (pinned host memory)
         fb.clear(CLEAR)
         pipe.render_mesh(sr.TRIANGLE, m).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
-        ctx.synchronize()
-        barrier()
-        if rank == 0:
-            fb.download(host_fb)  # D2H of the step's result
+        fb.download(host_fb)  # D2H of the step's result (synchronises)
         m.destroy()
 
     e2e_frame()
@@ -237,41 +273,59 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_frame()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": ntris / e2e_s / 1e6, "unit": "Mtris/s", "frames_per_s": 1.0 / e2e_s,
-           "h2d_bytes_per_step": int(host_v.nbytes + host_i.nbytes + 576), "d2h_bytes_per_step": int(w * h * 20),
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e = {"value": world * ntris / e2e_s / 1e6, "unit": "Mtris/s", "frames_per_s": world / e2e_s,
+           "h2d_bytes_per_step": int(host_v.nbytes + host_i.nbytes + 576) * world, "d2h_bytes_per_step": int(w * h * 20) * world,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         b_alg = algorithmic_bytes(nverts, ntris, w, h)
         achieved = b_alg / (ms_per_step * 1e-3) / 1e9
+        # the dominant kernel and its own algorithmic bytes
+        kernels = {
+            "k_vertex": {"ms": stage_acc.get("vertex_ms", 0.0), "alg_bytes": nverts * (24 + 48)},
+            "k_vis_init": {"ms": stage_acc.get("vis_init_ms", 0.0), "alg_bytes": w * h * 8},
+            "k_micro": {"ms": stage_acc.get("micro_ms", 0.0), "alg_bytes": 3 * ntris * 4 + nverts * 16},
+            "k_tile_opaque(+offsets)": {"ms": stage_acc.get("raster_ms", 0.0), "alg_bytes": w * h * (8 + 20)},
+        }
+        for k in kernels.values():
+            k["GBps"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
+            k["frac"] = k["GBps"] / peak if k["GBps"] else None
+        dom = max(kernels, key=lambda n: kernels[n]["ms"])
+        traffic = kernel_traffic()
         line = {
-            "metric": f"Mtris/s at {w}x{h}", "value": ntris / (ms_per_step * 1e-3) / 1e6, "unit": "Mtris/s",
-            "frames_per_s": 1e3 / ms_per_step,
+            "metric": f"Mtris/s at {w}x{h}", "value": world * ntris / (ms_per_step * 1e-3) / 1e6, "unit": "Mtris/s",
+            "frames_per_s": world * 1e3 / ms_per_step,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": args.config, "width": w, "height": h, "triangles": ntris, "vertices": nverts,
                        "shader": "suzanne Blinn-Phong", "depth_test": True,
-                       "parallelism": "1 GPU" if world == 1 else f"sort-first tile sharding over {world} GPUs, peer-store composite to rank 0",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"frame batching: {world} GPUs each render whole frames of the workload (no data-path collective); "
+                       f"the sort-first tile-sharded single frame is reported under 'sharded'",
                        "l2": "working set per frame (mesh 240 MB + shaded vertices 240 MB + framebuffer 166 MB) exceeds the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg,
-                         "scope": "whole frame (vertex + binning + tile raster kernels): B_alg / frame time",
-                         "stage_ms_last_step": stage},
+                         "traffic": traffic.get("frame_dram_bytes"), "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg,
+                         "scope": "whole frame: B_alg / frame time (SURVEY.md 8d); per-kernel figures under 'kernels'",
+                         "dominant_kernel": {"name": dom, "achieved": kernels[dom]["GBps"], "frac": kernels[dom]["frac"],
+                                             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
+                                             "traffic": traffic.get(dom),
+                                             "note": "issue-slot bound, not HBM bound (DESIGN.md section 4): see profiles/"},
+                         "kernels": kernels,
+                         "stage_ms_avg": stage_acc},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
+        if sharded:
+            line["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _, _ = cpu_reference_sample(args.config)
         print(json.dumps(line))
     barrier()
-    for x in (pipe, gmesh):
+    for x in (pipe, gmesh, fb):
         x.destroy()
     if world > 1:
         dist.destroy_process_group()

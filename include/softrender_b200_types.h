@@ -145,7 +145,8 @@ typedef struct sr_stage_times {
     float vertex_ms;
     float geometry_ms;
     float bin_ms;     /* per-tile lists of the ordered path (triangles with blend/stencil/discard, lines, points) */
-    float micro_ms;   /* opaque path: visibility-buffer init + per-triangle setup / small-triangle rasterisation */
+    float vis_init_ms;/* opaque path: visibility-buffer initialisation (k_vis_init) */
+    float micro_ms;   /* opaque path: per-triangle setup / small-triangle rasterisation (k_micro) */
     float raster_ms;  /* tile kernels: large triangles, resolve (shading) and the single write-back */
     float total_ms;
 } sr_stage_times;

@@ -28,7 +28,7 @@ pp = ctypes.POINTER(c_void_p)
 
 class StageTimes(ctypes.Structure):
     _fields_ = [("vertex_ms", ctypes.c_float), ("geometry_ms", ctypes.c_float), ("bin_ms", ctypes.c_float),
-                ("micro_ms", ctypes.c_float), ("raster_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
+                ("vis_init_ms", ctypes.c_float), ("micro_ms", ctypes.c_float), ("raster_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
 
 
 # every symbol include/softrender_b200.h declares: name -> (restype, argtypes)

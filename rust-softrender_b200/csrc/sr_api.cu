@@ -287,7 +287,7 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     p.tile_count = count->as<uint32_t>();
     const uint32_t grid = ceil_div(nprims, 256);
     SR_LAUNCH(c, k_bin_setup<NV>, grid, 256, 0, p);
-    SR_LAUNCH(c, k_tile_offsets, 1, 256, 0, count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), count->as<uint32_t>());
+    SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), count->as<uint32_t>());
     SR_CUDA(cudaMemcpyAsync(&b->total, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
     SR_TRY(c->alloc((size_t)std::max(b->total, 1u) * 4, &b->list));
@@ -361,6 +361,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         if (!fb->vis_buf) SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
         SR_LAUNCH(c, k_vis_init, owned, 256, 0, fb->vis_buf->as<unsigned long long>(), fb->view(), c->shard_rank, c->shard_world);
     }
+    record(c, 7);
     Buf count, off, lcount, lids, lrects, list;
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
@@ -388,7 +389,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         if (c->micro_precheck) SR_LAUNCH(c, k_micro<true>, grid, SR_MICRO_THREADS, 0, mp);
         else SR_LAUNCH(c, k_micro<false>, grid, SR_MICRO_THREADS, 0, mp);
         record(c, 5);
-        SR_LAUNCH(c, k_tile_offsets, 1, 256, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
+        SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
         if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
         SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
         SR_CUDA(cudaMemcpyAsync(&c->pinned[1], lcount->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -507,9 +508,10 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
     span(0, 1, &t.vertex_ms);
     span(1, 2, &t.geometry_ms);
     span(3, 4, &t.bin_ms);
-    span(4, 5, &t.micro_ms);
+    span(4, 7, &t.vis_init_ms);
+    span(7, 5, &t.micro_ms);
     span(5, 6, &t.raster_ms);
-    t.total_ms = t.vertex_ms + t.geometry_ms + t.bin_ms + t.micro_ms + t.raster_ms;
+    t.total_ms = t.vertex_ms + t.geometry_ms + t.bin_ms + t.vis_init_ms + t.micro_ms + t.raster_ms;
     *out = t;
     return SR_OK;
 }
@@ -1091,6 +1093,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl));
     SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp));
     record(c, 4);
+    record(c, 7);
     record(c, 5);
     tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>();
     tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>();

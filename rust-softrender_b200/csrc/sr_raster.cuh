@@ -157,22 +157,24 @@ __global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_fill(const SrBinParams p
     sr_bin_group<true>(p, rect, t >> 5);
 }
 
-// exclusive scan of the per-tile counts (a few thousand tiles: one block), total to off[ntiles]
-__global__ void __launch_bounds__(256) k_tile_offsets(const uint32_t *count, uint32_t ntiles, uint32_t *off, uint32_t *cursor) {
+// exclusive scan of the per-tile counts (a few thousand tiles: one block of 1024 threads, each thread owning a run of
+// consecutive tiles so that one block-wide scan suffices), total to off[ntiles]; the counts are zeroed for re-use as cursors
+#define SR_OFFSETS_THREADS 1024
+__global__ void __launch_bounds__(SR_OFFSETS_THREADS) k_tile_offsets(const uint32_t *count, uint32_t ntiles, uint32_t *off, uint32_t *cursor) {
     __shared__ uint32_t ws[32];
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < ntiles ? count[i] : 0;
-        uint32_t tot;
-        const uint32_t ex = sr_block_exclusive_scan(v, &tot, ws);
-        if (i < ntiles) {
-            off[i] = carry + ex;
-            cursor[i] = 0;
-        }
-        carry += tot;
+    const uint32_t per = (ntiles + SR_OFFSETS_THREADS - 1) / SR_OFFSETS_THREADS;
+    const uint32_t beg = min(threadIdx.x * per, ntiles), end = min(beg + per, ntiles);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; ++i) sum += count[i];
+    uint32_t total;
+    uint32_t run = sr_block_exclusive_scan(sum, &total, ws);
+    for (uint32_t i = beg; i < end; ++i) {
+        const uint32_t v = count[i];
+        off[i] = run;
+        cursor[i] = 0;
+        run += v;
     }
-    if (threadIdx.x == 0) off[ntiles] = carry;
+    if (threadIdx.x == 0) off[ntiles] = total;
 }
 
 // =====================================================================================================
