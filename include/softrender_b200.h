@@ -58,6 +58,12 @@ int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
  * area = 0 sends every triangle through the tile lists.  Draws onto existing (not freshly cleared) contents
  * use the visibility buffer only from `min_triangles` on.  Results never depend on these values. */
 int sr_context_set_micro(sr_context *, uint32_t area, uint32_t min_triangles, uint32_t precheck);
+/* capacity (u32 entries) of the arena that holds the opaque path's per-tile triangle lists.  A draw is enqueued
+ * against the current capacity without a host synchronisation; if its lists do not fit, the tile pass skips itself on
+ * the device and is enqueued again with a larger arena at the next call that touches the context.
+ * Setting a tiny capacity exercises that path in tests. */
+int sr_context_set_list_capacity(sr_context *, uint32_t entries);
+int sr_context_list_capacity(sr_context *, uint32_t *entries);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int sr_context_launch_count(sr_context *, uint64_t *out);
 

@@ -62,6 +62,13 @@ struct sr_context {
     uint32_t micro_min_tris = 65536;              // draws onto existing contents use the visibility buffer from this size on
     uint32_t micro_precheck = 0;  // read the key before the atomic: measured slower (load latency inside the per-lane loop)
     uint32_t *pinned = nullptr;                   // pinned host words for device->host counters
+    // per-tile lists of the opaque path live in one arena that only grows; a draw is launched optimistically against
+    // the current capacity and validated later (settle) so that no host synchronisation sits inside a frame
+    Buf list_arena;
+    uint32_t list_cap = 0;
+    struct PendingOpaque *pending = nullptr;
+    Buf zero_off;                                 // all-zero CSR offsets for empty primitive kinds
+    uint32_t zero_off_tiles = 0;
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);
     void release(void *p, size_t bytes) { free_list.emplace(bytes, p); }
@@ -240,7 +247,9 @@ static int exclusive_scan(sr_context *c, const uint32_t *in, uint64_t n, uint32_
     return SR_OK;
 }
 
+static int settle(sr_context *c);
 static int materialize_clear(sr_framebuffer *fb) {
+    SR_TRY(settle(fb->ctx));  // every read-back / host-visible access of a framebuffer passes through here
     if (!fb->pending_clear) return SR_OK;
     const uint64_t n = (uint64_t)fb->width * fb->height;
     SrFbView v = fb->view();
@@ -259,10 +268,15 @@ struct Bins {
 };
 
 static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
-    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
-    SR_CUDA(cudaMemsetAsync(b->off->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
-    SR_TRY(c->alloc(4, &b->rects));
-    SR_TRY(c->alloc(4, &b->list));
+    // one persistent all-zero offsets array serves every empty primitive kind (nothing ever writes to it)
+    if (!c->zero_off || c->zero_off_tiles < ntiles) {
+        SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &c->zero_off));
+        SR_CUDA(cudaMemsetAsync(c->zero_off->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
+        c->zero_off_tiles = ntiles;
+    }
+    b->off = c->zero_off;
+    b->rects = c->zero_off;
+    b->list = c->zero_off;
     b->total = 0;
     return SR_OK;
 }
@@ -351,10 +365,48 @@ static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, c
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
 }
 
+// A draw whose per-tile lists were sized optimistically.  The device kernels skip themselves when the lists do not fit
+// (k_large_fill / k_tile_opaque compare the scanned total with the capacity they were given); settle() reads the totals
+// once the stream has passed them and, in that rare case, grows the arena and enqueues the skipped pass again.
+struct PendingOpaque {
+    cudaEvent_t counted = nullptr;  // recorded after the totals were copied to pinned memory
+    uint32_t capacity = 0;
+    uint32_t fs = 0, owned = 0, ntiles = 0;
+    SrOpaqueParams op;
+    std::vector<Buf> keep;          // every device buffer the pass reads (the draw may be destroyed meanwhile)
+    Buf count, off, lcount, lids, lrects;
+    sr_framebuffer *fb = nullptr;
+};
+static int launch_opaque_pass(sr_context *c, PendingOpaque *q);
+static int settle(sr_context *c) {
+    PendingOpaque *q = c->pending;
+    if (!q) return SR_OK;
+    c->pending = nullptr;
+    std::unique_ptr<PendingOpaque> guard(q);
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_CUDA(cudaEventSynchronize(q->counted));
+    cudaEventDestroy(q->counted);
+    q->counted = nullptr;
+    const uint32_t total = c->pinned[0];
+    if (total <= q->capacity) return SR_OK;
+    // the pass skipped itself: grow the arena and run it again (framebuffer and visibility buffer are untouched)
+    Buf bigger;
+    const uint32_t cap = std::max<uint32_t>(total + total / 2, 1u << 20);
+    SR_TRY(c->alloc((size_t)cap * 4, &bigger));
+    c->list_arena = bigger;
+    c->list_cap = cap;
+    q->capacity = cap;
+    q->op.list = bigger->as<uint32_t>();
+    q->op.list_capacity = cap;
+    q->keep.push_back(bigger);
+    return launch_opaque_pass(c, q);
+}
+
 // The opaque triangle path (sr_raster.cuh): visibility-buffer init, k_micro (per-triangle setup + direct
 // rasterisation of small triangles + compaction/counting of the large ones), per-tile lists of the large
 // triangles, then the tile kernel (large triangles + resolve + single write-back).
-static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned) {
+static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
+                            const std::vector<Buf> &keep) {
     const uint32_t ntiles = fb->ntx * fb->nty;
     const bool use_micro = c->micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
     if (use_micro) {
@@ -362,7 +414,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         SR_LAUNCH(c, k_vis_init, owned, 256, 0, fb->vis_buf->as<unsigned long long>(), fb->view(), c->shard_rank, c->shard_world);
     }
     record(c, 7);
-    Buf count, off, lcount, lids, lrects, list;
+    Buf count, off, lcount, lids, lrects;
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
     SR_TRY(c->alloc(4, &lcount));
@@ -370,7 +422,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     SR_TRY(c->alloc((size_t)std::max(tp.ntris, 1u) * 4, &lrects));
     SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
     SR_CUDA(cudaMemsetAsync(lcount->ptr, 0, 4, c->stream));
-    uint32_t nlarge = 0, total = 0;
+    auto q = std::make_unique<PendingOpaque>();
     if (tp.ntris) {
         SrMicroParams mp;
         memset(&mp, 0, sizeof(mp));
@@ -388,35 +440,47 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         const uint32_t grid = ceil_div(tp.ntris, SR_MICRO_THREADS);
         if (c->micro_precheck) SR_LAUNCH(c, k_micro<true>, grid, SR_MICRO_THREADS, 0, mp);
         else SR_LAUNCH(c, k_micro<false>, grid, SR_MICRO_THREADS, 0, mp);
-        record(c, 5);
-        SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
-        if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
-        SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
-        SR_CUDA(cudaMemcpyAsync(&c->pinned[1], lcount->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
-        SR_CUDA(cudaStreamSynchronize(c->stream));
-        total = c->pinned[0];
-        nlarge = c->pinned[1];
-    } else {
-        SR_CUDA(cudaMemsetAsync(off->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
-        record(c, 5);
     }
-    SR_TRY(c->alloc((size_t)std::max(total, 1u) * 4, &list));
-    if (nlarge)
-        SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(nlarge, 256), 148u * 8u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
-                  lrects->as<uint32_t>(), fb->ntx, c->shard_rank, c->shard_world, off->as<uint32_t>(), count->as<uint32_t>(), list->as<uint32_t>());
-    SrOpaqueParams op;
-    memset(&op, 0, sizeof(op));
-    op.tris = tp.tris;
-    op.ntris = tp.ntris;
-    op.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
-    op.tile_off = off->as<uint32_t>();
-    op.list = list->as<uint32_t>();
-    op.fb = fb->view();
-    op.shard_rank = c->shard_rank; op.shard_world = c->shard_world;
-    op.fs = tp.fs;
-    SR_TRY(launch_opaque_fs(c, fs, owned, op));
+    record(c, 5);
+    SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
+    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+    SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaEventCreateWithFlags(&q->counted, cudaEventDisableTiming));
+    SR_CUDA(cudaEventRecord(q->counted, c->stream));
+    if (!c->list_arena) {
+        c->list_cap = 1u << 20;
+        SR_TRY(c->alloc((size_t)c->list_cap * 4, &c->list_arena));
+    }
+    q->capacity = c->list_cap;
+    q->fs = fs; q->owned = owned; q->ntiles = ntiles;
+    q->count = count; q->off = off; q->lcount = lcount; q->lids = lids; q->lrects = lrects;
+    q->keep = keep;
+    q->keep.push_back(c->list_arena);
+    if (use_micro) q->keep.push_back(fb->vis_buf);
+    q->fb = fb;
+    memset(&q->op, 0, sizeof(q->op));
+    q->op.tris = tp.tris;
+    q->op.ntris = tp.ntris;
+    q->op.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
+    q->op.tile_off = off->as<uint32_t>();
+    q->op.list = c->list_arena->as<uint32_t>();
+    q->op.list_capacity = c->list_cap;
+    q->op.ntiles = ntiles;
+    q->op.fb = fb->view();
+    q->op.shard_rank = c->shard_rank; q->op.shard_world = c->shard_world;
+    q->op.fs = tp.fs;
+    SR_TRY(launch_opaque_pass(c, q.get()));
     fb->pending_clear = false;
+    c->pending = q.release();
     return SR_OK;
+}
+// per-tile lists of the large triangles + the tile kernel (both skip themselves if the lists do not fit the arena)
+static int launch_opaque_pass(sr_context *c, PendingOpaque *q) {
+    if (q->op.ntris)
+        SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(q->op.ntris, 256), 148u * 2u), 256, 0, q->lcount->as<uint32_t>(),
+                  q->lids->as<uint32_t>(), q->lrects->as<uint32_t>(), q->op.fb.ntx, q->ntiles, q->op.shard_rank, q->op.shard_world,
+                  q->off->as<uint32_t>(), q->count->as<uint32_t>(), const_cast<uint32_t *>(q->op.list), q->capacity);
+    return launch_opaque_fs(c, q->fs, q->owned, q->op);
 }
 static int fs_nk(uint32_t fs) {
     switch (fs) {
@@ -461,6 +525,7 @@ int sr_context_create(int device, sr_context **out) {
     return SR_OK;
 }
 int sr_context_destroy(sr_context *c) {
+    settle(c);
     if (!c) return SR_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -474,6 +539,7 @@ int sr_context_destroy(sr_context *c) {
     return SR_OK;
 }
 int sr_context_synchronize(sr_context *c) {
+    SR_TRY(settle(c));
     if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null context");
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
@@ -493,12 +559,29 @@ int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, u
     c->micro_precheck = precheck ? 1u : 0u;
     return SR_OK;
 }
+int sr_context_set_list_capacity(sr_context *c, uint32_t entries) {
+    if (!c || entries == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad capacity");
+    SR_TRY(settle(c));
+    SR_CUDA(cudaSetDevice(c->device));
+    Buf arena;
+    SR_TRY(c->alloc((size_t)entries * 4, &arena));
+    c->list_arena = arena;
+    c->list_cap = entries;
+    return SR_OK;
+}
+int sr_context_list_capacity(sr_context *c, uint32_t *entries) {
+    if (!c || !entries) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(settle(c));
+    *entries = c->list_cap;
+    return SR_OK;
+}
 int sr_context_launch_count(sr_context *c, uint64_t *out) {
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     *out = c->launches;
     return SR_OK;
 }
 int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
+    SR_TRY(settle(c));
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     SR_CUDA(cudaStreamSynchronize(c->stream));
     sr_stage_times t = {};
@@ -537,6 +620,7 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     return SR_OK;
 }
 int sr_framebuffer_destroy(sr_framebuffer *fb) {
+    settle(fb->ctx);
     if (!fb) return SR_OK;
     if (fb->is_peer && fb->aos) cudaIpcCloseMemHandle(fb->aos);
     delete fb;
@@ -1055,6 +1139,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     sr_context *c = p->ctx;
     sr_framebuffer *fb = p->fb;
     SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(settle(c));
     if (fb->width < 2 || fb->height < 2) return SR_OK;  // fragment.rs:188-216: a 1-pixel-wide frame has no tiles, nothing is drawn
     if (fs == SR_FS_FULL_EXAMPLE_TEXTURED && !p->texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
 
@@ -1103,7 +1188,11 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         if (opaque_ok) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,
             // fragment.rs:268-311) through the ordered kernel
-            if (tp.ntris || fb->pending_clear) SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned));
+            if (tp.ntris || fb->pending_clear) {
+                std::vector<Buf> keep = {d->indices, d->indexed.pos, d->indexed.attr, d->gen[2].pos, d->gen[2].attr, d->tri_seq};
+                if (p->texture) keep.push_back(p->texture->rgba);
+                SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep));
+            }
             if (tp.nlines + tp.npoints) {
                 SrTileParams t2 = tp;
                 t2.ntris = 0;

@@ -528,8 +528,9 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
 
 // second pass over the large triangles only: write their ids into the per-tile lists
 __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count, const uint32_t *large_ids, const uint32_t *large_rects,
-                                                    uint32_t ntx, uint32_t shard_rank, uint32_t shard_world, const uint32_t *tile_off,
-                                                    uint32_t *tile_cursor, uint32_t *list) {
+                                                    uint32_t ntx, uint32_t ntiles, uint32_t shard_rank, uint32_t shard_world,
+                                                    const uint32_t *tile_off, uint32_t *tile_cursor, uint32_t *list, uint32_t capacity) {
+    if (tile_off[ntiles] > capacity) return;  // the lists do not fit: the host re-runs this pass with a larger arena
     const uint32_t n = *large_count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t t = large_ids[i], rect = large_rects[i];
@@ -560,6 +561,7 @@ struct SrOpaqueParams {
     const unsigned long long *vis;  // null: keys start from the framebuffer depth / the pending clear
     const uint32_t *tile_off;       // per-tile CSR offsets into `list` (large triangles)
     const uint32_t *list;
+    uint32_t list_capacity, ntiles;  // the pass skips itself when tile_off[ntiles] > list_capacity (see k_large_fill)
     SrFbView fb;
     uint32_t shard_rank, shard_world;
     SrFsConst fs;
@@ -575,6 +577,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
+    if (p.tile_off[p.ntiles] > p.list_capacity) return;
     const uint32_t lbeg = p.tile_off[tile], L = p.tile_off[tile + 1] - lbeg;
     if (L == 0 && !p.fb.pending_clear && p.vis == nullptr) return;  // nothing to draw, contents already in HBM
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -58,6 +58,14 @@ class Context:
         """Tuning of the opaque triangle path (results never depend on it): see sr_context_set_micro."""
         check(lib.sr_context_set_micro(self.h, area, min_triangles, 1 if precheck else 0))
 
+    def set_list_capacity(self, entries: int):
+        check(lib.sr_context_set_list_capacity(self.h, entries))
+
+    def list_capacity(self) -> int:
+        n = ctypes.c_uint32()
+        check(lib.sr_context_list_capacity(self.h, ctypes.byref(n)))
+        return n.value
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         check(lib.sr_context_launch_count(self.h, ctypes.byref(n)))

@@ -282,6 +282,24 @@ def test_opaque_path_split_is_invisible(P, ctx, area, min_tris, precheck):
     H.compare_framebuffers(out, ofb, exact_color=True, what=f"micro area {area}")
 
 
+def test_list_arena_overflow_is_replayed(P, ctx):
+    """The opaque path enqueues a draw against the current per-tile list capacity without synchronising; when the
+    lists do not fit, the tile pass skips itself on the device and is replayed with a larger arena.  Two draws back
+    to back with a 4-entry arena must still give the oracle's frame."""
+    rng = np.random.default_rng(79)
+    w, h, n = 320, 200, 400
+    verts = H.random_screen_triangles(rng, n, w, h, integer_depth=True)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    ctx.set_list_capacity(4)
+    try:
+        out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, draws=2)
+        assert ctx.list_capacity() > 4
+    finally:
+        ctx.set_list_capacity(1 << 20)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="replayed tile pass")
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_tile_sharding_is_invisible(P, ctx, world):
     """Sort-first sharding: `world` contexts each rasterise the tiles with index % world == rank into ONE shared
