@@ -255,28 +255,60 @@ def run_ours(args):
         barrier()
 
     # ---- end to end through the C ABI with HOST buffers: mesh upload + draw + framebuffer read-back each step ----
+    # Three frames are in flight (three contexts = three CUDA streams, one host thread each, the C ABI releases the GIL): the
+    # read-back of frame k (D2H) overlaps the mesh upload of frame k+1 (H2D) on the full-duplex PCIe link.  Every step
+    # still copies its own inputs from pinned host memory and reads its own result back inside the timed region.
     host_v = torch.from_numpy(mesh.vertices).pin_memory().numpy()
     host_i = torch.from_numpy(mesh.indices.astype(np.uint32)).pin_memory().numpy()
-    host_fb = torch.empty((w * h, 5), dtype=torch.float32).pin_memory().numpy()
-    e2e_steps = max(1, min(args.steps, 5))
+    depth = 3
+    lanes = []
+    for k in range(depth):
+        cx = ctx if k == 0 else P.Context(local_rank)
+        lfb = fb if k == 0 else P.RenderBuffer.with_dimensions(cx, w, h)
+        lp = pipe if k == 0 else P.Pipeline.from_framebuffer(lfb, u)
+        lanes.append((cx, lfb, lp, torch.empty((w * h, 5), dtype=torch.float32).pin_memory().numpy()))
+    e2e_steps = max(depth, min(args.steps, 9) // depth * depth)
 
-    def e2e_frame():
-        m = P.Mesh(ctx, vertices=host_v, indices=host_i)  # H2D of this step's inputs (pinned host memory)
-        fb.clear(CLEAR)
-        pipe.render_mesh(sr.TRIANGLE, m).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
-        fb.download(host_fb)  # D2H of the step's result (synchronises)
+    def e2e_frame(lane):
+        cx, lfb, lp, host_fb = lane
+        m = P.Mesh(cx, vertices=host_v, indices=host_i)  # H2D of this step's inputs (pinned host memory)
+        lfb.clear(CLEAR)
+        lp.render_mesh(sr.TRIANGLE, m).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+        lfb.download(host_fb)  # D2H of the step's result (synchronises)
         m.destroy()
 
-    e2e_frame()
+    def e2e_run(nsteps):
+        start = threading.Barrier(depth + 1)
+
+        def work(lane):
+            start.wait()
+            for _ in range(nsteps // depth):
+                e2e_frame(lane)
+
+        threads = [threading.Thread(target=work, args=(lane,)) for lane in lanes]
+        for t in threads:
+            t.start()
+        barrier()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in threads:
+            t.join()
+        return time.perf_counter() - t0
+
+    e2e_run(depth)  # warm-up (allocations, first touches)
+    e2e_s = max_over_ranks(e2e_run(e2e_steps) / e2e_steps)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_frame()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    # the last frame read back must be the frame the device-resident path produces
+    ref_fb = fb.download()
+    e2e_ok = bool(np.array_equal(lanes[-1][3].view(np.uint32), ref_fb.view(np.uint32)))
     e2e = {"value": world * ntris / e2e_s / 1e6, "unit": "Mtris/s", "frames_per_s": world / e2e_s,
            "h2d_bytes_per_step": int(host_v.nbytes + host_i.nbytes + 576) * world, "d2h_bytes_per_step": int(w * h * 20) * world,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "frames_in_flight": depth, "result_matches_resident_path": e2e_ok,
+           "note": "PCIe-bound: upload of frame k+1 overlaps read-back of frame k (three contexts/streams)"}
+    for cx, lfb, lp, _ in lanes[1:]:
+        lp.destroy()
+        lfb.destroy()
+        cx.close()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -333,7 +333,11 @@ static SrPrimSource prim_source(const sr_draw *d, uint32_t kind /*1 point,2 line
 // ---------------------------------------------------------------------------------------------------------
 template <int FS>
 static int launch_tiles(sr_context *c, uint32_t ntiles_owned, const SrTileParams &p) {
-    SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
+    static bool configured[16] = {};  // per device: opt in to the large dynamic shared memory once
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
+        configured[c->device & 15] = true;
+    }
     SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
     return SR_OK;
 }
@@ -350,7 +354,11 @@ static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, co
 }
 template <int FS>
 static int launch_opaque(sr_context *c, uint32_t ntiles_owned, const SrOpaqueParams &p) {
-    SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
+        configured[c->device & 15] = true;
+    }
     SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
     return SR_OK;
 }
@@ -797,15 +805,19 @@ int sr_mesh_create(sr_context *c, const float *vertices, uint64_t nverts, uint32
     }
     // range-check the indices on the device (the reference would panic on an out-of-range index)
     uint32_t maxidx = 0;
+    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
     if (nindices) {
         Buf mx;
         SR_TRY(c->alloc(4, &mx));
         SR_CUDA(cudaMemsetAsync(mx->ptr, 0, 4, c->stream));
         SR_LAUNCH(c, k_index_max, std::min<uint32_t>(ceil_div(nindices, 256), 1184u), 256, 0, m->indices->as<uint32_t>(), nindices, mx->as<uint32_t>());
-        SR_CUDA(cudaMemcpyAsync(&maxidx, mx->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+        // pinned destination: a pageable one would make this call block inside the driver until the upload has finished,
+        // stalling every other thread's CUDA calls (frames in flight on other contexts)
+        SR_CUDA(cudaMemcpyAsync(&c->pinned[2], mx->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
     }
     // "buffers passed in are copied before return"
     SR_CUDA(cudaStreamSynchronize(c->stream));
+    if (nindices) maxidx = c->pinned[2];
     if (nindices && maxidx >= nverts)
         return sr_fail(SR_ERR_INVALID_ARGUMENT, "index %u out of range (%llu vertices)", maxidx, (unsigned long long)nverts);
     *out = m.release();
