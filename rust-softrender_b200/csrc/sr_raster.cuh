@@ -438,6 +438,51 @@ __device__ __forceinline__ unsigned long long sr_ld_relaxed_u64(const unsigned l
     return v;
 }
 
+// The tightened path of k_micro: |det| in [1, 50], numerators below 2^7, no NaN.  Straight-line body (no divergent
+// branch inside the loop; lanes sit on different triangles, so every branch would be taken by somebody anyway):
+// u, v by the exact-division shortcut, the reduction as a predicated red.global.max.u64.  A numerator below the
+// shortcut's validity bound (|n| < 2^-60, e.g. a pixel centre exactly on an edge) makes the lane redo its box with
+// IEEE divisions afterwards (returns true); re-emitting a fragment is harmless because max is idempotent.
+__device__ __forceinline__ bool sr_micro_box(const SrTri &tr, float z1, float z2, float z3, int lx, int ly, int hx, int hy, uint32_t id,
+                                             unsigned long long *vis, uint32_t pitch) {
+    const float xf0 = (float)lx + 0.5f, xlast = (float)hx + 0.5f;
+    float xf = xf0, yf = (float)ly + 0.5f;
+    float dy = yf - tr.y3, bdy = tr.b * dy, ddy = tr.d * dy;
+    const uint32_t cw = (uint32_t)(hx - lx + 1), n = cw * (uint32_t)(hy - ly + 1);
+    uint32_t idx = (uint32_t)ly * pitch + (uint32_t)lx;
+    const uint32_t key_lo = id + 1u, row_skip = pitch - cw;
+    bool redo = false;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; ++i) {
+        const float dx = xf - tr.x3;
+        const float nu = tr.a * dx + bdy, nv = tr.c * dx + ddy;
+        const bool ok = fabsf(nu) >= 0x1p-60f && fabsf(nv) >= 0x1p-60f;
+        const float u = sr_div_exact(nu, tr.det, tr.rdet), v = sr_div_exact(nv, tr.det, tr.rdet);
+        const float w = 1.0f - u - v;
+        const float z = (z1 * u + z2 * v) + z3 * w;
+        const bool pass = ok && !(u < 0.0f || v < 0.0f || w < 0.0f) && z < 0.0f;  // triangle.rs:113,120
+        redo = redo || !ok;
+        // for negative z the order-preserving depth key is ~bits
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 k;\n\t"
+            "setp.ne.u32 p, %3, 0;\n\t"
+            "mov.b64 k, {%1, %2};\n\t"
+            "@p red.relaxed.gpu.global.max.u64 [%0], k;\n\t"
+            "}" ::"l"(vis + idx), "r"(key_lo), "r"(~__float_as_uint(z)), "r"((uint32_t)pass)
+            : "memory");
+        ++idx;
+        const bool wrap = xf >= xlast;
+        xf += 1.0f;
+        if (wrap) {
+            xf = xf0; idx += row_skip;
+            yf += 1.0f; dy = yf - tr.y3; bdy = tr.b * dy; ddy = tr.d * dy;
+        }
+    }
+    return redo;
+}
+
 #define SR_MICRO_THREADS 256
 template <bool PRECHECK>
 __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constant__ SrMicroParams p) {
@@ -482,8 +527,12 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
                 // reference's clamped bounding box intersected with the tightened range (rule above;
                 // for x >= 0 trunc(xmin) <= ceil(xmin - 0.5625) and floor(xmax - 0.4375) <= trunc(xmax), so the
                 // intersection is just the tightened range clamped to the frame)
-                raster(std::true_type(), max(0, sr_tight_lo(xmin)), max(0, sr_tight_lo(ymin)), min((int)p.width - 1, sr_tight_hi(xmax)),
-                       min((int)p.height - 1, sr_tight_hi(ymax)));
+                const int lx = max(0, sr_tight_lo(xmin)), ly = max(0, sr_tight_lo(ymin));
+                const int hx = min((int)p.width - 1, sr_tight_hi(xmax)), hy = min((int)p.height - 1, sr_tight_hi(ymax));
+                if (lx <= hx && ly <= hy) {
+                    if (sharded) raster(std::true_type(), lx, ly, hx, hy);
+                    else if (sr_micro_box(tr, A.z, B.z, C.z, lx, ly, hx, hy, t, p.vis, p.ntx * SR_TILE_W)) raster(std::false_type(), lx, ly, hx, hy);
+                }
             } else if (!(isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y))) {
                 // (the reference panics on NaN coordinates, cast(..).unwrap(); defined here as "skipped")
                 // triangle.rs:74-78 with tile = the whole frame
