@@ -120,7 +120,9 @@ struct sr_framebuffer {
     uint32_t width, height, format;
     uint32_t ntx, nty;
     Buf aos_buf, stencil_buf, winner_buf;
-    Buf vis_buf;                // tiled visibility buffer of the opaque path (allocated on first use)
+    Buf vis_buf;                // visibility buffer of the opaque path (allocated on first use)
+    bool vis_clean = false;     // every key of the tiles of shard (vis_rank, vis_world) is "far": the resolve hands it back that way
+    uint32_t vis_rank = 0, vis_world = 0;
     float *aos = nullptr;       // device (possibly peer) pointer
     bool is_peer = false;       // opened through cudaIpcOpenMemHandle
     bool pending_clear = false;
@@ -418,8 +420,16 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     const uint32_t ntiles = fb->ntx * fb->nty;
     const bool use_micro = c->micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
     if (use_micro) {
-        if (!fb->vis_buf) SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
-        SR_LAUNCH(c, k_vis_init, owned, 256, 0, fb->vis_buf->as<unsigned long long>(), fb->view(), c->shard_rank, c->shard_world);
+        if (!fb->vis_buf) {
+            SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
+            fb->vis_clean = false;
+        }
+        const bool clean = fb->vis_clean && fb->vis_rank == c->shard_rank && fb->vis_world == c->shard_world;
+        if (!(clean && fb->pending_clear))
+            SR_LAUNCH(c, k_vis_init, owned, 256, 0, fb->vis_buf->as<unsigned long long>(), fb->view(), c->shard_rank, c->shard_world);
+        fb->vis_clean = true;  // the tile kernel below resets the keys it consumes
+        fb->vis_rank = c->shard_rank;
+        fb->vis_world = c->shard_world;
     }
     record(c, 7);
     Buf count, off, lcount, lids, lrects;
@@ -470,6 +480,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     q->op.tris = tp.tris;
     q->op.ntris = tp.ntris;
     q->op.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
+    q->op.reset_vis = use_micro ? 1u : 0u;
     q->op.tile_off = off->as<uint32_t>();
     q->op.list = c->list_arena->as<uint32_t>();
     q->op.list_capacity = c->list_cap;

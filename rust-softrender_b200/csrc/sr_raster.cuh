@@ -601,13 +601,14 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
 #endif
 #define SR_OPQ_WARPS (SR_OPQ_THREADS / 32)
 #define SR_OPQ_STAGE_FLOATS (32 * 5)  // one warp's 32 finished pixels, AoS {r,g,b,a,depth}
-#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4 + 16)
+#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4 + SR_TILE_W * 8 + 16)
 static_assert(SR_TILE_W % 32 == 0, "a warp resolves 32 consecutive pixels of one tile row");
 
 struct SrOpaqueParams {
     SrPrimSource tris;
     uint32_t ntris;
-    const unsigned long long *vis;  // null: keys start from the framebuffer depth / the pending clear
+    unsigned long long *vis;        // null: keys start from the framebuffer depth / the pending clear
+    uint32_t reset_vis;             // write far keys back once the tile's keys are on chip (the next frame skips k_vis_init)
     const uint32_t *tile_off;       // per-tile CSR offsets into `list` (large triangles)
     const uint32_t *list;
     uint32_t list_capacity, ntiles;  // the pass skips itself when tile_off[ntiles] > list_capacity (see k_large_fill)
@@ -621,7 +622,8 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
     float *stage_all = reinterpret_cast<float *>(keys + SR_TILE_PIXELS);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(stage_all + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS);
+    unsigned long long *far_row = reinterpret_cast<unsigned long long *>(stage_all + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(far_row + SR_TILE_W);
 
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
@@ -641,7 +643,17 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         }
         __syncthreads();
         if (tid < SR_TILE_H) sr_bulk_g2s(keys + tid * SR_TILE_W, p.vis + sr_vis_index(x0, y0 + tid, p.fb.ntx), SR_TILE_W * 8, bar);
+        if (p.reset_vis && tid < SR_TILE_W) far_row[tid] = SR_VIS_FAR_KEY;
         sr_mbar_wait(bar, 0);
+        if (p.reset_vis) {
+            // the keys are on chip: hand the visibility buffer back all-far, so the next cleared frame needs no init pass
+            sr_fence_proxy_async();
+            __syncthreads();
+            if (tid < SR_TILE_H) {
+                sr_bulk_s2g(p.vis + sr_vis_index(x0, y0 + tid, p.fb.ntx), far_row, SR_TILE_W * 8);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
     } else {
         for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
             const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
@@ -806,7 +818,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
             dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; dst[4] = o[4];
         }
     }
-    if (nbulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if ((nbulk && lane == 0) || (p.vis != nullptr && p.reset_vis && tid < SR_TILE_H)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // =====================================================================================================
