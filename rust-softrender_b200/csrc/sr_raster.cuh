@@ -784,9 +784,13 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl) {
+#ifdef SR_EXPERIMENT_NOATTR
+                    const float4 ka = A, kb = B, kc = C;
+#else
                     const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi0);
                     const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi1);
                     const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi2);
+#endif
                     sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
                     sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
                     sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
