@@ -161,14 +161,14 @@ struct sr_pipeline {
     sr_texture *texture = nullptr;
 };
 
-struct VertexStream {  // one flat Vec of vertices in HBM: position plane + attribute planes
+struct VertexStream {  // one flat Vec of vertices in HBM: position array + attribute records (np float4 per vertex)
     Buf pos, attr;
-    uint64_t n = 0, stride = 0;
+    uint64_t n = 0, stride = 0, np = 1;  // stride = n padded to 4 (allocation size in vertices)
     SrVertexSet set() const {
         SrVertexSet s;
         s.pos = pos ? pos->as<float4>() : nullptr;
         s.attr = attr ? attr->as<float4>() : nullptr;
-        s.stride = stride;
+        s.np = np;
         return s;
     }
 };
@@ -211,8 +211,9 @@ static int alloc_stream(sr_context *c, uint64_t n, uint32_t nk, VertexStream *ou
     out->n = n;
     out->stride = (n + 3) & ~(uint64_t)3;
     if (out->stride == 0) out->stride = 4;
+    out->np = std::max(1u, nplanes_of(nk));
     SR_TRY(c->alloc(out->stride * sizeof(float4), &out->pos));
-    SR_TRY(c->alloc(out->stride * sizeof(float4) * std::max(1u, nplanes_of(nk)), &out->attr));
+    SR_TRY(c->alloc(out->stride * sizeof(float4) * out->np, &out->attr));
     return SR_OK;
 }
 
@@ -956,9 +957,9 @@ static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
     if (d->mesh_nverts) {
         float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
         const uint32_t grid1 = ceil_div(d->mesh_nverts, 256);
-        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.stride);
-        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.stride);
-        else SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, pos, attr, d->indexed.stride);
+        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.np);
+        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.np);
+        else SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, pos, attr, d->indexed.np);
     }
     record(c, 1);
     record(c, 2);
@@ -988,7 +989,7 @@ static int clip_small(sr_context *c, const SrGeoIn &in, uint32_t nk, VertexStrea
     uint32_t total = 0;
     SR_TRY(exclusive_scan(c, cnt->as<uint32_t>(), n, off->as<uint32_t>(), &total));
     SR_TRY(alloc_stream(c, (uint64_t)total * NV, nk, out));
-    SrGeoOut o = {out->pos->as<float4>(), out->attr->as<float4>(), out->stride};
+    SrGeoOut o = {out->pos->as<float4>(), out->attr->as<float4>(), out->np};
     if (NV == 2) SR_LAUNCH(c, k_clip_line<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
     else SR_LAUNCH(c, k_clip_point<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
     return SR_OK;
@@ -1045,7 +1046,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             SR_TRY(exclusive_scan(c, lit->as<uint32_t>(), n, lit_off->as<uint32_t>(), &literal_total));
             SR_TRY(alloc_stream(c, (uint64_t)kept_total * 3, d->nk, &ntris));
             SR_TRY(c->alloc((size_t)std::max(kept_total, 1u) * 4, &nseq));
-            SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.stride};
+            SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.np};
             SR_LAUNCH(c, k_clip_tri_emit, grid, 128, 0, tin, drop, kept_off->as<uint32_t>(), lit_off->as<uint32_t>(), o, nseq->as<uint32_t>());
         }
     } else {
@@ -1056,7 +1057,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             const SrGeoIn in = geo_in(1, true, true);
             const uint32_t n = in.ngen + in.nidx;
             SR_TRY(alloc_stream(c, n, d->nk, &npoints));
-            SrGeoOut o = {npoints.pos->as<float4>(), npoints.attr->as<float4>(), npoints.stride};
+            SrGeoOut o = {npoints.pos->as<float4>(), npoints.attr->as<float4>(), npoints.np};
             if (n) SR_LAUNCH(c, k_geo_reemit<1>, ceil_div(n, 128), 128, 0, in, o, (uint64_t)0);
         }
         // lines: [generated lines re-emitted | normals of generated triangles | indexed lines re-emitted or normals of indexed triangles]
@@ -1066,7 +1067,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             const uint32_t per_tri = gs == SR_GS_FACE_NORMALS ? 1u : 3u;
             const uint64_t total_lines = (uint64_t)gl.ngen + (uint64_t)gt.ngen * per_tri + il.nidx + (uint64_t)it.nidx * per_tri;
             SR_TRY(alloc_stream(c, total_lines * 2, d->nk, &nlines));
-            SrGeoOut o = {nlines.pos->as<float4>(), nlines.attr->as<float4>(), nlines.stride};
+            SrGeoOut o = {nlines.pos->as<float4>(), nlines.attr->as<float4>(), nlines.np};
             uint64_t base = 0;
             if (gl.ngen) SR_LAUNCH(c, k_geo_reemit<2>, ceil_div(gl.ngen, 128), 128, 0, gl, o, base);
             base += (uint64_t)gl.ngen * 2;
@@ -1244,7 +1245,7 @@ static int upload_records(sr_context *c, const float *verts, uint64_t n, uint32_
     Buf tmp;
     SR_TRY(c->alloc(n * (4 + nk) * 4, &tmp));
     SR_CUDA(cudaMemcpyAsync(tmp->ptr, verts, n * (4 + nk) * 4, cudaMemcpyHostToDevice, c->stream));
-    SR_LAUNCH(c, k_records_to_planes, ceil_div(n, 256), 256, 0, tmp->as<float>(), n, nk, out->pos->as<float4>(), out->attr->as<float4>(), out->stride);
+    SR_LAUNCH(c, k_records_to_planes, ceil_div(n, 256), 256, 0, tmp->as<float>(), n, nk, out->pos->as<float4>(), out->attr->as<float4>(), out->np);
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
@@ -1299,7 +1300,7 @@ int sr_draw_download(sr_draw *d, int which, float *dst, uint64_t capacity_floats
     SR_CUDA(cudaSetDevice(c->device));
     Buf tmp;
     SR_TRY(c->alloc(n * (4 + d->nk) * 4, &tmp));
-    SR_LAUNCH(c, k_planes_to_records, ceil_div(n, 256), 256, 0, s.pos->as<float4>(), s.attr->as<float4>(), s.stride, n, d->nk, tmp->as<float>());
+    SR_LAUNCH(c, k_planes_to_records, ceil_div(n, 256), 256, 0, s.pos->as<float4>(), s.attr->as<float4>(), s.np, n, d->nk, tmp->as<float>());
     SR_CUDA(cudaMemcpyAsync(dst, tmp->ptr, n * (4 + d->nk) * 4, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;

@@ -88,12 +88,26 @@ __device__ __forceinline__ float sr_bary(float u, float ux, float v, float vx, f
 __device__ __forceinline__ float sr_lerp(float t, float x1, float x2) { return (1.0f - t) * x1 + t * x2; }
 
 // ---- vertex storage in HBM ----------------------------------------------------------------------
-// One float4 position per vertex plus ceil(nk/4) float4 attribute planes of `stride` entries each.
+// One float4 position per vertex (its own array: setup and coverage read nothing else) plus one attribute RECORD per
+// vertex: `np` = ceil(nk/4) consecutive float4.  With np = 2 (the shipped shaders: world position + normal) a record is
+// exactly one 32-byte sector and moves with one 256-bit load / store.
 struct SrVertexSet {
     const float4 *pos;
     const float4 *attr;
-    uint64_t stride;
+    uint64_t np;
 };
+__host__ __device__ __forceinline__ uint64_t sr_attr_at(uint64_t np, uint64_t vertex, uint32_t plane) { return vertex * np + plane; }
+// the first two float4 of a vertex's record (np == 2: the whole record) with one 256-bit load
+__device__ __forceinline__ void sr_ldg_record2(const float4 *rec, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(rec));
+}
+__device__ __forceinline__ void sr_stg_record2(float4 *rec, const float4 &a, const float4 &b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rec), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
 // The primitives a fragment stage consumes, in the reference's canonical order
 // (src/pipeline/stages/fragment.rs:268-311): first the indexed mesh primitives, then the generated ones.
 struct SrPrimSource {

@@ -782,19 +782,27 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
                 sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
                 sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+                if (NP == 2 && (vs->np & 1u) == 0) {
+                    // the record's first two float4 are one aligned 32-byte sector: one 256-bit load per vertex
+                    float4 a0, a1, b0, b1, c0, c1;
+                    sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi0, 0), a0, a1);
+                    sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi1, 0), b0, b1);
+                    sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi2, 0), c0, c1);
+                    sv[4] = sr_bary(u, a0.x, v, b0.x, w, c0.x); sv[5] = sr_bary(u, a0.y, v, b0.y, w, c0.y);
+                    sv[6] = sr_bary(u, a0.z, v, b0.z, w, c0.z); sv[7] = sr_bary(u, a0.w, v, b0.w, w, c0.w);
+                    sv[8] = sr_bary(u, a1.x, v, b1.x, w, c1.x); sv[9] = sr_bary(u, a1.y, v, b1.y, w, c1.y);
+                    sv[10] = sr_bary(u, a1.z, v, b1.z, w, c1.z); sv[11] = sr_bary(u, a1.w, v, b1.w, w, c1.w);
+                } else {
 #pragma unroll
-                for (int pl = 0; pl < NP; ++pl) {
-#ifdef SR_EXPERIMENT_NOATTR
-                    const float4 ka = A, kb = B, kc = C;
-#else
-                    const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi0);
-                    const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi1);
-                    const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi2);
-#endif
-                    sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
-                    sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
-                    sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
-                    sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
+                        const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
+                        const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
+                        sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+                        sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                        sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+                        sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                    }
                 }
                 sr_fragment_shader<FS>(p.fs, sv, o);
                 o[4] = sv[2];
@@ -957,8 +965,8 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
     sv[3] = sr_lerp(t, L.ps.w, L.pe.w);
 #pragma unroll
     for (int pl = 0; pl < NP; ++pl) {
-        const float4 ka = __ldg(L.vs->attr + (uint64_t)pl * L.vs->stride + L.vi[0]);
-        const float4 kb = __ldg(L.vs->attr + (uint64_t)pl * L.vs->stride + L.vi[1]);
+        const float4 ka = __ldg(L.vs->attr + sr_attr_at(L.vs->np, L.vi[0], pl));
+        const float4 kb = __ldg(L.vs->attr + sr_attr_at(L.vs->np, L.vi[1], pl));
         sv[4 + pl * 4 + 0] = sr_lerp(t, ka.x, kb.x);
         sv[4 + pl * 4 + 1] = sr_lerp(t, ka.y, kb.y);
         sv[4 + pl * 4 + 2] = sr_lerp(t, ka.z, kb.z);
@@ -1050,7 +1058,7 @@ __device__ __noinline__ void sr_ord_point(const SrOrdCtx &c, uint32_t t) {
     sv[0] = P.x; sv[1] = P.y; sv[2] = P.z; sv[3] = P.w;
 #pragma unroll
     for (int pl = 0; pl < NP; ++pl) {
-        const float4 k = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
+        const float4 k = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
         sv[4 + pl * 4 + 0] = k.x; sv[4 + pl * 4 + 1] = k.y; sv[4 + pl * 4 + 2] = k.z; sv[4 + pl * 4 + 3] = k.w;
     }
     sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, p.point_base + sr_prim_canonical(p.points, t, 0));
@@ -1180,9 +1188,9 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     if (!(sv[2] < 0.0f) || !(sv[2] >= s_depth[li])) continue;
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl) {
-                        const float4 ka = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[0]);
-                        const float4 kb = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[1]);
-                        const float4 kc = __ldg(vs->attr + (uint64_t)pl * vs->stride + vi[2]);
+                        const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
+                        const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi[1], pl));
+                        const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi[2], pl));
                         sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
                         sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
                         sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);

@@ -94,10 +94,10 @@ struct SrMeshView {
 
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
-                                                float4 *attr, const uint64_t ostride) {
+                                                float4 *attr, const uint64_t onp) {
     constexpr int VIN = SrVsInfo<VS>::VIN, NK = SrVsInfo<VS>::NK, NP = (NK + 3) / 4;
     // One vertex per thread: a warp reads 128 contiguous bytes of every SoA input plane and writes 512 contiguous
-    // bytes (32 float4) of every output plane, so every sector that moves is fully used in both directions.
+    // bytes of positions plus 32 contiguous attribute records, so every sector that moves is fully used both ways.
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= m.nverts) return;
     float in[VIN];
@@ -109,14 +109,18 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsCons
     sr_vertex_shader<VS>(c, in, out);
     if (c.normalize) sr_normalize_vertex(c.vpm, out);
     pos[v] = make_float4(out[0], out[1], out[2], out[3]);
+    if (NP == 2) {
+        sr_stg_record2(attr + sr_attr_at(onp, v, 0), make_float4(out[4], out[5], out[6], out[7]), make_float4(out[8], out[9], out[10], out[11]));
+    } else {
 #pragma unroll
-    for (int p = 0; p < NP; ++p)
-        attr[(uint64_t)p * ostride + v] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
+        for (int p = 0; p < NP; ++p)
+            attr[sr_attr_at(onp, v, p)] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
+    }
 }
 
 // SR_VS_PASSTHROUGH (test shader): Vin = {x,y,z,w,k...}, any nk <= SR_MAX_NK; one vertex per thread.
 __global__ void __launch_bounds__(128) k_vertex_passthrough(const __grid_constant__ SrVsConst c, const SrMeshView m,
-                                                            float4 *pos, float4 *attr, const uint64_t ostride) {
+                                                            float4 *pos, float4 *attr, const uint64_t onp) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.nverts) return;
     float p[4];
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(128) k_vertex_passthrough(const __grid_constan
             const uint32_t ch = 4 + pl * 4 + j;
             k[j] = ch < m.vin ? m.planes[(uint64_t)ch * m.pstride + i] : 0.0f;
         }
-        attr[(uint64_t)pl * ostride + i] = make_float4(k[0], k[1], k[2], k[3]);
+        attr[sr_attr_at(onp, i, pl)] = make_float4(k[0], k[1], k[2], k[3]);
     }
 }
 
@@ -155,9 +159,9 @@ __global__ void __launch_bounds__(256) k_aos_to_planes(const float *aos, uint64_
     const uint32_t ch = (uint32_t)(i % nfloats);
     planes[(uint64_t)ch * pstride + v] = aos[i];
 }
-// records {pos4, k[nk]} (AoS) -> pos plane + attribute planes
+// records {pos4, k[nk]} (AoS) -> position array + attribute records
 __global__ void __launch_bounds__(256) k_records_to_planes(const float *rec, uint64_t n, uint32_t nk, float4 *pos, float4 *attr,
-                                                           uint64_t ostride) {
+                                                           uint64_t onp) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *r = rec + i * (4 + nk);
@@ -167,10 +171,10 @@ __global__ void __launch_bounds__(256) k_records_to_planes(const float *rec, uin
         float k[4];
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) k[j] = (p * 4 + j) < nk ? r[4 + p * 4 + j] : 0.0f;
-        attr[(uint64_t)p * ostride + i] = make_float4(k[0], k[1], k[2], k[3]);
+        attr[sr_attr_at(onp, i, p)] = make_float4(k[0], k[1], k[2], k[3]);
     }
 }
-__global__ void __launch_bounds__(256) k_planes_to_records(const float4 *pos, const float4 *attr, uint64_t stride, uint64_t n,
+__global__ void __launch_bounds__(256) k_planes_to_records(const float4 *pos, const float4 *attr, uint64_t anp, uint64_t n,
                                                            uint32_t nk, float *rec) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) k_planes_to_records(const float4 *pos, co
     r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
     const uint32_t np = (nk + 3) / 4;
     for (uint32_t pl = 0; pl < np; ++pl) {
-        const float4 a = attr[(uint64_t)pl * stride + i];
+        const float4 a = attr[sr_attr_at(anp, i, pl)];
         const float k[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
@@ -214,7 +218,7 @@ struct SrGeoIn {
 struct SrGeoOut {
     float4 *pos;
     float4 *attr;
-    uint64_t stride;
+    uint64_t np;
 };
 
 template <int NV>
@@ -226,7 +230,7 @@ __device__ __forceinline__ void sr_geo_load(const SrGeoIn &in, uint32_t prim, fl
         const float4 p = vs.pos[vi];
         rec[k][0] = p.x; rec[k][1] = p.y; rec[k][2] = p.z; rec[k][3] = p.w;
         for (uint32_t pl = 0; pl < in.nplanes; ++pl) {
-            const float4 a = vs.attr[(uint64_t)pl * vs.stride + vi];
+            const float4 a = vs.attr[sr_attr_at(vs.np, vi, pl)];
             rec[k][4 + pl * 4] = a.x; rec[k][5 + pl * 4] = a.y; rec[k][6 + pl * 4] = a.z; rec[k][7 + pl * 4] = a.w;
         }
     }
@@ -234,7 +238,7 @@ __device__ __forceinline__ void sr_geo_load(const SrGeoIn &in, uint32_t prim, fl
 __device__ __forceinline__ void sr_geo_store(const SrGeoOut &out, uint64_t at, const float *rec, uint32_t nplanes) {
     out.pos[at] = make_float4(rec[0], rec[1], rec[2], rec[3]);
     for (uint32_t pl = 0; pl < nplanes; ++pl)
-        out.attr[(uint64_t)pl * out.stride + at] = make_float4(rec[4 + pl * 4], rec[5 + pl * 4], rec[6 + pl * 4], rec[7 + pl * 4]);
+        out.attr[sr_attr_at(out.np, at, pl)] = make_float4(rec[4 + pl * 4], rec[5 + pl * 4], rec[6 + pl * 4], rec[7 + pl * 4]);
 }
 
 // ClippingPlane::has_inside / intersect (src/geometry/clip.rs:33-63)
