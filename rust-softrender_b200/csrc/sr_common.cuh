@@ -85,6 +85,8 @@ __device__ __forceinline__ float sr_hypot32(float x, float y) {
 __device__ __forceinline__ float sr_bary(float u, float ux, float v, float vx, float w, float wx) {
     return (ux * u + vx * v) + wx * w;
 }
+// contracted form for values that only feed lit shading (colour parity 1/255), never position or depth
+__device__ __forceinline__ float sr_bary_fast(float u, float ux, float v, float vx, float w, float wx) { return fmaf(wx, w, fmaf(vx, v, ux * u)); }
 __device__ __forceinline__ float sr_lerp(float t, float x1, float x2) { return (1.0f - t) * x1 + t * x2; }
 
 // ---- vertex storage in HBM ----------------------------------------------------------------------

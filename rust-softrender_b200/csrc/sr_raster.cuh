@@ -782,26 +782,29 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
                 sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
                 sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+                auto KB = [](float u_, float ux, float v_, float vx, float w_, float wx) {
+                    return SrFsInfo<FS>::LIT ? sr_bary_fast(u_, ux, v_, vx, w_, wx) : sr_bary(u_, ux, v_, vx, w_, wx);
+                };
                 if (NP == 2 && (vs->np & 1u) == 0) {
                     // the record's first two float4 are one aligned 32-byte sector: one 256-bit load per vertex
                     float4 a0, a1, b0, b1, c0, c1;
                     sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi0, 0), a0, a1);
                     sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi1, 0), b0, b1);
                     sr_ldg_record2(vs->attr + sr_attr_at(vs->np, vi2, 0), c0, c1);
-                    sv[4] = sr_bary(u, a0.x, v, b0.x, w, c0.x); sv[5] = sr_bary(u, a0.y, v, b0.y, w, c0.y);
-                    sv[6] = sr_bary(u, a0.z, v, b0.z, w, c0.z); sv[7] = sr_bary(u, a0.w, v, b0.w, w, c0.w);
-                    sv[8] = sr_bary(u, a1.x, v, b1.x, w, c1.x); sv[9] = sr_bary(u, a1.y, v, b1.y, w, c1.y);
-                    sv[10] = sr_bary(u, a1.z, v, b1.z, w, c1.z); sv[11] = sr_bary(u, a1.w, v, b1.w, w, c1.w);
+                    sv[4] = KB(u, a0.x, v, b0.x, w, c0.x); sv[5] = KB(u, a0.y, v, b0.y, w, c0.y);
+                    sv[6] = KB(u, a0.z, v, b0.z, w, c0.z); sv[7] = KB(u, a0.w, v, b0.w, w, c0.w);
+                    sv[8] = KB(u, a1.x, v, b1.x, w, c1.x); sv[9] = KB(u, a1.y, v, b1.y, w, c1.y);
+                    sv[10] = KB(u, a1.z, v, b1.z, w, c1.z); sv[11] = KB(u, a1.w, v, b1.w, w, c1.w);
                 } else {
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl) {
                         const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
                         const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
                         const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
-                        sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
-                        sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
-                        sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
-                        sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                        sv[4 + pl * 4 + 0] = KB(u, ka.x, v, kb.x, w, kc.x);
+                        sv[4 + pl * 4 + 1] = KB(u, ka.y, v, kb.y, w, kc.y);
+                        sv[4 + pl * 4 + 2] = KB(u, ka.z, v, kb.z, w, kc.z);
+                        sv[4 + pl * 4 + 3] = KB(u, ka.w, v, kb.w, w, kc.w);
                     }
                 }
                 sr_fragment_shader<FS>(p.fs, sv, o);

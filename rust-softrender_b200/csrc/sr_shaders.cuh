@@ -59,24 +59,29 @@ __device__ __forceinline__ void sr_vertex_shader(const SrVsConst &c, const float
 }
 
 // ---- fragment shaders ---------------------------------------------------------------------------------
-template <int FS> struct SrFsInfo;  // NK = interpolated floats the shader reads; DISCARDS = may return Fragment::Discard
-template <> struct SrFsInfo<SR_FS_FLAT> { static constexpr int NK = 4; static constexpr bool DISCARDS = false; };
-template <> struct SrFsInfo<SR_FS_SUZANNE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false; };
-template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false; };
-template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int NK = 10; static constexpr bool DISCARDS = false; };
-template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false; };
-template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true; };
+// NK = interpolated floats the shader reads; DISCARDS = may return Fragment::Discard; LIT = the colour goes through
+// transcendental shading arithmetic (parity bar 1/255), so the K interpolation feeding it may use FMA contraction; the
+// pass-through test shaders need K bit-exact.
+template <int FS> struct SrFsInfo;
+template <> struct SrFsInfo<SR_FS_FLAT> { static constexpr int NK = 4; static constexpr bool DISCARDS = false, LIT = false; };
+template <> struct SrFsInfo<SR_FS_SUZANNE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false, LIT = true; };
+template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE> { static constexpr int NK = 8; static constexpr bool DISCARDS = false, LIT = true; };
+template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int NK = 10; static constexpr bool DISCARDS = false, LIT = true; };
+template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false, LIT = false; };
+template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true, LIT = false; };
 
 // Fragment-shader arithmetic is NOT on the bit-exact path (colour parity is 1/255 per channel, and the reference's
 // powf is libm's): normalisation uses rsqrtf and powers use exp2(y*log2(x)) on the SFU unless SR_FS_EXACT is set.
 #ifdef SR_FS_EXACT
 __device__ __forceinline__ float sr_fs_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ float sr_fs_dot4(const float *a, const float *b) { return sr_dot4(a, b); }
 __device__ __forceinline__ void sr_fs_normalize4(const float *a, float *out) { sr_normalize4(a, out); }
 __device__ __forceinline__ float sr_fs_div(float a, float b) { return a / b; }
 #else
 __device__ __forceinline__ float sr_fs_pow(float x, float y) { return __powf(x, y); }
+__device__ __forceinline__ float sr_fs_dot4(const float *a, const float *b) { return fmaf(a[3], b[3], fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0]))); }
 __device__ __forceinline__ void sr_fs_normalize4(const float *a, float *out) {
-    const float inv = rsqrtf(sr_dot4(a, a));
+    const float inv = rsqrtf(sr_fs_dot4(a, a));
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = a[i] * inv;
 }
@@ -145,9 +150,9 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
         sr_fs_normalize4(h, halfway);
-        const float NdotL = fmaxf(fminf(sr_dot4(light_dir, normal), 1.0f), 0.0f);
-        const float NdotH = fmaxf(fminf(sr_dot4(normal, halfway), 1.0f), 0.0f);
-        const float VdotH = fmaxf(fminf(sr_dot4(view_dir, halfway), 1.0f), 0.0f);
+        const float NdotL = fmaxf(fminf(sr_fs_dot4(light_dir, normal), 1.0f), 0.0f);
+        const float NdotH = fmaxf(fminf(sr_fs_dot4(normal, halfway), 1.0f), 0.0f);
+        const float VdotH = fmaxf(fminf(sr_fs_dot4(view_dir, halfway), 1.0f), 0.0f);
         const float f = sr_fresnel_schlick(VdotH, 1.45f);
         const float diffuse = NdotL * (1.0f - f);
         const float specular = f * sr_fs_pow(NdotH, 32.0f * 2.0f);
@@ -188,9 +193,9 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
             for (int i = 0; i < 4; ++i) h[i] = light_dir[i] + view_dir[i];
             sr_fs_normalize4(h, halfway);
             const float intensity = sr_fs_div(light.intensity, sr_powi2(light_distance));
-            const float NdotL = sr_saturate(sr_dot4(light_dir, normal));
-            const float NdotH = sr_saturate(sr_dot4(normal, halfway));
-            const float VdotH = sr_saturate(sr_dot4(view_dir, halfway));
+            const float NdotL = sr_saturate(sr_fs_dot4(light_dir, normal));
+            const float NdotH = sr_saturate(sr_fs_dot4(normal, halfway));
+            const float VdotH = sr_saturate(sr_fs_dot4(view_dir, halfway));
             const float f = sr_fresnel_schlick(VdotH, 1.45f);
             const float diffuse = (1.0f - f) * NdotL;
             const float specular = f * sr_powi64(NdotH);
