@@ -672,7 +672,61 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
             unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
             if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
         };
-        for (uint32_t gb = warp * 32; gb < L; gb += SR_OPQ_WARPS * 32) {
+        // Short lists (few, typically big triangles -- e.g. a 1k-triangle model filling the frame): every warp walks the
+        // whole list but sweeps only its own band of tile rows, so the work is balanced whatever the triangle sizes are
+        // and a pixel's key is only ever touched by one warp, in list order per lane: a plain compare-and-store suffices.
+        const bool per_warp = L < SR_OPQ_WARPS * 32;
+        static_assert(SR_TILE_H % SR_OPQ_WARPS == 0, "tile rows split evenly over the warps");
+        constexpr uint32_t RH = SR_TILE_H / SR_OPQ_WARPS;
+        const uint32_t band_lo = y0 + warp * RH, band_hi = min(band_lo + RH - 1, ye);
+        for (uint32_t gb = 0; per_warp && gb < L; gb += 32) {
+            // 32 list entries are fetched lane-parallel (one chain of dependent gathers per 32 triangles, not per triangle)
+            // and then handed round the warp with shuffles
+            float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
+            uint32_t t = 0;
+            if (gb + lane < L) {
+                t = __ldg(p.list + lbeg + gb + lane);
+                const SrVertexSet *vs;
+                uint32_t vi[3];
+                sr_prim_vertices<3>(p.tris, t, vs, vi);
+                A = __ldg(vs->pos + vi[0]); B = __ldg(vs->pos + vi[1]); C = __ldg(vs->pos + vi[2]);
+            }
+            const uint32_t cnt = min(32u, L - gb);
+            for (uint32_t l = 0; l < cnt; ++l) {
+                const uint32_t st = __shfl_sync(0xffffffffu, t, l);
+                const float ax = __shfl_sync(0xffffffffu, A.x, l), ay = __shfl_sync(0xffffffffu, A.y, l), az = __shfl_sync(0xffffffffu, A.z, l);
+                const float bx = __shfl_sync(0xffffffffu, B.x, l), by = __shfl_sync(0xffffffffu, B.y, l), bz = __shfl_sync(0xffffffffu, B.z, l);
+                const float cx = __shfl_sync(0xffffffffu, C.x, l), cy = __shfl_sync(0xffffffffu, C.y, l), cz = __shfl_sync(0xffffffffu, C.z, l);
+                const uint32_t miny = max(sr_clamp_as_int(fminf(fminf(ay, by), cy), 0, H - 1), band_lo);
+                const uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(ay, by), cy), 0, H - 1), band_hi);
+                if (miny > maxy) continue;
+                const uint32_t minx = max(sr_clamp_as_int(fminf(fminf(ax, bx), cx), 0, W - 1), x0);
+                const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(ax, bx), cx), 0, W - 1), xe);
+                if (minx > maxx) continue;
+                const SrTri s = sr_tri_setup(ax, ay, bx, by, cx, cy);
+                // Fixed pixel ownership inside the band: lane -> row lane / LW, columns congruent to lane % LW.  A pixel's
+                // key is therefore only ever read and written by one lane, in list order: no atomics, no warp syncs,
+                // and no per-pixel division.
+                constexpr uint32_t LW = 32 / RH;
+                static_assert(32 % RH == 0, "band rows divide the warp");
+                const uint32_t py = band_lo + lane / LW;
+                if (py >= miny && py <= maxy) {
+                    for (uint32_t px = x0 + ((minx - x0) / LW) * LW + lane % LW; px <= maxx; px += LW) {
+                        if (px < minx) continue;
+                        float nu, nv, u, v, w;
+                        sr_tri_numerators(s, (float)px + 0.5f, (float)py + 0.5f, nu, nv);
+                        if (!sr_tri_inside(s, nu, nv, u, v, w)) continue;
+                        const float z = (az * u + bz * v) + cz * w;
+                        if (!(z < 0.0f)) continue;  // triangle.rs:120
+                        const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(st + 1u);
+                        unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
+                        if (key > *slot) *slot = key;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        for (uint32_t gb = warp * 32; !per_warp && gb < L; gb += SR_OPQ_WARPS * 32) {
             const bool have = gb + lane < L;
             uint32_t t = 0;
             SrTri tr;
