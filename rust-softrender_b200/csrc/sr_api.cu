@@ -237,7 +237,8 @@ static void fill_vs_const(const sr_pipeline *p, const sr_viewport *vp, SrVsConst
     }
 }
 
-static int exclusive_scan(sr_context *c, const uint32_t *in, uint64_t n, uint32_t *out, uint32_t *total_host) {
+// enqueue an exclusive scan; the grand total lands in pinned host word `slot` once the stream gets there
+static int exclusive_scan_async(sr_context *c, const uint32_t *in, uint64_t n, uint32_t *out, int slot) {
     const uint32_t nblocks = std::max(1u, ceil_div(n, SR_SCAN_BLOCK));
     Buf sums, total;
     SR_TRY(c->alloc((size_t)nblocks * 4, &sums));
@@ -245,8 +246,14 @@ static int exclusive_scan(sr_context *c, const uint32_t *in, uint64_t n, uint32_
     SR_LAUNCH(c, k_scan_reduce, nblocks, SR_SCAN_THREADS, 0, in, n, sums->as<uint32_t>());
     SR_LAUNCH(c, k_scan_sums, 1, SR_SCAN_THREADS, 0, sums->as<uint32_t>(), nblocks, total->as<uint32_t>());
     SR_LAUNCH(c, k_scan_apply, nblocks, SR_SCAN_THREADS, 0, in, n, sums->as<uint32_t>(), out);
-    SR_CUDA(cudaMemcpyAsync(total_host, total->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+    SR_CUDA(cudaMemcpyAsync(&c->pinned[slot], total->ptr, 4, cudaMemcpyDeviceToHost, c->stream));
+    return SR_OK;
+}
+static int exclusive_scan(sr_context *c, const uint32_t *in, uint64_t n, uint32_t *out, uint32_t *total_host) {
+    SR_TRY(exclusive_scan_async(c, in, n, out, 3));
     SR_CUDA(cudaStreamSynchronize(c->stream));
+    *total_host = c->pinned[3];
     return SR_OK;
 }
 
@@ -1041,9 +1048,21 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             SR_TRY(c->alloc((size_t)n * 4, &lit_off));
             const uint32_t grid = ceil_div(n, 128);
             SR_LAUNCH(c, k_clip_tri_count, grid, 128, 0, tin, drop, kept->as<uint32_t>(), lit->as<uint32_t>());
-            uint32_t kept_total = 0;
-            SR_TRY(exclusive_scan(c, kept->as<uint32_t>(), n, kept_off->as<uint32_t>(), &kept_total));
-            SR_TRY(exclusive_scan(c, lit->as<uint32_t>(), n, lit_off->as<uint32_t>(), &literal_total));
+            // both scans are enqueued before the one synchronisation that sizes the output stream
+            if (n <= SR_SCAN_BLOCK) {
+                Buf totals;
+                SR_TRY(c->alloc(8, &totals));
+                SR_LAUNCH(c, k_scan_pair_small, 1, SR_SCAN_THREADS, 0, kept->as<uint32_t>(), lit->as<uint32_t>(), n, kept_off->as<uint32_t>(),
+                          lit_off->as<uint32_t>(), totals->as<uint32_t>());
+                if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+                SR_CUDA(cudaMemcpyAsync(&c->pinned[3], totals->ptr, 8, cudaMemcpyDeviceToHost, c->stream));
+            } else {
+                SR_TRY(exclusive_scan_async(c, kept->as<uint32_t>(), n, kept_off->as<uint32_t>(), 3));
+                SR_TRY(exclusive_scan_async(c, lit->as<uint32_t>(), n, lit_off->as<uint32_t>(), 4));
+            }
+            SR_CUDA(cudaStreamSynchronize(c->stream));
+            const uint32_t kept_total = c->pinned[3];
+            literal_total = c->pinned[4];
             SR_TRY(alloc_stream(c, (uint64_t)kept_total * 3, d->nk, &ntris));
             SR_TRY(c->alloc((size_t)std::max(kept_total, 1u) * 4, &nseq));
             SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.np};

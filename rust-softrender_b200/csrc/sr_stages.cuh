@@ -81,6 +81,33 @@ __global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_apply(const uint32_t *
     }
 }
 
+// two independent exclusive scans of at most SR_SCAN_BLOCK elements each in ONE single-block launch (small meshes:
+// the clipper's kept/literal counts; launch latency, not work, dominates there)
+__global__ void __launch_bounds__(SR_SCAN_THREADS) k_scan_pair_small(const uint32_t *a, const uint32_t *b, uint32_t n, uint32_t *oa,
+                                                                     uint32_t *ob, uint32_t *totals) {
+    __shared__ uint32_t ws[32];
+    const uint32_t base = threadIdx.x * SR_SCAN_ITEMS;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+        const uint32_t *in = which ? b : a;
+        uint32_t *out = which ? ob : oa;
+        uint32_t v[SR_SCAN_ITEMS], s = 0;
+#pragma unroll
+        for (int i = 0; i < SR_SCAN_ITEMS; ++i) {
+            v[i] = base + i < n ? in[base + i] : 0;
+            s += v[i];
+        }
+        uint32_t total;
+        uint32_t ex = sr_block_exclusive_scan(s, &total, ws);
+#pragma unroll
+        for (int i = 0; i < SR_SCAN_ITEMS; ++i) {
+            if (base + i < n) out[base + i] = ex;
+            ex += v[i];
+        }
+        if (threadIdx.x == 0) totals[which] = total;
+    }
+}
+
 // =====================================================================================================
 // a2: vertex stage (VertexShader::run / run_to_fragment, src/pipeline/stages/vertex.rs:87-160)
 // One thread shades one vertex (see k_vertex).
