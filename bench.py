@@ -400,18 +400,113 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# config 5: 64-frame turntable of the Suzanne scene (frames/s; frames k % N per GPU)
+# ------------------------------------------------------------------------------------------------------------
+def run_turntable(args):
+    import torch
+    import torch.distributed as dist
+    import softrender_b200 as sr
+    from softrender_b200 import pipeline as P, scenes, sharding
+    import helpers as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    size, nframes = 1024, 64
+    mesh = H.suzanne_mesh()
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    uniforms = [scenes.suzanne_uniforms(size, size, rotation_y=np.deg2rad(3.0 * (k + 1))) for k in range(nframes)]
+    mine = sharding.frames_for_rank(nframes, rank, world)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_binding as ob
+        cores = os.cpu_count() or 1
+        fbo = ob.OracleFramebuffer(size, size)
+        t0 = time.perf_counter()
+        for u in uniforms:
+            fbo.clear(CLEAR)
+            d = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+            d.tile = (128, 128)
+            d.vertex_run(sr.VS_SUZANNE, u, mesh.vertices, nthreads=cores).clip_primitives().finish(vp)
+            d.fragment_run(fbo, sr.FS_SUZANNE, u, nthreads=cores)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"impl": "reference", "metric": "frames/s, 64-frame Suzanne turntable at 1024x1024", "value": nframes / dt,
+                          "unit": "frames/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "turntable", "frames": nframes, "width": size, "height": size, "triangles": mesh.ntris},
+                          "cpu_baseline": {"value": nframes / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                                           "sample": "all 64 frames, restated reference CPU path"},
+                          "e2e": {"value": nframes / dt, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = P.Context(local_rank)
+    fb = P.RenderBuffer.with_dimensions(ctx, size, size)
+    pipe = P.Pipeline.from_framebuffer(fb, uniforms[0])
+    gmesh = P.Mesh(ctx, mesh)
+    host_fb = torch.empty((size * size, 5), dtype=torch.float32).pin_memory().numpy()
+
+    def batch(readback):
+        for k in mine:
+            pipe.set_uniforms(uniforms[k])
+            fb.clear(CLEAR)
+            pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+            if readback:
+                fb.download(host_fb)
+        ctx.synchronize()
+
+    def timed(readback):
+        for _ in range(max(args.warmup, 1)):
+            batch(readback)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            batch(readback)
+        if world > 1:
+            dist.barrier()
+        return sharding.max_over_ranks((time.perf_counter() - t0) / args.steps)
+
+    launches0 = ctx.launch_count()
+    t_res = timed(False)
+    launches = (ctx.launch_count() - launches0) // (args.steps + max(args.warmup, 1)) * args.steps
+    t_e2e = timed(True)
+    if rank == 0:
+        print(json.dumps({"metric": "frames/s, 64-frame Suzanne turntable at 1024x1024", "value": nframes / t_res, "unit": "frames/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": t_res * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "turntable", "frames": nframes, "width": size, "height": size, "triangles": mesh.ntris,
+                                     "path": "render_mesh -> vertex run -> clip_primitives -> finish -> fragment run (examples/suzanne.rs:121-147)",
+                                     "parallelism": f"frames k % {world} per GPU"},
+                          "e2e": {"value": nframes / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 576 * len(mine) * world,
+                                  "d2h_bytes_per_step": size * size * 20 * nframes, "note": "uniform upload + framebuffer read-back per frame"},
+                          "gpu_launches": int(launches)}))
+    for x in (pipe, gmesh, fb):
+        x.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="grid10m", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="grid10m", choices=sorted(CONFIGS) + ["turntable"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=2, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.config == "turntable":
+        run_turntable(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
