@@ -504,7 +504,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
 // per-tile lists of the large triangles + the tile kernel (both skip themselves if the lists do not fit the arena)
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q) {
     if (q->op.ntris)
-        SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(q->op.ntris, 256), 148u * 2u), 256, 0, q->lcount->as<uint32_t>(),
+        SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(q->op.ntris, 8), 148u * 4u), 256, 0, q->lcount->as<uint32_t>(),
                   q->lids->as<uint32_t>(), q->lrects->as<uint32_t>(), q->op.fb.ntx, q->ntiles, q->op.shard_rank, q->op.shard_world,
                   q->off->as<uint32_t>(), q->count->as<uint32_t>(), const_cast<uint32_t *>(q->op.list), q->capacity);
     return launch_opaque_fs(c, q->fs, q->owned, q->op);

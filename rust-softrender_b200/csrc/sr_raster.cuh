@@ -566,12 +566,17 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
         const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
         p.large_ids[slot] = t;
         p.large_rects[slot] = rect;
-        const uint32_t tx0 = rect & 255u, ty0 = (rect >> 8) & 255u, tx1 = (rect >> 16) & 255u, ty1 = rect >> 24;
-        for (uint32_t ty = ty0; ty <= ty1; ++ty)
-            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                const uint32_t tile = ty * p.ntx + tx;
-                if (tile % p.shard_world == p.shard_rank) atomicAdd(p.tile_count + tile, 1u);
-            }
+    }
+    // per-tile counts: the warp walks its large triangles one at a time and spreads each tile rectangle over the lanes
+    // (a big triangle touches hundreds of tiles; one lane issuing that many dependent atomics would be the critical path)
+    for (uint32_t rest = m; rest; rest &= rest - 1) {
+        const uint32_t r = __shfl_sync(0xffffffffu, rect, __ffs(rest) - 1);
+        const uint32_t tx0 = r & 255u, ty0 = (r >> 8) & 255u, tx1 = (r >> 16) & 255u, ty1 = r >> 24;
+        const uint32_t rw = tx1 - tx0 + 1, n = rw * (ty1 - ty0 + 1);
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t tile = (ty0 + i / rw) * p.ntx + tx0 + i % rw;
+            if (tile % p.shard_world == p.shard_rank) atomicAdd(p.tile_count + tile, 1u);
+        }
     }
 }
 
@@ -581,15 +586,17 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
                                                     const uint32_t *tile_off, uint32_t *tile_cursor, uint32_t *list, uint32_t capacity) {
     if (tile_off[ntiles] > capacity) return;  // the lists do not fit: the host re-runs this pass with a larger arena
     const uint32_t n = *large_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t t = large_ids[i], rect = large_rects[i];
+    // one warp per large triangle, its tile rectangle spread over the lanes
+    const uint32_t lane = threadIdx.x & 31, nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += nwarps) {
+        const uint32_t t = large_ids[e], rect = large_rects[e];
         const uint32_t tx0 = rect & 255u, ty0 = (rect >> 8) & 255u, tx1 = (rect >> 16) & 255u, ty1 = rect >> 24;
-        for (uint32_t ty = ty0; ty <= ty1; ++ty)
-            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                const uint32_t tile = ty * ntx + tx;
-                if (tile % shard_world != shard_rank) continue;
-                list[tile_off[tile] + atomicAdd(tile_cursor + tile, 1u)] = t;
-            }
+        const uint32_t rw = tx1 - tx0 + 1, cnt = rw * (ty1 - ty0 + 1);
+        for (uint32_t i = lane; i < cnt; i += 32) {
+            const uint32_t tile = (ty0 + i / rw) * ntx + tx0 + i % rw;
+            if (tile % shard_world != shard_rank) continue;
+            list[tile_off[tile] + atomicAdd(tile_cursor + tile, 1u)] = t;
+        }
     }
 }
 
