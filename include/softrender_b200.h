@@ -58,6 +58,16 @@ int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
  * area = 0 sends every triangle through the tile lists.  Draws onto existing (not freshly cleared) contents
  * use the visibility buffer only from `min_triangles` on.  Results never depend on these values. */
 int sr_context_set_micro(sr_context *, uint32_t area, uint32_t min_triangles, uint32_t precheck);
+/* timeline introspection: time in ms from `base_event` (a cudaEvent_t recorded by the caller, timing enabled) to the
+ * internal stage events of the most recent draw: [0] vertex begin, [1] vertex end, [2] geometry end, [3] fragment begin,
+ * [4] ordered bins end, [7] visibility init end, [5] raster front end (k_micro) end, [6] fragment end; -1 = not recorded */
+int sr_context_stage_timestamps(sr_context *, void *base_event, float ms[8]);
+/* Cross-context ordering for frames in flight (one context = one CUDA stream; the reference has one frame in flight
+ * per pipeline, src/pipeline/stages/*.rs hold `&mut P`).  Work enqueued on `waiter` after this call starts only when
+ * `other` has reached `point`: 0 = everything enqueued on it so far; 1 = the raster front end (per-triangle setup and
+ * small-triangle rasterisation) of its most recent opaque draw -- the software-pipeline schedule "frame n+1's vertex
+ * stage and front end overlap frame n's tile resolve". */
+int sr_context_wait_for(sr_context *waiter, sr_context *other, uint32_t point);
 /* capacity (u32 entries) of the arena that holds the opaque path's per-tile triangle lists.  A draw is enqueued
  * against the current capacity without a host synchronisation; if its lists do not fit, the tile pass skips itself on
  * the device and is enqueued again with a larger arena at the next call that touches the context.

@@ -67,6 +67,8 @@ struct sr_context {
     Buf list_arena;
     uint32_t list_cap = 0;
     struct PendingOpaque *pending = nullptr;
+    cudaEvent_t ev_front = nullptr;               // recorded after the raster front end (k_micro) of the latest opaque draw
+    bool ev_front_valid = false;
     Buf zero_off;                                 // all-zero CSR offsets for empty primitive kinds
     uint32_t zero_off_tiles = 0;
     sr_stage_times times = {};
@@ -468,6 +470,9 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         else SR_LAUNCH(c, k_micro<false>, grid, SR_MICRO_THREADS, 0, mp);
     }
     record(c, 5);
+    if (!c->ev_front) SR_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
+    SR_CUDA(cudaEventRecord(c->ev_front, c->stream));
+    c->ev_front_valid = true;
     SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
     if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
     SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -560,6 +565,7 @@ int sr_context_destroy(sr_context *c) {
     c->free_list.clear();
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    if (c->ev_front) cudaEventDestroy(c->ev_front);
     cudaStreamDestroy(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
@@ -584,6 +590,35 @@ int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, u
     c->micro_area = area;
     c->micro_min_tris = min_triangles;
     c->micro_precheck = precheck ? 1u : 0u;
+    return SR_OK;
+}
+int sr_context_stage_timestamps(sr_context *c, void *base_event, float ms[8]) {
+    if (!c || !base_event || !ms) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(settle(c));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; ++i) {
+        ms[i] = -1.0f;
+        if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], (cudaEvent_t)base_event, c->ev[i]);
+    }
+    return SR_OK;
+}
+int sr_context_wait_for(sr_context *waiter, sr_context *other, uint32_t point) {
+    if (!waiter || !other || point > 1) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad wait");
+    if (waiter == other) return SR_OK;  // one stream: already ordered
+    if (point == 1) {
+        if (other->ev_front_valid) {
+            SR_CUDA(cudaSetDevice(waiter->device));
+            SR_CUDA(cudaStreamWaitEvent(waiter->stream, other->ev_front, 0));
+        }
+        return SR_OK;
+    }
+    cudaEvent_t ev;
+    SR_CUDA(cudaSetDevice(other->device));
+    SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SR_CUDA(cudaEventRecord(ev, other->stream));
+    SR_CUDA(cudaSetDevice(waiter->device));
+    SR_CUDA(cudaStreamWaitEvent(waiter->stream, ev, 0));
+    SR_CUDA(cudaEventDestroy(ev));  // released once the wait has been satisfied
     return SR_OK;
 }
 int sr_context_set_list_capacity(sr_context *c, uint32_t entries) {

@@ -58,6 +58,17 @@ class Context:
         """Tuning of the opaque triangle path (results never depend on it): see sr_context_set_micro."""
         check(lib.sr_context_set_micro(self.h, area, min_triangles, 1 if precheck else 0))
 
+    def stage_timestamps(self, base_event: int):
+        """ms from the caller's cudaEvent_t `base_event` to the stage events of the latest draw (see the C header)."""
+        out = (ctypes.c_float * 8)()
+        check(lib.sr_context_stage_timestamps(self.h, ctypes.c_void_p(base_event), out))
+        return list(out)
+
+    def wait_for(self, other: "Context", point: int = 0):
+        """Work enqueued on this context from now on starts only when `other` has reached `point`
+        (0: everything enqueued so far, 1: the raster front end of its latest opaque draw)."""
+        check(lib.sr_context_wait_for(self.h, other.h, point))
+
     def set_list_capacity(self, entries: int):
         check(lib.sr_context_set_list_capacity(self.h, entries))
 
