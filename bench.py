@@ -32,7 +32,8 @@ CONFIGS = {
     # name: (width, height, nx, ny, layers, seed, near, far)
     "grid10m": (3840, 2160, 1250, 1000, 4, 0x5EED0003, 0.1, 100.0),   # config 3 (the metric's config)
     "grid100m": (7680, 4320, 5000, 2500, 4, 0x5EED0004, 0.1, 100.0),  # config 4
-    "grid1m": (3840, 2160, 395, 316, 4, 0x5EED0003, 0.1, 100.0),      # reduced, for quick checks only
+    "grid1m": (3840, 2160, 395, 316, 4, 0x5EED0003, 0.1, 100.0),      # ~14 px^2 triangles: all through the per-tile lists
+    "grid100k": (3840, 2160, 125, 100, 4, 0x5EED0003, 0.1, 100.0),    # ~145 px^2 triangles
 }
 
 
