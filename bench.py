@@ -189,7 +189,7 @@ def run_ours(args):
     ctx = P.Context(local_rank)
     if os.environ.get("SR_MICRO"):  # tuning experiments only: "area,min_triangles,precheck"
         a, m, pc = (int(x) for x in os.environ["SR_MICRO"].split(","))
-        ctx.set_micro(a, m, bool(pc))
+        ctx.set_micro(a, m, int(pc))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     # every rank owns a framebuffer and the whole mesh (geometry replicated)

@@ -54,6 +54,7 @@ struct sr_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::multimap<size_t, void *> free_list;  // stream-ordered reuse of scratch allocations
+    int sm_count = 148;
     uint32_t shard_rank = 0, shard_world = 1;
     uint64_t launches = 0;
     cudaEvent_t ev[8] = {};  // vertex begin/end, geometry end, fragment begin, bins end, micro end, raster end
@@ -465,9 +466,14 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         mp.large_ids = lids->as<uint32_t>();
         mp.large_rects = lrects->as<uint32_t>();
         mp.tile_count = count->as<uint32_t>();
+        // micro_precheck: bit 0 = per-fragment key pre-check before the atomic, bit 1 = early depth rejection OFF
         const uint32_t grid = ceil_div(tp.ntris, SR_MICRO_THREADS);
-        if (c->micro_precheck) SR_LAUNCH(c, k_micro<true>, grid, SR_MICRO_THREADS, 0, mp);
-        else SR_LAUNCH(c, k_micro<false>, grid, SR_MICRO_THREADS, 0, mp);
+        switch (c->micro_precheck & 3u) {
+            case 0: SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp); break;
+            case 1: SR_LAUNCH(c, (k_micro<true, true>), grid, SR_MICRO_THREADS, 0, mp); break;
+            case 2: SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp); break;
+            default: SR_LAUNCH(c, (k_micro<true, false>), grid, SR_MICRO_THREADS, 0, mp); break;
+        }
     }
     record(c, 5);
     if (!c->ev_front) SR_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
@@ -548,6 +554,7 @@ int sr_context_create(int device, sr_context **out) {
     SR_CUDA(cudaSetDevice(device));
     auto *c = new sr_context();
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) c->sm_count = 148;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -589,7 +596,7 @@ int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, u
     if (area > SR_MICRO_AREA_MAX) return sr_fail(SR_ERR_INVALID_ARGUMENT, "micro area %u > %u", area, SR_MICRO_AREA_MAX);
     c->micro_area = area;
     c->micro_min_tris = min_triangles;
-    c->micro_precheck = precheck ? 1u : 0u;
+    c->micro_precheck = precheck & 3u;
     return SR_OK;
 }
 int sr_context_stage_timestamps(sr_context *c, void *base_event, float ms[8]) {

@@ -438,6 +438,46 @@ __device__ __forceinline__ unsigned long long sr_ld_relaxed_u64(const unsigned l
     return v;
 }
 
+// ---- early depth rejection of a whole small triangle ---------------------------------------------------------
+// A fragment only changes the visibility buffer if its key exceeds the stored one, i.e. if its depth key is >= the
+// stored depth key (triangle.rs:126, `d >= dt`).  Keys only grow while a frame is drawn, so a (possibly stale)
+// read of the candidate pixels' depth keys is a lower bound of what the fragment will meet.  If an upper bound of
+// every depth the triangle can produce is strictly below all of them, none of its fragments can win and the
+// triangle is skipped before any coverage arithmetic.  Upper bound: emitted fragments have finite u, v, w in [0, 1]
+// with |u + v + w - 1| <= 2^-23 (w = fl(fl(1-u)-v)); for z1, z2, z3 < 0 and M = max|zi| the f32 value
+// fl(fl(fl(z1 u) + fl(z2 v)) + fl(z3 w)) is at most zmax + M (2^-23 + 3 * 2^-24) * 1.001 < zmax + M 2^-21; the bound used
+// is fl(zmax + M 2^-20).  Triangles with a vertex at z >= 0 are never rejected here.  Results are bit-identical with
+// or without the rule (tests: test_opaque_path_split_is_invisible, full-size order/idempotence properties).
+__device__ __forceinline__ uint32_t sr_ld_depth_key(const unsigned long long *slot) {
+    uint32_t v;  // high word of the little-endian 64-bit key; L2-coherent load (L1 may hold the previous frame's keys)
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1+4];" : "=r"(v) : "l"(slot) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool sr_micro_occluded(const unsigned long long *vis, uint32_t pitch, int lx, int ly, int hx, int hy, float z1,
+                                                  float z2, float z3) {
+    const float zmax = fmaxf(fmaxf(z1, z2), z3), zmin = fminf(fminf(z1, z2), z3);
+    const float zb = zmax + zmin * -0x1p-20f;
+    if (!(zb < 0.0f)) return false;  // also NaN
+    const uint32_t kb = ~__float_as_uint(zb);  // depth key of a negative value
+    const uint32_t cw = (uint32_t)(hx - lx + 1), ch = (uint32_t)(hy - ly + 1);
+    const unsigned long long *row = vis + (uint32_t)ly * pitch + (uint32_t)lx;
+    uint32_t kmin = 0xFFFFFFFFu;
+    if (cw <= 3 && ch <= 3) {  // the common box: all loads in flight at once
+#pragma unroll
+        for (uint32_t r = 0; r < 3; ++r)
+#pragma unroll
+            for (uint32_t c = 0; c < 3; ++c) {
+                uint32_t k = 0xFFFFFFFFu;
+                if (r < ch && c < cw) k = sr_ld_depth_key(row + r * pitch + c);
+                kmin = min(kmin, k);
+            }
+    } else {
+        for (uint32_t r = 0; r < ch && kmin > kb; ++r, row += pitch)
+            for (uint32_t c = 0; c < cw; ++c) kmin = min(kmin, sr_ld_depth_key(row + c));
+    }
+    return kb < kmin;
+}
+
 // The tightened path of k_micro: |det| in [1, 50], numerators below 2^7, no NaN.  Straight-line body (no divergent
 // branch inside the loop; lanes sit on different triangles, so every branch would be taken by somebody anyway):
 // u, v by the exact-division shortcut, the reduction as a predicated red.global.max.u64.  A numerator below the
@@ -483,18 +523,17 @@ __device__ __forceinline__ bool sr_micro_box(const SrTri &tr, float z1, float z2
     return redo;
 }
 
-#define SR_MICRO_THREADS 256
-template <bool PRECHECK>
-__global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constant__ SrMicroParams p) {
-    const uint32_t t = blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
+// 128-thread CTAs, 12 per SM (40 registers): the finer CTA granularity keeps ~4 more warps resident than 6 x 256
+#define SR_MICRO_THREADS 128
+#define SR_MICRO_MIN_BLOCKS 12
+// Everything k_micro does for one triangle once its three screen positions are known (warp-collective: every lane of
+// the warp calls it, `valid` = the lane holds a triangle).
+template <bool PRECHECK, bool EARLYZ>
+__device__ __forceinline__ void sr_micro_triangle(const SrMicroParams &p, uint32_t t, bool valid, const float4 &A, const float4 &B,
+                                                  const float4 &C, uint32_t lane) {
     bool large = false;
     uint32_t rect = SR_RECT_INVALID;
-    if (t < p.ntris) {
-        const SrVertexSet *vs;
-        uint32_t vi[3];
-        sr_prim_vertices<3>(p.src, t, vs, vi);
-        const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+    if (valid) {
         bool culled = false;
         if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61 (a NaN area is "not negative", like is_sign_negative of the reference's NaN)
             const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
@@ -513,6 +552,7 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
                 const bool one_tile = tx0 == (uint32_t)hx / SR_TILE_W && ty0 == (uint32_t)hy / SR_TILE_H;
                 if (sharded && one_tile && (ty0 * p.ntx + tx0) % p.shard_world != p.shard_rank) return;
                 const bool per_pixel_owner = sharded && !one_tile;
+                if (EARLYZ && !per_pixel_owner && sr_micro_occluded(p.vis, p.ntx * SR_TILE_W, lx, ly, hx, hy, A.z, B.z, C.z)) return;
                 sr_raster_box<decltype(bounded)::value>(
                     tr, A.z, B.z, C.z, (uint32_t)lx, (uint32_t)ly, (uint32_t)(hx - lx + 1), (uint32_t)(hy - ly + 1), t,
                     [&](uint32_t px, uint32_t py, unsigned long long key) {
@@ -531,6 +571,7 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
                 const int hx = min((int)p.width - 1, sr_tight_hi(xmax)), hy = min((int)p.height - 1, sr_tight_hi(ymax));
                 if (lx <= hx && ly <= hy) {
                     if (sharded) raster(std::true_type(), lx, ly, hx, hy);
+                    else if (EARLYZ && sr_micro_occluded(p.vis, p.ntx * SR_TILE_W, lx, ly, hx, hy, A.z, B.z, C.z)) {}
                     else if (sr_micro_box(tr, A.z, B.z, C.z, lx, ly, hx, hy, t, p.vis, p.ntx * SR_TILE_W)) raster(std::false_type(), lx, ly, hx, hy);
                 }
             } else if (!(isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y))) {
@@ -578,6 +619,20 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS) k_micro(const __grid_constan
             if (tile % p.shard_world == p.shard_rank) atomicAdd(p.tile_count + tile, 1u);
         }
     }
+}
+
+// one thread per triangle, in submission order
+template <bool PRECHECK, bool EARLYZ>
+__global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro(const __grid_constant__ SrMicroParams p) {
+    const uint32_t t = blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
+    float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
+    if (t < p.ntris) {
+        const SrVertexSet *vs;
+        uint32_t vi[3];
+        sr_prim_vertices<3>(p.src, t, vs, vi);
+        A = __ldg(vs->pos + vi[0]); B = __ldg(vs->pos + vi[1]); C = __ldg(vs->pos + vi[2]);
+    }
+    sr_micro_triangle<PRECHECK, EARLYZ>(p, t, t < p.ntris, A, B, C, threadIdx.x & 31);
 }
 
 // second pass over the large triangles only: write their ids into the per-tile lists

@@ -260,7 +260,7 @@ def test_second_draw_uses_existing_depth(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="two draws")
 
 
-@pytest.mark.parametrize("area,min_tris,precheck", [(0, 65536, True), (16, 0, True), (64, 0, False), (4096, 0, True), (1, 0, True)])
+@pytest.mark.parametrize("area,min_tris,precheck", [(0, 65536, 1), (16, 0, 1), (16, 0, 0), (16, 0, 2), (64, 0, 0), (64, 0, 3), (4096, 0, 1), (4096, 0, 0), (1, 0, 1)])
 def test_opaque_path_split_is_invisible(P, ctx, area, min_tris, precheck):
     """The opaque path sends small triangles through the visibility buffer (k_micro) and the rest through per-tile
     lists; where the split lies (and whether a second draw re-initialises the keys from the stored depth) must not
@@ -649,7 +649,7 @@ def test_full_size_grid10m_properties(P, ctx, grid10m):
     H.assert_bits_equal(twice, ref, "second identical draw")
     assert np.array_equal(win2, win)
     # (2)
-    ctx.set_micro(0, 65536, False)
+    ctx.set_micro(0, 65536, 0)
     try:
         lists_only, win3 = _draw_grid(P, ctx, gmesh, w, h, vp, u)
     finally:
