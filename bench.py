@@ -396,8 +396,11 @@ def run_ours(args):
             line["cpu_baseline"], _, _ = cpu_reference_sample(args.config)
         print(json.dumps(line))
     barrier()
-    for x in (pipe, gmesh, fb):
-        x.destroy()
+    for cx, lfb, lp, lm, _ in lanes:
+        lp.destroy()
+        lm.destroy()
+        lfb.destroy()
+        cx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -448,20 +451,33 @@ def run_turntable(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = P.Context(local_rank)
-    fb = P.RenderBuffer.with_dimensions(ctx, size, size)
-    pipe = P.Pipeline.from_framebuffer(fb, uniforms[0])
-    gmesh = P.Mesh(ctx, mesh)
-    host_fb = torch.empty((size * size, 5), dtype=torch.float32).pin_memory().numpy()
+    # Frames are independent, so `depth` of them are in flight per GPU: one context (= CUDA stream, framebuffer, host
+    # thread) each; the C ABI releases the GIL.  Every frame is still a full clear + draw (+ read-back for e2e).
+    depth = max(1, args.in_flight)
+    lanes = []
+    for k in range(depth):
+        cx = P.Context(local_rank)
+        lfb = P.RenderBuffer.with_dimensions(cx, size, size)
+        lanes.append((cx, lfb, P.Pipeline.from_framebuffer(lfb, uniforms[0]), P.Mesh(cx, mesh),
+                      torch.empty((size * size, 5), dtype=torch.float32).pin_memory().numpy()))
+    ctx = lanes[0][0]
+
+    def lane_frames(lane, frames, readback):
+        cx, lfb, lp, lm, host_fb = lane
+        for k in frames:
+            lp.set_uniforms(uniforms[k])
+            lfb.clear(CLEAR)
+            lp.render_mesh(sr.TRIANGLE, lm).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+            if readback:
+                lfb.download(host_fb)
+        cx.synchronize()
 
     def batch(readback):
-        for k in mine:
-            pipe.set_uniforms(uniforms[k])
-            fb.clear(CLEAR)
-            pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
-            if readback:
-                fb.download(host_fb)
-        ctx.synchronize()
+        threads = [threading.Thread(target=lane_frames, args=(lane, mine[i::depth], readback)) for i, lane in enumerate(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
 
     def timed(readback):
         for _ in range(max(args.warmup, 1)):
@@ -475,9 +491,12 @@ def run_turntable(args):
             dist.barrier()
         return sharding.max_over_ranks((time.perf_counter() - t0) / args.steps)
 
-    launches0 = ctx.launch_count()
+    def launch_total():
+        return sum(lane[0].launch_count() for lane in lanes)
+
+    launches0 = launch_total()
     t_res = timed(False)
-    launches = (ctx.launch_count() - launches0) // (args.steps + max(args.warmup, 1)) * args.steps
+    launches = (launch_total() - launches0) // (args.steps + max(args.warmup, 1)) * args.steps
     t_e2e = timed(True)
     if rank == 0:
         print(json.dumps({"metric": "frames/s, 64-frame Suzanne turntable at 1024x1024", "value": nframes / t_res, "unit": "frames/s",
@@ -485,12 +504,15 @@ def run_turntable(args):
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "turntable", "frames": nframes, "width": size, "height": size, "triangles": mesh.ntris,
                                      "path": "render_mesh -> vertex run -> clip_primitives -> finish -> fragment run (examples/suzanne.rs:121-147)",
-                                     "parallelism": f"frames k % {world} per GPU"},
+                                     "parallelism": f"frames k % {world} per GPU", "frames_in_flight": depth},
                           "e2e": {"value": nframes / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 576 * len(mine) * world,
                                   "d2h_bytes_per_step": size * size * 20 * nframes, "note": "uniform upload + framebuffer read-back per frame"},
                           "gpu_launches": int(launches)}))
-    for x in (pipe, gmesh, fb):
-        x.destroy()
+    for cx, lfb, lp, lm, _ in lanes:
+        lp.destroy()
+        lm.destroy()
+        lfb.destroy()
+        cx.close()
     if world > 1:
         dist.destroy_process_group()
 
