@@ -92,6 +92,11 @@ int sr_framebuffer_dimensions(const sr_framebuffer *, uint32_t *width, uint32_t 
 /* read-back of the RenderBuffer's Vec<{color,depth}>: row-major, index = x + y*width
  * (src/geometry/coordinate.rs:47-51), 20 B/pixel {r,g,b,a,depth}. nbytes must be width*height*20. */
 int sr_framebuffer_download(sr_framebuffer *, void *dst, size_t nbytes);
+/* presentation read-back: the loop of realtime_example/src/main.rs:100-116, `(c.r * 255.0) as u8` per channel
+ * (truncating, saturating, NaN -> 0), converted on the device so that 4 instead of 20 bytes per pixel cross PCIe.
+ * order 0: bytes r,g,b,a (image crate Rgba<u8>, src/image/color.rs:60-90); order 1: a,b,g,r (the example's SDL
+ * RGBA8888 streaming texture).  nbytes must be width*height*4. */
+int sr_framebuffer_download_rgba8(sr_framebuffer *, uint8_t *dst, size_t nbytes, uint32_t order);
 /* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL */
 int sr_framebuffer_download_planes(sr_framebuffer *, float *color, float *depth, uint8_t *stencil);
 int sr_framebuffer_upload_planes(sr_framebuffer *, const float *color, const float *depth, const uint8_t *stencil);

@@ -717,6 +717,21 @@ int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
     SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
     return SR_OK;
 }
+int sr_framebuffer_download_rgba8(sr_framebuffer *fb, uint8_t *dst, size_t nbytes, uint32_t order) {
+    if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    if (nbytes != n * 4) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, (size_t)(n * 4));
+    if (order > 1) return sr_fail(SR_ERR_INVALID_ARGUMENT, "byte order %u", order);
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    Buf packed;
+    SR_TRY(c->alloc(n * 4, &packed));
+    SR_LAUNCH(c, k_fb_to_rgba8, ceil_div(ceil_div(n, 4), 256), 256, 0, fb->aos, n, order, packed->as<uint32_t>());
+    SR_CUDA(cudaMemcpyAsync(dst, packed->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    return SR_OK;
+}
 int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *depth, uint8_t *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     sr_context *c = fb->ctx;

@@ -62,6 +62,18 @@ __device__ __forceinline__ float sr_dot4(const float *a, const float *b) {
     for (int i = 0; i < 4; ++i) acc = acc + a[i] * b[i];
     return acc;
 }
+// Correctly rounded n/det without the generic division sequence.  r = RN(1/det); after one
+// Newton correction q is within one ulp of n/det, the residual n - q*det is then exact in an FMA, and
+// q' = RN(q + rem*r) is the correctly rounded quotient (Markstein's theorem).  Valid for |det| in
+// [2^-40, 2^40] and |n| in [2^-60, 2^60] (no over/underflow anywhere); checked against __fdiv_rn on the GPU
+// by tests/test_gpu_parity.py::test_exact_division_shortcut.
+__device__ __forceinline__ float sr_div_exact(float n, float det, float rdet) {
+    float q = n * rdet;
+    float rem = fmaf(-q, det, n);
+    q = fmaf(rem, rdet, q);
+    rem = fmaf(-q, det, n);
+    return fmaf(rem, rdet, q);
+}
 __device__ __forceinline__ float sr_norm4(const float *a) { return sqrtf(sr_dot4(a, a)); }
 __device__ __forceinline__ void sr_normalize4(const float *a, float *out) {
     const float n = sr_norm4(a);

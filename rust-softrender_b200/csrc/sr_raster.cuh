@@ -199,18 +199,6 @@ __device__ __forceinline__ SrTri sr_tri_setup(float x1, float y1, float x2, floa
     t.rdet = __frcp_rn(t.det);
     return t;
 }
-// Correctly rounded n/det without the generic division sequence.  r = RN(1/det); after one
-// Newton correction q is within one ulp of n/det, the residual n - q*det is then exact in an FMA, and
-// q' = RN(q + rem*r) is the correctly rounded quotient (Markstein's theorem).  Valid for |det| in
-// [2^-40, 2^40] and |n| in [2^-60, 2^60] (no over/underflow anywhere); checked against __fdiv_rn on the GPU
-// by tests/test_gpu_parity.py::test_exact_division_shortcut.
-__device__ __forceinline__ float sr_div_exact(float n, float det, float rdet) {
-    float q = n * rdet;
-    float rem = fmaf(-q, det, n);
-    q = fmaf(rem, rdet, q);
-    rem = fmaf(-q, det, n);
-    return fmaf(rem, rdet, q);
-}
 // numerators of u and v at pixel centre (x,y) (triangle.rs:108-109)
 __device__ __forceinline__ void sr_tri_numerators(const SrTri &t, float x, float y, float &nu, float &nv) {
     const float dx = x - t.x3, dy = y - t.y3;
@@ -1407,6 +1395,29 @@ __global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
     dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
     if (fb.stencil) fb.stencil[i] = 0;
     if (fb.winner) fb.winner[i] = 0;
+}
+// realtime_example/src/main.rs:100-116: the presentation loop `(c.x * 255.0) as u8` per channel.  Rust's float -> u8 `as`
+// cast truncates toward zero and saturates (NaN -> 0), which is what cvt.rzi.u32.f32 + min does.  order 0: bytes r,g,b,a;
+// order 1: a,b,g,r (what the example writes into SDL's RGBA8888 streaming texture).
+// Four pixels per thread: 80 contiguous bytes in (five 128-bit loads), 16 bytes out.
+__device__ __forceinline__ uint32_t sr_as_u8(float c) { return min(__float2uint_rz(c * 255.0f), 255u); }
+__global__ void __launch_bounds__(256) k_fb_to_rgba8(const float *aos, uint64_t n, uint32_t order, uint32_t *out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel quad
+    if (q * 4 >= n) return;
+    auto pack = [&](float r, float g, float b, float a) {
+        const uint32_t R = sr_as_u8(r), G = sr_as_u8(g), B = sr_as_u8(b), A = sr_as_u8(a);
+        return order ? (A | (B << 8) | (G << 16) | (R << 24)) : (R | (G << 8) | (B << 16) | (A << 24));
+    };
+    if (q * 4 + 4 <= n && (reinterpret_cast<uintptr_t>(aos) & 15u) == 0) {
+        const float4 *src = reinterpret_cast<const float4 *>(aos + q * 20);
+        const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1), v2 = __ldcs(src + 2), v3 = __ldcs(src + 3), v4 = __ldcs(src + 4);
+        // pixels: {v0.x v0.y v0.z v0.w | v1.x} {v1.y v1.z v1.w v2.x | v2.y} {v2.z v2.w v3.x v3.y | v3.z} {v3.w v4.x v4.y v4.z | v4.w}
+        const uint4 o = make_uint4(pack(v0.x, v0.y, v0.z, v0.w), pack(v1.y, v1.z, v1.w, v2.x), pack(v2.z, v2.w, v3.x, v3.y),
+                                   pack(v3.w, v4.x, v4.y, v4.z));
+        *reinterpret_cast<uint4 *>(out + q * 4) = o;
+    } else {
+        for (uint64_t i = q * 4; i < n && i < q * 4 + 4; ++i) out[i] = pack(aos[i * 5], aos[i * 5 + 1], aos[i * 5 + 2], aos[i * 5 + 3]);
+    }
 }
 __global__ void __launch_bounds__(256) k_fb_split(const float *aos, uint64_t n, float *color, float *depth) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -94,6 +94,22 @@ class Context:
         return {k: getattr(t, k) for k, _ in t._fields_}
 
 
+def write_png(path: str, rgba: np.ndarray):
+    """Minimal RGBA8 PNG writer (filter type 0 on every row)."""
+    import struct
+    import zlib
+    h, w, ch = rgba.shape
+    assert ch == 4 and rgba.dtype == np.uint8
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), np.ascontiguousarray(rgba).reshape(h, w * 4)], axis=1).tobytes()
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
 def tile_size():
     w, h = ctypes.c_uint32(), ctypes.c_uint32()
     check(lib.sr_tile_size(ctypes.byref(w), ctypes.byref(h)))
@@ -132,6 +148,23 @@ class RenderBuffer:
             out = np.empty((n, 5), np.float32)
         check(lib.sr_framebuffer_download(self.h, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
         return out
+
+    def download_rgba8(self, out: Optional[np.ndarray] = None, abgr: bool = False) -> np.ndarray:
+        """Presentation read-back, uint8 [height, width, 4]: `(c * 255.0) as u8` per channel, converted on the device
+        (realtime_example/src/main.rs:100-116).  abgr=True gives the byte order the example writes for SDL."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
+        check(lib.sr_framebuffer_download_rgba8(self.h, out.ctypes.data_as(_abi.u8p), out.nbytes, 1 if abgr else 0))
+        return out
+
+    def copy_to_image(self) -> np.ndarray:
+        """RenderBuffer::copy_to_image of the reference's `image_compat` feature (examples/suzanne.rs:186-193):
+        an RGBA8 image, row-major, top row first."""
+        return self.download_rgba8()
+
+    def save_png(self, path: str):
+        """`image.save(path)` of examples/suzanne.rs:191 (8-bit RGBA PNG, zlib from the Python standard library)."""
+        write_png(path, self.copy_to_image())
 
     def download_planes(self, stencil: bool = False):
         n = self.width * self.height

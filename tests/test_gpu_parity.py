@@ -689,6 +689,55 @@ def test_full_size_grid10m_reverse_order(P, ctx):
     assert same.mean() > 0.9999, f"{(~same).sum()} depth values differ between submission orders"
 
 
+def test_presentation_readback_rgba8(P, ctx, tmp_path):
+    """sr_framebuffer_download_rgba8 = the loop of realtime_example/src/main.rs:100-116, `(c * 255.0) as u8` per channel
+    (truncating, saturating, NaN -> 0), both byte orders; checked on hostile colour values and on a rendered frame,
+    and the PNG written from it decodes back to the same bytes."""
+    w, h = 37, 19  # odd size: exercises the non-vectorised tail
+    rng = np.random.default_rng(5)
+    color = rng.uniform(-0.5, 1.5, (w * h, 4)).astype(np.float32)
+    color[:12, 0] = [0.0, -0.0, 1.0, 0.999999, 1.0 / 255.0, 254.999 / 255.0, np.nan, np.inf, -np.inf, 1e30, -1e30, 0.5]
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)
+    fb.upload_planes(color=color, depth=np.zeros(w * h, np.float32))
+    with np.errstate(invalid="ignore", over="ignore"):
+        scaled = color * np.float32(255.0)
+        expect = np.where(np.isnan(scaled), 0.0, np.clip(np.trunc(scaled), 0.0, 255.0)).astype(np.uint8).reshape(h, w, 4)
+    assert np.array_equal(fb.download_rgba8(), expect)
+    assert np.array_equal(fb.download_rgba8(abgr=True), expect[..., ::-1])
+    fb.clear(H.CLEAR)  # a pending (lazy) clear must be visible too
+    assert np.array_equal(fb.download_rgba8()[0, 0], (np.asarray(H.CLEAR, np.float32) * np.float32(255)).astype(np.uint8))
+    fb.destroy()
+    # a rendered frame, 4-pixel vector path (width % 4 == 0), and the PNG round trip
+    size = 64
+    mesh = H.suzanne_mesh()
+    from softrender_b200 import scenes
+    import softrender_b200 as sr
+    fb = P.RenderBuffer.with_dimensions(ctx, size, size)
+    fb.clear(H.CLEAR)
+    pipe = P.Pipeline.from_framebuffer(fb, scenes.suzanne_uniforms(size, size))
+    gm = P.Mesh(ctx, mesh)
+    pipe.render_mesh(sr.TRIANGLE, gm).run_to_fragment(scenes.Viewport.new(size, size, 0.001, 1000.0), sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    f32 = fb.download()[:, :4].reshape(size, size, 4)
+    img = fb.copy_to_image()
+    assert np.array_equal(img, np.clip(np.trunc(f32 * np.float32(255.0)), 0, 255).astype(np.uint8))
+    assert (img[..., :3].max(axis=-1) > 60).sum() > 200  # the model is there
+    path = tmp_path / "frame.png"
+    fb.save_png(str(path))
+    import struct, zlib
+    blob = path.read_bytes()
+    assert blob[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", blob[16:24]) == (size, size)
+    pos, idat = 8, b""
+    while pos < len(blob):
+        n, tag = struct.unpack(">I", blob[pos:pos + 4])[0], blob[pos + 4:pos + 8]
+        assert zlib.crc32(blob[pos + 4:pos + 8 + n]) & 0xFFFFFFFF == struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])[0]
+        if tag == b"IDAT":
+            idat += blob[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(size, 1 + size * 4)
+    assert np.array_equal(rows[:, 1:].reshape(size, size, 4), img) and not rows[:, 0].any()
+    pipe.destroy(); gm.destroy(); fb.destroy()
+
+
 def test_exact_division_shortcut(P, ctx):
     """The coverage path replaces `n / det` by a reciprocal + two FMA corrections; it must be the IEEE quotient,
     bit for bit, over its whole validity range (4e9 random operand pairs incl. all-ones/sparse mantissas)."""
