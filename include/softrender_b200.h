@@ -55,10 +55,12 @@ void *sr_context_stream(sr_context *);
 int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
 /* tuning of the opaque triangle path: triangles whose frame-clamped bounding box holds at most
  * `area` pixels are rasterised per-triangle into the visibility buffer, the rest through per-tile lists.
- * area = 0 sends every triangle through the tile lists.  Draws onto existing (not freshly cleared) contents
+ * area = 0 sends every triangle through the tile lists; area = SR_MICRO_AREA_AUTO (the default) lets the library pick
+ * the split per draw from the triangle count.  Draws onto existing (not freshly cleared) contents
  * use the visibility buffer only from `min_triangles` on.  `precheck` bit 0: read a pixel's key before the atomic
  * (measured slower); bit 1: switch OFF the early depth rejection of whole small triangles.  Results never depend on
  * these values. */
+#define SR_MICRO_AREA_AUTO 0xFFFFFFFFu
 int sr_context_set_micro(sr_context *, uint32_t area, uint32_t min_triangles, uint32_t precheck);
 /* timeline introspection: time in ms from `base_event` (a cudaEvent_t recorded by the caller, timing enabled) to the
  * internal stage events of the most recent draw: [0] vertex begin, [1] vertex end, [2] geometry end, [3] fragment begin,

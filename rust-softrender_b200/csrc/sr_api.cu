@@ -60,6 +60,7 @@ struct sr_context {
     cudaEvent_t ev[8] = {};  // vertex begin/end, geometry end, fragment begin, bins end, micro end, raster end
     bool ev_valid[8] = {};
     uint32_t micro_area = SR_MICRO_AREA_DEFAULT;  // bbox pixels up to which k_micro rasterises a triangle itself (0: off)
+    bool micro_auto = true;                       // choose the split per draw from the triangle count (sr_micro_area_for)
     uint32_t micro_min_tris = 65536;              // draws onto existing contents use the visibility buffer from this size on
     uint32_t micro_precheck = 0;  // read the key before the atomic: measured slower (load latency inside the per-lane loop)
     uint32_t *pinned = nullptr;                   // pinned host words for device->host counters
@@ -423,13 +424,21 @@ static int settle(sr_context *c) {
     return launch_opaque_pass(c, q);
 }
 
+// Where the split between the per-triangle front end and the per-tile lists lies.  One thread walking a whole bounding box
+// is the cheapest way through a triangle as long as there are enough triangles to fill the machine (148 SMs x 2048
+// threads); below that the serial walks are the critical path and the tile kernel's cooperative sweep wins.  Measured
+// on 4-layer grids at 3840x2160 (scratch/area_sweep.py): 52k triangles of 280 px^2: 0.30 ms at area 16, 0.28 ms at 1024;
+// 100k x 146 px^2: 0.36 -> 0.25; 207k x 70 px^2: 0.46 -> 0.23; 1M x 15 px^2: 0.67 -> 0.23; 31k x 464 px^2: 0.27 -> 0.33.
+static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 1024u : SR_MICRO_AREA_DEFAULT; }
+
 // The opaque triangle path (sr_raster.cuh): visibility-buffer init, k_micro (per-triangle setup + direct
 // rasterisation of small triangles + compaction/counting of the large ones), per-tile lists of the large
 // triangles, then the tile kernel (large triangles + resolve + single write-back).
 static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
                             const std::vector<Buf> &keep) {
     const uint32_t ntiles = fb->ntx * fb->nty;
-    const bool use_micro = c->micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
+    const uint32_t micro_area = c->micro_auto ? sr_micro_area_for(tp.ntris) : c->micro_area;
+    const bool use_micro = micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
     if (use_micro) {
         if (!fb->vis_buf) {
             SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
@@ -460,7 +469,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         mp.cull = cull;
         mp.width = fb->width; mp.height = fb->height; mp.ntx = fb->ntx; mp.nty = fb->nty;
         mp.shard_rank = c->shard_rank; mp.shard_world = c->shard_world;
-        mp.micro_area = use_micro ? c->micro_area : 0u;
+        mp.micro_area = use_micro ? micro_area : 0u;
         mp.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
         mp.large_count = lcount->as<uint32_t>();
         mp.large_ids = lids->as<uint32_t>();
@@ -593,8 +602,9 @@ int sr_context_set_tile_shard(sr_context *c, uint32_t rank, uint32_t world) {
 }
 int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, uint32_t precheck) {
     if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null context");
-    if (area > SR_MICRO_AREA_MAX) return sr_fail(SR_ERR_INVALID_ARGUMENT, "micro area %u > %u", area, SR_MICRO_AREA_MAX);
-    c->micro_area = area;
+    if (area != SR_MICRO_AREA_AUTO && area > SR_MICRO_AREA_MAX) return sr_fail(SR_ERR_INVALID_ARGUMENT, "micro area %u > %u", area, SR_MICRO_AREA_MAX);
+    c->micro_auto = area == SR_MICRO_AREA_AUTO;
+    if (!c->micro_auto) c->micro_area = area;
     c->micro_min_tris = min_triangles;
     c->micro_precheck = precheck & 3u;
     return SR_OK;

@@ -54,7 +54,7 @@ class Context:
     def set_tile_shard(self, rank: int, world: int):
         check(lib.sr_context_set_tile_shard(self.h, rank, world))
 
-    def set_micro(self, area: int = 16, min_triangles: int = 65536, precheck: int = 0):
+    def set_micro(self, area: int = 0xFFFFFFFF, min_triangles: int = 65536, precheck: int = 0):
         """Tuning of the opaque triangle path (results never depend on it): see sr_context_set_micro.
         precheck: bit 0 = per-fragment key pre-check, bit 1 = early depth rejection off (library default 0)."""
         check(lib.sr_context_set_micro(self.h, area, min_triangles, int(precheck) & 3))

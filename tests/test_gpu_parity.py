@@ -282,6 +282,20 @@ def test_opaque_path_split_is_invisible(P, ctx, area, min_tris, precheck):
     H.compare_framebuffers(out, ofb, exact_color=True, what=f"micro area {area}")
 
 
+def test_auto_split_many_mid_size_triangles(P, ctx):
+    """From 49152 triangles on the library lets the per-triangle front end walk boxes of up to 1024 pixels (the default
+    `SR_MICRO_AREA_AUTO` split, sr_micro_area_for): 60k triangles of up to ~30x30 pixels with exact depth ties, drawn
+    twice, must still match the oracle bit for bit (winner ids, depth, flat colour)."""
+    rng = np.random.default_rng(4242)
+    w, h, n = 640, 360, 60000
+    verts = H.random_screen_triangles(rng, n, w, h, max_size=30.0, integer_depth=True)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    ctx.set_micro()  # auto
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, draws=2)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="auto split")
+
+
 def test_list_arena_overflow_is_replayed(P, ctx):
     """The opaque path enqueues a draw against the current per-tile list capacity without synchronising; when the
     lists do not fit, the tile pass skips itself on the device and is replayed with a larger arena.  Two draws back
