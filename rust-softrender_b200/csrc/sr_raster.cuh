@@ -651,7 +651,11 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
 #endif
 #define SR_OPQ_WARPS (SR_OPQ_THREADS / 32)
 #define SR_OPQ_STAGE_FLOATS (32 * 5)  // one warp's 32 finished pixels, AoS {r,g,b,a,depth}
-#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4 + SR_TILE_W * 8 + 16)
+// the short-list sweep's triangle records and the resolve's staging buffers share one region
+#define SR_OPQ_SWEEP_BYTES (SR_OPQ_WARPS * 32 * 64)
+#define SR_OPQ_STAGE_BYTES (SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4)
+#define SR_OPQ_REGION_BYTES (SR_OPQ_SWEEP_BYTES > SR_OPQ_STAGE_BYTES ? SR_OPQ_SWEEP_BYTES : SR_OPQ_STAGE_BYTES)
+#define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_REGION_BYTES + SR_TILE_W * 8 + 16)
 static_assert(SR_TILE_W % 32 == 0, "a warp resolves 32 consecutive pixels of one tile row");
 
 struct SrOpaqueParams {
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
     float *stage_all = reinterpret_cast<float *>(keys + SR_TILE_PIXELS);
-    unsigned long long *far_row = reinterpret_cast<unsigned long long *>(stage_all + SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS);
+    unsigned long long *far_row = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(stage_all) + SR_OPQ_REGION_BYTES);
     uint64_t *bar = reinterpret_cast<uint64_t *>(far_row + SR_TILE_W);
 
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
@@ -729,49 +733,59 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         static_assert(SR_TILE_H % SR_OPQ_WARPS == 0, "tile rows split evenly over the warps");
         constexpr uint32_t RH = SR_TILE_H / SR_OPQ_WARPS;
         const uint32_t band_lo = y0 + warp * RH, band_hi = min(band_lo + RH - 1, ye);
-        for (uint32_t gb = 0; per_warp && gb < L; gb += 32) {
-            // 32 list entries are fetched lane-parallel (one chain of dependent gathers per 32 triangles, not per triangle)
-            // and then handed round the warp with shuffles
-            float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
-            uint32_t t = 0;
-            if (gb + lane < L) {
-                t = __ldg(p.list + lbeg + gb + lane);
+        if (per_warp) {
+            // Setup once per triangle (one thread each: the chain of dependent gathers runs once per list, not per warp),
+            // published as a 64-byte record; a triangle that misses the tile gets an empty row range.
+            float4 *s_rec = reinterpret_cast<float4 *>(stage_all);  // aliases the resolve's staging buffers (used after the sweep)
+            if (tid < L) {
+                const uint32_t t = __ldg(p.list + lbeg + tid);
                 const SrVertexSet *vs;
                 uint32_t vi[3];
                 sr_prim_vertices<3>(p.tris, t, vs, vi);
-                A = __ldg(vs->pos + vi[0]); B = __ldg(vs->pos + vi[1]); C = __ldg(vs->pos + vi[2]);
+                const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+                uint32_t minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
+                uint32_t miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
+                const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
+                uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
+                if (minx > maxx) { miny = 1; maxy = 0; }
+                const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+                s_rec[tid * 4 + 0] = make_float4(tr.a, tr.b, tr.c, tr.d);
+                s_rec[tid * 4 + 1] = make_float4(tr.x3, tr.y3, tr.det, tr.rdet);
+                s_rec[tid * 4 + 2] = make_float4(A.z, B.z, C.z, __uint_as_float(t + 1u));
+                s_rec[tid * 4 + 3] = make_float4(__uint_as_float(minx | (maxx << 16)), __uint_as_float(miny | (maxy << 16)), 0.0f, 0.0f);
             }
-            const uint32_t cnt = min(32u, L - gb);
-            for (uint32_t l = 0; l < cnt; ++l) {
-                const uint32_t st = __shfl_sync(0xffffffffu, t, l);
-                const float ax = __shfl_sync(0xffffffffu, A.x, l), ay = __shfl_sync(0xffffffffu, A.y, l), az = __shfl_sync(0xffffffffu, A.z, l);
-                const float bx = __shfl_sync(0xffffffffu, B.x, l), by = __shfl_sync(0xffffffffu, B.y, l), bz = __shfl_sync(0xffffffffu, B.z, l);
-                const float cx = __shfl_sync(0xffffffffu, C.x, l), cy = __shfl_sync(0xffffffffu, C.y, l), cz = __shfl_sync(0xffffffffu, C.z, l);
-                const uint32_t miny = max(sr_clamp_as_int(fminf(fminf(ay, by), cy), 0, H - 1), band_lo);
-                const uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(ay, by), cy), 0, H - 1), band_hi);
-                if (miny > maxy) continue;
-                const uint32_t minx = max(sr_clamp_as_int(fminf(fminf(ax, bx), cx), 0, W - 1), x0);
-                const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(ax, bx), cx), 0, W - 1), xe);
-                if (minx > maxx) continue;
-                const SrTri s = sr_tri_setup(ax, ay, bx, by, cx, cy);
-                // Fixed pixel ownership inside the band: lane -> row lane / LW, columns congruent to lane % LW.  A pixel's
-                // key is therefore only ever read and written by one lane, in list order: no atomics, no warp syncs,
-                // and no per-pixel division.
-                constexpr uint32_t LW = 32 / RH;
-                static_assert(32 % RH == 0, "band rows divide the warp");
-                const uint32_t py = band_lo + lane / LW;
-                if (py >= miny && py <= maxy) {
-                    for (uint32_t px = x0 + ((minx - x0) / LW) * LW + lane % LW; px <= maxx; px += LW) {
-                        if (px < minx) continue;
-                        float nu, nv, u, v, w;
-                        sr_tri_numerators(s, (float)px + 0.5f, (float)py + 0.5f, nu, nv);
-                        if (!sr_tri_inside(s, nu, nv, u, v, w)) continue;
-                        const float z = (az * u + bz * v) + cz * w;
-                        if (!(z < 0.0f)) continue;  // triangle.rs:120
-                        const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | (unsigned long long)(st + 1u);
-                        unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
-                        if (key > *slot) *slot = key;
-                    }
+            __syncthreads();
+            // Fixed pixel ownership inside the band: lane -> row lane / LW, columns congruent to lane % LW.  A pixel's key is
+            // therefore only ever read and written by one lane, in list order: no atomics and no warp syncs.
+            constexpr uint32_t LW = 32 / RH;
+            static_assert(32 % RH == 0, "band rows divide the warp");
+            const uint32_t py = band_lo + lane / LW;
+            const float yf = (float)py + 0.5f;
+            unsigned long long *krow = keys + (py - y0) * SR_TILE_W - x0;
+            for (uint32_t l = 0; l < L; ++l) {
+                const float4 r3 = s_rec[l * 4 + 3];
+                const uint32_t bx = __float_as_uint(r3.x), by = __float_as_uint(r3.y);
+                if (max(by & 0xffffu, band_lo) > min(by >> 16, band_hi)) continue;  // (warp-uniform)
+                if (py < (by & 0xffffu) || py > (by >> 16)) continue;
+                const float4 r0 = s_rec[l * 4 + 0], r1 = s_rec[l * 4 + 1], r2 = s_rec[l * 4 + 2];
+                SrTri s;
+                s.a = r0.x; s.b = r0.y; s.c = r0.z; s.d = r0.w;
+                s.x3 = r1.x; s.y3 = r1.y; s.det = r1.z; s.rdet = r1.w;
+                s.dsign = __float_as_uint(s.det) & 0x80000000u;
+                s.fast = ((__float_as_uint(s.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                const uint32_t minx = bx & 0xffffu, maxx = bx >> 16;
+                const float dy = yf - s.y3, bdy = s.b * dy, ddy = s.d * dy;  // triangle.rs:105,108-109 (row terms hoisted, same roundings)
+                const unsigned long long id = (unsigned long long)__float_as_uint(r2.w);
+                for (uint32_t px = x0 + ((minx - x0) / LW) * LW + lane % LW; px <= maxx; px += LW) {
+                    if (px < minx) continue;
+                    const float dx = ((float)px + 0.5f) - s.x3;
+                    const float nu = s.a * dx + bdy, nv = s.c * dx + ddy;
+                    float u, v, w;
+                    if (!sr_tri_inside(s, nu, nv, u, v, w)) continue;
+                    const float z = (r2.x * u + r2.y * v) + r2.z * w;
+                    if (!(z < 0.0f)) continue;  // triangle.rs:120
+                    const unsigned long long key = ((unsigned long long)sr_depth_key(z) << 32) | id;
+                    if (key > krow[px]) krow[px] = key;
                 }
             }
         }
