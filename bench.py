@@ -259,6 +259,7 @@ def run_ours(args):
 
     # per-stage device times (CUDA events recorded by the library on its stream), averaged over a few more frames
     stage_acc, nstage = {}, 5
+    ctx.set_stage_timing(True)
     for _ in range(nstage):
         frame()
         for k, v in ctx.stage_times().items():

@@ -62,6 +62,9 @@ int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
  * these values. */
 #define SR_MICRO_AREA_AUTO 0xFFFFFFFFu
 int sr_context_set_micro(sr_context *, uint32_t area, uint32_t min_triangles, uint32_t precheck);
+/* record the per-stage CUDA events read by sr_context_stage_times / sr_context_stage_timestamps (off by default:
+ * eight timed events per draw are a measurable share of a small frame) */
+int sr_context_set_stage_timing(sr_context *, int enable);
 /* timeline introspection: time in ms from `base_event` (a cudaEvent_t recorded by the caller, timing enabled) to the
  * internal stage events of the most recent draw: [0] vertex begin, [1] vertex end, [2] geometry end, [3] fragment begin,
  * [4] ordered bins end, [7] visibility init end, [5] raster front end (k_micro) end, [6] fragment end; -1 = not recorded */

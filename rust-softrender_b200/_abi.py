@@ -42,6 +42,7 @@ SYMBOLS = {
     "sr_context_stream": (c_void_p, [c_void_p]),
     "sr_context_set_tile_shard": (c_int, [c_void_p, c_u32, c_u32]),
     "sr_context_set_micro": (c_int, [c_void_p, c_u32, c_u32, c_u32]),
+    "sr_context_set_stage_timing": (c_int, [c_void_p, c_int]),
     "sr_context_stage_timestamps": (c_int, [c_void_p, c_void_p, f32p]),
     "sr_context_wait_for": (c_int, [c_void_p, c_void_p, c_u32]),
     "sr_context_set_list_capacity": (c_int, [c_void_p, c_u32]),

@@ -59,6 +59,7 @@ struct sr_context {
     uint64_t launches = 0;
     cudaEvent_t ev[8] = {};  // vertex begin/end, geometry end, fragment begin, bins end, micro end, raster end
     bool ev_valid[8] = {};
+    bool stage_timing = false;  // sr_context_set_stage_timing
     uint32_t micro_area = SR_MICRO_AREA_DEFAULT;  // bbox pixels up to which k_micro rasterises a triangle itself (0: off)
     bool micro_auto = true;                       // choose the split per draw from the triangle count (sr_micro_area_for)
     uint32_t micro_min_tris = 65536;              // draws onto existing contents use the visibility buffer from this size on
@@ -206,6 +207,7 @@ static uint32_t nplanes_of(uint32_t nk) { return (nk + 3) / 4; }
 // helpers
 // ---------------------------------------------------------------------------------------------------------
 static void record(sr_context *c, int i) {
+    if (!c->stage_timing) return;  // eight timed events per draw are a measurable share of a small frame
     if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
     cudaEventRecord(c->ev[i], c->stream);
     c->ev_valid[i] = true;
@@ -398,8 +400,11 @@ struct PendingOpaque {
     std::vector<Buf> keep;          // every device buffer the pass reads (the draw may be destroyed meanwhile)
     Buf count, off, lcount, lids, lrects;
     sr_framebuffer *fb = nullptr;
+    bool small = false;             // front end = one k_bin_small launch (re-run as a whole on overflow)
+    SrMicroParams mp;
 };
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q);
+static int launch_bin_small(sr_context *c, PendingOpaque *q);
 static int settle(sr_context *c) {
     PendingOpaque *q = c->pending;
     if (!q) return SR_OK;
@@ -437,6 +442,51 @@ static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 102
 static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
                             const std::vector<Buf> &keep) {
     const uint32_t ntiles = fb->ntx * fb->nty;
+    // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
+    if (c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
+        record(c, 7);
+        auto q = std::make_unique<PendingOpaque>();
+        SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &q->off));
+        if (!c->list_arena) {
+            c->list_cap = 1u << 20;
+            SR_TRY(c->alloc((size_t)c->list_cap * 4, &c->list_arena));
+        }
+        q->small = true;
+        q->capacity = c->list_cap;
+        q->fs = fs; q->owned = owned; q->ntiles = ntiles;
+        memset(&q->mp, 0, sizeof(q->mp));
+        q->mp.src = tp.tris;
+        q->mp.ntris = tp.ntris;
+        q->mp.cull = cull;
+        q->mp.width = fb->width; q->mp.height = fb->height; q->mp.ntx = fb->ntx; q->mp.nty = fb->nty;
+        q->mp.shard_rank = c->shard_rank; q->mp.shard_world = c->shard_world;
+        q->keep = keep;
+        q->keep.push_back(c->list_arena);
+        q->fb = fb;
+        memset(&q->op, 0, sizeof(q->op));
+        q->op.tris = tp.tris;
+        q->op.ntris = tp.ntris;
+        q->op.tile_off = q->off->as<uint32_t>();
+        q->op.list = c->list_arena->as<uint32_t>();
+        q->op.list_capacity = c->list_cap;
+        q->op.ntiles = ntiles;
+        q->op.fb = fb->view();
+        q->op.shard_rank = c->shard_rank; q->op.shard_world = c->shard_world;
+        q->op.fs = tp.fs;
+        SR_TRY(launch_bin_small(c, q.get()));
+        record(c, 5);
+        if (!c->ev_front) SR_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
+        SR_CUDA(cudaEventRecord(c->ev_front, c->stream));
+        c->ev_front_valid = true;
+        if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+        SR_CUDA(cudaMemcpyAsync(&c->pinned[0], q->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaEventCreateWithFlags(&q->counted, cudaEventDisableTiming));
+        SR_CUDA(cudaEventRecord(q->counted, c->stream));
+        SR_TRY(launch_opaque_fs(c, fs, owned, q->op));
+        fb->pending_clear = false;
+        c->pending = q.release();
+        return SR_OK;
+    }
     const uint32_t micro_area = c->micro_auto ? sr_micro_area_for(tp.ntris) : c->micro_area;
     const bool use_micro = micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
     if (use_micro) {
@@ -522,7 +572,21 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     return SR_OK;
 }
 // per-tile lists of the large triangles + the tile kernel (both skip themselves if the lists do not fit the arena)
+static int launch_bin_small(sr_context *c, PendingOpaque *q) {
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_bin_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_BIN_SMALL_MAX_TILES * 4));
+        configured[c->device & 15] = true;
+    }
+    SR_LAUNCH(c, k_bin_small, 1, SR_BIN_SMALL_THREADS, (size_t)q->ntiles * 4, q->mp, q->off->as<uint32_t>(), const_cast<uint32_t *>(q->op.list),
+              q->capacity);
+    return SR_OK;
+}
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q) {
+    if (q->small) {
+        SR_TRY(launch_bin_small(c, q));
+        return launch_opaque_fs(c, q->fs, q->owned, q->op);
+    }
     if (q->op.ntris)
         SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(q->op.ntris, 8), 148u * 4u), 256, 0, q->lcount->as<uint32_t>(),
                   q->lids->as<uint32_t>(), q->lrects->as<uint32_t>(), q->op.fb.ntx, q->ntiles, q->op.shard_rank, q->op.shard_world,
@@ -607,6 +671,13 @@ int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, u
     if (!c->micro_auto) c->micro_area = area;
     c->micro_min_tris = min_triangles;
     c->micro_precheck = precheck & 3u;
+    return SR_OK;
+}
+int sr_context_set_stage_timing(sr_context *c, int enable) {
+    if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null context");
+    c->stage_timing = enable != 0;
+    if (!c->stage_timing)
+        for (bool &v : c->ev_valid) v = false;
     return SR_OK;
 }
 int sr_context_stage_timestamps(sr_context *c, void *base_event, float ms[8]) {

@@ -623,6 +623,119 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro
     sr_micro_triangle<PRECHECK, EARLYZ>(p, t, t < p.ntris, A, B, C, threadIdx.x & 31);
 }
 
+// Small draws (a model of a few thousand triangles): the whole front end -- triangle fetch, cull, tile rectangles,
+// per-tile counts, the exclusive scan of the counts and the list fill -- in ONE single-CTA launch with the counters
+// in shared memory, instead of two memsets + k_micro + k_tile_offsets + k_large_fill.  At this size the frame is
+// bound by the latency of that chain of tiny dependent launches, not by throughput.  Every triangle goes to the
+// tile lists (the tile kernel's short-list sweep); the visibility buffer is not used.
+#define SR_BIN_SMALL_THREADS 1024
+#define SR_BIN_SMALL_MAX_TRIS 8192
+#define SR_BIN_SMALL_MAX_TILES 8192
+__global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid_constant__ SrMicroParams p, uint32_t *tile_off,
+                                                                    uint32_t *list, uint32_t capacity) {
+    extern __shared__ uint32_t s_cnt[];  // per-tile counters, later the fill cursors
+    __shared__ uint32_t s_wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ntiles = p.ntx * p.nty;
+    for (uint32_t i = tid; i < ntiles; i += SR_BIN_SMALL_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    constexpr int PER = SR_BIN_SMALL_MAX_TRIS / SR_BIN_SMALL_THREADS;
+    uint32_t rects[PER];
+    // A lane walks its own triangle's tile rectangle when it is small (the usual case: a handful of tiles); a rectangle of
+    // more than 16 tiles is spread over the lanes of the warp (a big triangle touches hundreds of tiles).
+    const bool sharded = p.shard_world > 1;
+    auto spread = [&](uint32_t mine, uint32_t t, bool fill) {
+        bool big = false;
+        if (mine != SR_RECT_INVALID) {
+            const uint32_t tx0 = mine & 255u, ty0 = (mine >> 8) & 255u, tx1 = (mine >> 16) & 255u, ty1 = mine >> 24;
+            big = (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 16u;
+            if (!big) {
+                for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                    for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                        const uint32_t tile = ty * p.ntx + tx;
+                        if (sharded && tile % p.shard_world != p.shard_rank) continue;
+                        const uint32_t at = atomicAdd(&s_cnt[tile], 1u);
+                        if (fill) list[at] = t;
+                    }
+            }
+        }
+        for (uint32_t rest = __ballot_sync(0xffffffffu, big); rest; rest &= rest - 1) {
+            const int src = __ffs(rest) - 1;
+            const uint32_t r = __shfl_sync(0xffffffffu, mine, src), st = __shfl_sync(0xffffffffu, t, src);
+            const uint32_t tx0 = r & 255u, ty0 = (r >> 8) & 255u, tx1 = (r >> 16) & 255u, ty1 = r >> 24;
+            const uint32_t rw = tx1 - tx0 + 1, n = rw * (ty1 - ty0 + 1);
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t tile = (ty0 + i / rw) * p.ntx + tx0 + i % rw;
+                if (sharded && tile % p.shard_world != p.shard_rank) continue;
+                const uint32_t at = atomicAdd(&s_cnt[tile], 1u);
+                if (fill) list[at] = st;
+            }
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t t = (uint32_t)k * SR_BIN_SMALL_THREADS + tid;
+        uint32_t rect = SR_RECT_INVALID;
+        if (t < p.ntris) {
+            const SrVertexSet *vs;
+            uint32_t vi[3];
+            sr_prim_vertices<3>(p.src, t, vs, vi);
+            const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+            bool skip = isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y);  // (the reference panics)
+            if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
+                const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
+                skip = skip || (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) == p.cull;
+            }
+            if (!skip) {  // triangle.rs:74-78 with tile = the whole frame
+                const uint32_t minx = sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, p.width - 1);
+                const uint32_t maxx = sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, p.width - 1);
+                const uint32_t miny = sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, p.height - 1);
+                const uint32_t maxy = sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, p.height - 1);
+                if (minx <= maxx && miny <= maxy) rect = sr_pack_rect(minx / SR_TILE_W, miny / SR_TILE_H, maxx / SR_TILE_W, maxy / SR_TILE_H);
+            }
+        }
+        rects[k] = rect;
+        spread(rect, t, false);
+    }
+    __syncthreads();
+    // exclusive scan of the counters: a run of consecutive tiles per thread, warp scan, scan of the warp totals
+    const uint32_t chunk = (ntiles + SR_BIN_SMALL_THREADS - 1) / SR_BIN_SMALL_THREADS;
+    const uint32_t b = min(tid * chunk, ntiles), e = min(b + chunk, ntiles);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += s_cnt[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_wsum[lane];
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += v;
+        }
+        s_wsum[lane] = w;  // inclusive totals of the warps
+    }
+    __syncthreads();
+    const uint32_t total = s_wsum[31];
+    uint32_t run = (warp ? s_wsum[warp - 1] : 0u) + inc - sum;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t c = s_cnt[i];
+        tile_off[i] = run;
+        s_cnt[i] = run;
+        run += c;
+    }
+    if (tid == 0) tile_off[ntiles] = total;
+    __syncthreads();
+    if (total > capacity) return;  // the lists do not fit: the host re-runs this launch with a larger arena
+#pragma unroll
+    for (int k = 0; k < PER; ++k) spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
+}
+
 // second pass over the large triangles only: write their ids into the per-tile lists
 __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count, const uint32_t *large_ids, const uint32_t *large_rects,
                                                     uint32_t ntx, uint32_t ntiles, uint32_t shard_rank, uint32_t shard_world,

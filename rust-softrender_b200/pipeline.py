@@ -59,6 +59,10 @@ class Context:
         precheck: bit 0 = per-fragment key pre-check, bit 1 = early depth rejection off (library default 0)."""
         check(lib.sr_context_set_micro(self.h, area, min_triangles, int(precheck) & 3))
 
+    def set_stage_timing(self, enable: bool = True):
+        """Record the per-stage CUDA events `stage_times` / `stage_timestamps` read (off by default)."""
+        check(lib.sr_context_set_stage_timing(self.h, 1 if enable else 0))
+
     def stage_timestamps(self, base_event: int):
         """ms from the caller's cudaEvent_t `base_event` to the stage events of the latest draw (see the C header)."""
         out = (ctypes.c_float * 8)()
