@@ -81,6 +81,9 @@ int sr_context_wait_for(sr_context *waiter, sr_context *other, uint32_t point);
  * Setting a tiny capacity exercises that path in tests. */
 int sr_context_set_list_capacity(sr_context *, uint32_t entries);
 int sr_context_list_capacity(sr_context *, uint32_t *entries);
+/* the same for the ordered path's per-tile group lists: capacities of the point, line and triangle arenas
+ * (sr_context_set_list_capacity sets all of them) */
+int sr_context_ordered_list_capacity(sr_context *, uint32_t entries[3]);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int sr_context_launch_count(sr_context *, uint64_t *out);
 

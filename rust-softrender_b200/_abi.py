@@ -47,6 +47,7 @@ SYMBOLS = {
     "sr_context_wait_for": (c_int, [c_void_p, c_void_p, c_u32]),
     "sr_context_set_list_capacity": (c_int, [c_void_p, c_u32]),
     "sr_context_list_capacity": (c_int, [c_void_p, u32p]),
+    "sr_context_ordered_list_capacity": (c_int, [c_void_p, u32p]),
     "sr_context_launch_count": (c_int, [c_void_p, u64p]),
     "sr_context_stage_times": (c_int, [c_void_p, ctypes.POINTER(StageTimes)]),
     "sr_framebuffer_create": (c_int, [c_void_p, c_u32, c_u32, c_u32, pp]),

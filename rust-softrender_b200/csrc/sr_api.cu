@@ -70,6 +70,9 @@ struct sr_context {
     Buf list_arena;
     uint32_t list_cap = 0;
     struct PendingOpaque *pending = nullptr;
+    struct PendingOrdered *pending_ord = nullptr;
+    Buf ord_arena[3];                             // grow-only group-list arenas of the ordered path (points, lines, triangles)
+    uint32_t ord_cap[3] = {0, 0, 0};
     cudaEvent_t ev_front = nullptr;               // recorded after the raster front end (k_micro) of the latest opaque draw
     bool ev_front_valid = false;
     Buf zero_off;                                 // all-zero CSR offsets for empty primitive kinds
@@ -279,8 +282,12 @@ static int materialize_clear(sr_framebuffer *fb) {
 // bins
 // ---------------------------------------------------------------------------------------------------------
 struct Bins {
-    Buf rects, off, list;
+    Buf rects, off, list, count;
     uint32_t total = 0;
+    uint32_t capacity = 0xFFFFFFFFu;
+    SrBinParams params;  // of the fill pass (kept for a replay)
+    uint32_t grid = 0;
+    int nv = 0;          // 0: empty kind
 };
 
 static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
@@ -294,19 +301,24 @@ static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
     b->rects = c->zero_off;
     b->list = c->zero_off;
     b->total = 0;
+    b->nv = 0;
     return SR_OK;
 }
 
+// Per-tile group lists of one primitive kind.  exact = true sizes the list with a host synchronisation (introspection:
+// sr_draw_bins).  exact = false is the draw path: the list lives in a grow-only arena of the context, the fill pass and
+// the tile kernel are enqueued against its current capacity and skip themselves on the device if the scanned total does
+// not fit; the total travels to pinned memory (`total_slot`) and settle() re-runs the skipped passes with a larger arena.
 template <int NV>
-static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSource &src, uint32_t nprims, uint32_t cull, Bins *b) {
+static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSource &src, uint32_t nprims, uint32_t cull, Bins *b,
+                      bool exact = true, uint32_t *total_slot = nullptr) {
     const uint32_t ntiles = fb->ntx * fb->nty;
     if (nprims == 0) return zero_offsets(c, ntiles, b);
-    Buf count;
     SR_TRY(c->alloc(((size_t)nprims + 64) * 4, &b->rects));
-    SR_TRY(c->alloc((size_t)ntiles * 4, &count));
+    SR_TRY(c->alloc((size_t)ntiles * 4, &b->count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
-    SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)ntiles * 4, c->stream));
-    SrBinParams p;
+    SR_CUDA(cudaMemsetAsync(b->count->ptr, 0, (size_t)ntiles * 4, c->stream));
+    SrBinParams &p = b->params;
     memset(&p, 0, sizeof(p));
     p.src = src;
     p.nprims = nprims;
@@ -314,16 +326,30 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     p.width = fb->width; p.height = fb->height; p.ntx = fb->ntx; p.nty = fb->nty;
     p.shard_rank = c->shard_rank; p.shard_world = c->shard_world;
     p.rects = b->rects->as<uint32_t>();
-    p.tile_count = count->as<uint32_t>();
-    const uint32_t grid = ceil_div(nprims, 256);
-    SR_LAUNCH(c, k_bin_setup<NV>, grid, 256, 0, p);
-    SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), count->as<uint32_t>());
-    SR_CUDA(cudaMemcpyAsync(&b->total, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
-    SR_CUDA(cudaStreamSynchronize(c->stream));
-    SR_TRY(c->alloc((size_t)std::max(b->total, 1u) * 4, &b->list));
+    p.tile_count = b->count->as<uint32_t>();
+    b->grid = ceil_div(nprims, 256);
+    b->nv = NV;
+    SR_LAUNCH(c, k_bin_setup<NV>, b->grid, 256, 0, p);
+    SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, b->count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), b->count->as<uint32_t>());
     p.tile_off = b->off->as<uint32_t>();
+    if (exact) {
+        SR_CUDA(cudaMemcpyAsync(&b->total, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaStreamSynchronize(c->stream));
+        SR_TRY(c->alloc((size_t)std::max(b->total, 1u) * 4, &b->list));
+        b->capacity = std::max(b->total, 1u);
+    } else {
+        Buf &arena = c->ord_arena[NV - 1];
+        if (!arena) {
+            c->ord_cap[NV - 1] = 1u << 18;
+            SR_TRY(c->alloc((size_t)c->ord_cap[NV - 1] * 4, &arena));
+        }
+        b->list = arena;
+        b->capacity = c->ord_cap[NV - 1];
+        SR_CUDA(cudaMemcpyAsync(total_slot, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     p.list = b->list->as<uint32_t>();
-    SR_LAUNCH(c, k_bin_fill, grid, 256, 0, p);
+    p.capacity = b->capacity;
+    SR_LAUNCH(c, k_bin_fill, b->grid, 256, 0, p);
     return SR_OK;
 }
 
@@ -405,8 +431,50 @@ struct PendingOpaque {
 };
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q);
 static int launch_bin_small(sr_context *c, PendingOpaque *q);
+// The same for the ordered tile pass: its three group lists (points, lines, triangles) live in grow-only arenas.
+struct PendingOrdered {
+    cudaEvent_t counted = nullptr;
+    SrTileParams tp;
+    uint32_t fs = 0, owned = 0;
+    Bins bins[3];  // points, lines, triangles
+    std::vector<Buf> keep;
+};
+static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrTileParams &p);
+static int settle_ordered(sr_context *c) {
+    PendingOrdered *q = c->pending_ord;
+    if (!q) return SR_OK;
+    c->pending_ord = nullptr;
+    std::unique_ptr<PendingOrdered> guard(q);
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_CUDA(cudaEventSynchronize(q->counted));
+    cudaEventDestroy(q->counted);
+    q->counted = nullptr;
+    bool replay = false;
+    for (int k = 0; k < 3; ++k) {
+        Bins &b = q->bins[k];
+        if (b.nv == 0) continue;
+        const uint32_t total = c->pinned[8 + k];
+        if (total <= b.capacity) continue;
+        // this kind's fill pass (and therefore the tile kernel) skipped itself: larger arena, fill again
+        replay = true;
+        const uint32_t cap = std::max<uint32_t>(total + total / 2, 1u << 18);
+        SR_TRY(c->alloc((size_t)cap * 4, &c->ord_arena[k]));
+        c->ord_cap[k] = cap;
+        b.list = c->ord_arena[k];
+        b.capacity = cap;
+        b.params.list = b.list->as<uint32_t>();
+        b.params.capacity = cap;
+        SR_LAUNCH(c, k_bin_fill, b.grid, 256, 0, b.params);
+    }
+    if (!replay) return SR_OK;
+    q->tp.point_list = q->bins[0].list->as<uint32_t>(); q->tp.point_cap = q->bins[0].capacity;
+    q->tp.line_list = q->bins[1].list->as<uint32_t>(); q->tp.line_cap = q->bins[1].capacity;
+    q->tp.tri_list = q->bins[2].list->as<uint32_t>(); q->tp.tri_cap = q->bins[2].capacity;
+    return launch_tiles_fs(c, q->fs, q->owned, q->tp);
+}
 static int settle(sr_context *c) {
-    PendingOpaque *q = c->pending;
+    if (c && c->pending_ord && !c->pending) return settle_ordered(c);
+    PendingOpaque *q = c ? c->pending : nullptr;
     if (!q) return SR_OK;
     c->pending = nullptr;
     std::unique_ptr<PendingOpaque> guard(q);
@@ -415,7 +483,7 @@ static int settle(sr_context *c) {
     cudaEventDestroy(q->counted);
     q->counted = nullptr;
     const uint32_t total = c->pinned[0];
-    if (total <= q->capacity) return SR_OK;
+    if (total <= q->capacity) return settle_ordered(c);
     // the pass skipped itself: grow the arena and run it again (framebuffer and visibility buffer are untouched)
     Buf bigger;
     const uint32_t cap = std::max<uint32_t>(total + total / 2, 1u << 20);
@@ -426,7 +494,8 @@ static int settle(sr_context *c) {
     q->op.list = bigger->as<uint32_t>();
     q->op.list_capacity = cap;
     q->keep.push_back(bigger);
-    return launch_opaque_pass(c, q);
+    SR_TRY(launch_opaque_pass(c, q));
+    return settle_ordered(c);
 }
 
 // Where the split between the per-triangle front end and the per-tile lists lies.  One thread walking a whole bounding box
@@ -717,12 +786,22 @@ int sr_context_set_list_capacity(sr_context *c, uint32_t entries) {
     SR_TRY(c->alloc((size_t)entries * 4, &arena));
     c->list_arena = arena;
     c->list_cap = entries;
+    for (int k = 0; k < 3; ++k) {  // the ordered path's group-list arenas follow
+        SR_TRY(c->alloc((size_t)entries * 4, &c->ord_arena[k]));
+        c->ord_cap[k] = entries;
+    }
     return SR_OK;
 }
 int sr_context_list_capacity(sr_context *c, uint32_t *entries) {
     if (!c || !entries) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     SR_TRY(settle(c));
     *entries = c->list_cap;
+    return SR_OK;
+}
+int sr_context_ordered_list_capacity(sr_context *c, uint32_t entries[3]) {
+    if (!c || !entries) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(settle(c));
+    for (int k = 0; k < 3; ++k) entries[k] = c->ord_cap[k];
     return SR_OK;
 }
 int sr_context_launch_count(sr_context *c, uint64_t *out) {
@@ -1353,37 +1432,46 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     const uint32_t owned = ntiles > c->shard_rank ? (ntiles - c->shard_rank + c->shard_world - 1) / c->shard_world : 0;
     const bool stencil_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
     const bool opaque_ok = d->blend == SR_BLEND_REPLACE && !stencil_active && fs != SR_FS_DISCARD_CHECKER;
-    Bins bt, bl, bp;
+    const bool ordered_pass = !opaque_ok || tp.nlines + tp.npoints > 0;
+    auto q = std::make_unique<PendingOrdered>();
+    Bins &bp = q->bins[0], &bl = q->bins[1], &bt = q->bins[2];
+    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
     if (opaque_ok) SR_TRY(zero_offsets(c, ntiles, &bt));  // triangles go through opaque_triangles below
-    else SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt));
-    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl));
-    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp));
+    else SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt, false, &c->pinned[10]));
+    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl, false, &c->pinned[9]));
+    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp, false, &c->pinned[8]));
     record(c, 4);
     record(c, 7);
     record(c, 5);
-    tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>();
-    tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>();
-    tp.point_rects = bp.rects->as<uint32_t>(); tp.point_off = bp.off->as<uint32_t>(); tp.point_list = bp.list->as<uint32_t>();
+    tp.tri_rects = bt.rects->as<uint32_t>(); tp.tri_off = bt.off->as<uint32_t>(); tp.tri_list = bt.list->as<uint32_t>(); tp.tri_cap = bt.capacity;
+    tp.line_rects = bl.rects->as<uint32_t>(); tp.line_off = bl.off->as<uint32_t>(); tp.line_list = bl.list->as<uint32_t>(); tp.line_cap = bl.capacity;
+    tp.point_rects = bp.rects->as<uint32_t>(); tp.point_off = bp.off->as<uint32_t>(); tp.point_list = bp.list->as<uint32_t>(); tp.point_cap = bp.capacity;
 
     if (owned) {
+        std::vector<Buf> keep = {d->indices, d->indexed.pos, d->indexed.attr, d->gen[0].pos, d->gen[0].attr, d->gen[1].pos, d->gen[1].attr,
+                                 d->gen[2].pos, d->gen[2].attr, d->tri_seq};
+        if (p->texture) keep.push_back(p->texture->rgba);
+        SrTileParams ordered = tp;
         if (opaque_ok) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,
             // fragment.rs:268-311) through the ordered kernel
             if (tp.ntris || fb->pending_clear) {
-                std::vector<Buf> keep = {d->indices, d->indexed.pos, d->indexed.attr, d->gen[2].pos, d->gen[2].attr, d->tri_seq};
-                if (p->texture) keep.push_back(p->texture->rgba);
                 SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep));
+                if (ordered_pass) SR_TRY(settle(c));  // a replayed triangle pass must not land after the lines
             }
-            if (tp.nlines + tp.npoints) {
-                SrTileParams t2 = tp;
-                t2.ntris = 0;
-                t2.fb = fb->view();
-                SR_TRY(launch_tiles_fs(c, fs, owned, t2));
-            }
-        } else {
-            tp.fb = fb->view();
-            SR_TRY(launch_tiles_fs(c, fs, owned, tp));
+            ordered.ntris = 0;
+        }
+        if (ordered_pass) {
+            ordered.fb = fb->view();
+            // the scanned totals are on their way to pinned memory (build_bins): validated at the next call on this context
+            SR_CUDA(cudaEventCreateWithFlags(&q->counted, cudaEventDisableTiming));
+            SR_CUDA(cudaEventRecord(q->counted, c->stream));
+            SR_TRY(launch_tiles_fs(c, fs, owned, ordered));
             fb->pending_clear = false;
+            q->tp = ordered;
+            q->fs = fs; q->owned = owned;
+            q->keep = keep;
+            c->pending_ord = q.release();
         }
     }
     record(c, 6);

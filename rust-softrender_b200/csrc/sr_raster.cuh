@@ -33,6 +33,7 @@ struct SrBinParams {
     uint32_t *tile_count;  // count pass: entries per tile; fill pass: running cursor per tile
     const uint32_t *tile_off;
     uint32_t *list;        // fill pass: group ids per tile
+    uint32_t capacity;     // fill pass: entries `list` can hold (the pass skips itself if the scanned total exceeds it)
 };
 
 // ---- per-primitive tile rectangle ------------------------------------------------------------------------
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_setup(const SrBinParams 
 // pass 2: fill the per-tile group lists (order inside a list is arbitrary; consumers that need
 // submission order sort the list, which is tiny because entries are groups of 32 primitives)
 __global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_fill(const SrBinParams p) {
+    if (p.tile_off[p.ntx * p.nty] > p.capacity) return;  // lists do not fit: the host re-runs the pass with a larger arena
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t rect = t < p.nprims ? __ldg(p.rects + t) : SR_RECT_INVALID;
     sr_bin_group<true>(p, rect, t >> 5);
@@ -291,6 +293,7 @@ struct SrTileParams {
     const uint32_t *tri_rects, *line_rects, *point_rects;
     const uint32_t *tri_off, *line_off, *point_off;  // per-tile CSR offsets (ntiles+1) into the group lists
     uint32_t *tri_list, *line_list, *point_list;
+    uint32_t tri_cap, line_cap, point_cap;  // list capacities: the kernel skips itself if a scanned total exceeds its list
     SrFbView fb;
     uint32_t shard_rank, shard_world;
     uint32_t blend, stencil_test, stencil_op, stencil_value, aa_lines;
@@ -1072,12 +1075,18 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
 // submission order per pixel.  Tile colour, depth, stencil (and winner) live in shared memory; each
 // warp owns a band of tile rows, so all operations on a pixel are issued by one warp in program order.
 // =====================================================================================================
+// Everything the per-pixel loop needs of one triangle, produced once (one thread per triangle, 256 at a time) so that the
+// strictly ordered sweep -- a serial chain by construction -- contains no dependent global loads and no reciprocal.
 struct SrOrdSetup {
-    float x1, y1, x2, y2, x3, y3;
+    float4 e;         // a, b, c, d           (triangle.rs:108-109 edge terms)
+    float4 f;         // x3, y3, det, 1/det
+    float4 A, B, C;   // screen positions {x, y, z, 1/w}
     uint32_t bx, by;  // minx | maxx<<16, miny | maxy<<16 (frame-clamped bbox intersected with the tile)
-    uint32_t t;
+    uint32_t canonical, second;  // canonical primitive number; vertices come from the generated stream
+    uint32_t vi[3], pad;
 };
-#define SR_ORD_LIST_CAP 8192  // group ids sorted in shared memory; longer lists are sorted in place in HBM
+static_assert(sizeof(SrOrdSetup) == 112, "seven float4");
+#define SR_ORD_LIST_CAP 4096  // group ids sorted in shared memory; longer lists are sorted in place in HBM
 #define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4)
 
 struct SrOrdCtx {
@@ -1316,6 +1325,10 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
+    {   // optimistic list sizing (see build_bins): nothing may be touched if a list did not fit
+        const uint32_t nt = p.fb.ntx * p.fb.nty;
+        if (p.tri_off[nt] > p.tri_cap || p.line_off[nt] > p.line_cap || p.point_off[nt] > p.point_cap) return;
+    }
     const uint32_t tbeg = p.tri_off[tile], LT = p.tri_off[tile + 1] - tbeg;
     const uint32_t lbeg = p.line_off[tile], LL = p.line_off[tile + 1] - lbeg;
     const uint32_t pbeg = p.point_off[tile], LP = p.point_off[tile + 1] - pbeg;
@@ -1377,10 +1390,18 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), c.xe);
                     const uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), c.ye);
                     hit = minx <= maxx && miny <= maxy;
-                    su.x1 = A.x; su.y1 = A.y; su.x2 = B.x; su.y2 = B.y; su.x3 = C.x; su.y3 = C.y;
-                    su.bx = minx | (maxx << 16);
-                    su.by = miny | (maxy << 16);
-                    su.t = t;
+                    if (hit) {
+                        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+                        su.e = make_float4(tr.a, tr.b, tr.c, tr.d);
+                        su.f = make_float4(tr.x3, tr.y3, tr.det, tr.rdet);
+                        su.A = A; su.B = B; su.C = C;
+                        su.bx = minx | (maxx << 16);
+                        su.by = miny | (maxy << 16);
+                        su.canonical = sr_prim_canonical(p.tris, t, 0);
+                        su.second = t < p.tris.n0 ? 0u : 1u;
+                        su.vi[0] = vi[0]; su.vi[1] = vi[1]; su.vi[2] = vi[2];
+                        su.pad = 0;
+                    }
                 }
             }
             const uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -1397,34 +1418,37 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             __syncthreads();
             const uint32_t ry_lo = y0 + warp * RH, ry_hi = ry_lo + RH - 1;
             for (uint32_t s = 0; s < total; ++s) {
-                const SrOrdSetup q = s_setup[s];
-                const uint32_t minx = q.bx & 0xffffu, maxx = q.bx >> 16;
-                const uint32_t r0 = max(q.by & 0xffffu, ry_lo), r1 = min(q.by >> 16, ry_hi);
+                const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
+                const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
+                const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
                 if (r0 > r1) continue;
-                const SrTri tr = sr_tri_setup(q.x1, q.y1, q.x2, q.y2, q.x3, q.y3);
+                const SrOrdSetup &q = s_setup[s];
+                SrTri tr;
+                tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
+                tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
+                tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
+                tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                const float4 A = q.A, B = q.B, C = q.C;
                 const uint32_t bw = maxx - minx + 1, npix = bw * (r1 - r0 + 1);
-                const SrVertexSet *vs;
-                uint32_t vi[3];
-                sr_prim_vertices<3>(p.tris, q.t, vs, vi);
-                const uint32_t canonical = sr_prim_canonical(p.tris, q.t, 0);
+                const SrVertexSet *vs = q.second ? &p.tris.vs1 : &p.tris.vs0;
+                const uint32_t vi0 = q.vi[0], vi1 = q.vi[1], vi2 = q.vi[2], canonical = q.canonical;
                 for (uint32_t i = lane; i < npix; i += 32) {
                     const uint32_t px = minx + i % bw, py = r0 + i / bw;
                     const uint32_t li = (py - y0) * SR_TILE_W + (px - x0);
                     if (!sr_ord_stencil_step(c, li)) continue;
                     float u, v, w;
                     if (!sr_tri_bary(tr, px, py, u, v, w)) continue;
-                    const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
                     float sv[4 + NP * 4 + 1];
+                    sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+                    if (!(sv[2] < 0.0f) || !(sv[2] >= s_depth[li])) continue;
                     sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
                     sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
-                    sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
                     sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
-                    if (!(sv[2] < 0.0f) || !(sv[2] >= s_depth[li])) continue;
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl) {
-                        const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
-                        const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi[1], pl));
-                        const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi[2], pl));
+                        const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
+                        const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
+                        const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
                         sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
                         sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
                         sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);

@@ -77,6 +77,12 @@ class Context:
     def set_list_capacity(self, entries: int):
         check(lib.sr_context_set_list_capacity(self.h, entries))
 
+    def ordered_list_capacity(self):
+        """(points, lines, triangles) capacities of the ordered path's group-list arenas."""
+        n = (ctypes.c_uint32 * 3)()
+        check(lib.sr_context_ordered_list_capacity(self.h, n))
+        return tuple(n)
+
     def list_capacity(self) -> int:
         n = ctypes.c_uint32()
         check(lib.sr_context_list_capacity(self.h, ctypes.byref(n)))

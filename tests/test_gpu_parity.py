@@ -389,6 +389,26 @@ def test_alpha_over_blend_in_order(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="alpha over")
 
 
+def test_ordered_list_arena_overflow_is_replayed(P, ctx):
+    """The ordered path enqueues its bin fill and tile pass against the current capacity of its group-list arenas
+    without a host synchronisation; with 2-entry arenas both skip themselves on the device and are replayed with larger
+    arenas at the next call.  Blended triangles + lines + points of one draw, then a second blended draw on top."""
+    rng = np.random.default_rng(83)
+    w, h = 200, 150
+    tri = H.random_screen_triangles(rng, 300, w, h)
+    lines = H.random_screen_triangles(rng, 40, w, h)[:80]
+    pts = H.random_screen_triangles(rng, 100, w, h)[:300]
+    ctx.set_list_capacity(2)
+    try:
+        out, win, _, ofb = run_both_screen(P, ctx, w, h, tri, np.arange(len(tri), dtype=np.uint32), gen={2: lines, 1: pts},
+                                           blend=sr.BLEND_ALPHA_OVER, draws=2)
+        assert min(ctx.ordered_list_capacity()) > 2
+    finally:
+        ctx.set_list_capacity(1 << 20)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="replayed ordered pass")
+
+
 def test_discarding_shader(P, ctx):
     rng = np.random.default_rng(43)
     w, h, n = 130, 90, 300
