@@ -107,21 +107,35 @@ __device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect
     const bool any_valid = __any_sync(0xffffffffu, valid);
     const bool compact = any_valid && (gx1 - gx0 + 1) * (gy1 - gy0 + 1) <= SR_BIN_SLOTS;
     uint32_t nslots = 0;
-    if (any_valid) {
+    if (compact) {
         for (uint32_t ty = gy0; ty <= gy1; ++ty)
             for (uint32_t tx = gx0; tx <= gx1; ++tx) {
                 const bool hit = valid && sr_rect_hits(rect, tx, ty);
                 if (!__any_sync(0xffffffffu, hit)) continue;
                 const uint32_t tile = ty * p.ntx + tx;
                 if (tile % p.shard_world != p.shard_rank) continue;
-                if (compact) {
-                    if (lane == 0) s_tile[warp * SR_BIN_SLOTS + nslots] = tile;
-                    ++nslots;
-                } else if (lane == 0) {
-                    const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
-                    if (FILL) p.list[p.tile_off[tile] + at] = group;
-                }
+                if (lane == 0) s_tile[warp * SR_BIN_SLOTS + nslots] = tile;
+                ++nslots;
             }
+    } else if (any_valid) {
+        // a group of big primitives: the tiles of the group's union rectangle are dealt to the lanes, 32 at a time; every
+        // lane tests its tile against the 32 rectangles (handed round with shuffles) and posts its own atomic
+        const uint32_t gw = gx1 - gx0 + 1, n = gw * (gy1 - gy0 + 1);
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t tx = gx0 + i % gw, ty = gy0 + i / gw;
+            bool hit = false;
+#pragma unroll 4
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t r = __shfl_sync(0xffffffffu, rect, l);
+                hit = hit || (r != SR_RECT_INVALID && sr_rect_hits(r, tx, ty));
+            }
+            const uint32_t tile = ty * p.ntx + tx;
+            if (i < n && hit && tile % p.shard_world == p.shard_rank) {
+                const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
+                if (FILL) p.list[p.tile_off[tile] + at] = group;
+            }
+        }
     }
     if (lane == 0)
         for (uint32_t k = nslots; k < SR_BIN_SLOTS; ++k) s_tile[warp * SR_BIN_SLOTS + k] = 0xFFFFFFFFu;
@@ -1087,7 +1101,9 @@ struct SrOrdSetup {
 };
 static_assert(sizeof(SrOrdSetup) == 112, "seven float4");
 #define SR_ORD_LIST_CAP 4096  // group ids sorted in shared memory; longer lists are sorted in place in HBM
-#define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4)
+#define SR_ORD_RING 64  // fragments a warp can hold between coverage and shading (at most 31 carried over + 32 new)
+#define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4 + \
+                           SR_RASTER_WARPS * SR_ORD_RING * 16)
 
 struct SrOrdCtx {
     float4 *color;
@@ -1315,7 +1331,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     uint32_t *s_winner = reinterpret_cast<uint32_t *>(s_depth + SR_TILE_PIXELS);
     SrOrdSetup *s_setup = reinterpret_cast<SrOrdSetup *>(s_winner + SR_TILE_PIXELS);
     uint32_t *s_list = reinterpret_cast<uint32_t *>(s_setup + SR_RASTER_THREADS);
-    uint8_t *s_stencil = reinterpret_cast<uint8_t *>(s_list + SR_ORD_LIST_CAP);
+    uint4 *s_ring = reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + (threadIdx.x >> 5) * SR_ORD_RING;
+    uint8_t *s_stencil = reinterpret_cast<uint8_t *>(reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + SR_RASTER_WARPS * SR_ORD_RING);
     __shared__ uint32_t s_wcount[SR_RASTER_WARPS];
 
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
@@ -1417,6 +1434,100 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             if (hit) s_setup[base + __popc(mask & ((1u << lane) - 1u))] = su;
             __syncthreads();
             const uint32_t ry_lo = y0 + warp * RH, ry_hi = ry_lo + RH - 1;
+            if (!SrFsInfo<FS>::DISCARDS) {
+                // Deferred shading.  Whether a fragment passes depends only on coverage, z and the depth left by earlier
+                // fragments of its pixel (the shader cannot discard), so the in-order sweep only runs the cheap part --
+                // stencil step, exact barycentrics, depth test and depth update -- and queues every passing fragment
+                // {pixel, triangle, u, v} in the warp's ring.  As soon as 32 are queued the warp shades them together
+                // (all lanes busy whatever the triangle shapes are) and blends them into the tile in queue order; fragments
+                // of one pixel are queued in submission order because the pixel belongs to exactly one warp.
+                uint32_t head = 0, count = 0;  // (warp-uniform)
+                auto shade_and_blend = [&](uint32_t n) {
+                    float col[4];
+                    uint32_t li = 0xFFFFFFFFu - lane;  // distinct dummies for idle lanes
+                    if (lane < n) {
+                        const uint4 rec = s_ring[(head + lane) % SR_ORD_RING];
+                        li = rec.x & 0xffffu;
+                        const SrOrdSetup &q = s_setup[rec.x >> 16];
+                        const float u = __uint_as_float(rec.y), v = __uint_as_float(rec.z), w = 1.0f - u - v;  // triangle.rs:110
+                        const float4 A = q.A, B = q.B, C = q.C;
+                        float sv[4 + NP * 4 + 1];
+                        sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
+                        sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
+                        sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+                        sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+                        const SrVertexSet *vs = q.second ? &p.tris.vs1 : &p.tris.vs0;
+                        const uint32_t vi0 = q.vi[0], vi1 = q.vi[1], vi2 = q.vi[2];
+#pragma unroll
+                        for (int pl = 0; pl < NP; ++pl) {
+                            const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
+                            const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
+                            const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
+                            sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+                            sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                            sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+                            sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                        }
+                        sr_fragment_shader<FS>(p.fs, sv, col);
+                    }
+                    // blend in queue order: lanes that hold fragments of the same pixel take turns, lowest lane first
+                    const uint32_t peers = __match_any_sync(0xffffffffu, li);
+                    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                    const uint32_t rounds = __reduce_max_sync(0xffffffffu, lane < n ? (uint32_t)__popc(peers) : 0u);
+                    for (uint32_t r = 0; r < rounds; ++r) {
+                        if (lane < n && rank == r) {
+                            const float4 old = s_color[li];
+                            const float dstc[4] = {old.x, old.y, old.z, old.w};
+                            float outc[4];
+                            sr_blend(p.blend, col, dstc, outc);
+                            s_color[li] = make_float4(outc[0], outc[1], outc[2], outc[3]);
+                        }
+                        __syncwarp();
+                    }
+                    head = (head + n) % SR_ORD_RING;
+                    count -= n;
+                };
+                for (uint32_t s = 0; s < total; ++s) {
+                    const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
+                    const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
+                    const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
+                    if (r0 > r1) continue;
+                    const SrOrdSetup &q = s_setup[s];
+                    SrTri tr;
+                    tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
+                    tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
+                    tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
+                    tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                    const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
+                    const uint32_t bw = maxx - minx + 1, npix = bw * (r1 - r0 + 1), canonical = q.canonical;
+                    for (uint32_t base = 0; base < npix; base += 32) {
+                        const uint32_t i = base + lane;
+                        bool pass = false;
+                        uint32_t li = 0;
+                        float u = 0.0f, v = 0.0f, w;
+                        if (i < npix) {
+                            const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                            li = (py - y0) * SR_TILE_W + (px - x0);
+                            if (sr_ord_stencil_step(c, li) && sr_tri_bary(tr, px, py, u, v, w)) {
+                                const float z = sr_bary(u, z1, v, z2, w, z3);
+                                if (z < 0.0f && z >= s_depth[li]) {  // triangle.rs:120,126
+                                    pass = true;
+                                    s_depth[li] = z;
+                                    s_winner[li] = canonical + 1;
+                                }
+                            }
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                        if (pass)
+                            s_ring[(head + count + __popc(m & ((1u << lane) - 1u))) % SR_ORD_RING] =
+                                make_uint4(li | (s << 16), __float_as_uint(u), __float_as_uint(v), 0u);
+                        count += __popc(m);
+                        __syncwarp();
+                        if (count >= 32) shade_and_blend(32);
+                    }
+                }
+                if (count) shade_and_blend(count);  // the records refer to this batch's setups: drain before the next batch
+            } else {
             for (uint32_t s = 0; s < total; ++s) {
                 const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                 const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
@@ -1457,6 +1568,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, canonical);
                 }
                 __syncwarp();
+            }
             }
             __syncthreads();
         }
