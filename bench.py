@@ -397,11 +397,8 @@ def run_ours(args):
             line["cpu_baseline"], _, _ = cpu_reference_sample(args.config)
         print(json.dumps(line))
     barrier()
-    for cx, lfb, lp, lm, _ in lanes:
-        lp.destroy()
-        lm.destroy()
-        lfb.destroy()
-        cx.close()
+    for x in (pipe, gmesh, fb):
+        x.destroy()
     if world > 1:
         dist.destroy_process_group()
 
