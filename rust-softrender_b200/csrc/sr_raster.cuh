@@ -1116,6 +1116,12 @@ struct SrOrdCtx {
     uint8_t mesh_stencil;
 };
 
+// Lines and points: EVERY thread of the CTA walks every line / point of the tile in submission order, but only the
+// thread that owns a pixel plots it.  A pixel therefore still sees its fragments in order (one thread, program order),
+// while the fragments of one line are spread over the CTA: x + 7y separates the pixels of horizontal, vertical and
+// diagonal runs.  Walking is a few instructions per step; plotting (interpolation, shader, blend) is the expensive part.
+__device__ __forceinline__ bool sr_ord_owns(uint32_t x, uint32_t y) { return (x + 7u * y) % SR_RASTER_THREADS == threadIdx.x; }
+
 // stencil step (triangle.rs:91-99, line.rs:58-66, point.rs:52-60)
 __device__ __forceinline__ bool sr_ord_stencil_step(const SrOrdCtx &c, uint32_t li) {
     if (!c.has_stencil) return true;  // stencil type (): Always / Keep
@@ -1213,6 +1219,7 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
     // only this tile's pixels (the frame test also covers Wu's +1 neighbour past the last row/column,
     // where the reference would index out of bounds)
     if (x < (long long)c.x0 || x > (long long)c.xe || y < (long long)c.y0 || y > (long long)c.ye) return;
+    if (!sr_ord_owns((uint32_t)x, (uint32_t)y)) return;
     const uint32_t li = ((uint32_t)y - c.y0) * SR_TILE_W + ((uint32_t)x - c.x0);
     if (!sr_ord_stencil_step(c, li)) return;
     const float xf = (float)x + 0.5f, yf = (float)y + 0.5f;
@@ -1236,32 +1243,59 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
 
 __device__ __forceinline__ double sr_fract64(double x) { return x - trunc(x); }
 
-// rasterize_line (src/pipeline/stages/rasterization/line.rs:22-119) for one line, executed by one thread
+// rasterize_line (src/pipeline/stages/rasterization/line.rs:22-119).  Setup (fetch, Liang-Barsky clip against the frame,
+// clipped length) runs once per line, one thread each, 256 lines at a time; the record is what the walk needs.
+struct SrOrdLineRec {
+    float4 ps, pe;   // unclipped end-point positions
+    float cl[4];     // clipped end points (line.rs:51)
+    float d;         // clipped length (line.rs:52)
+    uint32_t vi0, vi1, canonical, second, valid;
+    uint32_t pad[2];
+};
+static_assert(sizeof(SrOrdLineRec) <= sizeof(SrOrdSetup), "line records reuse the triangle records' shared memory");
+__device__ __forceinline__ void sr_ord_line_setup(const SrTileParams &p, uint32_t t, SrOrdLineRec &r) {
+    const SrVertexSet *vs;
+    uint32_t vi[2];
+    sr_prim_vertices<2>(p.lines, t, vs, vi);
+    r.ps = __ldg(vs->pos + vi[0]);
+    r.pe = __ldg(vs->pos + vi[1]);
+    r.vi0 = vi[0]; r.vi1 = vi[1];
+    r.second = t < p.lines.n0 ? 0u : 1u;
+    r.canonical = p.line_base + sr_prim_canonical(p.lines, t, 0);
+    r.valid = 0;
+    // bounds = the one frame-sized tile ((0,0),(w-1,h-1)) cast to float (fragment.rs:255-258)
+    if (!sr_liang_barsky(r.ps.x, r.ps.y, r.pe.x, r.pe.y, 0.0f, 0.0f, (float)(p.fb.width - 1), (float)(p.fb.height - 1), r.cl)) return;
+    if (!isfinite(r.cl[0]) || !isfinite(r.cl[1]) || !isfinite(r.cl[2]) || !isfinite(r.cl[3])) return;  // reference would panic
+    r.d = sr_hypot32(r.cl[0] - r.cl[2], r.cl[1] - r.cl[3]);
+    r.valid = 1;
+}
+// the walk of one line: executed by every thread of the CTA, pixels are plotted by their owner (sr_ord_owns)
 template <int FS>
-__device__ void sr_ord_line(const SrOrdCtx &c, uint32_t t) {
+__device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
     const SrTileParams &p = *c.p;
     SrLineCtx L;
-    sr_prim_vertices<2>(p.lines, t, L.vs, L.vi);
-    L.ps = __ldg(L.vs->pos + L.vi[0]);
-    L.pe = __ldg(L.vs->pos + L.vi[1]);
-    L.canonical = p.line_base + sr_prim_canonical(p.lines, t, 0);
-    float cl[4];
-    // bounds = the one frame-sized tile ((0,0),(w-1,h-1)) cast to float (fragment.rs:255-258)
-    if (!sr_liang_barsky(L.ps.x, L.ps.y, L.pe.x, L.pe.y, 0.0f, 0.0f, (float)(p.fb.width - 1), (float)(p.fb.height - 1), cl)) return;
-    if (!isfinite(cl[0]) || !isfinite(cl[1]) || !isfinite(cl[2]) || !isfinite(cl[3])) return;  // reference would panic
+    L.vs = r.second ? &p.lines.vs1 : &p.lines.vs0;
+    L.vi[0] = r.vi0; L.vi[1] = r.vi1;
+    L.ps = r.ps; L.pe = r.pe;
+    L.canonical = r.canonical;
+    const float cl[4] = {r.cl[0], r.cl[1], r.cl[2], r.cl[3]};
     L.x1 = cl[0]; L.y1 = cl[1];
-    L.d = sr_hypot32(cl[0] - cl[2], cl[1] - cl[3]);
+    L.d = r.d;
+    // cheap inline filter in front of the (non-inlined) plot: this tile's pixels that this thread owns
+    const int tx0 = (int)c.x0, tx1 = (int)c.xe, ty0 = (int)c.y0, ty1 = (int)c.ye;
+    auto mine = [&](int x, int y) { return x >= tx0 && x <= tx1 && y >= ty0 && y <= ty1 && sr_ord_owns((uint32_t)x, (uint32_t)y); };
     if (!p.aa_lines) {
-        // draw_line_bresenham (line.rs:125-151)
-        long long bx0 = (long long)cl[0], by0 = (long long)cl[1];
-        const long long bx1 = (long long)cl[2], by1 = (long long)cl[3];
-        const long long dx = llabs(bx1 - bx0), dy = -llabs(by1 - by0);
-        const long long sx = bx0 < bx1 ? 1 : -1, sy = by0 < by1 ? 1 : -1;
-        long long err = dx + dy;
+        // draw_line_bresenham (line.rs:125-151).  The reference walks in i64; the clipped end points lie inside the frame
+        // (< 2^16), so every quantity below fits 32 bits with the same decisions.
+        int bx0 = (int)cl[0], by0 = (int)cl[1];
+        const int bx1 = (int)cl[2], by1 = (int)cl[3];
+        const int dx = abs(bx1 - bx0), dy = -abs(by1 - by0);
+        const int sx = bx0 < bx1 ? 1 : -1, sy = by0 < by1 ? 1 : -1;
+        int err = dx + dy;
         while (true) {
-            sr_ord_plot_line<FS>(c, L, bx0, by0, 1.0);
+            if (mine(bx0, by0)) sr_ord_plot_line<FS>(c, L, bx0, by0, 1.0);
             if (bx0 == bx1 && by0 == by1) break;
-            const long long e2 = 2 * err;
+            const int e2 = 2 * err;
             if (e2 >= dy) { err += dy; bx0 += sx; }
             if (e2 <= dx) { err += dx; by0 += sy; }
         }
@@ -1274,8 +1308,9 @@ __device__ void sr_ord_line(const SrOrdCtx &c, uint32_t t) {
         const double dx = wx1 - wx0, dy = wy1 - wy0;
         const double gradient = dx < 0.0001 ? 1.0 : dy / dx;
         auto plot_float = [&](double a, double b, double opacity) {
-            if (steep) sr_ord_plot_line<FS>(c, L, (long long)b, (long long)a, opacity);
-            else sr_ord_plot_line<FS>(c, L, (long long)a, (long long)b, opacity);
+            // (the coordinates are within a pixel of the frame: the i64 casts of the reference fit 32 bits)
+            const int x = steep ? (int)b : (int)a, y = steep ? (int)a : (int)b;
+            if (mine(x, y)) sr_ord_plot_line<FS>(c, L, x, y, opacity);
         };
         // both arms of the reference's `if steep` plot (x, y) / (y, x); plot_float takes (x_major, y_minor)
         double xend = round(wx0);
@@ -1300,27 +1335,31 @@ __device__ void sr_ord_line(const SrOrdCtx &c, uint32_t t) {
     }
 }
 
-// rasterize_point (src/pipeline/stages/rasterization/point.rs:21-86); membership in this tile was decided by the rect
+// rasterize_point (src/pipeline/stages/rasterization/point.rs:21-86); membership in this tile was decided by the rect.
+// Fetched one thread per point, 256 at a time; every thread then scans the records and plots the pixels it owns.
+struct SrOrdPointRec {
+    float4 P;
+    uint32_t vi, canonical, second, valid;
+};
 template <int FS>
-__device__ __noinline__ void sr_ord_point(const SrOrdCtx &c, uint32_t t) {
+__device__ __forceinline__ void sr_ord_point(const SrOrdCtx &c, const SrOrdPointRec &r) {
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     const SrTileParams &p = *c.p;
-    const SrVertexSet *vs;
-    uint32_t vi[1];
-    sr_prim_vertices<1>(p.points, t, vs, vi);
-    const float4 P = __ldg(vs->pos + vi[0]);
+    const float4 P = r.P;
     const uint32_t px = __float2uint_rz(P.x), py = __float2uint_rz(P.y);
     if (px < c.x0 || px > c.xe || py < c.y0 || py > c.ye) return;
+    if (!sr_ord_owns(px, py)) return;
     const uint32_t li = (py - c.y0) * SR_TILE_W + (px - c.x0);
     if (!sr_ord_stencil_step(c, li)) return;
+    const SrVertexSet *vs = r.second ? &p.points.vs1 : &p.points.vs0;
     float sv[4 + NP * 4 + 1];
     sv[0] = P.x; sv[1] = P.y; sv[2] = P.z; sv[3] = P.w;
 #pragma unroll
     for (int pl = 0; pl < NP; ++pl) {
-        const float4 k = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
+        const float4 k = __ldg(vs->attr + sr_attr_at(vs->np, r.vi, pl));
         sv[4 + pl * 4 + 0] = k.x; sv[4 + pl * 4 + 1] = k.y; sv[4 + pl * 4 + 2] = k.z; sv[4 + pl * 4 + 3] = k.w;
     }
-    sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, p.point_base + sr_prim_canonical(p.points, t, 0));
+    sr_ord_shade_write<FS>(c, li, sv, false, 1.0f, r.canonical);
 }
 
 template <int FS>
@@ -1574,7 +1613,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         }
     }
 
-    // ---------------- lines, then points (fragment.rs:284-311): one thread walks them in order ----------------
+    // ---------------- lines, then points (fragment.rs:284-311): walked in order, plotted by pixel owner (sr_ord_owns) ----------------
     for (int kind = 2; kind >= 1; --kind) {
         const uint32_t Ln = kind == 2 ? LL : LP;
         if (Ln == 0) continue;
@@ -1586,19 +1625,52 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         }
         sr_block_sort(lst, Ln);
         __syncthreads();
-        if (tid == 0) {
+        {
             const uint32_t nprim = kind == 2 ? p.nlines : p.npoints;
             const uint32_t *rects = kind == 2 ? p.line_rects : p.point_rects;
-            for (uint32_t gi = 0; gi < Ln; ++gi) {
-                const uint32_t g = lst[gi];
-                for (uint32_t j = 0; j < SR_GROUP; ++j) {
-                    const uint32_t t = g * SR_GROUP + j;
-                    if (t >= nprim) break;
-                    const uint32_t rect = __ldg(rects + t);
-                    if (rect == SR_RECT_INVALID || !sr_rect_hits(rect, tx, ty)) continue;
-                    if (kind == 2) sr_ord_line<FS>(c, t);
-                    else sr_ord_point<FS>(c, t);
+            SrOrdLineRec *s_line = reinterpret_cast<SrOrdLineRec *>(s_setup);
+            SrOrdPointRec *s_point = reinterpret_cast<SrOrdPointRec *>(s_setup);
+            // 8 groups = 256 primitives per batch: fetched and set up one thread each (the dependent gathers of a whole batch
+            // overlap), then walked in list order -- thread tid holds primitive lst[gb + tid/32] * 32 + tid%32 and the list
+            // is sorted, so record order is submission order
+            for (uint32_t gb = 0; gb < Ln; gb += SR_RASTER_WARPS) {
+                const uint32_t gi = gb + warp;
+                bool hit = false;
+                uint32_t t = 0;
+                if (gi < Ln) {
+                    t = lst[gi] * SR_GROUP + lane;
+                    const uint32_t rect = t < nprim ? __ldg(rects + t) : SR_RECT_INVALID;
+                    hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
                 }
+                if (kind == 2) {
+                    SrOrdLineRec r;
+                    r.valid = 0;
+                    if (hit) sr_ord_line_setup(p, t, r);
+                    s_line[tid] = r;
+                } else {
+                    SrOrdPointRec r;
+                    r.valid = 0;
+                    if (hit) {
+                        const SrVertexSet *vs;
+                        uint32_t vi[1];
+                        sr_prim_vertices<1>(p.points, t, vs, vi);
+                        r.P = __ldg(vs->pos + vi[0]);
+                        r.vi = vi[0];
+                        r.second = t < p.points.n0 ? 0u : 1u;
+                        r.canonical = p.point_base + sr_prim_canonical(p.points, t, 0);
+                        r.valid = 1;
+                    }
+                    s_point[tid] = r;
+                }
+                __syncthreads();
+                for (uint32_t k = 0; k < SR_RASTER_THREADS; ++k) {
+                    if (kind == 2) {
+                        if (s_line[k].valid) sr_ord_line<FS>(c, s_line[k]);
+                    } else {
+                        if (s_point[k].valid) sr_ord_point<FS>(c, s_point[k]);
+                    }
+                }
+                __syncthreads();
             }
         }
         __syncthreads();
