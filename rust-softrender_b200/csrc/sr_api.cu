@@ -594,16 +594,12 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         mp.large_ids = lids->as<uint32_t>();
         mp.large_rects = lrects->as<uint32_t>();
         mp.tile_count = count->as<uint32_t>();
-        // micro_precheck: bit 0 = per-fragment key pre-check before the atomic, bit 1 = early depth rejection OFF,
-        // bit 2 = one triangle per thread (k_micro) instead of two with batched loads (k_micro_pair; early depth always on)
+        // micro_precheck: bit 0 = per-fragment key pre-check before the atomic, bit 1 = early depth rejection OFF
         const uint32_t grid = ceil_div(tp.ntris, SR_MICRO_THREADS);
-        const uint32_t pair_grid = ceil_div(ceil_div(tp.ntris, 2), SR_MICRO_THREADS);
-        switch (c->micro_precheck & 7u) {
-            case 0: SR_LAUNCH(c, (k_micro_pair<false>), pair_grid, SR_MICRO_THREADS, 0, mp); break;
-            case 1: SR_LAUNCH(c, (k_micro_pair<true>), pair_grid, SR_MICRO_THREADS, 0, mp); break;
-            case 4: SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp); break;
-            case 5: SR_LAUNCH(c, (k_micro<true, true>), grid, SR_MICRO_THREADS, 0, mp); break;
-            case 2: case 6: SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp); break;
+        switch (c->micro_precheck & 3u) {
+            case 0: SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp); break;
+            case 1: SR_LAUNCH(c, (k_micro<true, true>), grid, SR_MICRO_THREADS, 0, mp); break;
+            case 2: SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp); break;
             default: SR_LAUNCH(c, (k_micro<true, false>), grid, SR_MICRO_THREADS, 0, mp); break;
         }
     }
@@ -743,7 +739,7 @@ int sr_context_set_micro(sr_context *c, uint32_t area, uint32_t min_triangles, u
     c->micro_auto = area == SR_MICRO_AREA_AUTO;
     if (!c->micro_auto) c->micro_area = area;
     c->micro_min_tris = min_triangles;
-    c->micro_precheck = precheck & 7u;
+    c->micro_precheck = precheck & 3u;
     return SR_OK;
 }
 int sr_context_set_stage_timing(sr_context *c, int enable) {

@@ -531,9 +531,6 @@ __device__ __forceinline__ bool sr_micro_box(const SrTri &tr, float z1, float z2
 // 128-thread CTAs, 12 per SM (40 registers): the finer CTA granularity keeps ~4 more warps resident than 6 x 256
 #define SR_MICRO_THREADS 128
 #define SR_MICRO_MIN_BLOCKS 12
-#ifndef SR_MICRO_PAIR_MIN_BLOCKS
-#define SR_MICRO_PAIR_MIN_BLOCKS 10
-#endif
 // Everything k_micro does for one triangle once its three screen positions are known (warp-collective: every lane of
 // the warp calls it, `valid` = the lane holds a triangle).
 template <bool PRECHECK, bool EARLYZ>
@@ -754,113 +751,6 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     if (total > capacity) return;  // the lists do not fit: the host re-runs this launch with a larger arena
 #pragma unroll
     for (int k = 0; k < PER; ++k) spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
-}
-
-// Two triangles per thread.  The front end is bound by the latency of three dependent round trips (indices -> positions ->
-// depth keys) at the occupancy the registers allow; a thread that owns triangles 2i and 2i+1 issues each of the three
-// levels for BOTH triangles before it consumes any of them, which halves the round trips per triangle at the same
-// number of resident warps.  The common case -- tightened candidate box of at most 3x3 pixels, unsharded frame -- is
-// handled inline (early depth rejection from the batched key reads, then sr_micro_box); everything else falls through
-// to sr_micro_triangle, which every lane calls for both triangles anyway (it is warp-collective).
-template <bool PRECHECK>
-__global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_PAIR_MIN_BLOCKS) k_micro_pair(const __grid_constant__ SrMicroParams p) {
-    const uint32_t t0 = (blockIdx.x * SR_MICRO_THREADS + threadIdx.x) * 2u;
-    const uint32_t pitch = p.ntx * SR_TILE_W;
-    float4 P[2][3];
-    bool valid[2];
-    {
-        uint32_t vi[2][3];
-        const float4 *base[2];
-        if (t0 + 1 < p.src.n0) {  // both indexed: 24 contiguous, 8-byte aligned bytes
-            const uint2 *q = reinterpret_cast<const uint2 *>(p.src.indices + (uint64_t)t0 * 3);
-            const uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-            vi[0][0] = a.x; vi[0][1] = a.y; vi[0][2] = b.x; vi[1][0] = b.y; vi[1][1] = c.x; vi[1][2] = c.y;
-            base[0] = base[1] = p.src.vs0.pos;
-            valid[0] = valid[1] = true;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t t = t0 + k;
-                valid[k] = t < p.ntris;
-                const SrVertexSet *vs = &p.src.vs0;
-                vi[k][0] = vi[k][1] = vi[k][2] = 0;
-                if (valid[k]) sr_prim_vertices<3>(p.src, t, vs, vi[k]);
-                base[k] = vs->pos;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) P[k][j] = valid[k] ? __ldg(base[k] + vi[k][j]) : make_float4(0, 0, 0, 0);
-    }
-    // classification of the common case + batched key reads
-    bool simple[2];
-    int lx[2], ly[2], hx[2], hy[2];
-    uint32_t kb[2], key[2][9];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float4 &A = P[k][0], &B = P[k][1], &C = P[k][2];
-        simple[k] = false;
-        lx[k] = ly[k] = 0; hx[k] = hy[k] = -1;
-        kb[k] = 0xFFFFFFFFu;
-        bool culled = false;
-        if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
-            const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
-            culled = (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) == p.cull;
-        }
-        if (culled) valid[k] = false;
-        if (valid[k] && p.shard_world == 1 && p.micro_area != 0) {
-            const float det = (B.y - C.y) * (A.x - C.x) + (C.x - B.x) * (A.y - C.y);  // == sr_tri_setup(...).det
-            const float xmin = fminf(fminf(A.x, B.x), C.x), xmax = fmaxf(fmaxf(A.x, B.x), C.x);
-            const float ymin = fminf(fminf(A.y, B.y), C.y), ymax = fmaxf(fmaxf(A.y, B.y), C.y);
-            if (sr_tightening_applies(xmin, xmax, ymin, ymax, det)) {
-                lx[k] = max(0, sr_tight_lo(xmin)); ly[k] = max(0, sr_tight_lo(ymin));
-                hx[k] = min((int)p.width - 1, sr_tight_hi(xmax)); hy[k] = min((int)p.height - 1, sr_tight_hi(ymax));
-                if (lx[k] > hx[k] || ly[k] > hy[k]) valid[k] = false;  // no candidate pixel: nothing to draw
-                else if (hx[k] - lx[k] < 3 && hy[k] - ly[k] < 3) {
-                    simple[k] = true;
-                    const float zmax = fmaxf(fmaxf(A.z, B.z), C.z), zmin = fminf(fminf(A.z, B.z), C.z);
-                    const float zb = zmax + zmin * -0x1p-20f;  // upper bound of every depth the triangle can produce (sr_micro_occluded)
-                    if (zb < 0.0f) kb[k] = ~__float_as_uint(zb);
-                }
-            }
-        }
-        const uint32_t cw = (uint32_t)(hx[k] - lx[k] + 1), ch = (uint32_t)(hy[k] - ly[k] + 1);
-        const unsigned long long *row = p.vis + (uint32_t)ly[k] * pitch + (uint32_t)lx[k];
-#pragma unroll
-        for (uint32_t r = 0; r < 3; ++r)
-#pragma unroll
-            for (uint32_t c = 0; c < 3; ++c) {
-                key[k][r * 3 + c] = 0xFFFFFFFFu;
-                if (simple[k] && kb[k] != 0xFFFFFFFFu && r < ch && c < cw) key[k][r * 3 + c] = sr_ld_depth_key(row + r * pitch + c);
-            }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (!simple[k]) continue;
-        uint32_t kmin = key[k][0];
-#pragma unroll
-        for (int j = 1; j < 9; ++j) kmin = min(kmin, key[k][j]);
-        if (kb[k] < kmin) continue;  // early depth rejection: every candidate pixel already holds a nearer depth
-        const float4 &A = P[k][0], &B = P[k][1], &C = P[k][2];
-        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
-        if (sr_micro_box(tr, A.z, B.z, C.z, lx[k], ly[k], hx[k], hy[k], t0 + k, p.vis, pitch)) {
-            sr_raster_box<false>(tr, A.z, B.z, C.z, (uint32_t)lx[k], (uint32_t)ly[k], (uint32_t)(hx[k] - lx[k] + 1), (uint32_t)(hy[k] - ly[k] + 1),
-                                 t0 + k, [&](uint32_t px, uint32_t py, unsigned long long kk) {
-                                     unsigned long long *slot = p.vis + sr_vis_index(px, py, p.ntx);
-                                     if (PRECHECK && !(kk > sr_ld_relaxed_u64(slot))) return;
-                                     sr_red_max_u64(slot, kk);
-                                 });
-        }
-    }
-    // everything that is not the common case (and the warp-collective bookkeeping of the large triangles)
-#pragma unroll 1
-    for (int k = 0; k < 2; ++k) {
-        const float4 A = k ? P[1][0] : P[0][0], B = k ? P[1][1] : P[0][1], C = k ? P[1][2] : P[0][2];
-        const bool v = (k ? valid[1] : valid[0]) && !(k ? simple[1] : simple[0]);
-        if (!__any_sync(0xffffffffu, v)) continue;
-        sr_micro_triangle<PRECHECK, true>(p, t0 + k, v, A, B, C, threadIdx.x & 31);
-    }
 }
 
 // second pass over the large triangles only: write their ids into the per-tile lists

@@ -57,7 +57,7 @@ class Context:
     def set_micro(self, area: int = 0xFFFFFFFF, min_triangles: int = 65536, precheck: int = 0):
         """Tuning of the opaque triangle path (results never depend on it): see sr_context_set_micro.
         precheck: bit 0 = per-fragment key pre-check, bit 1 = early depth rejection off (library default 0)."""
-        check(lib.sr_context_set_micro(self.h, area, min_triangles, int(precheck) & 7))
+        check(lib.sr_context_set_micro(self.h, area, min_triangles, int(precheck) & 3))
 
     def set_stage_timing(self, enable: bool = True):
         """Record the per-stage CUDA events `stage_times` / `stage_timestamps` read (off by default)."""
