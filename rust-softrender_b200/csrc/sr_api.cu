@@ -501,7 +501,7 @@ static int settle(sr_context *c) {
 // Where the split between the per-triangle front end and the per-tile lists lies.  One thread walking a whole bounding box
 // is the cheapest way through a triangle as long as there are enough triangles to fill the machine (148 SMs x 2048
 // threads); below that the serial walks are the critical path and the tile kernel's cooperative sweep wins.  Measured
-// on 4-layer grids at 3840x2160 (scratch/area_sweep.py): 52k triangles of 280 px^2: 0.30 ms at area 16, 0.28 ms at 1024;
+// on 4-layer grids at 3840x2160 (profiles/scripts/area_sweep.py): 52k triangles of 280 px^2: 0.30 ms at area 16, 0.28 ms at 1024;
 // 100k x 146 px^2: 0.36 -> 0.25; 207k x 70 px^2: 0.46 -> 0.23; 1M x 15 px^2: 0.67 -> 0.23; 31k x 464 px^2: 0.27 -> 0.33.
 static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 1024u : SR_MICRO_AREA_DEFAULT; }
 
