@@ -1116,11 +1116,15 @@ struct SrOrdCtx {
     uint8_t mesh_stencil;
 };
 
-// Lines and points: EVERY thread of the CTA walks every line / point of the tile in submission order, but only the
-// thread that owns a pixel plots it.  A pixel therefore still sees its fragments in order (one thread, program order),
-// while the fragments of one line are spread over the CTA: x + 7y separates the pixels of horizontal, vertical and
-// diagonal runs.  Walking is a few instructions per step; plotting (interpolation, shader, blend) is the expensive part.
-__device__ __forceinline__ bool sr_ord_owns(uint32_t x, uint32_t y) { return (x + 7u * y) % SR_RASTER_THREADS == threadIdx.x; }
+// Lines and points: the warps of the CTA walk the lines / points of the tile in submission order, but only the thread that
+// owns a pixel plots it -- warp = band of SR_TILE_H / SR_RASTER_WARPS tile rows, lane = column mod 32.  A pixel therefore
+// still sees its fragments in order (one thread, program order) while the fragments of one line are spread over the lanes,
+// and a warp skips every line that does not cross its band.  Walking is a few instructions per step; plotting
+// (interpolation, shader, blend) is the expensive part.
+#define SR_ORD_BAND (SR_TILE_H / SR_RASTER_WARPS)
+__device__ __forceinline__ bool sr_ord_owns(const SrOrdCtx &c, uint32_t x, uint32_t y) {  // (x, y) inside the tile
+    return (y - c.y0) / SR_ORD_BAND == (threadIdx.x >> 5) && (x & 31u) == (threadIdx.x & 31u);
+}
 
 // stencil step (triangle.rs:91-99, line.rs:58-66, point.rs:52-60)
 __device__ __forceinline__ bool sr_ord_stencil_step(const SrOrdCtx &c, uint32_t li) {
@@ -1219,7 +1223,7 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
     // only this tile's pixels (the frame test also covers Wu's +1 neighbour past the last row/column,
     // where the reference would index out of bounds)
     if (x < (long long)c.x0 || x > (long long)c.xe || y < (long long)c.y0 || y > (long long)c.ye) return;
-    if (!sr_ord_owns((uint32_t)x, (uint32_t)y)) return;
+    if (!sr_ord_owns(c, (uint32_t)x, (uint32_t)y)) return;
     const uint32_t li = ((uint32_t)y - c.y0) * SR_TILE_W + ((uint32_t)x - c.x0);
     if (!sr_ord_stencil_step(c, li)) return;
     const float xf = (float)x + 0.5f, yf = (float)y + 0.5f;
@@ -1281,9 +1285,15 @@ __device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
     const float cl[4] = {r.cl[0], r.cl[1], r.cl[2], r.cl[3]};
     L.x1 = cl[0]; L.y1 = cl[1];
     L.d = r.d;
-    // cheap inline filter in front of the (non-inlined) plot: this tile's pixels that this thread owns
-    const int tx0 = (int)c.x0, tx1 = (int)c.xe, ty0 = (int)c.y0, ty1 = (int)c.ye;
-    auto mine = [&](int x, int y) { return x >= tx0 && x <= tx1 && y >= ty0 && y <= ty1 && sr_ord_owns((uint32_t)x, (uint32_t)y); };
+    // cheap inline filter in front of the (non-inlined) plot: the pixels of this warp's band that this lane owns
+    const int tx0 = (int)c.x0, tx1 = (int)c.xe;
+    const int band_lo = (int)c.y0 + (int)(threadIdx.x >> 5) * SR_ORD_BAND, band_hi = min(band_lo + SR_ORD_BAND - 1, (int)c.ye);
+    {   // the whole line misses the band (one pixel of slack for Wu's second row): nothing to walk for this warp
+        const int ya = (int)cl[1], yb = (int)cl[3];
+        if (max(ya, yb) + 1 < band_lo || min(ya, yb) - 1 > band_hi) return;
+    }
+    const int lane = (int)(threadIdx.x & 31u);
+    auto mine = [&](int x, int y) { return y >= band_lo && y <= band_hi && x >= tx0 && x <= tx1 && (x & 31) == lane; };
     if (!p.aa_lines) {
         // draw_line_bresenham (line.rs:125-151).  The reference walks in i64; the clipped end points lie inside the frame
         // (< 2^16), so every quantity below fits 32 bits with the same decisions.
@@ -1295,6 +1305,7 @@ __device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
         while (true) {
             if (mine(bx0, by0)) sr_ord_plot_line<FS>(c, L, bx0, by0, 1.0);
             if (bx0 == bx1 && by0 == by1) break;
+            if (sy > 0 ? by0 > band_hi : by0 < band_lo) break;  // y is monotonic: the walk has left this warp's band for good
             const int e2 = 2 * err;
             if (e2 >= dy) { err += dy; bx0 += sx; }
             if (e2 <= dx) { err += dx; by0 += sy; }
@@ -1348,7 +1359,7 @@ __device__ __forceinline__ void sr_ord_point(const SrOrdCtx &c, const SrOrdPoint
     const float4 P = r.P;
     const uint32_t px = __float2uint_rz(P.x), py = __float2uint_rz(P.y);
     if (px < c.x0 || px > c.xe || py < c.y0 || py > c.ye) return;
-    if (!sr_ord_owns(px, py)) return;
+    if (!sr_ord_owns(c, px, py)) return;
     const uint32_t li = (py - c.y0) * SR_TILE_W + (px - c.x0);
     if (!sr_ord_stencil_step(c, li)) return;
     const SrVertexSet *vs = r.second ? &p.points.vs1 : &p.points.vs0;
@@ -1642,33 +1653,42 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     const uint32_t rect = t < nprim ? __ldg(rects + t) : SR_RECT_INVALID;
                     hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
                 }
+                // records of the primitives that touch this tile, compacted in list order (ballot + warp counts)
+                SrOrdLineRec lr;
+                SrOrdPointRec pr;
                 if (kind == 2) {
-                    SrOrdLineRec r;
-                    r.valid = 0;
-                    if (hit) sr_ord_line_setup(p, t, r);
-                    s_line[tid] = r;
-                } else {
-                    SrOrdPointRec r;
-                    r.valid = 0;
-                    if (hit) {
-                        const SrVertexSet *vs;
-                        uint32_t vi[1];
-                        sr_prim_vertices<1>(p.points, t, vs, vi);
-                        r.P = __ldg(vs->pos + vi[0]);
-                        r.vi = vi[0];
-                        r.second = t < p.points.n0 ? 0u : 1u;
-                        r.canonical = p.point_base + sr_prim_canonical(p.points, t, 0);
-                        r.valid = 1;
-                    }
-                    s_point[tid] = r;
+                    lr.valid = 0;
+                    if (hit) sr_ord_line_setup(p, t, lr);
+                    hit = hit && lr.valid;
+                } else if (hit) {
+                    const SrVertexSet *vs;
+                    uint32_t vi[1];
+                    sr_prim_vertices<1>(p.points, t, vs, vi);
+                    pr.P = __ldg(vs->pos + vi[0]);
+                    pr.vi = vi[0];
+                    pr.second = t < p.points.n0 ? 0u : 1u;
+                    pr.canonical = p.point_base + sr_prim_canonical(p.points, t, 0);
+                    pr.valid = 1;
+                }
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_wcount[warp] = __popc(mask);
+                __syncthreads();
+                uint32_t base = 0, total = 0;
+#pragma unroll
+                for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) {
+                    const uint32_t cnt = s_wcount[w2];
+                    if (w2 < warp) base += cnt;
+                    total += cnt;
+                }
+                if (hit) {
+                    const uint32_t at = base + __popc(mask & ((1u << lane) - 1u));
+                    if (kind == 2) s_line[at] = lr;
+                    else s_point[at] = pr;
                 }
                 __syncthreads();
-                for (uint32_t k = 0; k < SR_RASTER_THREADS; ++k) {
-                    if (kind == 2) {
-                        if (s_line[k].valid) sr_ord_line<FS>(c, s_line[k]);
-                    } else {
-                        if (s_point[k].valid) sr_ord_point<FS>(c, s_point[k]);
-                    }
+                for (uint32_t k = 0; k < total; ++k) {
+                    if (kind == 2) sr_ord_line<FS>(c, s_line[k]);
+                    else sr_ord_point<FS>(c, s_point[k]);
                 }
                 __syncthreads();
             }
