@@ -137,7 +137,7 @@ def run_reference(args):
         "impl": "reference", "metric": f"Mtris/s at {w}x{h}", "value": base["value"], "unit": "Mtris/s",
         "frames_per_s": base["value"] * 1e6 / (2 * nx * ny * layers),
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.config, "width": w, "height": h, "triangles": 2 * nx * ny * layers,
                    "shader": "suzanne Blinn-Phong", "depth_test": True,
                    "note": "restated reference CPU path on a bounded sample (the Rust reference cannot be built here)"},
@@ -370,7 +370,7 @@ def run_ours(args):
             "frames_per_s": world * 1e3 / ms_per_step,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3 * len(flights)), "ms_per_step": ms_per_step,
             "single_stream_ms_per_frame": single_ms,
-            "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.config, "width": w, "height": h, "triangles": ntris, "vertices": nverts,
                        "shader": "suzanne Blinn-Phong", "depth_test": True, "frames_in_flight": in_flight_used,
