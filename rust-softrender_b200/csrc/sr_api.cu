@@ -394,24 +394,27 @@ static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, co
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown fragment shader %u", fs);
 }
-template <int FS>
+template <int FS, bool EXTRA>
 static int launch_opaque(sr_context *c, uint32_t ntiles_owned, const SrOpaqueParams &p) {
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
-        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
         configured[c->device & 15] = true;
     }
-    SR_LAUNCH(c, k_tile_opaque<FS>, ntiles_owned, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
+    SR_LAUNCH(c, (k_tile_opaque<FS, EXTRA>), ntiles_owned, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
     return SR_OK;
 }
 static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+    const bool extra = p.nlines + p.npoints > 0;
+#define SR_OPQ_CASE(F) case F: return extra ? launch_opaque<F, true>(c, ntiles_owned, p) : launch_opaque<F, false>(c, ntiles_owned, p)
     switch (fs) {
-        case SR_FS_FLAT: return launch_opaque<SR_FS_FLAT>(c, ntiles_owned, p);
-        case SR_FS_SUZANNE: return launch_opaque<SR_FS_SUZANNE>(c, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE: return launch_opaque<SR_FS_FULL_EXAMPLE>(c, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
-        case SR_FS_GREEN: return launch_opaque<SR_FS_GREEN>(c, ntiles_owned, p);
+        SR_OPQ_CASE(SR_FS_FLAT);
+        SR_OPQ_CASE(SR_FS_SUZANNE);
+        SR_OPQ_CASE(SR_FS_FULL_EXAMPLE);
+        SR_OPQ_CASE(SR_FS_FULL_EXAMPLE_TEXTURED);
+        SR_OPQ_CASE(SR_FS_GREEN);
     }
+#undef SR_OPQ_CASE
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
 }
 
@@ -509,10 +512,10 @@ static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 102
 // rasterisation of small triangles + compaction/counting of the large ones), per-tile lists of the large
 // triangles, then the tile kernel (large triangles + resolve + single write-back).
 static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
-                            const std::vector<Buf> &keep) {
+                            const std::vector<Buf> &keep, bool extra) {
     const uint32_t ntiles = fb->ntx * fb->nty;
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
-    if (c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
+    if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
         record(c, 7);
         auto q = std::make_unique<PendingOpaque>();
         SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &q->off));
@@ -557,7 +560,8 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         return SR_OK;
     }
     const uint32_t micro_area = c->micro_auto ? sr_micro_area_for(tp.ntris) : c->micro_area;
-    const bool use_micro = micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris);
+    // `extra`: the draw's non-antialiased lines and points go through the visibility buffer as well (k_lines_vis, k_points_vis)
+    const bool use_micro = extra || (micro_area > 0 && tp.ntris > 0 && (fb->pending_clear || tp.ntris >= c->micro_min_tris));
     if (use_micro) {
         if (!fb->vis_buf) {
             SR_TRY(c->alloc((size_t)ntiles * SR_TILE_PIXELS * 8, &fb->vis_buf));
@@ -588,7 +592,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         mp.cull = cull;
         mp.width = fb->width; mp.height = fb->height; mp.ntx = fb->ntx; mp.nty = fb->nty;
         mp.shard_rank = c->shard_rank; mp.shard_world = c->shard_world;
-        mp.micro_area = use_micro ? micro_area : 0u;
+        mp.micro_area = use_micro ? micro_area : 0u;  // (0 with `extra` and the split switched off: every triangle through the lists)
         mp.vis = use_micro ? fb->vis_buf->as<unsigned long long>() : nullptr;
         mp.large_count = lcount->as<uint32_t>();
         mp.large_ids = lids->as<uint32_t>();
@@ -602,6 +606,17 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
             case 2: SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp); break;
             default: SR_LAUNCH(c, (k_micro<true, false>), grid, SR_MICRO_THREADS, 0, mp); break;
         }
+    }
+    if (extra) {
+        SrExtraParams ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.lines = tp.lines; ep.points = tp.points;
+        ep.nlines = tp.nlines; ep.npoints = tp.npoints; ep.ntris = tp.ntris;
+        ep.width = fb->width; ep.height = fb->height; ep.ntx = fb->ntx;
+        ep.shard_rank = c->shard_rank; ep.shard_world = c->shard_world;
+        ep.vis = fb->vis_buf->as<unsigned long long>();
+        if (tp.nlines) SR_LAUNCH(c, k_lines_vis, ceil_div(tp.nlines, 128), 128, 0, ep);
+        if (tp.npoints) SR_LAUNCH(c, k_points_vis, ceil_div(tp.npoints, 128), 128, 0, ep);
     }
     record(c, 5);
     if (!c->ev_front) SR_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
@@ -635,6 +650,11 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     q->op.fb = fb->view();
     q->op.shard_rank = c->shard_rank; q->op.shard_world = c->shard_world;
     q->op.fs = tp.fs;
+    if (extra) {
+        q->op.lines = tp.lines; q->op.points = tp.points;
+        q->op.nlines = tp.nlines; q->op.npoints = tp.npoints;
+        q->op.line_base = tp.line_base; q->op.point_base = tp.point_base;
+    }
     SR_TRY(launch_opaque_pass(c, q.get()));
     fb->pending_clear = false;
     c->pending = q.release();
@@ -1432,14 +1452,17 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     const uint32_t owned = ntiles > c->shard_rank ? (ntiles - c->shard_rank + c->shard_world - 1) / c->shard_world : 0;
     const bool stencil_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
     const bool opaque_ok = d->blend == SR_BLEND_REPLACE && !stencil_active && fs != SR_FS_DISCARD_CHECKER;
-    const bool ordered_pass = !opaque_ok || tp.nlines + tp.npoints > 0;
+    // non-antialiased lines and points of an opaque draw are order independent too: they join the triangles in the
+    // visibility buffer (k_lines_vis / k_points_vis) instead of the ordered tile pass
+    const bool extra_vis = opaque_ok && !d->aa_lines && tp.nlines + tp.npoints > 0 && (uint64_t)tp.ntris + tp.nlines + tp.npoints < 0xFFFFFFFFull;
+    const bool ordered_pass = !opaque_ok || (!extra_vis && tp.nlines + tp.npoints > 0);
     auto q = std::make_unique<PendingOrdered>();
     Bins &bp = q->bins[0], &bl = q->bins[1], &bt = q->bins[2];
     if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
     if (opaque_ok) SR_TRY(zero_offsets(c, ntiles, &bt));  // triangles go through opaque_triangles below
     else SR_TRY(build_bins<3>(c, fb, tp.tris, tp.ntris, d->cull, &bt, false, &c->pinned[10]));
-    SR_TRY(build_bins<2>(c, fb, tp.lines, tp.nlines, SR_CULL_NONE, &bl, false, &c->pinned[9]));
-    SR_TRY(build_bins<1>(c, fb, tp.points, tp.npoints, SR_CULL_NONE, &bp, false, &c->pinned[8]));
+    SR_TRY(build_bins<2>(c, fb, tp.lines, extra_vis ? 0u : tp.nlines, SR_CULL_NONE, &bl, false, &c->pinned[9]));
+    SR_TRY(build_bins<1>(c, fb, tp.points, extra_vis ? 0u : tp.npoints, SR_CULL_NONE, &bp, false, &c->pinned[8]));
     record(c, 4);
     record(c, 7);
     record(c, 5);
@@ -1455,8 +1478,8 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         if (opaque_ok) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,
             // fragment.rs:268-311) through the ordered kernel
-            if (tp.ntris || fb->pending_clear) {
-                SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep));
+            if (tp.ntris || fb->pending_clear || extra_vis) {
+                SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep, extra_vis));
                 if (ordered_pass) SR_TRY(settle(c));  // a replayed triangle pass must not land after the lines
             }
             ordered.ntris = 0;

@@ -753,6 +753,85 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     for (int k = 0; k < PER; ++k) spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
 }
 
+struct SrLineSetup {
+    float4 ps, pe;   // unclipped end-point positions: interpolation runs over these (line.rs:75-77)
+    float cl[4];     // end points clipped to the frame (line.rs:51)
+    float d;         // clipped length (line.rs:52)
+    uint32_t vi0, vi1, second;
+    bool valid;
+};
+__device__ __forceinline__ bool sr_liang_barsky(float x1, float y1, float x2, float y2, float xmin, float ymin, float xmax, float ymax, float *o);
+// fetch + Liang-Barsky clip against the one frame-sized tile ((0,0),(w-1,h-1)) (fragment.rs:255-258, line.rs:51-52)
+__device__ __forceinline__ void sr_line_setup(const SrPrimSource &lines, uint32_t width, uint32_t height, uint32_t t, SrLineSetup &r) {
+    const SrVertexSet *vs;
+    uint32_t vi[2];
+    sr_prim_vertices<2>(lines, t, vs, vi);
+    r.ps = __ldg(vs->pos + vi[0]);
+    r.pe = __ldg(vs->pos + vi[1]);
+    r.vi0 = vi[0]; r.vi1 = vi[1];
+    r.second = t < lines.n0 ? 0u : 1u;
+    r.valid = false;
+    if (!sr_liang_barsky(r.ps.x, r.ps.y, r.pe.x, r.pe.y, 0.0f, 0.0f, (float)(width - 1), (float)(height - 1), r.cl)) return;
+    if (!isfinite(r.cl[0]) || !isfinite(r.cl[1]) || !isfinite(r.cl[2]) || !isfinite(r.cl[3])) return;  // reference would panic
+    r.d = sr_hypot32(r.cl[0] - r.cl[2], r.cl[1] - r.cl[3]);
+    r.valid = true;
+}
+
+// Non-antialiased lines and points of an opaque draw (Blend = (), stencil Always/Keep, non-discarding shader).  Like the
+// triangles of that state, the in-order result at a pixel is the fragment maximising (z, submission index) -- a Bresenham
+// line plots every pixel once with alpha 1 (line.rs:125-151), a point plots one pixel -- so they are reduced into the
+// same visibility buffer, one thread per primitive, with key ids that sort after every triangle (fragment.rs:268-311:
+// triangles, then lines, then points).  The resolve of k_tile_opaque<FS, true> shades the winners.
+struct SrExtraParams {
+    SrPrimSource lines, points;
+    uint32_t nlines, npoints, ntris;
+    uint32_t width, height, ntx;
+    uint32_t shard_rank, shard_world;
+    unsigned long long *vis;
+};
+__global__ void __launch_bounds__(128) k_lines_vis(const __grid_constant__ SrExtraParams p) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.nlines) return;
+    SrLineSetup L;
+    sr_line_setup(p.lines, p.width, p.height, t, L);
+    if (!L.valid) return;
+    const unsigned long long id = (unsigned long long)(p.ntris + t + 1u);
+    // draw_line_bresenham (line.rs:125-151); the clipped end points lie inside the frame, 32 bits hold the reference's i64 walk
+    int bx0 = (int)L.cl[0], by0 = (int)L.cl[1];
+    const int bx1 = (int)L.cl[2], by1 = (int)L.cl[3];
+    const int dx = abs(bx1 - bx0), dy = -abs(by1 - by0);
+    const int sx = bx0 < bx1 ? 1 : -1, sy = by0 < by1 ? 1 : -1;
+    int err = dx + dy;
+    while (true) {
+        if (bx0 >= 0 && by0 >= 0) {  // line.rs:56
+            const float tt = sr_hypot32(L.cl[0] - ((float)bx0 + 0.5f), L.cl[1] - ((float)by0 + 0.5f)) / L.d;  // line.rs:75
+            const float z = sr_lerp(tt, L.ps.z, L.pe.z);
+            const uint32_t px = (uint32_t)bx0, py = (uint32_t)by0;
+            if (z < 0.0f && (p.shard_world == 1 || ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world == p.shard_rank))
+                sr_red_max_u64(p.vis + sr_vis_index(px, py, p.ntx), ((unsigned long long)(~__float_as_uint(z)) << 32) | id);
+        }
+        if (bx0 == bx1 && by0 == by1) break;
+        const int e2 = 2 * err;
+        if (e2 >= dy) { err += dy; bx0 += sx; }
+        if (e2 <= dx) { err += dx; by0 += sy; }
+    }
+}
+__global__ void __launch_bounds__(128) k_points_vis(const __grid_constant__ SrExtraParams p) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.npoints) return;
+    const SrVertexSet *vs;
+    uint32_t vi[1];
+    sr_prim_vertices<1>(p.points, t, vs, vi);
+    const float4 P = __ldg(vs->pos + vi[0]);
+    // point.rs:46: bounds.0 <= x < bounds.1 with bounds = (0,0)..(w-1,h-1) (NaN fails every comparison)
+    if (!(0.0f <= P.x && P.x < (float)(p.width - 1) && 0.0f <= P.y && P.y < (float)(p.height - 1))) return;
+    const uint32_t px = __float2uint_rz(P.x), py = __float2uint_rz(P.y);
+    if (!(P.z < 0.0f)) return;
+    if (p.shard_world > 1 && ((py / SR_TILE_H) * p.ntx + px / SR_TILE_W) % p.shard_world != p.shard_rank) return;
+    sr_red_max_u64(p.vis + sr_vis_index(px, py, p.ntx),
+                   ((unsigned long long)(~__float_as_uint(P.z)) << 32) | (unsigned long long)(p.ntris + p.nlines + t + 1u));
+}
+
 // second pass over the large triangles only: write their ids into the per-tile lists
 __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count, const uint32_t *large_ids, const uint32_t *large_rects,
                                                     uint32_t ntx, uint32_t ntiles, uint32_t shard_rank, uint32_t shard_world,
@@ -799,9 +878,14 @@ struct SrOpaqueParams {
     SrFbView fb;
     uint32_t shard_rank, shard_world;
     SrFsConst fs;
+    // EXTRA instantiation only: non-antialiased lines and points of the same draw were reduced into the visibility buffer
+    // by k_lines_vis / k_points_vis with key ids ntris + 1 + i (lines), ntris + nlines + 1 + i (points)
+    SrPrimSource lines, points;
+    uint32_t nlines, npoints;
+    uint32_t line_base, point_base;  // canonical numbers of the first line / point (winner plane)
 };
 
-template <int FS>
+template <int FS, bool EXTRA>
 __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrOpaqueParams p) {
     extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
@@ -990,6 +1074,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         id = (uint32_t)keys[i];
         if (id == 0) return;
         const uint32_t t = id - 1;
+        if (EXTRA && t >= p.ntris) return;  // a line or a point won: nothing to prefetch
         if (t < n0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) vi[k] = __ldg(p.tris.indices + (uint64_t)t * 3 + k);
@@ -1018,6 +1103,49 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                     o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
                     write = true;
                 }
+            } else if (EXTRA && id_cur - 1 >= p.ntris) {
+                // the fragment of a line (line.rs:70-100) or a point (point.rs:62-82) at this pixel, recomputed exactly as
+                // k_lines_vis / k_points_vis computed it
+                const uint32_t e = id_cur - 1 - p.ntris;
+                float sv[4 + NP * 4 + 1];
+                uint32_t canonical;
+                if (e < p.nlines) {
+                    SrLineSetup L;
+                    sr_line_setup(p.lines, W, H, e, L);
+                    const float t = sr_hypot32(L.cl[0] - ((float)px + 0.5f), L.cl[1] - ((float)py + 0.5f)) / L.d;
+                    sv[0] = sr_lerp(t, L.ps.x, L.pe.x);
+                    sv[1] = sr_lerp(t, L.ps.y, L.pe.y);
+                    sv[2] = sr_lerp(t, L.ps.z, L.pe.z);
+                    sv[3] = sr_lerp(t, L.ps.w, L.pe.w);
+                    const SrVertexSet *vs = L.second ? &p.lines.vs1 : &p.lines.vs0;
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, L.vi0, pl));
+                        const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, L.vi1, pl));
+                        sv[4 + pl * 4 + 0] = sr_lerp(t, ka.x, kb.x);
+                        sv[4 + pl * 4 + 1] = sr_lerp(t, ka.y, kb.y);
+                        sv[4 + pl * 4 + 2] = sr_lerp(t, ka.z, kb.z);
+                        sv[4 + pl * 4 + 3] = sr_lerp(t, ka.w, kb.w);
+                    }
+                    canonical = p.line_base + sr_prim_canonical(p.lines, e, 0);
+                } else {
+                    const uint32_t pt = e - p.nlines;
+                    const SrVertexSet *vs;
+                    uint32_t vi[1];
+                    sr_prim_vertices<1>(p.points, pt, vs, vi);
+                    const float4 P = __ldg(vs->pos + vi[0]);
+                    sv[0] = P.x; sv[1] = P.y; sv[2] = P.z; sv[3] = P.w;
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        const float4 k = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
+                        sv[4 + pl * 4 + 0] = k.x; sv[4 + pl * 4 + 1] = k.y; sv[4 + pl * 4 + 2] = k.z; sv[4 + pl * 4 + 3] = k.w;
+                    }
+                    canonical = p.point_base + sr_prim_canonical(p.points, pt, 0);
+                }
+                sr_fragment_shader<FS>(p.fs, sv, o);  // (a line's colour alpha is scaled by its coverage, 1.0 without antialiasing)
+                o[4] = sv[2];
+                write = true;
+                if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = canonical + 1;
             } else {
                 const uint32_t t = id_cur - 1;
                 const SrVertexSet *vs = t < n0 ? &p.tris.vs0 : &p.tris.vs1;
@@ -1258,20 +1386,14 @@ struct SrOrdLineRec {
 };
 static_assert(sizeof(SrOrdLineRec) <= sizeof(SrOrdSetup), "line records reuse the triangle records' shared memory");
 __device__ __forceinline__ void sr_ord_line_setup(const SrTileParams &p, uint32_t t, SrOrdLineRec &r) {
-    const SrVertexSet *vs;
-    uint32_t vi[2];
-    sr_prim_vertices<2>(p.lines, t, vs, vi);
-    r.ps = __ldg(vs->pos + vi[0]);
-    r.pe = __ldg(vs->pos + vi[1]);
-    r.vi0 = vi[0]; r.vi1 = vi[1];
-    r.second = t < p.lines.n0 ? 0u : 1u;
+    SrLineSetup L;
+    sr_line_setup(p.lines, p.fb.width, p.fb.height, t, L);
+    r.ps = L.ps; r.pe = L.pe;
+    r.cl[0] = L.cl[0]; r.cl[1] = L.cl[1]; r.cl[2] = L.cl[2]; r.cl[3] = L.cl[3];
+    r.d = L.d;
+    r.vi0 = L.vi0; r.vi1 = L.vi1; r.second = L.second;
     r.canonical = p.line_base + sr_prim_canonical(p.lines, t, 0);
-    r.valid = 0;
-    // bounds = the one frame-sized tile ((0,0),(w-1,h-1)) cast to float (fragment.rs:255-258)
-    if (!sr_liang_barsky(r.ps.x, r.ps.y, r.pe.x, r.pe.y, 0.0f, 0.0f, (float)(p.fb.width - 1), (float)(p.fb.height - 1), r.cl)) return;
-    if (!isfinite(r.cl[0]) || !isfinite(r.cl[1]) || !isfinite(r.cl[2]) || !isfinite(r.cl[3])) return;  // reference would panic
-    r.d = sr_hypot32(r.cl[0] - r.cl[2], r.cl[1] - r.cl[3]);
-    r.valid = 1;
+    r.valid = L.valid ? 1u : 0u;
 }
 // the walk of one line: executed by every thread of the CTA, pixels are plotted by their owner (sr_ord_owns)
 template <int FS>
