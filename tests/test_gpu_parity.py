@@ -492,6 +492,45 @@ def test_mixed_generated_primitives_order(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="mixed")
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_opaque_lines_and_points_through_the_visibility_buffer(P, ctx, world):
+    """With Blend=(), no stencil and Bresenham lines the whole draw is order independent: triangles, lines and points are
+    reduced into one visibility buffer (k_micro / k_lines_vis / k_points_vis) and the resolve shades whichever won.
+    Integer depths force ties between the three kinds (later kind / later primitive wins, fragment.rs:268-311); drawn
+    twice (the second draw starts from the stored depth) and, for world > 1, tile-sharded into one framebuffer."""
+    rng = np.random.default_rng(97)
+    w, h = 260, 170
+    tri = H.random_screen_triangles(rng, 400, w, h, integer_depth=True)
+    lines = H.random_screen_triangles(rng, 300, w, h, integer_depth=True)[:600]
+    lines[0, :2], lines[1, :2] = (-30.0, 20.5), (w + 40.0, 90.25)   # clipped on both sides
+    lines[2, :2], lines[3, :2] = (40.5, 40.5), (40.5, 40.5)          # zero length: nothing is drawn
+    pts = H.random_screen_triangles(rng, 400, w, h, integer_depth=True)[:1200]
+    pts[0, :2] = (w - 1 + 0.5, 10.5)                                 # last column: never drawn (point.rs:46)
+    idx = np.arange(len(tri), dtype=np.uint32)
+    out1, win1, _, ofb = run_both_screen(P, ctx, w, h, tri, idx, gen={2: lines, 1: pts}, draws=2)
+    assert np.array_equal(win1, ofb.winner)
+    H.compare_framebuffers(out1, ofb, exact_color=True, what="opaque lines/points")
+    kinds = np.digitize(ofb.winner[ofb.winner > 0] - 1, [len(tri) // 3, len(tri) // 3 + len(lines) // 2])
+    assert all((kinds == k).sum() > 50 for k in (0, 1, 2)), "every primitive kind must win some pixels"
+    if world > 1:
+        fb = make_fb(P, ctx, w, h)
+        pipe = P.Pipeline.from_framebuffer(fb, scenes.suzanne_uniforms(w, h))
+        try:
+            for rank in range(world):
+                ctx.set_tile_shard(rank, world)
+                fb.clear(H.CLEAR)
+                for _ in range(2):
+                    d = pipe.draw_from_vertices(sr.TRIANGLE, tri, idx, 1)
+                    d.set_generated(2, lines)
+                    d.set_generated(1, pts)
+                    d.run(sr.FS_FLAT)
+        finally:
+            ctx.set_tile_shard(0, 1)
+        H.assert_bits_equal(fb.download(), out1, "sharded opaque lines/points")
+        pipe.destroy()
+        fb.destroy()
+
+
 # ------------------------------------------------------------------------------------------------------
 # geometry stage
 # ------------------------------------------------------------------------------------------------------
