@@ -76,6 +76,13 @@ public:
         check(sr_framebuffer_download(h_, out.data(), out.size() * sizeof(PixelCD)));
         return out;
     }
+    // presentation read-back (realtime_example/src/main.rs:100-116): `(c * 255.0) as u8` per channel, converted on the device;
+    // abgr = the byte order the example writes into SDL's RGBA8888 streaming texture
+    std::vector<uint8_t> rgba8(bool abgr = false) {
+        std::vector<uint8_t> out((size_t)dim_.width * dim_.height * 4);
+        check(sr_framebuffer_download_rgba8(h_, out.data(), out.size(), abgr ? 1u : 0u));
+        return out;
+    }
     PixelCD pixel(uint32_t x, uint32_t y) {  // checked accessor: throws Error{SR_ERR_INVALID_PIXEL_COORDINATE}
         PixelCD p;
         check(sr_framebuffer_get_pixel(h_, x, y, &p.r, &p.depth, nullptr));
