@@ -70,7 +70,7 @@ int sr_context_set_stage_timing(sr_context *, int enable);
  * [4] ordered bins end, [7] visibility init end, [5] raster front end (k_micro) end, [6] fragment end; -1 = not recorded */
 int sr_context_stage_timestamps(sr_context *, void *base_event, float ms[8]);
 /* Cross-context ordering for frames in flight (one context = one CUDA stream; the reference has one frame in flight
- * per pipeline, src/pipeline/stages/*.rs hold `&mut P`).  Work enqueued on `waiter` after this call starts only when
+ * per pipeline, the stage structs in src/pipeline/stages/ hold `&mut P`).  Work enqueued on `waiter` after this call starts only when
  * `other` has reached `point`: 0 = everything enqueued on it so far; 1 = the raster front end (per-triangle setup and
  * small-triangle rasterisation) of its most recent opaque draw -- the software-pipeline schedule "frame n+1's vertex
  * stage and front end overlap frame n's tile resolve". */
