@@ -288,6 +288,7 @@ struct Bins {
     SrBinParams params;  // of the fill pass (kept for a replay)
     uint32_t grid = 0;
     int nv = 0;          // 0: empty kind
+    bool small = false;  // built by one k_bin_small_groups launch (replayed as a whole)
 };
 
 static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
@@ -310,6 +311,16 @@ static int zero_offsets(sr_context *c, uint32_t ntiles, Bins *b) {
 // the tile kernel are enqueued against its current capacity and skip themselves on the device if the scanned total does
 // not fit; the total travels to pinned memory (`total_slot`) and settle() re-runs the skipped passes with a larger arena.
 template <int NV>
+static int launch_bin_small_groups(sr_context *c, Bins *b) {
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_bin_small_groups<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_BIN_SMALL_MAX_TILES * 4));
+        configured[c->device & 15] = true;
+    }
+    SR_LAUNCH(c, k_bin_small_groups<NV>, 1, SR_BIN_SMALL_G_THREADS, (size_t)b->params.ntx * b->params.nty * 4, b->params, b->off->as<uint32_t>());
+    return SR_OK;
+}
+template <int NV>
 static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSource &src, uint32_t nprims, uint32_t cull, Bins *b,
                       bool exact = true, uint32_t *total_slot = nullptr) {
     const uint32_t ntiles = fb->ntx * fb->nty;
@@ -317,7 +328,6 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     SR_TRY(c->alloc(((size_t)nprims + 64) * 4, &b->rects));
     SR_TRY(c->alloc((size_t)ntiles * 4, &b->count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &b->off));
-    SR_CUDA(cudaMemsetAsync(b->count->ptr, 0, (size_t)ntiles * 4, c->stream));
     SrBinParams &p = b->params;
     memset(&p, 0, sizeof(p));
     p.src = src;
@@ -329,6 +339,24 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     p.tile_count = b->count->as<uint32_t>();
     b->grid = ceil_div(nprims, 256);
     b->nv = NV;
+    if (!exact && nprims <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
+        // small draw: rectangles, counts, scan and fill in one single-CTA launch (no memset, no separate scan / fill)
+        Buf &arena = c->ord_arena[NV - 1];
+        if (!arena) {
+            c->ord_cap[NV - 1] = 1u << 18;
+            SR_TRY(c->alloc((size_t)c->ord_cap[NV - 1] * 4, &arena));
+        }
+        b->list = arena;
+        b->capacity = c->ord_cap[NV - 1];
+        b->small = true;
+        p.tile_off = b->off->as<uint32_t>();
+        p.list = b->list->as<uint32_t>();
+        p.capacity = b->capacity;
+        SR_TRY(launch_bin_small_groups<NV>(c, b));
+        SR_CUDA(cudaMemcpyAsync(total_slot, b->off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+        return SR_OK;
+    }
+    SR_CUDA(cudaMemsetAsync(b->count->ptr, 0, (size_t)ntiles * 4, c->stream));
     SR_LAUNCH(c, k_bin_setup<NV>, b->grid, 256, 0, p);
     SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, b->count->as<uint32_t>(), ntiles, b->off->as<uint32_t>(), b->count->as<uint32_t>());
     p.tile_off = b->off->as<uint32_t>();
@@ -467,7 +495,13 @@ static int settle_ordered(sr_context *c) {
         b.capacity = cap;
         b.params.list = b.list->as<uint32_t>();
         b.params.capacity = cap;
-        SR_LAUNCH(c, k_bin_fill, b.grid, 256, 0, b.params);
+        if (b.small) {
+            if (b.nv == 3) SR_TRY(launch_bin_small_groups<3>(c, &b));
+            else if (b.nv == 2) SR_TRY(launch_bin_small_groups<2>(c, &b));
+            else SR_TRY(launch_bin_small_groups<1>(c, &b));
+        } else {
+            SR_LAUNCH(c, k_bin_fill, b.grid, 256, 0, b.params);
+        }
     }
     if (!replay) return SR_OK;
     q->tp.point_list = q->bins[0].list->as<uint32_t>(); q->tp.point_cap = q->bins[0].capacity;

@@ -173,6 +173,129 @@ __global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_fill(const SrBinParams p
     sr_bin_group<true>(p, rect, t >> 5);
 }
 
+// The ordered path's bins for small draws (<= 8192 primitives) in ONE single-CTA launch: per-primitive rectangles, per-tile
+// counts of 32-primitive groups (shared-memory counters), exclusive scan, list fill -- instead of a memset + k_bin_setup +
+// k_tile_offsets + k_bin_fill, each of which costs a launch and a few dependent round trips (20 us apiece for a
+// 968-triangle model, profiles/r1i_ordered_kernels_summary.txt).  One warp per group; the tiles of the group's union
+// rectangle are dealt to the lanes and tested against the 32 rectangles (handed round with shuffles).
+#define SR_BIN_SMALL_G_THREADS 1024
+template <int NV>
+__global__ void __launch_bounds__(SR_BIN_SMALL_G_THREADS) k_bin_small_groups(const SrBinParams p, uint32_t *tile_off) {
+    extern __shared__ uint32_t s_cnt[];  // per-tile counters, later the fill cursors
+    __shared__ uint32_t s_wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ntiles = p.ntx * p.nty;
+    const uint32_t ngroups = (p.nprims + 31u) / 32u;
+    for (uint32_t i = tid; i < ntiles; i += SR_BIN_SMALL_G_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    __shared__ uint32_t s_bits[SR_BIN_SMALL_G_THREADS / 32][32];  // per warp: which tiles of the group's union rectangle are hit
+    auto place = [&](uint32_t rect, uint32_t group, bool fill) {
+        const bool valid = rect != SR_RECT_INVALID;
+        if (!__any_sync(0xffffffffu, valid)) return;
+        uint32_t gx0 = valid ? (rect & 255u) : 255u, gy0 = valid ? ((rect >> 8) & 255u) : 255u;
+        uint32_t gx1 = valid ? ((rect >> 16) & 255u) : 0u, gy1 = valid ? (rect >> 24) : 0u;
+        gx0 = __reduce_min_sync(0xffffffffu, gx0);
+        gy0 = __reduce_min_sync(0xffffffffu, gy0);
+        gx1 = __reduce_max_sync(0xffffffffu, gx1);
+        gy1 = __reduce_max_sync(0xffffffffu, gy1);
+        const uint32_t gw = gx1 - gx0 + 1, n = gw * (gy1 - gy0 + 1);
+        if (n <= 1024u) {
+            // every primitive marks the tiles of its own rectangle in a bitmap of the union rectangle (rectangles of more
+            // than 32 tiles are spread over the lanes), then each lane posts the set bits of one bitmap word
+            uint32_t *bits = s_bits[warp];
+            bits[lane] = 0;
+            __syncwarp();
+            const uint32_t rx0 = rect & 255u, ry0 = (rect >> 8) & 255u, rx1 = (rect >> 16) & 255u, ry1 = rect >> 24;
+            const uint32_t rw = rx1 - rx0 + 1, rn = valid ? rw * (ry1 - ry0 + 1) : 0u;
+            const bool big = rn > 32u;
+            if (!big)
+                for (uint32_t i = 0; i < rn; ++i) {
+                    const uint32_t at = (ry0 + i / rw - gy0) * gw + (rx0 + i % rw - gx0);
+                    atomicOr(&bits[at >> 5], 1u << (at & 31u));
+                }
+            for (uint32_t rest = __ballot_sync(0xffffffffu, big); rest; rest &= rest - 1) {
+                const uint32_t r = __shfl_sync(0xffffffffu, rect, __ffs(rest) - 1);
+                const uint32_t bx0 = r & 255u, by0 = (r >> 8) & 255u, bx1 = (r >> 16) & 255u, by1 = r >> 24;
+                const uint32_t bw = bx1 - bx0 + 1, bn = bw * (by1 - by0 + 1);
+                for (uint32_t i = lane; i < bn; i += 32) {
+                    const uint32_t at = (by0 + i / bw - gy0) * gw + (bx0 + i % bw - gx0);
+                    atomicOr(&bits[at >> 5], 1u << (at & 31u));
+                }
+            }
+            __syncwarp();
+            for (uint32_t word = bits[lane]; word; word &= word - 1) {
+                const uint32_t i = lane * 32u + (uint32_t)(__ffs(word) - 1);
+                const uint32_t tile = (gy0 + i / gw) * p.ntx + gx0 + i % gw;
+                if (tile % p.shard_world != p.shard_rank) continue;
+                const uint32_t at = atomicAdd(&s_cnt[tile], 1u);
+                if (fill) p.list[at] = group;
+            }
+            __syncwarp();
+            return;
+        }
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t tx = gx0 + i % gw, ty = gy0 + i / gw;
+            bool hit = false;
+#pragma unroll 4
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t r = __shfl_sync(0xffffffffu, rect, l);
+                hit = hit || (r != SR_RECT_INVALID && sr_rect_hits(r, tx, ty));
+            }
+            const uint32_t tile = ty * p.ntx + tx;
+            if (i < n && hit && tile % p.shard_world == p.shard_rank) {
+                const uint32_t at = atomicAdd(&s_cnt[tile], 1u);
+                if (fill) p.list[at] = group;
+            }
+        }
+    };
+    constexpr uint32_t GW = SR_BIN_SMALL_G_THREADS / 32;  // groups in flight
+    for (uint32_t g = warp; g < ngroups; g += GW) {
+        const uint32_t t = g * 32 + lane;
+        const uint32_t rect = t < p.nprims ? sr_prim_rect<NV>(p, t) : SR_RECT_INVALID;
+        p.rects[t] = rect;  // (the array is padded to whole groups)
+        place(rect, g, false);
+    }
+    __syncthreads();
+    const uint32_t chunk = (ntiles + SR_BIN_SMALL_G_THREADS - 1) / SR_BIN_SMALL_G_THREADS;
+    const uint32_t b = min(tid * chunk, ntiles), e = min(b + chunk, ntiles);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += s_cnt[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_wsum[lane];
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += v;
+        }
+        s_wsum[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t total = s_wsum[31];
+    uint32_t run = (warp ? s_wsum[warp - 1] : 0u) + inc - sum;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t c = s_cnt[i];
+        tile_off[i] = run;
+        s_cnt[i] = run;
+        run += c;
+    }
+    if (tid == 0) tile_off[ntiles] = total;
+    __syncthreads();
+    if (total > p.capacity) return;  // lists do not fit: the host re-runs this launch with a larger arena
+    for (uint32_t g = warp; g < ngroups; g += GW) {
+        const uint32_t t = g * 32 + lane;
+        place(p.rects[t], g, true);
+    }
+}
+
 // exclusive scan of the per-tile counts (a few thousand tiles: one block of 1024 threads, each thread owning a run of
 // consecutive tiles so that one block-wide scan suffices), total to off[ntiles]; the counts are zeroed for re-use as cursors
 #define SR_OFFSETS_THREADS 1024
