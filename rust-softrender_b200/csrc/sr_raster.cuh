@@ -96,6 +96,7 @@ __device__ __forceinline__ uint32_t sr_prim_rect(const SrBinParams &p, uint32_t 
 template <bool FILL>
 __device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect, uint32_t group) {
     __shared__ uint32_t s_tile[SR_BIN_WARPS * SR_BIN_SLOTS];
+    __shared__ uint32_t s_bits[SR_BIN_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = rect != SR_RECT_INVALID;
     uint32_t gx0 = valid ? (rect & 255u) : 255u, gy0 = valid ? ((rect >> 8) & 255u) : 255u;
@@ -118,22 +119,55 @@ __device__ __forceinline__ void sr_bin_group(const SrBinParams &p, uint32_t rect
                 ++nslots;
             }
     } else if (any_valid) {
-        // a group of big primitives: the tiles of the group's union rectangle are dealt to the lanes, 32 at a time; every
-        // lane tests its tile against the 32 rectangles (handed round with shuffles) and posts its own atomic
+        // a group that spans more tiles: every primitive marks the tiles of its own rectangle in a bitmap of the group's
+        // union rectangle (rectangles of more than 32 tiles are spread over the lanes), then each lane posts the set bits of
+        // one bitmap word with its own atomic.  Union rectangles above 1024 tiles: tiles dealt to the lanes and tested
+        // against the 32 rectangles handed round with shuffles.
         const uint32_t gw = gx1 - gx0 + 1, n = gw * (gy1 - gy0 + 1);
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t tx = gx0 + i % gw, ty = gy0 + i / gw;
-            bool hit = false;
-#pragma unroll 4
-            for (int l = 0; l < 32; ++l) {
-                const uint32_t r = __shfl_sync(0xffffffffu, rect, l);
-                hit = hit || (r != SR_RECT_INVALID && sr_rect_hits(r, tx, ty));
+        if (n <= 1024u) {
+            uint32_t *bits = s_bits[warp];
+            bits[lane] = 0;
+            __syncwarp();
+            const uint32_t rx0 = rect & 255u, ry0 = (rect >> 8) & 255u, rx1 = (rect >> 16) & 255u, ry1 = rect >> 24;
+            const uint32_t rw = rx1 - rx0 + 1, rn = valid ? rw * (ry1 - ry0 + 1) : 0u;
+            const bool big = rn > 32u;
+            if (!big)
+                for (uint32_t i = 0; i < rn; ++i) {
+                    const uint32_t at = (ry0 + i / rw - gy0) * gw + (rx0 + i % rw - gx0);
+                    atomicOr(&bits[at >> 5], 1u << (at & 31u));
+                }
+            for (uint32_t rest = __ballot_sync(0xffffffffu, big); rest; rest &= rest - 1) {
+                const uint32_t r = __shfl_sync(0xffffffffu, rect, __ffs(rest) - 1);
+                const uint32_t bx0 = r & 255u, by0 = (r >> 8) & 255u, bx1 = (r >> 16) & 255u, by1 = r >> 24;
+                const uint32_t bw = bx1 - bx0 + 1, bn = bw * (by1 - by0 + 1);
+                for (uint32_t i = lane; i < bn; i += 32) {
+                    const uint32_t at = (by0 + i / bw - gy0) * gw + (bx0 + i % bw - gx0);
+                    atomicOr(&bits[at >> 5], 1u << (at & 31u));
+                }
             }
-            const uint32_t tile = ty * p.ntx + tx;
-            if (i < n && hit && tile % p.shard_world == p.shard_rank) {
+            __syncwarp();
+            for (uint32_t word = bits[lane]; word; word &= word - 1) {
+                const uint32_t i = lane * 32u + (uint32_t)(__ffs(word) - 1);
+                const uint32_t tile = (gy0 + i / gw) * p.ntx + gx0 + i % gw;
+                if (tile % p.shard_world != p.shard_rank) continue;
                 const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
                 if (FILL) p.list[p.tile_off[tile] + at] = group;
+            }
+        } else {
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t tx = gx0 + i % gw, ty = gy0 + i / gw;
+                bool hit = false;
+#pragma unroll 4
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t r = __shfl_sync(0xffffffffu, rect, l);
+                    hit = hit || (r != SR_RECT_INVALID && sr_rect_hits(r, tx, ty));
+                }
+                const uint32_t tile = ty * p.ntx + tx;
+                if (i < n && hit && tile % p.shard_world == p.shard_rank) {
+                    const uint32_t at = atomicAdd(p.tile_count + tile, 1u);
+                    if (FILL) p.list[p.tile_off[tile] + at] = group;
+                }
             }
         }
     }
