@@ -160,6 +160,31 @@ def kernel_traffic():
         return {}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this rank's host threads (and so first-touch its pinned buffers) on the NUMA node its GPU hangs
+    off, so the end-to-end copies do not cross the socket interconnect.  Returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no allowed cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # containers without sysfs topology, single-socket boxes, ...
+        return f"unbound ({type(e).__name__})"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -170,6 +195,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("SR_NO_NUMA", "0") == "0" else "off"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -343,7 +369,7 @@ def run_ours(args):
     e2e_ok = bool(np.array_equal(lanes[-1][3].view(np.uint32), ref_fb.view(np.uint32)))
     e2e = {"value": world * ntris / e2e_s / 1e6, "unit": "Mtris/s", "frames_per_s": world / e2e_s,
            "h2d_bytes_per_step": int(host_v.nbytes + host_i.nbytes + 576) * world, "d2h_bytes_per_step": int(w * h * 20) * world,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "frames_in_flight": depth, "result_matches_resident_path": e2e_ok,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "frames_in_flight": depth, "host_affinity": numa, "result_matches_resident_path": e2e_ok,
            "note": "PCIe-bound: upload of frame k+1 overlaps read-back of frame k (three contexts/streams)"}
     for cx, lfb, lp, _ in lanes[1:]:
         lp.destroy()
