@@ -1663,6 +1663,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     uint4 *s_ring = reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + (threadIdx.x >> 5) * SR_ORD_RING;
     uint8_t *s_stencil = reinterpret_cast<uint8_t *>(reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + SR_RASTER_WARPS * SR_ORD_RING);
     __shared__ uint32_t s_wcount[SR_RASTER_WARPS];
+    __shared__ uint8_t s_wband[SR_RASTER_WARPS][SR_RASTER_WARPS];     // [warp][band]: hits of that warp's group crossing the band
+    __shared__ uint8_t s_band[SR_RASTER_WARPS][SR_RASTER_THREADS];  // per band: compacted record indices, in list order
 
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     constexpr uint32_t RH = SR_TILE_H / SR_RASTER_WARPS;  // tile rows owned by each warp
@@ -1750,8 +1752,24 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     }
                 }
             }
+            // Compaction in list order (ballot + warp counts) and, per band of rows, the ordered list of the hits that cross
+            // it: a warp then visits only the triangles of its own band instead of scanning every record of the batch.
             const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            uint32_t bandmask = 0;  // bands (= warps) this triangle's rows cross
+            if (hit) {
+                const uint32_t b0 = ((su.by & 0xffffu) - y0) / RH, b1 = ((su.by >> 16) - y0) / RH;
+                bandmask = ((2u << b1) - 1u) & ~((1u << b0) - 1u);
+            }
+            uint32_t bm[SR_RASTER_WARPS];
+#pragma unroll
+            for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b) bm[b] = __ballot_sync(0xffffffffu, (bandmask >> b) & 1u);
             if (lane == 0) s_wcount[warp] = __popc(mask);
+            if (lane < SR_RASTER_WARPS) {
+                uint32_t mine = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b) mine = lane == b ? bm[b] : mine;
+                s_wband[warp][lane] = (uint8_t)__popc(mine);
+            }
             __syncthreads();
             uint32_t base = 0, total = 0;
 #pragma unroll
@@ -1760,7 +1778,20 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 if (w2 < warp) base += cnt;
                 total += cnt;
             }
-            if (hit) s_setup[base + __popc(mask & ((1u << lane) - 1u))] = su;
+            const uint32_t at = base + __popc(mask & ((1u << lane) - 1u));
+            if (hit) {
+                s_setup[at] = su;
+#pragma unroll
+                for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b)
+                    if ((bandmask >> b) & 1u) {
+                        uint32_t bbase = 0;
+                        for (uint32_t w2 = 0; w2 < warp; ++w2) bbase += s_wband[w2][b];
+                        s_band[b][bbase + __popc(bm[b] & ((1u << lane) - 1u))] = (uint8_t)at;
+                    }
+            }
+            uint32_t nband = 0;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) nband += s_wband[w2][warp];
             __syncthreads();
             const uint32_t ry_lo = y0 + warp * RH, ry_hi = ry_lo + RH - 1;
             if (!SrFsInfo<FS>::DISCARDS) {
@@ -1816,11 +1847,11 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     head = (head + n) % SR_ORD_RING;
                     count -= n;
                 };
-                for (uint32_t s = 0; s < total; ++s) {
+                for (uint32_t k = 0; k < nband; ++k) {
+                    const uint32_t s = s_band[warp][k];
                     const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                     const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
                     const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
-                    if (r0 > r1) continue;
                     const SrOrdSetup &q = s_setup[s];
                     SrTri tr;
                     tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
@@ -1857,11 +1888,11 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 }
                 if (count) shade_and_blend(count);  // the records refer to this batch's setups: drain before the next batch
             } else {
-            for (uint32_t s = 0; s < total; ++s) {
+            for (uint32_t k = 0; k < nband; ++k) {
+                const uint32_t s = s_band[warp][k];
                 const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                 const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
                 const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
-                if (r0 > r1) continue;
                 const SrOrdSetup &q = s_setup[s];
                 SrTri tr;
                 tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
