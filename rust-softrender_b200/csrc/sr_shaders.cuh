@@ -109,10 +109,15 @@ __device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, fl
     const uchar4 t10 = __ldg((const uchar4 *)c.tex + (size_t)y0 * c.tex_w + x1);
     const uchar4 t01 = __ldg((const uchar4 *)c.tex + (size_t)y1 * c.tex_w + x0);
     const uchar4 t11 = __ldg((const uchar4 *)c.tex + (size_t)y1 * c.tex_w + x1);
-    const float a00[4] = {(float)t00.x / 255.0f, (float)t00.y / 255.0f, (float)t00.z / 255.0f, (float)t00.w / 255.0f};
-    const float a10[4] = {(float)t10.x / 255.0f, (float)t10.y / 255.0f, (float)t10.z / 255.0f, (float)t10.w / 255.0f};
-    const float a01[4] = {(float)t01.x / 255.0f, (float)t01.y / 255.0f, (float)t01.z / 255.0f, (float)t01.w / 255.0f};
-    const float a11[4] = {(float)t11.x / 255.0f, (float)t11.y / 255.0f, (float)t11.z / 255.0f, (float)t11.w / 255.0f};
+    // texel / 255 (texture.rs:66-69): correctly rounded quotients through the shared-divisor shortcut (sr_div_exact with
+    // r = RN(1/255); 0 / 255 comes out as +0) instead of sixteen IEEE division sequences -- same bits
+    const float r255 = __frcp_rn(255.0f);
+    auto unorm = [&](const uchar4 &t, float *a) {
+        a[0] = sr_div_exact((float)t.x, 255.0f, r255); a[1] = sr_div_exact((float)t.y, 255.0f, r255);
+        a[2] = sr_div_exact((float)t.z, 255.0f, r255); a[3] = sr_div_exact((float)t.w, 255.0f, r255);
+    };
+    float a00[4], a10[4], a01[4], a11[4];
+    unorm(t00, a00); unorm(t10, a10); unorm(t01, a01); unorm(t11, a11);
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         const float val = (a00[ch] * u_opp + a10[ch] * u_ratio) * v_opp + (a01[ch] * u_opp + a11[ch] * u_ratio) * v_ratio;
