@@ -18,5 +18,6 @@ for it in range(3):
     a = pipe.render_mesh(sr.TRIANGLE, gm).run(sr.VS_FULL_EXAMPLE); ctx.synchronize(); t1 = time.perf_counter()
     b = a.run(sr.GS_FACE_NORMALS); ctx.synchronize(); t2 = time.perf_counter()
     c = b.finish(vp); ctx.synchronize(); t3 = time.perf_counter()
+    if len(sys.argv) > 1 and sys.argv[1] == 'aa': c = c.antialiased_lines(True).with_blend(sr.BLEND_ALPHA_OVER)
     c.run(sr.FS_GREEN); ctx.synchronize(); t4 = time.perf_counter()
     print("vertex %.3f  gs %.3f  finish %.3f  fragment %.3f ms" % ((t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3, (t4-t3)*1e3), ctx.stage_times())

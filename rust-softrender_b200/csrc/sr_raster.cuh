@@ -1508,7 +1508,6 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
     // only this tile's pixels (the frame test also covers Wu's +1 neighbour past the last row/column,
     // where the reference would index out of bounds)
     if (x < (long long)c.x0 || x > (long long)c.xe || y < (long long)c.y0 || y > (long long)c.ye) return;
-    if (!sr_ord_owns(c, (uint32_t)x, (uint32_t)y)) return;
     const uint32_t li = ((uint32_t)y - c.y0) * SR_TILE_W + ((uint32_t)x - c.x0);
     if (!sr_ord_stencil_step(c, li)) return;
     const float xf = (float)x + 0.5f, yf = (float)y + 0.5f;
@@ -1552,28 +1551,13 @@ __device__ __forceinline__ void sr_ord_line_setup(const SrTileParams &p, uint32_
     r.canonical = p.line_base + sr_prim_canonical(p.lines, t, 0);
     r.valid = L.valid ? 1u : 0u;
 }
-// the walk of one line: executed by every thread of the CTA, pixels are plotted by their owner (sr_ord_owns)
-template <int FS>
-__device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
-    const SrTileParams &p = *c.p;
-    SrLineCtx L;
-    L.vs = r.second ? &p.lines.vs1 : &p.lines.vs0;
-    L.vi[0] = r.vi0; L.vi[1] = r.vi1;
-    L.ps = r.ps; L.pe = r.pe;
-    L.canonical = r.canonical;
+// The walk of one line (line.rs:125-239), restricted to the pixels of one band of tile rows: calls plot(x, y, alpha) for
+// every plotted pixel with band_lo <= y <= band_hi and tx0 <= x <= tx1, in the reference's plotting order.
+template <class Plot>
+__device__ __forceinline__ void sr_line_walk(const SrOrdLineRec &r, bool aa, int band_lo, int band_hi, int tx0, int tx1, Plot plot) {
     const float cl[4] = {r.cl[0], r.cl[1], r.cl[2], r.cl[3]};
-    L.x1 = cl[0]; L.y1 = cl[1];
-    L.d = r.d;
-    // cheap inline filter in front of the (non-inlined) plot: the pixels of this warp's band that this lane owns
-    const int tx0 = (int)c.x0, tx1 = (int)c.xe;
-    const int band_lo = (int)c.y0 + (int)(threadIdx.x >> 5) * SR_ORD_BAND, band_hi = min(band_lo + SR_ORD_BAND - 1, (int)c.ye);
-    {   // the whole line misses the band (one pixel of slack for Wu's second row): nothing to walk for this warp
-        const int ya = (int)cl[1], yb = (int)cl[3];
-        if (max(ya, yb) + 1 < band_lo || min(ya, yb) - 1 > band_hi) return;
-    }
-    const int lane = (int)(threadIdx.x & 31u);
-    auto mine = [&](int x, int y) { return y >= band_lo && y <= band_hi && x >= tx0 && x <= tx1 && (x & 31) == lane; };
-    if (!p.aa_lines) {
+    auto inside = [&](int x, int y) { return y >= band_lo && y <= band_hi && x >= tx0 && x <= tx1; };
+    if (!aa) {
         // draw_line_bresenham (line.rs:125-151).  The reference walks in i64; the clipped end points lie inside the frame
         // (< 2^16), so every quantity below fits 32 bits with the same decisions.
         int bx0 = (int)cl[0], by0 = (int)cl[1];
@@ -1582,9 +1566,9 @@ __device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
         const int sx = bx0 < bx1 ? 1 : -1, sy = by0 < by1 ? 1 : -1;
         int err = dx + dy;
         while (true) {
-            if (mine(bx0, by0)) sr_ord_plot_line<FS>(c, L, bx0, by0, 1.0);
+            if (inside(bx0, by0)) plot(bx0, by0, 1.0);
             if (bx0 == bx1 && by0 == by1) break;
-            if (sy > 0 ? by0 > band_hi : by0 < band_lo) break;  // y is monotonic: the walk has left this warp's band for good
+            if (sy > 0 ? by0 > band_hi : by0 < band_lo) break;  // y is monotonic: the walk has left the band for good
             const int e2 = 2 * err;
             if (e2 >= dy) { err += dy; bx0 += sx; }
             if (e2 <= dx) { err += dx; by0 += sy; }
@@ -1598,9 +1582,10 @@ __device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
         const double dx = wx1 - wx0, dy = wy1 - wy0;
         const double gradient = dx < 0.0001 ? 1.0 : dy / dx;
         auto plot_float = [&](double a, double b, double opacity) {
-            // (the coordinates are within a pixel of the frame: the i64 casts of the reference fit 32 bits)
+            // (the coordinates are within a pixel of the frame: the i64 casts of the reference fit 32 bits; negative
+            // coordinates are not plotted, line.rs:56)
             const int x = steep ? (int)b : (int)a, y = steep ? (int)a : (int)b;
-            if (mine(x, y)) sr_ord_plot_line<FS>(c, L, x, y, opacity);
+            if (inside(x, y)) plot(x, y, opacity);
         };
         // both arms of the reference's `if steep` plot (x, y) / (y, x); plot_float takes (x_major, y_minor)
         double xend = round(wx0);
@@ -1622,6 +1607,61 @@ __device__ void sr_ord_line(const SrOrdCtx &c, const SrOrdLineRec &r) {
             plot_float(x, y + 1.0, sr_fract64(intery));
             intery += gradient;
         }
+    }
+}
+
+// Up to 32 consecutive line records, one per lane, rasterised by ONE warp into its band of tile rows with every pixel still
+// seeing its fragments in submission order.  Rounds: (A) every lane walks its line and bids for the pixels of its
+// not-yet-plotted fragments with atomicMax of (round << 8 | 255 - lane) -- the earliest line of the chunk wins a pixel;
+// (B) every lane walks again and plots its fragments in order for as long as it holds the pixel, stopping at the first
+// pixel an earlier line still has to plot.  A lane's plotted fragments are therefore a prefix of its walk, the earliest
+// unfinished line always completes, and a later line can never overtake an earlier one on a pixel.  Lines seldom share
+// pixels inside a band, so almost every chunk finishes in one round with all its lines walked in parallel.
+template <int FS>
+__device__ void sr_ord_lines_chunk(const SrOrdCtx &c, const SrOrdLineRec *recs, uint32_t n, uint32_t *claim, uint32_t &round) {
+    const SrTileParams &p = *c.p;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int tx0 = (int)c.x0, tx1 = (int)c.xe;
+    const int band_lo = (int)c.y0 + (int)(threadIdx.x >> 5) * SR_ORD_BAND, band_hi = min(band_lo + SR_ORD_BAND - 1, (int)c.ye);
+    bool active = false;
+    if (lane < n) {  // the whole line misses the band (one pixel of slack for Wu's second row): nothing to walk
+        const int ya = (int)recs[lane].cl[1], yb = (int)recs[lane].cl[3];
+        active = !(max(ya, yb) + 1 < band_lo || min(ya, yb) - 1 > band_hi);
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
+    const SrOrdLineRec &r = recs[min(lane, n - 1)];
+    SrLineCtx L;
+    L.vs = r.second ? &p.lines.vs1 : &p.lines.vs0;
+    L.vi[0] = r.vi0; L.vi[1] = r.vi1;
+    L.ps = r.ps; L.pe = r.pe;
+    L.canonical = r.canonical;
+    L.x1 = r.cl[0]; L.y1 = r.cl[1];
+    L.d = r.d;
+    const bool aa = p.aa_lines != 0;
+    uint32_t ndone = 0;  // fragments of this lane's walk (inside the band) already plotted
+    while (__any_sync(0xffffffffu, active)) {
+        ++round;
+        const uint32_t bid = (round << 8) | (255u - lane);
+        if (active) {
+            uint32_t j = 0;
+            sr_line_walk(r, aa, band_lo, band_hi, tx0, tx1, [&](int x, int y, double) {
+                if (j++ >= ndone) atomicMax(&claim[(y - band_lo) * SR_TILE_W + (x - tx0)], bid);
+            });
+        }
+        __syncwarp();
+        bool more = false;
+        if (active) {
+            uint32_t j = 0;
+            bool blocked = false;
+            sr_line_walk(r, aa, band_lo, band_hi, tx0, tx1, [&](int x, int y, double alpha) {
+                if (j++ < ndone || blocked) return;
+                if (claim[(y - band_lo) * SR_TILE_W + (x - tx0)] != bid) { blocked = true; more = true; return; }
+                sr_ord_plot_line<FS>(c, L, x, y, alpha);
+                ++ndone;
+            });
+        }
+        __syncwarp();
+        active = more;
     }
 }
 
@@ -1663,6 +1703,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     uint4 *s_ring = reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + (threadIdx.x >> 5) * SR_ORD_RING;
     uint8_t *s_stencil = reinterpret_cast<uint8_t *>(reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + SR_RASTER_WARPS * SR_ORD_RING);
     __shared__ uint32_t s_wcount[SR_RASTER_WARPS];
+    __shared__ uint32_t s_claim[SR_RASTER_WARPS][SR_ORD_BAND * SR_TILE_W];  // per warp: bids for the pixels of its band (sr_ord_lines_chunk)
     __shared__ uint8_t s_wband[SR_RASTER_WARPS][SR_RASTER_WARPS];     // [warp][band]: hits of that warp's group crossing the band
     __shared__ uint8_t s_band[SR_RASTER_WARPS][SR_RASTER_THREADS];  // per band: compacted record indices, in list order
 
@@ -1691,6 +1732,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     c.has_stencil = p.fb.stencil != nullptr;
     c.mesh_stencil = (uint8_t)p.stencil_value;
 
+    for (uint32_t i = lane; i < SR_ORD_BAND * SR_TILE_W; i += 32) s_claim[warp][i] = 0;
+    uint32_t claim_round = 0;  // (warp-uniform) bidding round of sr_ord_lines_chunk
     // load the tile (or generate the pending clear on chip)
     for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
@@ -1996,9 +2039,10 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     else s_point[at] = pr;
                 }
                 __syncthreads();
-                for (uint32_t k = 0; k < total; ++k) {
-                    if (kind == 2) sr_ord_line<FS>(c, s_line[k]);
-                    else sr_ord_point<FS>(c, s_point[k]);
+                if (kind == 2) {
+                    for (uint32_t k = 0; k < total; k += 32) sr_ord_lines_chunk<FS>(c, s_line + k, min(32u, total - k), s_claim[warp], claim_round);
+                } else {
+                    for (uint32_t k = 0; k < total; ++k) sr_ord_point<FS>(c, s_point[k]);
                 }
                 __syncthreads();
             }
