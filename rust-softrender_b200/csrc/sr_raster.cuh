@@ -1385,7 +1385,7 @@ struct SrOrdSetup {
     uint32_t vi[3], pad;
 };
 static_assert(sizeof(SrOrdSetup) == 112, "seven float4");
-#define SR_ORD_LIST_CAP 4096  // group ids sorted in shared memory; longer lists are sorted in place in HBM
+#define SR_ORD_LIST_CAP 2048  // group ids sorted in shared memory; longer lists are sorted in place in HBM
 #define SR_ORD_RING 64  // fragments a warp can hold between coverage and shading (at most 31 carried over + 32 new)
 #define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4 + \
                            SR_RASTER_WARPS * SR_ORD_RING * 16)
@@ -1753,6 +1753,50 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     }
     __syncthreads();
 
+    // Dense batches.  A tile's lists hold GROUPS of 32 consecutive primitives; when the submission order is not spatially
+    // coherent most primitives of a listed group miss the tile, and a batch of 8 groups would set up only a handful of
+    // primitives between its barriers.  `gather` therefore walks the group list with the cheap test only (packed tile
+    // rectangle against this tile) and queues the ids of the primitives that hit, in list order, until 256 are waiting
+    // (or the list ends); the expensive part -- dependent fetches, clipping, edge setup, the in-order sweep -- always runs
+    // on full batches.  Ids beyond the batch are carried over to the next one.
+    __shared__ uint32_t s_hits[2 * SR_RASTER_THREADS];
+    auto gather = [&](const uint32_t *lst, uint32_t Ln, const uint32_t *rects, uint32_t nprim, uint32_t &gpos, uint32_t nh) -> uint32_t {
+        while (nh < SR_RASTER_THREADS && gpos < Ln) {
+            const uint32_t gi = gpos + warp;
+            bool hit = false;
+            uint32_t t = 0;
+            if (gi < Ln) {
+                t = lst[gi] * SR_GROUP + lane;
+                const uint32_t rect = t < nprim ? __ldg(rects + t) : SR_RECT_INVALID;
+                hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcount[warp] = __popc(mask);
+            __syncthreads();
+            uint32_t base = 0, total = 0;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) {
+                const uint32_t cnt = s_wcount[w2];
+                if (w2 < warp) base += cnt;
+                total += cnt;
+            }
+            if (hit) s_hits[nh + base + __popc(mask & ((1u << lane) - 1u))] = t;
+            __syncthreads();
+            nh += total;
+            gpos += SR_RASTER_WARPS;
+        }
+        return nh;
+    };
+    // the ids beyond the batch just processed move to the front of the queue
+    auto carry_over = [&](uint32_t nh, uint32_t nb) -> uint32_t {
+        const uint32_t rest = nh - nb;
+        const uint32_t v = tid < rest ? s_hits[nb + tid] : 0u;
+        __syncthreads();
+        if (tid < rest) s_hits[tid] = v;
+        __syncthreads();
+        return rest;
+    };
+
     // ---------------- triangles ----------------
     if (LT > 0) {
         uint32_t *lst = p.tri_list + tbeg;
@@ -1763,14 +1807,14 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         }
         sr_block_sort(lst, LT);
         __syncthreads();
-        for (uint32_t gb = 0; gb < LT; gb += SR_RASTER_WARPS) {
-            const uint32_t gi = gb + warp;
-            bool hit = false;
+        uint32_t gpos = 0, queued = 0;
+        while (gpos < LT || queued > 0) {
+            const uint32_t nh = gather(lst, LT, p.tri_rects, p.ntris, gpos, queued);
+            const uint32_t nb = min(nh, (uint32_t)SR_RASTER_THREADS);
+            bool hit = tid < nb;
             SrOrdSetup su;
-            if (gi < LT) {
-                const uint32_t t = lst[gi] * SR_GROUP + lane;
-                const uint32_t rect = t < p.ntris ? __ldg(p.tri_rects + t) : SR_RECT_INVALID;
-                hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
+            {
+                const uint32_t t = hit ? s_hits[tid] : 0u;
                 if (hit) {
                     const SrVertexSet *vs;
                     uint32_t vi[3];
@@ -1974,6 +2018,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             }
             }
             __syncthreads();
+            queued = carry_over(nh, nb);
         }
     }
 
@@ -1997,15 +2042,12 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             // 8 groups = 256 primitives per batch: fetched and set up one thread each (the dependent gathers of a whole batch
             // overlap), then walked in list order -- thread tid holds primitive lst[gb + tid/32] * 32 + tid%32 and the list
             // is sorted, so record order is submission order
-            for (uint32_t gb = 0; gb < Ln; gb += SR_RASTER_WARPS) {
-                const uint32_t gi = gb + warp;
-                bool hit = false;
-                uint32_t t = 0;
-                if (gi < Ln) {
-                    t = lst[gi] * SR_GROUP + lane;
-                    const uint32_t rect = t < nprim ? __ldg(rects + t) : SR_RECT_INVALID;
-                    hit = rect != SR_RECT_INVALID && sr_rect_hits(rect, tx, ty);
-                }
+            uint32_t gpos = 0, queued = 0;
+            while (gpos < Ln || queued > 0) {
+                const uint32_t nh = gather(lst, Ln, rects, nprim, gpos, queued);
+                const uint32_t nb = min(nh, (uint32_t)SR_RASTER_THREADS);
+                bool hit = tid < nb;
+                const uint32_t t = hit ? s_hits[tid] : 0u;
                 // records of the primitives that touch this tile, compacted in list order (ballot + warp counts)
                 SrOrdLineRec lr;
                 SrOrdPointRec pr;
@@ -2045,6 +2087,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     for (uint32_t k = 0; k < total; ++k) sr_ord_point<FS>(c, s_point[k]);
                 }
                 __syncthreads();
+                queued = carry_over(nh, nb);
             }
         }
         __syncthreads();
