@@ -65,3 +65,32 @@ def test_product_sources_do_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "sr_oracle" not in text and "oracle_binding" not in text and "libsr_oracle" not in text, f
+
+
+def test_png_writer_round_trip(tmp_path):
+    """`image.save` of examples/suzanne.rs:191 in the host mirror: an 8-bit RGBA PNG that decodes back to the same bytes
+    (zlib + CRCs checked chunk by chunk; no GPU involved)."""
+    _ensure_built()
+    import struct
+    import zlib
+    import numpy as np
+    from softrender_b200 import pipeline
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    path = tmp_path / "t.png"
+    pipeline.write_png(str(path), img)
+    blob = path.read_bytes()
+    assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, seen = 8, b"", []
+    while pos < len(blob):
+        n, tag = struct.unpack(">I", blob[pos:pos + 4])[0], blob[pos + 4:pos + 8]
+        assert zlib.crc32(blob[pos + 4:pos + 8 + n]) & 0xFFFFFFFF == struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])[0]
+        seen.append(tag)
+        if tag == b"IHDR":
+            assert struct.unpack(">IIBBBBB", blob[pos + 8:pos + 8 + n]) == (53, 37, 8, 6, 0, 0, 0)
+        if tag == b"IDAT":
+            idat += blob[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    assert seen[0] == b"IHDR" and seen[-1] == b"IEND"
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(37, 1 + 53 * 4)
+    assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(37, 53, 4), img)
