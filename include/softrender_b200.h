@@ -161,7 +161,8 @@ int sr_vertex_run(sr_draw *, uint32_t vertex_shader);
 int sr_vertex_run_to_fragment(sr_draw *, const sr_viewport *, uint32_t vertex_shader);
 /* GeometryShader::run (src/pipeline/stages/geometry.rs:132-258) with a registered shader */
 int sr_geometry_run(sr_draw *, uint32_t geometry_shader);
-/* GeometryShader::clip_primitives (geometry.rs:261-336) */
+/* GeometryShader::clip_primitives (geometry.rs:261-336): the reference's clipper, restated literally.
+ * sr_geometry_run(d, SR_GS_CLIP_SH) is the opt-in correct one (Sutherland-Hodgman, same planes and intersect()). */
 int sr_geometry_clip_primitives(sr_draw *);
 /* GeometryShader::finish (geometry.rs:60-129) */
 int sr_geometry_finish(sr_draw *, const sr_viewport *);

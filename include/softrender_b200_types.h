@@ -104,7 +104,10 @@ enum sr_fragment_shader {
 enum sr_geometry_shader {
     SR_GS_CLIP = 0,            /* GeometryShader::clip_primitives, src/pipeline/stages/geometry.rs:261-336 */
     SR_GS_FACE_NORMALS = 1,    /* full_example/src/shaders.rs:63-89 */
-    SR_GS_VERTEX_NORMALS = 2   /* full_example/src/shaders.rs:35-61 */
+    SR_GS_VERTEX_NORMALS = 2,  /* full_example/src/shaders.rs:35-61 */
+    SR_GS_CLIP_SH = 3          /* opt-in: a CORRECT clipper (Sutherland-Hodgman against the same six planes, src/geometry/clip.rs:37-42)
+                                * for triangles -- the fix the reference asks for (src/lib.rs "Glaring Problems: Clipping");
+                                * lines and points as SR_GS_CLIP */
 };
 
 enum sr_blend {

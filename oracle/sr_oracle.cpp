@@ -277,6 +277,37 @@ void clip_triangle(Storage &out, const float *a, const float *b, const float *c,
     }
 }
 
+// SR_GS_CLIP_SH: Sutherland-Hodgman against the six planes of clip.rs:37-42, one plane after the other; an edge runs
+// from the previous vertex s to the current vertex p and crossings are intersect(plane, s, p) (clip.rs:47-63).  Not a
+// restatement of reference behaviour (the reference's clipper is clip_triangle above) but of the opt-in correct
+// clipper the library offers; the oracle carries the same definition so that it can be checked bit for bit.
+void clip_triangle_sh(Storage &out, const float *a, const float *b, const float *c, uint32_t S) {
+    std::vector<float> cur, nxt, tmp(S);
+    push_vertex(cur, a, S); push_vertex(cur, b, S); push_vertex(cur, c, S);
+    for (int plane = 0; plane < 6 && !cur.empty(); ++plane) {
+        nxt.clear();
+        const size_t n = cur.size() / S;
+        for (size_t i = 0; i < n; ++i) {
+            const float *s = &cur[((i + n - 1) % n) * S], *p = &cur[i * S];
+            const bool s_in = has_inside(plane, s), p_in = has_inside(plane, p);
+            if (p_in) {
+                if (!s_in) { intersect(plane, s, p, S, tmp.data()); push_vertex(nxt, tmp.data(), S); }
+                push_vertex(nxt, p, S);
+            } else if (s_in) {
+                intersect(plane, s, p, S, tmp.data());
+                push_vertex(nxt, tmp.data(), S);
+            }
+        }
+        cur.swap(nxt);
+    }
+    const size_t len = cur.size() / S;
+    for (size_t i = 1; i + 1 < len; ++i) {  // fan around the first vertex
+        push_vertex(out.tris, &cur[0], S);
+        push_vertex(out.tris, &cur[i * S], S);
+        push_vertex(out.tris, &cur[(i + 1) * S], S);
+    }
+}
+
 void clip_line(Storage &out, const float *start_in, const float *end_in, uint32_t S) {
     std::vector<float> start(start_in, start_in + S), end(end_in, end_in + S), isect(S);
     int intersections = 0;
@@ -309,8 +340,8 @@ constexpr float NORMAL_LENGTH = 0.05f;  // ref: full_example/src/shaders.rs:33
 void gs_apply(int gs, Storage &out, int kind, const float *a, const float *b, const float *c, uint32_t S,
               const sr_uniforms *u) {
     // kind: 1 point (a), 2 line (a,b), 3 triangle (a,b,c)
-    if (gs == SR_GS_CLIP) {
-        if (kind == 3) clip_triangle(out, a, b, c, S);
+    if (gs == SR_GS_CLIP || gs == SR_GS_CLIP_SH) {
+        if (kind == 3) { if (gs == SR_GS_CLIP) clip_triangle(out, a, b, c, S); else clip_triangle_sh(out, a, b, c, S); }
         else if (kind == 2) clip_line(out, a, b, S);
         else clip_point(out, a, S);
         return;
@@ -842,8 +873,8 @@ int so_draw_set_generated(so_draw *d, int which, const float *verts, uint64_t nv
 // concatenated in thread order (the reference merges in mutex-acquisition order).
 int so_draw_geometry_run(so_draw *d, int gs, const sr_uniforms *u, int nthreads) {
     if (!d || d->space != 0) return SR_ERR_INVALID_STATE;
-    if (gs < SR_GS_CLIP || gs > SR_GS_VERTEX_NORMALS) return SR_ERR_INVALID_ARGUMENT;
-    if (gs != SR_GS_CLIP && (!u || d->nk < 8)) return SR_ERR_INVALID_ARGUMENT;
+    if (gs < SR_GS_CLIP || gs > SR_GS_CLIP_SH) return SR_ERR_INVALID_ARGUMENT;
+    if (gs != SR_GS_CLIP && gs != SR_GS_CLIP_SH && (!u || d->nk < 8)) return SR_ERR_INVALID_ARGUMENT;
     const uint32_t S = 4 + d->nk;
     const int nt = nthreads < 1 ? 1 : nthreads;
     std::vector<Storage> locals(nt);

@@ -79,11 +79,25 @@ struct sr_context {
     uint32_t zero_off_tiles = 0;
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);
-    void release(void *p, size_t bytes) { free_list.emplace(bytes, p); }
+    // Lifetime: every device buffer keeps its context alive (refs), so children destroyed after sr_context_destroy -- a
+    // garbage collector tearing objects down in arbitrary order -- still find a valid context; `closed` contexts give
+    // memory straight back to the driver.
+    int refs = 1;
+    bool closed = false;
+    void release(void *p, size_t bytes) {
+        if (closed) cudaFree(p);
+        else free_list.emplace(bytes, p);
+    }
 };
+static void ctx_unref(sr_context *c) {
+    if (--c->refs == 0) delete c;
+}
 
 DevBuf::~DevBuf() {
-    if (ptr && ctx) ctx->release(ptr, bytes);
+    if (ptr && ctx) {
+        ctx->release(ptr, bytes);
+        ctx_unref(ctx);
+    }
 }
 
 int sr_context::alloc(size_t bytes, Buf *out) {
@@ -107,6 +121,7 @@ int sr_context::alloc(size_t bytes, Buf *out) {
     }
     auto b = std::make_shared<DevBuf>();
     b->ctx = this;
+    ++refs;
     b->ptr = p;
     b->bytes = bytes;
     *out = b;
@@ -762,16 +777,24 @@ int sr_context_create(int device, sr_context **out) {
 int sr_context_destroy(sr_context *c) {
     settle(c);
     if (!c) return SR_OK;
+    if (c->closed) return sr_fail(SR_ERR_INVALID_STATE, "context already destroyed");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    // the context's own buffers first (they hold references to it), then the cache, stream and events; the object itself
+    // goes when the last buffer of a still-living child (framebuffer, mesh, draw ...) has been released
+    c->list_arena.reset();
+    for (auto &a : c->ord_arena) a.reset();
+    c->zero_off.reset();
+    c->closed = true;
     for (auto &kv : c->free_list) cudaFree(kv.second);
     c->free_list.clear();
     for (auto &e : c->ev)
-        if (e) cudaEventDestroy(e);
-    if (c->ev_front) cudaEventDestroy(c->ev_front);
+        if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (c->ev_front) { cudaEventDestroy(c->ev_front); c->ev_front = nullptr; }
     cudaStreamDestroy(c->stream);
-    if (c->pinned) cudaFreeHost(c->pinned);
-    delete c;
+    c->stream = nullptr;
+    if (c->pinned) { cudaFreeHost(c->pinned); c->pinned = nullptr; }
+    ctx_unref(c);
     return SR_OK;
 }
 int sr_context_synchronize(sr_context *c) {
@@ -1262,13 +1285,15 @@ static int clip_small(sr_context *c, const SrGeoIn &in, uint32_t nk, VertexStrea
     SR_TRY(c->alloc((size_t)n * 4, &off));
     SrGeoOut none = {};
     const uint32_t grid = ceil_div(n, 128);
-    if (NV == 2) SR_LAUNCH(c, k_clip_line<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);
+    if (NV == 3) SR_LAUNCH(c, k_clip_tri_sh<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);  // SR_GS_CLIP_SH
+    else if (NV == 2) SR_LAUNCH(c, k_clip_line<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);
     else SR_LAUNCH(c, k_clip_point<0>, grid, 128, 0, in, cnt->as<uint32_t>(), nullptr, none);
     uint32_t total = 0;
     SR_TRY(exclusive_scan(c, cnt->as<uint32_t>(), n, off->as<uint32_t>(), &total));
     SR_TRY(alloc_stream(c, (uint64_t)total * NV, nk, out));
     SrGeoOut o = {out->pos->as<float4>(), out->attr->as<float4>(), out->np};
-    if (NV == 2) SR_LAUNCH(c, k_clip_line<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
+    if (NV == 3) SR_LAUNCH(c, k_clip_tri_sh<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
+    else if (NV == 2) SR_LAUNCH(c, k_clip_line<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
     else SR_LAUNCH(c, k_clip_point<1>, grid, 128, 0, in, nullptr, off->as<uint32_t>(), o);
     return SR_OK;
 }
@@ -1277,8 +1302,8 @@ extern "C" {
 int sr_geometry_run(sr_draw *d, uint32_t gs) {
     if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (d->stage != STAGE_GEOMETRY) return sr_fail(SR_ERR_INVALID_STATE, "geometry stage needs clip-space vertices");
-    if (gs > SR_GS_VERTEX_NORMALS) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown geometry shader %u", gs);
-    if (gs != SR_GS_CLIP && d->nk < 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "normal visualisation needs K = {position4, normal4, ..}");
+    if (gs > SR_GS_CLIP_SH) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown geometry shader %u", gs);
+    if (gs != SR_GS_CLIP && gs != SR_GS_CLIP_SH && d->nk < 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "normal visualisation needs K = {position4, normal4, ..}");
     sr_pipeline *p = d->pipeline;
     sr_context *c = p->ctx;
     SR_CUDA(cudaSetDevice(c->device));
@@ -1301,12 +1326,15 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
     VertexStream npoints, nlines, ntris;
     Buf nseq;
     uint32_t literal_total = 0;
-    if (gs == SR_GS_CLIP) {
+    if (gs == SR_GS_CLIP || gs == SR_GS_CLIP_SH) {
         SR_TRY(clip_small<1>(c, geo_in(1, true, true), d->nk, &npoints));
         SR_TRY(clip_small<2>(c, geo_in(2, true, true), d->nk, &nlines));
         const SrGeoIn tin = geo_in(3, true, true);
         const uint32_t n = tin.ngen + tin.nidx;
-        if (n == 0) {
+        if (gs == SR_GS_CLIP_SH) {
+            // the opt-in correct clipper: every output triangle is kept and numbered in output order (no literal sequence)
+            SR_TRY(clip_small<3>(c, tin, d->nk, &ntris));
+        } else if (n == 0) {
             SR_TRY(alloc_stream(c, 0, d->nk, &ntris));
         } else {
             // zero-area outputs of the literal clipper are dropped unless a stencil op could observe them

@@ -376,6 +376,51 @@ __global__ void __launch_bounds__(128) k_clip_tri_emit(const SrGeoIn in, uint32_
     }
 }
 
+// SR_GS_CLIP_SH: Sutherland-Hodgman against the same six planes, one plane after the other; an edge runs from the
+// previous vertex s to the current vertex p and crossings are intersect(plane, s, p) (clip.rs:47-63).  A triangle
+// clipped by six planes has at most nine vertices; the result is fanned around its first vertex.  MODE 0 = count, 1 = emit.
+#define SR_SH_MAX 9
+template <int MODE>
+__global__ void __launch_bounds__(128) k_clip_tri_sh(const SrGeoIn in, uint32_t *count, const uint32_t *off, SrGeoOut out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.ngen + in.nidx) return;
+    float rec[3][4 + SR_MAX_NK];
+    sr_geo_load<3>(in, t, rec);
+    const uint32_t nfloats = 4 + in.nplanes * 4;
+    float poly[2][SR_SH_MAX][4 + SR_MAX_NK];
+    int n = 3, cur = 0;
+    for (int k = 0; k < 3; ++k)
+        for (uint32_t i = 0; i < nfloats; ++i) poly[0][k][i] = rec[k][i];
+    for (int plane = 0; plane < 6 && n > 0; ++plane) {
+        int m = 0;
+        float(*src)[4 + SR_MAX_NK] = poly[cur], (*dst)[4 + SR_MAX_NK] = poly[cur ^ 1];
+        for (int i = 0; i < n; ++i) {
+            const float *s = src[(i + n - 1) % n], *p = src[i];
+            const bool s_in = sr_has_inside(plane, s), p_in = sr_has_inside(plane, p);
+            if (p_in) {
+                if (!s_in && m < SR_SH_MAX) sr_intersect(plane, s, p, nfloats, dst[m++]);
+                if (m < SR_SH_MAX) { for (uint32_t j = 0; j < nfloats; ++j) dst[m][j] = p[j]; ++m; }
+            } else if (s_in && m < SR_SH_MAX) {
+                sr_intersect(plane, s, p, nfloats, dst[m++]);
+            }
+        }
+        n = m;
+        cur ^= 1;
+    }
+    const int nt = n >= 3 ? n - 2 : 0;
+    if (MODE == 0) {
+        count[t] = (uint32_t)nt;
+    } else {
+        uint64_t o = (uint64_t)off[t] * 3;
+        for (int i = 1; i + 1 < n; ++i) {
+            sr_geo_store(out, o, poly[cur][0], in.nplanes);
+            sr_geo_store(out, o + 1, poly[cur][i], in.nplanes);
+            sr_geo_store(out, o + 2, poly[cur][i + 1], in.nplanes);
+            o += 3;
+        }
+    }
+}
+
 // line clipper (geometry.rs:300-327): MODE 0 = count, 1 = emit
 template <int MODE>
 __global__ void __launch_bounds__(128) k_clip_line(const SrGeoIn in, uint32_t *count, const uint32_t *off, SrGeoOut out) {

@@ -325,8 +325,13 @@ class GeometryShader(_Stage):
         check(lib.sr_geometry_run(self.h, geometry_shader))
         return GeometryShader(self.pipeline, self._take())
 
-    def clip_primitives(self) -> "GeometryShader":
-        check(lib.sr_geometry_clip_primitives(self.h))
+    def clip_primitives(self, correct: bool = False) -> "GeometryShader":
+        """GeometryShader::clip_primitives (geometry.rs:261-336), literally.  correct=True is the opt-in Sutherland-Hodgman
+        clipper (SR_GS_CLIP_SH) the reference's author asks for (src/lib.rs, "Glaring Problems: Clipping")."""
+        if correct:
+            check(lib.sr_geometry_run(self.h, 3))
+        else:
+            check(lib.sr_geometry_clip_primitives(self.h))
         return GeometryShader(self.pipeline, self._take())
 
     def finish(self, viewport: Viewport) -> "FragmentShader":

@@ -168,8 +168,8 @@ class OracleDraw:
         self._ck(lib().so_draw_geometry_run(self.h, gs, ctypes.byref(uniforms) if uniforms is not None else None, nthreads))
         return self
 
-    def clip_primitives(self, nthreads=1):
-        return self.geometry_run(sr.GS_CLIP, None, nthreads)
+    def clip_primitives(self, nthreads=1, correct=False):
+        return self.geometry_run(sr.GS_CLIP_SH if correct else sr.GS_CLIP, None, nthreads)
 
     def finish(self, viewport, nthreads=1):
         self._ck(lib().so_draw_finish(self.h, ctypes.byref(viewport), nthreads))

@@ -576,6 +576,45 @@ def test_clip_primitives_random(P, ctx, prim):
     fb.destroy()
 
 
+def test_correct_clipper_opt_in(P, ctx):
+    """SR_GS_CLIP_SH, the opt-in Sutherland-Hodgman clipper (the fix src/lib.rs asks for): bit-identical with the oracle's
+    definition, every output vertex inside the frustum (up to rounding of the intersections), triangles entirely inside
+    come through unchanged, and the rendered frame matches."""
+    rng = np.random.default_rng(73)
+    n = 900
+    verts = _clip_space_triangles(rng, n)
+    idx = rng.integers(0, len(verts), 3 * 700).astype(np.uint32)
+    w, h = 96, 80
+    u = scenes.suzanne_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.1, 100.0)
+    fb = make_fb(P, ctx, w, h)
+    ofb = oracle_fb(w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 0).clip_primitives(correct=True)
+    gs = pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 0).clip_primitives(correct=True)
+    S = verts.shape[1]
+    g = gs.download(3).reshape(-1, 3, S)
+    o = od.data(3).reshape(-1, 3, S)
+    H.assert_bits_equal(g, o, "Sutherland-Hodgman output")
+    assert 0 < len(g) <= 7 * 700
+    x, y, z, ww = (g[..., k].astype(np.float64) for k in range(4))
+    eps = 1e-4 * np.maximum(1.0, np.abs(ww))
+    assert (x >= -ww - eps).all() and (x <= ww + eps).all() and (y >= -ww - eps).all() and (y <= ww + eps).all()
+    assert (z >= -eps).all() and (z <= ww + eps).all()
+    tri = verts[idx].reshape(-1, 3, S)
+    inside = ((np.abs(tri[..., 0]) <= tri[..., 3]) & (np.abs(tri[..., 1]) <= tri[..., 3]) & (tri[..., 2] >= 0) & (tri[..., 2] <= tri[..., 3])).all(axis=1)
+    assert inside.sum() >= 2
+    gset = {bytes(t.tobytes()) for t in g}
+    assert all(bytes(t.tobytes()) in gset for t in tri[inside])
+    od.finish(vp).fragment_run(ofb, sr.FS_FLAT, u)
+    gs.finish(vp).run(sr.FS_FLAT)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="correct clipper frame")
+    pipe.destroy()
+    fb.destroy()
+
+
 @pytest.mark.parametrize("gs_id", [sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS])
 def test_normal_visualisation_geometry_shaders(P, ctx, gs_id):
     size = 200
@@ -816,6 +855,23 @@ def test_exact_division_shortcut(P, ctx):
     bit for bit, over its whole validity range (4e9 random operand pairs incl. all-ones/sparse mantissas)."""
     for seed in (1, 0xDEADBEEF):
         assert ctx.selftest_division(seed, 2_000_000_000) == 0
+
+
+def test_children_may_outlive_their_context(P):
+    """A garbage collector destroys handles in arbitrary order: children released after sr_context_destroy must still find a
+    valid context (every device buffer keeps it alive), and a second destroy of the context is an error, not a crash."""
+    from softrender_b200._abi import SoftrenderError
+    c2 = P.Context(0)
+    fb = P.RenderBuffer.with_dimensions(c2, 64, 48)
+    mesh = P.Mesh(c2, H.suzanne_mesh())
+    pipe = P.Pipeline.from_framebuffer(fb, scenes.suzanne_uniforms(64, 48))
+    fb.clear(H.CLEAR)
+    pipe.render_mesh(sr.TRIANGLE, mesh).run_to_fragment(scenes.Viewport.new(64, 48, 0.001, 1000.0), sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    st = pipe.render_mesh(sr.TRIANGLE, mesh).run(sr.VS_SUZANNE)  # a draw left unfinished
+    assert (fb.download()[:, :3].max(axis=1) > 0.05).sum() > 50
+    c2.close()
+    for x in (st, pipe, mesh, fb):
+        x.destroy()
 
 
 def test_error_behaviour(P, ctx):
