@@ -66,15 +66,17 @@ __device__ __forceinline__ uint32_t sr_prim_rect(const SrBinParams &p, uint32_t 
         maxx = sr_clamp_as_int(fmaxf(fmaxf(x[0], x[1]), x[2]), 0, p.width - 1);
         maxy = sr_clamp_as_int(fmaxf(fmaxf(y[0], y[1]), y[2]), 0, p.height - 1);
     } else if (NV == 2) {
-        // conservative: every pixel rasterize_line can plot lies in the end-point box (+1 pixel)
+        // conservative: every pixel rasterize_line can plot lies in the end-point box widened by two pixels (Wu plots the
+        // minor coordinates trunc(yend) and trunc(yend) + 1 with yend up to half a pixel past the clipped end point, and
+        // rounds the major coordinate of the end points, line.rs:181-199)
         minx = sr_clamp_as_int(fminf(x[0], x[NV - 1]), 0, p.width - 1);
         miny = sr_clamp_as_int(fminf(y[0], y[NV - 1]), 0, p.height - 1);
         maxx = sr_clamp_as_int(fmaxf(x[0], x[NV - 1]), 0, p.width - 1);
         maxy = sr_clamp_as_int(fmaxf(y[0], y[NV - 1]), 0, p.height - 1);
-        minx = minx > 0 ? minx - 1 : 0;
-        miny = miny > 0 ? miny - 1 : 0;
-        maxx = maxx + 1 < p.width ? maxx + 1 : p.width - 1;
-        maxy = maxy + 1 < p.height ? maxy + 1 : p.height - 1;
+        minx = minx > 2 ? minx - 2 : 0;
+        miny = miny > 2 ? miny - 2 : 0;
+        maxx = maxx + 2 < p.width ? maxx + 2 : p.width - 1;
+        maxy = maxy + 2 < p.height ? maxy + 2 : p.height - 1;
     } else {
         // point.rs:46: bounds.0 <= x < bounds.1 with bounds = (0,0)..(w-1,h-1)
         if (!(0.0f <= x[0] && x[0] < (float)(p.width - 1) && 0.0f <= y[0] && y[0] < (float)(p.height - 1))) return SR_RECT_INVALID;
@@ -1624,9 +1626,11 @@ __device__ void sr_ord_lines_chunk(const SrOrdCtx &c, const SrOrdLineRec *recs, 
     const int tx0 = (int)c.x0, tx1 = (int)c.xe;
     const int band_lo = (int)c.y0 + (int)(threadIdx.x >> 5) * SR_ORD_BAND, band_hi = min(band_lo + SR_ORD_BAND - 1, (int)c.ye);
     bool active = false;
-    if (lane < n) {  // the whole line misses the band (one pixel of slack for Wu's second row): nothing to walk
+    if (lane < n) {
+        // the whole line misses the band: nothing to walk.  Wu plots rows trunc(yend) and trunc(yend) + 1 with yend up to
+        // half a pixel past the clipped end point (line.rs:181-199), i.e. up to two rows beyond trunc(y) of the end points
         const int ya = (int)recs[lane].cl[1], yb = (int)recs[lane].cl[3];
-        active = !(max(ya, yb) + 1 < band_lo || min(ya, yb) - 1 > band_hi);
+        active = !(max(ya, yb) + 2 < band_lo || min(ya, yb) - 2 > band_hi);
     }
     if (!__any_sync(0xffffffffu, active)) return;
     const SrOrdLineRec &r = recs[min(lane, n - 1)];

@@ -857,6 +857,40 @@ def test_exact_division_shortcut(P, ctx):
         assert ctx.selftest_division(seed, 2_000_000_000) == 0
 
 
+def test_randomised_scenarios(P, ctx):
+    """250 random scenarios (tests/fuzz_scenarios.py): frame sizes, triangle / line / point mixes, blend, stencil, cull,
+    antialiased lines, one or two draws, every split setting -- each must equal the oracle bit for bit.  The seeds
+    include the ones with which the campaign (profiles/scripts/fuzz.py) found the too-narrow tile rectangle of Wu lines."""
+    from fuzz_scenarios import run_scenario
+    failures = [m for m in (run_scenario(P, ctx, run_both_screen, seed) for seed in list(range(1000, 1240)) + [1291, 1558, 2010, 2052]
+                            + list(range(5000, 5006))) if m]
+    assert not failures, "\n".join(failures)
+
+
+def test_antialiased_lines_across_tile_and_band_boundaries(P, ctx):
+    """Wu plots the rows trunc(yend) and trunc(yend) + 1 with yend up to half a pixel past the clipped end point, so a line
+    reaches up to two rows / columns beyond the truncated end-point box: lines ending just before tile rows (multiples of 32),
+    tile columns (64) and band rows (4) must not lose those pixels (found by the randomised campaign)."""
+    w, h = 200, 140
+    rows = []
+    for k, edge in enumerate([31.95, 63.6, 95.99, 3.9, 7.51, 127.75]):
+        for j, slope in enumerate([0.0, 0.45, -0.45, 0.95]):
+            x0 = 5.3 + 7.1 * j + 3.3 * k
+            rows.append(((x0, edge - 20 * slope), (x0 + 20.0, edge)))          # non-steep, ends next to a tile / band row
+            rows.append(((edge + 0.2, 8.2 + 5 * j), (edge + 0.2 + 9 * slope, 40.7 + 5 * j)))  # steep, next to a tile column
+    v = np.zeros((2 * len(rows), 8), np.float32)
+    for i, (a, b) in enumerate(rows):
+        v[2 * i, :2], v[2 * i + 1, :2] = a, b
+    v[:, 2] = -1.0 - 0.01 * np.arange(len(v))
+    v[:, 3] = 1.0
+    v[:, 4:] = np.random.default_rng(7).uniform(0.2, 1.0, (len(v), 4))
+    idx = np.arange(len(v), dtype=np.uint32)
+    for blend in (sr.BLEND_ALPHA_OVER, sr.BLEND_REPLACE):
+        out, win, _, ofb = run_both_screen(P, ctx, w, h, v, idx, prim=sr.LINE, aa=True, blend=blend)
+        assert np.array_equal(win, ofb.winner)
+        H.compare_framebuffers(out, ofb, exact_color=True, what="antialiased lines at tile boundaries")
+
+
 def test_children_may_outlive_their_context(P):
     """A garbage collector destroys handles in arbitrary order: children released after sr_context_destroy must still find a
     valid context (every device buffer keeps it alive), and a second destroy of the context is an error, not a crash."""
