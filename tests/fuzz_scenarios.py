@@ -63,3 +63,85 @@ def run_scenario(P, ctx, run_both_screen, seed: int) -> str:
     finally:
         ctx.set_micro()
     return ""
+
+
+def run_pipeline_scenario(P, ctx, ob, scenes, seed: int) -> str:
+    """The whole builder chain on a random scene: Suzanne / subdivided Suzanne / a small displaced grid, random camera
+    distance (meshes cross the frustum planes when close), rotation and frame size, both example shader sets, with or
+    without the geometry stage (literal or Sutherland-Hodgman clipper), blend, cull, optionally tile-sharded.
+    Winner plane and depth must be bit-exact, colour within 1/255."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(16, 500)), int(rng.integers(16, 400))
+    kind = int(rng.integers(0, 4))
+    full = kind >= 2  # full_example shader set (needs uv) vs suzanne shader set
+    if kind == 3:
+        mesh = scenes.make_grid(int(rng.integers(4, 40)), int(rng.integers(4, 30)), int(rng.integers(1, 4)), seed=seed)
+        full = False
+    else:
+        mesh = H.suzanne_mesh(with_uv=full)
+        if rng.random() < 0.25:
+            mesh = scenes.subdivide(mesh, 1)
+    dist = float(rng.choice([0.6, 0.9, 1.3, 2.0, 3.5]))
+    rot = float(rng.uniform(0, 2 * np.pi))
+    if kind == 3:
+        u = scenes.grid_uniforms(w, h)
+        near, far = 0.1, 100.0
+    elif full:
+        u = scenes.full_example_uniforms(w / h, np.deg2rad(75.0), dist, rot, np.deg2rad(65.0), float(rng.uniform(-1.5, 1.5)))
+        near, far = 0.1, 1000.0
+    else:
+        u = scenes.suzanne_uniforms(w, h, rotation_y=rot)
+        near, far = 0.001, 1000.0
+    vp = scenes.Viewport.new(w, h, near, far)
+    vs = sr.VS_FULL_EXAMPLE if full else sr.VS_SUZANNE
+    textured = full and rng.random() < 0.5
+    fs = (sr.FS_FULL_EXAMPLE_TEXTURED if textured else sr.FS_FULL_EXAMPLE) if full else sr.FS_SUZANNE
+    clip = int(rng.integers(0, 3))  # 0: run_to_fragment, 1: literal clipper, 2: Sutherland-Hodgman
+    blend = sr.BLEND_ALPHA_OVER if rng.random() < 0.35 else sr.BLEND_REPLACE
+    cull = [None, sr.CLOCKWISE, sr.COUNTER_CLOCKWISE][int(rng.integers(0, 3))]
+    # (single-process emulation of sharding: every rank draws into the same framebuffer object, so each rank must own a tile --
+    # a rank without tiles would leave its lazily recorded clear pending for the whole frame)
+    world = min(int(rng.choice([1, 1, 2, 3])), ((w + 63) // 64) * ((h + 31) // 32))
+    draws = int(rng.integers(1, 3))
+    what = (f"pipeline seed {seed}: {w}x{h} mesh kind {kind} ({mesh.ntris} tris) dist {dist} clip {clip} fs {fs} blend {blend} cull {cull} "
+            f"world {world} draws {draws}")
+    tex = scenes.checker_texture(64, 8) if textured else None
+    ofb = ob.OracleFramebuffer(w, h)
+    ofb.clear(H.CLEAR)
+    for _ in range(draws):
+        od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        od.cull = sr.CULL_NONE if cull is None else cull
+        od.blend = blend
+        if clip == 0:
+            od.vertex_run_to_fragment(vp, vs, u, mesh.vertices)
+        else:
+            od.vertex_run(vs, u, mesh.vertices).clip_primitives(correct=(clip == 2)).finish(vp)
+        od.fragment_run(ofb, fs, u, texture=tex)
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)
+    fb.enable_winner(True)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    gtex = P.Texture(ctx, tex) if textured else None
+    if gtex is not None:
+        pipe.bind_texture(gtex)
+    try:
+        for rank in range(world):
+            ctx.set_tile_shard(rank, world)
+            fb.clear(H.CLEAR)
+            for _ in range(draws):
+                st = pipe.render_mesh(sr.TRIANGLE, gmesh)
+                st = st.run_to_fragment(vp, vs) if clip == 0 else st.run(vs).clip_primitives(correct=(clip == 2)).finish(vp)
+                st.cull_faces(cull).with_blend(blend).run(fs)
+        ctx.set_tile_shard(0, 1)
+        win = fb.download_winner()
+        out = fb.download()
+        if world == 1 and not np.array_equal(win, ofb.winner):  # (the winner plane is per draw call and rank: compared unsharded only)
+            return what + f": winner plane differs at {int((win != ofb.winner).sum())} pixels"
+        H.compare_framebuffers(out, ofb, color_tol=1.0 / 255.0, what=what)
+    except AssertionError as e:
+        return what + ": " + str(e)[:200]
+    finally:
+        ctx.set_tile_shard(0, 1)
+        for x in (pipe, gmesh, fb) + ((gtex,) if gtex is not None else ()):
+            x.destroy()
+    return ""

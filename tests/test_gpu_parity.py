@@ -867,6 +867,16 @@ def test_randomised_scenarios(P, ctx):
     assert not failures, "\n".join(failures)
 
 
+def test_randomised_pipeline_scenarios(P, ctx):
+    """80 random scenes through the whole builder chain (tests/fuzz_scenarios.py::run_pipeline_scenario): Suzanne, subdivided
+    Suzanne or a displaced grid; random camera distance (meshes cross the frustum planes when close), rotation, frame size;
+    both example shader sets, textured or not; run_to_fragment / literal clipper / Sutherland-Hodgman clipper; blend, cull,
+    one or two draws, optionally tile-sharded.  Winner and depth bit-exact, colour within 1/255."""
+    from fuzz_scenarios import run_pipeline_scenario
+    failures = [m for m in (run_pipeline_scenario(P, ctx, ob, scenes, seed) for seed in range(100, 180)) if m]
+    assert not failures, "\n".join(failures)
+
+
 def test_antialiased_lines_across_tile_and_band_boundaries(P, ctx):
     """Wu plots the rows trunc(yend) and trunc(yend) + 1 with yend up to half a pixel past the clipped end point, so a line
     reaches up to two rows / columns beyond the truncated end-point box: lines ending just before tile rows (multiples of 32),
