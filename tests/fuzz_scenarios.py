@@ -8,12 +8,18 @@ import softrender_b200 as sr
 import helpers as H
 
 
-def run_scenario(P, ctx, run_both_screen, seed: int) -> str:
-    """Runs one scenario; returns "" when the GPU frame equals the oracle's, a description of the mismatch otherwise."""
+def run_scenario(P, ctx, run_both_screen, seed: int, big: bool = False) -> str:
+    """Runs one scenario; returns "" when the GPU frame equals the oracle's, a description of the mismatch otherwise.
+    big: frames of up to 2200x1400 with 60k-300k triangles (the wide per-draw split, many tiles, long lists)."""
     rng = np.random.default_rng(seed)
-    w, h = int(rng.integers(2, 400)), int(rng.integers(2, 300))
-    ntri = int(rng.choice([0, 1, 7, 100, 900, 5000, 60000], p=[.05, .05, .1, .25, .3, .2, .05]))
-    max_size = float(rng.choice([1.5, 3.0, 8.0, 30.0, 0.35 * min(w, h) + 1]))
+    if big:
+        w, h = int(rng.integers(600, 2200)), int(rng.integers(400, 1400))
+        ntri = int(rng.choice([60000, 150000, 300000]))
+        max_size = float(rng.choice([1.5, 3.0, 8.0, 30.0]))
+    else:
+        w, h = int(rng.integers(2, 400)), int(rng.integers(2, 300))
+        ntri = int(rng.choice([0, 1, 7, 100, 900, 5000, 60000], p=[.05, .05, .1, .25, .3, .2, .05]))
+        max_size = float(rng.choice([1.5, 3.0, 8.0, 30.0, 0.35 * min(w, h) + 1]))
     integer_depth = bool(rng.integers(0, 2))
     tri = H.random_screen_triangles(rng, max(ntri, 1), w, h, max_size=max_size, integer_depth=integer_depth)[:3 * ntri]
     gen = {}
