@@ -151,3 +151,64 @@ def run_pipeline_scenario(P, ctx, ob, scenes, seed: int) -> str:
         for x in (pipe, gmesh, fb) + ((gtex,) if gtex is not None else ()):
             x.destroy()
     return ""
+
+
+def run_geometry_scenario(P, ctx, ob, scenes, seed: int) -> str:
+    """Line / point meshes and the normal-visualisation geometry shaders through the builder chain: Suzanne's vertices drawn
+    as points or as lines over random index pairs (clipped or not), or face / vertex normals (full_example/src/shaders.rs:35-89)
+    with Bresenham or Wu lines, on top of the shaded mesh or alone.  Winner and depth bit-exact, colour within 1/255."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(16, 420)), int(rng.integers(16, 320))
+    mesh = H.suzanne_mesh(with_uv=True)
+    dist = float(rng.choice([0.7, 1.0, 2.0, 3.0]))
+    u = scenes.full_example_uniforms(w / h, np.deg2rad(75.0), dist, float(rng.uniform(0, 6.28)), np.deg2rad(65.0), float(rng.uniform(-1.0, 1.0)))
+    vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
+    mode = int(rng.integers(0, 4))  # 0 points, 1 lines, 2 face normals, 3 vertex normals
+    aa = bool(rng.integers(0, 2)) and mode != 0
+    blend = sr.BLEND_ALPHA_OVER if (aa or rng.random() < 0.3) else sr.BLEND_REPLACE
+    under = mode >= 2 and rng.random() < 0.5  # draw the shaded mesh first, normals on top (config 2's two passes)
+    clip = bool(rng.integers(0, 2))
+    what = f"geometry seed {seed}: {w}x{h} mode {mode} aa {aa} blend {blend} clip {clip} mesh-under {under} dist {dist}"
+    nv = len(mesh.vertices)
+    if mode == 0:
+        prim, idx = sr.POINT, rng.integers(0, nv, int(rng.integers(1, 3000))).astype(np.uint32)
+    elif mode == 1:
+        prim, idx = sr.LINE, rng.integers(0, nv, 2 * int(rng.integers(1, 800))).astype(np.uint32)
+    else:
+        prim, idx = sr.TRIANGLE, mesh.indices
+    gs = [None, None, sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS][mode]
+    fs_top = sr.FS_GREEN if mode >= 2 else sr.FS_FULL_EXAMPLE
+    ofb = ob.OracleFramebuffer(w, h)
+    ofb.clear(H.CLEAR)
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)
+    fb.enable_winner(True)
+    fb.clear(H.CLEAR)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, vertices=mesh.vertices, indices=idx)
+    gfull = P.Mesh(ctx, mesh) if under else None
+    try:
+        if under:
+            od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+            od.vertex_run_to_fragment(vp, sr.VS_FULL_EXAMPLE, u, mesh.vertices).fragment_run(ofb, sr.FS_FULL_EXAMPLE, u)
+            pipe.render_mesh(sr.TRIANGLE, gfull).run_to_fragment(vp, sr.VS_FULL_EXAMPLE).run(sr.FS_FULL_EXAMPLE)
+        od = ob.OracleDraw(prim, idx)
+        od.blend, od.aa = blend, aa
+        od.vertex_run(sr.VS_FULL_EXAMPLE, u, mesh.vertices)
+        st = pipe.render_mesh(prim, gmesh).run(sr.VS_FULL_EXAMPLE)
+        if gs is not None:
+            od.geometry_run(gs, u)
+            st = st.run(gs)
+        if clip:
+            od.clip_primitives()
+            st = st.clip_primitives()
+        od.finish(vp).fragment_run(ofb, fs_top, u)
+        st.finish(vp).with_blend(blend).antialiased_lines(aa).run(fs_top)
+        if not np.array_equal(fb.download_winner(), ofb.winner):
+            return what + ": winner plane differs"
+        H.compare_framebuffers(fb.download(), ofb, color_tol=1.0 / 255.0, what=what)
+    except AssertionError as e:
+        return what + ": " + str(e)[:200]
+    finally:
+        for x in (pipe, gmesh, fb) + ((gfull,) if gfull is not None else ()):
+            x.destroy()
+    return ""

@@ -877,6 +877,14 @@ def test_randomised_pipeline_scenarios(P, ctx):
     assert not failures, "\n".join(failures)
 
 
+def test_randomised_geometry_scenarios(P, ctx):
+    """60 random scenes of point / line meshes and the normal-visualisation geometry shaders (Bresenham or Wu, blended or
+    not, clipped or not, alone or on top of the shaded mesh): tests/fuzz_scenarios.py::run_geometry_scenario."""
+    from fuzz_scenarios import run_geometry_scenario
+    failures = [m for m in (run_geometry_scenario(P, ctx, ob, scenes, seed) for seed in range(100, 160)) if m]
+    assert not failures, "\n".join(failures)
+
+
 def test_antialiased_lines_across_tile_and_band_boundaries(P, ctx):
     """Wu plots the rows trunc(yend) and trunc(yend) + 1 with yend up to half a pixel past the clipped end point, so a line
     reaches up to two rows / columns beyond the truncated end-point box: lines ending just before tile rows (multiples of 32),
