@@ -54,8 +54,11 @@ def run_scenario(P, ctx, run_both_screen, seed: int, big: bool = False) -> str:
     idx = np.arange(len(tri), dtype=np.uint32)
     if ntri and rng.random() < 0.3:
         idx = (rng.permutation(ntri).astype(np.uint32)[:, None] * 3 + np.arange(3, dtype=np.uint32)[None, :]).reshape(-1)
+    tiny_arena = rng.random() < 0.12  # per-tile list arenas too small: the passes skip themselves and are replayed
+    if tiny_arena:
+        ctx.set_list_capacity(int(rng.integers(1, 48)))
     what = (f"seed {seed}: {w}x{h} ntri {ntri} size {max_size:.1f} gen {[(k, len(v)) for k, v in gen.items()]} blend {blend} aa {aa} "
-            f"fs {fs} cull {cull} stencil {stencil} draws {draws} split mode {mode}")
+            f"fs {fs} cull {cull} stencil {stencil} draws {draws} split mode {mode} tiny arena {tiny_arena}")
     try:
         out, win, st, ofb = run_both_screen(P, ctx, w, h, tri if ntri else np.zeros((0, 8), np.float32), idx, fs=fs, cull=cull, blend=blend,
                                             aa=aa, gen=gen or None, draws=draws, **kw)
@@ -68,6 +71,8 @@ def run_scenario(P, ctx, run_both_screen, seed: int, big: bool = False) -> str:
         return what + ": " + str(e)[:200]
     finally:
         ctx.set_micro()
+        if tiny_arena:
+            ctx.set_list_capacity(1 << 20)
     return ""
 
 
