@@ -185,6 +185,67 @@ def bind_to_gpu_numa_node(local_rank: int):
         return f"unbound ({type(e).__name__})"
 
 
+def other_configs(ctx):
+    """Single-stream frame times of the other BASELINE configs on the same box (reported beside the headline, not part of it):
+    config 1 (Suzanne 1024x1024, examples/suzanne.rs path) and config 2 as composed in SURVEY.md 8d (three Suzanne instances
+    at 1920x1080, textured 4-light shader, alpha_over blend, then the face-normal line pass with the green shader)."""
+    import softrender_b200 as sr
+    from softrender_b200 import pipeline as P, scenes
+    import helpers as H
+
+    def per_frame_us(frame, n):
+        for _ in range(5):
+            frame()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            frame()
+        ctx.synchronize()
+        return (time.perf_counter() - t0) / n * 1e6
+
+    out = {}
+    size = 1024
+    mesh = H.suzanne_mesh()
+    fb = P.RenderBuffer.with_dimensions(ctx, size, size)
+    pipe = P.Pipeline.from_framebuffer(fb, scenes.suzanne_uniforms(size, size))
+    gm = P.Mesh(ctx, mesh)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+
+    def suzanne():
+        fb.clear(CLEAR)
+        pipe.render_mesh(sr.TRIANGLE, gm).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+
+    out["config1_suzanne_1024_us_per_frame"] = per_frame_us(suzanne, 64)
+    for x in (pipe, gm, fb):
+        x.destroy()
+
+    w, h = 1920, 1080
+    mesh = H.suzanne_mesh(with_uv=True)
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)
+    tex = P.Texture(ctx, scenes.checker_texture(512, 8))
+    gm = P.Mesh(ctx, mesh)
+    us = [scenes.full_example_uniforms(w / h, np.deg2rad(75.0), 2.0, np.deg2rad(rot), np.deg2rad(65.0), off)
+          for rot, off in [(45.0, -1.6), (165.0, 0.0), (285.0, 1.6)]]
+    pipe = P.Pipeline.from_framebuffer(fb, us[0])
+    pipe.bind_texture(tex)
+    vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
+
+    def full_example():
+        fb.clear(CLEAR)
+        for u in us:
+            pipe.set_uniforms(u)
+            pipe.render_mesh(sr.TRIANGLE, gm).run(sr.VS_FULL_EXAMPLE).finish(vp).with_blend(sr.BLEND_ALPHA_OVER).run(sr.FS_FULL_EXAMPLE_TEXTURED)
+        for u in us:
+            pipe.set_uniforms(u)
+            pipe.render_mesh(sr.TRIANGLE, gm).run(sr.VS_FULL_EXAMPLE).run(sr.GS_FACE_NORMALS).finish(vp).run(sr.FS_GREEN)
+
+    out["config2_full_example_1080p_us_per_frame"] = per_frame_us(full_example, 32)
+    out["config2_composition"] = "3 x 968 triangles, textured 4-light shader, alpha_over; then 3 x 968 face-normal lines, green shader"
+    for x in (pipe, gm, tex, fb):
+        x.destroy()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -290,6 +351,7 @@ def run_ours(args):
         frame()
         for k, v in ctx.stage_times().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / nstage
+    ctx.set_stage_timing(False)
 
     # ---- N>1: sort-first tile sharding of ONE frame, peer-store composite into rank 0's framebuffer over NVLink ----
     sharded = None
@@ -419,6 +481,11 @@ def run_ours(args):
         }
         if sharded:
             line["sharded"] = sharded
+        if world == 1 and args.config == "grid10m":
+            try:
+                line["other_configs"] = other_configs(ctx)
+            except Exception as e:  # never let the side measurements take the headline line down
+                line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _, _ = cpu_reference_sample(args.config)
         print(json.dumps(line))
