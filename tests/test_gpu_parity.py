@@ -926,6 +926,46 @@ def test_children_may_outlive_their_context(P):
         x.destroy()
 
 
+def test_duplicate_and_with_framebuffer(P, ctx):
+    """`duplicate()` (vertex.rs:44, geometry.rs:43, fragment.rs:122) re-uses one stage's output for several passes; both
+    copies must stay usable and independent (finish() normalises a shared position buffer copy-on-write).
+    `Pipeline::with_framebuffer` (mod.rs:126-140) swaps the target and RESETS the stencil configuration."""
+    w, h = 120, 90
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.001, 1000.0)
+    vp2 = scenes.Viewport.new(w // 2, h // 2, 0.001, 1000.0)  # second pass into the top-left quarter
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    gs = pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE)
+    dup = gs.duplicate()
+    gs.clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+    dup.finish(vp2).with_blend(sr.BLEND_ALPHA_OVER).run(sr.FS_SUZANNE)
+    ofb = oracle_fb(w, h)
+    for view, clip, blend in ((vp, True, sr.BLEND_REPLACE), (vp2, False, sr.BLEND_ALPHA_OVER)):
+        od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        od.blend = blend
+        od.vertex_run(sr.VS_SUZANNE, u, mesh.vertices)
+        if clip:
+            od.clip_primitives()
+        od.finish(view).fragment_run(ofb, sr.FS_SUZANNE, u)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="duplicate")
+    # with_framebuffer: a configuration that would reject everything is reset to Always / Keep
+    fbs = make_fb(P, ctx, w, h, stencil=True)
+    pipe.set_stencil_config(sr.STENCIL_NEVER, sr.STENCIL_ZERO)
+    pipe.with_framebuffer(fbs)
+    pipe.render_mesh(sr.TRIANGLE, gmesh, stencil=3).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    ofs = oracle_fb(w, h, stencil=True)
+    od = ob.OracleDraw(sr.TRIANGLE, mesh.indices, 3)
+    od.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices).fragment_run(ofs, sr.FS_SUZANNE, u, sr.STENCIL_ALWAYS, sr.STENCIL_KEEP)
+    assert np.array_equal(fbs.download_winner(), ofs.winner) and (ofs.winner > 0).sum() > 100
+    H.compare_framebuffers(fbs.download(), ofs, color_tol=COLOR_TOL, what="with_framebuffer")
+    for x in (pipe, gmesh, fb, fbs):
+        x.destroy()
+
+
 def test_error_behaviour(P, ctx):
     from softrender_b200._abi import SoftrenderError
     u = scenes.suzanne_uniforms(8, 8)
