@@ -43,6 +43,12 @@ int sr_version(void);
 /* internal GPU tile (pixels).  Results do not depend on it. */
 int sr_tile_size(uint32_t *width, uint32_t *height);
 
+/* ---- shader registry --------------------------------------------------------------------
+ * Closures cannot cross a C ABI: the reference's vertex / geometry / fragment closures and Blend impls are a registered set
+ * of device functions.  Enumeration: call with index = 0, 1, ... until SR_ERR_INVALID_ARGUMENT; `info->id` is the value
+ * to pass to sr_vertex_run / sr_geometry_run / sr_fragment_run / sr_fragment_set_blend.  Needs no device. */
+int sr_registry_entry(uint32_t kind /* sr_registry_kind */, uint32_t index, sr_shader_info *info);
+
 /* ---- context: owns the device, stream and scratch memory.  Replaces the thread pool
  *      Pipeline::new creates (src/pipeline/mod.rs:110-117). ---------------------------- */
 int sr_context_create(int device_ordinal, sr_context **out);

@@ -154,6 +154,18 @@ typedef struct sr_stage_times {
     float total_ms;
 } sr_stage_times;
 
+/* one entry of the shader registry (sr_registry_entry) */
+typedef struct sr_shader_info {
+    uint32_t id;
+    uint32_t vin_floats;   /* vertex shaders: floats per input vertex (0 = any: pass-through) */
+    uint32_t nk;           /* vertex shaders: interpolated floats produced; fragment shaders: interpolated floats read */
+    uint32_t discards;     /* fragment shaders: may return Fragment::Discard (such draws take the ordered path) */
+    uint32_t needs_texture;
+    char name[40];
+    char reference[72];    /* the closure of the reference this device function mirrors (file:line) */
+} sr_shader_info;
+enum sr_registry_kind { SR_REGISTRY_VERTEX = 0, SR_REGISTRY_GEOMETRY = 1, SR_REGISTRY_FRAGMENT = 2, SR_REGISTRY_BLEND = 3 };
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ SYMBOLS = {
     "sr_version": (c_int, []),
     "sr_tile_size": (c_int, [u32p, u32p]),
     "sr_context_create": (c_int, [c_int, pp]),
+    "sr_registry_entry": (c_int, [c_u32, c_u32, c_void_p]),
     "sr_context_destroy": (c_int, [c_void_p]),
     "sr_context_synchronize": (c_int, [c_void_p]),
     "sr_context_stream": (c_void_p, [c_void_p]),

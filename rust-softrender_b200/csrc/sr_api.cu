@@ -756,6 +756,52 @@ int sr_tile_size(uint32_t *w, uint32_t *h) {
     return SR_OK;
 }
 
+// ---- shader registry -------------------------------------------------------------------------------------
+int sr_registry_entry(uint32_t kind, uint32_t index, sr_shader_info *info) {
+    if (!info) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    struct Row { uint32_t id, vin, nk, discards, tex; const char *name, *ref; };
+    static const Row vs[] = {
+        {SR_VS_PASSTHROUGH, 0, 0, 0, 0, "passthrough", "test shader: Vin = {x,y,z,w,k...} copied"},
+        {SR_VS_SUZANNE, SrVsInfo<SR_VS_SUZANNE>::VIN, SrVsInfo<SR_VS_SUZANNE>::NK, 0, 0, "suzanne", "examples/suzanne.rs:123-141"},
+        {SR_VS_FULL_EXAMPLE, SrVsInfo<SR_VS_FULL_EXAMPLE>::VIN, SrVsInfo<SR_VS_FULL_EXAMPLE>::NK, 0, 0, "full_example", "full_example/src/shaders.rs:8-31"},
+    };
+    static const Row gs[] = {
+        {SR_GS_CLIP, 0, 0, 0, 0, "clip_primitives", "src/pipeline/stages/geometry.rs:261-336"},
+        {SR_GS_FACE_NORMALS, 0, 8, 0, 0, "face_normals", "full_example/src/shaders.rs:63-89"},
+        {SR_GS_VERTEX_NORMALS, 0, 8, 0, 0, "vertex_normals", "full_example/src/shaders.rs:35-61"},
+        {SR_GS_CLIP_SH, 0, 0, 0, 0, "clip_sutherland_hodgman", "opt-in correct clipper, planes of src/geometry/clip.rs:33-63"},
+    };
+    static const Row fsr[] = {
+        {SR_FS_FLAT, 0, SrFsInfo<SR_FS_FLAT>::NK, 0, 0, "flat", "test shader: colour = K[0..4)"},
+        {SR_FS_SUZANNE, 0, SrFsInfo<SR_FS_SUZANNE>::NK, 0, 0, "suzanne_blinn_phong", "examples/suzanne.rs:147-183"},
+        {SR_FS_FULL_EXAMPLE, 0, SrFsInfo<SR_FS_FULL_EXAMPLE>::NK, 0, 0, "full_example_4light", "full_example/src/shaders.rs:108-162"},
+        {SR_FS_FULL_EXAMPLE_TEXTURED, 0, SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED>::NK, 0, 1, "full_example_4light_textured",
+         "full_example/src/shaders.rs:108-162 + texture.rs:47-84"},
+        {SR_FS_GREEN, 0, SrFsInfo<SR_FS_GREEN>::NK, 0, 0, "green", "full_example/src/shaders.rs:102"},
+        {SR_FS_DISCARD_CHECKER, 0, SrFsInfo<SR_FS_DISCARD_CHECKER>::NK, 1, 0, "discard_checker", "test shader: Fragment::Discard (fragment.rs:61-66)"},
+    };
+    static const Row bl[] = {
+        {SR_BLEND_REPLACE, 0, 0, 0, 0, "replace", "Blend for (): src/color/blend.rs:28-31"},
+        {SR_BLEND_ALPHA_OVER, 0, 0, 0, 0, "alpha_over", "full_example/src/color.rs:5-17"},
+    };
+    const Row *rows = nullptr;
+    uint32_t n = 0;
+    switch (kind) {
+        case SR_REGISTRY_VERTEX: rows = vs; n = sizeof(vs) / sizeof(vs[0]); break;
+        case SR_REGISTRY_GEOMETRY: rows = gs; n = sizeof(gs) / sizeof(gs[0]); break;
+        case SR_REGISTRY_FRAGMENT: rows = fsr; n = sizeof(fsr) / sizeof(fsr[0]); break;
+        case SR_REGISTRY_BLEND: rows = bl; n = sizeof(bl) / sizeof(bl[0]); break;
+        default: return sr_fail(SR_ERR_INVALID_ARGUMENT, "registry kind %u", kind);
+    }
+    if (index >= n) return sr_fail(SR_ERR_INVALID_ARGUMENT, "registry index %u of %u", index, n);
+    memset(info, 0, sizeof(*info));
+    info->id = rows[index].id; info->vin_floats = rows[index].vin; info->nk = rows[index].nk;
+    info->discards = rows[index].discards; info->needs_texture = rows[index].tex;
+    snprintf(info->name, sizeof(info->name), "%s", rows[index].name);
+    snprintf(info->reference, sizeof(info->reference), "%s", rows[index].ref);
+    return SR_OK;
+}
+
 // ---- context ---------------------------------------------------------------------------------------------
 int sr_context_create(int device, sr_context **out) {
     if (!out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "out is null");

@@ -104,6 +104,24 @@ class Context:
         return {k: getattr(t, k) for k, _ in t._fields_}
 
 
+class ShaderInfo(ctypes.Structure):  # sr_shader_info
+    _fields_ = [("id", ctypes.c_uint32), ("vin_floats", ctypes.c_uint32), ("nk", ctypes.c_uint32), ("discards", ctypes.c_uint32),
+                ("needs_texture", ctypes.c_uint32), ("name", ctypes.c_char * 40), ("reference", ctypes.c_char * 72)]
+
+
+def registry(kind: int):
+    """The registered device functions of one kind (0 vertex, 1 geometry, 2 fragment, 3 blend) that stand in for the
+    reference's closures: list of dicts with id, name, expected layouts and the reference closure each one mirrors."""
+    out, i = [], 0
+    while True:
+        info = ShaderInfo()
+        if lib.sr_registry_entry(kind, i, ctypes.byref(info)) != 0:
+            return out
+        out.append({"id": info.id, "name": info.name.decode(), "vin_floats": info.vin_floats, "nk": info.nk,
+                    "discards": bool(info.discards), "needs_texture": bool(info.needs_texture), "reference": info.reference.decode()})
+        i += 1
+
+
 def write_png(path: str, rgba: np.ndarray):
     """Minimal RGBA8 PNG writer (filter type 0 on every row)."""
     import struct

@@ -94,3 +94,20 @@ def test_png_writer_round_trip(tmp_path):
     assert seen[0] == b"IHDR" and seen[-1] == b"IEND"
     rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(37, 1 + 53 * 4)
     assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(37, 53, 4), img)
+
+
+def test_shader_registry_enumerates_without_a_device():
+    """sr_registry_entry: the closures of the reference as a registered set -- ids match the header's enums, layouts match
+    the scene definitions (Vin / K sizes of SURVEY section 8), enumeration ends with an error status."""
+    _ensure_built()
+    import softrender_b200 as sr
+    from softrender_b200 import pipeline
+    vs, gs, fs, bl = (pipeline.registry(k) for k in range(4))
+    assert [e["id"] for e in vs] == [sr.VS_PASSTHROUGH, sr.VS_SUZANNE, sr.VS_FULL_EXAMPLE]
+    assert {e["name"]: (e["vin_floats"], e["nk"]) for e in vs}["suzanne"] == (6, 8)        # pos3+normal3 -> {position4, normal4}
+    assert {e["name"]: (e["vin_floats"], e["nk"]) for e in vs}["full_example"] == (8, 10)  # + uv2
+    assert [e["id"] for e in gs] == [sr.GS_CLIP, sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS, sr.GS_CLIP_SH]
+    assert [e["id"] for e in fs] == [sr.FS_FLAT, sr.FS_SUZANNE, sr.FS_FULL_EXAMPLE, sr.FS_FULL_EXAMPLE_TEXTURED, sr.FS_GREEN, sr.FS_DISCARD_CHECKER]
+    assert [e["name"] for e in fs if e["discards"]] == ["discard_checker"] and [e["name"] for e in fs if e["needs_texture"]] == ["full_example_4light_textured"]
+    assert [e["name"] for e in bl] == ["replace", "alpha_over"] and pipeline.registry(9) == []
+    assert all(e["reference"] for e in vs + gs + fs + bl)
