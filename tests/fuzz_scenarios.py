@@ -116,7 +116,10 @@ def run_pipeline_scenario(P, ctx, ob, scenes, seed: int) -> str:
     draws = int(rng.integers(1, 3))
     what = (f"pipeline seed {seed}: {w}x{h} mesh kind {kind} ({mesh.ntris} tris) dist {dist} clip {clip} fs {fs} blend {blend} cull {cull} "
             f"world {world} draws {draws}")
-    tex = scenes.checker_texture(64, 8) if textured else None
+    tex = None
+    if textured:  # any size, including 1x1 and non-square: the bilinear taps at the last row / column are clamped
+        tex = (scenes.checker_texture(64, 8) if rng.random() < 0.3 else
+               rng.integers(0, 256, (int(rng.integers(1, 70)), int(rng.integers(1, 70)), 4), dtype=np.uint8))
     ofb = ob.OracleFramebuffer(w, h)
     ofb.clear(H.CLEAR)
     for _ in range(draws):
