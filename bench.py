@@ -356,6 +356,10 @@ def run_ours(args):
     # ---- N>1: sort-first tile sharding of ONE frame, peer-store composite into rank 0's framebuffer over NVLink ----
     sharded = None
     if world > 1:
+        single_gpu_frame = None
+        if rank == 0:  # the unsharded frame, to check the composited one against (bit for bit)
+            frame()
+            single_gpu_frame = fb.download()
         handle = [fb.ipc_export() if rank == 0 else None]
         dist.broadcast_object_list(handle, src=0)
         ctx.set_tile_shard(rank, world)
@@ -374,7 +378,11 @@ def run_ours(args):
         for _ in range(n_sh):
             sharded_frame()
         sh_ms = max_over_ranks((time.perf_counter() - t0) / n_sh * 1e3)
-        sharded = {"ms_per_frame": sh_ms, "Mtris_per_s": ntris / (sh_ms * 1e-3) / 1e6, "frames_per_s": 1e3 / sh_ms,
+        same = None
+        if rank == 0:
+            same = bool(np.array_equal(fb.download().view(np.uint32), single_gpu_frame.view(np.uint32)))
+            single_gpu_frame = None
+        sharded = {"ms_per_frame": sh_ms, "identical_to_single_gpu_frame": same, "Mtris_per_s": ntris / (sh_ms * 1e-3) / 1e6, "frames_per_s": 1e3 / sh_ms,
                    "timing": "host clock around draw + stream sync + barrier, max over ranks",
                    "composite": "tile rasteriser stores finished tiles into rank 0's framebuffer (CUDA IPC peer pointer, NVLink)"}
         ctx.set_tile_shard(0, 1)
