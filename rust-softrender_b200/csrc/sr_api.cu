@@ -972,8 +972,8 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     return SR_OK;
 }
 int sr_framebuffer_destroy(sr_framebuffer *fb) {
-    settle(fb->ctx);
     if (!fb) return SR_OK;
+    settle(fb->ctx);
     if (fb->is_peer && fb->aos) cudaIpcCloseMemHandle(fb->aos);
     delete fb;
     return SR_OK;

@@ -111,3 +111,16 @@ def test_shader_registry_enumerates_without_a_device():
     assert [e["name"] for e in fs if e["discards"]] == ["discard_checker"] and [e["name"] for e in fs if e["needs_texture"]] == ["full_example_4light_textured"]
     assert [e["name"] for e in bl] == ["replace", "alpha_over"] and pipeline.registry(9) == []
     assert all(e["reference"] for e in vs + gs + fs + bl)
+
+
+def test_destroy_and_query_entries_accept_null():
+    """Every *_destroy accepts a null handle (free(NULL) convention) and the null-argument paths of a few entries return an
+    error status instead of dereferencing -- checked without a device."""
+    _ensure_built()
+    from softrender_b200._abi import lib
+    for name in ("sr_context_destroy", "sr_framebuffer_destroy", "sr_mesh_destroy", "sr_texture_destroy", "sr_pipeline_destroy",
+                 "sr_draw_destroy"):
+        assert getattr(lib, name)(None) == 0, name
+    assert lib.sr_context_synchronize(None) != 0
+    assert lib.sr_registry_entry(0, 0, None) != 0
+    assert lib.sr_last_error()
