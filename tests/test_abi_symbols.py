@@ -124,3 +124,14 @@ def test_destroy_and_query_entries_accept_null():
     assert lib.sr_context_synchronize(None) != 0
     assert lib.sr_registry_entry(0, 0, None) != 0
     assert lib.sr_last_error()
+
+
+def test_every_entry_point_survives_null_arguments():
+    """Calling each exported function with null handles / pointers and zero scalars returns (an error status for the ones that
+    need an object) instead of dereferencing: the boundary never aborts (header conventions)."""
+    _ensure_built()
+    import ctypes
+    from softrender_b200 import _abi
+    for name, (_res, args) in sorted(_abi.SYMBOLS.items()):
+        vals = [None if (a is ctypes.c_void_p or (isinstance(a, type) and issubclass(a, ctypes._Pointer))) else 0 for a in args]
+        getattr(_abi.lib, name)(*vals)  # must return
