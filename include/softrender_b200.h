@@ -155,6 +155,16 @@ int sr_pipeline_set_framebuffer(sr_pipeline *, sr_framebuffer *);
 /* PipelineObject::stencil_config_mut with GenericStencilConfig{op,test} (src/stencil.rs:177-199) */
 int sr_pipeline_set_stencil_config(sr_pipeline *, uint32_t test, uint32_t op);
 int sr_pipeline_bind_texture(sr_pipeline *, sr_texture *);
+/* Render-to-texture: the colour attachment of `src` becomes the pipeline's texture IN PLACE -- the zero-cost
+ * TextureBufferRef of src/framebuffer/texturebuffer.rs:12-58 ("re-used as textures without copying", :63-66).
+ * Texels are the f32 RGBA colours as rendered (no /255, no gamma decode: a render target holds linear colour).
+ * NULL unbinds; binding replaces an image texture bound with sr_pipeline_bind_texture and vice versa.  A draw that
+ * renders into `src` itself, or whose pipeline lives in another context than `src`, fails with SR_ERR_INVALID_STATE;
+ * a recorded clear of `src` is materialised before the sampling draw. */
+int sr_pipeline_bind_framebuffer_texture(sr_pipeline *, sr_framebuffer *src);
+/* Filter and Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45) for every sampling shader of the pipeline.
+ * border_rgba: 4 floats, read only for SR_EDGE_BORDER (NULL = transparent black).  Default: BILINEAR, CLAMP. */
+int sr_pipeline_set_sampler(sr_pipeline *, uint32_t filter, uint32_t edge, const float *border_rgba);
 
 /* ---- draw: the VertexShader -> GeometryShader -> FragmentShader chain ---------------------- */
 /* Pipeline::render_mesh (mod.rs:146-157); errors if nindices % num_vertices(primitive) != 0 (assert mod.rs:148).

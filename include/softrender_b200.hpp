@@ -162,6 +162,10 @@ public:
     RenderBuffer &framebuffer() { return *fb_; }
     void set_uniforms(const sr_uniforms &u) { check(sr_pipeline_set_uniforms(h_, &u)); }  // *uniforms_mut() = u
     void set_stencil_config(sr_stencil_test t, sr_stencil_op o) { check(sr_pipeline_set_stencil_config(h_, t, o)); }
+    /* render-to-texture: the colour of `src` sampled in place (TextureBufferRef, src/framebuffer/texturebuffer.rs:12-58) */
+    void bind_framebuffer_texture(RenderBuffer *src) { check(sr_pipeline_bind_framebuffer_texture(h_, src ? src->handle() : nullptr)); }
+    /* Filter / Edge of texture(t, coord, filter, edge), src/texture.rs:14-45 */
+    void set_sampler(sr_texture_filter f, sr_texture_edge e, const float *border_rgba = nullptr) { check(sr_pipeline_set_sampler(h_, f, e, border_rgba)); }
     template <class T>
     VertexShader render_mesh(T, const Mesh &mesh, std::optional<uint32_t> stencil = std::nullopt) {
         sr_draw *d;

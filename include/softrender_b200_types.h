@@ -98,7 +98,22 @@ enum sr_fragment_shader {
     SR_FS_FULL_EXAMPLE = 2,  /* full_example/src/shaders.rs:108-162 (4-light Blinn-Phong + ACES + gamma) */
     SR_FS_FULL_EXAMPLE_TEXTURED = 3, /* same, material colour * bilinear/clamp texture sample (full_example/src/texture.rs:47-84) */
     SR_FS_GREEN = 4,         /* full_example/src/shaders.rs:102 */
-    SR_FS_DISCARD_CHECKER = 5 /* test shader: Fragment::Discard on odd (floor(x)+floor(y)), else colour = K[0..4) (fragment.rs:61-66) */
+    SR_FS_DISCARD_CHECKER = 5, /* test shader: Fragment::Discard on odd (floor(x)+floor(y)), else colour = K[0..4) (fragment.rs:61-66) */
+    SR_FS_TEXTURE_UNLIT = 6  /* second-pass shader of a render-to-texture chain: colour = texture(bound texture, uv = K[0..2), filter, edge)
+                              * -- the call of src/texture.rs:14-18 and nothing else */
+};
+
+/* texture sampling state (src/texture.rs:21-45); the arithmetic is the sampler the reference ships,
+ * full_example/src/texture.rs:25-84 (TextureRead::sample itself is unimplemented!() there, src/texture.rs:49-52) */
+enum sr_texture_filter {
+    SR_FILTER_NEAREST = 0,   /* Filter::Nearest: texel (round(u (w-1)), round(v (h-1))), full_example/src/texture.rs:52-57 */
+    SR_FILTER_BILINEAR = 1   /* Filter::Bilinear, full_example/src/texture.rs:58-82 (what the shipped scene uses; the pipeline default) */
+};
+enum sr_texture_edge {
+    SR_EDGE_CLAMP = 0,       /* Edge::Clamp  = GL_CLAMP_TO_EDGE: (u.min(1).max(0), v.min(1).max(0)), full_example/src/texture.rs:28 */
+    SR_EDGE_WRAP = 1,        /* Edge::Wrap   = GL_REPEAT: (u.fract(), v.fract()), full_example/src/texture.rs:29 (fract of a negative is negative) */
+    SR_EDGE_BORDER = 2       /* Edge::Border(C) = GL_CLAMP_TO_BORDER (src/texture.rs:43-44): a coordinate outside [0,1]^2 (or NaN)
+                              * returns the border colour unchanged, inside it samples as Clamp */
 };
 
 enum sr_geometry_shader {

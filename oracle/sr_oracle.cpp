@@ -442,31 +442,57 @@ inline float fresnel_schlick(float cos_theta, float ior) {
     return f0 + (1.0f - f0) * powi(1.0f - cos_theta, 5);
 }
 
-// full_example/src/texture.rs:47-84, Bilinear + Clamp.  Deviation: the reference reads
-// texel x+1 / y+1 unclamped (the image crate would panic at u==1 or v==1); here the
-// neighbour index is clamped to the last texel.
-void texture_sample_bilinear_clamp(const so_texture *t, float u, float v, float *out) {
-    u = fmaxf(fminf(u, 1.0f), 0.0f);
-    v = fmaxf(fminf(v, 1.0f), 0.0f);
-    float uu = (u * (float)(t->width - 1)) + 0.5f;
-    float vv = (v * (float)(t->height - 1)) + 0.5f;
-    uint32_t x = (uint32_t)floorf(uu);
-    uint32_t y = (uint32_t)floorf(vv);
-    float u_ratio = uu - (float)x;
-    float v_ratio = vv - (float)y;
-    float u_opp = 1.0f - u_ratio;
-    float v_opp = 1.0f - v_ratio;
-    uint32_t x0 = x < t->width ? x : t->width - 1, y0 = y < t->height ? y : t->height - 1;
-    uint32_t x1 = x + 1 < t->width ? x + 1 : t->width - 1;
-    uint32_t y1 = y + 1 < t->height ? y + 1 : t->height - 1;
-    auto texel = [&](uint32_t px, uint32_t py, int ch) {
-        return (float)t->rgba[((size_t)py * t->width + px) * 4 + ch] / 255.0f;
-    };
-    for (int ch = 0; ch < 4; ++ch) {
-        float xy = texel(x0, y0, ch), x1y = texel(x1, y0, ch), xy1 = texel(x0, y1, ch), x1y1 = texel(x1, y1, ch);
-        float val = (xy * u_opp + x1y * u_ratio) * v_opp + (xy1 * u_opp + x1y1 * u_ratio) * v_ratio;
-        out[ch] = ch < 3 ? powf(val, 2.2f) : val;  // decode_gamma leaves alpha (color.rs:48-55)
+// Rust's `f as u32` (saturating; NaN -> 0), which the sampler of full_example/src/texture.rs:52-62 relies on
+inline uint32_t as_u32(float f) {
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)f;
+}
+
+// texture(t, coord, filter, edge): src/texture.rs:14-45 names the call, full_example/src/texture.rs:25-84 is the only
+// sampler the reference ships (TextureRead::sample is unimplemented!(), src/texture.rs:49-52), restated here for every
+// Filter / Edge and both texel formats.  Definitions where the reference has none: Edge::Border(C) returns C for a
+// coordinate outside [0,1]^2 (or NaN) and samples as Clamp inside (GL_CLAMP_TO_BORDER, src/texture.rs:43-44); a
+// framebuffer colour plane (TextureBufferRef, texturebuffer.rs:12-58) yields its f32 colour as stored -- no /255 and no
+// decode_gamma, which full_example applies to 8-bit sRGB images only.  Deviation: the reference reads texel x+1 / y+1
+// unclamped (the image crate would panic at u==1 or v==1); texel indices it would read out of bounds are clamped to
+// the last row / column.
+void texture_sample(const so_texture *t, float u, float v, float *out) {
+    if (t->edge == SR_EDGE_WRAP) {
+        u = u - truncf(u);  // f32::fract
+        v = v - truncf(v);
+    } else {
+        if (t->edge == SR_EDGE_BORDER && !(u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f)) {
+            for (int ch = 0; ch < 4; ++ch) out[ch] = t->border[ch];
+            return;
+        }
+        u = fmaxf(fminf(u, 1.0f), 0.0f);
+        v = fmaxf(fminf(v, 1.0f), 0.0f);
     }
+    const uint32_t lastx = t->width - 1, lasty = t->height - 1;
+    const bool image = t->rgba != nullptr;
+    auto texel = [&](uint32_t px, uint32_t py, int ch) {
+        px = px < lastx ? px : lastx;
+        py = py < lasty ? py : lasty;
+        const size_t i = (size_t)py * t->width + px;
+        return image ? (float)t->rgba[i * 4 + ch] / 255.0f : t->texels_f32[i * t->stride + ch];
+    };
+    float val[4];
+    if (t->filter == SR_FILTER_NEAREST) {
+        const uint32_t x = as_u32(roundf(u * (float)lastx)), y = as_u32(roundf(v * (float)lasty));
+        for (int ch = 0; ch < 4; ++ch) val[ch] = texel(x, y, ch);
+    } else {
+        const float uu = (u * (float)lastx) + 0.5f, vv = (v * (float)lasty) + 0.5f;
+        const uint32_t x = as_u32(floorf(uu)), y = as_u32(floorf(vv));
+        const float u_ratio = uu - (float)x, v_ratio = vv - (float)y;
+        const float u_opp = 1.0f - u_ratio, v_opp = 1.0f - v_ratio;
+        const uint32_t x1 = x == 0xFFFFFFFFu ? x : x + 1, y1 = y == 0xFFFFFFFFu ? y : y + 1;
+        for (int ch = 0; ch < 4; ++ch) {
+            float xy = texel(x, y, ch), x1y = texel(x1, y, ch), xy1 = texel(x, y1, ch), x1y1 = texel(x1, y1, ch);
+            val[ch] = (xy * u_opp + x1y * u_ratio) * v_opp + (xy1 * u_opp + x1y1 * u_ratio) * v_ratio;
+        }
+    }
+    for (int ch = 0; ch < 4; ++ch) out[ch] = (image && ch < 3) ? powf(val[ch], 2.2f) : val[ch];
 }
 
 bool fragment_shader(int fs, const float *sv, const sr_uniforms *u, const so_texture *tex, float *out) {
@@ -477,6 +503,10 @@ bool fragment_shader(int fs, const float *sv, const sr_uniforms *u, const so_tex
             return true;
         case SR_FS_GREEN:
             out[0] = 0.0f; out[1] = 1.0f; out[2] = 0.0f; out[3] = 1.0f;
+            return true;
+        case SR_FS_TEXTURE_UNLIT:
+            if (tex && (tex->rgba || tex->texels_f32)) texture_sample(tex, K[0], K[1], out);
+            else out[0] = out[1] = out[2] = out[3] = 0.0f;
             return true;
         case SR_FS_DISCARD_CHECKER: {
             int xi = (int)floorf(sv[0]), yi = (int)floorf(sv[1]);
@@ -515,9 +545,9 @@ bool fragment_shader(int fs, const float *sv, const sr_uniforms *u, const so_tex
             normalize4(d, view_dir);
             const float m = powf(0.25f, 2.2f);  // decode_gamma(material colour)
             float material[3] = {m, m, m};
-            if (fs == SR_FS_FULL_EXAMPLE_TEXTURED && tex && tex->rgba) {
+            if (fs == SR_FS_FULL_EXAMPLE_TEXTURED && tex && (tex->rgba || tex->texels_f32)) {
                 float t[4];
-                texture_sample_bilinear_clamp(tex, K[8], K[9], t);
+                texture_sample(tex, K[8], K[9], t);
                 for (int i = 0; i < 3; ++i) material[i] = material[i] * t[i];
             }
             const float albedo = 0.7f;
@@ -926,7 +956,8 @@ int so_draw_fragment_run(so_draw *d, so_framebuffer *fb, const so_raster_state *
                          const so_texture *tex, int nthreads) {
     if (!d || !fb || !st || !u) return SR_ERR_INVALID_ARGUMENT;
     if (d->space != 1) return SR_ERR_INVALID_STATE;
-    if (fs < SR_FS_FLAT || fs > SR_FS_DISCARD_CHECKER) return SR_ERR_INVALID_ARGUMENT;
+    if (fs < SR_FS_FLAT || fs > SR_FS_TEXTURE_UNLIT) return SR_ERR_INVALID_ARGUMENT;
+    if (fs == SR_FS_TEXTURE_UNLIT && d->nk < 2) return SR_ERR_INVALID_ARGUMENT;
     const uint32_t S = 4 + d->nk;
     if ((fs == SR_FS_FLAT || fs == SR_FS_DISCARD_CHECKER) && d->nk < 4) return SR_ERR_INVALID_ARGUMENT;
     if ((fs == SR_FS_SUZANNE || fs == SR_FS_FULL_EXAMPLE) && d->nk < 8) return SR_ERR_INVALID_ARGUMENT;
@@ -977,6 +1008,8 @@ int so_draw_fragment_run(so_draw *d, so_framebuffer *fb, const so_raster_state *
     });
     return SR_OK;
 }
+
+void so_texture_sample(const so_texture *t, float u, float v, float out[4]) { texture_sample(t, u, v, out); }
 
 uint64_t so_draw_count(const so_draw *d, int which) {
     if (!d) return 0;

@@ -41,7 +41,13 @@ typedef struct so_framebuffer {
 
 typedef struct so_texture {
     uint32_t width, height;
-    const uint8_t *rgba; /* width*height*4 */
+    const uint8_t *rgba; /* width*height*4 image texels (full_example/src/texture.rs:6), or NULL */
+    /* render-to-texture source (src/framebuffer/texturebuffer.rs:12-58): f32 RGBA every `stride` floats, used when rgba is NULL */
+    const float *texels_f32;
+    uint32_t stride;
+    uint32_t filter;     /* sr_texture_filter (src/texture.rs:21-25) */
+    uint32_t edge;       /* sr_texture_edge (src/texture.rs:33-41) */
+    float border[4];     /* Edge::Border(C) */
 } so_texture;
 
 /* FragmentShader builder state (src/pipeline/stages/fragment.rs:45-56) +
@@ -80,6 +86,9 @@ int so_draw_finish(so_draw *, const sr_viewport *, int nthreads);
 /* FragmentShader::run (fragment.rs:168) */
 int so_draw_fragment_run(so_draw *, so_framebuffer *, const so_raster_state *, int fs,
                          const sr_uniforms *, const so_texture *, int nthreads);
+
+/* texture(t, coord, filter, edge) (src/texture.rs:14-18) with the arithmetic of full_example/src/texture.rs:25-84 */
+void so_texture_sample(const so_texture *, float u, float v, float out[4]);
 
 /* introspection: which = 0 indexed vertices, 1 points, 2 lines, 3 tris */
 uint64_t so_draw_count(const so_draw *, int which);

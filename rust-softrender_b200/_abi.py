@@ -75,6 +75,8 @@ SYMBOLS = {
     "sr_pipeline_set_framebuffer": (c_int, [c_void_p, c_void_p]),
     "sr_pipeline_set_stencil_config": (c_int, [c_void_p, c_u32, c_u32]),
     "sr_pipeline_bind_texture": (c_int, [c_void_p, c_void_p]),
+    "sr_pipeline_bind_framebuffer_texture": (c_int, [c_void_p, c_void_p]),
+    "sr_pipeline_set_sampler": (c_int, [c_void_p, c_u32, c_u32, ctypes.POINTER(ctypes.c_float)]),
     "sr_render_mesh": (c_int, [c_void_p, c_void_p, c_u32, c_int, c_u32, pp]),
     "sr_vertex_run": (c_int, [c_void_p, c_u32]),
     "sr_vertex_run_to_fragment": (c_int, [c_void_p, ctypes.POINTER(Viewport), c_u32]),

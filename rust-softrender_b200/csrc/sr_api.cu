@@ -182,6 +182,9 @@ struct sr_pipeline {
     sr_uniforms uniforms;
     uint32_t stencil_test = SR_STENCIL_ALWAYS, stencil_op = SR_STENCIL_KEEP;
     sr_texture *texture = nullptr;
+    sr_framebuffer *fb_texture = nullptr;  // render-to-texture source, sampled in place (texturebuffer.rs:12-58)
+    uint32_t tex_filter = SR_FILTER_BILINEAR, tex_edge = SR_EDGE_CLAMP;  // what the shipped scene samples with
+    float tex_border[4] = {0, 0, 0, 0};
 };
 
 struct VertexStream {  // one flat Vec of vertices in HBM: position array + attribute records (np float4 per vertex)
@@ -434,6 +437,7 @@ static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, co
         case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_tiles<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
         case SR_FS_GREEN: return launch_tiles<SR_FS_GREEN>(c, ntiles_owned, p);
         case SR_FS_DISCARD_CHECKER: return launch_tiles<SR_FS_DISCARD_CHECKER>(c, ntiles_owned, p);
+        case SR_FS_TEXTURE_UNLIT: return launch_tiles<SR_FS_TEXTURE_UNLIT>(c, ntiles_owned, p);
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown fragment shader %u", fs);
 }
@@ -456,6 +460,7 @@ static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, c
         SR_OPQ_CASE(SR_FS_FULL_EXAMPLE);
         SR_OPQ_CASE(SR_FS_FULL_EXAMPLE_TEXTURED);
         SR_OPQ_CASE(SR_FS_GREEN);
+        SR_OPQ_CASE(SR_FS_TEXTURE_UNLIT);
     }
 #undef SR_OPQ_CASE
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
@@ -739,6 +744,7 @@ static int fs_nk(uint32_t fs) {
         case SR_FS_FULL_EXAMPLE_TEXTURED: return SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED>::NK;
         case SR_FS_GREEN: return SrFsInfo<SR_FS_GREEN>::NK;
         case SR_FS_DISCARD_CHECKER: return SrFsInfo<SR_FS_DISCARD_CHECKER>::NK;
+        case SR_FS_TEXTURE_UNLIT: return SrFsInfo<SR_FS_TEXTURE_UNLIT>::NK;
     }
     return -1;
 }
@@ -779,6 +785,7 @@ int sr_registry_entry(uint32_t kind, uint32_t index, sr_shader_info *info) {
          "full_example/src/shaders.rs:108-162 + texture.rs:47-84"},
         {SR_FS_GREEN, 0, SrFsInfo<SR_FS_GREEN>::NK, 0, 0, "green", "full_example/src/shaders.rs:102"},
         {SR_FS_DISCARD_CHECKER, 0, SrFsInfo<SR_FS_DISCARD_CHECKER>::NK, 1, 0, "discard_checker", "test shader: Fragment::Discard (fragment.rs:61-66)"},
+        {SR_FS_TEXTURE_UNLIT, 0, SrFsInfo<SR_FS_TEXTURE_UNLIT>::NK, 0, 1, "texture_unlit", "texture(t, uv, filter, edge): src/texture.rs:14-18 + full_example/src/texture.rs:25-84"},
     };
     static const Row bl[] = {
         {SR_BLEND_REPLACE, 0, 0, 0, 0, "replace", "Blend for (): src/color/blend.rs:28-31"},
@@ -1244,6 +1251,21 @@ int sr_pipeline_set_stencil_config(sr_pipeline *p, uint32_t test, uint32_t op) {
 int sr_pipeline_bind_texture(sr_pipeline *p, sr_texture *t) {
     if (!p) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     p->texture = t;
+    p->fb_texture = nullptr;
+    return SR_OK;
+}
+int sr_pipeline_bind_framebuffer_texture(sr_pipeline *p, sr_framebuffer *src) {
+    if (!p) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (src && (src->width == 0 || src->height == 0)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "texture source framebuffer is empty");
+    p->fb_texture = src;
+    p->texture = nullptr;
+    return SR_OK;
+}
+int sr_pipeline_set_sampler(sr_pipeline *p, uint32_t filter, uint32_t edge, const float *border_rgba) {
+    if (!p || filter > SR_FILTER_BILINEAR || edge > SR_EDGE_BORDER) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad sampler state");
+    p->tex_filter = filter;
+    p->tex_edge = edge;
+    for (int i = 0; i < 4; ++i) p->tex_border[i] = border_rgba ? border_rgba[i] : 0.0f;
     return SR_OK;
 }
 
@@ -1529,7 +1551,14 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(settle(c));
     if (fb->width < 2 || fb->height < 2) return SR_OK;  // fragment.rs:188-216: a 1-pixel-wide frame has no tiles, nothing is drawn
-    if (fs == SR_FS_FULL_EXAMPLE_TEXTURED && !p->texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
+    const bool samples = fs == SR_FS_FULL_EXAMPLE_TEXTURED || fs == SR_FS_TEXTURE_UNLIT;
+    if (samples && !p->texture && !p->fb_texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
+    if (samples && p->fb_texture) {
+        sr_framebuffer *src = p->fb_texture;
+        if (src == fb || src->aos == fb->aos) return sr_fail(SR_ERR_INVALID_STATE, "a framebuffer cannot be sampled by a draw that renders into it");
+        if (src->ctx != c) return sr_fail(SR_ERR_INVALID_STATE, "texture source framebuffer belongs to another context");
+        SR_TRY(materialize_clear(src));  // a recorded clear becomes pixels before they are sampled
+    }
 
     SrTileParams tp;
     memset(&tp, 0, sizeof(tp));
@@ -1547,10 +1576,19 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     tp.stencil_test = p->stencil_test; tp.stencil_op = p->stencil_op; tp.stencil_value = d->stencil_value;
     tp.aa_lines = d->aa_lines;
     tp.fs.u = p->uniforms;
-    if (p->texture) {
+    tp.fs.tex_filter = p->tex_filter; tp.fs.tex_edge = p->tex_edge;
+    for (int i = 0; i < 4; ++i) tp.fs.tex_border[i] = p->tex_border[i];
+    if (p->fb_texture && samples) {
+        tp.fs.tex = reinterpret_cast<const uint8_t *>(p->fb_texture->aos);
+        tp.fs.tex_w = p->fb_texture->width;
+        tp.fs.tex_h = p->fb_texture->height;
+        tp.fs.tex_kind = SR_TEX_F32;
+        tp.fs.tex_stride = 5;  // AoS pixel: RGBA f32 + depth f32
+    } else if (p->texture) {
         tp.fs.tex = p->texture->rgba->as<uint8_t>();
         tp.fs.tex_w = p->texture->width;
         tp.fs.tex_h = p->texture->height;
+        tp.fs.tex_kind = SR_TEX_RGBA8;
     }
 
     if (fb->winner_enabled && fb->winner_buf)  // winner plane reports the primitives of THIS draw
@@ -1582,6 +1620,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         std::vector<Buf> keep = {d->indices, d->indexed.pos, d->indexed.attr, d->gen[0].pos, d->gen[0].attr, d->gen[1].pos, d->gen[1].attr,
                                  d->gen[2].pos, d->gen[2].attr, d->tri_seq};
         if (p->texture) keep.push_back(p->texture->rgba);
+        if (p->fb_texture && samples && p->fb_texture->aos_buf) keep.push_back(p->fb_texture->aos_buf);
         SrTileParams ordered = tp;
         if (opaque_ok) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,

@@ -16,10 +16,15 @@ struct SrVsConst {
     int normalize;  // run_to_fragment: apply ClipVertex::normalize after the shader
 };
 
+#define SR_TEX_RGBA8 0u  // image texture: u8 texels / 255, then decode_gamma (full_example/src/texture.rs:33-40,84)
+#define SR_TEX_F32 1u    // a framebuffer's colour bound in place (texturebuffer.rs:12-58): f32 RGBA every tex_stride floats, linear
 struct SrFsConst {
     sr_uniforms u;
-    const uint8_t *tex;  // RGBA8
+    const uint8_t *tex;  // RGBA8 texels, or the f32 AoS pixels of the source framebuffer
     uint32_t tex_w, tex_h;
+    uint32_t tex_kind, tex_stride;    // SR_TEX_*; floats per texel of an SR_TEX_F32 source
+    uint32_t tex_filter, tex_edge;    // sr_texture_filter, sr_texture_edge (src/texture.rs:21-45)
+    float tex_border[4];              // Edge::Border(C)
 };
 
 template <int VS> struct SrVsInfo;  // VIN = input floats (0 = runtime), NK = interpolated floats (0 = runtime)
@@ -69,6 +74,7 @@ template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE> { static constexpr int NK = 8; s
 template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int NK = 10; static constexpr bool DISCARDS = false, LIT = true; };
 template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false, LIT = false; };
 template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true, LIT = false; };
+template <> struct SrFsInfo<SR_FS_TEXTURE_UNLIT> { static constexpr int NK = 2; static constexpr bool DISCARDS = false, LIT = false; };
 
 // Fragment-shader arithmetic is NOT on the bit-exact path (colour parity is 1/255 per channel, and the reference's
 // powf is libm's): normalisation uses rsqrtf and powers use exp2(y*log2(x)) on the SFU unless SR_FS_EXACT is set.
@@ -125,6 +131,65 @@ __device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, fl
     }
 }
 
+// texture(t, coord, filter, edge) (src/texture.rs:14-18) for any Filter / Edge / texel format: the arithmetic of
+// full_example/src/texture.rs:25-84 with Rust's saturating `as u32` (negative and NaN -> 0; CUDA's float->uint conversion
+// saturates the same way) and every texel index clamped to the last row / column where the reference would index out
+// of bounds.  Not inlined: the shipped scene's Bilinear + Clamp + RGBA8 case keeps its own straight-line body above.
+__device__ __noinline__ float4 sr_texture_sample_general(const SrFsConst &c, float u, float v) {
+    if (c.tex_edge == SR_EDGE_WRAP) {
+        u = u - truncf(u);  // f32::fract
+        v = v - truncf(v);
+    } else {
+        if (c.tex_edge == SR_EDGE_BORDER && !(u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f)) {
+            return make_float4(c.tex_border[0], c.tex_border[1], c.tex_border[2], c.tex_border[3]);
+        }
+        u = fmaxf(fminf(u, 1.0f), 0.0f);
+        v = fmaxf(fminf(v, 1.0f), 0.0f);
+    }
+    const uint32_t lastx = c.tex_w - 1, lasty = c.tex_h - 1;
+    const bool f32 = c.tex_kind == SR_TEX_F32;
+    const float r255 = __frcp_rn(255.0f);
+    auto texel = [&](uint32_t x, uint32_t y, float *a) {
+        x = min(x, lastx); y = min(y, lasty);
+        const size_t i = (size_t)y * c.tex_w + x;
+        if (f32) {
+            const float *t = reinterpret_cast<const float *>(c.tex) + i * c.tex_stride;
+            a[0] = t[0]; a[1] = t[1]; a[2] = t[2]; a[3] = t[3];
+        } else {
+            const uchar4 t = __ldg((const uchar4 *)c.tex + i);
+            a[0] = sr_div_exact((float)t.x, 255.0f, r255); a[1] = sr_div_exact((float)t.y, 255.0f, r255);
+            a[2] = sr_div_exact((float)t.z, 255.0f, r255); a[3] = sr_div_exact((float)t.w, 255.0f, r255);
+        }
+    };
+    float val[4];
+    if (c.tex_filter == SR_FILTER_NEAREST) {
+        texel((uint32_t)roundf(u * (float)lastx), (uint32_t)roundf(v * (float)lasty), val);
+    } else {
+        const float uu = (u * (float)lastx) + 0.5f, vv = (v * (float)lasty) + 0.5f;
+        const uint32_t x = (uint32_t)floorf(uu), y = (uint32_t)floorf(vv);
+        const float u_ratio = uu - (float)x, v_ratio = vv - (float)y;
+        const float u_opp = 1.0f - u_ratio, v_opp = 1.0f - v_ratio;
+        const uint32_t x1 = x == 0xFFFFFFFFu ? x : x + 1, y1 = y == 0xFFFFFFFFu ? y : y + 1;
+        float a00[4], a10[4], a01[4], a11[4];
+        texel(x, y, a00); texel(x1, y, a10); texel(x, y1, a01); texel(x1, y1, a11);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+            val[ch] = (a00[ch] * u_opp + a10[ch] * u_ratio) * v_opp + (a01[ch] * u_opp + a11[ch] * u_ratio) * v_ratio;
+    }
+    if (!f32) {  // decode_gamma (full_example/src/color.rs:48-55): image textures only
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) val[ch] = sr_fs_pow(val[ch], 2.2f);
+    }
+    return make_float4(val[0], val[1], val[2], val[3]);
+}
+__device__ __forceinline__ void sr_texture_sample(const SrFsConst &c, float u, float v, float *out) {
+    if (c.tex_kind == SR_TEX_RGBA8 && c.tex_filter == SR_FILTER_BILINEAR && c.tex_edge == SR_EDGE_CLAMP) sr_texture_bilinear_clamp(c, u, v, out);
+    else {
+        const float4 t = sr_texture_sample_general(c, u, v);
+        out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+    }
+}
+
 // `sv` = interpolated ScreenVertex: position[4] then K.  Returns false for Fragment::Discard.
 template <int FS>
 __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const float *sv, float *out) {
@@ -135,6 +200,10 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
         return true;
     } else if (FS == SR_FS_GREEN) {  // full_example/src/shaders.rs:102
         out[0] = 0.0f; out[1] = 1.0f; out[2] = 0.0f; out[3] = 1.0f;
+        return true;
+    } else if (FS == SR_FS_TEXTURE_UNLIT) {  // texture(t, uv, filter, edge), src/texture.rs:14-18
+        if (c.tex != nullptr) sr_texture_sample(c, K[0], K[1], out);
+        else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 0.0f; }
         return true;
     } else if (FS == SR_FS_DISCARD_CHECKER) {
         const int xi = (int)floorf(sv[0]), yi = (int)floorf(sv[1]);
@@ -178,7 +247,7 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
         if (FS == SR_FS_FULL_EXAMPLE_TEXTURED) {
             if (c.tex != nullptr) {
                 float t[4];
-                sr_texture_bilinear_clamp(c, K[8], K[9], t);
+                sr_texture_sample(c, K[8], K[9], t);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) material[i] = material[i] * t[i];
             }

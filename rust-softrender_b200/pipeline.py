@@ -440,6 +440,16 @@ class Pipeline:
     def bind_texture(self, tex: Optional[Texture]):
         check(lib.sr_pipeline_bind_texture(self.h, tex.h if tex else None))
 
+    def bind_framebuffer_texture(self, src: Optional["RenderBuffer"]):
+        """Render-to-texture: `src`'s colour attachment becomes the texture in place, no copy
+        (TextureBufferRef, src/framebuffer/texturebuffer.rs:12-58)."""
+        check(lib.sr_pipeline_bind_framebuffer_texture(self.h, src.h if src else None))
+
+    def set_sampler(self, filter: int, edge: int, border=None):
+        """Filter / Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45); `border` = Edge::Border's colour."""
+        b = (ctypes.c_float * 4)(*[float(x) for x in border]) if border is not None else None
+        check(lib.sr_pipeline_set_sampler(self.h, filter, edge, b))
+
     def render_mesh(self, primitive: int, mesh: Mesh, stencil: Optional[int] = None) -> VertexShader:
         h = ctypes.c_void_p()
         check(lib.sr_render_mesh(self.h, mesh.h, primitive, 0 if stencil is None else 1, stencil or 0, ctypes.byref(h)))

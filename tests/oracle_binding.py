@@ -27,7 +27,29 @@ class SoFramebuffer(ctypes.Structure):
 
 
 class SoTexture(ctypes.Structure):
-    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("rgba", u8p)]
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("rgba", u8p), ("texels_f32", f32p),
+                ("stride", ctypes.c_uint32), ("filter", ctypes.c_uint32), ("edge", ctypes.c_uint32), ("border", ctypes.c_float * 4)]
+
+
+def make_texture(texture, sampler=None):
+    """so_texture of a (h, w, 4) array: uint8 = image texels, float32 = a framebuffer's colour sampled in place
+    (texturebuffer.rs:12-58).  sampler = (filter, edge, border) or None for the shipped scene's Bilinear + Clamp.
+    Returns (struct, array kept alive)."""
+    filt, edge, border = sampler if sampler is not None else (1, 0, None)
+    b = (ctypes.c_float * 4)(*([float(x) for x in border] if border is not None else [0.0] * 4))
+    if np.asarray(texture).dtype == np.float32:
+        t = np.ascontiguousarray(texture, np.float32)
+        return SoTexture(t.shape[1], t.shape[0], None, t.ctypes.data_as(f32p), 4, filt, edge, b), t
+    t = np.ascontiguousarray(texture, np.uint8)
+    return SoTexture(t.shape[1], t.shape[0], t.ctypes.data_as(u8p), None, 0, filt, edge, b), t
+
+
+def texture_sample(texture, u, v, sampler=None) -> np.ndarray:
+    """texture(t, (u, v), filter, edge) of the oracle for one coordinate."""
+    tex, _keep = make_texture(texture, sampler)
+    out = (ctypes.c_float * 4)()
+    lib().so_texture_sample(ctypes.byref(tex), ctypes.c_float(u), ctypes.c_float(v), out)
+    return np.array(out[:], np.float32)
 
 
 class SoRasterState(ctypes.Structure):
@@ -64,6 +86,8 @@ def lib():
         L.so_draw_finish.argtypes = [ctypes.c_void_p, ctypes.POINTER(Viewport), ctypes.c_int]
         L.so_draw_fragment_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(SoFramebuffer), ctypes.POINTER(SoRasterState),
                                            ctypes.c_int, ctypes.POINTER(Uniforms), ctypes.POINTER(SoTexture), ctypes.c_int]
+        L.so_texture_sample.restype = None
+        L.so_texture_sample.argtypes = [ctypes.POINTER(SoTexture), ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_float)]
         L.so_draw_count.restype = ctypes.c_uint64
         L.so_draw_count.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.so_draw_data.restype = f32p
@@ -175,15 +199,14 @@ class OracleDraw:
         self._ck(lib().so_draw_finish(self.h, ctypes.byref(viewport), nthreads))
         return self
 
-    def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1):
+    def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1, sampler=None):
         tw, th = self.tile if self.tile else (max(fb.width, 1), max(fb.height, 1))
         st = SoRasterState(self.cull, self.blend, 1 if self.aa else 0, tw, th, stencil_test, stencil_op)
         fb.winner[:] = 0  # winner plane = primitives of THIS draw
         s = fb.struct()
         tex = None
         if texture is not None:
-            t = np.ascontiguousarray(texture, np.uint8)
-            tex = SoTexture(t.shape[1], t.shape[0], t.ctypes.data_as(u8p))
+            tex, _keep = make_texture(texture, sampler)
         self._ck(lib().so_draw_fragment_run(self.h, ctypes.byref(s), ctypes.byref(st), fs, ctypes.byref(uniforms),
                                             ctypes.byref(tex) if tex is not None else None, nthreads))
         return self

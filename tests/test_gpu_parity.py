@@ -984,3 +984,162 @@ def test_error_behaviour(P, ctx):
     assert np.float32(depth).view(np.uint32) == sr.DEPTH_FAR_BITS and np.allclose(rgba, H.CLEAR)
     for x in (pipe, mesh, fb, fb0):
         x.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# render-to-texture: a framebuffer's colour sampled in place by a later pass
+# (TextureBufferRef, src/framebuffer/texturebuffer.rs:12-58) with every Filter / Edge of src/texture.rs:21-45
+# ------------------------------------------------------------------------------------------------------
+def _uv_triangles(rng, n, w, h, lo=-0.8, hi=1.9):
+    """n random screen-space triangles whose K is a texture coordinate reaching well outside [0, 1]."""
+    v = H.random_screen_triangles(rng, n, w, h, nk=2, max_size=0.6 * min(w, h))
+    v[:, 4:6] = rng.uniform(lo, hi, (3 * n, 2)).astype(np.float32)
+    return v
+
+
+@pytest.mark.parametrize("blend", [sr.BLEND_REPLACE, sr.BLEND_ALPHA_OVER])
+@pytest.mark.parametrize("edge", [sr.EDGE_CLAMP, sr.EDGE_WRAP, sr.EDGE_BORDER])
+@pytest.mark.parametrize("filt", [sr.FILTER_NEAREST, sr.FILTER_BILINEAR])
+def test_render_to_texture(P, ctx, filt, edge, blend):
+    """Pass 1 renders flat triangles into A; pass 2 draws uv-mapped triangles into B with the texture_unlit shader
+    sampling A's colour attachment in place.  f32 texels, no transcendental: colours are bit-exact."""
+    rng = np.random.default_rng(1000 + 10 * filt + edge)
+    wa, ha, wb, hb = 97, 61, 230, 170
+    border = (0.25, 0.5, 0.75, 0.5)
+    # pass 1 (alpha of the flat colours is random: pass 2's alpha_over then really blends)
+    va = H.random_screen_triangles(rng, 120, wa, ha)
+    ia = np.arange(va.shape[0], dtype=np.uint32)
+    out_a, _, _, ofa = run_both_screen_keep(P, ctx, wa, ha, va, ia)
+    fba, pipe_a = out_a
+    H.compare_framebuffers(fba.download(), ofa, exact_color=True, what="pass 1")
+    # pass 2
+    vb = _uv_triangles(rng, 60, wb, hb)
+    ib = np.arange(vb.shape[0], dtype=np.uint32)
+    u = scenes.suzanne_uniforms(wb, hb)
+    ofb = oracle_fb(wb, hb)
+    od = ob.OracleDraw(sr.TRIANGLE, ib, None)
+    od.set_vertices(vb, 1)
+    od.cull, od.blend, od.aa, od.tile = sr.CULL_NONE, blend, False, None
+    od.fragment_run(ofb, sr.FS_TEXTURE_UNLIT, u, texture=ofa.color.reshape(ha, wa, 4), sampler=(filt, edge, border))
+    fbb = make_fb(P, ctx, wb, hb)
+    pipe = P.Pipeline.from_framebuffer(fbb, u)
+    pipe.bind_framebuffer_texture(fba)
+    pipe.set_sampler(filt, edge, border)
+    pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).with_blend(blend).run(sr.FS_TEXTURE_UNLIT)
+    assert np.array_equal(fbb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fbb.download(), ofb, exact_color=True, what=f"render-to-texture filter {filt} edge {edge} blend {blend}")
+    # the source is untouched by being sampled
+    H.compare_framebuffers(fba.download(), ofa, exact_color=True, what="source after sampling")
+    for x in (pipe, fbb, pipe_a, fba):
+        x.destroy()
+
+
+def run_both_screen_keep(P, ctx, w, h, verts, indices, fs=sr.FS_FLAT):
+    """One opaque screen-space draw on both sides; returns the live GPU framebuffer + pipeline and the oracle's."""
+    u = scenes.suzanne_uniforms(w, h)
+    ofb = oracle_fb(w, h)
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    od = ob.OracleDraw(sr.TRIANGLE, indices, None)
+    od.set_vertices(verts, 1)
+    od.cull, od.blend, od.aa, od.tile = sr.CULL_NONE, sr.BLEND_REPLACE, False, None
+    od.fragment_run(ofb, fs, u)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, indices, 1).run(fs)
+    return (fb, pipe), None, None, ofb
+
+
+@pytest.mark.parametrize("edge", [sr.EDGE_CLAMP, sr.EDGE_WRAP, sr.EDGE_BORDER])
+@pytest.mark.parametrize("filt", [sr.FILTER_NEAREST, sr.FILTER_BILINEAR])
+def test_image_texture_sampler_modes(P, ctx, filt, edge):
+    """The same Filter / Edge set on an 8-bit image texture (texel / 255, decode_gamma: full_example/src/texture.rs:33-40,84);
+    coverage and depth bit-exact, colour within 1/255 (powf)."""
+    rng = np.random.default_rng(2000 + 10 * filt + edge)
+    w, h = 210, 140
+    img = rng.integers(0, 256, (23, 37, 4), dtype=np.uint8)
+    border = (0.9, 0.1, 0.3, 1.0)
+    vb = _uv_triangles(rng, 50, w, h)
+    ib = np.arange(vb.shape[0], dtype=np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    ofb = oracle_fb(w, h)
+    od = ob.OracleDraw(sr.TRIANGLE, ib, None)
+    od.set_vertices(vb, 1)
+    od.cull, od.blend, od.aa, od.tile = sr.CULL_NONE, sr.BLEND_REPLACE, False, None
+    od.fragment_run(ofb, sr.FS_TEXTURE_UNLIT, u, texture=img, sampler=(filt, edge, border))
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    tex = P.Texture(ctx, img)
+    pipe.bind_texture(tex)
+    pipe.set_sampler(filt, edge, border)
+    pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).run(sr.FS_TEXTURE_UNLIT)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    out = fb.download()
+    H.assert_bits_equal(out[:, 4], ofb.depth, "image sampler depth")
+    # Bilinear + Wrap extrapolates for negative coordinates (fract keeps the sign, the ratio goes negative): colours leave
+    # [0, 1] (NaN where decode_gamma meets a negative value), so the 1/255 bar is taken relative to the magnitude there
+    assert np.array_equal(np.isnan(out[:, :4]), np.isnan(ofb.color))
+    err = np.nan_to_num(np.abs(out[:, :4].astype(np.float64) - ofb.color), nan=0.0)
+    assert np.all(err <= COLOR_TOL * np.maximum(1.0, np.nan_to_num(np.abs(ofb.color), nan=0.0))), f"image sampler filter {filt} edge {edge}: {err.max()}"
+    for x in (pipe, tex, fb):
+        x.destroy()
+
+
+def test_render_to_texture_lit_scene_and_state(P, ctx):
+    """The shipped textured shader (full_example/src/shaders.rs:108-162) fed from a render target instead of an image;
+    a source whose clear is still only recorded; binding rules."""
+    from softrender_b200._abi import SoftrenderError
+    w, h = 320, 200
+    mesh = H.suzanne_mesh(with_uv=True)
+    u = scenes.full_example_uniforms(w / h, np.deg2rad(75.0), 2.0, np.deg2rad(45.0), np.deg2rad(65.0), 0.0)
+    # source: a cleared-only framebuffer (the clear is lazy: it must be materialised before it is sampled) ...
+    src = P.RenderBuffer.with_dimensions(ctx, 16, 9)
+    src.clear((0.2, 0.4, 0.6, 0.8))
+    osrc = ob.OracleFramebuffer(16, 9)
+    osrc.clear((0.2, 0.4, 0.6, 0.8))
+    rng = np.random.default_rng(77)
+    vb = _uv_triangles(rng, 30, w, h)
+    ib = np.arange(vb.shape[0], dtype=np.uint32)
+    us = scenes.suzanne_uniforms(w, h)
+    ofb = oracle_fb(w, h)
+    od = ob.OracleDraw(sr.TRIANGLE, ib, None)
+    od.set_vertices(vb, 1)
+    od.cull, od.blend, od.aa, od.tile = sr.CULL_NONE, sr.BLEND_REPLACE, False, None
+    od.fragment_run(ofb, sr.FS_TEXTURE_UNLIT, us, texture=osrc.color.reshape(9, 16, 4), sampler=(sr.FILTER_BILINEAR, sr.EDGE_WRAP, None))
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, us)
+    with pytest.raises(SoftrenderError):  # no texture bound
+        pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).run(sr.FS_TEXTURE_UNLIT)
+    pipe.bind_framebuffer_texture(fb)
+    with pytest.raises(SoftrenderError) as e:  # a target cannot be its own texture (&mut vs & borrow in the reference)
+        pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).run(sr.FS_TEXTURE_UNLIT)
+    assert e.value.status == sr.ERR_INVALID_STATE
+    with pytest.raises(SoftrenderError):
+        pipe.set_sampler(2, 0)
+    with pytest.raises(SoftrenderError):
+        pipe.set_sampler(0, 3)
+    pipe.bind_framebuffer_texture(src)
+    pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_WRAP)
+    pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).run(sr.FS_TEXTURE_UNLIT)
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="cleared-only source")
+    # ... then the lit, textured full_example shader sampling a rendered target (uv of the mesh), Nearest + Clamp
+    if True:
+        rs = np.random.default_rng(5)
+        va = H.random_screen_triangles(rs, 80, 64, 48)
+        ia = np.arange(va.shape[0], dtype=np.uint32)
+        (fba, pipe_a), _, _, ofa = run_both_screen_keep(P, ctx, 64, 48, va, ia)
+        vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
+        ofb2 = oracle_fb(w, h)
+        od2 = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        od2.vertex_run_to_fragment(vp, sr.VS_FULL_EXAMPLE, u, mesh.vertices)
+        od2.fragment_run(ofb2, sr.FS_FULL_EXAMPLE_TEXTURED, u, texture=ofa.color.reshape(48, 64, 4), sampler=(sr.FILTER_NEAREST, sr.EDGE_CLAMP, None))
+        fb2 = make_fb(P, ctx, w, h)
+        pipe2 = P.Pipeline.from_framebuffer(fb2, u)
+        pipe2.bind_framebuffer_texture(fba)
+        pipe2.set_sampler(sr.FILTER_NEAREST, sr.EDGE_CLAMP)
+        gm = P.Mesh(ctx, mesh)
+        pipe2.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp, sr.VS_FULL_EXAMPLE).run(sr.FS_FULL_EXAMPLE_TEXTURED)
+        assert np.array_equal(fb2.download_winner(), ofb2.winner)
+        H.compare_framebuffers(fb2.download(), ofb2, color_tol=COLOR_TOL, what="lit scene textured from a render target")
+        for x in (pipe2, gm, fb2, pipe_a, fba):
+            x.destroy()
+    for x in (pipe, fb, src):
+        x.destroy()

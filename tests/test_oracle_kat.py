@@ -235,3 +235,45 @@ def test_grid_generator_counts():
     # config 3 / 4 sizes without building them
     assert 4 * 2 * 1250 * 1000 == 10_000_000 and 4 * 1251 * 1001 == 5_009_004
     assert 4 * 2 * 5000 * 2500 == 100_000_000 and 4 * 5001 * 2501 == 50_030_004
+
+
+def test_texture_sampler_known_answers():
+    """texture(t, coord, filter, edge) (src/texture.rs:14-45) with the arithmetic of full_example/src/texture.rs:25-84,
+    worked by hand on a 3x2 texture: row 0 = 0, 10, 20 (red), row 1 = 100, 110, 120; green = 1, blue = 2, alpha = 3."""
+    t = np.zeros((2, 3, 4), np.float32)
+    t[..., 0] = np.array([[0, 10, 20], [100, 110, 120]], np.float32)
+    t[..., 1], t[..., 2], t[..., 3] = 1, 2, 3
+    N, B = 0, 1
+    CLAMP, WRAP, BORDER = 0, 1, 2
+    s = lambda u, v, f, e, b=None: ob.texture_sample(t, u, v, (f, e, b))
+    # Nearest: x = round(u * 2), y = round(v * 1); round is half away from zero (texture.rs:53-54)
+    assert s(0.0, 0.0, N, CLAMP)[0] == 0 and s(0.24, 0.0, N, CLAMP)[0] == 0 and s(0.25, 0.0, N, CLAMP)[0] == 10
+    assert s(0.75, 0.49, N, CLAMP)[0] == 20 and s(0.74, 0.5, N, CLAMP)[0] == 110 and s(1.0, 1.0, N, CLAMP)[0] == 120
+    assert list(s(0.5, 0.0, N, CLAMP)) == [10, 1, 2, 3]  # f32 colours come back as stored: no /255, no gamma
+    # Clamp: (u.min(1).max(0), v.min(1).max(0)) (texture.rs:28); NaN.min(1) = 1 in Rust
+    assert s(-3.0, 7.0, N, CLAMP)[0] == 100 and s(9.0, -1.0, N, CLAMP)[0] == 20 and s(float("nan"), 0.0, N, CLAMP)[0] == 20
+    # Wrap: fract keeps the sign (texture.rs:29): 1.25 -> 0.25, -0.75 -> -0.75 -> round(-1.5) = -2 -> `as u32` saturates to 0
+    assert s(1.25, 2.0, N, WRAP)[0] == 10 and s(3.5, 1.75, N, WRAP)[0] == 110 and s(-0.75, 0.0, N, WRAP)[0] == 0
+    # Border(C): outside [0,1]^2 or NaN -> C, inside as Clamp (src/texture.rs:43-44)
+    c = [0.5, 0.25, 0.125, 1.0]
+    assert list(s(1.0001, 0.5, N, BORDER, c)) == c and list(s(0.5, -1e-9, B, BORDER, c)) == c and list(s(float("nan"), 0.5, B, BORDER, c)) == c
+    assert s(1.0, 1.0, N, BORDER, c)[0] == 120 and s(0.0, 0.0, B, BORDER, c)[0] == s(0.0, 0.0, B, CLAMP)[0]
+    # Bilinear (texture.rs:58-82): uu = u*2 + 0.5, x = floor(uu), ratio = uu - x; vv = v*1 + 0.5
+    # u = 0.5, v = 0.25: uu = 1.5 -> x = 1, ur = 0.5; vv = 0.75 -> y = 0, vr = 0.75
+    #   (10*0.5 + 20*0.5) * 0.25 + (110*0.5 + 120*0.5) * 0.75 = 3.75 + 86.25 = 90
+    assert s(0.5, 0.25, B, CLAMP)[0] == 90.0
+    # u = 0, v = 0: uu = 0.5 -> x = 0, ur = 0.5; vv = 0.5 -> y = 0, vr = 0.5: (0*.5 + 10*.5)*.5 + (100*.5 + 110*.5)*.5 = 55
+    assert s(0.0, 0.0, B, CLAMP)[0] == 55.0
+    # u = 1, v = 1: uu = 2.5 -> x = 2, x+1 = 3 clamped to the last column (the reference would index out of bounds):
+    #   vv = 1.5 -> y = 1, y+1 clamped: every tap is texel (2,1) = 120
+    assert s(1.0, 1.0, B, CLAMP)[0] == 120.0
+    # image texels: u8 / 255 then decode_gamma on r, g, b only (texture.rs:33-40,84)
+    img = np.zeros((1, 1, 4), np.uint8)
+    img[0, 0] = (255, 128, 0, 64)
+    r = ob.texture_sample(img, 0.3, 0.6, (N, CLAMP, None))
+    exp = np.array([1.0, np.float32(128 / 255) ** np.float32(2.2), 0.0, np.float32(64) / np.float32(255)], np.float32)
+    assert np.allclose(r, exp, rtol=1e-6, atol=0) and r[3] == exp[3]
+    # default sampler state = the shipped scene's Bilinear + Clamp (full_example/src/shaders.rs)
+    chk = scenes.checker_texture(16, 4)
+    for u, v in [(0.1, 0.9), (0.5, 0.5), (1.0, 0.0), (0.333, 0.777)]:
+        assert np.array_equal(ob.texture_sample(chk, u, v, (B, CLAMP, None)), ob.texture_sample(chk, u, v, None))
