@@ -807,13 +807,19 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro
 #define SR_BIN_SMALL_THREADS 1024
 #define SR_BIN_SMALL_MAX_TRIS 8192
 #define SR_BIN_SMALL_MAX_TILES 8192
+#define SR_BIN_SMALL_HUGE 256      // tiles
+#define SR_BIN_SMALL_MAX_HUGE 64
 __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid_constant__ SrMicroParams p, uint32_t *tile_off,
                                                                     uint32_t *list, uint32_t capacity) {
     extern __shared__ uint32_t s_cnt[];  // per-tile counters, later the fill cursors
     __shared__ uint32_t s_wsum[32];
+    // triangles covering more than SR_BIN_SMALL_HUGE tiles (a full-screen quad of a post-processing pass: every tile of the
+    // frame, twice) are walked by the whole CTA instead of one warp
+    __shared__ uint32_t s_huge_rect[SR_BIN_SMALL_MAX_HUGE], s_huge_tri[SR_BIN_SMALL_MAX_HUGE], s_nhuge;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ntiles = p.ntx * p.nty;
     for (uint32_t i = tid; i < ntiles; i += SR_BIN_SMALL_THREADS) s_cnt[i] = 0;
+    if (tid == 0) s_nhuge = 0;
     __syncthreads();
     constexpr int PER = SR_BIN_SMALL_MAX_TRIS / SR_BIN_SMALL_THREADS;
     uint32_t rects[PER];
@@ -850,6 +856,7 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     };
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
+        if ((uint32_t)k * SR_BIN_SMALL_THREADS >= p.ntris) break;  // CTA-uniform: a 2-triangle draw runs one round, not eight
         const uint32_t t = (uint32_t)k * SR_BIN_SMALL_THREADS + tid;
         uint32_t rect = SR_RECT_INVALID;
         if (t < p.ntris) {
@@ -870,9 +877,33 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
                 if (minx <= maxx && miny <= maxy) rect = sr_pack_rect(minx / SR_TILE_W, miny / SR_TILE_H, maxx / SR_TILE_W, maxy / SR_TILE_H);
             }
         }
+        if (rect != SR_RECT_INVALID && ((rect >> 16 & 255u) - (rect & 255u) + 1) * ((rect >> 24) - (rect >> 8 & 255u) + 1) > SR_BIN_SMALL_HUGE) {
+            const uint32_t slot = atomicAdd(&s_nhuge, 1u);
+            if (slot < SR_BIN_SMALL_MAX_HUGE) {  // (a full table leaves the triangle to its warp)
+                s_huge_rect[slot] = rect;
+                s_huge_tri[slot] = t;
+                rect = SR_RECT_INVALID;
+            }
+        }
         rects[k] = rect;
         spread(rect, t, false);
     }
+    __syncthreads();
+    const uint32_t nhuge = min(s_nhuge, (uint32_t)SR_BIN_SMALL_MAX_HUGE);
+    auto spread_huge = [&](bool fill) {
+        for (uint32_t h = 0; h < nhuge; ++h) {
+            const uint32_t r = s_huge_rect[h], st = s_huge_tri[h];
+            const uint32_t tx0 = r & 255u, ty0 = (r >> 8) & 255u, tx1 = (r >> 16) & 255u, ty1 = r >> 24;
+            const uint32_t rw = tx1 - tx0 + 1, n = rw * (ty1 - ty0 + 1);
+            for (uint32_t i = tid; i < n; i += SR_BIN_SMALL_THREADS) {
+                const uint32_t tile = (ty0 + i / rw) * p.ntx + tx0 + i % rw;
+                if (sharded && tile % p.shard_world != p.shard_rank) continue;
+                const uint32_t at = atomicAdd(&s_cnt[tile], 1u);
+                if (fill) list[at] = st;
+            }
+        }
+    };
+    spread_huge(false);
     __syncthreads();
     // exclusive scan of the counters: a run of consecutive tiles per thread, warp scan, scan of the warp totals
     const uint32_t chunk = (ntiles + SR_BIN_SMALL_THREADS - 1) / SR_BIN_SMALL_THREADS;
@@ -909,7 +940,11 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     __syncthreads();
     if (total > capacity) return;  // the lists do not fit: the host re-runs this launch with a larger arena
 #pragma unroll
-    for (int k = 0; k < PER; ++k) spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
+    for (int k = 0; k < PER; ++k) {
+        if ((uint32_t)k * SR_BIN_SMALL_THREADS >= p.ntris) break;
+        spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
+    }
+    spread_huge(true);
 }
 
 struct SrLineSetup {

@@ -149,14 +149,15 @@ __device__ __noinline__ float4 sr_texture_sample_general(const SrFsConst &c, flo
     const uint32_t lastx = c.tex_w - 1, lasty = c.tex_h - 1;
     const bool f32 = c.tex_kind == SR_TEX_F32;
     const float r255 = __frcp_rn(255.0f);
+    const uint32_t texel_bytes = f32 ? c.tex_stride * 4u : 4u;
     auto texel = [&](uint32_t x, uint32_t y, float *a) {
         x = min(x, lastx); y = min(y, lasty);
-        const size_t i = (size_t)y * c.tex_w + x;
+        const uint8_t *at = c.tex + (size_t)y * (c.tex_w * texel_bytes) + x * texel_bytes;  // (a row is below 4 GB)
         if (f32) {
-            const float *t = reinterpret_cast<const float *>(c.tex) + i * c.tex_stride;
-            a[0] = t[0]; a[1] = t[1]; a[2] = t[2]; a[3] = t[3];
+            const float *t = reinterpret_cast<const float *>(at);
+            a[0] = __ldg(t); a[1] = __ldg(t + 1); a[2] = __ldg(t + 2); a[3] = __ldg(t + 3);
         } else {
-            const uchar4 t = __ldg((const uchar4 *)c.tex + i);
+            const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(at));
             a[0] = sr_div_exact((float)t.x, 255.0f, r255); a[1] = sr_div_exact((float)t.y, 255.0f, r255);
             a[2] = sr_div_exact((float)t.z, 255.0f, r255); a[3] = sr_div_exact((float)t.w, 255.0f, r255);
         }
