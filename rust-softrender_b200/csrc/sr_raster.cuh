@@ -1371,6 +1371,15 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                         const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
                         const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
                         const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
+                        if (pl >= 2) {
+                            // planes past position + normal carry texture coordinates: exact, because a Nearest sampler is a
+                            // step function of them (one ulp of contraction can select the neighbouring texel)
+                            sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x);
+                            sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                            sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z);
+                            sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                            continue;
+                        }
                         sv[4 + pl * 4 + 0] = KB(u, ka.x, v, kb.x, w, kc.x);
                         sv[4 + pl * 4 + 1] = KB(u, ka.y, v, kb.y, w, kc.y);
                         sv[4 + pl * 4 + 2] = KB(u, ka.z, v, kb.z, w, kc.z);

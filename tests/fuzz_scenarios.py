@@ -120,6 +120,17 @@ def run_pipeline_scenario(P, ctx, ob, scenes, seed: int) -> str:
     if textured:  # any size, including 1x1 and non-square: the bilinear taps at the last row / column are clamped
         tex = (scenes.checker_texture(64, 8) if rng.random() < 0.3 else
                rng.integers(0, 256, (int(rng.integers(1, 70)), int(rng.integers(1, 70)), 4), dtype=np.uint8))
+    # sampler state and texel format from a stream of their own (the scenarios of earlier campaigns keep their seeds):
+    # Filter x Edge of src/texture.rs:21-45; the texture is an 8-bit image or a render target sampled in place
+    sampler, rtt = None, False
+    if textured:
+        srng = np.random.default_rng(seed ^ 0x7E57)
+        if srng.random() < 0.6:
+            sampler = (int(srng.integers(0, 2)), int(srng.integers(0, 3)), tuple(float(x) for x in srng.uniform(0, 1, 4)))
+        rtt = srng.random() < 0.4
+        if rtt:
+            tex = srng.uniform(0, 1, (tex.shape[0], tex.shape[1], 4)).astype(np.float32)
+        what += f" sampler {sampler} rtt {rtt}"
     ofb = ob.OracleFramebuffer(w, h)
     ofb.clear(H.CLEAR)
     for _ in range(draws):
@@ -130,14 +141,21 @@ def run_pipeline_scenario(P, ctx, ob, scenes, seed: int) -> str:
             od.vertex_run_to_fragment(vp, vs, u, mesh.vertices)
         else:
             od.vertex_run(vs, u, mesh.vertices).clip_primitives(correct=(clip == 2)).finish(vp)
-        od.fragment_run(ofb, fs, u, texture=tex)
+        od.fragment_run(ofb, fs, u, texture=tex, sampler=sampler)
     fb = P.RenderBuffer.with_dimensions(ctx, w, h)
     fb.enable_winner(True)
     pipe = P.Pipeline.from_framebuffer(fb, u)
     gmesh = P.Mesh(ctx, mesh)
-    gtex = P.Texture(ctx, tex) if textured else None
-    if gtex is not None:
+    gtex = None
+    if textured and rtt:
+        gtex = P.RenderBuffer.with_dimensions(ctx, tex.shape[1], tex.shape[0])
+        gtex.upload_planes(tex.reshape(-1, 4), np.zeros(tex.shape[0] * tex.shape[1], np.float32), None)
+        pipe.bind_framebuffer_texture(gtex)
+    elif textured:
+        gtex = P.Texture(ctx, tex)
         pipe.bind_texture(gtex)
+    if sampler is not None:
+        pipe.set_sampler(*sampler)
     try:
         for rank in range(world):
             ctx.set_tile_shard(rank, world)

@@ -870,10 +870,14 @@ def test_randomised_scenarios(P, ctx):
 def test_randomised_pipeline_scenarios(P, ctx):
     """80 random scenes through the whole builder chain (tests/fuzz_scenarios.py::run_pipeline_scenario): Suzanne, subdivided
     Suzanne or a displaced grid; random camera distance (meshes cross the frustum planes when close), rotation, frame size;
-    both example shader sets, textured or not; run_to_fragment / literal clipper / Sutherland-Hodgman clipper; blend, cull,
-    one or two draws, optionally tile-sharded.  Winner and depth bit-exact, colour within 1/255."""
+    both example shader sets, textured or not (8-bit image or a render target sampled in place, any Filter / Edge);
+    run_to_fragment / literal clipper / Sutherland-Hodgman clipper; blend, cull, one or two draws, optionally tile-sharded.
+    Winner and depth bit-exact, colour within 1/255."""
     from fuzz_scenarios import run_pipeline_scenario
-    failures = [m for m in (run_pipeline_scenario(P, ctx, ob, scenes, seed) for seed in range(100, 180)) if m]
+    # the four seeds past the range are regressions: Nearest sampling is a step function of the interpolated uv, which the lit
+    # shaders' contracted (FMA) attribute interpolation moved by an ulp across a texel boundary -- the uv plane is exact now
+    seeds = list(range(100, 180)) + [1005969, 1009630, 1012157, 1012189]
+    failures = [m for m in (run_pipeline_scenario(P, ctx, ob, scenes, seed) for seed in seeds) if m]
     assert not failures, "\n".join(failures)
 
 
