@@ -134,8 +134,8 @@ __device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, fl
 // texture(t, coord, filter, edge) (src/texture.rs:14-18) for any Filter / Edge / texel format: the arithmetic of
 // full_example/src/texture.rs:25-84 with Rust's saturating `as u32` (negative and NaN -> 0; CUDA's float->uint conversion
 // saturates the same way) and every texel index clamped to the last row / column where the reference would index out
-// of bounds.  Not inlined: the shipped scene's Bilinear + Clamp + RGBA8 case keeps its own straight-line body above.
-__device__ __noinline__ float4 sr_texture_sample_general(const SrFsConst &c, float u, float v) {
+// of bounds.
+__device__ __forceinline__ float4 sr_texture_sample_body(const SrFsConst &c, float u, float v) {
     if (c.tex_edge == SR_EDGE_WRAP) {
         u = u - truncf(u);  // f32::fract
         v = v - truncf(v);
@@ -183,6 +183,9 @@ __device__ __noinline__ float4 sr_texture_sample_general(const SrFsConst &c, flo
     }
     return make_float4(val[0], val[1], val[2], val[3]);
 }
+// Out of line for the lit shaders: the shipped scene's Bilinear + Clamp + RGBA8 case keeps its own straight-line body above and
+// the kernels their register budget; the unlit second-pass shader (nothing else to keep live) inlines the body.
+__device__ __noinline__ float4 sr_texture_sample_general(const SrFsConst &c, float u, float v) { return sr_texture_sample_body(c, u, v); }
 __device__ __forceinline__ void sr_texture_sample(const SrFsConst &c, float u, float v, float *out) {
     if (c.tex_kind == SR_TEX_RGBA8 && c.tex_filter == SR_FILTER_BILINEAR && c.tex_edge == SR_EDGE_CLAMP) sr_texture_bilinear_clamp(c, u, v, out);
     else {
@@ -203,8 +206,10 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
         out[0] = 0.0f; out[1] = 1.0f; out[2] = 0.0f; out[3] = 1.0f;
         return true;
     } else if (FS == SR_FS_TEXTURE_UNLIT) {  // texture(t, uv, filter, edge), src/texture.rs:14-18
-        if (c.tex != nullptr) sr_texture_sample(c, K[0], K[1], out);
-        else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 0.0f; }
+        if (c.tex != nullptr) {
+            const float4 t = sr_texture_sample_body(c, K[0], K[1]);
+            out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+        } else { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 0.0f; }
         return true;
     } else if (FS == SR_FS_DISCARD_CHECKER) {
         const int xi = (int)floorf(sv[0]), yi = (int)floorf(sv[1]);
