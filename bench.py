@@ -241,6 +241,25 @@ def other_configs(ctx):
 
     out["config2_full_example_1080p_us_per_frame"] = per_frame_us(full_example, 32)
     out["config2_composition"] = "3 x 968 triangles, textured 4-light shader, alpha_over; then 3 x 968 face-normal lines, green shader"
+
+    # render-to-texture: the config-2 frame above sampled in place by a full-screen second pass
+    # (2 triangles through the passthrough vertex shader, texture_unlit, Bilinear + Clamp) into a second 1920x1080 target
+    fb2 = P.RenderBuffer.with_dimensions(ctx, w, h)
+    pipe2 = P.Pipeline.from_framebuffer(fb2, us[0])
+    pipe2.bind_framebuffer_texture(fb)
+    pipe2.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
+    quad = np.array([[-1, -1, 0, 1, 0, 1], [1, -1, 0, 1, 1, 1], [1, 1, 0, 1, 1, 0], [-1, 1, 0, 1, 0, 0]], np.float32)  # clip xyzw + uv
+    qm = P.Mesh(ctx, vertices=quad, indices=np.array([0, 1, 2, 0, 2, 3], np.uint32))
+
+    def second_pass():
+        fb2.clear(CLEAR)
+        pipe2.render_mesh(sr.TRIANGLE, qm).run_to_fragment(vp, sr.VS_PASSTHROUGH).run(sr.FS_TEXTURE_UNLIT)
+
+    out["render_to_texture_second_pass_1080p_us"] = per_frame_us(second_pass, 32)
+    covered = int((fb2.download()[:, 4] > np.float32(-3e38)).sum())
+    out["render_to_texture_second_pass_pixels"] = covered
+    for x in (pipe2, qm, fb2):
+        x.destroy()
     for x in (pipe, gm, tex, fb):
         x.destroy()
     return out

@@ -1147,3 +1147,40 @@ def test_render_to_texture_lit_scene_and_state(P, ctx):
             x.destroy()
     for x in (pipe, fb, src):
         x.destroy()
+
+
+def test_render_to_texture_full_screen_pass_through_the_builder_chain(P, ctx):
+    """The post-processing shape of the feature (what bench.py times): pass 1 renders Suzanne, pass 2 is a clip-space quad
+    through the passthrough vertex shader (Vin = clip xyzw + uv) and run_to_fragment, texture_unlit sampling pass 1 in place."""
+    w, h = 300, 180
+    mesh = H.suzanne_mesh()
+    u = scenes.suzanne_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.001, 1000.0)
+    ofa, fba = oracle_fb(w, h), make_fb(P, ctx, w, h)
+    ob.OracleDraw(sr.TRIANGLE, mesh.indices).vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices).fragment_run(ofa, sr.FS_SUZANNE, u)
+    pa = P.Pipeline.from_framebuffer(fba, u)
+    gm = P.Mesh(ctx, mesh)
+    pa.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+    quad = np.array([[-1, -1, 0, 1, 0, 1], [1, -1, 0, 1, 1, 1], [1, 1, 0, 1, 1, 0], [-1, 1, 0, 1, 0, 0]], np.float32)
+    qi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    # the oracle samples ITS pass-1 image (lit colours agree within 1/255 only, so pass 2 inherits that tolerance);
+    # sampling the GPU's own pass-1 pixels instead makes pass 2 bit-exact
+    src = fba.download()[:, :4].reshape(h, w, 4).copy()
+    for filt in (sr.FILTER_NEAREST, sr.FILTER_BILINEAR):
+        ofb = oracle_fb(w, h)
+        ob.OracleDraw(sr.TRIANGLE, qi).vertex_run_to_fragment(vp, sr.VS_PASSTHROUGH, u, quad).fragment_run(
+            ofb, sr.FS_TEXTURE_UNLIT, u, texture=src, sampler=(filt, sr.EDGE_CLAMP, None))
+        fbb = make_fb(P, ctx, w, h)
+        pb = P.Pipeline.from_framebuffer(fbb, u)
+        pb.bind_framebuffer_texture(fba)
+        pb.set_sampler(filt, sr.EDGE_CLAMP)
+        qm = P.Mesh(ctx, vertices=quad, indices=qi)
+        pb.render_mesh(sr.TRIANGLE, qm).run_to_fragment(vp, sr.VS_PASSTHROUGH).run(sr.FS_TEXTURE_UNLIT)
+        out = fbb.download()
+        assert np.array_equal(fbb.download_winner(), ofb.winner) and int((ofb.winner > 0).sum()) == w * h  # every pixel, once
+        H.compare_framebuffers(out, ofb, exact_color=True, what=f"full-screen second pass filter {filt}")
+        for x in (pb, qm, fbb):
+            x.destroy()
+    H.compare_framebuffers(fba.download(), ofa, color_tol=COLOR_TOL, what="pass 1")
+    for x in (pa, gm, fba):
+        x.destroy()
