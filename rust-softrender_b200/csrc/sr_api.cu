@@ -718,10 +718,12 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
 static int launch_bin_small(sr_context *c, PendingOpaque *q) {
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
-        SR_CUDA(cudaFuncSetAttribute(k_bin_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_BIN_SMALL_MAX_TILES * 4));
+        SR_CUDA(cudaFuncSetAttribute(k_bin_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (SR_BIN_SMALL_MAX_TILES + SR_BIN_SMALL_MAX_TRIS) * 4));
         configured[c->device & 15] = true;
     }
-    SR_LAUNCH(c, k_bin_small, 1, SR_BIN_SMALL_THREADS, (size_t)q->ntiles * 4, q->mp, q->off->as<uint32_t>(), const_cast<uint32_t *>(q->op.list),
+    // per-tile counters + one tile rectangle per triangle (whole rounds of SR_BIN_SMALL_THREADS)
+    const size_t smem = ((size_t)q->ntiles + (size_t)ceil_div(q->mp.ntris, SR_BIN_SMALL_THREADS) * SR_BIN_SMALL_THREADS) * 4;
+    SR_LAUNCH(c, k_bin_small, 1, SR_BIN_SMALL_THREADS, smem, q->mp, q->off->as<uint32_t>(), const_cast<uint32_t *>(q->op.list),
               q->capacity);
     return SR_OK;
 }

@@ -821,8 +821,11 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     for (uint32_t i = tid; i < ntiles; i += SR_BIN_SMALL_THREADS) s_cnt[i] = 0;
     if (tid == 0) s_nhuge = 0;
     __syncthreads();
-    constexpr int PER = SR_BIN_SMALL_MAX_TRIS / SR_BIN_SMALL_THREADS;
-    uint32_t rects[PER];
+    // one round of SR_BIN_SMALL_THREADS triangles at a time, NOT unrolled: this kernel runs once, on one CTA, with a cold
+    // instruction cache -- unrolled eight times it was 11.6 k SASS instructions and most of its time was instruction fetch
+    // (ncu: 24 of 30 stall cycles per issue `no_instruction`).  The rectangles wait for the fill phase in shared memory.
+    uint32_t *s_rect = s_cnt + ntiles;  // [rounds * SR_BIN_SMALL_THREADS], each thread reads back only its own entries
+    const uint32_t rounds = (p.ntris + SR_BIN_SMALL_THREADS - 1) / SR_BIN_SMALL_THREADS;
     // A lane walks its own triangle's tile rectangle when it is small (the usual case: a handful of tiles); a rectangle of
     // more than 16 tiles is spread over the lanes of the warp (a big triangle touches hundreds of tiles).
     const bool sharded = p.shard_world > 1;
@@ -854,10 +857,9 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
             }
         }
     };
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        if ((uint32_t)k * SR_BIN_SMALL_THREADS >= p.ntris) break;  // CTA-uniform: a 2-triangle draw runs one round, not eight
-        const uint32_t t = (uint32_t)k * SR_BIN_SMALL_THREADS + tid;
+#pragma unroll 1
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t t = k * SR_BIN_SMALL_THREADS + tid;
         uint32_t rect = SR_RECT_INVALID;
         if (t < p.ntris) {
             const SrVertexSet *vs;
@@ -885,7 +887,7 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
                 rect = SR_RECT_INVALID;
             }
         }
-        rects[k] = rect;
+        s_rect[t] = rect;
         spread(rect, t, false);
     }
     __syncthreads();
@@ -939,11 +941,8 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     if (tid == 0) tile_off[ntiles] = total;
     __syncthreads();
     if (total > capacity) return;  // the lists do not fit: the host re-runs this launch with a larger arena
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        if ((uint32_t)k * SR_BIN_SMALL_THREADS >= p.ntris) break;
-        spread(rects[k], (uint32_t)k * SR_BIN_SMALL_THREADS + tid, true);
-    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < rounds; ++k) spread(s_rect[k * SR_BIN_SMALL_THREADS + tid], k * SR_BIN_SMALL_THREADS + tid, true);
     spread_huge(true);
 }
 
