@@ -4,6 +4,7 @@
 // build() as the "does the host mirror compile and link" check and runnable on a GPU box.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 
 #include "../../include/softrender_b200.hpp"
 
@@ -45,6 +46,21 @@ int main() {
         size_t covered = 0;
         for (const PixelCD &p : fb.pixels()) covered += p.depth > -1e30f;
         std::printf("builder_example: %zu of %u pixels covered\n", covered, 256u * 256u);
+        // second pass (render-to-texture): the frame above sampled in place by a full-screen quad, Nearest + Clamp at the same
+        // size is a 1:1 copy of the colours (texturebuffer.rs:12-58, texture.rs:14-45)
+        auto fb2 = RenderBuffer::with_dimensions(ctx, Dimensions{256, 256});
+        fb2.clear(clear);
+        auto post = Pipeline::from_framebuffer(ctx, fb2, u);
+        post.bind_framebuffer_texture(&fb);
+        post.set_sampler(SR_FILTER_NEAREST, SR_EDGE_CLAMP);
+        const float quad[4 * 6] = {-1, -1, 0, 1, 0, 1, 1, -1, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, -1, 1, 0, 1, 0, 0};  // clip xyzw + uv
+        Mesh qmesh(ctx, quad, 4, 6, idx, 6);
+        post.render_mesh(Triangle{}, qmesh).run_to_fragment(vp, SR_VS_PASSTHROUGH).run(SR_FS_TEXTURE_UNLIT);
+        size_t same = 0;
+        const auto a = fb.pixels(), b = fb2.pixels();
+        for (size_t i = 0; i < a.size(); ++i) same += std::memcmp(&a[i].r, &b[i].r, 4 * sizeof(float)) == 0;
+        std::printf("render-to-texture copy pass: %zu of %zu pixels identical\n", same, a.size());
+        if (same != a.size()) return 3;
         try {
             fb.pixel(256, 0);
         } catch (const Error &e) {
