@@ -29,8 +29,10 @@ img = P.Texture(ctx, scenes.checker_texture(1024, 16))
 names = {0: "nearest", 1: "bilinear"}, {0: "clamp", 1: "wrap", 2: "border"}
 for label, bind in (("render target f32 (in place)", lambda: p2.bind_framebuffer_texture(src)), ("image rgba8 1024^2", lambda: p2.bind_texture(img))):
     bind()
-    for filt in (0, 1):
-        for edge in (0, 1, 2):
+    modes = [(f, e) for f in (0, 1) for e in (0, 1, 2)]
+    if os.environ.get("RTT_REVERSE") == "1": modes.reverse()  # (order check: a mode's time must not depend on its position)
+    for filt, edge in modes:
+        if True:
             p2.set_sampler(filt, edge, (0, 0, 0, 1))
             def frame():
                 dst.clear(H.CLEAR); p2.draw_from_vertices(sr.TRIANGLE, quad, idx, 1).run(sr.FS_TEXTURE_UNLIT)
