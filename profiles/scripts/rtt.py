@@ -32,13 +32,12 @@ for label, bind in (("render target f32 (in place)", lambda: p2.bind_framebuffer
     modes = [(f, e) for f in (0, 1) for e in (0, 1, 2)]
     if os.environ.get("RTT_REVERSE") == "1": modes.reverse()  # (order check: a mode's time must not depend on its position)
     for filt, edge in modes:
-        if True:
-            p2.set_sampler(filt, edge, (0, 0, 0, 1))
-            def frame():
-                dst.clear(H.CLEAR); p2.draw_from_vertices(sr.TRIANGLE, quad, idx, 1).run(sr.FS_TEXTURE_UNLIT)
-            ms = timeit(frame)
-            gbs = w * h * (20 + (16 if "f32" in label else 0)) / ms / 1e6
-            print(f"{label:30s} {names[0][filt]:8s} {names[1][edge]:6s}: {ms*1e3:7.1f} us/pass  ({gbs:6.0f} GB/s algorithmic)")
+        p2.set_sampler(filt, edge, (0, 0, 0, 1))
+        def frame():
+            dst.clear(H.CLEAR); p2.draw_from_vertices(sr.TRIANGLE, quad, idx, 1).run(sr.FS_TEXTURE_UNLIT)
+        ms = timeit(frame)
+        gbs = w * h * (20 + (16 if "f32" in label else 0)) / ms / 1e6
+        print(f"{label:30s} {names[0][filt]:8s} {names[1][edge]:6s}: {ms*1e3:7.1f} us/pass  ({gbs:6.0f} GB/s algorithmic)")
 # where the time of the pass goes: library stage timers, and the same quad with the flat shader (no sampling) for comparison
 ctx.set_stage_timing(True)
 p2.bind_framebuffer_texture(src); p2.set_sampler(0, 0)

@@ -1125,26 +1125,25 @@ def test_render_to_texture_lit_scene_and_state(P, ctx):
     pipe.draw_from_vertices(sr.TRIANGLE, vb, ib, 1).run(sr.FS_TEXTURE_UNLIT)
     H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="cleared-only source")
     # ... then the lit, textured full_example shader sampling a rendered target (uv of the mesh), Nearest + Clamp
-    if True:
-        rs = np.random.default_rng(5)
-        va = H.random_screen_triangles(rs, 80, 64, 48)
-        ia = np.arange(va.shape[0], dtype=np.uint32)
-        (fba, pipe_a), _, _, ofa = run_both_screen_keep(P, ctx, 64, 48, va, ia)
-        vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
-        ofb2 = oracle_fb(w, h)
-        od2 = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
-        od2.vertex_run_to_fragment(vp, sr.VS_FULL_EXAMPLE, u, mesh.vertices)
-        od2.fragment_run(ofb2, sr.FS_FULL_EXAMPLE_TEXTURED, u, texture=ofa.color.reshape(48, 64, 4), sampler=(sr.FILTER_NEAREST, sr.EDGE_CLAMP, None))
-        fb2 = make_fb(P, ctx, w, h)
-        pipe2 = P.Pipeline.from_framebuffer(fb2, u)
-        pipe2.bind_framebuffer_texture(fba)
-        pipe2.set_sampler(sr.FILTER_NEAREST, sr.EDGE_CLAMP)
-        gm = P.Mesh(ctx, mesh)
-        pipe2.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp, sr.VS_FULL_EXAMPLE).run(sr.FS_FULL_EXAMPLE_TEXTURED)
-        assert np.array_equal(fb2.download_winner(), ofb2.winner)
-        H.compare_framebuffers(fb2.download(), ofb2, color_tol=COLOR_TOL, what="lit scene textured from a render target")
-        for x in (pipe2, gm, fb2, pipe_a, fba):
-            x.destroy()
+    rs = np.random.default_rng(5)
+    va = H.random_screen_triangles(rs, 80, 64, 48)
+    ia = np.arange(va.shape[0], dtype=np.uint32)
+    (fba, pipe_a), _, _, ofa = run_both_screen_keep(P, ctx, 64, 48, va, ia)
+    vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
+    ofb2 = oracle_fb(w, h)
+    od2 = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    od2.vertex_run_to_fragment(vp, sr.VS_FULL_EXAMPLE, u, mesh.vertices)
+    od2.fragment_run(ofb2, sr.FS_FULL_EXAMPLE_TEXTURED, u, texture=ofa.color.reshape(48, 64, 4), sampler=(sr.FILTER_NEAREST, sr.EDGE_CLAMP, None))
+    fb2 = make_fb(P, ctx, w, h)
+    pipe2 = P.Pipeline.from_framebuffer(fb2, u)
+    pipe2.bind_framebuffer_texture(fba)
+    pipe2.set_sampler(sr.FILTER_NEAREST, sr.EDGE_CLAMP)
+    gm = P.Mesh(ctx, mesh)
+    pipe2.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp, sr.VS_FULL_EXAMPLE).run(sr.FS_FULL_EXAMPLE_TEXTURED)
+    assert np.array_equal(fb2.download_winner(), ofb2.winner)
+    H.compare_framebuffers(fb2.download(), ofb2, color_tol=COLOR_TOL, what="lit scene textured from a render target")
+    for x in (pipe2, gm, fb2, pipe_a, fba):
+        x.destroy()
     for x in (pipe, fb, src):
         x.destroy()
 
