@@ -652,6 +652,10 @@ def main():
     ap.add_argument("--in-flight", type=int, default=3, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # no cyclic-garbage collections inside timed regions (a full collection is a millisecond-scale host pause, several frames
+    # of this workload; seen as a +50..85 us/frame outlier in profiles/scripts/rtt.py before it did the same)
+    import gc
+    gc.disable()
     if args.config == "turntable":
         run_turntable(args)
     elif args.impl == "reference":

@@ -1,7 +1,8 @@
 """Render-to-texture second pass: a full-screen quad (2 triangles) at 3840x2160 with the texture_unlit shader sampling a
 3840x2160 render target in place, for every Filter / Edge, plus the same pass from an 8-bit image texture.
 Algorithmic bytes of the pass: 20 B/pixel written + 16 B/pixel of source colour read (Nearest, 1:1 mapping)."""
-import sys, os, time
+import sys, os, time, gc
+gc.disable()  # a full collection in the middle of one mode's timed frames showed up as +50..85 us on that line
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import numpy as np
 import softrender_b200 as sr
