@@ -267,6 +267,9 @@ def test_texture_sampler_known_answers():
     # u = 1, v = 1: uu = 2.5 -> x = 2, x+1 = 3 clamped to the last column (the reference would index out of bounds):
     #   vv = 1.5 -> y = 1, y+1 clamped: every tap is texel (2,1) = 120
     assert s(1.0, 1.0, B, CLAMP)[0] == 120.0
+    # Bilinear + Wrap below zero extrapolates: u = -0.5 -> fract = -0.5, uu = -0.5, floor = -1 -> `as u32` = 0, ratio = -0.5,
+    # opposite = 1.5: row 0: 0*1.5 + 10*(-0.5) = -5; row 1: 100*1.5 + 110*(-0.5) = 95; v = 0 -> vr = 0.5: (-5 + 95) / 2 = 45
+    assert s(-0.5, 0.0, B, WRAP)[0] == 45.0
     # image texels: u8 / 255 then decode_gamma on r, g, b only (texture.rs:33-40,84)
     img = np.zeros((1, 1, 4), np.uint8)
     img[0, 0] = (255, 128, 0, 64)
