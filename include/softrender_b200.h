@@ -160,7 +160,8 @@ int sr_pipeline_bind_texture(sr_pipeline *, sr_texture *);
  * Texels are the f32 RGBA colours as rendered (no /255, no gamma decode: a render target holds linear colour).
  * NULL unbinds; binding replaces an image texture bound with sr_pipeline_bind_texture and vice versa.  A draw that
  * renders into `src` itself, or whose pipeline lives in another context than `src`, fails with SR_ERR_INVALID_STATE;
- * a recorded clear of `src` is materialised before the sampling draw. */
+ * a recorded clear of `src` is materialised before the sampling draw.  Like an image texture, `src` must stay alive while it
+ * is bound (the pipeline borrows it, as `TextureBufferRef<'a>` borrows its parent); unbind with NULL before destroying it. */
 int sr_pipeline_bind_framebuffer_texture(sr_pipeline *, sr_framebuffer *src);
 /* Filter and Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45) for every sampling shader of the pipeline.
  * border_rgba: 4 floats, read only for SR_EDGE_BORDER (NULL = transparent black).  Default: BILINEAR, CLAMP. */
