@@ -719,7 +719,8 @@ def test_turntable_frames(P, ctx):
 
 
 # ------------------------------------------------------------------------------------------------------
-# BASELINE.json's full sizes, through size-independent properties (the oracle would need hours per frame)
+# BASELINE.json's full sizes through size-independent properties of the CUDA path (idempotence, split and shard
+# invariance); the full-size comparison with the oracle itself is tests/test_gpu_sizes_full.py
 # ------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def grid10m():
