@@ -92,58 +92,111 @@ def build_scene(name: str):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the restated reference CPU path (oracle) on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(name: str, steps: int = 1, warmup: int = 0):
-    """Times the oracle's threaded mode (thread pool + atomic cursors, every 128x128 tile visits every primitive:
-    the reference's structure) on a BOUNDED sample of the workload: same frame size, camera and shader, the mesh
-    generator at 1/16 of the triangle count.  Cost is O(tiles x triangles), so Mtris/s is size-independent."""
-    import softrender_b200 as sr
-    from softrender_b200 import scenes
-    import oracle_binding as ob
-    w, h, nx, ny, layers, seed, near, far = CONFIGS[name]
-    mesh = scenes.make_grid(max(nx // 4, 1), max(ny // 4, 1), layers, seed=seed)
-    u = scenes.grid_uniforms(w, h)
-    vp = scenes.Viewport.new(w, h, near, far)
-    cores = os.cpu_count() or 1
-    fb = ob.OracleFramebuffer(w, h)
-    times = []
-    for it in range(warmup + steps):
+def native_oracle():
+    """Builds oracle/libsr_oracle_native.so (-O3 -march=native -ffp-contract=off) ON the host that
+    times it and points the binding at it; falls back to the portable -O3 build.  Returns the flag string for the record."""
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=300)
+        os.environ["SR_ORACLE_SO"] = os.path.join(ROOT, "oracle", "libsr_oracle_native.so")
+        return "-O3 -march=native -ffp-contract=off"
+    except Exception:
+        return "-O3 -ffp-contract=off (portable build; native build failed)"
+
+
+def workload_config(name: str, in_flight: int, world: int) -> dict:
+    """The `config` object of the JSON line; both arms print the same one (the CPU arm times this workload)."""
+    w, h, nx, ny, layers = CONFIGS[name][:5]
+    nverts = layers * (nx + 1) * (ny + 1)
+    return {"workload": name, "width": w, "height": h, "triangles": 2 * nx * ny * layers, "vertices": nverts,
+            "shader": "suzanne Blinn-Phong", "depth_test": True, "frames_in_flight": in_flight,
+            "parallelism": "1 GPU" if world == 1 else
+            f"frame batching: {world} GPUs each render whole frames of the workload (no data-path collective); the "
+            f"tile-sharded single frame (sort-last front end, sort-first resolve, NVLink merge + composite) is under 'sharded'",
+            "l2": "working set per frame (mesh + shaded vertices + framebuffer) exceeds the 126 MB L2; no flush needed"}
+
+
+class CpuFrame:
+    """One frame of a grid config on the restated reference CPU path (the oracle's threaded mode: thread pool, atomic
+    cursors, every 128x128 reference tile visits EVERY triangle -- fragment.rs:29,240-311), cut into `nslices` slices
+    of the reference's tile list: slice i = tiles i, i+nslices, ...  All slices together are exactly one full frame
+    of the full-size workload; the vertex stage (all vertices) and the clear run in slice 0."""
+
+    def __init__(self, name: str, nslices: int):
+        import softrender_b200 as sr
+        from softrender_b200 import scenes
+        import oracle_binding as ob
+        self.sr, self.ob = sr, ob
+        self.w, self.h, nx, ny, layers, seed, near, far = CONFIGS[name]
+        self.mesh = scenes.make_grid(nx, ny, layers, seed=seed)
+        self.u = scenes.grid_uniforms(self.w, self.h)
+        self.vp = scenes.Viewport.new(self.w, self.h, near, far)
+        self.cores = os.cpu_count() or 1
+        self.fb = ob.OracleFramebuffer(self.w, self.h)
+        self.nslices = nslices
+        self.ntiles = len(ob.tiles(self.w, self.h, 128, 128))
+        self.draw = None
+
+    def slice(self, i: int) -> float:
+        sr, ob = self.sr, self.ob
         t0 = time.perf_counter()
-        fb.clear(CLEAR)
-        d = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
-        d.tile = (128, 128)
-        d.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices, nthreads=cores)
-        d.fragment_run(fb, sr.FS_SUZANNE, u, nthreads=cores)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    t = float(np.mean(times))
-    return {"value": mesh.ntris / t / 1e6, "unit": "Mtris/s", "cores": cores, "kind": "port",
-            "sample": f"{name} frame {w}x{h}, generator at 1/16 triangles ({mesh.ntris} tris), 128x128 reference tiles, "
-                      f"{t:.2f} s/frame on {cores} threads"}, t, mesh.ntris
+        if i == 0 or self.draw is None:
+            self.fb.clear(CLEAR)
+            self.draw = ob.OracleDraw(sr.TRIANGLE, self.mesh.indices)
+            self.draw.tile = (128, 128)
+            self.draw.vertex_run_to_fragment(self.vp, sr.VS_SUZANNE, self.u, self.mesh.vertices, nthreads=self.cores)
+        self.draw.fragment_run(self.fb, sr.FS_SUZANNE, self.u, nthreads=self.cores, tile_slice=(i, self.nslices), keep_winner=True)
+        return time.perf_counter() - t0
+
+    def tiles_in(self, i: int) -> int:
+        return len(range(i, self.ntiles, self.nslices))
+
+
+def cpu_baseline_sample(name: str, flags: str, stride: int = 3):
+    """`cpu_baseline` of our arm: one slice (every `stride`-th reference tile, all triangles, plus the whole vertex stage) of
+    the full-size frame on all host threads, scaled by the tile fraction -- a bounded sample of about 10 s."""
+    f = CpuFrame(name, stride)
+    t = f.slice(0)
+    frac = f.tiles_in(0) / f.ntiles
+    return {"value": f.mesh.ntris * frac / t / 1e6, "unit": "Mtris/s", "cores": f.cores, "kind": "port",
+            "sample": f"{name} at full size ({f.mesh.ntris} triangles, {f.w}x{f.h}): vertex stage + {f.tiles_in(0)} of the "
+                      f"{f.ntiles} reference tiles (every {stride}th, each visiting every triangle), {t:.2f} s on {f.cores} "
+                      f"threads; value = triangles x tile fraction / time; oracle built {flags}"}
 
 
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.  The Rust crate
     cannot be built in this image (no rustc/cargo, un-vendored dependencies), so this is the oracle's threaded mode --
-    the restated reference CPU path with the reference's structure (thread pool, atomic cursors, every 128x128 tile
-    visits every primitive).  Each step is a bounded sample of the workload (see cpu_reference_sample)."""
+    the restated reference CPU path with the reference's structure.  The K timed steps are the K tile slices of ONE
+    full frame of the full-size workload (CpuFrame), so `value` = triangles / (sum of the K step times) is a whole-frame,
+    same-config measurement while each step stays bounded; the W warm-up steps are slices of a frame that is discarded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, h, nx, ny, layers = CONFIGS[args.config][:5]
+    flags = native_oracle()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    base, t, ntris = cpu_reference_sample(args.config, steps=steps, warmup=warmup)
+    f = CpuFrame(args.config, steps)
+    for i in range(warmup):
+        f.slice(i % steps)
+    f.draw = None
+    times = [f.slice(i) for i in range(steps)]
+    total = float(sum(times))
+    value = f.mesh.ntris / total / 1e6
+    base = {"value": value, "unit": "Mtris/s", "cores": f.cores, "kind": "port",
+            "sample": f"one full {args.config} frame ({f.mesh.ntris} triangles, {f.w}x{f.h}, all {f.ntiles} reference tiles of "
+                      f"128x128, each visiting every triangle) timed as {steps} tile slices: {total:.2f} s on {f.cores} threads; "
+                      f"oracle built {flags}"}
     line = {
-        "impl": "reference", "metric": f"Mtris/s at {w}x{h}", "value": base["value"], "unit": "Mtris/s",
-        "frames_per_s": base["value"] * 1e6 / (2 * nx * ny * layers),
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3,
+        "impl": "reference", "metric": f"Mtris/s at {f.w}x{f.h}", "value": value, "unit": "Mtris/s",
+        "frames_per_s": 1.0 / total,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": total / steps * 1e3, "frame_s": total,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "width": w, "height": h, "triangles": 2 * nx * ny * layers,
-                   "shader": "suzanne Blinn-Phong", "depth_test": True,
-                   "note": "restated reference CPU path on a bounded sample (the Rust reference cannot be built here)"},
+        "config": workload_config(args.config, args.in_flight, args.gpus),
         "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "restated reference CPU path (the Rust reference cannot be built here); `config` describes the workload, "
+                "its GPU-side keys (frames_in_flight, parallelism, l2) do not apply to this arm",
     }
     print(json.dumps(line))
 
@@ -514,7 +567,7 @@ def run_ours(args):
             except Exception as e:  # never let the side measurements take the headline line down
                 line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _, _ = cpu_reference_sample(args.config)
+            line["cpu_baseline"] = cpu_baseline_sample(args.config, native_oracle())
         print(json.dumps(line))
     barrier()
     for x in (pipe, gmesh, fb):

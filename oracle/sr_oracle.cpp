@@ -954,7 +954,15 @@ int so_draw_finish(so_draw *d, const sr_viewport *vp, int nthreads) {
 // FragmentShader::run (ref: src/pipeline/stages/fragment.rs:168-319)
 int so_draw_fragment_run(so_draw *d, so_framebuffer *fb, const so_raster_state *st, int fs, const sr_uniforms *u,
                          const so_texture *tex, int nthreads) {
-    if (!d || !fb || !st || !u) return SR_ERR_INVALID_ARGUMENT;
+    return so_draw_fragment_run_tiles(d, fb, st, fs, u, tex, nthreads, 0, 1);
+}
+
+// The same driver restricted to the tiles first, first+stride, first+2*stride, ... of the reference's tile list
+// (fragment.rs:188-216): every selected tile still visits every primitive (fragment.rs:268-311).  bench.py's CPU arm
+// times a whole frame as `stride` such slices, one per step; (0, 1) is the whole frame.
+int so_draw_fragment_run_tiles(so_draw *d, so_framebuffer *fb, const so_raster_state *st, int fs, const sr_uniforms *u,
+                               const so_texture *tex, int nthreads, uint64_t tile_first, uint64_t tile_stride) {
+    if (!d || !fb || !st || !u || tile_stride == 0) return SR_ERR_INVALID_ARGUMENT;
     if (d->space != 1) return SR_ERR_INVALID_STATE;
     if (fs < SR_FS_FLAT || fs > SR_FS_TEXTURE_UNLIT) return SR_ERR_INVALID_ARGUMENT;
     if (fs == SR_FS_TEXTURE_UNLIT && d->nk < 2) return SR_ERR_INVALID_ARGUMENT;
@@ -976,7 +984,7 @@ int so_draw_fragment_run(so_draw *d, so_framebuffer *fb, const so_raster_state *
     run_threads(nthreads < 1 ? 1 : nthreads, [&](int) {
         std::vector<float> scratch(S);
         while (true) {
-            const uint64_t ti = cursor.fetch_add(1, std::memory_order_relaxed);
+            const uint64_t ti = tile_first + cursor.fetch_add(1, std::memory_order_relaxed) * tile_stride;
             if (ti >= tiles.size()) break;
             const Tile &tile = tiles[ti];
             RasterArgs A;

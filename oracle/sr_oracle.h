@@ -87,6 +87,12 @@ int so_draw_finish(so_draw *, const sr_viewport *, int nthreads);
 int so_draw_fragment_run(so_draw *, so_framebuffer *, const so_raster_state *, int fs,
                          const sr_uniforms *, const so_texture *, int nthreads);
 
+/* FragmentShader::run over the tiles first, first+stride, ... of its tile list only (each still visits every primitive);
+ * (0, 1) = the whole frame.  bench.py's CPU arm times one frame as `stride` slices. */
+int so_draw_fragment_run_tiles(so_draw *, so_framebuffer *, const so_raster_state *, int fs,
+                               const sr_uniforms *, const so_texture *, int nthreads,
+                               uint64_t tile_first, uint64_t tile_stride);
+
 /* texture(t, coord, filter, edge) (src/texture.rs:14-18) with the arithmetic of full_example/src/texture.rs:25-84 */
 void so_texture_sample(const so_texture *, float u, float v, float out[4]);
 

@@ -59,6 +59,10 @@ class SoRasterState(ctypes.Structure):
 
 
 def build_oracle() -> str:
+    # bench.py's CPU arm points SR_ORACLE_SO at the -march=native build it made on the box it times (oracle/Makefile)
+    override = os.environ.get("SR_ORACLE_SO")
+    if override and os.path.exists(override):
+        return override
     src = os.path.join(ORACLE_DIR, "sr_oracle.cpp")
     if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
@@ -86,6 +90,7 @@ def lib():
         L.so_draw_finish.argtypes = [ctypes.c_void_p, ctypes.POINTER(Viewport), ctypes.c_int]
         L.so_draw_fragment_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(SoFramebuffer), ctypes.POINTER(SoRasterState),
                                            ctypes.c_int, ctypes.POINTER(Uniforms), ctypes.POINTER(SoTexture), ctypes.c_int]
+        L.so_draw_fragment_run_tiles.argtypes = L.so_draw_fragment_run.argtypes + [ctypes.c_uint64, ctypes.c_uint64]
         L.so_texture_sample.restype = None
         L.so_texture_sample.argtypes = [ctypes.POINTER(SoTexture), ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_float)]
         L.so_draw_count.restype = ctypes.c_uint64
@@ -199,16 +204,21 @@ class OracleDraw:
         self._ck(lib().so_draw_finish(self.h, ctypes.byref(viewport), nthreads))
         return self
 
-    def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1, sampler=None):
+    def fragment_run(self, fb: OracleFramebuffer, fs, uniforms, stencil_test=0, stencil_op=0, texture=None, nthreads=1, sampler=None,
+                     tile_slice=(0, 1), keep_winner=False):
+        """tile_slice = (first, stride): only the tiles first, first+stride, ... of the reference's tile list (each still
+        visits every primitive); the default is the whole frame."""
         tw, th = self.tile if self.tile else (max(fb.width, 1), max(fb.height, 1))
         st = SoRasterState(self.cull, self.blend, 1 if self.aa else 0, tw, th, stencil_test, stencil_op)
-        fb.winner[:] = 0  # winner plane = primitives of THIS draw
+        if not keep_winner:
+            fb.winner[:] = 0  # winner plane = primitives of THIS draw
         s = fb.struct()
         tex = None
         if texture is not None:
             tex, _keep = make_texture(texture, sampler)
-        self._ck(lib().so_draw_fragment_run(self.h, ctypes.byref(s), ctypes.byref(st), fs, ctypes.byref(uniforms),
-                                            ctypes.byref(tex) if tex is not None else None, nthreads))
+        self._ck(lib().so_draw_fragment_run_tiles(self.h, ctypes.byref(s), ctypes.byref(st), fs, ctypes.byref(uniforms),
+                                                  ctypes.byref(tex) if tex is not None else None, nthreads,
+                                                  tile_slice[0], tile_slice[1]))
         return self
 
     def data(self, which: int) -> np.ndarray:
