@@ -59,6 +59,40 @@ void *sr_context_stream(sr_context *);
 /* sort-first tile sharding: this context rasterises only the GPU tiles with
  * tile_index % world == rank (geometry stages still run for the whole mesh). */
 int sr_context_set_tile_shard(sr_context *, uint32_t rank, uint32_t world);
+
+/* ---- tile-sharded frames whose per-triangle front end is sharded too -------------------------------------
+ * The reference parallelises FragmentShader::run by tile (src/pipeline/stages/fragment.rs:240-253: a pool of
+ * threads pulls tiles from an atomic cursor, every tile visits every primitive).  Across GPUs the same split is
+ * "rank r owns the tiles with index % world == r" (sr_context_set_tile_shard); an sr_shard group additionally
+ * splits the per-triangle work: rank r rasterises the triangles [r*T/world, (r+1)*T/world) of an opaque draw into
+ * a full-frame key buffer of its own, and the owner of a tile pulls the other ranks' keys of that tile over
+ * NVLink inside its tile kernel (TMA bulk loads from peer-mapped memory), max-merges them and resolves.  The
+ * merged key -- max over all fragments of (depth, submission index) -- is exactly what one GPU reduces, so the
+ * frame is bit-identical to the single-GPU frame.  Ranks synchronise through progress words in each other's
+ * exchange block (no host round trip, no NCCL call per frame).
+ *
+ *   sr_shard_create   allocates this rank's exchange block (`lanes` key buffers + progress words) for frames
+ *                     of width x height; the context must already carry its (rank, world) tile shard.
+ *   sr_shard_export   64-byte CUDA IPC handle of the block (one process per GPU: all-gather these).
+ *   sr_shard_connect  opens the peers' handles (array of world x 64 bytes, entry `rank` ignored).
+ *   sr_shard_connect_local  the same for ranks that live in ONE process (tests; peers[] = world handles).
+ *   sr_context_attach_shard  eligible draws of this context (opaque triangles onto a freshly cleared frame,
+ *                     >= 65536 triangles) take the range-sharded path on `lane`; every rank must issue the same
+ *                     sequence of such draws per lane.  Contexts of one rank that work on different lanes keep
+ *                     independent frames in flight.  shard = NULL detaches.
+ *   sr_shard_status   0, or 1 + the peer a wait gave up on (a rank died or never issued its draw).
+ * Everything not eligible falls back to plain sort-first tile sharding, which needs no exchange. */
+typedef struct sr_shard sr_shard;
+int sr_shard_create(sr_context *, uint32_t width, uint32_t height, uint32_t lanes, sr_shard **out);
+int sr_shard_export(sr_shard *, void *handle64);
+int sr_shard_connect(sr_shard *, const void *handles64, uint32_t count);
+int sr_shard_connect_local(sr_shard *, sr_shard *const *peers, uint32_t count);
+int sr_context_attach_shard(sr_context *, sr_shard *, uint32_t lane);
+int sr_shard_status(sr_shard *, uint32_t *status);
+int sr_shard_destroy(sr_shard *);
+/* a second handle on the pixels of `src` for another context of the SAME process (a rank of a single-process
+ * shard group draws into rank 0's framebuffer through it); colour + depth only, does not own the memory */
+int sr_framebuffer_alias(sr_context *, sr_framebuffer *src, sr_framebuffer **out);
 /* tuning of the opaque triangle path: triangles whose frame-clamped bounding box holds at most
  * `area` pixels are rasterised per-triangle into the visibility buffer, the rest through per-tile lists.
  * area = 0 sends every triangle through the tile lists; area = SR_MICRO_AREA_AUTO (the default) lets the library pick

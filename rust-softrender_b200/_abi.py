@@ -16,6 +16,9 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
         "or make -C rust-softrender_b200/csrc). softrender_b200 has no CPU fallback.")
 
+# Range-sharded frames keep a spinning wait kernel on the stream; a lazily loaded kernel's first launch could stall behind it.
+# The library pre-loads what such frames launch (sr_shard_create); eager loading covers the rest when CUDA is not up yet.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 lib = ctypes.CDLL(LIB_PATH)
 
 c_void_p, c_int, c_u32, c_u64, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
@@ -65,6 +68,14 @@ SYMBOLS = {
     "sr_framebuffer_device_ptr": (c_void_p, [c_void_p]),
     "sr_framebuffer_ipc_export": (c_int, [c_void_p, c_void_p]),
     "sr_framebuffer_ipc_open": (c_int, [c_void_p, c_void_p, c_u32, c_u32, c_u32, pp]),
+    "sr_framebuffer_alias": (c_int, [c_void_p, c_void_p, pp]),
+    "sr_shard_create": (c_int, [c_void_p, c_u32, c_u32, c_u32, pp]),
+    "sr_shard_export": (c_int, [c_void_p, c_void_p]),
+    "sr_shard_connect": (c_int, [c_void_p, c_void_p, c_u32]),
+    "sr_shard_connect_local": (c_int, [c_void_p, pp, c_u32]),
+    "sr_context_attach_shard": (c_int, [c_void_p, c_void_p, c_u32]),
+    "sr_shard_status": (c_int, [c_void_p, u32p]),
+    "sr_shard_destroy": (c_int, [c_void_p]),
     "sr_mesh_create": (c_int, [c_void_p, c_void_p, c_u64, c_u32, c_void_p, c_u64, c_u32, pp]),
     "sr_mesh_destroy": (c_int, [c_void_p]),
     "sr_texture_create": (c_int, [c_void_p, u8p, c_u32, c_u32, pp]),

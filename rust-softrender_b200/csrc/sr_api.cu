@@ -77,6 +77,8 @@ struct sr_context {
     bool ev_front_valid = false;
     Buf zero_off;                                 // all-zero CSR offsets for empty primitive kinds
     uint32_t zero_off_tiles = 0;
+    struct sr_shard *shard = nullptr;             // range-sharded front end (sr_context_attach_shard)
+    uint32_t shard_lane = 0;
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);
     // Lifetime: every device buffer keeps its context alive (refs), so children destroyed after sr_context_destroy -- a
@@ -161,6 +163,24 @@ struct sr_framebuffer {
         for (int i = 0; i < 4; ++i) v.clear[i] = clear[i];
         return v;
     }
+};
+
+// Exchange block of one rank of a shard group (include/softrender_b200.h): per lane one full-frame key buffer and two
+// arrays of progress words (ready: "my keys of frame n are complete", done: "I have finished reading everybody's keys of
+// frame n"), then one error word.  One cudaMalloc so that one IPC handle exports it.
+struct sr_shard {
+    sr_context *ctx = nullptr;
+    uint32_t rank = 0, world = 1, width = 0, height = 0, ntx = 0, nty = 0, lanes = 1;
+    unsigned char *block = nullptr;
+    size_t vis_bytes = 0, lane_stride = 0, block_bytes = 0;
+    unsigned char *peer[SR_SHARD_MAX_WORLD] = {};  // peers' blocks mapped into this process (null: me / not connected)
+    bool peer_ipc[SR_SHARD_MAX_WORLD] = {};
+    bool connected = false;
+    uint32_t frame[8] = {};  // frames issued per lane
+    unsigned long long *vis(unsigned char *base, uint32_t lane) const { return reinterpret_cast<unsigned long long *>(base + lane * lane_stride); }
+    uint32_t *ready(unsigned char *base, uint32_t lane) const { return reinterpret_cast<uint32_t *>(base + lane * lane_stride + vis_bytes); }
+    uint32_t *done(unsigned char *base, uint32_t lane) const { return ready(base, lane) + SR_SHARD_MAX_WORLD; }
+    uint32_t *error() const { return reinterpret_cast<uint32_t *>(block + lanes * lane_stride); }
 };
 
 struct sr_mesh {
@@ -451,6 +471,37 @@ static int launch_opaque(sr_context *c, uint32_t ntiles_owned, const SrOpaquePar
     SR_LAUNCH(c, (k_tile_opaque<FS, EXTRA>), ntiles_owned, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
     return SR_OK;
 }
+// range-sharded frames: PHASE 1 (list sweep into the rank's own keys; no shading, one instantiation) and PHASE 2 (merge + resolve)
+static int launch_opaque_sweep(sr_context *c, uint32_t ntiles, const SrOpaqueParams &p) {
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<SR_FS_FLAT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_SMEM_BYTES));
+        configured[c->device & 15] = true;
+    }
+    SR_LAUNCH(c, (k_tile_opaque<SR_FS_FLAT, false, 1>), ntiles, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
+    return SR_OK;
+}
+template <int FS>
+static int launch_opaque_merge(sr_context *c, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_MERGE_SMEM_BYTES));
+        configured[c->device & 15] = true;
+    }
+    SR_LAUNCH(c, (k_tile_opaque<FS, false, 2>), ntiles_owned, SR_OPQ_THREADS, SR_OPQ_MERGE_SMEM_BYTES, p);
+    return SR_OK;
+}
+static int launch_opaque_merge_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+    switch (fs) {
+        case SR_FS_FLAT: return launch_opaque_merge<SR_FS_FLAT>(c, ntiles_owned, p);
+        case SR_FS_SUZANNE: return launch_opaque_merge<SR_FS_SUZANNE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE: return launch_opaque_merge<SR_FS_FULL_EXAMPLE>(c, ntiles_owned, p);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque_merge<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
+        case SR_FS_GREEN: return launch_opaque_merge<SR_FS_GREEN>(c, ntiles_owned, p);
+        case SR_FS_TEXTURE_UNLIT: return launch_opaque_merge<SR_FS_TEXTURE_UNLIT>(c, ntiles_owned, p);
+    }
+    return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
+}
 static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
     const bool extra = p.nlines + p.npoints > 0;
 #define SR_OPQ_CASE(F) case F: return extra ? launch_opaque<F, true>(c, ntiles_owned, p) : launch_opaque<F, false>(c, ntiles_owned, p)
@@ -478,10 +529,13 @@ struct PendingOpaque {
     Buf count, off, lcount, lids, lrects;
     sr_framebuffer *fb = nullptr;
     bool small = false;             // front end = one k_bin_small launch (re-run as a whole on overflow)
+    bool ranged = false;            // range-sharded frame: cannot be replayed (the peers have moved on) -- overflow is an error
     SrMicroParams mp;
 };
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q);
 static int launch_bin_small(sr_context *c, PendingOpaque *q);
+static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
+                                   const std::vector<Buf> &keep);
 // The same for the ordered tile pass: its three group lists (points, lines, triangles) live in grow-only arenas.
 struct PendingOrdered {
     cudaEvent_t counted = nullptr;
@@ -547,6 +601,10 @@ static int settle(sr_context *c) {
     SR_TRY(c->alloc((size_t)cap * 4, &bigger));
     c->list_arena = bigger;
     c->list_cap = cap;
+    if (q->ranged)
+        return sr_fail(SR_ERR_INVALID_STATE, "range-sharded draw: the per-tile lists of its large triangles (%u entries) exceeded the arena (%u); "
+                       "the frame is incomplete and cannot be replayed (the peers have moved on) -- the arena has been grown, draw the frame again",
+                       total, q->capacity);
     q->capacity = cap;
     q->op.list = bigger->as<uint32_t>();
     q->op.list_capacity = cap;
@@ -568,6 +626,9 @@ static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 102
 static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
                             const std::vector<Buf> &keep, bool extra) {
     const uint32_t ntiles = fb->ntx * fb->nty;
+    if (c->shard && c->shard->connected && !extra && fb->pending_clear && tp.ntris >= 65536u && (c->micro_auto || c->micro_area > 0) &&
+        c->shard->world == c->shard_world && c->shard->rank == c->shard_rank && c->shard->ntx == fb->ntx && c->shard->nty == fb->nty && ntiles >= c->shard_world)
+        return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep);
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
     if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
         record(c, 7);
@@ -643,6 +704,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         memset(&mp, 0, sizeof(mp));
         mp.src = tp.tris;
         mp.ntris = tp.ntris;
+        mp.tri_begin = 0; mp.tri_end = tp.ntris;
         mp.cull = cull;
         mp.width = fb->width; mp.height = fb->height; mp.ntx = fb->ntx; mp.nty = fb->nty;
         mp.shard_rank = c->shard_rank; mp.shard_world = c->shard_world;
@@ -714,6 +776,110 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     c->pending = q.release();
     return SR_OK;
 }
+// The opaque triangle path of a range-sharded frame (include/softrender_b200.h).  Per frame n of a lane:
+//   a. wait until every peer has finished reading my keys of frame n-1            (done words)
+//   b. hand the keys of the tiles I do not own back "far" (my own tiles were reset by my resolve)
+//   c. k_micro over MY triangle range, all tiles, global triangle ids; large triangles -> lists of all tiles -> PHASE 1 sweep
+//   d. publish "frame n ready" to every peer                                      (ready words)
+//   e. wait until every peer's keys of frame n are ready
+//   f. PHASE 2: merge the peers' keys of my tiles over NVLink + resolve + write-back (to rank 0's framebuffer)
+//   g. publish "frame n done"
+// All of it is enqueued on the context's stream; nothing synchronises with the host.
+static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
+                                   const std::vector<Buf> &keep) {
+    sr_shard *sh = c->shard;
+    const uint32_t lane = c->shard_lane, ntiles = fb->ntx * fb->nty;
+    const uint32_t n = ++sh->frame[lane];
+    unsigned long long *vis = sh->vis(sh->block, lane);
+    const unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+    SrShardPeers ready_peers, done_peers;
+    memset(&ready_peers, 0, sizeof(ready_peers));
+    memset(&done_peers, 0, sizeof(done_peers));
+    for (uint32_t p = 0; p < sh->world; ++p)
+        if (p != sh->rank) {
+            ready_peers.word[p] = sh->ready(sh->peer[p], lane);
+            done_peers.word[p] = sh->done(sh->peer[p], lane);
+        }
+    if (n > 1) SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->done(sh->block, lane), sh->world, sh->rank, n - 1, timeout_ns, sh->error());
+    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->ntx, sh->rank, sh->world, n == 1 ? 1u : 0u);
+    record(c, 7);
+    Buf count, off, lcount, lids, lrects;
+    const uint32_t t0 = (uint32_t)((uint64_t)tp.ntris * sh->rank / sh->world), t1 = (uint32_t)((uint64_t)tp.ntris * (sh->rank + 1) / sh->world);
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
+    SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
+    SR_TRY(c->alloc(4, &lcount));
+    SR_TRY(c->alloc((size_t)std::max(t1 - t0, 1u) * 4, &lids));
+    SR_TRY(c->alloc((size_t)std::max(t1 - t0, 1u) * 4, &lrects));
+    SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
+    SR_CUDA(cudaMemsetAsync(lcount->ptr, 0, 4, c->stream));
+    auto q = std::make_unique<PendingOpaque>();
+    SrMicroParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.src = tp.tris;
+    mp.ntris = tp.ntris;
+    mp.tri_begin = t0; mp.tri_end = t1;
+    mp.cull = cull;
+    mp.width = fb->width; mp.height = fb->height; mp.ntx = fb->ntx; mp.nty = fb->nty;
+    mp.shard_rank = 0; mp.shard_world = 1;  // every tile: ownership only matters from the merge on
+    mp.micro_area = c->micro_auto ? sr_micro_area_for(tp.ntris) : c->micro_area;
+    mp.vis = vis;
+    mp.large_count = lcount->as<uint32_t>();
+    mp.large_ids = lids->as<uint32_t>();
+    mp.large_rects = lrects->as<uint32_t>();
+    mp.tile_count = count->as<uint32_t>();
+    if (t1 > t0) {
+        const uint32_t grid = ceil_div(t1 - t0, SR_MICRO_THREADS);
+        if (c->micro_precheck & 2u) SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp);
+        else SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp);
+    }
+    record(c, 5);
+    SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
+    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
+    SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaEventCreateWithFlags(&q->counted, cudaEventDisableTiming));
+    SR_CUDA(cudaEventRecord(q->counted, c->stream));
+    if (!c->list_arena) {
+        c->list_cap = 1u << 20;
+        SR_TRY(c->alloc((size_t)c->list_cap * 4, &c->list_arena));
+    }
+    q->capacity = c->list_cap;
+    q->ranged = true;
+    q->fs = fs; q->owned = owned; q->ntiles = ntiles;
+    q->count = count; q->off = off; q->lcount = lcount; q->lids = lids; q->lrects = lrects;
+    q->keep = keep;
+    q->keep.push_back(c->list_arena);
+    q->fb = fb;
+    SrOpaqueParams &op = q->op;
+    memset(&op, 0, sizeof(op));
+    op.tris = tp.tris;
+    op.ntris = tp.ntris;
+    op.vis = vis;
+    op.tile_off = off->as<uint32_t>();
+    op.list = c->list_arena->as<uint32_t>();
+    op.list_capacity = c->list_cap;
+    op.ntiles = ntiles;
+    op.fb = fb->view();
+    op.fs = tp.fs;
+    // c (continued): large triangles of my range, every tile
+    op.shard_rank = 0; op.shard_world = 1;
+    op.reset_vis = 0;
+    SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(std::max(t1 - t0, 1u), 8), 148u * 4u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
+              lrects->as<uint32_t>(), fb->ntx, ntiles, 0u, 1u, off->as<uint32_t>(), count->as<uint32_t>(), c->list_arena->as<uint32_t>(), c->list_cap);
+    SR_TRY(launch_opaque_sweep(c, ntiles, op));
+    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, ready_peers, sh->rank, n);                                                    // d
+    SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->ready(sh->block, lane), sh->world, sh->rank, n, timeout_ns, sh->error());   // e
+    // f: my tiles, merged with every peer's keys
+    op.shard_rank = sh->rank; op.shard_world = sh->world;
+    op.reset_vis = 1;
+    for (uint32_t p = 0; p < sh->world; ++p)
+        if (p != sh->rank) op.peer_vis[op.npeers++] = sh->vis(sh->peer[p], lane);
+    if (owned) SR_TRY(launch_opaque_merge_fs(c, fs, owned, op));
+    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, done_peers, sh->rank, n);                                                     // g
+    fb->pending_clear = false;
+    c->pending = q.release();
+    return SR_OK;
+}
+
 // per-tile lists of the large triangles + the tile kernel (both skip themselves if the lists do not fit the arena)
 static int launch_bin_small(sr_context *c, PendingOpaque *q) {
     static bool configured[16] = {};
@@ -749,6 +915,42 @@ static int fs_nk(uint32_t fs) {
         case SR_FS_TEXTURE_UNLIT: return SrFsInfo<SR_FS_TEXTURE_UNLIT>::NK;
     }
     return -1;
+}
+
+// CUDA loads kernels lazily, and the first launch of a not-yet-loaded kernel can wait for the device to go idle.  A rank whose
+// wait kernel is spinning for a peer must never be held up like that (in a single process it would be a deadlock until the
+// wait's timeout), so every kernel a range-sharded frame can launch is loaded before the first such frame.
+template <class K>
+static void preload(K kernel) {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, kernel);
+}
+static void preload_ranged_kernels() {
+    preload(k_shard_wait);
+    preload(k_shard_signal);
+    preload(k_vis_clear_foreign);
+    preload(k_micro<false, true>);
+    preload(k_micro<false, false>);
+    preload(k_tile_offsets);
+    preload(k_large_fill);
+    preload(k_tile_opaque<SR_FS_FLAT, false, 1>);
+    preload(k_tile_opaque<SR_FS_FLAT, false, 2>);
+    preload(k_tile_opaque<SR_FS_SUZANNE, false, 2>);
+    preload(k_tile_opaque<SR_FS_FULL_EXAMPLE, false, 2>);
+    preload(k_tile_opaque<SR_FS_FULL_EXAMPLE_TEXTURED, false, 2>);
+    preload(k_tile_opaque<SR_FS_GREEN, false, 2>);
+    preload(k_tile_opaque<SR_FS_TEXTURE_UNLIT, false, 2>);
+    preload(k_vertex<SR_VS_SUZANNE>);
+    preload(k_vertex<SR_VS_FULL_EXAMPLE>);
+    preload(k_vertex_passthrough);
+    preload(k_normalize);
+    preload(k_aos_to_planes);
+    preload(k_records_to_planes);
+    preload(k_fb_fill);
+    preload(k_scan_reduce);
+    preload(k_scan_sums);
+    preload(k_scan_apply);
+    cudaGetLastError();
 }
 
 // =========================================================================================================
@@ -825,6 +1027,14 @@ int sr_context_create(int device, sr_context **out) {
     if (e != cudaSuccess) {
         delete c;
         return sr_fail(SR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    // pinned words for device->host counters: allocated here, not lazily -- a page-locked allocation may synchronise with
+    // the device, which must not happen while a peer's wait kernel is spinning (range-sharded frames)
+    e = cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return sr_fail(SR_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
     }
     *out = c;
     return SR_OK;
@@ -1134,6 +1344,129 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
     fb->is_peer = true;
     fb->pending_clear = false;
     *out = fb;
+    return SR_OK;
+}
+
+int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **out) {
+    if (!c || !src || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (src->format != SR_FB_RGBAF32_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "aliased framebuffers carry colour+depth only");
+    SR_TRY(materialize_clear(src));
+    SR_CUDA(cudaSetDevice(src->ctx->device));
+    SR_CUDA(cudaStreamSynchronize(src->ctx->stream));
+    if (c->device != src->ctx->device) {
+        SR_CUDA(cudaSetDevice(c->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return sr_fail(SR_ERR_CUDA, "peer access %d -> %d: %s", c->device, src->ctx->device, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    auto *fb = new sr_framebuffer();
+    fb->ctx = c;
+    fb->width = src->width; fb->height = src->height; fb->format = src->format;
+    fb->ntx = src->ntx; fb->nty = src->nty;
+    fb->aos = src->aos;
+    fb->aos_buf = src->aos_buf;  // shares ownership: the pixels outlive either handle
+    fb->pending_clear = false;
+    *out = fb;
+    return SR_OK;
+}
+
+// ---- shard groups (range-sharded front end) --------------------------------------------------------------
+int sr_shard_create(sr_context *c, uint32_t width, uint32_t height, uint32_t lanes, sr_shard **out) {
+    if (!c || !out || lanes == 0 || lanes > 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad shard group");
+    if (c->shard_world < 2 || c->shard_world > SR_SHARD_MAX_WORLD)
+        return sr_fail(SR_ERR_INVALID_STATE, "set the context's tile shard (2..%d ranks) before creating its shard group", SR_SHARD_MAX_WORLD);
+    SR_CUDA(cudaSetDevice(c->device));
+    preload_ranged_kernels();
+    auto sh = std::make_unique<sr_shard>();
+    sh->ctx = c;
+    sh->rank = c->shard_rank; sh->world = c->shard_world;
+    sh->width = width; sh->height = height; sh->lanes = lanes;
+    sh->ntx = ceil_div(width, SR_TILE_W); sh->nty = ceil_div(height, SR_TILE_H);
+    sh->vis_bytes = (size_t)sh->ntx * sh->nty * SR_TILE_PIXELS * 8;
+    sh->lane_stride = sh->vis_bytes + 256;
+    sh->block_bytes = sh->lane_stride * lanes + 256;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sh->block_bytes);
+    if (e != cudaSuccess) return sr_fail(SR_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) for the exchange block failed: %s", sh->block_bytes, cudaGetErrorString(e));
+    sh->block = reinterpret_cast<unsigned char *>(p);
+    for (uint32_t l = 0; l < lanes; ++l) SR_CUDA(cudaMemsetAsync(sh->block + l * sh->lane_stride + sh->vis_bytes, 0, 256, c->stream));
+    SR_CUDA(cudaMemsetAsync(sh->error(), 0, 256, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    ++c->refs;
+    *out = sh.release();
+    return SR_OK;
+}
+int sr_shard_export(sr_shard *sh, void *handle64) {
+    if (!sh || !handle64) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_CUDA(cudaSetDevice(sh->ctx->device));
+    cudaIpcMemHandle_t h;
+    SR_CUDA(cudaIpcGetMemHandle(&h, sh->block));
+    memcpy(handle64, &h, 64);
+    return SR_OK;
+}
+int sr_shard_connect(sr_shard *sh, const void *handles64, uint32_t count) {
+    if (!sh || !handles64) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (count != sh->world) return sr_fail(SR_ERR_INVALID_ARGUMENT, "%u handles for a group of %u ranks", count, sh->world);
+    if (sh->connected) return sr_fail(SR_ERR_INVALID_STATE, "shard group already connected");
+    SR_CUDA(cudaSetDevice(sh->ctx->device));
+    for (uint32_t p = 0; p < sh->world; ++p) {
+        if (p == sh->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const unsigned char *>(handles64) + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        SR_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        sh->peer[p] = reinterpret_cast<unsigned char *>(ptr);
+        sh->peer_ipc[p] = true;
+    }
+    sh->connected = true;
+    return SR_OK;
+}
+int sr_shard_connect_local(sr_shard *sh, sr_shard *const *peers, uint32_t count) {
+    if (!sh || !peers) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (count != sh->world) return sr_fail(SR_ERR_INVALID_ARGUMENT, "%u peers for a group of %u ranks", count, sh->world);
+    if (sh->connected) return sr_fail(SR_ERR_INVALID_STATE, "shard group already connected");
+    SR_CUDA(cudaSetDevice(sh->ctx->device));
+    for (uint32_t p = 0; p < sh->world; ++p) {
+        if (p == sh->rank) continue;
+        const sr_shard *o = peers[p];
+        if (!o || o->rank != p || o->world != sh->world || o->block_bytes != sh->block_bytes || o->lanes != sh->lanes)
+            return sr_fail(SR_ERR_INVALID_ARGUMENT, "peer %u does not belong to this group", p);
+        if (o->ctx->device != sh->ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return sr_fail(SR_ERR_CUDA, "peer access %d -> %d: %s", sh->ctx->device, o->ctx->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        sh->peer[p] = o->block;
+    }
+    sh->connected = true;
+    return SR_OK;
+}
+int sr_context_attach_shard(sr_context *c, sr_shard *sh, uint32_t lane) {
+    if (!c) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(settle(c));
+    if (!sh) { c->shard = nullptr; return SR_OK; }
+    if (lane >= sh->lanes) return sr_fail(SR_ERR_INVALID_ARGUMENT, "lane %u of %u", lane, sh->lanes);
+    if (c->device != sh->ctx->device) return sr_fail(SR_ERR_INVALID_STATE, "the shard group lives on device %d", sh->ctx->device);
+    if (c->shard_rank != sh->rank || c->shard_world != sh->world) return sr_fail(SR_ERR_INVALID_STATE, "the context's tile shard is %u/%u, the group's %u/%u", c->shard_rank, c->shard_world, sh->rank, sh->world);
+    c->shard = sh;
+    c->shard_lane = lane;
+    return SR_OK;
+}
+int sr_shard_status(sr_shard *sh, uint32_t *status) {
+    if (!sh || !status) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_CUDA(cudaSetDevice(sh->ctx->device));
+    SR_CUDA(cudaMemcpy(status, sh->error(), 4, cudaMemcpyDeviceToHost));
+    return SR_OK;
+}
+int sr_shard_destroy(sr_shard *sh) {
+    if (!sh) return SR_OK;
+    cudaSetDevice(sh->ctx->device);
+    cudaDeviceSynchronize();
+    for (uint32_t p = 0; p < SR_SHARD_MAX_WORLD; ++p)
+        if (sh->peer[p] && sh->peer_ipc[p]) cudaIpcCloseMemHandle(sh->peer[p]);
+    cudaFree(sh->block);
+    ctx_unref(sh->ctx);
+    delete sh;
     return SR_OK;
 }
 

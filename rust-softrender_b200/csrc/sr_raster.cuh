@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(SR_BIN_THREADS) k_bin_setup(const SrBinParams 
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // grid covers whole warps
     uint32_t rect = SR_RECT_INVALID;
     if (t < p.nprims) rect = sr_prim_rect<NV>(p, t);
-    if (t < ((p.nprims + 31u) & ~31u)) p.rects[t] = rect;  // the rect array is padded to whole groups (bulk-copied per group)
+    if (t < ((p.nprims + 31u) & ~31u)) p.rects[t] = rect;  // the rect array is padded to whole groups (a warp reads a group's 32 rectangles with one coalesced load)
     sr_bin_group<false>(p, rect, t >> 5);
 }
 // pass 2: fill the per-tile group lists (order inside a list is arbitrary; consumers that need
@@ -447,18 +447,7 @@ __device__ __forceinline__ void sr_bulk_g2s(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void sr_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sr_smem_u32(src)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void sr_bulk_commit_wait_all() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
 __device__ __forceinline__ void sr_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void sr_cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sr_smem_u32(dst)), "l"(src) : "memory");
-}
-// makes `bar` receive one (pre-counted) arrival when all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void sr_cp_async_arrive_noinc(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sr_smem_u32(bar)) : "memory");
-}
 
 struct SrTileParams {
     SrPrimSource tris, lines, points;
@@ -503,6 +492,7 @@ __device__ __forceinline__ uint32_t sr_vis_index(uint32_t px, uint32_t py, uint3
 struct SrMicroParams {
     SrPrimSource src;
     uint32_t ntris, cull;
+    uint32_t tri_begin, tri_end;  // k_micro walks [tri_begin, tri_end) (the whole draw unless the front end is range-sharded, section 6)
     uint32_t width, height, ntx, nty;
     uint32_t shard_rank, shard_world;
     uint32_t micro_area;          // bbox pixels up to which a triangle is rasterised by k_micro (0: none)
@@ -526,6 +516,53 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
         }
         *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(px, py, fb.ntx)) =
             make_ulonglong2((unsigned long long)dk0 << 32, (unsigned long long)dk1 << 32);
+    }
+}
+
+// ---- range-sharded front end: every rank rasterises its own triangle range into a full-frame
+// key buffer of its own; the tile's owner pulls the other ranks' keys over NVLink and max-merges them (k_tile_opaque,
+// PHASE 2).  Keys of tiles the rank does not own are handed back "far" here (its own tiles are reset by its resolve).
+__global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *vis, uint32_t ntx, uint32_t shard_rank, uint32_t shard_world,
+                                                           uint32_t all) {
+    const uint32_t tile = blockIdx.x;
+    if (!all && tile % shard_world == shard_rank) return;
+    const uint32_t x0 = (tile % ntx) * SR_TILE_W, y0 = (tile / ntx) * SR_TILE_H;
+    for (uint32_t i = threadIdx.x * 2; i < SR_TILE_PIXELS; i += 512)
+        *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(x0 + i % SR_TILE_W, y0 + i / SR_TILE_W, ntx)) =
+            make_ulonglong2(SR_VIS_FAR_KEY, SR_VIS_FAR_KEY);
+}
+// Cross-rank progress words live in every rank's exchange block; a rank publishes its frame number by storing it into
+// slot `me` of every peer's block (system-scope release after a system fence: everything earlier kernels of this stream
+// wrote is visible to a peer that acquires the word), and waits by polling its OWN block.
+#define SR_SHARD_MAX_WORLD 8
+struct SrShardPeers {
+    uint32_t *word[SR_SHARD_MAX_WORLD];  // peer p's copy of the word array (null for p == me / absent)
+};
+__global__ void k_shard_signal(const SrShardPeers peers, uint32_t me, uint32_t value) {
+    const uint32_t p = threadIdx.x;
+    if (p >= SR_SHARD_MAX_WORLD || peers.word[p] == nullptr) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.word[p] + me), "r"(value) : "memory");
+}
+// spins until every peer's word is >= value; gives up after `timeout_ns` (a peer died) and raises *error so that the host
+// reports a failure instead of hanging the GPU
+__global__ void k_shard_wait(const uint32_t *words, uint32_t world, uint32_t me, uint32_t value, unsigned long long timeout_ns,
+                             uint32_t *error) {
+    const uint32_t p = threadIdx.x;
+    if (p >= world || p == me) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(words + p) : "memory");
+        if ((int32_t)(v - value) >= 0) return;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicExch(error, 1u + p);
+            return;
+        }
+        __nanosleep(200);
     }
 }
 
@@ -788,15 +825,15 @@ __device__ __forceinline__ void sr_micro_triangle(const SrMicroParams &p, uint32
 // one thread per triangle, in submission order
 template <bool PRECHECK, bool EARLYZ>
 __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro(const __grid_constant__ SrMicroParams p) {
-    const uint32_t t = blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
+    const uint32_t t = p.tri_begin + blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
     float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
-    if (t < p.ntris) {
+    if (t < p.tri_end) {
         const SrVertexSet *vs;
         uint32_t vi[3];
         sr_prim_vertices<3>(p.src, t, vs, vi);
         A = __ldg(vs->pos + vi[0]); B = __ldg(vs->pos + vi[1]); C = __ldg(vs->pos + vi[2]);
     }
-    sr_micro_triangle<PRECHECK, EARLYZ>(p, t, t < p.ntris, A, B, C, threadIdx.x & 31);
+    sr_micro_triangle<PRECHECK, EARLYZ>(p, t, t < p.tri_end, A, B, C, threadIdx.x & 31);
 }
 
 // Small draws (a model of a few thousand triangles): the whole front end -- triangle fetch, cull, tile rectangles,
@@ -1058,6 +1095,10 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
 #define SR_OPQ_STAGE_BYTES (SR_OPQ_WARPS * 2 * SR_OPQ_STAGE_FLOATS * 4)
 #define SR_OPQ_REGION_BYTES (SR_OPQ_SWEEP_BYTES > SR_OPQ_STAGE_BYTES ? SR_OPQ_SWEEP_BYTES : SR_OPQ_STAGE_BYTES)
 #define SR_OPQ_SMEM_BYTES (SR_TILE_PIXELS * 8 + SR_OPQ_REGION_BYTES + SR_TILE_W * 8 + 16)
+// PHASE 2 (merge + resolve of a range-sharded frame): a second 16 KB staging buffer for a peer's keys + two mbarriers
+#define SR_OPQ_MERGE_OFFSET ((SR_OPQ_SMEM_BYTES + 127) / 128 * 128)
+#define SR_OPQ_MERGE_SMEM_BYTES (SR_OPQ_MERGE_OFFSET + SR_TILE_PIXELS * 8 + 16)
+static_assert(SR_OPQ_REGION_BYTES >= SR_TILE_PIXELS * 8, "the sweep/staging region doubles as the first peer-key buffer");
 static_assert(SR_TILE_W % 32 == 0, "a warp resolves 32 consecutive pixels of one tile row");
 
 struct SrOpaqueParams {
@@ -1076,9 +1117,19 @@ struct SrOpaqueParams {
     SrPrimSource lines, points;
     uint32_t nlines, npoints;
     uint32_t line_base, point_base;  // canonical numbers of the first line / point (winner plane)
+    // PHASE 2 only: the other ranks' key buffers (peer-mapped over NVLink, same layout as `vis`)
+    const unsigned long long *peer_vis[SR_SHARD_MAX_WORLD - 1];
+    uint32_t npeers;
 };
 
-template <int FS, bool EXTRA>
+// PHASE 0: the whole pass (keys -> list sweep -> resolve -> write-back).
+// PHASE 1: range-sharded front end, list sweep only: the tile's keys (this rank's own buffer) take the rank's large
+//          triangles and go back to the buffer; no resolve.  CTAs of tiles with an empty list return at once.
+// PHASE 2: range-sharded merge + resolve: the owner of the tile loads its own keys and, double-buffered, every peer's
+//          keys of the same tile with TMA bulk copies from peer-mapped memory, max-merges them in shared memory and
+//          resolves -- the exchange is fused into the resolve, there is no staging copy in HBM and no separate collective.
+//          The merged key is exactly the key one GPU would have reduced: max over all fragments of (depth key, primitive+1).
+template <int FS, bool EXTRA, int PHASE = 0>
 __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrOpaqueParams p) {
     extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
@@ -1090,7 +1141,10 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
     if (p.tile_off[p.ntiles] > p.list_capacity) return;
-    const uint32_t lbeg = p.tile_off[tile], L = p.tile_off[tile + 1] - lbeg;
+    const uint32_t lbeg = p.tile_off[tile];
+    uint32_t L = p.tile_off[tile + 1] - lbeg;
+    if (PHASE == 2) L = 0;  // the lists were swept into the keys by every rank's PHASE 1
+    if (PHASE == 1 && L == 0) return;
     if (L == 0 && !p.fb.pending_clear && p.vis == nullptr) return;  // nothing to draw, contents already in HBM
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t W = p.fb.width, H = p.fb.height;
@@ -1125,10 +1179,48 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         __syncthreads();
     }
 
+    if (PHASE == 2) {
+        unsigned long long *pbuf[2] = {reinterpret_cast<unsigned long long *>(stage_all),
+                                       reinterpret_cast<unsigned long long *>(sr_smem + SR_OPQ_MERGE_OFFSET)};
+        uint64_t *mb = reinterpret_cast<uint64_t *>(sr_smem + SR_OPQ_MERGE_OFFSET + SR_TILE_PIXELS * 8);
+        if (tid == 0) {
+            sr_mbar_init(mb + 0, 1);
+            sr_mbar_init(mb + 1, 1);
+            sr_mbar_init_fence();
+        }
+        __syncthreads();
+        // warp 0 issues: one 512 B bulk copy per tile row straight from the peer's HBM over NVLink
+        auto issue = [&](uint32_t k) {
+            if (warp != 0) return;
+            if (lane == 0) sr_mbar_arrive_expect_tx(mb + (k & 1u), SR_TILE_PIXELS * 8);
+            __syncwarp();
+            static_assert(SR_TILE_H <= 32, "one lane per tile row");
+            if (lane < SR_TILE_H)
+                sr_bulk_g2s(pbuf[k & 1u] + lane * SR_TILE_W, p.peer_vis[k] + sr_vis_index(x0, y0 + lane, p.fb.ntx), SR_TILE_W * 8, mb + (k & 1u));
+        };
+        for (uint32_t k = 0; k < p.npeers && k < 2; ++k) issue(k);
+        for (uint32_t k = 0; k < p.npeers; ++k) {
+            sr_mbar_wait(mb + (k & 1u), (k >> 1) & 1u);
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(pbuf[k & 1u]);
+            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(keys);
+            for (uint32_t i = tid; i < SR_TILE_PIXELS / 2; i += SR_OPQ_THREADS) {
+                const ulonglong2 a = src[i];
+                ulonglong2 b = dst[i];
+                b.x = a.x > b.x ? a.x : b.x;
+                b.y = a.y > b.y ? a.y : b.y;
+                dst[i] = b;
+            }
+            sr_fence_proxy_async();
+            __syncthreads();
+            if (k + 2 < p.npeers) issue(k + 2);
+        }
+        if (p.npeers == 0) __syncthreads();
+    }
+
     const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;  // last pixel of the tile in the frame
 
     // ---------------- the tile's triangle list: 32 triangles per warp step, setup per lane ----------------
-    if (L > 0) {
+    if (PHASE != 2 && L > 0) {
         auto emit = [&](uint32_t px, uint32_t py, unsigned long long key) {
             unsigned long long *slot = keys + (py - y0) * SR_TILE_W + (px - x0);
             if (key > *reinterpret_cast<volatile unsigned long long *>(slot)) atomicMax(slot, key);
@@ -1249,6 +1341,18 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         __syncthreads();
     }
 
+    if (PHASE == 1) {
+        // the swept keys go back to this rank's buffer (the sweep ended with a CTA barrier); a full wait, not .read: the
+        // stores must have landed before the stream's next kernel publishes the frame number to the peers
+        sr_fence_proxy_async();
+        __syncthreads();
+        if (tid < SR_TILE_H) {
+            sr_bulk_s2g(p.vis + sr_vis_index(x0, y0 + tid, p.fb.ntx), keys + tid * SR_TILE_W, SR_TILE_W * 8);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
     // ---------------- resolve: shade every pixel once, write colour + depth (+winner) to HBM once ----------------
     // A warp finishes 32 consecutive pixels of a tile row at a time.  When the whole frame is being (re)written
     // (pending clear) the 640 B of AoS pixels are staged in shared memory and leave with one TMA bulk store.

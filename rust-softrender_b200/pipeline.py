@@ -233,11 +233,61 @@ class RenderBuffer:
         check(lib.sr_framebuffer_ipc_export(self.h, buf))
         return buf.raw
 
+    def alias(self, ctx: Context) -> "RenderBuffer":
+        """A second handle on the same pixels for another context of this process (sr_framebuffer_alias)."""
+        h = ctypes.c_void_p()
+        check(lib.sr_framebuffer_alias(ctx.h, self.h, ctypes.byref(h)))
+        return RenderBuffer(ctx, h, self.width, self.height, FB_RGBAF32_DF32)
+
     @staticmethod
     def ipc_open(ctx: Context, handle: bytes, width: int, height: int) -> "RenderBuffer":
         h = ctypes.c_void_p()
         check(lib.sr_framebuffer_ipc_open(ctx.h, ctypes.create_string_buffer(handle, 64), width, height, FB_RGBAF32_DF32, ctypes.byref(h)))
         return RenderBuffer(ctx, h, width, height, FB_RGBAF32_DF32)
+
+
+class ShardGroup:
+    """This rank's end of a shard group (sr_shard): tile-sharded frames whose per-triangle front end is sharded by
+    triangle range as well; the tile owner merges the ranks' keys over NVLink inside its tile kernel
+    (include/softrender_b200.h; the reference's tile-parallel loop is src/pipeline/stages/fragment.rs:240-253).
+    The context must already carry its tile shard (Context.set_tile_shard)."""
+
+    def __init__(self, ctx: Context, width: int, height: int, lanes: int = 1):
+        h = ctypes.c_void_p()
+        check(lib.sr_shard_create(ctx.h, width, height, lanes, ctypes.byref(h)))
+        self.ctx, self.h, self.lanes = ctx, h, lanes
+
+    def export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        check(lib.sr_shard_export(self.h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the exported handles of all ranks in rank order (one process per GPU)."""
+        blob = ctypes.create_string_buffer(b"".join(bytes(x).ljust(64, b"\0") for x in handles), 64 * len(handles))
+        check(lib.sr_shard_connect(self.h, blob, len(handles)))
+
+    def connect_local(self, groups):
+        """groups: the ShardGroup of every rank in rank order, all living in this process (tests)."""
+        arr = (ctypes.c_void_p * len(groups))(*[g.h for g in groups])
+        check(lib.sr_shard_connect_local(self.h, arr, len(groups)))
+
+    def attach(self, ctx: Context, lane: int = 0):
+        check(lib.sr_context_attach_shard(ctx.h, self.h, lane))
+
+    @staticmethod
+    def detach(ctx: Context):
+        check(lib.sr_context_attach_shard(ctx.h, None, 0))
+
+    def status(self) -> int:
+        n = ctypes.c_uint32()
+        check(lib.sr_shard_status(self.h, ctypes.byref(n)))
+        return n.value
+
+    def destroy(self):
+        if self.h:
+            lib.sr_shard_destroy(self.h)
+            self.h = None
 
 
 class Mesh:
