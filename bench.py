@@ -5,10 +5,12 @@
 
 A "step" is one frame: clear + vertex stage + binning + tile rasterisation of the synthetic 10M-triangle
 shaded mesh at 3840x2160 (config 3) with the mesh already resident in HBM.
-N>1 (torchrun, one rank per GPU): sort-first tile sharding -- geometry replicated, GPU tiles interleaved over
-the ranks, every rank's tile rasteriser stores its finished tiles straight into rank 0's framebuffer over
-NVLink peer memory (no staging copy, no separate collective); NCCL carries only the barrier and the timing
-reduction.  Prints ONE JSON line (rank 0).
+N>1 (torchrun, one rank per GPU): `value` is frame batching (every GPU renders whole frames, no data-path
+collective; "weak" scaling).  The north_star's split of ONE frame -- tiles sharded over the GPUs, every finished
+tile stored straight into rank 0's framebuffer over NVLink peer memory, and the per-triangle front end sharded by
+triangle range with the keys merged over NVLink inside the tile kernel -- is measured beside it for config 3
+(`sharded`) and config 4 (`sharded_config4`) and compared bit for bit with the single-GPU frame.  NCCL carries
+only rendezvous, barriers between batches and the timing reduction.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -75,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -318,6 +320,165 @@ def other_configs(ctx):
     return out
 
 
+def nvlink_counters(index: int):
+    """Sum of the NVLink data counters of one GPU (nvidia-smi nvlink -gt d), bytes: (tx, rx) or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=10).stdout
+        tx = rx = 0
+        seen = False
+        for ln in out.splitlines():
+            ln = ln.strip()
+            if "Data Tx" in ln or "Data Rx" in ln:
+                kib = float(ln.split(":")[-1].strip().split()[0])
+                seen = True
+                if "Data Tx" in ln:
+                    tx += int(kib * 1024)
+                else:
+                    rx += int(kib * 1024)
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
+def run_sharded(name, world, rank, local_rank, P, sr, dist, barrier, max_over_ranks, nframes):
+    """ONE frame split over the GPUs the way the north_star asks: the framebuffer is sharded by screen tiles (tile i belongs
+    to rank i % N, the reference's tile-parallel loop fragment.rs:240-253 across GPUs), every finished tile is stored
+    straight into rank 0's framebuffer over NVLink, and -- new in round 2 -- the per-triangle front end is sharded by
+    triangle range: the tile owner merges the ranks' keys over NVLink inside its tile kernel (sr_shard).  Timed with CUDA
+    events on the lanes' streams over `nframes` pipelined frames (two frames in flight = two lanes, no host barrier inside
+    the batch), max over ranks; the composited frames are compared bit for bit with the single-GPU frame."""
+    import torch
+    w, h, mesh, u, vp = build_scene(name)
+    ntris = mesh.ntris
+    lanes = 2
+    ctxs = [P.Context(local_rank) for _ in range(lanes)]
+    for c in ctxs:
+        c.set_tile_shard(rank, world)
+    single_frame, single_ms = None, None
+    if rank == 0:  # the unsharded frame on one GPU: the bit-exact yardstick and the time the speed-up is quoted against
+        c1 = P.Context(local_rank)
+        fb1 = P.RenderBuffer.with_dimensions(c1, w, h)
+        p1 = P.Pipeline.from_framebuffer(fb1, u)
+        m1 = P.Mesh(c1, mesh)
+        st1 = torch.cuda.ExternalStream(c1.stream, device=torch.device("cuda", local_rank))
+
+        def one():
+            fb1.clear(CLEAR)
+            p1.render_mesh(sr.TRIANGLE, m1).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+        for _ in range(3):
+            one()
+        c1.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st1)
+        for _ in range(10):
+            one()
+        e1.record(st1)
+        c1.synchronize()
+        single_ms = e0.elapsed_time(e1) / 10
+        single_frame = fb1.download()
+        for x in (p1, m1, fb1):
+            x.destroy()
+        c1.close()
+    group = P.ShardGroup(ctxs[0], w, h, lanes)
+    handles = [None] * world
+    dist.all_gather_object(handles, group.export())
+    group.connect(handles)
+    for lane, c in enumerate(ctxs):
+        group.attach(c, lane)
+    targets = [P.RenderBuffer.with_dimensions(ctxs[lane], w, h) for lane in range(lanes)] if rank == 0 else None
+    th = [[t.ipc_export() for t in targets] if rank == 0 else None]
+    dist.broadcast_object_list(th, src=0)
+    fbs = targets if rank == 0 else [P.RenderBuffer.ipc_open(ctxs[lane], th[0][lane], w, h) for lane in range(lanes)]
+    pipes = [P.Pipeline.from_framebuffer(fbs[lane], u) for lane in range(lanes)]
+    meshes = [P.Mesh(ctxs[lane], mesh) for lane in range(lanes)]
+    streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local_rank)) for c in ctxs]
+
+    def frame(lane):
+        fbs[lane].clear(CLEAR)
+        pipes[lane].render_mesh(sr.TRIANGLE, meshes[lane]).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+
+    def batch(nlanes, n):
+        for c in ctxs:
+            c.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(nlanes)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(nlanes)]
+        for lane in range(nlanes):
+            starts[lane].record(streams[lane])
+        for f in range(n):
+            frame(f % nlanes)
+        for lane in range(nlanes):
+            ends[lane].record(streams[lane])
+        for c in ctxs:
+            c.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(max(starts[0].elapsed_time(e) for e in ends)) / n
+
+    for f in range(2 * lanes):
+        frame(f % lanes)
+    nv0 = nvlink_counters(local_rank) if rank == 0 else None
+    ms_pipelined = batch(lanes, nframes)
+    nv1 = nvlink_counters(local_rank) if rank == 0 else None
+    ms_latency = batch(1, max(nframes // 2, 4))
+    stage_ms = None
+    if os.environ.get("SR_SHARD_STAGES"):  # diagnosis: per-stage device times of this rank's part of a sharded frame
+        acc = {}
+        ctxs[0].set_stage_timing(True)
+        for _ in range(4):
+            frame(0)
+            for k, v in ctxs[0].stage_times().items():
+                acc[k] = acc.get(k, 0.0) + v / 4
+            barrier()
+        ctxs[0].set_stage_timing(False)
+        allst = [None] * world
+        dist.all_gather_object(allst, {k: round(v, 4) for k, v in acc.items()})
+        stage_ms = allst
+    status = group.status()
+    st = torch.tensor([status], device="cuda", dtype=torch.int64)
+    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    same = None
+    if rank == 0:
+        same = all(bool(np.array_equal(t.download().view(np.uint32), single_frame.view(np.uint32))) for t in targets)
+    barrier()
+    for c in ctxs:
+        P.ShardGroup.detach(c)
+    for x in pipes + meshes:
+        x.destroy()
+    if rank != 0:
+        for fb in fbs:
+            fb.destroy()
+    barrier()
+    if rank == 0:
+        for fb in fbs:
+            fb.destroy()
+    group.destroy()
+    for c in ctxs:
+        c.close()
+    if rank != 0:
+        return None
+    ingest = w * h * 20 * (world - 1) / world
+    rec = {"config": name, "width": w, "height": h, "triangles": ntris, "n_gpus": world,
+           "ms_per_frame": ms_pipelined, "Mtris_per_s": ntris / (ms_pipelined * 1e-3) / 1e6, "frames_per_s": 1e3 / ms_pipelined,
+           "frames_in_flight": lanes, "frames_timed": nframes,
+           "ms_per_frame_one_in_flight": ms_latency,
+           "single_gpu_ms_per_frame": single_ms, "speedup_vs_single_gpu": single_ms / ms_pipelined,
+           "speedup_vs_single_gpu_one_in_flight": single_ms / ms_latency,
+           "identical_to_single_gpu_frame": same, "peer_wait_timeouts": int(st.item()),
+           "rank0_ingest_bytes_per_frame": int(ingest),
+           "rank0_ingest_bound_ms_at_770GBps": ingest / 770e9 * 1e3,
+           "timing": "CUDA events on the lanes' streams around the whole batch of pipelined frames, max over ranks; one barrier per batch",
+           "split": "tiles i % N (sort-first resolve, peer-store composite into rank 0) + triangle ranges r*T/N..(r+1)*T/N "
+                    "(sort-last front end, keys merged over NVLink inside the tile kernel); vertex stage replicated"}
+    if stage_ms:
+        rec["stage_ms_per_rank"] = stage_ms
+    if nv0 and nv1:
+        rec["nvlink_rank0_rx_bytes_per_frame"] = (nv1[1] - nv0[1]) / nframes
+        rec["nvlink_rank0_tx_bytes_per_frame"] = (nv1[0] - nv0[0]) / nframes
+    return rec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -369,41 +530,57 @@ def run_ours(args):
         ffb = P.RenderBuffer.with_dimensions(cx, w, h)
         flights.append((cx, ffb, P.Pipeline.from_framebuffer(ffb, u), P.Mesh(cx, mesh),
                         torch.cuda.ExternalStream(cx.stream, device=torch.device("cuda", local_rank))))
+    for lane in flights:  # untimed set-up: every stream allocates its scratch memory and warms its caches once
+        for _ in range(3):
+            frame(lane[2], lane[1], lane[3])
+        lane[0].synchronize()
 
-    def timed(lanes, steps, warmup):
+    def timed(lanes, steps, warmup, min_seconds=0.5, max_blocks=300):
+        """W warm-up steps, then blocks of exactly K steps, each bracketed by barrier + synchronize and timed with CUDA
+        events on the launching streams; blocks are repeated until the timed region reaches `min_seconds` (a 20-step block
+        is only ~6 ms) and the MEDIAN block (max over ranks per block) is reported."""
         def go(i):
             cx, ffb, fp, fm, _ = lanes[i % len(lanes)]
             frame(fp, ffb, fm)
-        for i in range(max(warmup, 3 * len(lanes))):  # every stream needs its own warm-up frames (allocator, caches)
+
+        def block():
+            for lane in lanes:
+                lane[0].synchronize()
+            barrier()
+            torch.cuda.synchronize()
+            starts = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+            ends = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+            for lane, e in zip(lanes, starts):
+                e.record(lane[4])
+            for i in range(steps):
+                go(i)
+            for lane, e in zip(lanes, ends):
+                e.record(lane[4])
+            for lane in lanes:
+                lane[0].synchronize()
+            torch.cuda.synchronize()
+            barrier()
+            return max(starts[0].elapsed_time(e) for e in ends)
+
+        for i in range(warmup):
             go(i)
-        for lane in lanes:
-            lane[0].synchronize()
-        barrier()
-        torch.cuda.synchronize()
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ends = [torch.cuda.Event(enable_timing=True) for _ in lanes]
-        starts = [torch.cuda.Event(enable_timing=True) for _ in lanes]
-        for lane, e in zip(lanes, starts):
-            e.record(lane[4])
-        ev0 = starts[0]
-        for i in range(steps):
-            go(i)
-        for lane, e in zip(lanes, ends):
-            e.record(lane[4])
-        for lane in lanes:
-            lane[0].synchronize()
-        torch.cuda.synchronize()
-        barrier()
-        return max_over_ranks(max(ev0.elapsed_time(e) for e in ends)) / steps
+        first = max_over_ranks(block())
+        nblocks = int(min(max_blocks, max(3, np.ceil(min_seconds * 1e3 / max(first, 1e-3)))))
+        times = [block() for _ in range(nblocks)]
+        if world > 1:
+            t = torch.tensor(times, device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times = t.tolist()
+        return float(np.median(times)) / steps, nblocks, float(np.sum(times)) * 1e-3
 
     # ---- headline: whole frames per GPU (N>1: frame batching, independent frame streams per rank) ----
     sampler = ClockSampler(local_rank)
     if not os.environ.get("SR_NO_SAMPLER"):
         sampler.start()
     launches0 = sum(f[0].launch_count() for f in flights)
-    ms_per_step = timed(flights, args.steps, args.warmup)
-    launches = (sum(f[0].launch_count() for f in flights) - launches0) // (args.steps + max(args.warmup, 3 * len(flights))) * args.steps
-    single_ms = timed(flights[:1], args.steps, args.warmup) if len(flights) > 1 else ms_per_step
+    ms_per_step, nblocks, region_s = timed(flights, args.steps, args.warmup, min_seconds=0.0 if args.quick else 0.5)
+    launches_per_step = (sum(f[0].launch_count() for f in flights) - launches0) / (args.warmup + (nblocks + 1) * args.steps)
+    single_ms, _, _ = timed(flights[:1], args.steps, args.warmup, min_seconds=0.0 if args.quick else 0.5) if len(flights) > 1 else (ms_per_step, 0, 0)
     in_flight_used = len(flights)
     if single_ms < ms_per_step:  # frames too large to profit from overlap (config 4): report the single-stream number
         ms_per_step, in_flight_used = single_ms, 1
@@ -425,42 +602,15 @@ def run_ours(args):
             stage_acc[k] = stage_acc.get(k, 0.0) + v / nstage
     ctx.set_stage_timing(False)
 
-    # ---- N>1: sort-first tile sharding of ONE frame, peer-store composite into rank 0's framebuffer over NVLink ----
-    sharded = None
+    # ---- N>1: ONE frame sharded over the GPUs (tiles + triangle ranges), configs 3 and 4 ----
+    sharded, sharded4 = None, None
     if world > 1:
-        single_gpu_frame = None
-        if rank == 0:  # the unsharded frame, to check the composited one against (bit for bit)
-            frame()
-            single_gpu_frame = fb.download()
-        handle = [fb.ipc_export() if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        ctx.set_tile_shard(rank, world)
-        sfb = fb if rank == 0 else P.RenderBuffer.ipc_open(ctx, handle[0], w, h)
-        spipe = pipe if rank == 0 else P.Pipeline.from_framebuffer(sfb, u)
-
-        def sharded_frame():
-            frame(spipe, sfb)
-            ctx.synchronize()
-            barrier()  # the frame is complete when every rank's tiles have landed in rank 0's HBM
-
-        for _ in range(3):
-            sharded_frame()
-        t0 = time.perf_counter()
-        n_sh = max(3, min(args.steps, 10))
-        for _ in range(n_sh):
-            sharded_frame()
-        sh_ms = max_over_ranks((time.perf_counter() - t0) / n_sh * 1e3)
-        same = None
-        if rank == 0:
-            same = bool(np.array_equal(fb.download().view(np.uint32), single_gpu_frame.view(np.uint32)))
-            single_gpu_frame = None
-        sharded = {"ms_per_frame": sh_ms, "identical_to_single_gpu_frame": same, "Mtris_per_s": ntris / (sh_ms * 1e-3) / 1e6, "frames_per_s": 1e3 / sh_ms,
-                   "timing": "host clock around draw + stream sync + barrier, max over ranks",
-                   "composite": "tile rasteriser stores finished tiles into rank 0's framebuffer (CUDA IPC peer pointer, NVLink)"}
-        ctx.set_tile_shard(0, 1)
-        if rank != 0:
-            spipe.destroy()
-        barrier()
+        sharded = run_sharded(args.config, world, rank, local_rank, P, sr, dist, barrier, max_over_ranks, max(20, args.steps))
+        if args.config == "grid10m" and not os.environ.get("SR_NO_CONFIG4") and not (args.quick and os.environ.get("SR_QUICK_CONFIG3_ONLY")):
+            try:
+                sharded4 = run_sharded("grid100m", world, rank, local_rank, P, sr, dist, barrier, max_over_ranks, 20)
+            except Exception as e:
+                sharded4 = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- end to end through the C ABI with HOST buffers: mesh upload + draw + framebuffer read-back each step ----
     # Three frames are in flight (three contexts = three CUDA streams, one host thread each, the C ABI releases the GIL): the
@@ -475,7 +625,7 @@ def run_ours(args):
         lfb = fb if k == 0 else P.RenderBuffer.with_dimensions(cx, w, h)
         lp = pipe if k == 0 else P.Pipeline.from_framebuffer(lfb, u)
         lanes.append((cx, lfb, lp, torch.empty((w * h, 5), dtype=torch.float32).pin_memory().numpy()))
-    e2e_steps = max(depth, min(args.steps, 9) // depth * depth)
+    e2e_steps = max(depth, (args.steps + depth - 1) // depth * depth)
 
     def e2e_frame(lane):
         cx, lfb, lp, host_fb = lane
@@ -503,6 +653,8 @@ def run_ours(args):
             t.join()
         return time.perf_counter() - t0
 
+    if args.quick:
+        e2e_steps = depth
     e2e_run(depth)  # warm-up (allocations, first touches)
     e2e_s = max_over_ranks(e2e_run(e2e_steps) / e2e_steps)
     barrier()
@@ -522,51 +674,58 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         b_alg = algorithmic_bytes(nverts, ntris, w, h)
         achieved = b_alg / (ms_per_step * 1e-3) / 1e9
-        # the dominant kernel and its own algorithmic bytes
+        # Per-kernel figures.  `pipeline_bytes` = what this implementation's launch has to move by design (inputs +
+        # intermediates: shaded vertices, keys), `alg_bytes` = the launch's share of SURVEY 8d's algorithmic bytes only
+        # (input vertices for k_vertex, indices for k_micro, the 20 B/pixel frame for the resolve).
         kernels = {
-            "k_vertex": {"ms": stage_acc.get("vertex_ms", 0.0), "alg_bytes": nverts * (24 + 48)},
-            "k_micro": {"ms": stage_acc.get("micro_ms", 0.0), "alg_bytes": 3 * ntris * 4 + nverts * 16},
-            "k_tile_opaque(+offsets)": {"ms": stage_acc.get("raster_ms", 0.0), "alg_bytes": w * h * (8 + 8 + 20)},
+            "k_vertex": {"ms": stage_acc.get("vertex_ms", 0.0), "pipeline_bytes": nverts * (24 + 48), "alg_bytes": nverts * 24},
+            "k_micro": {"ms": stage_acc.get("micro_ms", 0.0), "pipeline_bytes": 3 * ntris * 4 + nverts * 16, "alg_bytes": 3 * ntris * 4},
+            "k_tile_opaque(+offsets)": {"ms": stage_acc.get("raster_ms", 0.0), "pipeline_bytes": w * h * (8 + 8 + 20), "alg_bytes": w * h * 20},
         }
         for k in kernels.values():
-            k["GBps"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
-            k["frac"] = k["GBps"] / peak if k["GBps"] else None
+            for which in ("pipeline", "alg"):
+                gbs = k[f"{which}_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
+                k[f"{which}_GBps"] = gbs
+                k[f"{which}_frac"] = gbs / peak if gbs else None
         dom = max(kernels, key=lambda n: kernels[n]["ms"])
-        traffic = kernel_traffic()
+        traffic = kernel_traffic().get(args.config, {})  # per config; absent -> null
         line = {
             "metric": f"Mtris/s at {w}x{h}", "value": world * ntris / (ms_per_step * 1e-3) / 1e6, "unit": "Mtris/s",
+            "value_definition": f"throughput with {in_flight_used} independent frame(s) in flight per GPU; one full draw on one stream is "
+                                f"single_stream_ms_per_frame (SURVEY.md 8d)",
             "frames_per_s": world * 1e3 / ms_per_step,
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3 * len(flights)), "ms_per_step": ms_per_step,
-            "single_stream_ms_per_frame": single_ms,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "timed_blocks": nblocks, "timed_region_s": region_s,
+            "single_stream_ms_per_frame": single_ms, "single_stream_Mtris_per_s": ntris / (single_ms * 1e-3) / 1e6,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.config, "width": w, "height": h, "triangles": ntris, "vertices": nverts,
-                       "shader": "suzanne Blinn-Phong", "depth_test": True, "frames_in_flight": in_flight_used,
-                       "parallelism": "1 GPU" if world == 1 else
-                       f"frame batching: {world} GPUs each render whole frames of the workload (no data-path collective); "
-                       f"the sort-first tile-sharded single frame is reported under 'sharded'",
-                       "l2": "working set per frame (mesh 240 MB + shaded vertices 240 MB + framebuffer 166 MB) exceeds the 126 MB L2; no flush needed"},
+            "config": workload_config(args.config, args.in_flight, world),
+            "frames_in_flight_used": in_flight_used,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_single_stream": b_alg / (single_ms * 1e-3) / 1e9 / peak,
                          "traffic": traffic.get("frame_dram_bytes"), "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg,
                          "scope": "whole frame: B_alg / frame time (SURVEY.md 8d); per-kernel figures under 'kernels'",
-                         "dominant_kernel": {"name": dom, "achieved": kernels[dom]["GBps"], "frac": kernels[dom]["frac"],
-                                             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
+                         "dominant_kernel": {"name": dom, "achieved": kernels[dom]["alg_GBps"], "frac": kernels[dom]["alg_frac"],
+                                             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "pipeline_bytes_per_launch": kernels[dom]["pipeline_bytes"],
+                                             "pipeline_frac": kernels[dom]["pipeline_frac"], "ms_per_launch": kernels[dom]["ms"],
                                              "traffic": traffic.get(dom),
                                              "note": "issue-slot bound, not HBM bound (DESIGN.md section 4): see profiles/"},
                          "kernels": kernels,
                          "stage_ms_avg": stage_acc},
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": sampler.summary(),
         }
         if sharded:
             line["sharded"] = sharded
-        if world == 1 and args.config == "grid10m":
+        if sharded4:
+            line["sharded_config4"] = sharded4
+        if world == 1 and args.config == "grid10m" and not args.quick:
             try:
                 line["other_configs"] = other_configs(ctx)
             except Exception as e:  # never let the side measurements take the headline line down
                 line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:200]}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             line["cpu_baseline"] = cpu_baseline_sample(args.config, native_oracle())
         print(json.dumps(line))
     barrier()
@@ -702,6 +861,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="grid10m", choices=sorted(CONFIGS) + ["turntable"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="development runs: short timed region, no side measurements (not a bench line)")
     ap.add_argument("--in-flight", type=int, default=3, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

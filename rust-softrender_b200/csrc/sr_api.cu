@@ -45,6 +45,8 @@ struct DevBuf {
     sr_context *ctx = nullptr;
     void *ptr = nullptr;
     size_t bytes = 0;
+    // an index buffer remembers the vertex range its triangles [t0, t1) reference (range-sharded frames; computed once)
+    uint32_t vr_t0 = 0, vr_t1 = 0, vr_lo = 0, vr_hi = 0;
     ~DevBuf();
     template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
 };
@@ -79,6 +81,8 @@ struct sr_context {
     uint32_t zero_off_tiles = 0;
     struct sr_shard *shard = nullptr;             // range-sharded front end (sr_context_attach_shard)
     uint32_t shard_lane = 0;
+    cudaEvent_t ev_dbg[6] = {};                   // SR_SHARD_DEBUG: finer timestamps inside a range-sharded frame (diagnosis only)
+    bool ev_dbg_valid = false;
     sr_stage_times times = {};
     int alloc(size_t bytes, Buf *out);
     // Lifetime: every device buffer keeps its context alive (refs), so children destroyed after sr_context_destroy -- a
@@ -177,9 +181,14 @@ struct sr_shard {
     bool peer_ipc[SR_SHARD_MAX_WORLD] = {};
     bool connected = false;
     uint32_t frame[8] = {};  // frames issued per lane
+    SrTileOwners owners;     // tile -> rank of the range-sharded frames (identical on every rank)
+    uint32_t owned_cap = 0;  // upper bound of the tiles this rank owns per period (diagnostics)
+    uint32_t merge_ctas = 0; // resident merge CTAs per SM (0: the kernel's natural 4); fewer leave room for the next frame's front end
+    bool fused_merge = false; // merge the peers' keys inside the resolve (PHASE 2 pulls) instead of the streaming k_shard_merge
     unsigned long long *vis(unsigned char *base, uint32_t lane) const { return reinterpret_cast<unsigned long long *>(base + lane * lane_stride); }
     uint32_t *ready(unsigned char *base, uint32_t lane) const { return reinterpret_cast<uint32_t *>(base + lane * lane_stride + vis_bytes); }
     uint32_t *done(unsigned char *base, uint32_t lane) const { return ready(base, lane) + SR_SHARD_MAX_WORLD; }
+    uint32_t *touched(unsigned char *base, uint32_t lane) const { return reinterpret_cast<uint32_t *>(base + lane * lane_stride + vis_bytes + 256); }
     uint32_t *error() const { return reinterpret_cast<uint32_t *>(block + lanes * lane_stride); }
 };
 
@@ -240,6 +249,11 @@ struct sr_draw {
     // FragmentShader builder state (fragment.rs:45-56)
     uint32_t cull = SR_CULL_NONE, blend = SR_BLEND_REPLACE, aa_lines = 0;
     uint32_t tile_w = 128, tile_h = 128;  // DEFAULT_TILE_SIZE (fragment.rs:29); accepted, not used
+    // run_to_fragment on a context with a shard group attached: the vertex stage is recorded, not run -- a range-sharded
+    // fragment stage shades only the vertices this rank needs; every other consumer shades the whole mesh first
+    bool vertex_lazy = false;
+    uint32_t lazy_vs = 0;
+    SrVsConst lazy_vc;
 };
 
 static uint32_t nplanes_of(uint32_t nk) { return (nk + 3) / 4; }
@@ -481,24 +495,29 @@ static int launch_opaque_sweep(sr_context *c, uint32_t ntiles, const SrOpaquePar
     SR_LAUNCH(c, (k_tile_opaque<SR_FS_FLAT, false, 1>), ntiles, SR_OPQ_THREADS, SR_OPQ_SMEM_BYTES, p);
     return SR_OK;
 }
+// `ctas_per_sm` > 0 pads the dynamic shared memory so that at most that many merge CTAs are resident per SM: on the ranks whose
+// write-back crosses NVLink the resolve waits on the link, and leaving registers free lets the next frame's front end (another lane)
+// run beside it
 template <int FS>
-static int launch_opaque_merge(sr_context *c, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+static int launch_opaque_merge(sr_context *c, uint32_t ntiles, const SrOpaqueParams &p, uint32_t ctas_per_sm) {
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
-        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_OPQ_MERGE_SMEM_BYTES));
+        SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[c->device & 15] = true;
     }
-    SR_LAUNCH(c, (k_tile_opaque<FS, false, 2>), ntiles_owned, SR_OPQ_THREADS, SR_OPQ_MERGE_SMEM_BYTES, p);
+    size_t smem = SR_OPQ_MERGE_SMEM_BYTES;
+    if (ctas_per_sm > 0) smem = std::max<size_t>(smem, std::min<size_t>(200 * 1024, (size_t)(227 * 1024) / (ctas_per_sm + 1) + 1024));
+    SR_LAUNCH(c, (k_tile_opaque<FS, false, 2>), ntiles, SR_OPQ_THREADS, smem, p);
     return SR_OK;
 }
-static int launch_opaque_merge_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
+static int launch_opaque_merge_fs(sr_context *c, uint32_t fs, uint32_t ntiles, const SrOpaqueParams &p, uint32_t ctas_per_sm) {
     switch (fs) {
-        case SR_FS_FLAT: return launch_opaque_merge<SR_FS_FLAT>(c, ntiles_owned, p);
-        case SR_FS_SUZANNE: return launch_opaque_merge<SR_FS_SUZANNE>(c, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE: return launch_opaque_merge<SR_FS_FULL_EXAMPLE>(c, ntiles_owned, p);
-        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque_merge<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles_owned, p);
-        case SR_FS_GREEN: return launch_opaque_merge<SR_FS_GREEN>(c, ntiles_owned, p);
-        case SR_FS_TEXTURE_UNLIT: return launch_opaque_merge<SR_FS_TEXTURE_UNLIT>(c, ntiles_owned, p);
+        case SR_FS_FLAT: return launch_opaque_merge<SR_FS_FLAT>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_SUZANNE: return launch_opaque_merge<SR_FS_SUZANNE>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_FULL_EXAMPLE: return launch_opaque_merge<SR_FS_FULL_EXAMPLE>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque_merge<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_GREEN: return launch_opaque_merge<SR_FS_GREEN>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_TEXTURE_UNLIT: return launch_opaque_merge<SR_FS_TEXTURE_UNLIT>(c, ntiles, p, ctas_per_sm);
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
 }
@@ -535,7 +554,8 @@ struct PendingOpaque {
 static int launch_opaque_pass(sr_context *c, PendingOpaque *q);
 static int launch_bin_small(sr_context *c, PendingOpaque *q);
 static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
-                                   const std::vector<Buf> &keep);
+                                   const std::vector<Buf> &keep, sr_draw *d);
+static int materialize_vertices(sr_draw *d);
 // The same for the ordered tile pass: its three group lists (points, lines, triangles) live in grow-only arenas.
 struct PendingOrdered {
     cudaEvent_t counted = nullptr;
@@ -623,12 +643,17 @@ static uint32_t sr_micro_area_for(uint32_t ntris) { return ntris >= 49152u ? 102
 // The opaque triangle path (sr_raster.cuh): visibility-buffer init, k_micro (per-triangle setup + direct
 // rasterisation of small triangles + compaction/counting of the large ones), per-tile lists of the large
 // triangles, then the tile kernel (large triangles + resolve + single write-back).
-static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
-                            const std::vector<Buf> &keep, bool extra) {
+static bool ranged_eligible(const sr_context *c, const sr_framebuffer *fb, const SrTileParams &tp, bool extra) {
     const uint32_t ntiles = fb->ntx * fb->nty;
-    if (c->shard && c->shard->connected && !extra && fb->pending_clear && tp.ntris >= 65536u && (c->micro_auto || c->micro_area > 0) &&
-        c->shard->world == c->shard_world && c->shard->rank == c->shard_rank && c->shard->ntx == fb->ntx && c->shard->nty == fb->nty && ntiles >= c->shard_world)
-        return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep);
+    return c->shard && c->shard->connected && !extra && fb->pending_clear && tp.ntris >= 65536u && tp.tris.n1 == 0 && (c->micro_auto || c->micro_area > 0) &&
+           c->shard->world == c->shard_world && c->shard->rank == c->shard_rank && c->shard->ntx == fb->ntx && c->shard->nty == fb->nty &&
+           ntiles >= c->shard_world;
+}
+static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
+                            const std::vector<Buf> &keep, bool extra, sr_draw *d = nullptr) {
+    const uint32_t ntiles = fb->ntx * fb->nty;
+    if (ranged_eligible(c, fb, tp, extra)) return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep, d);
+    if (d) SR_TRY(materialize_vertices(d));
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
     if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
         record(c, 7);
@@ -776,20 +801,96 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     c->pending = q.release();
     return SR_OK;
 }
+static int launch_vertex(sr_context *c, sr_draw *d, uint32_t vs, const SrVsConst &vc, const SrVertexSpan &span) {
+    if (span.end <= span.begin) return SR_OK;
+    SrMeshView mv;
+    mv.planes = d->mesh_planes->as<float>();
+    mv.pstride = d->mesh_pstride;
+    mv.nverts = d->mesh_nverts;
+    mv.vin = d->vin;
+    float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
+    if (span.mask != nullptr) {  // one warp per 1024 vertices
+        const uint32_t grid = ceil_div(ceil_div(span.end - span.begin, 1024), 8);
+        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex_marked<SR_VS_SUZANNE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
+        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex_marked<SR_VS_FULL_EXAMPLE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
+        else return sr_fail(SR_ERR_INVALID_ARGUMENT, "vertex shader %u", vs);
+        return SR_OK;
+    }
+    const uint32_t grid = ceil_div(span.end - span.begin, 256);
+    if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
+    else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
+    else return sr_fail(SR_ERR_INVALID_ARGUMENT, "vertex shader %u", vs);
+    return SR_OK;
+}
+// a recorded (lazy) vertex stage becomes vertices: the whole mesh, for every consumer but the range-sharded fragment stage
+static int materialize_vertices(sr_draw *d) {
+    if (!d->vertex_lazy) return SR_OK;
+    d->vertex_lazy = false;
+    const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0};
+    return launch_vertex(d->pipeline->ctx, d, d->lazy_vs, d->lazy_vc, whole);
+}
 // The opaque triangle path of a range-sharded frame (include/softrender_b200.h).  Per frame n of a lane:
-//   a. wait until every peer has finished reading my keys of frame n-1            (done words)
-//   b. hand the keys of the tiles I do not own back "far" (my own tiles were reset by my resolve)
-//   c. k_micro over MY triangle range, all tiles, global triangle ids; large triangles -> lists of all tiles -> PHASE 1 sweep
-//   d. publish "frame n ready" to every peer                                      (ready words)
-//   e. wait until every peer's keys of frame n are ready
-//   f. PHASE 2: merge the peers' keys of my tiles over NVLink + resolve + write-back (to rank 0's framebuffer)
-//   g. publish "frame n done"
-// All of it is enqueued on the context's stream; nothing synchronises with the host.
+//   a. (lazy vertex stage) shade the vertex range MY triangles reference
+//   b. wait until every peer has finished reading my keys of frame n-1            (done words)
+//   c. hand the keys of the tiles I do not own back "far" (my own tiles were reset by my resolve); rank 0 also pre-fills the
+//      framebuffer pixels of the tiles it does not own with the clear, so that their owners only send what was drawn on
+//   d. k_micro over MY triangle range, all tiles, global triangle ids; large triangles -> lists of all tiles -> PHASE 1 sweep
+//   e. publish "frame n ready" to every peer                                      (ready words)
+//   f. wait until every peer's keys of frame n are ready
+//   g. merge the peers' keys of my tiles over NVLink (k_shard_merge, or inside the resolve: sr_shard::fused_merge) and mark the
+//      vertices the winners reference; (lazy vertex stage) shade exactly those
+//   h. resolve my tiles + write-back (to rank 0's framebuffer)
+//   i. publish "frame n done"
+// All of it is enqueued on the context's stream; nothing synchronises with the host (except, once per mesh, the reduction that
+// finds the vertex range of the rank's triangles).
 static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
-                                   const std::vector<Buf> &keep) {
+                                   const std::vector<Buf> &keep, sr_draw *d) {
     sr_shard *sh = c->shard;
     const uint32_t lane = c->shard_lane, ntiles = fb->ntx * fb->nty;
+    const uint32_t t0 = (uint32_t)((uint64_t)tp.ntris * sh->rank / sh->world), t1 = (uint32_t)((uint64_t)tp.ntris * (sh->rank + 1) / sh->world);
+    const bool lazy = d && d->vertex_lazy;
+    uint32_t vlo = 0, vhi = 0;
+    Buf mark;
+    if (lazy) {
+        DevBuf *ib = d->indices.get();
+        if (!(ib->vr_t1 > ib->vr_t0 && ib->vr_t0 == t0 && ib->vr_t1 == t1)) {  // once per mesh and (rank, world)
+            Buf mm;
+            SR_TRY(c->alloc(8, &mm));
+            const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+            SR_CUDA(cudaMemcpyAsync(mm->ptr, init, 8, cudaMemcpyHostToDevice, c->stream));
+            if (t1 > t0) SR_LAUNCH(c, k_index_minmax, 148 * 8, 256, 0, d->indices->as<uint32_t>() + (uint64_t)t0 * 3, (uint64_t)(t1 - t0) * 3, mm->as<uint32_t>());
+            uint32_t out[2] = {0, 0};
+            SR_CUDA(cudaMemcpyAsync(out, mm->ptr, 8, cudaMemcpyDeviceToHost, c->stream));
+            SR_CUDA(cudaStreamSynchronize(c->stream));
+            ib->vr_t0 = t0; ib->vr_t1 = t1;
+            ib->vr_lo = t1 > t0 ? out[0] : 0; ib->vr_hi = t1 > t0 ? std::min<uint64_t>(out[1], d->mesh_nverts) : 0;
+        }
+        vlo = ib->vr_lo; vhi = ib->vr_hi;
+        record(c, 0);
+        const SrVertexSpan own = {vlo, vhi, nullptr, 0, 0};
+        SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, own));                                                        // a
+        record(c, 1);
+        record(c, 2);
+        record(c, 3);
+        record(c, 4);
+        SR_TRY(c->alloc(((size_t)d->mesh_nverts + 31) / 32 * 4 + 4, &mark));
+        SR_CUDA(cudaMemsetAsync(mark->ptr, 0, ((size_t)d->mesh_nverts + 31) / 32 * 4 + 4, c->stream));
+        // (the draw stays "lazy": only part of its vertices is shaded, any other consumer shades the whole mesh first)
+    }
     const uint32_t n = ++sh->frame[lane];
+    static const bool dbg = getenv("SR_SHARD_DEBUG") != nullptr;
+    auto stamp = [&](int i) {
+        if (!dbg) return;
+        if (!c->ev_dbg[i]) cudaEventCreate(&c->ev_dbg[i]);
+        cudaEventRecord(c->ev_dbg[i], c->stream);
+    };
+    if (dbg && c->ev_dbg_valid) {  // the previous frame of this context, printed once it has completed
+        cudaEventSynchronize(c->ev_dbg[5]);
+        float t[5] = {};
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], c->ev_dbg[i], c->ev_dbg[i + 1]);
+        fprintf(stderr, "[shard rank %u lane %u frame %u] wait_ready %.3f  merge+mark %.3f  vertex(winners) %.3f  resolve %.3f  signal %.3f ms\n",
+                sh->rank, lane, n - 1, t[0], t[1], t[2], t[3], t[4]);
+    }
     unsigned long long *vis = sh->vis(sh->block, lane);
     const unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
     SrShardPeers ready_peers, done_peers;
@@ -800,11 +901,10 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
             ready_peers.word[p] = sh->ready(sh->peer[p], lane);
             done_peers.word[p] = sh->done(sh->peer[p], lane);
         }
-    if (n > 1) SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->done(sh->block, lane), sh->world, sh->rank, n - 1, timeout_ns, sh->error());
-    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->ntx, sh->rank, sh->world, n == 1 ? 1u : 0u);
+    if (n > 1) SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->done(sh->block, lane), sh->world, sh->rank, n - 1, timeout_ns, sh->error());   // b
+    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->view(), sh->owners, sh->rank, n == 1 ? 1u : 0u, sh->rank == 0 ? 1u : 0u);  // c
     record(c, 7);
     Buf count, off, lcount, lids, lrects;
-    const uint32_t t0 = (uint32_t)((uint64_t)tp.ntris * sh->rank / sh->world), t1 = (uint32_t)((uint64_t)tp.ntris * (sh->rank + 1) / sh->world);
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
     SR_TRY(c->alloc(4, &lcount));
@@ -827,14 +927,13 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     mp.large_ids = lids->as<uint32_t>();
     mp.large_rects = lrects->as<uint32_t>();
     mp.tile_count = count->as<uint32_t>();
-    if (t1 > t0) {
+    if (t1 > t0) {                                                                                                       // d
         const uint32_t grid = ceil_div(t1 - t0, SR_MICRO_THREADS);
         if (c->micro_precheck & 2u) SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp);
         else SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp);
     }
     record(c, 5);
     SR_LAUNCH(c, k_tile_offsets, 1, SR_OFFSETS_THREADS, 0, count->as<uint32_t>(), ntiles, off->as<uint32_t>(), count->as<uint32_t>());
-    if (!c->pinned) SR_CUDA(cudaHostAlloc((void **)&c->pinned, 64, cudaHostAllocDefault));
     SR_CUDA(cudaMemcpyAsync(&c->pinned[0], off->as<uint32_t>() + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaEventCreateWithFlags(&q->counted, cudaEventDisableTiming));
     SR_CUDA(cudaEventRecord(q->counted, c->stream));
@@ -848,6 +947,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     q->count = count; q->off = off; q->lcount = lcount; q->lids = lids; q->lrects = lrects;
     q->keep = keep;
     q->keep.push_back(c->list_arena);
+    if (mark) q->keep.push_back(mark);
     q->fb = fb;
     SrOpaqueParams &op = q->op;
     memset(&op, 0, sizeof(op));
@@ -860,21 +960,53 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     op.ntiles = ntiles;
     op.fb = fb->view();
     op.fs = tp.fs;
-    // c (continued): large triangles of my range, every tile
-    op.shard_rank = 0; op.shard_world = 1;
+    op.shard_rank = 0; op.shard_world = 1;  // (d, continued) the large triangles of my range, every tile
     op.reset_vis = 0;
     SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(std::max(t1 - t0, 1u), 8), 148u * 4u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
               lrects->as<uint32_t>(), fb->ntx, ntiles, 0u, 1u, off->as<uint32_t>(), count->as<uint32_t>(), c->list_arena->as<uint32_t>(), c->list_cap);
     SR_TRY(launch_opaque_sweep(c, ntiles, op));
-    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, ready_peers, sh->rank, n);                                                    // d
-    SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->ready(sh->block, lane), sh->world, sh->rank, n, timeout_ns, sh->error());   // e
-    // f: my tiles, merged with every peer's keys
+    SR_LAUNCH(c, k_vis_rows_touched, ntiles, 256, 0, vis, fb->ntx, sh->owners, sh->rank, sh->touched(sh->block, lane));
+    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, ready_peers, sh->rank, n);                                                    // e
+    stamp(0);
+    SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->ready(sh->block, lane), sh->world, sh->rank, n, timeout_ns, sh->error());   // f
+    stamp(1);
     op.shard_rank = sh->rank; op.shard_world = sh->world;
     op.reset_vis = 1;
-    for (uint32_t p = 0; p < sh->world; ++p)
-        if (p != sh->rank) op.peer_vis[op.npeers++] = sh->vis(sh->peer[p], lane);
-    if (owned) SR_TRY(launch_opaque_merge_fs(c, fs, owned, op));
-    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, done_peers, sh->rank, n);                                                     // g
+    op.owners = sh->owners;
+    op.elide_clear = sh->rank != 0 ? 1u : 0u;
+    const bool fused = sh->fused_merge && !lazy;  // (the winners' vertices must be known before the resolve when they are shaded on demand)
+    if (fused) {
+        for (uint32_t p = 0; p < sh->world; ++p)
+            if (p != sh->rank) op.peer_vis[op.npeers++] = sh->vis(sh->peer[p], lane);
+    } else {                                                                                                             // g
+        SrMergeParams mg;
+        memset(&mg, 0, sizeof(mg));
+        mg.vis = vis;
+        for (uint32_t p = 0; p < sh->world; ++p)
+            if (p != sh->rank) {
+                mg.peer_touched[mg.npeers] = sh->touched(sh->peer[p], lane);
+                mg.peer_vis[mg.npeers++] = sh->vis(sh->peer[p], lane);
+            }
+        mg.ntx = fb->ntx; mg.rank = sh->rank;
+        mg.owners = sh->owners;
+        mg.indices = tp.tris.indices;
+        mg.ntris = tp.tris.n0;
+        mg.mark = lazy ? mark->as<uint32_t>() : nullptr;
+        mg.skip_lo = vlo; mg.skip_hi = vhi;
+        SR_LAUNCH(c, k_shard_merge, ntiles, 256, 0, mg);
+        stamp(2);
+        if (lazy) {
+            const SrVertexSpan winners = {0, d->mesh_nverts, mark->as<uint32_t>(), vlo, vhi};
+            SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, winners));
+        }
+    }
+    if (fused) stamp(2);
+    stamp(3);
+    SR_TRY(launch_opaque_merge_fs(c, fs, ntiles, op, sh->merge_ctas));                                                   // h
+    stamp(4);
+    SR_LAUNCH(c, k_shard_signal, 1, 32, 0, done_peers, sh->rank, n);                                                     // i
+    stamp(5);
+    c->ev_dbg_valid = dbg;
     fb->pending_clear = false;
     c->pending = q.release();
     return SR_OK;
@@ -929,6 +1061,11 @@ static void preload_ranged_kernels() {
     preload(k_shard_wait);
     preload(k_shard_signal);
     preload(k_vis_clear_foreign);
+    preload(k_shard_merge);
+    preload(k_vis_rows_touched);
+    preload(k_vertex_marked<SR_VS_SUZANNE>);
+    preload(k_vertex_marked<SR_VS_FULL_EXAMPLE>);
+    preload(k_index_minmax);
     preload(k_micro<false, true>);
     preload(k_micro<false, false>);
     preload(k_tile_offsets);
@@ -1371,6 +1508,26 @@ int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **ou
 }
 
 // ---- shard groups (range-sharded front end) --------------------------------------------------------------
+// ownership pattern: rank 0 holds `k0` of every k0 + k*(world-1) consecutive tiles, every other rank k, spread evenly
+static int shard_set_shares(sr_shard *sh, uint32_t k0, uint32_t k) {
+    const uint32_t period = k0 + k * (sh->world - 1);
+    if (k == 0 || period == 0 || period > SR_OWNER_PERIOD_MAX) return sr_fail(SR_ERR_INVALID_ARGUMENT, "tile shares %u:%u need a period of 1..%d", k0, k, SR_OWNER_PERIOD_MAX);
+    uint32_t want[SR_SHARD_MAX_WORLD], got[SR_SHARD_MAX_WORLD] = {};
+    for (uint32_t r = 0; r < sh->world; ++r) want[r] = r == 0 ? k0 : k;
+    for (uint32_t i = 0; i < period; ++i) {  // slot i goes to the rank that is furthest behind its share
+        uint32_t best = 0;
+        double worst = -1e30;
+        for (uint32_t r = 0; r < sh->world; ++r) {
+            if (got[r] >= want[r]) continue;
+            const double deficit = (double)want[r] * (i + 1) / period - got[r];
+            if (deficit > worst + 1e-12) { worst = deficit; best = r; }
+        }
+        sh->owners.owner[i] = (uint8_t)best;
+        ++got[best];
+    }
+    sh->owners.period = period;
+    return SR_OK;
+}
 int sr_shard_create(sr_context *c, uint32_t width, uint32_t height, uint32_t lanes, sr_shard **out) {
     if (!c || !out || lanes == 0 || lanes > 8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad shard group");
     if (c->shard_world < 2 || c->shard_world > SR_SHARD_MAX_WORLD)
@@ -1383,8 +1540,17 @@ int sr_shard_create(sr_context *c, uint32_t width, uint32_t height, uint32_t lan
     sh->width = width; sh->height = height; sh->lanes = lanes;
     sh->ntx = ceil_div(width, SR_TILE_W); sh->nty = ceil_div(height, SR_TILE_H);
     sh->vis_bytes = (size_t)sh->ntx * sh->nty * SR_TILE_PIXELS * 8;
-    sh->lane_stride = sh->vis_bytes + 256;
+    sh->lane_stride = sh->vis_bytes + 256 + (((size_t)sh->ntx * sh->nty * 4 + 255) & ~(size_t)255);  // keys, progress words, row masks
     sh->block_bytes = sh->lane_stride * lanes + 256;
+    shard_set_shares(sh.get(), 1, 1);
+    if (const char *env = getenv("SR_SHARD_SHARES")) {  // tuning experiments: "rank0_slots,other_slots[,merge_ctas]"
+        unsigned a = 1, b = 1, m = 0;
+        if (sscanf(env, "%u,%u,%u", &a, &b, &m) >= 2) {
+            if (shard_set_shares(sh.get(), a, b) != SR_OK) return SR_ERR_INVALID_ARGUMENT;
+            sh->merge_ctas = m & 15u;
+            sh->fused_merge = (m & 16u) != 0;
+        }
+    }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, sh->block_bytes);
     if (e != cudaSuccess) return sr_fail(SR_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) for the exchange block failed: %s", sh->block_bytes, cudaGetErrorString(e));
@@ -1658,12 +1824,19 @@ static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
     mv.nverts = d->mesh_nverts;
     mv.vin = d->vin;
     record(c, 0);
-    if (d->mesh_nverts) {
-        float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
-        const uint32_t grid1 = ceil_div(d->mesh_nverts, 256);
-        if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex<SR_VS_SUZANNE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.np);
-        else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex<SR_VS_FULL_EXAMPLE>, grid1, 256, 0, vc, mv, pos, attr, d->indexed.np);
-        else SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, pos, attr, d->indexed.np);
+    static const bool no_lazy = getenv("SR_SHARD_NO_LAZY_VERTEX") != nullptr;  // A/B switch (tuning): shade the whole mesh on every rank
+    if (!no_lazy && vp && c->shard && c->shard->connected && vs != SR_VS_PASSTHROUGH && d->primitive == SR_TRIANGLE && d->nindices / 3 >= 65536u) {
+        d->vertex_lazy = true;  // decided by the fragment stage (opaque_triangles_ranged / materialize_vertices)
+        d->lazy_vs = vs;
+        d->lazy_vc = vc;
+    } else if (d->mesh_nverts) {
+        if (vs == SR_VS_PASSTHROUGH) {
+            SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, d->indexed.pos->as<float4>(),
+                      d->indexed.attr->as<float4>(), d->indexed.np);
+        } else {
+            const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0};
+            SR_TRY(launch_vertex(c, d, vs, vc, whole));
+        }
     }
     record(c, 1);
     record(c, 2);
@@ -1886,6 +2059,10 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(settle(c));
     if (fb->width < 2 || fb->height < 2) return SR_OK;  // fragment.rs:188-216: a 1-pixel-wide frame has no tiles, nothing is drawn
+    {   // a recorded vertex stage stays recorded only for the range-sharded opaque triangle pass
+        const bool st_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
+        if (d->vertex_lazy && !(d->blend == SR_BLEND_REPLACE && !st_active && fs != SR_FS_DISCARD_CHECKER)) SR_TRY(materialize_vertices(d));
+    }
     const bool samples = fs == SR_FS_FULL_EXAMPLE_TEXTURED || fs == SR_FS_TEXTURE_UNLIT;
     if (samples && !p->texture && !p->fb_texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
     if (samples && p->fb_texture) {
@@ -1961,7 +2138,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
             // triangles through the order-independent resolve; lines/points (always after all triangles,
             // fragment.rs:268-311) through the ordered kernel
             if (tp.ntris || fb->pending_clear || extra_vis) {
-                SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep, extra_vis));
+                SR_TRY(opaque_triangles(c, fb, tp, d->cull, fs, owned, keep, extra_vis, d));
                 if (ordered_pass) SR_TRY(settle(c));  // a replayed triangle pass must not land after the lines
             }
             ordered.ntris = 0;
@@ -2048,6 +2225,7 @@ int sr_draw_download(sr_draw *d, int which, float *dst, uint64_t capacity_floats
     if (capacity_floats < n * (4 + d->nk)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "capacity too small");
     sr_context *c = d->pipeline->ctx;
     SR_CUDA(cudaSetDevice(c->device));
+    if (which == 0) SR_TRY(materialize_vertices(d));
     Buf tmp;
     SR_TRY(c->alloc(n * (4 + d->nk) * 4, &tmp));
     SR_LAUNCH(c, k_planes_to_records, ceil_div(n, 256), 256, 0, s.pos->as<float4>(), s.attr->as<float4>(), s.np, n, d->nk, tmp->as<float>());
@@ -2090,6 +2268,7 @@ int sr_draw_bins(sr_draw *d, uint64_t *offsets, uint32_t *ids, uint64_t ids_capa
     sr_context *c = p->ctx;
     sr_framebuffer *fb = p->fb;
     SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_vertices(d));
     const SrPrimSource src = prim_source(d, 3);
     const uint32_t ntris = src.n0 + src.n1, ntiles = fb->ntx * fb->nty;
     Bins b;

@@ -522,19 +522,121 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
 // ---- range-sharded front end: every rank rasterises its own triangle range into a full-frame
 // key buffer of its own; the tile's owner pulls the other ranks' keys over NVLink and max-merges them (k_tile_opaque,
 // PHASE 2).  Keys of tiles the rank does not own are handed back "far" here (its own tiles are reset by its resolve).
-__global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *vis, uint32_t ntx, uint32_t shard_rank, uint32_t shard_world,
-                                                           uint32_t all) {
+// Tile ownership of a range-sharded frame: tile t belongs to rank owner[t % period].  Rank 0 -- whose write-back is local
+// while every other rank's crosses NVLink, but whose tiles cost (world-1) key pulls -- may hold a different share than the rest.
+#define SR_OWNER_PERIOD_MAX 64
+#define SR_SHARD_MAX_WORLD 8
+struct SrTileOwners {
+    uint8_t owner[SR_OWNER_PERIOD_MAX];
+    uint32_t period;
+};
+// `fill`: rank 0 also writes the clear colour + far depth into the framebuffer pixels of the tiles it does NOT own, so that their
+// owners need not send pixels nothing was drawn on over NVLink (the frame starts from a clear: that is what selects this path).
+__global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *vis, const SrFbView fb, const SrTileOwners own, uint32_t rank,
+                                                           uint32_t all, uint32_t fill) {
     const uint32_t tile = blockIdx.x;
-    if (!all && tile % shard_world == shard_rank) return;
-    const uint32_t x0 = (tile % ntx) * SR_TILE_W, y0 = (tile / ntx) * SR_TILE_H;
+    const bool mine = own.owner[tile % own.period] == rank;
+    if (!all && mine) return;
+    const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
     for (uint32_t i = threadIdx.x * 2; i < SR_TILE_PIXELS; i += 512)
-        *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(x0 + i % SR_TILE_W, y0 + i / SR_TILE_W, ntx)) =
+        *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(x0 + i % SR_TILE_W, y0 + i / SR_TILE_W, fb.ntx)) =
             make_ulonglong2(SR_VIS_FAR_KEY, SR_VIS_FAR_KEY);
+    if (!fill || mine || x0 >= fb.width) return;
+    const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
+    const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
+        float *row = fb.aos + ((uint64_t)(y0 + r) * fb.width + x0) * 5;
+        for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i % 5];
+    }
 }
+// The merge of a range-sharded frame as a streaming kernel of its own (the alternative to merging inside the resolve,
+// k_tile_opaque PHASE 2 with npeers > 0): one light CTA per owned tile pulls the peers' keys of that tile straight from
+// peer-mapped memory (16-byte coalesced loads over NVLink, all peers' loads of a thread in flight together), max-merges them
+// into the rank's own buffer and marks the vertices the winners reference in `mark` (one bit per vertex), so that the vertex
+// stage can afterwards shade exactly those -- the rank's vertex stage no longer runs over the whole mesh.
+// Per foreign tile: which of its 32 key rows hold anything but "far" (bit r = row r).  The owner of the tile reads the word
+// first and pulls only those rows -- a rank whose triangles leave part of the frame untouched sends nothing for it.
+__global__ void __launch_bounds__(256) k_vis_rows_touched(const unsigned long long *vis, uint32_t ntx, const SrTileOwners own, uint32_t rank,
+                                                          uint32_t *touched) {
+    const uint32_t tile = blockIdx.x;
+    if (own.owner[tile % own.period] == rank) return;
+    __shared__ uint32_t bits;
+    if (threadIdx.x == 0) bits = 0;
+    __syncthreads();
+    const uint32_t x0 = (tile % ntx) * SR_TILE_W, y0 = (tile / ntx) * SR_TILE_H;
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SR_TILE_PIXELS / 2 / 256; ++j) {
+        const uint32_t i = (j * 256 + threadIdx.x) * 2;
+        const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(vis + sr_vis_index(x0 + i % SR_TILE_W, y0 + i / SR_TILE_W, ntx));
+        if (k.x != SR_VIS_FAR_KEY || k.y != SR_VIS_FAR_KEY) mine |= 1u << (i / SR_TILE_W);
+    }
+    static_assert(SR_TILE_H <= 32, "one bit per tile row");
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicOr(&bits, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) touched[tile] = bits;
+}
+struct SrMergeParams {
+    unsigned long long *vis;
+    const unsigned long long *peer_vis[SR_SHARD_MAX_WORLD - 1];
+    const uint32_t *peer_touched[SR_SHARD_MAX_WORLD - 1];  // the peers' row masks (k_vis_rows_touched)
+    uint32_t npeers, ntx, rank;
+    SrTileOwners owners;
+    const uint32_t *indices;  // winners' vertex indices (indexed triangles only)
+    uint32_t ntris;
+    uint32_t *mark;           // or null
+    uint32_t skip_lo, skip_hi;  // vertices in [skip_lo, skip_hi) are shaded already
+};
+__global__ void __launch_bounds__(256) k_shard_merge(const __grid_constant__ SrMergeParams p) {
+    const uint32_t tile = blockIdx.x;
+    if (p.owners.owner[tile % p.owners.period] != p.rank) return;
+    const uint32_t x0 = (tile % p.ntx) * SR_TILE_W, y0 = (tile / p.ntx) * SR_TILE_H;
+    __shared__ uint32_t rows[SR_SHARD_MAX_WORLD - 1];
+    if (threadIdx.x < p.npeers) rows[threadIdx.x] = __ldcv(p.peer_touched[threadIdx.x] + tile);
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < SR_TILE_PIXELS / 2 / 256; ++j) {
+        const uint32_t i = (j * 256 + threadIdx.x) * 2;
+        const uint32_t row = i / SR_TILE_W;
+        const uint32_t at = sr_vis_index(x0 + i % SR_TILE_W, y0 + row, p.ntx);
+        ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(p.vis + at);
+        ulonglong2 r[SR_SHARD_MAX_WORLD - 1];
+        bool any = false;
+#pragma unroll
+        for (uint32_t q = 0; q < SR_SHARD_MAX_WORLD - 1; ++q) {
+            r[q] = make_ulonglong2(0ull, 0ull);
+            if (q < p.npeers && ((rows[q] >> row) & 1u)) {
+                r[q] = __ldcv(reinterpret_cast<const ulonglong2 *>(p.peer_vis[q] + at));
+                any = true;
+            }
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < SR_SHARD_MAX_WORLD - 1; ++q) {
+            k.x = r[q].x > k.x ? r[q].x : k.x;
+            k.y = r[q].y > k.y ? r[q].y : k.y;
+        }
+        if (any) *reinterpret_cast<ulonglong2 *>(p.vis + at) = k;
+        if (p.mark != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t id = (uint32_t)(h ? k.y : k.x);
+                if (id == 0 || id - 1 >= p.ntris) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t v = __ldg(p.indices + (uint64_t)(id - 1) * 3 + c);
+                    if (v >= p.skip_lo && v < p.skip_hi) continue;
+                    const uint32_t bit = 1u << (v & 31u);
+                    if ((p.mark[v >> 5] & bit) == 0) atomicOr(p.mark + (v >> 5), bit);
+                }
+            }
+        }
+    }
+}
+
 // Cross-rank progress words live in every rank's exchange block; a rank publishes its frame number by storing it into
 // slot `me` of every peer's block (system-scope release after a system fence: everything earlier kernels of this stream
 // wrote is visible to a peer that acquires the word), and waits by polling its OWN block.
-#define SR_SHARD_MAX_WORLD 8
 struct SrShardPeers {
     uint32_t *word[SR_SHARD_MAX_WORLD];  // peer p's copy of the word array (null for p == me / absent)
 };
@@ -1120,6 +1222,8 @@ struct SrOpaqueParams {
     // PHASE 2 only: the other ranks' key buffers (peer-mapped over NVLink, same layout as `vis`)
     const unsigned long long *peer_vis[SR_SHARD_MAX_WORLD - 1];
     uint32_t npeers;
+    SrTileOwners owners;     // PHASE 2: the launch covers every tile, a CTA whose tile belongs to another rank returns
+    uint32_t elide_clear;    // PHASE 2, ranks other than 0: 32-pixel runs nothing was drawn on are not stored (rank 0 pre-filled them)
 };
 
 // PHASE 0: the whole pass (keys -> list sweep -> resolve -> write-back).
@@ -1137,7 +1241,8 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
     unsigned long long *far_row = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(stage_all) + SR_OPQ_REGION_BYTES);
     uint64_t *bar = reinterpret_cast<uint64_t *>(far_row + SR_TILE_W);
 
-    const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
+    const uint32_t tile = PHASE == 2 ? blockIdx.x : p.shard_rank + blockIdx.x * p.shard_world;
+    if (PHASE == 2 && p.owners.owner[tile % p.owners.period] != p.shard_rank) return;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
     if (p.tile_off[p.ntiles] > p.list_capacity) return;
@@ -1495,6 +1600,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
                 if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = sr_prim_canonical(p.tris, t, 0) + 1;
             }
         }
+        if (PHASE == 2 && p.elide_clear && __all_sync(0xffffffffu, id_cur == 0 || !in_frame)) continue;  // rank 0 already holds the clear
         if (bulk) {
             float *sb = stage + (nbulk & 1u) * SR_OPQ_STAGE_FLOATS;
             if (nbulk >= 2) {  // the bulk store that last read this buffer must have finished reading it

@@ -119,14 +119,18 @@ struct SrMeshView {
     uint32_t vin;
 };
 
+// Which vertices a k_vertex launch shades: [begin, end), optionally only those whose bit is set in `mask` and that lie outside
+// [skip_lo, skip_hi).  The whole mesh is {0, nverts, null, 0, 0}; a range-sharded frame shades the vertex
+// range of the rank's own triangles first and, after the key merge, only the vertices the winners of its tiles reference.
+struct SrVertexSpan {
+    uint64_t begin, end;
+    const uint32_t *mask;
+    uint64_t skip_lo, skip_hi;
+};
 template <int VS>
-__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
-                                                float4 *attr, const uint64_t onp) {
+__device__ __forceinline__ void sr_vertex_one(const SrVsConst &c, const SrMeshView &m, float4 *pos, float4 *attr, const uint64_t onp,
+                                              const uint64_t v) {
     constexpr int VIN = SrVsInfo<VS>::VIN, NK = SrVsInfo<VS>::NK, NP = (NK + 3) / 4;
-    // One vertex per thread: a warp reads 128 contiguous bytes of every SoA input plane and writes 512 contiguous
-    // bytes of positions plus 32 contiguous attribute records, so every sector that moves is fully used both ways.
-    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= m.nverts) return;
     float in[VIN];
 #pragma unroll
     for (int ch = 0; ch < VIN; ++ch) in[ch] = __ldg(m.planes + (uint64_t)ch * m.pstride + v);
@@ -142,6 +146,36 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsCons
 #pragma unroll
         for (int p = 0; p < NP; ++p)
             attr[sr_attr_at(onp, v, p)] = make_float4(out[4 + 4 * p], out[5 + 4 * p], out[6 + 4 * p], out[7 + 4 * p]);
+    }
+}
+template <int VS>
+__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
+                                                float4 *attr, const uint64_t onp, const SrVertexSpan span) {
+    // One vertex per thread: a warp reads 128 contiguous bytes of every SoA input plane and writes 512 contiguous
+    // bytes of positions plus 32 contiguous attribute records, so every sector that moves is fully used both ways.
+    const uint64_t v = span.begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= span.end) return;
+    sr_vertex_one<VS>(c, m, pos, attr, onp, v);
+}
+// The marked vertices of [span.begin, span.end) outside [skip_lo, skip_hi): a warp takes 1024 consecutive vertices, reads their
+// 32 mask words with one coalesced load and walks only the non-zero words (32 consecutive vertices each, one per lane) -- a
+// sparse mask costs one 128-byte load per 1024 vertices instead of a thread per vertex.
+template <int VS>
+__global__ void __launch_bounds__(256) k_vertex_marked(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
+                                                       float4 *attr, const uint64_t onp, const SrVertexSpan span) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base = span.begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 1024;  // span.begin is a multiple of 32
+    if (base >= span.end) return;
+    const uint64_t wi = (base >> 5) + lane;
+    uint32_t word = wi * 32 < span.end ? span.mask[wi] : 0u;
+    if (__ballot_sync(0xffffffffu, word != 0u) == 0u) return;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t wj = __shfl_sync(0xffffffffu, word, j);
+        if (wj == 0u) continue;
+        const uint64_t v = base + j * 32 + lane;
+        if (((wj >> lane) & 1u) == 0u || v >= span.end || (v >= span.skip_lo && v < span.skip_hi)) continue;
+        sr_vertex_one<VS>(c, m, pos, attr, onp, v);
     }
 }
 
@@ -175,6 +209,22 @@ __global__ void __launch_bounds__(256) k_normalize(float4 *pos, uint64_t n, cons
     float p[4] = {v.x, v.y, v.z, v.w};
     sr_normalize_vertex(c.vpm, p);
     pos[i] = make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// smallest and one-past-largest vertex index a run of indices references (out[0] = min, out[1] = max + 1; out preset to ~0, 0)
+__global__ void __launch_bounds__(256) k_index_minmax(const uint32_t *idx, uint64_t n, uint32_t *out) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = idx[i];
+        lo = min(lo, v);
+        hi = max(hi, v + 1u);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
 }
 
 // AoS -> SoA plane transpose used by mesh upload and vertex injection

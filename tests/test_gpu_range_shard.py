@@ -105,6 +105,73 @@ def test_range_sharded_frame_is_bit_identical(P, ctx, world, lanes):
                 c.close()
 
 
+@pytest.mark.parametrize("world,fused", [(2, False), (3, False), (2, True)])
+def test_range_sharded_mesh_with_lazy_vertex_stage(P, ctx, world, fused, monkeypatch):
+    """A real mesh through run_to_fragment: with a shard group attached the vertex stage is recorded and each rank shades
+    only the vertex range of its own triangles plus the vertices the winners of its tiles reference (marked by the merge
+    kernel).  `fused` = the variant that merges the peers' keys inside the resolve (whole mesh shaded on every rank).
+    Frame bit-identical to the single-context frame; a later consumer of the draw's vertices still sees the whole mesh."""
+    w, h = 640, 360
+    mesh = scenes.make_grid(200, 170, 4, seed=0x5EED0003)
+    assert mesh.ntris >= 65536
+    u = scenes.grid_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.1, 100.0)
+
+    def draw(pipe, gmesh):
+        return pipe.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE)
+
+    fb1 = P.RenderBuffer.with_dimensions(ctx, w, h)
+    fb1.clear(H.CLEAR)
+    p1, m1 = P.Pipeline.from_framebuffer(fb1, u), P.Mesh(ctx, mesh)
+    d1 = draw(p1, m1)
+    verts_expect = d1.download(0)
+    d1.run(sr.FS_SUZANNE)
+    expect = fb1.download()
+    for x in (p1, m1, fb1):
+        x.destroy()
+
+    monkeypatch.setenv("SR_SHARD_SHARES", "1,1,16" if fused else "2,1,0")  # (read by sr_shard_create: tuning knob)
+    ctxs = [P.Context(0) for _ in range(world)]
+    groups = []
+    for r, c in enumerate(ctxs):
+        c.set_tile_shard(r, world)
+        groups.append(P.ShardGroup(c, w, h, 1))
+    for g in groups:
+        g.connect_local(groups)
+    for g, c in zip(groups, ctxs):
+        g.attach(c, 0)
+    target = P.RenderBuffer.with_dimensions(ctxs[0], w, h)
+    fbs = [target] + [target.alias(c) for c in ctxs[1:]]
+    pipes = [P.Pipeline.from_framebuffer(fb, u) for fb in fbs]
+    meshes = [P.Mesh(c, mesh) for c in ctxs]
+    last = None
+    for f in range(3):
+        stages = []
+        for r in range(world):
+            fbs[r].clear(H.CLEAR)
+            stages.append(draw(pipes[r], meshes[r]))
+        for st in stages:
+            dup = st.duplicate()
+            st.run(sr.FS_SUZANNE)
+            last = dup
+    for c in ctxs:
+        c.synchronize()
+    assert [g.status() for g in groups] == [0] * world
+    H.assert_bits_equal(target.download(), expect, f"range-sharded mesh frame, world {world}")
+    # the duplicate of the last rank's draw (lazy vertex stage, partly shaded by its frame) yields the whole mesh on demand
+    H.assert_bits_equal(last.download(0), verts_expect, "vertices after a lazy vertex stage")
+    for c in ctxs:
+        P.ShardGroup.detach(c)
+    for x in pipes + meshes:
+        x.destroy()
+    for fb in fbs[::-1]:
+        fb.destroy()
+    for g in groups:
+        g.destroy()
+    for c in ctxs:
+        c.close()
+
+
 def test_range_shard_falls_back_for_ineligible_draws(P, ctx):
     """Draws the range path does not take (few triangles, draws onto existing contents, blending) use plain sort-first
     tile sharding on the same contexts and still composite to the single-context frame."""
