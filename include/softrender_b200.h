@@ -20,6 +20,14 @@
  *    defined for every later call on the same context (downloads synchronise), which is
  *    the observable behaviour of the reference's `pool.scoped` joins.
  *  - there is NO CPU fallback: every entry point needs a CUDA device.
+ *  - lifetimes: a handle may be destroyed as soon as the calls that take it have returned, EXCEPT that a pipeline keeps
+ *    plain references to its framebuffer and bound texture / texture-source framebuffer, and a draw to its pipeline:
+ *    destroy draws before their pipeline, a pipeline before its framebuffer and textures (the reference's borrows,
+ *    `&'a mut P` in src/pipeline/stages/, enforce the same order at compile time).  Device buffers themselves are
+ *    reference counted: a mesh, texture or framebuffer may be destroyed while enqueued work still reads it, and a
+ *    context stays valid until its last child is gone.  All objects of one draw must belong to one context;
+ *    handles of different contexts are rejected with SR_ERR_INVALID_STATE (sr_framebuffer_alias / _ipc_open give another
+ *    context a handle on the same pixels; detach a shard group from its contexts before destroying it).
  */
 #ifndef SOFTRENDER_B200_H
 #define SOFTRENDER_B200_H

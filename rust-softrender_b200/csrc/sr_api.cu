@@ -81,6 +81,8 @@ struct sr_context {
     uint32_t zero_off_tiles = 0;
     struct sr_shard *shard = nullptr;             // range-sharded front end (sr_context_attach_shard)
     uint32_t shard_lane = 0;
+    cudaStream_t aux = nullptr;                   // second stream: rank 0's clear pre-fill of foreign tiles runs beside its k_micro
+    cudaEvent_t ev_aux[2] = {};
     cudaEvent_t ev_dbg[6] = {};                   // SR_SHARD_DEBUG: finer timestamps inside a range-sharded frame (diagnosis only)
     bool ev_dbg_valid = false;
     sr_stage_times times = {};
@@ -902,7 +904,20 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
             done_peers.word[p] = sh->done(sh->peer[p], lane);
         }
     if (n > 1) SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->done(sh->block, lane), sh->world, sh->rank, n - 1, timeout_ns, sh->error());   // b
-    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->view(), sh->owners, sh->rank, n == 1 ? 1u : 0u, sh->rank == 0 ? 1u : 0u);  // c
+    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->view(), sh->owners, sh->rank, n == 1 ? 1u : 0u, 0u);                     // c
+    if (sh->rank == 0) {  // the framebuffer pre-fill is pure HBM writes, k_micro is latency bound: they share the GPU well
+        if (!c->aux) {
+            SR_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+            SR_CUDA(cudaEventCreateWithFlags(&c->ev_aux[0], cudaEventDisableTiming));
+            SR_CUDA(cudaEventCreateWithFlags(&c->ev_aux[1], cudaEventDisableTiming));
+        }
+        SR_CUDA(cudaEventRecord(c->ev_aux[0], c->stream));
+        SR_CUDA(cudaStreamWaitEvent(c->aux, c->ev_aux[0], 0));
+        k_fb_fill_foreign<<<ntiles, 256, 0, c->aux>>>(fb->view(), sh->owners, sh->rank);
+        c->launches++;
+        SR_CUDA(cudaGetLastError());
+        SR_CUDA(cudaEventRecord(c->ev_aux[1], c->aux));
+    }
     record(c, 7);
     Buf count, off, lcount, lids, lrects;
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
@@ -966,6 +981,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
               lrects->as<uint32_t>(), fb->ntx, ntiles, 0u, 1u, off->as<uint32_t>(), count->as<uint32_t>(), c->list_arena->as<uint32_t>(), c->list_cap);
     SR_TRY(launch_opaque_sweep(c, ntiles, op));
     SR_LAUNCH(c, k_vis_rows_touched, ntiles, 256, 0, vis, fb->ntx, sh->owners, sh->rank, sh->touched(sh->block, lane));
+    if (sh->rank == 0) SR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_aux[1], 0));  // the pre-fill is in place before "ready" goes out
     SR_LAUNCH(c, k_shard_signal, 1, 32, 0, ready_peers, sh->rank, n);                                                    // e
     stamp(0);
     SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->ready(sh->block, lane), sh->world, sh->rank, n, timeout_ns, sh->error());   // f
@@ -1063,6 +1079,7 @@ static void preload_ranged_kernels() {
     preload(k_vis_clear_foreign);
     preload(k_shard_merge);
     preload(k_vis_rows_touched);
+    preload(k_fb_fill_foreign);
     preload(k_vertex_marked<SR_VS_SUZANNE>);
     preload(k_vertex_marked<SR_VS_FULL_EXAMPLE>);
     preload(k_index_minmax);
@@ -1195,6 +1212,9 @@ int sr_context_destroy(sr_context *c) {
     if (c->ev_front) { cudaEventDestroy(c->ev_front); c->ev_front = nullptr; }
     cudaStreamDestroy(c->stream);
     c->stream = nullptr;
+    if (c->aux) { cudaStreamDestroy(c->aux); c->aux = nullptr; }
+    for (auto &e : c->ev_aux)
+        if (e) { cudaEventDestroy(e); e = nullptr; }
     if (c->pinned) { cudaFreeHost(c->pinned); c->pinned = nullptr; }
     ctx_unref(c);
     return SR_OK;
@@ -1248,6 +1268,9 @@ int sr_context_wait_for(sr_context *waiter, sr_context *other, uint32_t point) {
         }
         return SR_OK;
     }
+    // "everything enqueued so far" includes a pass that skipped itself on the device because its tile lists overflowed: it is
+    // re-enqueued here (settle), before the event, so that the waiter can never start ahead of the replay
+    SR_TRY(settle(other));
     cudaEvent_t ev;
     SR_CUDA(cudaSetDevice(other->device));
     SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1329,9 +1352,12 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
 }
 int sr_framebuffer_destroy(sr_framebuffer *fb) {
     if (!fb) return SR_OK;
-    settle(fb->ctx);
-    if (fb->is_peer && fb->aos) cudaIpcCloseMemHandle(fb->aos);
+    sr_context *c = fb->ctx;
+    const bool peer = fb->is_peer;
+    if (!c->closed) settle(c);
+    if (peer && fb->aos) cudaIpcCloseMemHandle(fb->aos);
     delete fb;
+    if (peer) ctx_unref(c);
     return SR_OK;
 }
 int sr_framebuffer_clear(sr_framebuffer *fb, const float color[4]) {
@@ -1393,6 +1419,7 @@ int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *dept
 }
 int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const float *depth, const uint8_t *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (stencil && !fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");  // before anything is enqueued
     sr_context *c = fb->ctx;
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
@@ -1480,6 +1507,7 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
     fb->aos = reinterpret_cast<float *>(p);
     fb->is_peer = true;
     fb->pending_clear = false;
+    ++c->refs;  // owns no buffer of the context, so it holds the reference itself (released by sr_framebuffer_destroy)
     *out = fb;
     return SR_OK;
 }
@@ -1718,6 +1746,7 @@ int sr_pipeline_create(sr_context *c, sr_framebuffer *fb, const sr_uniforms *u, 
     if (!c || !fb || !u || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (fb->width == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero width");
     if (fb->height == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero height");
+    if (fb->ctx != c) return sr_fail(SR_ERR_INVALID_STATE, "framebuffer belongs to another context (use sr_framebuffer_alias / sr_framebuffer_ipc_open)");
     auto *p = new sr_pipeline();
     p->ctx = c;
     p->fb = fb;
@@ -1738,6 +1767,7 @@ int sr_pipeline_set_framebuffer(sr_pipeline *p, sr_framebuffer *fb) {
     if (!p || !fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (fb->width == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero width");
     if (fb->height == 0) return sr_fail(SR_ERR_INVALID_ARGUMENT, "Framebuffer must have a non-zero height");
+    if (fb->ctx != p->ctx) return sr_fail(SR_ERR_INVALID_STATE, "framebuffer belongs to another context (use sr_framebuffer_alias / sr_framebuffer_ipc_open)");
     p->fb = fb;
     p->stencil_test = SR_STENCIL_ALWAYS;  // with_framebuffer: stencil_config: Default::default() (mod.rs:137)
     p->stencil_op = SR_STENCIL_KEEP;
@@ -1751,6 +1781,7 @@ int sr_pipeline_set_stencil_config(sr_pipeline *p, uint32_t test, uint32_t op) {
 }
 int sr_pipeline_bind_texture(sr_pipeline *p, sr_texture *t) {
     if (!p) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (t && t->ctx != p->ctx) return sr_fail(SR_ERR_INVALID_STATE, "texture belongs to another context");
     p->texture = t;
     p->fb_texture = nullptr;
     return SR_OK;
@@ -1774,6 +1805,7 @@ int sr_pipeline_set_sampler(sr_pipeline *p, uint32_t filter, uint32_t edge, cons
 int sr_render_mesh(sr_pipeline *p, sr_mesh *m, uint32_t primitive, int has_sv, uint32_t sv, sr_draw **out) {
     if (!p || !m || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (primitive < SR_POINT || primitive > SR_TRIANGLE) return sr_fail(SR_ERR_INVALID_ARGUMENT, "primitive %u", primitive);
+    if (m->ctx != p->ctx) return sr_fail(SR_ERR_INVALID_STATE, "mesh and pipeline belong to different contexts (one stream orders their work)");
     if (m->nindices % primitive != 0)
         return sr_fail(SR_ERR_INVALID_ARGUMENT, "assertion failed: mesh.indices.len() %% T::num_vertices() == 0 (%llu %% %u)",
                        (unsigned long long)m->nindices, primitive);

@@ -66,7 +66,9 @@ __device__ __forceinline__ float sr_dot4(const float *a, const float *b) {
 // Newton correction q is within one ulp of n/det, the residual n - q*det is then exact in an FMA, and
 // q' = RN(q + rem*r) is the correctly rounded quotient (Markstein's theorem).  Valid for |det| in
 // [2^-40, 2^40] and |n| in [2^-60, 2^60] (no over/underflow anywhere); checked against __fdiv_rn on the GPU
-// by tests/test_gpu_parity.py::test_exact_division_shortcut.
+// by tests/test_gpu_parity.py::test_exact_division_shortcut.  A zero numerator is outside that range (the sign of the zero
+// quotient would not follow IEEE for n = -0): every coverage call site tests |n| >= 2^-60 first and divides generically
+// otherwise; the texel/255 call sites only ever pass n >= +0 over a positive divisor, where +0 comes out.
 __device__ __forceinline__ float sr_div_exact(float n, float det, float rdet) {
     float q = n * rdet;
     float rem = fmaf(-q, det, n);

@@ -530,6 +530,14 @@ struct SrTileOwners {
     uint8_t owner[SR_OWNER_PERIOD_MAX];
     uint32_t period;
 };
+__device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t x0, uint32_t y0) {
+    const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
+    const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
+        float *row = fb.aos + ((uint64_t)(y0 + r) * fb.width + x0) * 5;
+        for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i % 5];
+    }
+}
 // `fill`: rank 0 also writes the clear colour + far depth into the framebuffer pixels of the tiles it does NOT own, so that their
 // owners need not send pixels nothing was drawn on over NVLink (the frame starts from a clear: that is what selects this path).
 __global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *vis, const SrFbView fb, const SrTileOwners own, uint32_t rank,
@@ -542,6 +550,16 @@ __global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *v
         *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(x0 + i % SR_TILE_W, y0 + i / SR_TILE_W, fb.ntx)) =
             make_ulonglong2(SR_VIS_FAR_KEY, SR_VIS_FAR_KEY);
     if (!fill || mine || x0 >= fb.width) return;
+    sr_fill_tile_clear(fb, x0, y0);
+}
+// the framebuffer half of the above on its own (rank 0 runs it on a second stream, beside its k_micro)
+__global__ void __launch_bounds__(256) k_fb_fill_foreign(const SrFbView fb, const SrTileOwners own, uint32_t rank) {
+    const uint32_t tile = blockIdx.x;
+    if (own.owner[tile % own.period] == rank) return;
+    const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
+    if (x0 < fb.width) sr_fill_tile_clear(fb, x0, y0);
+}
+#if 0
     const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
     const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
     for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
@@ -549,6 +567,7 @@ __global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *v
         for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i % 5];
     }
 }
+#endif
 // The merge of a range-sharded frame as a streaming kernel of its own (the alternative to merging inside the resolve,
 // k_tile_opaque PHASE 2 with npeers > 0): one light CTA per owned tile pulls the peers' keys of that tile straight from
 // peer-mapped memory (16-byte coalesced loads over NVLink, all peers' loads of a thread in flight together), max-merges them

@@ -314,6 +314,63 @@ def test_list_arena_overflow_is_replayed(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="replayed tile pass")
 
 
+def test_wait_for_covers_a_replayed_pass(P, ctx):
+    """sr_context_wait_for(waiter, other, 0) promises that the waiter starts after everything enqueued on `other` so far.
+    A draw whose tile lists overflowed skipped itself on the device and is only re-enqueued by the next call that settles
+    the context: wait_for must settle `other` before it records its event, or a consumer on the waiter's stream would read
+    an incomplete frame.  The consumer here is a render-to-texture-style pass on a second context that draws into the
+    SAME pixels through an alias: a second opaque draw of nearer triangles, whose result depends on the first frame being
+    complete underneath it (it starts from the depth already stored)."""
+    rng = np.random.default_rng(81)
+    w, h, n = 320, 200, 400
+    far = H.random_screen_triangles(rng, n, w, h, integer_depth=True)
+    near = H.random_screen_triangles(rng, 60, w, h, integer_depth=True)
+    near[:, 2] = -0.5  # in front of everything in `far` (depths -1 .. -5)
+    idx_far, idx_near = np.arange(3 * n, dtype=np.uint32), np.arange(3 * 60, dtype=np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    ofb = oracle_fb(w, h)
+    for v, ix in ((far, idx_far), (near, idx_near)):
+        od = ob.OracleDraw(sr.TRIANGLE, ix)
+        od.set_vertices(v, 1)
+        od.fragment_run(ofb, sr.FS_FLAT, u)
+    other, waiter = P.Context(0), P.Context(0)
+    fb = make_fb(P, other, w, h)
+    view = fb.alias(waiter)
+    p_other, p_waiter = P.Pipeline.from_framebuffer(fb, u), P.Pipeline.from_framebuffer(view, u)
+    other.set_list_capacity(4)  # the first draw's lists cannot fit: its tile pass skips itself
+    p_other.draw_from_vertices(sr.TRIANGLE, far, idx_far, 1).run(sr.FS_FLAT)
+    waiter.wait_for(other, 0)   # must re-enqueue the skipped pass on `other` before the event
+    p_waiter.draw_from_vertices(sr.TRIANGLE, near, idx_near, 1).run(sr.FS_FLAT)
+    waiter.synchronize()
+    other.synchronize()
+    assert other.list_capacity() > 4
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="consumer after wait_for")
+    for x in (p_waiter, p_other, view, fb):
+        x.destroy()
+    waiter.close()
+    other.close()
+
+
+def test_handles_of_different_contexts_are_rejected(P, ctx):
+    """Every object of a draw lives in one context (= one CUDA stream that orders their work and their memory reuse)."""
+    other = P.Context(0)
+    u = scenes.suzanne_uniforms(64, 64)
+    fb = make_fb(P, ctx, 64, 64)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    mesh = P.Mesh(other, H.suzanne_mesh())
+    with pytest.raises(Exception, match="different contexts"):
+        pipe.render_mesh(sr.TRIANGLE, mesh)
+    tex = P.Texture(other, scenes.checker_texture(16, 2))
+    with pytest.raises(Exception, match="another context"):
+        pipe.bind_texture(tex)
+    fb2 = make_fb(P, other, 64, 64)
+    with pytest.raises(Exception, match="another context"):
+        pipe.with_framebuffer(fb2)
+    for x in (tex, mesh, fb2, pipe, fb):
+        x.destroy()
+    other.close()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_tile_sharding_is_invisible(P, ctx, world):
     """Sort-first sharding: `world` contexts each rasterise the tiles with index % world == rank into ONE shared

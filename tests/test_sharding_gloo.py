@@ -77,6 +77,60 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         dist.destroy_process_group()
 
 
+def _worker_ranged(rank: int, world: int, port: int, out_dir: str):
+    """Range-sharded front end on the host side: every rank rasterises ITS triangle range (with the oracle, global
+    primitive numbers), the ranks' (depth, winner) planes become keys, the per-pixel max over ranks must be the frame the
+    oracle renders from the whole mesh -- depth ties between ranges included."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import softrender_b200 as sr
+        from softrender_b200 import scenes, sharding
+        import helpers as H
+        import oracle_binding as ob
+
+        w, h = 160, 120
+        rng = np.random.default_rng(11)
+        n = 900
+        verts = H.random_screen_triangles(rng, n, w, h, integer_depth=True, max_size=25.0)
+        idx = np.arange(3 * n, dtype=np.uint32)
+        u = scenes.suzanne_uniforms(w, h)
+
+        def render(i0, i1):
+            ofb = ob.OracleFramebuffer(w, h)
+            ofb.clear(H.CLEAR)
+            od = ob.OracleDraw(sr.TRIANGLE, idx[3 * i0:3 * i1])
+            od.set_vertices(verts, 1)
+            od.fragment_run(ofb, sr.FS_FLAT, u)
+            win = np.where(ofb.winner > 0, ofb.winner + np.uint32(i0), np.uint32(0))  # global primitive numbers
+            return ofb.depth.copy(), win
+
+        t0, t1 = sharding.triangle_range(n, rank, world)
+        d, wv = render(t0, t1)
+        mine = sharding.depth_keys(d, wv)
+        parts = [torch.zeros(w * h, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(mine.view(np.int64)))
+        merged = sharding.merge_keys([p.numpy().view(np.uint64) for p in parts])
+        if rank == 0:
+            fd, fw = render(0, n)
+            assert np.array_equal(merged, sharding.depth_keys(fd, fw)), "max-merge of the ranks' keys != single-rank keys"
+            ranges = [sharding.triangle_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            for k0, k in [(1, 1), (2, 1), (0, 1), (1, 3)]:
+                t = sharding.owner_table(world, k0, k)
+                assert len(t) == k0 + k * (world - 1) and t.count(0) == k0 and all(t.count(r) == k for r in range(1, world))
+            open(os.path.join(out_dir, "ok_ranged"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_range_sharded_key_merge(tmp_path):
+    world = 2
+    mp.spawn(_worker_ranged, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok_ranged").exists()
+
+
 def test_two_rank_tile_composite_and_timing(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
