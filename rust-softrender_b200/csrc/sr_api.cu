@@ -507,7 +507,7 @@ static int launch_opaque_merge(sr_context *c, uint32_t ntiles, const SrOpaquePar
         SR_CUDA(cudaFuncSetAttribute(k_tile_opaque<FS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[c->device & 15] = true;
     }
-    size_t smem = SR_OPQ_MERGE_SMEM_BYTES;
+    size_t smem = p.npeers > 0 ? SR_OPQ_MERGE_SMEM_BYTES : SR_OPQ_SMEM_BYTES;  // the peer-key staging buffer only when peers are pulled here
     if (ctas_per_sm > 0) smem = std::max<size_t>(smem, std::min<size_t>(200 * 1024, (size_t)(227 * 1024) / (ctas_per_sm + 1) + 1024));
     SR_LAUNCH(c, (k_tile_opaque<FS, false, 2>), ntiles, SR_OPQ_THREADS, smem, p);
     return SR_OK;

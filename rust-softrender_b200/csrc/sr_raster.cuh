@@ -1252,8 +1252,13 @@ struct SrOpaqueParams {
 //          keys of the same tile with TMA bulk copies from peer-mapped memory, max-merges them in shared memory and
 //          resolves -- the exchange is fused into the resolve, there is no staging copy in HBM and no separate collective.
 //          The merged key is exactly the key one GPU would have reduced: max over all fragments of (depth key, primitive+1).
+#ifndef SR_OPQ_RESOLVE_CTAS
+#define SR_OPQ_RESOLVE_CTAS 5  // the resolve without the list sweep needs 51 registers without spilling.  (Measured on config 3, one GPU:
+                               // sweep and resolve as two launches with 6 resolve CTAs per SM = 0.1268 ms against 0.1264 ms for the
+                               // combined kernel at 4 -- occupancy is not what bounds the resolve; the combined kernel stays.)
+#endif
 template <int FS, bool EXTRA, int PHASE = 0>
-__global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrOpaqueParams p) {
+__global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CTAS : SR_OPQ_MIN_CTAS) k_tile_opaque(const __grid_constant__ SrOpaqueParams p) {
     extern __shared__ __align__(128) unsigned char sr_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sr_smem);
     float *stage_all = reinterpret_cast<float *>(keys + SR_TILE_PIXELS);
@@ -1303,7 +1308,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
         __syncthreads();
     }
 
-    if (PHASE == 2) {
+    if (PHASE == 2 && p.npeers > 0) {  // (npeers == 0: the keys are already merged -- k_shard_merge -- or there is one GPU)
         unsigned long long *pbuf[2] = {reinterpret_cast<unsigned long long *>(stage_all),
                                        reinterpret_cast<unsigned long long *>(sr_smem + SR_OPQ_MERGE_OFFSET)};
         uint64_t *mb = reinterpret_cast<uint64_t *>(sr_smem + SR_OPQ_MERGE_OFFSET + SR_TILE_PIXELS * 8);
@@ -1338,7 +1343,6 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, SR_OPQ_MIN_CTAS) k_tile_opaque
             __syncthreads();
             if (k + 2 < p.npeers) issue(k + 2);
         }
-        if (p.npeers == 0) __syncthreads();
     }
 
     const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;  // last pixel of the tile in the frame
