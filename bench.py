@@ -283,6 +283,7 @@ def other_configs(ctx):
           for rot, off in [(45.0, -1.6), (165.0, 0.0), (285.0, 1.6)]]
     pipe = P.Pipeline.from_framebuffer(fb, us[0])
     pipe.bind_texture(tex)
+    pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
     vp = scenes.Viewport.new(w, h, 0.1, 1000.0)
 
     def full_example():

@@ -206,7 +206,8 @@ int sr_pipeline_bind_texture(sr_pipeline *, sr_texture *);
  * is bound (the pipeline borrows it, as `TextureBufferRef<'a>` borrows its parent); unbind with NULL before destroying it. */
 int sr_pipeline_bind_framebuffer_texture(sr_pipeline *, sr_framebuffer *src);
 /* Filter and Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45) for every sampling shader of the pipeline.
- * border_rgba: 4 floats, read only for SR_EDGE_BORDER (NULL = transparent black).  Default: BILINEAR, CLAMP. */
+ * border_rgba: 4 floats, read only for SR_EDGE_BORDER (NULL = transparent black).  Default: NEAREST, CLAMP -- `impl Default for Filter` /
+ * `for Edge` (src/texture.rs:27-31,43-45); the config-2 scene sets BILINEAR explicitly. */
 int sr_pipeline_set_sampler(sr_pipeline *, uint32_t filter, uint32_t edge, const float *border_rgba);
 
 /* ---- draw: the VertexShader -> GeometryShader -> FragmentShader chain ---------------------- */

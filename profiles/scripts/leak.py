@@ -13,7 +13,7 @@ vp = scenes.Viewport.new(size, size, 0.1, 1000.0)
 fb = P.RenderBuffer.with_dimensions(ctx, size, size)
 tex = P.Texture(ctx, scenes.checker_texture(64, 8))
 u = scenes.full_example_uniforms(1.0, np.deg2rad(75.0), 1.0, 0.3, np.deg2rad(65.0), 0.0)
-pipe = P.Pipeline.from_framebuffer(fb, u); pipe.bind_texture(tex)
+pipe = P.Pipeline.from_framebuffer(fb, u); pipe.bind_texture(tex); pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
 marks = []
 for it in range(3001):
     gm = P.Mesh(ctx, mesh)  # upload + destroy every frame (the e2e pattern)

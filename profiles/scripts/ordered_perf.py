@@ -21,7 +21,7 @@ fb = P.RenderBuffer.with_dimensions(ctx, w, h)
 for name, mesh in (("suzanne", H.suzanne_mesh(with_uv=True)), ("suzanne x2 subdivided", scenes.subdivide(H.suzanne_mesh(with_uv=True), 2))):
     gm = P.Mesh(ctx, mesh)
     us = [scenes.full_example_uniforms(w / h, np.deg2rad(75.0), 2.0, np.deg2rad(rot), np.deg2rad(65.0), off) for rot, off in [(45.0, -1.6), (165.0, 0.0), (285.0, 1.6)]]
-    pipe = P.Pipeline.from_framebuffer(fb, us[0]); pipe.bind_texture(tex)
+    pipe = P.Pipeline.from_framebuffer(fb, us[0]); pipe.bind_texture(tex); pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
     for blend in (None, sr.BLEND_ALPHA_OVER):
         def frame():
             fb.clear(H.CLEAR)

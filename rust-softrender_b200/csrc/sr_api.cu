@@ -8,6 +8,8 @@
 #include <vector>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sr_common.cuh"
 #include "sr_shaders.cuh"
 #include "sr_stages.cuh"
@@ -146,6 +148,15 @@ int sr_context::alloc(size_t bytes, Buf *out) {
 
 static inline uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// NVTX range around the host side of a stage (tracing): visible on the timeline of any NVTX-aware tool,
+// free when none is attached (NVTX3 is header-only and resolves its injection library lazily)
+struct SrRange {
+    explicit SrRange(const char *name) { nvtxRangePushA(name); }
+    ~SrRange() { nvtxRangePop(); }
+    SrRange(const SrRange &) = delete;
+    SrRange &operator=(const SrRange &) = delete;
+};
+
 struct sr_framebuffer {
     sr_context *ctx;
     uint32_t width, height, format;
@@ -214,7 +225,7 @@ struct sr_pipeline {
     uint32_t stencil_test = SR_STENCIL_ALWAYS, stencil_op = SR_STENCIL_KEEP;
     sr_texture *texture = nullptr;
     sr_framebuffer *fb_texture = nullptr;  // render-to-texture source, sampled in place (texturebuffer.rs:12-58)
-    uint32_t tex_filter = SR_FILTER_BILINEAR, tex_edge = SR_EDGE_CLAMP;  // what the shipped scene samples with
+    uint32_t tex_filter = SR_FILTER_NEAREST, tex_edge = SR_EDGE_CLAMP;  // impl Default for Filter / Edge (src/texture.rs:27-31,43-45)
     float tex_border[4] = {0, 0, 0, 0};
 };
 
@@ -847,6 +858,7 @@ static int materialize_vertices(sr_draw *d) {
 // finds the vertex range of the rank's triangles).
 static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
                                    const std::vector<Buf> &keep, sr_draw *d) {
+    SrRange nvtx("softrender: range-sharded opaque pass");
     sr_shard *sh = c->shard;
     const uint32_t lane = c->shard_lane, ntiles = fb->ntx * fb->nty;
     const uint32_t t0 = (uint32_t)((uint64_t)tp.ntris * sh->rank / sh->world), t1 = (uint32_t)((uint64_t)tp.ntris * (sh->rank + 1) / sh->world);
@@ -1373,6 +1385,7 @@ int sr_framebuffer_dimensions(const sr_framebuffer *fb, uint32_t *w, uint32_t *h
     return SR_OK;
 }
 int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
+    SrRange nvtx("softrender: framebuffer download");
     if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     const size_t need = (size_t)fb->width * fb->height * 20;
     if (nbytes != need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, need);
@@ -1825,6 +1838,7 @@ int sr_render_mesh(sr_pipeline *p, sr_mesh *m, uint32_t primitive, int has_sv, u
 }
 
 static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
+    SrRange nvtx("softrender: vertex stage");
     if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (d->stage != STAGE_VERTEX || !d->mesh_planes) return sr_fail(SR_ERR_INVALID_STATE, "vertex stage already consumed");
     sr_pipeline *p = d->pipeline;
@@ -1908,6 +1922,7 @@ static int clip_small(sr_context *c, const SrGeoIn &in, uint32_t nk, VertexStrea
 extern "C" {
 
 int sr_geometry_run(sr_draw *d, uint32_t gs) {
+    SrRange nvtx("softrender: geometry stage");
     if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (d->stage != STAGE_GEOMETRY) return sr_fail(SR_ERR_INVALID_STATE, "geometry stage needs clip-space vertices");
     if (gs > SR_GS_CLIP_SH) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown geometry shader %u", gs);
@@ -2025,6 +2040,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
 int sr_geometry_clip_primitives(sr_draw *d) { return sr_geometry_run(d, SR_GS_CLIP); }
 
 int sr_geometry_finish(sr_draw *d, const sr_viewport *vp) {
+    SrRange nvtx("softrender: finish");
     if (!d || !vp) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (d->stage != STAGE_GEOMETRY) return sr_fail(SR_ERR_INVALID_STATE, "finish needs clip-space vertices");
     sr_pipeline *p = d->pipeline;
@@ -2080,6 +2096,7 @@ int sr_fragment_set_blend(sr_draw *d, uint32_t blend) {
 }
 
 int sr_fragment_run(sr_draw *d, uint32_t fs) {
+    SrRange nvtx("softrender: fragment stage");
     if (!d) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (d->stage != STAGE_FRAGMENT) return sr_fail(SR_ERR_INVALID_STATE, "fragment stage needs screen-space vertices (finish / run_to_fragment)");
     const int need = fs_nk(fs);

@@ -33,9 +33,9 @@ class SoTexture(ctypes.Structure):
 
 def make_texture(texture, sampler=None):
     """so_texture of a (h, w, 4) array: uint8 = image texels, float32 = a framebuffer's colour sampled in place
-    (texturebuffer.rs:12-58).  sampler = (filter, edge, border) or None for the shipped scene's Bilinear + Clamp.
+    (texturebuffer.rs:12-58).  sampler = (filter, edge, border) or None for the reference's defaults (Nearest, Clamp: src/texture.rs:27-45).
     Returns (struct, array kept alive)."""
-    filt, edge, border = sampler if sampler is not None else (1, 0, None)
+    filt, edge, border = sampler if sampler is not None else (0, 0, None)  # Filter::default() = Nearest, Edge::default() = Clamp
     b = (ctypes.c_float * 4)(*([float(x) for x in border] if border is not None else [0.0] * 4))
     if np.asarray(texture).dtype == np.float32:
         t = np.ascontiguousarray(texture, np.float32)

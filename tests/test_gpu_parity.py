@@ -714,6 +714,7 @@ def test_full_example_scene(P, ctx, textured, camera_distance):
         if pipe is None:
             pipe = P.Pipeline.from_framebuffer(fb, u)
             pipe.bind_texture(gtex)
+            pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)  # config 2 samples Bilinear + Clamp
         else:
             pipe.set_uniforms(u)
         od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
@@ -724,7 +725,7 @@ def test_full_example_scene(P, ctx, textured, camera_distance):
         if camera_distance < 1.0:
             od.clip_primitives()
             gs = gs.clip_primitives()
-        od.finish(vp).fragment_run(ofb, fs, u, texture=tex)
+        od.finish(vp).fragment_run(ofb, fs, u, texture=tex, sampler=(sr.FILTER_BILINEAR, sr.EDGE_CLAMP, None) if tex is not None else None)
         gs.finish(vp).with_blend(sr.BLEND_ALPHA_OVER).run(fs)
     assert np.array_equal(fb.download_winner(), ofb.winner)
     H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="full_example")

@@ -107,6 +107,7 @@ def test_config2_full_example_1080p_vs_oracle(P, ctx, camera_distance):
           for rot, off in [(45.0, -1.6), (165.0, 0.0), (285.0, 1.6)]]
     pipe = P.Pipeline.from_framebuffer(fb, us[0])
     pipe.bind_texture(gtex)
+    pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
     clip = camera_distance < 1.0
     for u in us:
         pipe.set_uniforms(u)
@@ -117,7 +118,7 @@ def test_config2_full_example_1080p_vs_oracle(P, ctx, camera_distance):
         if clip:
             od.clip_primitives()
             gs = gs.clip_primitives()
-        od.finish(vp).fragment_run(ofb, sr.FS_FULL_EXAMPLE_TEXTURED, u, texture=tex)
+        od.finish(vp).fragment_run(ofb, sr.FS_FULL_EXAMPLE_TEXTURED, u, texture=tex, sampler=(sr.FILTER_BILINEAR, sr.EDGE_CLAMP, None))
         gs.finish(vp).with_blend(sr.BLEND_ALPHA_OVER).run(sr.FS_FULL_EXAMPLE_TEXTURED)
     assert np.array_equal(fb.download_winner(), ofb.winner), "config 2 triangle pass: winner ids of the last instance"
     H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="config 2 triangle pass")

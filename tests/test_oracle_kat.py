@@ -276,7 +276,7 @@ def test_texture_sampler_known_answers():
     r = ob.texture_sample(img, 0.3, 0.6, (N, CLAMP, None))
     exp = np.array([1.0, np.float32(128 / 255) ** np.float32(2.2), 0.0, np.float32(64) / np.float32(255)], np.float32)
     assert np.allclose(r, exp, rtol=1e-6, atol=0) and r[3] == exp[3]
-    # default sampler state = the shipped scene's Bilinear + Clamp (full_example/src/shaders.rs)
+    # default sampler state = `impl Default for Filter` / `for Edge`: Nearest + Clamp (src/texture.rs:27-31,43-45)
     chk = scenes.checker_texture(16, 4)
     for u, v in [(0.1, 0.9), (0.5, 0.5), (1.0, 0.0), (0.333, 0.777)]:
-        assert np.array_equal(ob.texture_sample(chk, u, v, (B, CLAMP, None)), ob.texture_sample(chk, u, v, None))
+        assert np.array_equal(ob.texture_sample(chk, u, v, (N, CLAMP, None)), ob.texture_sample(chk, u, v, None))
