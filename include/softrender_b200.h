@@ -153,12 +153,16 @@ int sr_framebuffer_download(sr_framebuffer *, void *dst, size_t nbytes);
  * order 0: bytes r,g,b,a (image crate Rgba<u8>, src/image/color.rs:60-90); order 1: a,b,g,r (the example's SDL
  * RGBA8888 streaming texture).  nbytes must be width*height*4. */
 int sr_framebuffer_download_rgba8(sr_framebuffer *, uint8_t *dst, size_t nbytes, uint32_t order);
-/* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL */
-int sr_framebuffer_download_planes(sr_framebuffer *, float *color, float *depth, uint8_t *stencil);
-int sr_framebuffer_upload_planes(sr_framebuffer *, const float *color, const float *depth, const uint8_t *stencil);
-/* checked accessor: PixelRead::pixel_ref / FramebufferAccessor (src/pixels/mod.rs:56-63,
- * src/framebuffer/accessor.rs:4-18); out-of-range -> SR_ERR_INVALID_PIXEL_COORDINATE */
-int sr_framebuffer_get_pixel(sr_framebuffer *, uint32_t x, uint32_t y, float rgba[4], float *depth, uint8_t *stencil);
+/* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL.  `stencil` holds width*height elements of the
+ * format's stencil type (u8, u16 or u32: src/stencil.rs:9-60). */
+int sr_framebuffer_download_planes(sr_framebuffer *, float *color, float *depth, void *stencil);
+int sr_framebuffer_upload_planes(sr_framebuffer *, const float *color, const float *depth, const void *stencil);
+/* checked accessors: PixelRead::pixel_ref / FramebufferAccessor::{get_depth, get_stencil} (src/pixels/mod.rs:56-63,
+ * src/framebuffer/accessor.rs:28-38) and PixelWrite::pixel_mut / FramebufferAccessorMut::{set_depth, set_stencil}
+ * (src/pixels/mod.rs:77-98, src/framebuffer/accessor.rs:52-70); out-of-range -> SR_ERR_INVALID_PIXEL_COORDINATE.
+ * The stencil value travels as u32 whatever the attachment's width (set: it must fit); any pointer may be NULL. */
+int sr_framebuffer_get_pixel(sr_framebuffer *, uint32_t x, uint32_t y, float rgba[4], float *depth, uint32_t *stencil);
+int sr_framebuffer_set_pixel(sr_framebuffer *, uint32_t x, uint32_t y, const float rgba[4], const float *depth, const uint32_t *stencil);
 /* parity introspection: per pixel, 1 + canonical index of the last primitive of the most recent
  * draw that wrote it (0 = untouched by that draw).  Enable before drawing. */
 int sr_framebuffer_enable_winner(sr_framebuffer *, int enable);

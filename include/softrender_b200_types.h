@@ -69,8 +69,10 @@ enum sr_stencil_op {
 /* ---- framebuffer formats: RenderBuffer<ColorDepth[Stencil]Attachments<RGBAf32Color,f32[,u8]>>
  *      (src/framebuffer/renderbuffer/mod.rs:16-30, attachments/predefined.rs:11-26) */
 enum sr_fb_format {
-    SR_FB_RGBAF32_DF32 = 0,    /* stencil type (): 20 B/pixel AoS {r,g,b,a,depth} */
-    SR_FB_RGBAF32_DF32_S8 = 1  /* stencil type u8: colour+depth AoS as above, stencil in its own u8 plane */
+    SR_FB_RGBAF32_DF32 = 0,     /* stencil type (): 20 B/pixel AoS {r,g,b,a,depth} */
+    SR_FB_RGBAF32_DF32_S8 = 1,  /* stencil type u8: colour+depth AoS as above, stencil in its own u8 plane */
+    SR_FB_RGBAF32_DF32_S16 = 2, /* stencil type u16 (the Stencil trait covers every integer width, src/stencil.rs:9-60) */
+    SR_FB_RGBAF32_DF32_S32 = 3  /* stencil type u32 */
 };
 
 /* ---- Viewport (src/geometry/clipvertex.rs:40-48) ------------------------ */
@@ -127,7 +129,9 @@ enum sr_geometry_shader {
 
 enum sr_blend {
     SR_BLEND_REPLACE = 0,     /* Blend for (): src/color/blend.rs:28-31 */
-    SR_BLEND_ALPHA_OVER = 1   /* full_example/src/color.rs:5-17 */
+    SR_BLEND_ALPHA_OVER = 1,  /* full_example/src/color.rs:5-17 */
+    SR_BLEND_ADDITIVE = 2     /* a user blend function, GenericBlend::new(|a, b| a + b) (src/color/blend.rs:57-76): the worked example of
+                               * how a third blend is registered -- INTEGRATION.md "Adding a blend function" */
 };
 
 /* ---- global uniforms ------------------------------------------------------

@@ -386,9 +386,11 @@ void gs_apply(int gs, Storage &out, int kind, const float *a, const float *b, co
 }
 
 // ---------------------------------------------------------------------------
-// a14: stencil (ref: src/stencil.rs:112-123,147-158), u8 buffers
+// a14: stencil (ref: src/stencil.rs:112-123,147-158) for the unsigned stencil types u8 / u16 / u32 (the Stencil trait,
+// src/stencil.rs:9-60: wrapping_add / wrapping_sub / saturating_* / not of the primitive type); values are held in 32 bits,
+// smax = the type's MAX
 // ---------------------------------------------------------------------------
-inline bool stencil_test(uint32_t test, uint8_t value, uint8_t mask) {
+inline bool stencil_test(uint32_t test, uint32_t value, uint32_t mask) {
     switch (test) {
         case SR_STENCIL_ALWAYS: return true;
         case SR_STENCIL_NEVER: return false;
@@ -401,18 +403,33 @@ inline bool stencil_test(uint32_t test, uint8_t value, uint8_t mask) {
     }
     return false;
 }
-inline uint8_t stencil_op(uint32_t op, uint8_t value, uint8_t mask) {
+inline uint32_t stencil_op(uint32_t op, uint32_t value, uint32_t mask, uint32_t smax = 0xFFu) {
     switch (op) {
         case SR_STENCIL_KEEP: return value;
-        case SR_STENCIL_INVERT: return (uint8_t)~value;
+        case SR_STENCIL_INVERT: return ~value & smax;                                     // Stencil::not
         case SR_STENCIL_ZERO: return 0;
         case SR_STENCIL_REPLACE: return mask;
-        case SR_STENCIL_INCREMENT_WRAP: return (uint8_t)(value + 1);
-        case SR_STENCIL_DECREMENT_WRAP: return (uint8_t)(value - 1);
-        case SR_STENCIL_INCREMENT_SAT: return value == 255 ? 255 : (uint8_t)(value + 1);
-        case SR_STENCIL_DECREMENT_SAT: return value == 0 ? 0 : (uint8_t)(value - 1);
+        case SR_STENCIL_INCREMENT_WRAP: return (value + 1u) & smax;                       // wrapping_add(one)
+        case SR_STENCIL_DECREMENT_WRAP: return (value - 1u) & smax;                       // wrapping_sub(one)
+        case SR_STENCIL_INCREMENT_SAT: return value == smax ? smax : value + 1u;          // saturating_add(one)
+        case SR_STENCIL_DECREMENT_SAT: return value == 0 ? 0u : value - 1u;               // saturating_sub(one)
     }
     return value;
+}
+inline uint32_t stencil_bytes_of(const so_framebuffer *fb) { return fb->stencil_bytes ? fb->stencil_bytes : 1u; }
+inline uint32_t stencil_load(const so_framebuffer *fb, uint64_t i) {
+    switch (stencil_bytes_of(fb)) {
+        case 2: return reinterpret_cast<const uint16_t *>(fb->stencil)[i];
+        case 4: return reinterpret_cast<const uint32_t *>(fb->stencil)[i];
+    }
+    return fb->stencil[i];
+}
+inline void stencil_store(so_framebuffer *fb, uint64_t i, uint32_t v) {
+    switch (stencil_bytes_of(fb)) {
+        case 2: reinterpret_cast<uint16_t *>(fb->stencil)[i] = (uint16_t)v; return;
+        case 4: reinterpret_cast<uint32_t *>(fb->stencil)[i] = v; return;
+    }
+    fb->stencil[i] = (uint8_t)v;
 }
 
 // ---------------------------------------------------------------------------
@@ -427,6 +444,8 @@ inline void blend(uint32_t mode, const float *a /*src*/, const float *b /*dst*/,
         float r[4] = {over(a[0], b[0], a[3], b[3]), over(a[1], b[1], a[3], b[3]), over(a[2], b[2], a[3], b[3]),
                       a[3] + b[3] * (1.0f - a[3])};
         for (int i = 0; i < 4; ++i) out[i] = r[i];
+    } else if (mode == SR_BLEND_ADDITIVE) {  // a user blend, GenericBlend::new(|a, b| a + b) (ref: src/color/blend.rs:57-76)
+        for (int i = 0; i < 4; ++i) out[i] = a[i] + b[i];
     } else {
         for (int i = 0; i < 4; ++i) out[i] = a[i];
     }
@@ -592,7 +611,7 @@ struct RasterArgs {
     uint32_t width, height;
     uint32_t tx0, ty0, tx1, ty1;  // tile, inclusive
     float bx0, by0, bx1, by1;     // bounds = tile cast to float
-    uint8_t stencil_value;
+    uint32_t stencil_value;
     uint32_t stencil_test, stencil_op;
     bool aa_lines;
     uint32_t cull;
@@ -626,9 +645,10 @@ inline void shade_and_write(const RasterArgs &A, so_framebuffer *fb, uint64_t in
 
 inline bool stencil_step(const RasterArgs &A, so_framebuffer *fb, uint64_t index) {
     if (!fb->stencil) return true;  // stencil type (): test Always, op Keep (ref: src/stencil.rs:65-86,169-175)
-    uint8_t sval = fb->stencil[index];
-    if (!stencil_test(A.stencil_test, sval, A.stencil_value)) return false;
-    fb->stencil[index] = stencil_op(A.stencil_op, sval, A.stencil_value);
+    const uint32_t bytes = stencil_bytes_of(fb), smax = bytes == 1 ? 0xFFu : bytes == 2 ? 0xFFFFu : 0xFFFFFFFFu;
+    const uint32_t sval = stencil_load(fb, index), mesh = A.stencil_value & smax;  // the mesh's value is of the buffer's type
+    if (!stencil_test(A.stencil_test, sval, mesh)) return false;
+    stencil_store(fb, index, stencil_op(A.stencil_op, sval, mesh, smax));
     return true;
 }
 
@@ -991,7 +1011,7 @@ int so_draw_fragment_run_tiles(so_draw *d, so_framebuffer *fb, const so_raster_s
             A.width = fb->width; A.height = fb->height;
             A.tx0 = tile.x0; A.ty0 = tile.y0; A.tx1 = tile.x1; A.ty1 = tile.y1;
             A.bx0 = (float)tile.x0; A.by0 = (float)tile.y0; A.bx1 = (float)tile.x1; A.by1 = (float)tile.y1;
-            A.stencil_value = (uint8_t)d->stencil_value;
+            A.stencil_value = d->stencil_value;
             A.stencil_test = st->stencil_test; A.stencil_op = st->stencil_op;
             A.aa_lines = st->antialiased_lines != 0;
             A.cull = st->cull_faces; A.blend = st->blend; A.fs = fs; A.uniforms = u; A.tex = tex; A.S = S;
@@ -1106,7 +1126,10 @@ uint64_t so_coordinate_index(uint32_t x, uint32_t y, uint32_t width) {
     return (uint64_t)x + (uint64_t)y * (uint64_t)width;  // ref: src/geometry/coordinate.rs:47-51
 }
 int so_stencil_test(uint32_t test, uint8_t value, uint8_t mask) { return stencil_test(test, value, mask) ? 1 : 0; }
-uint8_t so_stencil_op(uint32_t op, uint8_t value, uint8_t mask) { return stencil_op(op, value, mask); }
+uint8_t so_stencil_op(uint32_t op, uint8_t value, uint8_t mask) { return (uint8_t)stencil_op(op, value, mask, 0xFFu); }
+uint32_t so_stencil_op_wide(uint32_t op, uint32_t value, uint32_t mask, uint32_t bits) {
+    return stencil_op(op, value, mask, bits == 8 ? 0xFFu : bits == 16 ? 0xFFFFu : 0xFFFFFFFFu);
+}
 
 float so_depth_far(void) {
     // Depth::far() = Bounded::min_value() = f32::MIN (ref: src/framebuffer/attachments/depth.rs:31)
@@ -1123,7 +1146,7 @@ void so_framebuffer_clear(so_framebuffer *fb, const float color[4]) {
     for (uint64_t i = 0; i < n; ++i) {
         for (int c = 0; c < 4; ++c) fb->color[i * 4 + c] = color[c];
         fb->depth[i] = far_;
-        if (fb->stencil) fb->stencil[i] = 0;
+        if (fb->stencil) stencil_store(fb, i, 0);
         if (fb->winner) fb->winner[i] = 0;
     }
 }

@@ -37,6 +37,7 @@ typedef struct so_framebuffer {
     float *depth;      /* width*height */
     uint8_t *stencil;  /* width*height or NULL (stencil type `()`) */
     uint32_t *winner;  /* optional: 1 + canonical index of the last primitive that wrote the pixel in this draw */
+    uint32_t stencil_bytes; /* element size of `stencil`: 1 (u8; 0 means 1), 2 (u16) or 4 (u32) -- src/stencil.rs:9-60 */
 } so_framebuffer;
 
 typedef struct so_texture {
@@ -117,6 +118,8 @@ uint64_t so_coordinate_index(uint32_t x, uint32_t y, uint32_t width);
 /* StencilTest::test / StencilOp::op on u8 (src/stencil.rs:112-123,147-158) */
 int so_stencil_test(uint32_t test, uint8_t value, uint8_t mask);
 uint8_t so_stencil_op(uint32_t op, uint8_t value, uint8_t mask);
+/* the same on the u8 / u16 / u32 stencil types (bits = 8, 16, 32) */
+uint32_t so_stencil_op_wide(uint32_t op, uint32_t value, uint32_t mask, uint32_t bits);
 
 /* f32::MIN bit pattern used by Depth::far (src/framebuffer/attachments/depth.rs:31) */
 float so_depth_far(void);

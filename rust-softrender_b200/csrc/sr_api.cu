@@ -162,6 +162,7 @@ struct sr_framebuffer {
     uint32_t width, height, format;
     uint32_t ntx, nty;
     Buf aos_buf, stencil_buf, winner_buf;
+    uint32_t stencil_bytes = 0;  // element size of the stencil attachment: 1, 2 or 4 (0: stencil type `()`)
     Buf vis_buf;                // visibility buffer of the opaque path (allocated on first use)
     bool vis_clean = false;     // every key of the tiles of shard (vis_rank, vis_world) is "far": the resolve hands it back that way
     uint32_t vis_rank = 0, vis_world = 0;
@@ -174,6 +175,7 @@ struct sr_framebuffer {
         SrFbView v;
         v.aos = aos;
         v.stencil = stencil_buf ? stencil_buf->as<uint8_t>() : nullptr;
+        v.stencil_bytes = stencil_bytes;
         v.winner = (winner_enabled && winner_buf) ? winner_buf->as<uint32_t>() : nullptr;
         v.width = width; v.height = height; v.ntx = ntx; v.nty = nty;
         v.pending_clear = pending_clear ? 1u : 0u;
@@ -470,10 +472,12 @@ template <int FS>
 static int launch_tiles(sr_context *c, uint32_t ntiles_owned, const SrTileParams &p) {
     static bool configured[16] = {};  // per device: opt in to the large dynamic shared memory once
     if (!configured[c->device & 15]) {
-        SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_ORD_SMEM_BYTES));
+        SR_CUDA(cudaFuncSetAttribute(k_tile_ordered<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SR_ORD_SMEM_BYTES + 3 * SR_TILE_PIXELS)));
         configured[c->device & 15] = true;
     }
-    SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, SR_ORD_SMEM_BYTES, p);
+    // the tile's stencil values end the dynamic shared memory: 1 byte per pixel is in SR_ORD_SMEM_BYTES, wider types add the rest
+    const size_t smem = SR_ORD_SMEM_BYTES + (p.fb.stencil && p.fb.stencil_bytes > 1 ? (size_t)(p.fb.stencil_bytes - 1) * SR_TILE_PIXELS : 0);
+    SR_LAUNCH(c, k_tile_ordered<FS>, ntiles_owned, SR_RASTER_THREADS, smem, p);
     return SR_OK;
 }
 static int launch_tiles_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrTileParams &p) {
@@ -1160,6 +1164,7 @@ int sr_registry_entry(uint32_t kind, uint32_t index, sr_shader_info *info) {
     static const Row bl[] = {
         {SR_BLEND_REPLACE, 0, 0, 0, 0, "replace", "Blend for (): src/color/blend.rs:28-31"},
         {SR_BLEND_ALPHA_OVER, 0, 0, 0, 0, "alpha_over", "full_example/src/color.rs:5-17"},
+        {SR_BLEND_ADDITIVE, 0, 0, 0, 0, "additive", "GenericBlend::new(|a, b| a + b): src/color/blend.rs:57-76"},
     };
     const Row *rows = nullptr;
     uint32_t n = 0;
@@ -1345,7 +1350,7 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
 // ---- framebuffer -----------------------------------------------------------------------------------------
 int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out) {
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format > SR_FB_RGBAF32_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
+    if (format > SR_FB_RGBAF32_DF32_S32) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
     if (width > 256u * SR_TILE_W || height > 256u * SR_TILE_H || width > 65535u || height > 65535u)
         return sr_fail(SR_ERR_UNSUPPORTED, "framebuffer %ux%u exceeds %ux%u", width, height, 256u * SR_TILE_W, 256u * SR_TILE_H);
     SR_CUDA(cudaSetDevice(c->device));
@@ -1356,7 +1361,8 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     const uint64_t n = (uint64_t)width * height;
     SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * 20, &fb->aos_buf));
     fb->aos = fb->aos_buf->as<float>();
-    if (format == SR_FB_RGBAF32_DF32_S8) SR_TRY(c->alloc(std::max<uint64_t>(n, 1), &fb->stencil_buf));
+    fb->stencil_bytes = format == SR_FB_RGBAF32_DF32_S8 ? 1u : format == SR_FB_RGBAF32_DF32_S16 ? 2u : format == SR_FB_RGBAF32_DF32_S32 ? 4u : 0u;
+    if (fb->stencil_bytes) SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->stencil_bytes, &fb->stencil_buf));
     // RenderBuffer::with_dimensions: Color::empty() (zeros), Depth::far(), stencil default -- recorded lazily
     fb->pending_clear = true;
     *out = fb.release();
@@ -1410,7 +1416,7 @@ int sr_framebuffer_download_rgba8(sr_framebuffer *fb, uint8_t *dst, size_t nbyte
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
-int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *depth, uint8_t *stencil) {
+int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *depth, void *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     sr_context *c = fb->ctx;
     SR_CUDA(cudaSetDevice(c->device));
@@ -1425,12 +1431,12 @@ int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *dept
     if (depth) SR_CUDA(cudaMemcpyAsync(depth, dd->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (stencil) {
         if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
-        SR_CUDA(cudaMemcpyAsync(stencil, fb->stencil_buf->ptr, n, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaMemcpyAsync(stencil, fb->stencil_buf->ptr, n * fb->stencil_bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
-int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const float *depth, const uint8_t *stencil) {
+int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const float *depth, const void *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (stencil && !fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");  // before anything is enqueued
     sr_context *c = fb->ctx;
@@ -1450,12 +1456,12 @@ int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const f
         SR_LAUNCH(c, k_fb_merge, ceil_div(n, 256), 256, 0, fb->aos, n, color ? dc->as<float>() : nullptr, depth ? dd->as<float>() : nullptr);
     if (stencil) {
         if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
-        SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->ptr, stencil, n, cudaMemcpyHostToDevice, c->stream));
+        SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->ptr, stencil, n * fb->stencil_bytes, cudaMemcpyHostToDevice, c->stream));
     }
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
-int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float rgba[4], float *depth, uint8_t *stencil) {
+int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float rgba[4], float *depth, uint32_t *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (x >= fb->width || y >= fb->height)
         return sr_fail(SR_ERR_INVALID_PIXEL_COORDINATE, "pixel (%u,%u) outside %ux%u", x, y, fb->width, fb->height);
@@ -1465,12 +1471,33 @@ int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float r
     float px[5];
     const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
     SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
-    uint8_t s = 0;
-    if (stencil && fb->stencil_buf) SR_CUDA(cudaMemcpyAsync(&s, fb->stencil_buf->as<uint8_t>() + idx, 1, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t s = 0;  // (little-endian: the low bytes of `s` receive a u8 / u16 element)
+    if (stencil && fb->stencil_buf)
+        SR_CUDA(cudaMemcpyAsync(&s, fb->stencil_buf->as<uint8_t>() + idx * fb->stencil_bytes, fb->stencil_bytes, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
     if (rgba) memcpy(rgba, px, 16);
     if (depth) *depth = px[4];
     if (stencil) *stencil = s;
+    return SR_OK;
+}
+// PixelWrite::set_pixel + FramebufferAccessorMut::{set_depth, set_stencil} (src/pixels/mod.rs:77-98, src/framebuffer/accessor.rs:18-60)
+int sr_framebuffer_set_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, const float rgba[4], const float *depth, const uint32_t *stencil) {
+    if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (x >= fb->width || y >= fb->height)
+        return sr_fail(SR_ERR_INVALID_PIXEL_COORDINATE, "pixel (%u,%u) outside %ux%u", x, y, fb->width, fb->height);
+    if (stencil && !fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
+    if (rgba) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5, rgba, 16, cudaMemcpyHostToDevice, c->stream));
+    if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5 + 4, depth, 4, cudaMemcpyHostToDevice, c->stream));
+    if (stencil) {
+        const uint32_t smax = fb->stencil_bytes == 1 ? 0xFFu : fb->stencil_bytes == 2 ? 0xFFFFu : 0xFFFFFFFFu;
+        if (*stencil > smax) return sr_fail(SR_ERR_INVALID_ARGUMENT, "stencil value %u does not fit the attachment's %u-bit type", *stencil, fb->stencil_bytes * 8);
+        SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->as<uint8_t>() + idx * fb->stencil_bytes, stencil, fb->stencil_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    SR_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffers are copied before the call returns
     return SR_OK;
 }
 int sr_framebuffer_enable_winner(sr_framebuffer *fb, int enable) {
@@ -2090,7 +2117,7 @@ int sr_fragment_set_tile_size(sr_draw *d, uint32_t w, uint32_t h) {
     return SR_OK;
 }
 int sr_fragment_set_blend(sr_draw *d, uint32_t blend) {
-    if (!d || blend > SR_BLEND_ALPHA_OVER) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad blend");
+    if (!d || blend > SR_BLEND_ADDITIVE) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad blend");
     d->blend = blend;
     return SR_OK;
 }

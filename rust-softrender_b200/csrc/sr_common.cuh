@@ -159,7 +159,8 @@ __device__ __forceinline__ uint32_t sr_prim_canonical(const SrPrimSource &s, uin
 // ---- framebuffer view ---------------------------------------------------------------------------
 struct SrFbView {
     float *aos;        // width*height*5 floats {r,g,b,a,depth}; may be a peer (NVLink) address
-    uint8_t *stencil;  // or null
+    uint8_t *stencil;  // or null; elements of stencil_bytes (1, 2 or 4) bytes
+    uint32_t stencil_bytes;
     uint32_t *winner;  // or null
     uint32_t width, height;
     uint32_t ntx, nty;       // tile grid

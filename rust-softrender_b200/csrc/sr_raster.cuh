@@ -1676,7 +1676,8 @@ struct SrOrdCtx {
     const SrTileParams *p;
     uint32_t x0, y0, xe, ye;  // tile pixel rectangle inside the frame (inclusive)
     bool has_stencil;
-    uint8_t mesh_stencil;
+    uint32_t sbytes, smax;   // stencil element size and the type's MAX
+    uint32_t mesh_stencil;
 };
 
 // Lines and points: the warps of the CTA walk the lines / points of the tile in submission order, but only the thread that
@@ -1692,9 +1693,9 @@ __device__ __forceinline__ bool sr_ord_owns(const SrOrdCtx &c, uint32_t x, uint3
 // stencil step (triangle.rs:91-99, line.rs:58-66, point.rs:52-60)
 __device__ __forceinline__ bool sr_ord_stencil_step(const SrOrdCtx &c, uint32_t li) {
     if (!c.has_stencil) return true;  // stencil type (): Always / Keep
-    const uint8_t sval = c.stencil[li];
+    const uint32_t sval = sr_stencil_load(c.stencil, c.sbytes, li);
     if (!sr_stencil_test_fn(c.p->stencil_test, sval, c.mesh_stencil)) return false;
-    c.stencil[li] = sr_stencil_op_fn(c.p->stencil_op, sval, c.mesh_stencil);
+    sr_stencil_store(c.stencil, c.sbytes, li, sr_stencil_op_fn(c.p->stencil_op, sval, c.mesh_stencil, c.smax));
     return true;
 }
 // everything after the stencil step of one fragment (triangle.rs:117-143, line.rs:81-106, point.rs:62-82)
@@ -2010,7 +2011,9 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     c.x0 = x0; c.y0 = y0;
     c.xe = min(x0 + SR_TILE_W, W) - 1; c.ye = min(y0 + SR_TILE_H, H) - 1;
     c.has_stencil = p.fb.stencil != nullptr;
-    c.mesh_stencil = (uint8_t)p.stencil_value;
+    c.sbytes = c.has_stencil ? p.fb.stencil_bytes : 1u;  // (the tile's stencil values sit at the end of the dynamic shared memory: sbytes per pixel)
+    c.smax = c.sbytes == 1 ? 0xFFu : c.sbytes == 2 ? 0xFFFFu : 0xFFFFFFFFu;
+    c.mesh_stencil = p.stencil_value & c.smax;  // the mesh's stencil value is of the buffer's type
 
     for (uint32_t i = lane; i < SR_ORD_BAND * SR_TILE_W; i += 32) s_claim[warp][i] = 0;
     uint32_t claim_round = 0;  // (warp-uniform) bidding round of sr_ord_lines_chunk
@@ -2019,16 +2022,16 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         float4 col = make_float4(p.fb.clear[0], p.fb.clear[1], p.fb.clear[2], p.fb.clear[3]);
         float d = __uint_as_float(SR_DEPTH_FAR_BITS);
-        uint8_t s = 0;
+        uint32_t s = 0;
         if (!p.fb.pending_clear && px < W && py < H) {
             const float *src = sr_fb_pixel(p.fb, px, py);
             col = make_float4(src[0], src[1], src[2], src[3]);
             d = src[4];
-            if (c.has_stencil) s = p.fb.stencil[(uint64_t)py * W + px];
+            if (c.has_stencil) s = sr_stencil_load(p.fb.stencil, c.sbytes, (uint64_t)py * W + px);
         }
         s_color[i] = col;
         s_depth[i] = d;
-        s_stencil[i] = s;
+        sr_stencil_store(s_stencil, c.sbytes, i, s);
         s_winner[i] = 0;
     }
     __syncthreads();
@@ -2381,7 +2384,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
         const float4 col = s_color[i];
         dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; dst[3] = col.w;
         dst[4] = s_depth[i];
-        if (c.has_stencil) p.fb.stencil[(uint64_t)py * W + px] = s_stencil[i];
+        if (c.has_stencil) sr_stencil_store(p.fb.stencil, c.sbytes, (uint64_t)py * W + px, sr_stencil_load(s_stencil, c.sbytes, i));
         if (p.fb.winner && s_winner[i]) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];  // plane is zeroed per draw
     }
 }
@@ -2425,7 +2428,7 @@ __global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
     float *dst = fb.aos + i * 5;
     dst[0] = fb.clear[0]; dst[1] = fb.clear[1]; dst[2] = fb.clear[2]; dst[3] = fb.clear[3];
     dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
-    if (fb.stencil) fb.stencil[i] = 0;
+    if (fb.stencil) sr_stencil_store(fb.stencil, fb.stencil_bytes, i, 0u);
     if (fb.winner) fb.winner[i] = 0;
 }
 // realtime_example/src/main.rs:100-116: the presentation loop `(c.x * 255.0) as u8` per channel.  Rust's float -> u8 `as`

@@ -305,6 +305,9 @@ __device__ __forceinline__ void sr_blend(uint32_t mode, const float *a, const fl
         r[3] = a[3] + b[3] * (1.0f - a[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = r[i];
+    } else if (mode == SR_BLEND_ADDITIVE) {  // GenericBlend::new(|a, b| a + b), component-wise Vector4 addition
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = a[i] + b[i];
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = a[i];
@@ -312,7 +315,8 @@ __device__ __forceinline__ void sr_blend(uint32_t mode, const float *a, const fl
 }
 
 // StencilTest::test / StencilOp::op (src/stencil.rs:112-123,147-158) on u8
-__device__ __forceinline__ bool sr_stencil_test_fn(uint32_t test, uint8_t value, uint8_t mask) {
+// value / mask are u8, u16 or u32 stencil values held in 32 bits; smax = the type's MAX (wrapping and saturation bounds)
+__device__ __forceinline__ bool sr_stencil_test_fn(uint32_t test, uint32_t value, uint32_t mask) {
     switch (test) {
         case SR_STENCIL_ALWAYS: return true;
         case SR_STENCIL_NEVER: return false;
@@ -324,15 +328,23 @@ __device__ __forceinline__ bool sr_stencil_test_fn(uint32_t test, uint8_t value,
         default: return mask != value;
     }
 }
-__device__ __forceinline__ uint8_t sr_stencil_op_fn(uint32_t op, uint8_t value, uint8_t mask) {
+__device__ __forceinline__ uint32_t sr_stencil_op_fn(uint32_t op, uint32_t value, uint32_t mask, uint32_t smax) {
     switch (op) {
         case SR_STENCIL_KEEP: return value;
-        case SR_STENCIL_INVERT: return (uint8_t)~value;
+        case SR_STENCIL_INVERT: return ~value & smax;
         case SR_STENCIL_ZERO: return 0;
         case SR_STENCIL_REPLACE: return mask;
-        case SR_STENCIL_INCREMENT_WRAP: return (uint8_t)(value + 1);
-        case SR_STENCIL_DECREMENT_WRAP: return (uint8_t)(value - 1);
-        case SR_STENCIL_INCREMENT_SAT: return value == 255 ? (uint8_t)255 : (uint8_t)(value + 1);
-        default: return value == 0 ? (uint8_t)0 : (uint8_t)(value - 1);
+        case SR_STENCIL_INCREMENT_WRAP: return (value + 1u) & smax;
+        case SR_STENCIL_DECREMENT_WRAP: return (value - 1u) & smax;
+        case SR_STENCIL_INCREMENT_SAT: return value == smax ? smax : value + 1u;
+        default: return value == 0 ? 0u : value - 1u;
     }
+}
+__device__ __forceinline__ uint32_t sr_stencil_load(const uint8_t *base, uint32_t bytes, uint64_t i) {
+    return bytes == 1 ? (uint32_t)base[i] : bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(base)[i] : reinterpret_cast<const uint32_t *>(base)[i];
+}
+__device__ __forceinline__ void sr_stencil_store(uint8_t *base, uint32_t bytes, uint64_t i, uint32_t v) {
+    if (bytes == 1) base[i] = (uint8_t)v;
+    else if (bytes == 2) reinterpret_cast<uint16_t *>(base)[i] = (uint16_t)v;
+    else reinterpret_cast<uint32_t *>(base)[i] = v;
 }

@@ -150,9 +150,13 @@ class RenderBuffer:
     def __init__(self, ctx: Context, handle, width, height, fmt):
         self.ctx, self.h, self.width, self.height, self.format = ctx, handle, width, height, fmt
 
+    _STENCIL_DTYPE = {FB_RGBAF32_DF32_S8: np.uint8, FB_RGBAF32_DF32_S16: np.uint16, FB_RGBAF32_DF32_S32: np.uint32}
+
     @staticmethod
-    def with_dimensions(ctx: Context, width: int, height: int, stencil: bool = False) -> "RenderBuffer":
-        fmt = FB_RGBAF32_DF32_S8 if stencil else FB_RGBAF32_DF32
+    def with_dimensions(ctx: Context, width: int, height: int, stencil=False) -> "RenderBuffer":
+        """stencil: False = stencil type `()`, True / 8 = u8, 16 = u16, 32 = u32 (the Stencil trait, src/stencil.rs:9-60)."""
+        fmt = {False: FB_RGBAF32_DF32, True: FB_RGBAF32_DF32_S8, 8: FB_RGBAF32_DF32_S8, 16: FB_RGBAF32_DF32_S16,
+               32: FB_RGBAF32_DF32_S32}[stencil]
         h = ctypes.c_void_p()
         check(lib.sr_framebuffer_create(ctx.h, width, height, fmt, ctypes.byref(h)))
         return RenderBuffer(ctx, h, width, height, fmt)
@@ -197,25 +201,32 @@ class RenderBuffer:
     def download_planes(self, stencil: bool = False):
         n = self.width * self.height
         color, depth = np.empty((n, 4), np.float32), np.empty(n, np.float32)
-        st = np.empty(n, np.uint8) if stencil else None
+        st = np.empty(n, self._STENCIL_DTYPE[self.format]) if stencil else None
         check(lib.sr_framebuffer_download_planes(self.h, color.ctypes.data_as(_abi.f32p), depth.ctypes.data_as(_abi.f32p),
-                                                 st.ctypes.data_as(_abi.u8p) if st is not None else None))
+                                                 st.ctypes.data_as(ctypes.c_void_p) if st is not None else None))
         return color, depth, st
 
     def upload_planes(self, color=None, depth=None, stencil=None):
         c = np.ascontiguousarray(color, np.float32) if color is not None else None
         d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
-        s = np.ascontiguousarray(stencil, np.uint8) if stencil is not None else None
+        s = np.ascontiguousarray(stencil, self._STENCIL_DTYPE.get(self.format, np.uint8)) if stencil is not None else None
         check(lib.sr_framebuffer_upload_planes(self.h, c.ctypes.data_as(_abi.f32p) if c is not None else None,
                                                d.ctypes.data_as(_abi.f32p) if d is not None else None,
-                                               s.ctypes.data_as(_abi.u8p) if s is not None else None))
+                                               s.ctypes.data_as(ctypes.c_void_p) if s is not None else None))
 
     def pixel(self, x: int, y: int):
         """Checked accessor (PixelRead::pixel_ref): raises SoftrenderError(ERR_INVALID_PIXEL_COORDINATE) out of range."""
         rgba = (ctypes.c_float * 4)()
-        d, s = ctypes.c_float(), ctypes.c_uint8()
+        d, s = ctypes.c_float(), ctypes.c_uint32()
         check(lib.sr_framebuffer_get_pixel(self.h, x, y, rgba, ctypes.byref(d), ctypes.byref(s)))
         return tuple(rgba), d.value, s.value
+
+    def set_pixel(self, x: int, y: int, rgba=None, depth=None, stencil=None):
+        """Checked write accessor (PixelWrite::pixel_mut, FramebufferAccessorMut::set_depth / set_stencil)."""
+        c = (ctypes.c_float * 4)(*[float(v) for v in rgba]) if rgba is not None else None
+        d = ctypes.byref(ctypes.c_float(depth)) if depth is not None else None
+        s = ctypes.byref(ctypes.c_uint32(stencil)) if stencil is not None else None
+        check(lib.sr_framebuffer_set_pixel(self.h, x, y, c, d, s))
 
     def enable_winner(self, enable: bool = True):
         check(lib.sr_framebuffer_enable_winner(self.h, 1 if enable else 0))

@@ -23,7 +23,7 @@ u8p = ctypes.POINTER(ctypes.c_uint8)
 
 class SoFramebuffer(ctypes.Structure):
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("color", f32p), ("depth", f32p),
-                ("stencil", u8p), ("winner", u32p)]
+                ("stencil", u8p), ("winner", u32p), ("stencil_bytes", ctypes.c_uint32)]
 
 
 class SoTexture(ctypes.Structure):
@@ -109,6 +109,8 @@ def lib():
         L.so_stencil_test.argtypes = [ctypes.c_uint32, ctypes.c_uint8, ctypes.c_uint8]
         L.so_stencil_op.restype = ctypes.c_uint8
         L.so_stencil_op.argtypes = [ctypes.c_uint32, ctypes.c_uint8, ctypes.c_uint8]
+        L.so_stencil_op_wide.restype = ctypes.c_uint32
+        L.so_stencil_op_wide.argtypes = [ctypes.c_uint32] * 4
         L.so_depth_far.restype = ctypes.c_float
         L.so_framebuffer_clear.argtypes = [ctypes.POINTER(SoFramebuffer), f32p]
         _lib = L
@@ -134,13 +136,13 @@ class OracleFramebuffer:
         n = self.width * self.height
         self.color = np.zeros((n, 4), np.float32)
         self.depth = np.full(n, lib().so_depth_far(), np.float32)
-        self.stencil = np.zeros(n, np.uint8) if self.stencil_bits else None
+        self.stencil = np.zeros(n, {16: np.uint16, 32: np.uint32}.get(self.stencil_bits, np.uint8)) if self.stencil_bits else None
         self.winner = np.zeros(n, np.uint32)
 
     def struct(self) -> SoFramebuffer:
         return SoFramebuffer(self.width, self.height, _fp(self.color), _fp(self.depth),
                              self.stencil.ctypes.data_as(u8p) if self.stencil is not None else None,
-                             self.winner.ctypes.data_as(u32p))
+                             self.winner.ctypes.data_as(u32p), self.stencil.itemsize if self.stencil is not None else 0)
 
     def clear(self, color):
         c = np.asarray(color, np.float32)

@@ -109,7 +109,7 @@ def test_shader_registry_enumerates_without_a_device():
     assert [e["id"] for e in gs] == [sr.GS_CLIP, sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS, sr.GS_CLIP_SH]
     assert [e["id"] for e in fs] == [sr.FS_FLAT, sr.FS_SUZANNE, sr.FS_FULL_EXAMPLE, sr.FS_FULL_EXAMPLE_TEXTURED, sr.FS_GREEN, sr.FS_DISCARD_CHECKER, sr.FS_TEXTURE_UNLIT]
     assert [e["name"] for e in fs if e["discards"]] == ["discard_checker"] and [e["name"] for e in fs if e["needs_texture"]] == ["full_example_4light_textured", "texture_unlit"]
-    assert [e["name"] for e in bl] == ["replace", "alpha_over"] and pipeline.registry(9) == []
+    assert [e["name"] for e in bl] == ["replace", "alpha_over", "additive"] and pipeline.registry(9) == []
     assert all(e["reference"] for e in vs + gs + fs + bl)
 
 

@@ -33,7 +33,7 @@ def make_fb(P, ctx, w, h, stencil=False, winner=True):
 
 
 def oracle_fb(w, h, stencil=False):
-    fb = ob.OracleFramebuffer(w, h, 8 if stencil else 0)
+    fb = ob.OracleFramebuffer(w, h, {False: 0, True: 8}.get(stencil, stencil))  # stencil: False, True (u8), 16 or 32
     fb.clear(H.CLEAR)
     return fb
 
@@ -494,6 +494,85 @@ def test_stencil(P, ctx, test, op):
     assert np.array_equal(st, ofb.stencil)
     assert np.array_equal(win, ofb.winner)
     H.compare_framebuffers(out, ofb, exact_color=True, what="stencil")
+
+
+@pytest.mark.parametrize("bits", [16, 32])
+@pytest.mark.parametrize("op", [sr.STENCIL_INVERT, sr.STENCIL_REPLACE, sr.STENCIL_INCREMENT_WRAP, sr.STENCIL_DECREMENT_WRAP,
+                                sr.STENCIL_INCREMENT_SAT, sr.STENCIL_DECREMENT_SAT])
+def test_stencil_wider_types(P, ctx, bits, op):
+    """u16 and u32 stencil attachments (the Stencil trait covers every integer width, src/stencil.rs:9-60): initial values
+    around 0 and the type's MAX so that wrapping and saturation happen at the type's own bounds; triangles, lines and
+    points all run the stencil step."""
+    rng = np.random.default_rng(4700 + bits + op)
+    w, h, n = 100, 84, 90
+    smax = (1 << bits) - 1
+    verts = H.random_screen_triangles(rng, n, w, h)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    lines = np.zeros((40, 8), np.float32)
+    lines[:, 0], lines[:, 1] = rng.uniform(0, w, 40), rng.uniform(0, h, 40)
+    lines[:, 2], lines[:, 3], lines[:, 4:] = -0.2, 1, rng.uniform(0, 1, (40, 4))
+    pts = lines[:15].copy()
+    pts[:, :2] = rng.uniform(0, 80, (15, 2))
+    edge = np.array([0, 1, 2, smax - 2, smax - 1, smax, 300 & smax, 70000 & smax], np.uint64)
+    init = (np.tile(np.float32(H.CLEAR), (w * h, 1)), np.full(w * h, np.float32(-3.4028235e38)),
+            edge[rng.integers(0, len(edge), w * h)].astype(np.uint16 if bits == 16 else np.uint32))
+    value = smax - 1  # the mesh's stencil value is of the buffer's type
+    out, win, st, ofb = run_both_screen(P, ctx, w, h, verts, idx, stencil=bits, stencil_cfg=(sr.STENCIL_LESS_THAN_EQ, op),
+                                        stencil_value=value, init=init, gen={2: lines, 1: pts}, draws=2)
+    assert st.dtype == ofb.stencil.dtype and st.dtype.itemsize * 8 == bits
+    assert np.array_equal(st, ofb.stencil)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what=f"u{bits} stencil")
+    assert (ofb.stencil != init[2]).any()
+
+
+def test_user_blend_function_additive(P, ctx):
+    """A third registered blend, the stand-in for a user's GenericBlend::new(|a, b| a + b) (src/color/blend.rs:57-76; recipe in
+    INTEGRATION.md): strictly ordered path, triangles + antialiased lines + points, colours bit-exact (f32 addition is not
+    associative, so submission order is observable)."""
+    rng = np.random.default_rng(613)
+    w, h, n = 150, 110, 400
+    verts = H.random_screen_triangles(rng, n, w, h, max_size=40.0)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    lines = np.zeros((60, 8), np.float32)
+    lines[:, 0], lines[:, 1] = rng.uniform(0, w, 60), rng.uniform(0, h, 60)
+    lines[:, 2], lines[:, 3], lines[:, 4:] = -0.05, 1, rng.uniform(0, 1, (60, 4))
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, blend=sr.BLEND_ADDITIVE, aa=True, gen={2: lines, 1: lines[:20]}, draws=2)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="additive blend")
+    assert ofb.color.max() > 2.0  # contributions accumulated
+    assert [r["name"] for r in P.registry(3)] == ["replace", "alpha_over", "additive"]
+
+
+def test_pixel_write_accessors(P, ctx):
+    """PixelWrite::pixel_mut / FramebufferAccessorMut::{set_depth, set_stencil} (src/pixels/mod.rs:77-98,
+    src/framebuffer/accessor.rs:52-70) through sr_framebuffer_set_pixel: a depth written by hand is what the next draw's
+    depth test sees, a stencil value written by hand is what its stencil test sees."""
+    w, h = 40, 30
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h, stencil=16)
+    fb.clear(H.CLEAR)
+    fb.set_pixel(5, 6, rgba=(0.25, 0.5, 0.75, 1.0), depth=-0.125, stencil=40000)
+    assert fb.pixel(5, 6) == ((0.25, 0.5, 0.75, 1.0), -0.125, 40000)
+    assert fb.pixel(6, 6)[2] == 0 and fb.pixel(6, 6)[0] == tuple(np.float32(H.CLEAR).tolist())
+    with pytest.raises(Exception):
+        fb.set_pixel(w, 0, depth=-1.0)  # RenderError::InvalidPixelCoordinate
+    with pytest.raises(Exception):
+        fb.set_pixel(0, 0, stencil=70000)  # does not fit u16
+    # a full-frame triangle at z = -1: the hand-written pixel (depth -0.125, nearer) must survive the depth test
+    u = scenes.suzanne_uniforms(w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    tri = np.array([[-50, -50, -1, 1, 1, 0, 0, 1], [200, -50, -1, 1, 1, 0, 0, 1], [-50, 200, -1, 1, 1, 0, 0, 1]], np.float32)
+    pipe.draw_from_vertices(sr.TRIANGLE, tri, np.arange(3, dtype=np.uint32), 1).run(sr.FS_FLAT)
+    assert fb.pixel(5, 6)[0] == (0.25, 0.5, 0.75, 1.0) and fb.pixel(5, 6)[1] == -0.125
+    assert fb.pixel(6, 6)[0] == (1.0, 0.0, 0.0, 1.0) and fb.pixel(6, 6)[1] == -1.0
+    # stencil Equal against 40000 with a nearer triangle: only the hand-written pixel passes
+    pipe.set_stencil_config(sr.STENCIL_EQUAL, sr.STENCIL_KEEP)
+    tri[:, 2] = -0.01
+    tri[:, 4:8] = [0, 1, 0, 1]
+    pipe.draw_from_vertices(sr.TRIANGLE, tri, np.arange(3, dtype=np.uint32), 1, stencil=40000).run(sr.FS_FLAT)
+    assert fb.pixel(5, 6)[0] == (0.0, 1.0, 0.0, 1.0) and fb.pixel(6, 6)[0] == (1.0, 0.0, 0.0, 1.0)
+    pipe.destroy()
+    fb.destroy()
 
 
 @pytest.mark.parametrize("aa", [False, True])

@@ -280,3 +280,18 @@ def test_texture_sampler_known_answers():
     chk = scenes.checker_texture(16, 4)
     for u, v in [(0.1, 0.9), (0.5, 0.5), (1.0, 0.0), (0.333, 0.777)]:
         assert np.array_equal(ob.texture_sample(chk, u, v, (N, CLAMP, None)), ob.texture_sample(chk, u, v, None))
+
+
+def test_stencil_ops_on_wider_types():
+    """StencilOp::op over the Stencil trait's wrapping / saturating / not (src/stencil.rs:9-60,147-158) at the bounds of u8,
+    u16 and u32, worked by hand."""
+    import softrender_b200 as sr
+    f = ob.lib().so_stencil_op_wide
+    for bits in (8, 16, 32):
+        m = (1 << bits) - 1
+        assert f(sr.STENCIL_INCREMENT_WRAP, m, 0, bits) == 0 and f(sr.STENCIL_DECREMENT_WRAP, 0, 0, bits) == m
+        assert f(sr.STENCIL_INCREMENT_SAT, m, 0, bits) == m and f(sr.STENCIL_DECREMENT_SAT, 0, 0, bits) == 0
+        assert f(sr.STENCIL_INCREMENT_SAT, m - 1, 0, bits) == m and f(sr.STENCIL_DECREMENT_SAT, 1, 0, bits) == 0
+        assert f(sr.STENCIL_INVERT, 0, 0, bits) == m and f(sr.STENCIL_INVERT, 0x5A, 0, bits) == m ^ 0x5A
+        assert f(sr.STENCIL_REPLACE, 3, m - 7, bits) == m - 7 and f(sr.STENCIL_ZERO, m, 1, bits) == 0 and f(sr.STENCIL_KEEP, m, 1, bits) == m
+    assert f(sr.STENCIL_INCREMENT_WRAP, 255, 0, 16) == 256 and f(sr.STENCIL_INCREMENT_WRAP, 65535, 0, 32) == 65536
