@@ -262,6 +262,12 @@ int sr_draw_download_sequence(sr_draw *, uint32_t *dst, uint64_t capacity);
 /* per-GPU-tile triangle lists of a finished (screen-space) draw: CSR offsets[ntiles+1] + ids
  * (canonical triangle index, ascending per tile).  ids may be NULL to query *total. */
 int sr_draw_bins(sr_draw *, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total);
+/* the same for the lists the opaque fast path actually built for the latest opaque draw of the context (k_bin_small, or
+ * k_micro + k_large_fill: only the triangles whose frame-clamped bounding box exceeds *micro_area pixels go through per-tile
+ * lists there, the rest are rasterised per triangle; *micro_area = 0: every triangle).  ids ascending per tile;
+ * offsets holds ntiles + 1 entries (ntiles from the framebuffer's size and sr_tile_size). */
+int sr_context_last_opaque_lists(sr_context *, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total,
+                                 uint32_t *micro_area);
 /* self-test: compares the rasteriser's exact-division shortcut with IEEE division on `count` random operand
  * pairs over its whole validity range; *mismatches must come back 0 */
 int sr_selftest_division(sr_context *, uint64_t seed, uint64_t count, uint64_t *mismatches);

@@ -107,6 +107,7 @@ SYMBOLS = {
     "sr_draw_count": (c_int, [c_void_p, c_int, u64p, u32p]),
     "sr_draw_download": (c_int, [c_void_p, c_int, f32p, c_u64]),
     "sr_draw_download_sequence": (c_int, [c_void_p, u32p, c_u64]),
+    "sr_context_last_opaque_lists": (c_int, [c_void_p, u64p, u32p, c_u64, u64p, u32p]),
     "sr_draw_bins": (c_int, [c_void_p, u64p, u32p, c_u64, u64p]),
     "sr_selftest_division": (c_int, [c_void_p, c_u64, c_u64, u64p]),
 }

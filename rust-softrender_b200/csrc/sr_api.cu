@@ -81,6 +81,8 @@ struct sr_context {
     bool ev_front_valid = false;
     Buf zero_off;                                 // all-zero CSR offsets for empty primitive kinds
     uint32_t zero_off_tiles = 0;
+    Buf last_off, last_list;                      // per-tile triangle lists of the latest opaque draw (sr_context_last_opaque_lists)
+    uint32_t last_ntiles = 0, last_micro_area = 0;
     struct sr_shard *shard = nullptr;             // range-sharded front end (sr_context_attach_shard)
     uint32_t shard_lane = 0;
     cudaStream_t aux = nullptr;                   // second stream: rank 0's clear pre-fill of foreign tiles runs beside its k_micro
@@ -703,6 +705,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         q->op.shard_rank = c->shard_rank; q->op.shard_world = c->shard_world;
         q->op.fs = tp.fs;
         SR_TRY(launch_bin_small(c, q.get()));
+        c->last_off = q->off; c->last_list = c->list_arena; c->last_ntiles = ntiles; c->last_micro_area = 0;
         record(c, 5);
         if (!c->ev_front) SR_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
         SR_CUDA(cudaEventRecord(c->ev_front, c->stream));
@@ -814,6 +817,7 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         q->op.line_base = tp.line_base; q->op.point_base = tp.point_base;
     }
     SR_TRY(launch_opaque_pass(c, q.get()));
+    c->last_off = off; c->last_list = c->list_arena; c->last_ntiles = ntiles; c->last_micro_area = use_micro ? micro_area : 0u;
     fb->pending_clear = false;
     c->pending = q.release();
     return SR_OK;
@@ -1219,6 +1223,8 @@ int sr_context_destroy(sr_context *c) {
     // the context's own buffers first (they hold references to it), then the cache, stream and events; the object itself
     // goes when the last buffer of a still-living child (framebuffer, mesh, draw ...) has been released
     c->list_arena.reset();
+    c->last_off.reset();
+    c->last_list.reset();
     for (auto &a : c->ord_arena) a.reset();
     c->zero_off.reset();
     c->closed = true;
@@ -2324,6 +2330,35 @@ int sr_draw_download_sequence(sr_draw *d, uint32_t *dst, uint64_t capacity) {
     return SR_OK;
 }
 
+// parity introspection: the per-tile triangle lists the HEADLINE path built for the latest opaque draw of this
+// context -- k_bin_small's lists (every triangle of a small draw) or k_micro + k_large_fill's (the triangles whose clamped
+// bounding box exceeds *micro_area pixels and that the tightened small-triangle path did not take; *micro_area = 0: all).
+// CSR offsets (ntiles + 1), ids ascending per tile.  ids may be NULL to query *total.
+int sr_context_last_opaque_lists(sr_context *c, uint64_t *offsets, uint32_t *ids, uint64_t ids_capacity, uint64_t *total, uint32_t *micro_area) {
+    if (!c || !total) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(settle(c));  // (an overflowed pass is replayed with a larger arena first)
+    if (!c->last_off || !c->last_list) return sr_fail(SR_ERR_INVALID_STATE, "no opaque draw on this context yet");
+    SR_CUDA(cudaSetDevice(c->device));
+    const uint32_t ntiles = c->last_ntiles;
+    std::vector<uint32_t> off(ntiles + 1);
+    SR_CUDA(cudaMemcpyAsync(off.data(), c->last_off->ptr, (size_t)(ntiles + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    const uint32_t n = off[ntiles];
+    if (n > c->list_cap) return sr_fail(SR_ERR_INVALID_STATE, "lists (%u entries) exceed the arena (%u)", n, c->list_cap);
+    std::vector<uint32_t> list(std::max(n, 1u));
+    if (n) SR_CUDA(cudaMemcpyAsync(list.data(), c->list_arena->ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        std::sort(list.begin() + off[t], list.begin() + off[t + 1]);  // fill order within a tile is not deterministic (atomic cursors)
+        if (offsets) offsets[t] = off[t];
+    }
+    if (offsets) offsets[ntiles] = n;
+    if (ids)
+        for (uint64_t i = 0; i < n && i < ids_capacity; ++i) ids[i] = list[i];
+    *total = n;
+    if (micro_area) *micro_area = c->last_micro_area;
+    return SR_OK;
+}
 int sr_selftest_division(sr_context *c, uint64_t seed, uint64_t count, uint64_t *mismatches) {
     if (!c || !mismatches) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     SR_CUDA(cudaSetDevice(c->device));

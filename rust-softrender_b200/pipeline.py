@@ -74,6 +74,16 @@ class Context:
         (0: everything enqueued so far, 1: the raster front end of its latest opaque draw)."""
         check(lib.sr_context_wait_for(self.h, other.h, point))
 
+    def last_opaque_lists(self, ntiles: int):
+        """(offsets[ntiles + 1], ids, micro_area): the per-tile triangle lists the opaque fast path built for its latest draw."""
+        total, area = ctypes.c_uint64(), ctypes.c_uint32()
+        check(lib.sr_context_last_opaque_lists(self.h, None, None, 0, ctypes.byref(total), ctypes.byref(area)))
+        n = total.value
+        ids, off = np.zeros(max(n, 1), np.uint32), np.zeros(ntiles + 1, np.uint64)
+        check(lib.sr_context_last_opaque_lists(self.h, off.ctypes.data_as(_abi.u64p), ids.ctypes.data_as(_abi.u32p), n,
+                                               ctypes.byref(total), ctypes.byref(area)))
+        return off, ids[:n], area.value
+
     def set_list_capacity(self, entries: int):
         check(lib.sr_context_set_list_capacity(self.h, entries))
 

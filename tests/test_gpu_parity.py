@@ -433,6 +433,59 @@ def test_tile_bins_match_oracle(P, ctx, cull):
     fb.destroy()
 
 
+def _clamped_boxes(verts, idx, w, h):
+    """Per triangle, in f32 as the kernels and triangle.rs:64-78 compute them: frame-clamped bounding box area, the
+    candidate-tightening predicate and 'has a NaN coordinate'."""
+    p = verts[idx].reshape(-1, 3, verts.shape[1]).astype(np.float32)
+    x, y = p[:, :, 0], p[:, :, 1]
+    det = (y[:, 1] - y[:, 2]) * (x[:, 0] - x[:, 2]) + (x[:, 2] - x[:, 1]) * (y[:, 0] - y[:, 2])
+    xmin, xmax, ymin, ymax = x.min(1), x.max(1), y.min(1), y.max(1)
+    tight = (xmax - xmin < np.float32(4.99)) & (ymax - ymin < np.float32(4.99)) & (np.abs(det) >= 1)
+
+    def clamp(v, hi):
+        return np.where(v < 0, 0, np.where(v > hi, hi, np.trunc(np.nan_to_num(v)))).astype(np.int64)
+    area = (clamp(xmax, w - 1) - clamp(xmin, w - 1) + 1) * (clamp(ymax, h - 1) - clamp(ymin, h - 1) + 1)
+    return area, tight, np.isnan(x).any(1) | np.isnan(y).any(1)
+
+
+@pytest.mark.parametrize("n_small,n_big", [(90_000, 2500), (0, 3000)])
+def test_opaque_fast_path_lists_match_oracle_bins(P, ctx, n_small, n_big):
+    """SURVEY 8 a7 on the HEADLINE path: the per-tile lists k_micro + k_large_fill (big draws) and k_bin_small (draws of
+    <= 8192 triangles) build equal the oracle's bins restricted to the triangles that path sends through lists: those
+    whose frame-clamped bounding box exceeds the draw's split area and that the tightened small-triangle path does not
+    take (every triangle for a small draw)."""
+    rng = np.random.default_rng(33 + n_small)
+    w, h = 700, 450
+    parts = [H.random_screen_triangles(rng, n_big, w, h, max_size=90)]
+    if n_small:
+        parts.append(H.random_screen_triangles(rng, n_small, w, h, max_size=2.5))
+    verts = np.concatenate(parts)
+    n = len(verts) // 3
+    idx = rng.permutation(3 * n).astype(np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_FLAT)
+    tw, th = P.tile_size()
+    ntiles = ((w + tw - 1) // tw) * ((h + th - 1) // th)
+    g_off, g_ids, area_split = ctx.last_opaque_lists(ntiles)
+    assert (area_split > 0) == (n > 8192)
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 1)
+    o_off, o_ids = od.bins(w, h, tw, th, 0)
+    area, tight, nan = _clamped_boxes(verts, idx, w, h)
+    listed = ~nan & ((area > area_split) & ~tight if area_split else np.ones(n, bool))
+    keep = listed[o_ids]
+    want_ids = o_ids[keep]
+    tile_of_entry = np.repeat(np.arange(ntiles), np.diff(o_off.astype(np.int64)))
+    want_off = np.concatenate([[0], np.cumsum(np.bincount(tile_of_entry[keep], minlength=ntiles))])
+    assert np.array_equal(g_ids, want_ids)
+    assert np.array_equal(g_off.astype(np.int64), want_off)
+    assert len(want_ids) > 1000
+    pipe.destroy()
+    fb.destroy()
+
+
 # ------------------------------------------------------------------------------------------------------
 # ordered path: blend, stencil, discard, lines, points
 # ------------------------------------------------------------------------------------------------------
