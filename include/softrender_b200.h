@@ -146,21 +146,24 @@ int sr_framebuffer_clear(sr_framebuffer *, const float color[4]);
 /* HasDimensions::dimensions (src/geometry/dimension.rs:29) */
 int sr_framebuffer_dimensions(const sr_framebuffer *, uint32_t *width, uint32_t *height);
 /* read-back of the RenderBuffer's Vec<{color,depth}>: row-major, index = x + y*width
- * (src/geometry/coordinate.rs:47-51), 20 B/pixel {r,g,b,a,depth}. nbytes must be width*height*20. */
+ * (src/geometry/coordinate.rs:47-51), 20 B/pixel {r,g,b,a,depth} -- 8 B/pixel {r,g,b,a as u8, f32 depth} for an RGBAu8Color
+ * target.  nbytes must be width*height*20 (resp. *8). */
 int sr_framebuffer_download(sr_framebuffer *, void *dst, size_t nbytes);
 /* presentation read-back: the loop of realtime_example/src/main.rs:100-116, `(c.r * 255.0) as u8` per channel
  * (truncating, saturating, NaN -> 0), converted on the device so that 4 instead of 20 bytes per pixel cross PCIe.
  * order 0: bytes r,g,b,a (image crate Rgba<u8>, src/image/color.rs:60-90); order 1: a,b,g,r (the example's SDL
  * RGBA8888 streaming texture).  nbytes must be width*height*4. */
 int sr_framebuffer_download_rgba8(sr_framebuffer *, uint8_t *dst, size_t nbytes, uint32_t order);
-/* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL.  `stencil` holds width*height elements of the
- * format's stencil type (u8, u16 or u32: src/stencil.rs:9-60). */
-int sr_framebuffer_download_planes(sr_framebuffer *, float *color, float *depth, void *stencil);
-int sr_framebuffer_upload_planes(sr_framebuffer *, const float *color, const float *depth, const void *stencil);
+/* plane views (texturebuffer.rs:72-198 layout): any pointer may be NULL.  `color` holds width*height colours of the format's
+ * colour type (4 x f32, or 4 x u8 for an RGBAu8Color target), `stencil` width*height elements of its stencil type (u8, u16 or
+ * u32: src/stencil.rs:9-60). */
+int sr_framebuffer_download_planes(sr_framebuffer *, void *color, float *depth, void *stencil);
+int sr_framebuffer_upload_planes(sr_framebuffer *, const void *color, const float *depth, const void *stencil);
 /* checked accessors: PixelRead::pixel_ref / FramebufferAccessor::{get_depth, get_stencil} (src/pixels/mod.rs:56-63,
  * src/framebuffer/accessor.rs:28-38) and PixelWrite::pixel_mut / FramebufferAccessorMut::{set_depth, set_stencil}
  * (src/pixels/mod.rs:77-98, src/framebuffer/accessor.rs:52-70); out-of-range -> SR_ERR_INVALID_PIXEL_COORDINATE.
- * The stencil value travels as u32 whatever the attachment's width (set: it must fit); any pointer may be NULL. */
+ * The stencil value travels as u32 whatever the attachment's width (set: it must fit); the channels of an RGBAu8Color target
+ * travel as their values 0..255 in floats (set: they must be such values); any pointer may be NULL. */
 int sr_framebuffer_get_pixel(sr_framebuffer *, uint32_t x, uint32_t y, float rgba[4], float *depth, uint32_t *stencil);
 int sr_framebuffer_set_pixel(sr_framebuffer *, uint32_t x, uint32_t y, const float rgba[4], const float *depth, const uint32_t *stencil);
 /* parity introspection: per pixel, 1 + canonical index of the last primitive of the most recent

@@ -72,7 +72,11 @@ enum sr_fb_format {
     SR_FB_RGBAF32_DF32 = 0,     /* stencil type (): 20 B/pixel AoS {r,g,b,a,depth} */
     SR_FB_RGBAF32_DF32_S8 = 1,  /* stencil type u8: colour+depth AoS as above, stencil in its own u8 plane */
     SR_FB_RGBAF32_DF32_S16 = 2, /* stencil type u16 (the Stencil trait covers every integer width, src/stencil.rs:9-60) */
-    SR_FB_RGBAF32_DF32_S32 = 3  /* stencil type u32 */
+    SR_FB_RGBAF32_DF32_S32 = 3, /* stencil type u32 */
+    SR_FB_RGBAU8_DF32 = 4,      /* colour RGBAu8Color (src/color/predefined.rs:26): 8 B/pixel AoS {r,g,b,a as u8, f32 depth}.  A registered
+                                 * shader's f32 colour c is stored as `(c * 255.0) as u8` per channel; Blend = () only; lines scale the
+                                 * alpha channel with the integer rule of src/color/helper.rs:36-42 */
+    SR_FB_RGBAU8_DF32_S8 = 5    /* the same with a u8 stencil plane */
 };
 
 /* ---- Viewport (src/geometry/clipvertex.rs:40-48) ------------------------ */

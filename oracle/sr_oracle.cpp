@@ -623,14 +623,42 @@ struct RasterArgs {
 };
 
 // Shared tail of all three rasterisers after the stencil step: z<0, depth test, shade, blend.
+// RGBAu8Color targets (ref: src/color/predefined.rs:26).  The registered shaders compute f32 colours; their u8 form is
+// `(c * 255.0) as u8` per channel -- Rust's saturating, truncating `as` (NaN -> 0), the conversion of the reference's own
+// presentation loop (realtime_example/src/main.rs:100-116).
+inline uint8_t as_u8(float c) {
+    const float v = c * 255.0f;
+    if (!(v > 0.0f)) return 0;  // negative, zero, NaN
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+// AlphaMultiply for u8 (ref: src/color/helper.rs:36-42): (channel as f32 * (alpha as f32 / 255.0)) as u8
+inline uint8_t mul_alpha_u8(uint8_t channel, uint8_t alpha) {
+    const float v = (float)channel * ((float)alpha / 255.0f);
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
 inline void shade_and_write(const RasterArgs &A, so_framebuffer *fb, uint64_t index, const float *sv, float alpha,
-                            bool use_alpha, uint32_t prim_id) {
+                            bool use_alpha, uint32_t prim_id, double alpha_f64 = 1.0) {
     const float z = sv[2];
     if (z < 0.0f) {
         const float d = z;  // Depth::from_scalar
         const float dt = fb->depth[index];
         if (d >= dt) {
             float c[4];
+            if (fb->color_u8) {  // Blend = () on a u8 colour: blend(c.mul_alpha(..), p) = the source colour
+                if (!fragment_shader(A.fs, sv, A.uniforms, A.tex, c)) return;
+                uint8_t q[4] = {as_u8(c[0]), as_u8(c[1]), as_u8(c[2]), as_u8(c[3])};
+                // lines: c.mul_alpha(ColorAlpha::from_scalar(alpha)) (line.rs:100); from_scalar is NumCast f64 -> u8, i.e. the
+                // coverage truncates to 0 or 1 (src/color/mod.rs:26-33) -- kept as the reference has it
+                if (use_alpha) q[3] = mul_alpha_u8(q[3], (uint8_t)alpha_f64);
+                for (int i = 0; i < 4; ++i) fb->color_u8[index * 4 + i] = q[i];
+                fb->depth[index] = d;
+                if (fb->winner) fb->winner[index] = prim_id + 1;
+                return;
+            }
             if (fragment_shader(A.fs, sv, A.uniforms, A.tex, c)) {
                 if (use_alpha) c[3] = c[3] * alpha;  // Color::mul_alpha scales the alpha channel only (predefined.rs:82-86)
                 float outc[4];
@@ -811,7 +839,7 @@ void rasterize_line(const RasterArgs &A, so_framebuffer *fb, const float *start,
             const float xf = (float)x + 0.5f, yf = (float)y + 0.5f;
             const float t = hypot32(x1 - xf, y1 - yf) / d;
             for (uint32_t i = 0; i < S; ++i) scratch[i] = lerp(t, start[i], end[i]);
-            shade_and_write(A, fb, index, scratch, (float)alpha, true, prim_id);
+            shade_and_write(A, fb, index, scratch, (float)alpha, true, prim_id, alpha);
         }
     };
     if (A.aa_lines) draw_line_xiaolin_wu((double)x1, (double)y1, (double)x2, (double)y2, plot);
@@ -1144,7 +1172,8 @@ void so_framebuffer_clear(so_framebuffer *fb, const float color[4]) {
     const uint64_t n = (uint64_t)fb->width * fb->height;
     const float far_ = so_depth_far();
     for (uint64_t i = 0; i < n; ++i) {
-        for (int c = 0; c < 4; ++c) fb->color[i * 4 + c] = color[c];
+        if (fb->color_u8) for (int c = 0; c < 4; ++c) fb->color_u8[i * 4 + c] = as_u8(color[c]);
+        else for (int c = 0; c < 4; ++c) fb->color[i * 4 + c] = color[c];
         fb->depth[i] = far_;
         if (fb->stencil) stencil_store(fb, i, 0);
         if (fb->winner) fb->winner[i] = 0;

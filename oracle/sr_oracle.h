@@ -38,6 +38,8 @@ typedef struct so_framebuffer {
     uint8_t *stencil;  /* width*height or NULL (stencil type `()`) */
     uint32_t *winner;  /* optional: 1 + canonical index of the last primitive that wrote the pixel in this draw */
     uint32_t stencil_bytes; /* element size of `stencil`: 1 (u8; 0 means 1), 2 (u16) or 4 (u32) -- src/stencil.rs:9-60 */
+    uint8_t *color_u8;      /* non-NULL: the colour attachment is RGBAu8Color (src/color/predefined.rs:26), width*height*4 bytes;
+                             * `color` is then unused.  Blend = () only. */
 } so_framebuffer;
 
 typedef struct so_texture {

@@ -60,8 +60,8 @@ SYMBOLS = {
     "sr_framebuffer_dimensions": (c_int, [c_void_p, u32p, u32p]),
     "sr_framebuffer_download": (c_int, [c_void_p, c_void_p, c_size_t]),
     "sr_framebuffer_download_rgba8": (c_int, [c_void_p, u8p, c_size_t, c_u32]),
-    "sr_framebuffer_download_planes": (c_int, [c_void_p, f32p, f32p, c_void_p]),
-    "sr_framebuffer_upload_planes": (c_int, [c_void_p, f32p, f32p, c_void_p]),
+    "sr_framebuffer_download_planes": (c_int, [c_void_p, c_void_p, f32p, c_void_p]),
+    "sr_framebuffer_upload_planes": (c_int, [c_void_p, c_void_p, f32p, c_void_p]),
     "sr_framebuffer_get_pixel": (c_int, [c_void_p, c_u32, c_u32, f32p, f32p, u32p]),
     "sr_framebuffer_set_pixel": (c_int, [c_void_p, c_u32, c_u32, f32p, f32p, u32p]),
     "sr_framebuffer_enable_winner": (c_int, [c_void_p, c_int]),

@@ -165,6 +165,8 @@ struct sr_framebuffer {
     uint32_t ntx, nty;
     Buf aos_buf, stencil_buf, winner_buf;
     uint32_t stencil_bytes = 0;  // element size of the stencil attachment: 1, 2 or 4 (0: stencil type `()`)
+    bool u8color = false;        // RGBAu8Color target: 8-byte AoS pixels {rgba8, f32 depth}
+    size_t px_bytes() const { return u8color ? 8 : 20; }
     Buf vis_buf;                // visibility buffer of the opaque path (allocated on first use)
     bool vis_clean = false;     // every key of the tiles of shard (vis_rank, vis_world) is "far": the resolve hands it back that way
     uint32_t vis_rank = 0, vis_world = 0;
@@ -178,6 +180,7 @@ struct sr_framebuffer {
         v.aos = aos;
         v.stencil = stencil_buf ? stencil_buf->as<uint8_t>() : nullptr;
         v.stencil_bytes = stencil_bytes;
+        v.u8color = u8color ? 1u : 0u;
         v.winner = (winner_enabled && winner_buf) ? winner_buf->as<uint32_t>() : nullptr;
         v.width = width; v.height = height; v.ntx = ntx; v.nty = nty;
         v.pending_clear = pending_clear ? 1u : 0u;
@@ -1356,7 +1359,7 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
 // ---- framebuffer -----------------------------------------------------------------------------------------
 int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out) {
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format > SR_FB_RGBAF32_DF32_S32) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
+    if (format > SR_FB_RGBAU8_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
     if (width > 256u * SR_TILE_W || height > 256u * SR_TILE_H || width > 65535u || height > 65535u)
         return sr_fail(SR_ERR_UNSUPPORTED, "framebuffer %ux%u exceeds %ux%u", width, height, 256u * SR_TILE_W, 256u * SR_TILE_H);
     SR_CUDA(cudaSetDevice(c->device));
@@ -1365,9 +1368,11 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     fb->width = width; fb->height = height; fb->format = format;
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     const uint64_t n = (uint64_t)width * height;
-    SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * 20, &fb->aos_buf));
+    fb->u8color = format == SR_FB_RGBAU8_DF32 || format == SR_FB_RGBAU8_DF32_S8;
+    SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->px_bytes(), &fb->aos_buf));
     fb->aos = fb->aos_buf->as<float>();
-    fb->stencil_bytes = format == SR_FB_RGBAF32_DF32_S8 ? 1u : format == SR_FB_RGBAF32_DF32_S16 ? 2u : format == SR_FB_RGBAF32_DF32_S32 ? 4u : 0u;
+    fb->stencil_bytes = (format == SR_FB_RGBAF32_DF32_S8 || format == SR_FB_RGBAU8_DF32_S8) ? 1u : format == SR_FB_RGBAF32_DF32_S16 ? 2u
+                        : format == SR_FB_RGBAF32_DF32_S32 ? 4u : 0u;
     if (fb->stencil_bytes) SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->stencil_bytes, &fb->stencil_buf));
     // RenderBuffer::with_dimensions: Color::empty() (zeros), Depth::far(), stencil default -- recorded lazily
     fb->pending_clear = true;
@@ -1399,7 +1404,7 @@ int sr_framebuffer_dimensions(const sr_framebuffer *fb, uint32_t *w, uint32_t *h
 int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
     SrRange nvtx("softrender: framebuffer download");
     if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    const size_t need = (size_t)fb->width * fb->height * 20;
+    const size_t need = (size_t)fb->width * fb->height * fb->px_bytes();
     if (nbytes != need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, need);
     SR_CUDA(cudaSetDevice(fb->ctx->device));
     SR_TRY(materialize_clear(fb));
@@ -1417,23 +1422,28 @@ int sr_framebuffer_download_rgba8(sr_framebuffer *fb, uint8_t *dst, size_t nbyte
     SR_TRY(materialize_clear(fb));
     Buf packed;
     SR_TRY(c->alloc(n * 4, &packed));
-    SR_LAUNCH(c, k_fb_to_rgba8, ceil_div(ceil_div(n, 4), 256), 256, 0, fb->aos, n, order, packed->as<uint32_t>());
+    if (fb->u8color) SR_LAUNCH(c, k_fb8_to_rgba8, ceil_div(n, 256), 256, 0, reinterpret_cast<const uint2 *>(fb->aos), n, order, packed->as<uint32_t>());
+    else SR_LAUNCH(c, k_fb_to_rgba8, ceil_div(ceil_div(n, 4), 256), 256, 0, fb->aos, n, order, packed->as<uint32_t>());
     SR_CUDA(cudaMemcpyAsync(dst, packed->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
-int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *depth, void *stencil) {
+int sr_framebuffer_download_planes(sr_framebuffer *fb, void *color, float *depth, void *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     sr_context *c = fb->ctx;
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
     const uint64_t n = (uint64_t)fb->width * fb->height;
     Buf dc, dd;
-    if (color) SR_TRY(c->alloc(n * 16, &dc));
+    const size_t cbytes = fb->u8color ? 4 : 16;  // colour plane element: Vector4<u8> or Vector4<f32>
+    if (color) SR_TRY(c->alloc(n * cbytes, &dc));
     if (depth) SR_TRY(c->alloc(n * 4, &dd));
-    if (color || depth)
+    if ((color || depth) && fb->u8color)
+        SR_LAUNCH(c, k_fb8_split, ceil_div(n, 256), 256, 0, reinterpret_cast<const uint2 *>(fb->aos), n, color ? dc->as<uint32_t>() : nullptr,
+                  depth ? dd->as<float>() : nullptr);
+    else if (color || depth)
         SR_LAUNCH(c, k_fb_split, ceil_div(n, 256), 256, 0, fb->aos, n, color ? dc->as<float>() : nullptr, depth ? dd->as<float>() : nullptr);
-    if (color) SR_CUDA(cudaMemcpyAsync(color, dc->ptr, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (color) SR_CUDA(cudaMemcpyAsync(color, dc->ptr, n * cbytes, cudaMemcpyDeviceToHost, c->stream));
     if (depth) SR_CUDA(cudaMemcpyAsync(depth, dd->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (stencil) {
         if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
@@ -1442,7 +1452,7 @@ int sr_framebuffer_download_planes(sr_framebuffer *fb, float *color, float *dept
     SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
-int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const float *depth, const void *stencil) {
+int sr_framebuffer_upload_planes(sr_framebuffer *fb, const void *color, const float *depth, const void *stencil) {
     if (!fb) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (stencil && !fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");  // before anything is enqueued
     sr_context *c = fb->ctx;
@@ -1450,15 +1460,19 @@ int sr_framebuffer_upload_planes(sr_framebuffer *fb, const float *color, const f
     SR_TRY(materialize_clear(fb));
     const uint64_t n = (uint64_t)fb->width * fb->height;
     Buf dc, dd;
+    const size_t cbytes = fb->u8color ? 4 : 16;
     if (color) {
-        SR_TRY(c->alloc(n * 16, &dc));
-        SR_CUDA(cudaMemcpyAsync(dc->ptr, color, n * 16, cudaMemcpyHostToDevice, c->stream));
+        SR_TRY(c->alloc(n * cbytes, &dc));
+        SR_CUDA(cudaMemcpyAsync(dc->ptr, color, n * cbytes, cudaMemcpyHostToDevice, c->stream));
     }
     if (depth) {
         SR_TRY(c->alloc(n * 4, &dd));
         SR_CUDA(cudaMemcpyAsync(dd->ptr, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    if (color || depth)
+    if ((color || depth) && fb->u8color)
+        SR_LAUNCH(c, k_fb8_merge, ceil_div(n, 256), 256, 0, reinterpret_cast<uint2 *>(fb->aos), n, color ? dc->as<uint32_t>() : nullptr,
+                  depth ? dd->as<float>() : nullptr);
+    else if (color || depth)
         SR_LAUNCH(c, k_fb_merge, ceil_div(n, 256), 256, 0, fb->aos, n, color ? dc->as<float>() : nullptr, depth ? dd->as<float>() : nullptr);
     if (stencil) {
         if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
@@ -1474,13 +1488,19 @@ int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float r
     sr_context *c = fb->ctx;
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
-    float px[5];
+    float px[5] = {0, 0, 0, 0, 0};
+    uint32_t px8[2] = {0, 0};
     const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
-    SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
+    if (fb->u8color) SR_CUDA(cudaMemcpyAsync(px8, reinterpret_cast<unsigned char *>(fb->aos) + idx * 8, 8, cudaMemcpyDeviceToHost, c->stream));
+    else SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
     uint32_t s = 0;  // (little-endian: the low bytes of `s` receive a u8 / u16 element)
     if (stencil && fb->stencil_buf)
         SR_CUDA(cudaMemcpyAsync(&s, fb->stencil_buf->as<uint8_t>() + idx * fb->stencil_bytes, fb->stencil_bytes, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
+    if (fb->u8color) {  // channel values 0..255, as floats
+        for (int i = 0; i < 4; ++i) px[i] = (float)((px8[0] >> (8 * i)) & 255u);
+        memcpy(&px[4], &px8[1], 4);
+    }
     if (rgba) memcpy(rgba, px, 16);
     if (depth) *depth = px[4];
     if (stencil) *stencil = s;
@@ -1496,8 +1516,22 @@ int sr_framebuffer_set_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, const f
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
     const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
-    if (rgba) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5, rgba, 16, cudaMemcpyHostToDevice, c->stream));
-    if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5 + 4, depth, 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t packed = 0;
+    if (fb->u8color) {
+        unsigned char *px = reinterpret_cast<unsigned char *>(fb->aos) + idx * 8;
+        if (rgba) {
+            for (int i = 0; i < 4; ++i) {
+                if (!(rgba[i] >= 0.0f && rgba[i] <= 255.0f) || rgba[i] != (float)(uint32_t)rgba[i])
+                    return sr_fail(SR_ERR_INVALID_ARGUMENT, "channel %d = %g is not a u8 value (RGBAu8Color target: pass 0..255)", i, (double)rgba[i]);
+                packed |= (uint32_t)rgba[i] << (8 * i);
+            }
+            SR_CUDA(cudaMemcpyAsync(px, &packed, 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (depth) SR_CUDA(cudaMemcpyAsync(px + 4, depth, 4, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if (rgba) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5, rgba, 16, cudaMemcpyHostToDevice, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 5 + 4, depth, 4, cudaMemcpyHostToDevice, c->stream));
+    }
     if (stencil) {
         const uint32_t smax = fb->stencil_bytes == 1 ? 0xFFu : fb->stencil_bytes == 2 ? 0xFFFFu : 0xFFFFFFFFu;
         if (*stencil > smax) return sr_fail(SR_ERR_INVALID_ARGUMENT, "stencil value %u does not fit the attachment's %u-bit type", *stencil, fb->stencil_bytes * 8);
@@ -1540,7 +1574,7 @@ int sr_framebuffer_ipc_export(sr_framebuffer *fb, void *handle64) {
 int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width, uint32_t height, uint32_t format,
                             sr_framebuffer **out) {
     if (!c || !handle64 || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format != SR_FB_RGBAF32_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "peer framebuffers carry colour+depth only");
+    if (format != SR_FB_RGBAF32_DF32 && format != SR_FB_RGBAU8_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "peer framebuffers carry colour+depth only");
     SR_CUDA(cudaSetDevice(c->device));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
@@ -1551,6 +1585,7 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
     fb->width = width; fb->height = height; fb->format = format;
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     fb->aos = reinterpret_cast<float *>(p);
+    fb->u8color = format == SR_FB_RGBAU8_DF32;
     fb->is_peer = true;
     fb->pending_clear = false;
     ++c->refs;  // owns no buffer of the context, so it holds the reference itself (released by sr_framebuffer_destroy)
@@ -1560,7 +1595,7 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
 
 int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **out) {
     if (!c || !src || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (src->format != SR_FB_RGBAF32_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "aliased framebuffers carry colour+depth only");
+    if (src->format != SR_FB_RGBAF32_DF32 && src->format != SR_FB_RGBAU8_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "aliased framebuffers carry colour+depth only");
     SR_TRY(materialize_clear(src));
     SR_CUDA(cudaSetDevice(src->ctx->device));
     SR_CUDA(cudaStreamSynchronize(src->ctx->stream));
@@ -1575,6 +1610,7 @@ int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **ou
     fb->width = src->width; fb->height = src->height; fb->format = src->format;
     fb->ntx = src->ntx; fb->nty = src->nty;
     fb->aos = src->aos;
+    fb->u8color = src->u8color;
     fb->aos_buf = src->aos_buf;  // shares ownership: the pixels outlive either handle
     fb->pending_clear = false;
     *out = fb;
@@ -2145,7 +2181,12 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         const bool st_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
         if (d->vertex_lazy && !(d->blend == SR_BLEND_REPLACE && !st_active && fs != SR_FS_DISCARD_CHECKER)) SR_TRY(materialize_vertices(d));
     }
+    if (fb->u8color && d->blend != SR_BLEND_REPLACE)
+        return sr_fail(SR_ERR_UNSUPPORTED, "RGBAu8Color targets take Blend = () only: the registered blend functions are defined on f32 colours "
+                       "(full_example/src/color.rs:5-17); see INTEGRATION.md for registering a u8 blend");
     const bool samples = fs == SR_FS_FULL_EXAMPLE_TEXTURED || fs == SR_FS_TEXTURE_UNLIT;
+    if (samples && p->fb_texture && p->fb_texture->u8color)
+        return sr_fail(SR_ERR_UNSUPPORTED, "an RGBAu8Color target cannot be bound as a texture source (sampler semantics are defined for f32 targets and RGBA8 images)");
     if (samples && !p->texture && !p->fb_texture) return sr_fail(SR_ERR_INVALID_STATE, "textured shader without a bound texture");
     if (samples && p->fb_texture) {
         sr_framebuffer *src = p->fb_texture;

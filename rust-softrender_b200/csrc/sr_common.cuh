@@ -159,6 +159,7 @@ __device__ __forceinline__ uint32_t sr_prim_canonical(const SrPrimSource &s, uin
 // ---- framebuffer view ---------------------------------------------------------------------------
 struct SrFbView {
     float *aos;        // width*height*5 floats {r,g,b,a,depth}; may be a peer (NVLink) address
+    uint32_t u8color;  // colour attachment RGBAu8Color (src/color/predefined.rs:26): the AoS pixel is {rgba8, f32 depth} = 8 bytes instead of 20
     uint8_t *stencil;  // or null; elements of stencil_bytes (1, 2 or 4) bytes
     uint32_t stencil_bytes;
     uint32_t *winner;  // or null
@@ -167,6 +168,54 @@ struct SrFbView {
     uint32_t pending_clear;  // contents are the lazily-recorded clear colour, not yet in HBM
     float clear[4];
 };
+
+// ---- u8 colour targets ---------------------------------------------------------------------------------------
+// The registered fragment shaders compute f32 colours; on an RGBAu8Color target a shader's result is `(c * 255.0) as u8` per
+// channel (the conversion the reference's own presentation loop applies, realtime_example/src/main.rs:100-116; Rust's `as`
+// truncates toward zero and saturates, NaN -> 0: exactly cvt.rzi.u32.f32 + min).
+__device__ __forceinline__ uint32_t sr_as_u8(float c) { return min(__float2uint_rz(c * 255.0f), 255u); }
+// Color::mul_alpha of a u8 colour (src/color/predefined.rs:82-86 -> AlphaMultiply for u8, src/color/helper.rs:36-42):
+// (channel as f32 * (alpha as f32 / 255.0)) as u8, applied to the alpha channel only
+__device__ __forceinline__ uint32_t sr_mul_alpha_u8(uint32_t channel, uint32_t alpha) {
+    return min(__float2uint_rz((float)channel * ((float)alpha / 255.0f)), 255u);
+}
+// shader colour -> the four u8 channels, held as exact small floats (what the tile kernels keep in registers / shared memory);
+// line_alpha: the fragment of a line, whose coverage `alpha_u8` = ColorAlpha::from_scalar(alpha) (NumCast f64 -> u8: truncation,
+// so 0 or 1 -- a quirk of the reference that is kept: src/color/mod.rs:26-33, rasterization/line.rs:100) multiplies the alpha channel
+__device__ __forceinline__ void sr_quantise_u8(float *c, bool line_alpha, uint32_t alpha_u8) {
+    uint32_t q[4] = {sr_as_u8(c[0]), sr_as_u8(c[1]), sr_as_u8(c[2]), sr_as_u8(c[3])};
+    if (line_alpha) q[3] = sr_mul_alpha_u8(q[3], alpha_u8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (float)q[i];
+}
+__device__ __forceinline__ uint32_t sr_pack_u8(const float *q) {  // q: channel values 0..255 as floats
+    return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+}
+__device__ __forceinline__ void sr_unpack_u8(uint32_t v, float *q) {
+    q[0] = (float)(v & 255u); q[1] = (float)((v >> 8) & 255u); q[2] = (float)((v >> 16) & 255u); q[3] = (float)(v >> 24);
+}
+// one pixel of either AoS layout; colours of a u8 target travel as channel values 0..255 in floats
+__device__ __forceinline__ void sr_fb_store_pixel(const SrFbView &fb, uint64_t index, const float *o /* r,g,b,a,depth */) {
+    if (fb.u8color) {
+        *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(fb.aos) + index * 8) = make_uint2(sr_pack_u8(o), __float_as_uint(o[4]));
+    } else {
+        float *dst = fb.aos + index * 5;
+        dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; dst[4] = o[4];
+    }
+}
+__device__ __forceinline__ void sr_fb_load_pixel(const SrFbView &fb, uint64_t index, float *o) {
+    if (fb.u8color) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(fb.aos) + index * 8);
+        sr_unpack_u8(v.x, o);
+        o[4] = __uint_as_float(v.y);
+    } else {
+        const float *src = fb.aos + index * 5;
+        o[0] = src[0]; o[1] = src[1]; o[2] = src[2]; o[3] = src[3]; o[4] = src[4];
+    }
+}
+__device__ __forceinline__ float sr_fb_load_depth(const SrFbView &fb, uint64_t index) {
+    return fb.u8color ? reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(fb.aos) + index * 8)[1] : fb.aos[index * 5 + 4];
+}
 
 // packed tile rectangle of a primitive: tx0 | ty0<<8 | tx1<<16 | ty1<<24
 __device__ __forceinline__ uint32_t sr_pack_rect(uint32_t tx0, uint32_t ty0, uint32_t tx1, uint32_t ty1) {

@@ -463,8 +463,11 @@ struct SrTileParams {
     SrFsConst fs;
 };
 
-__device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, uint32_t py) {
+__device__ __forceinline__ float *sr_fb_pixel(const SrFbView &fb, uint32_t px, uint32_t py) {  // (20-byte pixels; 8-byte ones: address below)
     return fb.aos + ((uint64_t)py * fb.width + px) * 5;
+}
+__device__ __forceinline__ void *sr_fb_pixel_addr(const SrFbView &fb, uint32_t px, uint32_t py) {
+    return reinterpret_cast<unsigned char *>(fb.aos) + ((uint64_t)py * fb.width + px) * (fb.u8color ? 8u : 20u);
 }
 
 // =====================================================================================================
@@ -511,8 +514,8 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         uint32_t dk0 = ~SR_DEPTH_FAR_BITS, dk1 = ~SR_DEPTH_FAR_BITS;
         if (!fb.pending_clear && py < fb.height) {
-            if (px < fb.width) dk0 = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px) * 5 + 4]);
-            if (px + 1 < fb.width) dk1 = sr_depth_key(fb.aos[((uint64_t)py * fb.width + px + 1) * 5 + 4]);
+            if (px < fb.width) dk0 = sr_depth_key(sr_fb_load_depth(fb, (uint64_t)py * fb.width + px));
+            if (px + 1 < fb.width) dk1 = sr_depth_key(sr_fb_load_depth(fb, (uint64_t)py * fb.width + px + 1));
         }
         *reinterpret_cast<ulonglong2 *>(vis + sr_vis_index(px, py, fb.ntx)) =
             make_ulonglong2((unsigned long long)dk0 << 32, (unsigned long long)dk1 << 32);
@@ -531,6 +534,17 @@ struct SrTileOwners {
     uint32_t period;
 };
 __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t x0, uint32_t y0) {
+    if (fb.u8color) {
+        float q[4] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3]};
+        sr_quantise_u8(q, false, 0);
+        const uint32_t pat[2] = {sr_pack_u8(q), SR_DEPTH_FAR_BITS};
+        const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 2;  // words per tile row inside the frame
+        for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
+            uint32_t *row = reinterpret_cast<uint32_t *>(fb.aos) + ((uint64_t)(y0 + r) * fb.width + x0) * 2;
+            for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i & 1u];
+        }
+        return;
+    }
     const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
     const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
     for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
@@ -559,15 +573,6 @@ __global__ void __launch_bounds__(256) k_fb_fill_foreign(const SrFbView fb, cons
     const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
     if (x0 < fb.width) sr_fill_tile_clear(fb, x0, y0);
 }
-#if 0
-    const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
-    const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
-    for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
-        float *row = fb.aos + ((uint64_t)(y0 + r) * fb.width + x0) * 5;
-        for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i % 5];
-    }
-}
-#endif
 // The merge of a range-sharded frame as a streaming kernel of its own (the alternative to merging inside the resolve,
 // k_tile_opaque PHASE 2 with npeers > 0): one light CTA per owned tile pulls the peers' keys of that tile straight from
 // peer-mapped memory (16-byte coalesced loads over NVLink, all peers' loads of a thread in flight together), max-merges them
@@ -1302,7 +1307,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
         for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) {
             const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
             uint32_t dk = ~SR_DEPTH_FAR_BITS;
-            if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_pixel(p.fb, px, py)[4]);
+            if (!p.fb.pending_clear && px < W && py < H) dk = sr_depth_key(sr_fb_load_depth(p.fb, (uint64_t)py * W + px));
             keys[i] = (unsigned long long)dk << 32;
         }
         __syncthreads();
@@ -1486,7 +1491,8 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
     // (pending clear) the 640 B of AoS pixels are staged in shared memory and leave with one TMA bulk store.
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     float *stage = stage_all + warp * 2 * SR_OPQ_STAGE_FLOATS;
-    const bool row_aligned = (W % 4u) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
+    const bool u8c = p.fb.u8color != 0;  // RGBAu8Color target: 8-byte pixels, colours quantised when they are produced
+    const bool row_aligned = (W % (u8c ? 2u : 4u)) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
     uint32_t nbulk = 0;
     // The winner's vertex indices are fetched one chunk ahead, so the two dependent gathers (indices, then vertices) of
     // consecutive chunks overlap instead of adding up.
@@ -1525,6 +1531,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
             if (id_cur == 0) {
                 if (p.fb.pending_clear) {
                     o[0] = p.fb.clear[0]; o[1] = p.fb.clear[1]; o[2] = p.fb.clear[2]; o[3] = p.fb.clear[3];
+                    if (u8c) sr_quantise_u8(o, false, 0);
                     o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
                     write = true;
                 }
@@ -1568,6 +1575,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
                     canonical = p.point_base + sr_prim_canonical(p.points, pt, 0);
                 }
                 sr_fragment_shader<FS>(p.fs, sv, o);  // (a line's colour alpha is scaled by its coverage, 1.0 without antialiasing)
+                if (u8c) sr_quantise_u8(o, e < p.nlines, 1u);  // (u8 colours: mul_alpha by the coverage 1.0 is NOT the identity, helper.rs:36-42)
                 o[4] = sv[2];
                 write = true;
                 if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = canonical + 1;
@@ -1618,6 +1626,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
                     }
                 }
                 sr_fragment_shader<FS>(p.fs, sv, o);
+                if (u8c) sr_quantise_u8(o, false, 0);
                 o[4] = sv[2];
                 write = true;
                 if (p.fb.winner) p.fb.winner[(uint64_t)py * W + px] = sr_prim_canonical(p.tris, t, 0) + 1;
@@ -1630,18 +1639,21 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
             }
+            if (u8c) {
+                reinterpret_cast<uint2 *>(sb)[lane] = make_uint2(sr_pack_u8(o), __float_as_uint(o[4]));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 5; ++k) sb[lane * 5 + k] = o[k];
+                for (int k = 0; k < 5; ++k) sb[lane * 5 + k] = o[k];
+            }
             sr_fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                sr_bulk_s2g(sr_fb_pixel(p.fb, cx0, py), sb, 32 * 20);
+                sr_bulk_s2g(sr_fb_pixel_addr(p.fb, cx0, py), sb, u8c ? 32 * 8 : 32 * 20);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             ++nbulk;
         } else if (write) {
-            float *dst = sr_fb_pixel(p.fb, px, py);
-            dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3]; dst[4] = o[4];
+            sr_fb_store_pixel(p.fb, (uint64_t)py * W + px, o);
         }
     }
     if ((nbulk && lane == 0) || (p.vis != nullptr && p.reset_vis && tid < SR_TILE_H)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1701,12 +1713,19 @@ __device__ __forceinline__ bool sr_ord_stencil_step(const SrOrdCtx &c, uint32_t 
 // everything after the stencil step of one fragment (triangle.rs:117-143, line.rs:81-106, point.rs:62-82)
 template <int FS>
 __device__ __forceinline__ void sr_ord_shade_write(const SrOrdCtx &c, uint32_t li, const float *sv, bool use_alpha, float alpha,
-                                                   uint32_t canonical) {
+                                                   uint32_t canonical, uint32_t alpha_u8 = 1u) {
     const float z = sv[2];
     if (!(z < 0.0f)) return;
     if (!(z >= c.depth[li])) return;
     float col[4];
     if (!sr_fragment_shader<FS>(c.p->fs, sv, col)) return;  // Fragment::Discard
+    if (c.p->fb.u8color) {  // RGBAu8Color target (Blend = () only): the tile holds channel values 0..255
+        sr_quantise_u8(col, use_alpha, alpha_u8);
+        c.color[li] = make_float4(col[0], col[1], col[2], col[3]);
+        c.depth[li] = z;
+        c.winner[li] = canonical + 1;
+        return;
+    }
     if (use_alpha) col[3] = col[3] * alpha;                 // Color::mul_alpha (src/color/predefined.rs:82-86)
     const float4 old = c.color[li];
     const float dstc[4] = {old.x, old.y, old.z, old.w};
@@ -1805,7 +1824,7 @@ __device__ __noinline__ void sr_ord_plot_line(const SrOrdCtx &c, const SrLineCtx
         sv[4 + pl * 4 + 2] = sr_lerp(t, ka.z, kb.z);
         sv[4 + pl * 4 + 3] = sr_lerp(t, ka.w, kb.w);
     }
-    sr_ord_shade_write<FS>(c, li, sv, true, (float)alpha, L.canonical);
+    sr_ord_shade_write<FS>(c, li, sv, true, (float)alpha, L.canonical, (uint32_t)alpha /* NumCast f64 -> u8 */);
 }
 
 __device__ __forceinline__ double sr_fract64(double x) { return x - trunc(x); }
@@ -2020,11 +2039,14 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     // load the tile (or generate the pending clear on chip)
     for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
-        float4 col = make_float4(p.fb.clear[0], p.fb.clear[1], p.fb.clear[2], p.fb.clear[3]);
+        float cl[4] = {p.fb.clear[0], p.fb.clear[1], p.fb.clear[2], p.fb.clear[3]};
+        if (p.fb.u8color) sr_quantise_u8(cl, false, 0);
+        float4 col = make_float4(cl[0], cl[1], cl[2], cl[3]);
         float d = __uint_as_float(SR_DEPTH_FAR_BITS);
         uint32_t s = 0;
         if (!p.fb.pending_clear && px < W && py < H) {
-            const float *src = sr_fb_pixel(p.fb, px, py);
+            float src[5];
+            sr_fb_load_pixel(p.fb, (uint64_t)py * W + px, src);
             col = make_float4(src[0], src[1], src[2], src[3]);
             d = src[4];
             if (c.has_stencil) s = sr_stencil_load(p.fb.stencil, c.sbytes, (uint64_t)py * W + px);
@@ -2380,10 +2402,9 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_RASTER_THREADS) {
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         if (px >= W || py >= H) continue;
-        float *dst = sr_fb_pixel(p.fb, px, py);
         const float4 col = s_color[i];
-        dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; dst[3] = col.w;
-        dst[4] = s_depth[i];
+        const float o5[5] = {col.x, col.y, col.z, col.w, s_depth[i]};
+        sr_fb_store_pixel(p.fb, (uint64_t)py * W + px, o5);
         if (c.has_stencil) sr_stencil_store(p.fb.stencil, c.sbytes, (uint64_t)py * W + px, sr_stencil_load(s_stencil, c.sbytes, i));
         if (p.fb.winner && s_winner[i]) p.fb.winner[(uint64_t)py * W + px] = s_winner[i];  // plane is zeroed per draw
     }
@@ -2425,9 +2446,9 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t seed, uint64
 __global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint64_t)fb.width * fb.height) return;
-    float *dst = fb.aos + i * 5;
-    dst[0] = fb.clear[0]; dst[1] = fb.clear[1]; dst[2] = fb.clear[2]; dst[3] = fb.clear[3];
-    dst[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+    float o[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    if (fb.u8color) sr_quantise_u8(o, false, 0);
+    sr_fb_store_pixel(fb, i, o);
     if (fb.stencil) sr_stencil_store(fb.stencil, fb.stencil_bytes, i, 0u);
     if (fb.winner) fb.winner[i] = 0;
 }
@@ -2435,7 +2456,6 @@ __global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
 // cast truncates toward zero and saturates (NaN -> 0), which is what cvt.rzi.u32.f32 + min does.  order 0: bytes r,g,b,a;
 // order 1: a,b,g,r (what the example writes into SDL's RGBA8888 streaming texture).
 // Four pixels per thread: 80 contiguous bytes in (five 128-bit loads), 16 bytes out.
-__device__ __forceinline__ uint32_t sr_as_u8(float c) { return min(__float2uint_rz(c * 255.0f), 255u); }
 __global__ void __launch_bounds__(256) k_fb_to_rgba8(const float *aos, uint64_t n, uint32_t order, uint32_t *out) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel quad
     if (q * 4 >= n) return;
@@ -2465,4 +2485,26 @@ __global__ void __launch_bounds__(256) k_fb_merge(float *aos, uint64_t n, const 
     if (i >= n) return;
     if (color) { aos[i * 5] = color[i * 4]; aos[i * 5 + 1] = color[i * 4 + 1]; aos[i * 5 + 2] = color[i * 4 + 2]; aos[i * 5 + 3] = color[i * 4 + 3]; }
     if (depth) aos[i * 5 + 4] = depth[i];
+}
+// the same three for the 8-byte pixels of an RGBAu8Color target (the colour plane is u8 x 4 per pixel, stored as is)
+__global__ void __launch_bounds__(256) k_fb8_to_rgba8(const uint2 *aos, uint64_t n, uint32_t order, uint32_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = aos[i].x;
+    out[i] = order ? __byte_perm(v, 0, 0x0123) : v;
+}
+__global__ void __launch_bounds__(256) k_fb8_split(const uint2 *aos, uint64_t n, uint32_t *color, float *depth) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 v = aos[i];
+    if (color) color[i] = v.x;
+    if (depth) depth[i] = __uint_as_float(v.y);
+}
+__global__ void __launch_bounds__(256) k_fb8_merge(uint2 *aos, uint64_t n, const uint32_t *color, const float *depth) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 v = aos[i];
+    if (color) v.x = color[i];
+    if (depth) v.y = __float_as_uint(depth[i]);
+    aos[i] = v;
 }

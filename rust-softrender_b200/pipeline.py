@@ -160,13 +160,23 @@ class RenderBuffer:
     def __init__(self, ctx: Context, handle, width, height, fmt):
         self.ctx, self.h, self.width, self.height, self.format = ctx, handle, width, height, fmt
 
-    _STENCIL_DTYPE = {FB_RGBAF32_DF32_S8: np.uint8, FB_RGBAF32_DF32_S16: np.uint16, FB_RGBAF32_DF32_S32: np.uint32}
+    _STENCIL_DTYPE = {FB_RGBAF32_DF32_S8: np.uint8, FB_RGBAF32_DF32_S16: np.uint16, FB_RGBAF32_DF32_S32: np.uint32,
+                      FB_RGBAU8_DF32_S8: np.uint8}
+    U8_PIXEL = np.dtype([("rgba", np.uint8, 4), ("depth", np.float32)])  # the 8-byte AoS pixel of an RGBAu8Color target
+
+    @property
+    def u8_color(self) -> bool:
+        return self.format in (FB_RGBAU8_DF32, FB_RGBAU8_DF32_S8)
 
     @staticmethod
-    def with_dimensions(ctx: Context, width: int, height: int, stencil=False) -> "RenderBuffer":
-        """stencil: False = stencil type `()`, True / 8 = u8, 16 = u16, 32 = u32 (the Stencil trait, src/stencil.rs:9-60)."""
-        fmt = {False: FB_RGBAF32_DF32, True: FB_RGBAF32_DF32_S8, 8: FB_RGBAF32_DF32_S8, 16: FB_RGBAF32_DF32_S16,
-               32: FB_RGBAF32_DF32_S32}[stencil]
+    def with_dimensions(ctx: Context, width: int, height: int, stencil=False, u8_color: bool = False) -> "RenderBuffer":
+        """stencil: False = stencil type `()`, True / 8 = u8, 16 = u16, 32 = u32 (the Stencil trait, src/stencil.rs:9-60).
+        u8_color: colour attachment RGBAu8Color instead of RGBAf32Color (src/color/predefined.rs:17,26)."""
+        if u8_color:
+            fmt = {False: FB_RGBAU8_DF32, True: FB_RGBAU8_DF32_S8, 8: FB_RGBAU8_DF32_S8}[stencil]
+        else:
+            fmt = {False: FB_RGBAF32_DF32, True: FB_RGBAF32_DF32_S8, 8: FB_RGBAF32_DF32_S8, 16: FB_RGBAF32_DF32_S16,
+                   32: FB_RGBAF32_DF32_S32}[stencil]
         h = ctypes.c_void_p()
         check(lib.sr_framebuffer_create(ctx.h, width, height, fmt, ctypes.byref(h)))
         return RenderBuffer(ctx, h, width, height, fmt)
@@ -184,10 +194,11 @@ class RenderBuffer:
         check(lib.sr_framebuffer_clear(self.h, c))
 
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """AoS read-back: float32 [height*width, 5] = {r,g,b,a,depth}, index = x + y*width."""
+        """AoS read-back: float32 [height*width, 5] = {r,g,b,a,depth}, index = x + y*width (an RGBAu8Color target: a
+        structured array of U8_PIXEL = {rgba: 4 x u8, depth: f32})."""
         n = self.width * self.height
         if out is None:
-            out = np.empty((n, 5), np.float32)
+            out = np.empty(n, self.U8_PIXEL) if self.u8_color else np.empty((n, 5), np.float32)
         check(lib.sr_framebuffer_download(self.h, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
         return out
 
@@ -210,17 +221,17 @@ class RenderBuffer:
 
     def download_planes(self, stencil: bool = False):
         n = self.width * self.height
-        color, depth = np.empty((n, 4), np.float32), np.empty(n, np.float32)
+        color, depth = np.empty((n, 4), np.uint8 if self.u8_color else np.float32), np.empty(n, np.float32)
         st = np.empty(n, self._STENCIL_DTYPE[self.format]) if stencil else None
-        check(lib.sr_framebuffer_download_planes(self.h, color.ctypes.data_as(_abi.f32p), depth.ctypes.data_as(_abi.f32p),
+        check(lib.sr_framebuffer_download_planes(self.h, color.ctypes.data_as(ctypes.c_void_p), depth.ctypes.data_as(_abi.f32p),
                                                  st.ctypes.data_as(ctypes.c_void_p) if st is not None else None))
         return color, depth, st
 
     def upload_planes(self, color=None, depth=None, stencil=None):
-        c = np.ascontiguousarray(color, np.float32) if color is not None else None
+        c = np.ascontiguousarray(color, np.uint8 if self.u8_color else np.float32) if color is not None else None
         d = np.ascontiguousarray(depth, np.float32) if depth is not None else None
         s = np.ascontiguousarray(stencil, self._STENCIL_DTYPE.get(self.format, np.uint8)) if stencil is not None else None
-        check(lib.sr_framebuffer_upload_planes(self.h, c.ctypes.data_as(_abi.f32p) if c is not None else None,
+        check(lib.sr_framebuffer_upload_planes(self.h, c.ctypes.data_as(ctypes.c_void_p) if c is not None else None,
                                                d.ctypes.data_as(_abi.f32p) if d is not None else None,
                                                s.ctypes.data_as(ctypes.c_void_p) if s is not None else None))
 
@@ -258,7 +269,7 @@ class RenderBuffer:
         """A second handle on the same pixels for another context of this process (sr_framebuffer_alias)."""
         h = ctypes.c_void_p()
         check(lib.sr_framebuffer_alias(ctx.h, self.h, ctypes.byref(h)))
-        return RenderBuffer(ctx, h, self.width, self.height, FB_RGBAF32_DF32)
+        return RenderBuffer(ctx, h, self.width, self.height, self.format)
 
     @staticmethod
     def ipc_open(ctx: Context, handle: bytes, width: int, height: int) -> "RenderBuffer":

@@ -23,7 +23,7 @@ u8p = ctypes.POINTER(ctypes.c_uint8)
 
 class SoFramebuffer(ctypes.Structure):
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("color", f32p), ("depth", f32p),
-                ("stencil", u8p), ("winner", u32p), ("stencil_bytes", ctypes.c_uint32)]
+                ("stencil", u8p), ("winner", u32p), ("stencil_bytes", ctypes.c_uint32), ("color_u8", u8p)]
 
 
 class SoTexture(ctypes.Structure):
@@ -127,6 +127,7 @@ class OracleFramebuffer:
     width: int
     height: int
     stencil_bits: int = 0
+    u8_color: bool = False  # colour attachment RGBAu8Color (src/color/predefined.rs:26) instead of RGBAf32Color
     color: np.ndarray = field(init=False)
     depth: np.ndarray = field(init=False)
     stencil: np.ndarray | None = field(init=False)
@@ -134,15 +135,16 @@ class OracleFramebuffer:
 
     def __post_init__(self):
         n = self.width * self.height
-        self.color = np.zeros((n, 4), np.float32)
+        self.color = np.zeros((n, 4), np.uint8 if self.u8_color else np.float32)
         self.depth = np.full(n, lib().so_depth_far(), np.float32)
         self.stencil = np.zeros(n, {16: np.uint16, 32: np.uint32}.get(self.stencil_bits, np.uint8)) if self.stencil_bits else None
         self.winner = np.zeros(n, np.uint32)
 
     def struct(self) -> SoFramebuffer:
-        return SoFramebuffer(self.width, self.height, _fp(self.color), _fp(self.depth),
+        return SoFramebuffer(self.width, self.height, None if self.u8_color else _fp(self.color), _fp(self.depth),
                              self.stencil.ctypes.data_as(u8p) if self.stencil is not None else None,
-                             self.winner.ctypes.data_as(u32p), self.stencil.itemsize if self.stencil is not None else 0)
+                             self.winner.ctypes.data_as(u32p), self.stencil.itemsize if self.stencil is not None else 0,
+                             self.color.ctypes.data_as(u8p) if self.u8_color else None)
 
     def clear(self, color):
         c = np.asarray(color, np.float32)
