@@ -76,7 +76,11 @@ enum sr_fb_format {
     SR_FB_RGBAU8_DF32 = 4,      /* colour RGBAu8Color (src/color/predefined.rs:26): 8 B/pixel AoS {r,g,b,a as u8, f32 depth}.  A registered
                                  * shader's f32 colour c is stored as `(c * 255.0) as u8` per channel; Blend = () only; lines scale the
                                  * alpha channel with the integer rule of src/color/helper.rs:36-42 */
-    SR_FB_RGBAU8_DF32_S8 = 5    /* the same with a u8 stencil plane */
+    SR_FB_RGBAU8_DF32_S8 = 5,   /* the same with a u8 stencil plane */
+    SR_FB_TEXTURE_RGBAF32_DF32 = 6,    /* RGBAf32TextureBuffer (src/framebuffer/texturebuffer.rs:200-210, declare_texture_buffer! :72-198): the colour
+                                        * attachment is its own plane of width*height Vector4<f32> ("re-used as textures without copying", :63-66) and
+                                        * the depths another: 16 + 4 B/pixel, structure of arrays */
+    SR_FB_TEXTURE_RGBAF32_DF32_S8 = 7  /* the same with a u8 stencil plane */
 };
 
 /* ---- Viewport (src/geometry/clipvertex.rs:40-48) ------------------------ */

@@ -166,6 +166,7 @@ struct sr_framebuffer {
     Buf aos_buf, stencil_buf, winner_buf;
     uint32_t stencil_bytes = 0;  // element size of the stencil attachment: 1, 2 or 4 (0: stencil type `()`)
     bool u8color = false;        // RGBAu8Color target: 8-byte AoS pixels {rgba8, f32 depth}
+    bool soa = false;            // texture-buffer storage: colour plane (float4 per pixel) followed by the depth plane
     size_t px_bytes() const { return u8color ? 8 : 20; }
     Buf vis_buf;                // visibility buffer of the opaque path (allocated on first use)
     bool vis_clean = false;     // every key of the tiles of shard (vis_rank, vis_world) is "far": the resolve hands it back that way
@@ -181,6 +182,7 @@ struct sr_framebuffer {
         v.stencil = stencil_buf ? stencil_buf->as<uint8_t>() : nullptr;
         v.stencil_bytes = stencil_bytes;
         v.u8color = u8color ? 1u : 0u;
+        v.soa = soa ? 1u : 0u;
         v.winner = (winner_enabled && winner_buf) ? winner_buf->as<uint32_t>() : nullptr;
         v.width = width; v.height = height; v.ntx = ntx; v.nty = nty;
         v.pending_clear = pending_clear ? 1u : 0u;
@@ -1359,7 +1361,7 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
 // ---- framebuffer -----------------------------------------------------------------------------------------
 int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out) {
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format > SR_FB_RGBAU8_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
+    if (format > SR_FB_TEXTURE_RGBAF32_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
     if (width > 256u * SR_TILE_W || height > 256u * SR_TILE_H || width > 65535u || height > 65535u)
         return sr_fail(SR_ERR_UNSUPPORTED, "framebuffer %ux%u exceeds %ux%u", width, height, 256u * SR_TILE_W, 256u * SR_TILE_H);
     SR_CUDA(cudaSetDevice(c->device));
@@ -1369,9 +1371,11 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     const uint64_t n = (uint64_t)width * height;
     fb->u8color = format == SR_FB_RGBAU8_DF32 || format == SR_FB_RGBAU8_DF32_S8;
+    fb->soa = format == SR_FB_TEXTURE_RGBAF32_DF32 || format == SR_FB_TEXTURE_RGBAF32_DF32_S8;
     SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->px_bytes(), &fb->aos_buf));
     fb->aos = fb->aos_buf->as<float>();
-    fb->stencil_bytes = (format == SR_FB_RGBAF32_DF32_S8 || format == SR_FB_RGBAU8_DF32_S8) ? 1u : format == SR_FB_RGBAF32_DF32_S16 ? 2u
+    fb->stencil_bytes = (format == SR_FB_RGBAF32_DF32_S8 || format == SR_FB_RGBAU8_DF32_S8 || format == SR_FB_TEXTURE_RGBAF32_DF32_S8) ? 1u
+                        : format == SR_FB_RGBAF32_DF32_S16 ? 2u
                         : format == SR_FB_RGBAF32_DF32_S32 ? 4u : 0u;
     if (fb->stencil_bytes) SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->stencil_bytes, &fb->stencil_buf));
     // RenderBuffer::with_dimensions: Color::empty() (zeros), Depth::far(), stencil default -- recorded lazily
@@ -1408,6 +1412,14 @@ int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
     if (nbytes != need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, need);
     SR_CUDA(cudaSetDevice(fb->ctx->device));
     SR_TRY(materialize_clear(fb));
+    if (fb->soa) {  // the reference's PixelRead view of a texture buffer: gathered into the same 20-byte records
+        Buf tmp;
+        SR_TRY(fb->ctx->alloc(need, &tmp));
+        SR_LAUNCH(fb->ctx, k_soa_to_aos, ceil_div((uint64_t)fb->width * fb->height, 256), 256, 0, fb->view(), tmp->as<float>());
+        SR_CUDA(cudaMemcpyAsync(dst, tmp->ptr, need, cudaMemcpyDeviceToHost, fb->ctx->stream));
+        SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
+        return SR_OK;
+    }
     SR_CUDA(cudaMemcpyAsync(dst, fb->aos, need, cudaMemcpyDeviceToHost, fb->ctx->stream));
     SR_CUDA(cudaStreamSynchronize(fb->ctx->stream));
     return SR_OK;
@@ -1422,7 +1434,8 @@ int sr_framebuffer_download_rgba8(sr_framebuffer *fb, uint8_t *dst, size_t nbyte
     SR_TRY(materialize_clear(fb));
     Buf packed;
     SR_TRY(c->alloc(n * 4, &packed));
-    if (fb->u8color) SR_LAUNCH(c, k_fb8_to_rgba8, ceil_div(n, 256), 256, 0, reinterpret_cast<const uint2 *>(fb->aos), n, order, packed->as<uint32_t>());
+    if (fb->soa) SR_LAUNCH(c, k_soa_to_rgba8, ceil_div(n, 256), 256, 0, fb->view(), order, packed->as<uint32_t>());
+    else if (fb->u8color) SR_LAUNCH(c, k_fb8_to_rgba8, ceil_div(n, 256), 256, 0, reinterpret_cast<const uint2 *>(fb->aos), n, order, packed->as<uint32_t>());
     else SR_LAUNCH(c, k_fb_to_rgba8, ceil_div(ceil_div(n, 4), 256), 256, 0, fb->aos, n, order, packed->as<uint32_t>());
     SR_CUDA(cudaMemcpyAsync(dst, packed->ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
     SR_CUDA(cudaStreamSynchronize(c->stream));
@@ -1434,6 +1447,16 @@ int sr_framebuffer_download_planes(sr_framebuffer *fb, void *color, float *depth
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
     const uint64_t n = (uint64_t)fb->width * fb->height;
+    if (fb->soa) {  // the planes ARE the storage: straight copies
+        if (color) SR_CUDA(cudaMemcpyAsync(color, fb->aos, n * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(depth, fb->aos + 4 * n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (stencil) {
+            if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
+            SR_CUDA(cudaMemcpyAsync(stencil, fb->stencil_buf->ptr, n * fb->stencil_bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+        SR_CUDA(cudaStreamSynchronize(c->stream));
+        return SR_OK;
+    }
     Buf dc, dd;
     const size_t cbytes = fb->u8color ? 4 : 16;  // colour plane element: Vector4<u8> or Vector4<f32>
     if (color) SR_TRY(c->alloc(n * cbytes, &dc));
@@ -1459,6 +1482,13 @@ int sr_framebuffer_upload_planes(sr_framebuffer *fb, const void *color, const fl
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_clear(fb));
     const uint64_t n = (uint64_t)fb->width * fb->height;
+    if (fb->soa) {
+        if (color) SR_CUDA(cudaMemcpyAsync(fb->aos, color, n * 16, cudaMemcpyHostToDevice, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * n, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (stencil) SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->ptr, stencil, n * fb->stencil_bytes, cudaMemcpyHostToDevice, c->stream));
+        SR_CUDA(cudaStreamSynchronize(c->stream));
+        return SR_OK;
+    }
     Buf dc, dd;
     const size_t cbytes = fb->u8color ? 4 : 16;
     if (color) {
@@ -1491,7 +1521,11 @@ int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float r
     float px[5] = {0, 0, 0, 0, 0};
     uint32_t px8[2] = {0, 0};
     const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
-    if (fb->u8color) SR_CUDA(cudaMemcpyAsync(px8, reinterpret_cast<unsigned char *>(fb->aos) + idx * 8, 8, cudaMemcpyDeviceToHost, c->stream));
+    const uint64_t npix = (uint64_t)fb->width * fb->height;
+    if (fb->soa) {
+        SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 4, 16, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaMemcpyAsync(px + 4, fb->aos + 4 * npix + idx, 4, cudaMemcpyDeviceToHost, c->stream));
+    } else if (fb->u8color) SR_CUDA(cudaMemcpyAsync(px8, reinterpret_cast<unsigned char *>(fb->aos) + idx * 8, 8, cudaMemcpyDeviceToHost, c->stream));
     else SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
     uint32_t s = 0;  // (little-endian: the low bytes of `s` receive a u8 / u16 element)
     if (stencil && fb->stencil_buf)
@@ -1517,7 +1551,11 @@ int sr_framebuffer_set_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, const f
     SR_TRY(materialize_clear(fb));
     const uint64_t idx = (uint64_t)x + (uint64_t)y * fb->width;
     uint32_t packed = 0;
-    if (fb->u8color) {
+    if (fb->soa) {
+        const uint64_t npix = (uint64_t)fb->width * fb->height;
+        if (rgba) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 4, rgba, 16, cudaMemcpyHostToDevice, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * npix + idx, depth, 4, cudaMemcpyHostToDevice, c->stream));
+    } else if (fb->u8color) {
         unsigned char *px = reinterpret_cast<unsigned char *>(fb->aos) + idx * 8;
         if (rgba) {
             for (int i = 0; i < 4; ++i) {
@@ -1574,7 +1612,8 @@ int sr_framebuffer_ipc_export(sr_framebuffer *fb, void *handle64) {
 int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width, uint32_t height, uint32_t format,
                             sr_framebuffer **out) {
     if (!c || !handle64 || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format != SR_FB_RGBAF32_DF32 && format != SR_FB_RGBAU8_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "peer framebuffers carry colour+depth only");
+    if (format != SR_FB_RGBAF32_DF32 && format != SR_FB_RGBAU8_DF32 && format != SR_FB_TEXTURE_RGBAF32_DF32)
+        return sr_fail(SR_ERR_UNSUPPORTED, "peer framebuffers carry colour+depth only");
     SR_CUDA(cudaSetDevice(c->device));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
@@ -1586,6 +1625,7 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     fb->aos = reinterpret_cast<float *>(p);
     fb->u8color = format == SR_FB_RGBAU8_DF32;
+    fb->soa = format == SR_FB_TEXTURE_RGBAF32_DF32;
     fb->is_peer = true;
     fb->pending_clear = false;
     ++c->refs;  // owns no buffer of the context, so it holds the reference itself (released by sr_framebuffer_destroy)
@@ -1595,7 +1635,8 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
 
 int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **out) {
     if (!c || !src || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (src->format != SR_FB_RGBAF32_DF32 && src->format != SR_FB_RGBAU8_DF32) return sr_fail(SR_ERR_UNSUPPORTED, "aliased framebuffers carry colour+depth only");
+    if (src->format != SR_FB_RGBAF32_DF32 && src->format != SR_FB_RGBAU8_DF32 && src->format != SR_FB_TEXTURE_RGBAF32_DF32)
+        return sr_fail(SR_ERR_UNSUPPORTED, "aliased framebuffers carry colour+depth only");
     SR_TRY(materialize_clear(src));
     SR_CUDA(cudaSetDevice(src->ctx->device));
     SR_CUDA(cudaStreamSynchronize(src->ctx->stream));
@@ -1611,6 +1652,7 @@ int sr_framebuffer_alias(sr_context *c, sr_framebuffer *src, sr_framebuffer **ou
     fb->ntx = src->ntx; fb->nty = src->nty;
     fb->aos = src->aos;
     fb->u8color = src->u8color;
+    fb->soa = src->soa;
     fb->aos_buf = src->aos_buf;  // shares ownership: the pixels outlive either handle
     fb->pending_clear = false;
     *out = fb;
@@ -2218,7 +2260,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         tp.fs.tex_w = p->fb_texture->width;
         tp.fs.tex_h = p->fb_texture->height;
         tp.fs.tex_kind = SR_TEX_F32;
-        tp.fs.tex_stride = 5;  // AoS pixel: RGBA f32 + depth f32
+        tp.fs.tex_stride = p->fb_texture->soa ? 4 : 5;  // texture buffer: the colour plane itself (TextureBufferRef, texturebuffer.rs:12-47); RenderBuffer: the 20-byte AoS pixel
     } else if (p->texture) {
         tp.fs.tex = p->texture->rgba->as<uint8_t>();
         tp.fs.tex_w = p->texture->width;

@@ -159,6 +159,8 @@ __device__ __forceinline__ uint32_t sr_prim_canonical(const SrPrimSource &s, uin
 // ---- framebuffer view ---------------------------------------------------------------------------
 struct SrFbView {
     float *aos;        // width*height*5 floats {r,g,b,a,depth}; may be a peer (NVLink) address
+    uint32_t soa;      // texture-buffer storage (declare_texture_buffer!, src/framebuffer/texturebuffer.rs:72-110): the colour attachment is
+                       // its own plane of width*height float4 at `aos` (re-usable as a texture without copying), the depths follow it
     uint32_t u8color;  // colour attachment RGBAu8Color (src/color/predefined.rs:26): the AoS pixel is {rgba8, f32 depth} = 8 bytes instead of 20
     uint8_t *stencil;  // or null; elements of stencil_bytes (1, 2 or 4) bytes
     uint32_t stencil_bytes;
@@ -195,8 +197,12 @@ __device__ __forceinline__ void sr_unpack_u8(uint32_t v, float *q) {
     q[0] = (float)(v & 255u); q[1] = (float)((v >> 8) & 255u); q[2] = (float)((v >> 16) & 255u); q[3] = (float)(v >> 24);
 }
 // one pixel of either AoS layout; colours of a u8 target travel as channel values 0..255 in floats
+__device__ __forceinline__ float *sr_fb_depth_plane(const SrFbView &fb) { return fb.aos + 4ull * fb.width * fb.height; }  // (soa)
 __device__ __forceinline__ void sr_fb_store_pixel(const SrFbView &fb, uint64_t index, const float *o /* r,g,b,a,depth */) {
-    if (fb.u8color) {
+    if (fb.soa) {
+        reinterpret_cast<float4 *>(fb.aos)[index] = make_float4(o[0], o[1], o[2], o[3]);
+        sr_fb_depth_plane(fb)[index] = o[4];
+    } else if (fb.u8color) {
         *reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(fb.aos) + index * 8) = make_uint2(sr_pack_u8(o), __float_as_uint(o[4]));
     } else {
         float *dst = fb.aos + index * 5;
@@ -204,7 +210,11 @@ __device__ __forceinline__ void sr_fb_store_pixel(const SrFbView &fb, uint64_t i
     }
 }
 __device__ __forceinline__ void sr_fb_load_pixel(const SrFbView &fb, uint64_t index, float *o) {
-    if (fb.u8color) {
+    if (fb.soa) {
+        const float4 v = reinterpret_cast<const float4 *>(fb.aos)[index];
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        o[4] = sr_fb_depth_plane(fb)[index];
+    } else if (fb.u8color) {
         const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(fb.aos) + index * 8);
         sr_unpack_u8(v.x, o);
         o[4] = __uint_as_float(v.y);
@@ -214,6 +224,7 @@ __device__ __forceinline__ void sr_fb_load_pixel(const SrFbView &fb, uint64_t in
     }
 }
 __device__ __forceinline__ float sr_fb_load_depth(const SrFbView &fb, uint64_t index) {
+    if (fb.soa) return sr_fb_depth_plane(fb)[index];
     return fb.u8color ? reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(fb.aos) + index * 8)[1] : fb.aos[index * 5 + 4];
 }
 

@@ -534,6 +534,15 @@ struct SrTileOwners {
     uint32_t period;
 };
 __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t x0, uint32_t y0) {
+    if (fb.soa) {
+        const float o[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+        const uint32_t cols = min(x0 + SR_TILE_W, fb.width) - x0;
+        for (uint32_t i = threadIdx.x; i < cols * SR_TILE_H; i += 256) {
+            const uint32_t py = y0 + i / cols;
+            if (py < fb.height) sr_fb_store_pixel(fb, (uint64_t)py * fb.width + x0 + i % cols, o);
+        }
+        return;
+    }
     if (fb.u8color) {
         float q[4] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3]};
         sr_quantise_u8(q, false, 0);
@@ -1492,6 +1501,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     float *stage = stage_all + warp * 2 * SR_OPQ_STAGE_FLOATS;
     const bool u8c = p.fb.u8color != 0;  // RGBAu8Color target: 8-byte pixels, colours quantised when they are produced
+    const bool soa = p.fb.soa != 0;      // texture-buffer storage: colour plane + depth plane, two bulk stores per 32-pixel run
     const bool row_aligned = (W % (u8c ? 2u : 4u)) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
     uint32_t nbulk = 0;
     // The winner's vertex indices are fetched one chunk ahead, so the two dependent gathers (indices, then vertices) of
@@ -1639,7 +1649,10 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
             }
-            if (u8c) {
+            if (soa) {  // 32 colours (512 B), then 32 depths (128 B): the same 640 bytes of staging
+                reinterpret_cast<float4 *>(sb)[lane] = make_float4(o[0], o[1], o[2], o[3]);
+                sb[128 + lane] = o[4];
+            } else if (u8c) {
                 reinterpret_cast<uint2 *>(sb)[lane] = make_uint2(sr_pack_u8(o), __float_as_uint(o[4]));
             } else {
 #pragma unroll
@@ -1648,7 +1661,13 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
             sr_fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                sr_bulk_s2g(sr_fb_pixel_addr(p.fb, cx0, py), sb, u8c ? 32 * 8 : 32 * 20);
+                if (soa) {
+                    const uint64_t i0 = (uint64_t)py * W + cx0;
+                    sr_bulk_s2g(reinterpret_cast<float4 *>(p.fb.aos) + i0, sb, 32 * 16);
+                    sr_bulk_s2g(sr_fb_depth_plane(p.fb) + i0, sb + 128, 32 * 4);
+                } else {
+                    sr_bulk_s2g(sr_fb_pixel_addr(p.fb, cx0, py), sb, u8c ? 32 * 8 : 32 * 20);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             ++nbulk;
@@ -2485,6 +2504,23 @@ __global__ void __launch_bounds__(256) k_fb_merge(float *aos, uint64_t n, const 
     if (i >= n) return;
     if (color) { aos[i * 5] = color[i * 4]; aos[i * 5 + 1] = color[i * 4 + 1]; aos[i * 5 + 2] = color[i * 4 + 2]; aos[i * 5 + 3] = color[i * 4 + 3]; }
     if (depth) aos[i * 5 + 4] = depth[i];
+}
+// texture-buffer storage -> the 20-byte AoS pixels sr_framebuffer_download returns, and its presentation read-back
+__global__ void __launch_bounds__(256) k_soa_to_aos(const SrFbView fb, float *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)fb.width * fb.height) return;
+    float o[5];
+    sr_fb_load_pixel(fb, i, o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) out[i * 5 + k] = o[k];
+}
+__global__ void __launch_bounds__(256) k_soa_to_rgba8(const SrFbView fb, uint32_t order, uint32_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)fb.width * fb.height) return;
+    float o[5];
+    sr_fb_load_pixel(fb, i, o);
+    const uint32_t R = sr_as_u8(o[0]), G = sr_as_u8(o[1]), B = sr_as_u8(o[2]), A = sr_as_u8(o[3]);
+    out[i] = order ? (A | (B << 8) | (G << 16) | (R << 24)) : (R | (G << 8) | (B << 16) | (A << 24));
 }
 // the same three for the 8-byte pixels of an RGBAu8Color target (the colour plane is u8 x 4 per pixel, stored as is)
 __global__ void __launch_bounds__(256) k_fb8_to_rgba8(const uint2 *aos, uint64_t n, uint32_t order, uint32_t *out) {

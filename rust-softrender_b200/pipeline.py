@@ -161,7 +161,7 @@ class RenderBuffer:
         self.ctx, self.h, self.width, self.height, self.format = ctx, handle, width, height, fmt
 
     _STENCIL_DTYPE = {FB_RGBAF32_DF32_S8: np.uint8, FB_RGBAF32_DF32_S16: np.uint16, FB_RGBAF32_DF32_S32: np.uint32,
-                      FB_RGBAU8_DF32_S8: np.uint8}
+                      FB_RGBAU8_DF32_S8: np.uint8, FB_TEXTURE_RGBAF32_DF32_S8: np.uint8}
     U8_PIXEL = np.dtype([("rgba", np.uint8, 4), ("depth", np.float32)])  # the 8-byte AoS pixel of an RGBAu8Color target
 
     @property
@@ -169,10 +169,15 @@ class RenderBuffer:
         return self.format in (FB_RGBAU8_DF32, FB_RGBAU8_DF32_S8)
 
     @staticmethod
-    def with_dimensions(ctx: Context, width: int, height: int, stencil=False, u8_color: bool = False) -> "RenderBuffer":
+    def with_dimensions(ctx: Context, width: int, height: int, stencil=False, u8_color: bool = False,
+                        texture_buffer: bool = False) -> "RenderBuffer":
         """stencil: False = stencil type `()`, True / 8 = u8, 16 = u16, 32 = u32 (the Stencil trait, src/stencil.rs:9-60).
-        u8_color: colour attachment RGBAu8Color instead of RGBAf32Color (src/color/predefined.rs:17,26)."""
-        if u8_color:
+        u8_color: colour attachment RGBAu8Color instead of RGBAf32Color (src/color/predefined.rs:17,26).
+        texture_buffer: RGBAf32TextureBuffer storage -- colour and depth in planes of their own, the colour plane re-usable
+        as a texture without copying (src/framebuffer/texturebuffer.rs:63-66,200-210)."""
+        if texture_buffer:
+            fmt = {False: FB_TEXTURE_RGBAF32_DF32, True: FB_TEXTURE_RGBAF32_DF32_S8, 8: FB_TEXTURE_RGBAF32_DF32_S8}[stencil]
+        elif u8_color:
             fmt = {False: FB_RGBAU8_DF32, True: FB_RGBAU8_DF32_S8, 8: FB_RGBAU8_DF32_S8}[stencil]
         else:
             fmt = {False: FB_RGBAF32_DF32, True: FB_RGBAF32_DF32_S8, 8: FB_RGBAF32_DF32_S8, 16: FB_RGBAF32_DF32_S16,

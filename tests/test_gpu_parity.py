@@ -579,6 +579,59 @@ def test_stencil_wider_types(P, ctx, bits, op):
     assert (ofb.stencil != init[2]).any()
 
 
+def test_texture_buffer_storage(P, ctx):
+    """RGBAf32TextureBuffer storage (declare_texture_buffer!, src/framebuffer/texturebuffer.rs:72-210): colour and depth live in
+    planes of their own.  The opaque path (big and small draws, a second draw onto existing contents), the ordered path
+    (alpha_over + stencil) and the accessors must give exactly what the AoS RenderBuffer gives, i.e. the oracle's frame; the
+    colour plane is then bound IN PLACE as the texture of a second pass (TextureBufferRef, texturebuffer.rs:12-47)."""
+    rng = np.random.default_rng(909)
+    w, h = 328, 200
+    u = scenes.suzanne_uniforms(w, h)
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h, stencil=True, texture_buffer=True)
+    fb.enable_winner(True)
+    fb.clear(H.CLEAR)
+    ofb = oracle_fb(w, h, True)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    draws = [(70_000, 3.0, sr.BLEND_REPLACE, (0, 0)), (500, 40.0, sr.BLEND_REPLACE, (0, 0)),
+             (300, 40.0, sr.BLEND_ALPHA_OVER, (sr.STENCIL_LESS_THAN_EQ, sr.STENCIL_INCREMENT_WRAP))]
+    for n, size, blend, st in draws:
+        verts = H.random_screen_triangles(rng, n, w, h, max_size=size)
+        idx = np.arange(3 * n, dtype=np.uint32)
+        od = ob.OracleDraw(sr.TRIANGLE, idx, 2)
+        od.set_vertices(verts, 1)
+        od.blend = blend
+        od.fragment_run(ofb, sr.FS_FLAT, u, *st)
+        pipe.set_stencil_config(*st)
+        pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1, stencil=2).with_blend(blend).run(sr.FS_FLAT)
+        assert np.array_equal(fb.download_winner(), ofb.winner)
+        H.compare_framebuffers(fb.download(), ofb, exact_color=True, what=f"texture buffer, {n} triangles")  # the PixelRead view (AoS records)
+        col, dep, st_plane = fb.download_planes(stencil=True)                                                # the planes themselves
+        H.assert_bits_equal(col, ofb.color, "colour plane")
+        H.assert_bits_equal(dep, ofb.depth, "depth plane")
+        assert np.array_equal(st_plane, ofb.stencil)
+    fb.set_pixel(7, 9, rgba=(0.5, 0.25, 0.125, 1.0), depth=-0.75)
+    assert fb.pixel(7, 9)[:2] == ((0.5, 0.25, 0.125, 1.0), -0.75)
+    assert np.array_equal(fb.download_rgba8().reshape(-1, 4)[9 * w + 7], [127, 63, 31, 255])
+    # second pass: the colour plane sampled in place by a full-screen pass into an ordinary RenderBuffer
+    src_color = fb.download_planes()[0].reshape(h, w, 4)
+    fb2 = make_fb(P, ctx, w, h)
+    p2 = P.Pipeline.from_framebuffer(fb2, u)
+    p2.bind_framebuffer_texture(fb)
+    p2.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_WRAP)
+    quad = np.array([[-1, -1, 0, 1, -0.3, 1.2], [1, -1, 0, 1, 1.4, 1.2], [1, 1, 0, 1, 1.4, -0.1], [-1, 1, 0, 1, -0.3, -0.1]], np.float32)
+    qi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    vp = scenes.Viewport.new(w, h, 0.1, 10.0)
+    qm = P.Mesh(ctx, vertices=quad, indices=qi)
+    p2.render_mesh(sr.TRIANGLE, qm).run_to_fragment(vp, sr.VS_PASSTHROUGH).run(sr.FS_TEXTURE_UNLIT)
+    ofb2 = oracle_fb(w, h)
+    od2 = ob.OracleDraw(sr.TRIANGLE, qi)
+    od2.vertex_run_to_fragment(vp, sr.VS_PASSTHROUGH, u, quad)
+    od2.fragment_run(ofb2, sr.FS_TEXTURE_UNLIT, u, texture=src_color, sampler=(sr.FILTER_BILINEAR, sr.EDGE_WRAP, None))
+    H.compare_framebuffers(fb2.download(), ofb2, exact_color=True, what="second pass over the texture buffer's colour plane")
+    for x in (p2, qm, fb2, pipe, fb):
+        x.destroy()
+
+
 def test_user_blend_function_additive(P, ctx):
     """A third registered blend, the stand-in for a user's GenericBlend::new(|a, b| a + b) (src/color/blend.rs:57-76; recipe in
     INTEGRATION.md): strictly ordered path, triangles + antialiased lines + points, colours bit-exact (f32 addition is not
