@@ -318,6 +318,47 @@ def other_configs(ctx):
         x.destroy()
     for x in (pipe, gm, tex, fb):
         x.destroy()
+
+    # config 5: the 64-frame Suzanne turntable at 1024x1024 on this GPU (clip path), device resident, one stream
+    size = 1024
+    mesh = H.suzanne_mesh()
+    fb = P.RenderBuffer.with_dimensions(ctx, size, size)
+    gm = P.Mesh(ctx, mesh)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    tt_uniforms = [scenes.suzanne_uniforms(size, size, rotation_y=np.deg2rad(3.0 * (k + 1))) for k in range(64)]
+    pipe = P.Pipeline.from_framebuffer(fb, tt_uniforms[0])
+
+    def turntable():
+        for uu in tt_uniforms:
+            pipe.set_uniforms(uu)
+            fb.clear(CLEAR)
+            pipe.render_mesh(sr.TRIANGLE, gm).run(sr.VS_SUZANNE).clip_primitives().finish(vp).run(sr.FS_SUZANNE)
+
+    out["config5_turntable_64_frames_fps_one_stream"] = 64e6 / per_frame_us(turntable, 3)
+    out["config5_note"] = "bench.py --config turntable measures the same batch with four frames in flight, with read-back, and across GPUs"
+    for x in (pipe, gm, fb):
+        x.destroy()
+
+    # config 4 on ONE GPU (the yardstick of the tile-sharded runs at N > 1): 100 M sub-pixel triangles at 7680x4320
+    try:
+        w4, h4, mesh4, u4, vp4 = build_scene("grid100m")
+        fb = P.RenderBuffer.with_dimensions(ctx, w4, h4)
+        pipe = P.Pipeline.from_framebuffer(fb, u4)
+        gm = P.Mesh(ctx, mesh4)
+
+        def grid100m():
+            fb.clear(CLEAR)
+            pipe.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp4, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+
+        us = per_frame_us(grid100m, 10)
+        out["config4_grid100m_8k_ms_per_frame"] = us / 1e3
+        out["config4_grid100m_8k_Mtris_per_s"] = mesh4.ntris / us
+        b4 = algorithmic_bytes(len(mesh4.vertices), mesh4.ntris, w4, h4)
+        out["config4_roofline_frac"] = b4 / (us * 1e-6) / 1e9 / measured_peak_gbs()[0]
+        for x in (pipe, gm, fb):
+            x.destroy()
+    except Exception as e:
+        out["config4_error"] = f"{type(e).__name__}: {e}"[:200]
     return out
 
 

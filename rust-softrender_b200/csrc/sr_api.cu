@@ -676,6 +676,11 @@ static bool ranged_eligible(const sr_context *c, const sr_framebuffer *fb, const
 static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParams &tp, uint32_t cull, uint32_t fs, uint32_t owned,
                             const std::vector<Buf> &keep, bool extra, sr_draw *d = nullptr) {
     const uint32_t ntiles = fb->ntx * fb->nty;
+    // a recorded clear also resets the stencil attachment (renderbuffer/mod.rs:126-133: stencil = Default::default()); the opaque path
+    // never touches the stencil plane (stencil Always / Keep), so the reset is made here -- found by compute-sanitizer's memcheck run, whose
+    // allocations are not zero-filled
+    if (fb->pending_clear && fb->stencil_buf)
+        SR_CUDA(cudaMemsetAsync(fb->stencil_buf->ptr, 0, (size_t)fb->width * fb->height * fb->stencil_bytes, c->stream));
     if (ranged_eligible(c, fb, tp, extra)) return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep, d);
     if (d) SR_TRY(materialize_vertices(d));
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
@@ -919,7 +924,12 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
                 sh->rank, lane, n - 1, t[0], t[1], t[2], t[3], t[4]);
     }
     unsigned long long *vis = sh->vis(sh->block, lane);
-    const unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+    // a wait gives up after 10 s (a peer died); SR_SHARD_TIMEOUT_MS shortens it for tools that serialise kernels (compute-sanitizer),
+    // under which the ranks of a single-process group can never overlap and every wait runs into its timeout
+    static const unsigned long long timeout_ns = [] {
+        const char *e = getenv("SR_SHARD_TIMEOUT_MS");
+        return (e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 10000ull) * 1000ull * 1000ull;
+    }();
     SrShardPeers ready_peers, done_peers;
     memset(&ready_peers, 0, sizeof(ready_peers));
     memset(&done_peers, 0, sizeof(done_peers));

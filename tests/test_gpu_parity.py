@@ -650,6 +650,28 @@ def test_user_blend_function_additive(P, ctx):
     assert [r["name"] for r in P.registry(3)] == ["replace", "alpha_over", "additive"]
 
 
+def test_clear_resets_the_stencil_plane_on_the_opaque_path(P, ctx):
+    """RenderBuffer::clear resets stencil to its default (renderbuffer/mod.rs:126-133).  The clear is recorded and produced on
+    chip by the next draw; when that draw takes the opaque path (stencil Always / Keep never touches the plane) the stencil
+    values of the previous frame must still be gone."""
+    rng = np.random.default_rng(17)
+    w, h, n = 120, 90, 150
+    verts = H.random_screen_triangles(rng, n, w, h)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    u = scenes.suzanne_uniforms(w, h)
+    fb = make_fb(P, ctx, w, h, stencil=True)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    pipe.set_stencil_config(sr.STENCIL_ALWAYS, sr.STENCIL_INCREMENT_WRAP)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_FLAT)
+    assert fb.download_planes(stencil=True)[2].max() > 0
+    fb.clear(H.CLEAR)
+    pipe.set_stencil_config(sr.STENCIL_ALWAYS, sr.STENCIL_KEEP)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_FLAT)  # opaque path, lazy clear
+    assert fb.download_planes(stencil=True)[2].max() == 0
+    pipe.destroy()
+    fb.destroy()
+
+
 def test_pixel_write_accessors(P, ctx):
     """PixelWrite::pixel_mut / FramebufferAccessorMut::{set_depth, set_stencil} (src/pixels/mod.rs:77-98,
     src/framebuffer/accessor.rs:52-70) through sr_framebuffer_set_pixel: a depth written by hand is what the next draw's

@@ -4,6 +4,8 @@ memory exactly as ranks on different GPUs do over NVLink (the kernels, the progr
 code; only the pointers come from sr_shard_connect_local instead of CUDA IPC).  The composited frame must be
 bit-identical to the single-context frame, which the other parity tests compare with the oracle
 (the reference's tile-parallel loop: src/pipeline/stages/fragment.rs:240-253)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,6 +16,10 @@ import helpers as H
 import oracle_binding as ob
 
 pytestmark = pytest.mark.gpu
+# compute-sanitizer serialises kernels: the ranks of a single-process group cannot overlap, every cross-rank wait times out
+# (SR_SHARD_TIMEOUT_MS keeps that short) and the frames are incomplete.  The run is then only a memory / race check of the
+# kernels; the result assertions are skipped.
+SERIALISED = bool(os.environ.get("SR_UNDER_SANITIZER"))
 
 
 @pytest.fixture(scope="module")
@@ -84,10 +90,11 @@ def test_range_sharded_frame_is_bit_identical(P, ctx, world, lanes):
         for r in range(world):
             for c in ctxs[r]:
                 c.synchronize()
-        assert [g.status() for g in groups] == [0] * world, "a rank gave up waiting for a peer"
         assert ctxs[1][0].launch_count() > before
-        for lane in range(lanes):
-            H.assert_bits_equal(targets[lane].download(), expect, f"range-sharded frame, world {world}, lane {lane}")
+        if not SERIALISED:
+            assert [g.status() for g in groups] == [0] * world, "a rank gave up waiting for a peer"
+            for lane in range(lanes):
+                H.assert_bits_equal(targets[lane].download(), expect, f"range-sharded frame, world {world}, lane {lane}")
     finally:
         for r in range(world):
             for c in ctxs[r]:
@@ -156,8 +163,9 @@ def test_range_sharded_mesh_with_lazy_vertex_stage(P, ctx, world, fused, monkeyp
             last = dup
     for c in ctxs:
         c.synchronize()
-    assert [g.status() for g in groups] == [0] * world
-    H.assert_bits_equal(target.download(), expect, f"range-sharded mesh frame, world {world}")
+    if not SERIALISED:
+        assert [g.status() for g in groups] == [0] * world
+        H.assert_bits_equal(target.download(), expect, f"range-sharded mesh frame, world {world}")
     # the duplicate of the last rank's draw (lazy vertex stage, partly shaded by its frame) yields the whole mesh on demand
     H.assert_bits_equal(last.download(0), verts_expect, "vertices after a lazy vertex stage")
     for c in ctxs:
