@@ -840,8 +840,8 @@ static int launch_vertex(sr_context *c, sr_draw *d, uint32_t vs, const SrVsConst
     mv.nverts = d->mesh_nverts;
     mv.vin = d->vin;
     float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
-    if (span.mask != nullptr) {  // one warp per 1024 vertices
-        const uint32_t grid = ceil_div(ceil_div(span.end - span.begin, 1024), 8);
+    if (span.mask != nullptr) {  // one warp per 128 vertices
+        const uint32_t grid = ceil_div(ceil_div(span.end - span.begin, 128), 8);
         if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex_marked<SR_VS_SUZANNE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
         else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex_marked<SR_VS_FULL_EXAMPLE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
         else return sr_fail(SR_ERR_INVALID_ARGUMENT, "vertex shader %u", vs);
@@ -905,8 +905,9 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
         record(c, 2);
         record(c, 3);
         record(c, 4);
-        SR_TRY(c->alloc(((size_t)d->mesh_nverts + 31) / 32 * 4 + 4, &mark));
-        SR_CUDA(cudaMemsetAsync(mark->ptr, 0, ((size_t)d->mesh_nverts + 31) / 32 * 4 + 4, c->stream));
+        const size_t mark_bytes = ((size_t)d->mesh_nverts + 127) / 128 * 16 + 16;  // one bit per vertex, whole 16-byte groups
+        SR_TRY(c->alloc(mark_bytes, &mark));
+        SR_CUDA(cudaMemsetAsync(mark->ptr, 0, mark_bytes, c->stream));
         // (the draw stays "lazy": only part of its vertices is shaded, any other consumer shades the whole mesh first)
     }
     const uint32_t n = ++sh->frame[lane];

@@ -556,6 +556,16 @@ __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t 
     }
     const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
     const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    if ((fb.width & 3u) == 0 && (run & 3u) == 0 && (reinterpret_cast<uintptr_t>(fb.aos) & 15u) == 0) {
+        // 16-byte stores: the 20-byte pixel pattern repeats every five float4 (x0 is a multiple of 64 pixels = 1280 bytes)
+        const uint32_t run4 = run / 4, rows = min(SR_TILE_H, fb.height - y0);
+        for (uint32_t i = threadIdx.x; i < run4 * rows; i += 256) {
+            const uint32_t r = i / run4, q = i % run4, k = (q % 5u) * 4u;
+            float4 *row = reinterpret_cast<float4 *>(fb.aos + ((uint64_t)(y0 + r) * fb.width + x0) * 5);
+            row[q] = make_float4(pat[k % 5u], pat[(k + 1u) % 5u], pat[(k + 2u) % 5u], pat[(k + 3u) % 5u]);
+        }
+        return;
+    }
     for (uint32_t r = 0; r < SR_TILE_H && y0 + r < fb.height; ++r) {
         float *row = fb.aos + ((uint64_t)(y0 + r) * fb.width + x0) * 5;
         for (uint32_t i = threadIdx.x; i < run; i += 256) row[i] = pat[i % 5];
