@@ -840,8 +840,8 @@ static int launch_vertex(sr_context *c, sr_draw *d, uint32_t vs, const SrVsConst
     mv.nverts = d->mesh_nverts;
     mv.vin = d->vin;
     float4 *pos = d->indexed.pos->as<float4>(), *attr = d->indexed.attr->as<float4>();
-    if (span.mask != nullptr) {  // one warp per 128 vertices
-        const uint32_t grid = ceil_div(ceil_div(span.end - span.begin, 128), 8);
+    if (span.mask != nullptr) {  // one warp per 1024 vertices
+        const uint32_t grid = ceil_div(ceil_div(span.end - span.begin, 1024), 8);
         if (vs == SR_VS_SUZANNE) SR_LAUNCH(c, k_vertex_marked<SR_VS_SUZANNE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
         else if (vs == SR_VS_FULL_EXAMPLE) SR_LAUNCH(c, k_vertex_marked<SR_VS_FULL_EXAMPLE>, grid, 256, 0, vc, mv, pos, attr, d->indexed.np, span);
         else return sr_fail(SR_ERR_INVALID_ARGUMENT, "vertex shader %u", vs);

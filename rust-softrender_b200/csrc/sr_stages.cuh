@@ -157,23 +157,26 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsCons
     if (v >= span.end) return;
     sr_vertex_one<VS>(c, m, pos, attr, onp, v);
 }
-// The marked vertices of [span.begin, span.end) outside [skip_lo, skip_hi): a warp takes 128 consecutive vertices = four mask words
-// (each read once, broadcast) and walks only the non-zero ones, 32 consecutive vertices per step, one per lane.  (A first version
-// gave a warp 1024 vertices: 13 % of the warp slots active on config 3 -- profiles/r2a_shard_kernels_summary.txt -- the marks
-// cluster where the rank's tiles are, so few warps carried all the work.)
+// The marked vertices of [span.begin, span.end) outside [skip_lo, skip_hi): a warp takes 1024 consecutive vertices, reads their
+// 32 mask words with one coalesced load and walks only the non-zero words (32 consecutive vertices each, one per lane) -- a
+// sparse mask costs one 128-byte load per 1024 vertices instead of a thread per vertex.  (One warp per 128 vertices was measured
+// too: better balanced where the marks are dense, but the scan of an empty mask went from 0.010 to 0.050 ms on config 4's
+// 50 M vertices and the dense rank did not gain, 0.127 -> 0.154 ms: kept coarse.)
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex_marked(const __grid_constant__ SrVsConst c, const SrMeshView m, float4 *pos,
                                                        float4 *attr, const uint64_t onp, const SrVertexSpan span) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t base = span.begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 128;  // span.begin is a multiple of 32
+    const uint64_t base = span.begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 1024;  // span.begin is a multiple of 32
     if (base >= span.end) return;
-    const uint4 words = *reinterpret_cast<const uint4 *>(span.mask + (base >> 5));  // (the mask is padded to whole 16-byte groups)
-    const uint32_t w[4] = {words.x, words.y, words.z, words.w};
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        if (w[j] == 0u) continue;
+    const uint64_t wi = (base >> 5) + lane;
+    uint32_t word = wi * 32 < span.end ? span.mask[wi] : 0u;
+    if (__ballot_sync(0xffffffffu, word != 0u) == 0u) return;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t wj = __shfl_sync(0xffffffffu, word, j);
+        if (wj == 0u) continue;
         const uint64_t v = base + j * 32 + lane;
-        if (((w[j] >> lane) & 1u) == 0u || v >= span.end || (v >= span.skip_lo && v < span.skip_hi)) continue;
+        if (((wj >> lane) & 1u) == 0u || v >= span.end || (v >= span.skip_lo && v < span.skip_hi)) continue;
         sr_vertex_one<VS>(c, m, pos, attr, onp, v);
     }
 }
