@@ -49,6 +49,10 @@ struct DevBuf {
     size_t bytes = 0;
     // an index buffer remembers the vertex range its triangles [t0, t1) reference (range-sharded frames; computed once)
     uint32_t vr_t0 = 0, vr_t1 = 0, vr_lo = 0, vr_hi = 0;
+    // ... and, for the chunk-culled front end: the vertex range of every 1024-triangle chunk, the object-space box of every 256-vertex
+    // block of the mesh it indexes (static per mesh, computed once), and whether the mesh is coherent enough for that mode
+    std::shared_ptr<DevBuf> chunk_vr, blk_aabb;
+    const void *aabb_planes = nullptr;
     ~DevBuf();
     template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
 };
@@ -203,6 +207,7 @@ struct sr_shard {
     bool peer_ipc[SR_SHARD_MAX_WORLD] = {};
     bool connected = false;
     uint32_t frame[8] = {};  // frames issued per lane
+    int last_by_rows[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // ownership function of the lane's previous frame (a change clears every key)
     SrTileOwners owners;     // tile -> rank of the range-sharded frames (identical on every rank)
     uint32_t owned_cap = 0;  // upper bound of the tiles this rank owns per period (diagnostics)
     uint32_t merge_ctas = 0; // resident merge CTAs per SM (0: the kernel's natural 4); fewer leave room for the next frame's front end
@@ -857,7 +862,7 @@ static int launch_vertex(sr_context *c, sr_draw *d, uint32_t vs, const SrVsConst
 static int materialize_vertices(sr_draw *d) {
     if (!d->vertex_lazy) return SR_OK;
     d->vertex_lazy = false;
-    const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0};
+    const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0, nullptr};
     return launch_vertex(d->pipeline->ctx, d, d->lazy_vs, d->lazy_vc, whole);
 }
 // The opaque triangle path of a range-sharded frame (include/softrender_b200.h).  Per frame n of a lane:
@@ -881,8 +886,9 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     const uint32_t lane = c->shard_lane, ntiles = fb->ntx * fb->nty;
     const uint32_t t0 = (uint32_t)((uint64_t)tp.ntris * sh->rank / sh->world), t1 = (uint32_t)((uint64_t)tp.ntris * (sh->rank + 1) / sh->world);
     const bool lazy = d && d->vertex_lazy;
-    uint32_t vlo = 0, vhi = 0;
-    Buf mark;
+    uint32_t vlo = 0, vhi = 0, nchunk = 0;
+    bool chunked = false;
+    Buf mark, chunk_list, blocks;
     if (lazy) {
         DevBuf *ib = d->indices.get();
         if (!(ib->vr_t1 > ib->vr_t0 && ib->vr_t0 == t0 && ib->vr_t1 == t1)) {  // once per mesh and (rank, world)
@@ -899,8 +905,47 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
         }
         vlo = ib->vr_lo; vhi = ib->vr_hi;
         record(c, 0);
-        const SrVertexSpan own = {vlo, vhi, nullptr, 0, 0};
-        SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, own));                                                        // a
+        // ---- chunk-culled front end: which 1024-triangle chunks can reach MY tile rows (row y belongs to rank y % world)? ----
+        // Opt-in (SR_SHARD_CHUNKS=1): measured on configs 3 / 4 it LOSES to plain triangle ranges (N = 2, config 4: 2.63 against 1.94 ms) --
+        // those index buffers run in long strips along wavy grid rows, so a chunk reaches 3-4 tile rows, nearly every rank keeps nearly
+        // every chunk and the vertex blocks of a kept chunk cover whole grid rows.  It needs index buffers whose chunks are compact on
+        // screen; kept because it is exact and tested (tests/test_gpu_range_shard.py), not because it is the default.
+        const bool no_chunks = getenv("SR_SHARD_CHUNKS") == nullptr;
+        nchunk = ceil_div(tp.ntris, SR_CHUNK_TRIS);
+        const uint32_t nblk = ceil_div(d->mesh_nverts, SR_VERTEX_BLOCK);
+        if (!no_chunks && fb->nty >= sh->world) {
+            if (!ib->chunk_vr || !ib->blk_aabb || ib->aabb_planes != d->mesh_planes->ptr) {  // static per mesh
+                SR_TRY(c->alloc((size_t)nchunk * 8, &ib->chunk_vr));
+                SR_TRY(c->alloc((size_t)nblk * 24, &ib->blk_aabb));
+                SR_LAUNCH(c, k_chunk_vrange, nchunk, 256, 0, d->indices->as<uint32_t>(), tp.ntris, (uint32_t)SR_CHUNK_TRIS, ib->chunk_vr->as<uint2>());
+                SR_LAUNCH(c, k_block_aabb, nblk, SR_VERTEX_BLOCK, 0, d->mesh_planes->as<float>(), d->mesh_pstride, d->mesh_nverts, ib->blk_aabb->as<float>());
+                ib->aabb_planes = d->mesh_planes->ptr;
+            }
+            Buf rows, flag, pos;
+            SR_TRY(c->alloc((size_t)nblk * 4, &rows));
+            SR_TRY(c->alloc((size_t)nchunk * 4, &flag));
+            SR_TRY(c->alloc((size_t)nchunk * 4, &pos));
+            SR_TRY(c->alloc((size_t)nchunk * 4 + 4, &chunk_list));
+            SR_TRY(c->alloc((size_t)nblk + 16, &blocks));
+            SR_CUDA(cudaMemsetAsync(blocks->ptr, 0, (size_t)nblk + 16, c->stream));
+            SR_LAUNCH(c, k_block_rows, ceil_div(nblk, 256), 256, 0, ib->blk_aabb->as<float>(), nblk, d->lazy_vc, fb->height, fb->nty, (uint32_t)SR_TILE_H,
+                      rows->as<uint32_t>());
+            SR_LAUNCH(c, k_chunk_select, ceil_div(nchunk, 256), 256, 0, ib->chunk_vr->as<uint2>(), rows->as<uint32_t>(), nchunk, sh->rank, sh->world,
+                      flag->as<uint32_t>(), blocks->as<uint8_t>());
+            SR_TRY(exclusive_scan_async(c, flag->as<uint32_t>(), nchunk, pos->as<uint32_t>(), 4));
+            SR_LAUNCH(c, k_chunk_compact, ceil_div(nchunk, 256), 256, 0, flag->as<uint32_t>(), pos->as<uint32_t>(), nchunk, chunk_list->as<uint32_t>(),
+                      chunk_list->as<uint32_t>() + nchunk);
+            chunked = true;
+        }
+        if (chunked) {
+            const SrVertexSpan mine = {0, d->mesh_nverts, nullptr, 0, 0, blocks->as<uint8_t>()};
+            SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, mine));                                                   // a (chunks)
+            vlo = vhi = 0;
+        } else {
+            blocks.reset();
+            const SrVertexSpan own = {vlo, vhi, nullptr, 0, 0, nullptr};
+            SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, own));                                                    // a (range)
+        }
         record(c, 1);
         record(c, 2);
         record(c, 3);
@@ -939,8 +984,13 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
             ready_peers.word[p] = sh->ready(sh->peer[p], lane);
             done_peers.word[p] = sh->done(sh->peer[p], lane);
         }
+    SrTileOwners owners = sh->owners;
+    owners.by_rows = chunked ? 1u : 0u;  // the resolve follows the front end: a rank resolves the rows it rasterised (hardly any key crosses NVLink)
+    owners.ntx = fb->ntx; owners.world = sh->world;
+    const bool owners_changed = sh->last_by_rows[lane] != (int)owners.by_rows;  // (tiles reset under the other function may be dirty)
+    sh->last_by_rows[lane] = (int)owners.by_rows;
     if (n > 1) SR_LAUNCH(c, k_shard_wait, 1, 32, 0, sh->done(sh->block, lane), sh->world, sh->rank, n - 1, timeout_ns, sh->error());   // b
-    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->view(), sh->owners, sh->rank, n == 1 ? 1u : 0u, 0u);                     // c
+    SR_LAUNCH(c, k_vis_clear_foreign, ntiles, 256, 0, vis, fb->view(), owners, sh->rank, (n == 1 || owners_changed) ? 1u : 0u, 0u);     // c
     if (sh->rank == 0) {  // the framebuffer pre-fill is pure HBM writes, k_micro is latency bound: they share the GPU well
         if (!c->aux) {
             SR_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
@@ -949,7 +999,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
         }
         SR_CUDA(cudaEventRecord(c->ev_aux[0], c->stream));
         SR_CUDA(cudaStreamWaitEvent(c->aux, c->ev_aux[0], 0));
-        k_fb_fill_foreign<<<ntiles, 256, 0, c->aux>>>(fb->view(), sh->owners, sh->rank);
+        k_fb_fill_foreign<<<ntiles, 256, 0, c->aux>>>(fb->view(), owners, sh->rank);
         c->launches++;
         SR_CUDA(cudaGetLastError());
         SR_CUDA(cudaEventRecord(c->ev_aux[1], c->aux));
@@ -959,8 +1009,9 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &count));
     SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &off));
     SR_TRY(c->alloc(4, &lcount));
-    SR_TRY(c->alloc((size_t)std::max(t1 - t0, 1u) * 4, &lids));
-    SR_TRY(c->alloc((size_t)std::max(t1 - t0, 1u) * 4, &lrects));
+    const uint32_t lcap = chunked ? tp.ntris : std::max(t1 - t0, 1u);  // (chunks: the rank's triangle count is only known on the device)
+    SR_TRY(c->alloc((size_t)lcap * 4, &lids));
+    SR_TRY(c->alloc((size_t)lcap * 4, &lrects));
     SR_CUDA(cudaMemsetAsync(count->ptr, 0, (size_t)(ntiles + 1) * 4, c->stream));
     SR_CUDA(cudaMemsetAsync(lcount->ptr, 0, 4, c->stream));
     auto q = std::make_unique<PendingOpaque>();
@@ -978,7 +1029,13 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     mp.large_ids = lids->as<uint32_t>();
     mp.large_rects = lrects->as<uint32_t>();
     mp.tile_count = count->as<uint32_t>();
-    if (t1 > t0) {                                                                                                       // d
+    if (chunked) {                                                                                                       // d (chunks)
+        mp.tri_begin = 0; mp.tri_end = tp.ntris;
+        const uint32_t grid = nchunk * (SR_CHUNK_TRIS / SR_MICRO_THREADS);
+        const uint32_t *list = chunk_list->as<uint32_t>();
+        if (c->micro_precheck & 2u) SR_LAUNCH(c, (k_micro_chunks<false, false>), grid, SR_MICRO_THREADS, 0, mp, list, list + nchunk);
+        else SR_LAUNCH(c, (k_micro_chunks<false, true>), grid, SR_MICRO_THREADS, 0, mp, list, list + nchunk);
+    } else if (t1 > t0) {                                                                                                // d (range)
         const uint32_t grid = ceil_div(t1 - t0, SR_MICRO_THREADS);
         if (c->micro_precheck & 2u) SR_LAUNCH(c, (k_micro<false, false>), grid, SR_MICRO_THREADS, 0, mp);
         else SR_LAUNCH(c, (k_micro<false, true>), grid, SR_MICRO_THREADS, 0, mp);
@@ -999,6 +1056,8 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     q->keep = keep;
     q->keep.push_back(c->list_arena);
     if (mark) q->keep.push_back(mark);
+    if (chunk_list) q->keep.push_back(chunk_list);
+    if (blocks) q->keep.push_back(blocks);
     q->fb = fb;
     SrOpaqueParams &op = q->op;
     memset(&op, 0, sizeof(op));
@@ -1013,10 +1072,10 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     op.fs = tp.fs;
     op.shard_rank = 0; op.shard_world = 1;  // (d, continued) the large triangles of my range, every tile
     op.reset_vis = 0;
-    SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(std::max(t1 - t0, 1u), 8), 148u * 4u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
+    SR_LAUNCH(c, k_large_fill, std::min<uint32_t>(ceil_div(lcap, 8), 148u * 4u), 256, 0, lcount->as<uint32_t>(), lids->as<uint32_t>(),
               lrects->as<uint32_t>(), fb->ntx, ntiles, 0u, 1u, off->as<uint32_t>(), count->as<uint32_t>(), c->list_arena->as<uint32_t>(), c->list_cap);
     SR_TRY(launch_opaque_sweep(c, ntiles, op));
-    SR_LAUNCH(c, k_vis_rows_touched, ntiles, 256, 0, vis, fb->ntx, sh->owners, sh->rank, sh->touched(sh->block, lane));
+    SR_LAUNCH(c, k_vis_rows_touched, ntiles, 256, 0, vis, fb->ntx, owners, sh->rank, sh->touched(sh->block, lane));
     if (sh->rank == 0) SR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_aux[1], 0));  // the pre-fill is in place before "ready" goes out
     SR_LAUNCH(c, k_shard_signal, 1, 32, 0, ready_peers, sh->rank, n);                                                    // e
     stamp(0);
@@ -1024,7 +1083,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
     stamp(1);
     op.shard_rank = sh->rank; op.shard_world = sh->world;
     op.reset_vis = 1;
-    op.owners = sh->owners;
+    op.owners = owners;
     op.elide_clear = sh->rank != 0 ? 1u : 0u;
     const bool fused = sh->fused_merge && !lazy;  // (the winners' vertices must be known before the resolve when they are shaded on demand)
     if (fused) {
@@ -1040,7 +1099,8 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
                 mg.peer_vis[mg.npeers++] = sh->vis(sh->peer[p], lane);
             }
         mg.ntx = fb->ntx; mg.rank = sh->rank;
-        mg.owners = sh->owners;
+        mg.owners = owners;
+        mg.shaded_blocks = chunked ? blocks->as<uint8_t>() : nullptr;
         mg.indices = tp.tris.indices;
         mg.ntris = tp.tris.n0;
         mg.mark = lazy ? mark->as<uint32_t>() : nullptr;
@@ -1048,7 +1108,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
         SR_LAUNCH(c, k_shard_merge, ntiles, 256, 0, mg);
         stamp(2);
         if (lazy) {
-            const SrVertexSpan winners = {0, d->mesh_nverts, mark->as<uint32_t>(), vlo, vhi};
+            const SrVertexSpan winners = {0, d->mesh_nverts, mark->as<uint32_t>(), vlo, vhi, chunked ? blocks->as<uint8_t>() : nullptr};
             SR_TRY(launch_vertex(c, d, d->lazy_vs, d->lazy_vc, winners));
         }
     }
@@ -1114,6 +1174,13 @@ static void preload_ranged_kernels() {
     preload(k_shard_signal);
     preload(k_vis_clear_foreign);
     preload(k_shard_merge);
+    preload(k_micro_chunks<false, true>);
+    preload(k_micro_chunks<false, false>);
+    preload(k_chunk_vrange);
+    preload(k_block_aabb);
+    preload(k_block_rows);
+    preload(k_chunk_select);
+    preload(k_chunk_compact);
     preload(k_vis_rows_touched);
     preload(k_fb_fill_foreign);
     preload(k_vertex_marked<SR_VS_SUZANNE>);
@@ -2002,7 +2069,7 @@ static int vertex_stage(sr_draw *d, const sr_viewport *vp, uint32_t vs) {
             SR_LAUNCH(c, k_vertex_passthrough, ceil_div(d->mesh_nverts, 128), 128, 0, vc, mv, d->indexed.pos->as<float4>(),
                       d->indexed.attr->as<float4>(), d->indexed.np);
         } else {
-            const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0};
+            const SrVertexSpan whole = {0, d->mesh_nverts, nullptr, 0, 0, nullptr};
             SR_TRY(launch_vertex(c, d, vs, vc, whole));
         }
     }

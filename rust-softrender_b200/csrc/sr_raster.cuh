@@ -532,7 +532,11 @@ __global__ void __launch_bounds__(256) k_vis_init(unsigned long long *vis, const
 struct SrTileOwners {
     uint8_t owner[SR_OWNER_PERIOD_MAX];
     uint32_t period;
+    uint32_t by_rows, ntx, world;  // by_rows: tile ROW y belongs to rank y % world (frames whose front end is culled by screen rows, below)
 };
+__device__ __forceinline__ uint32_t sr_tile_owner(const SrTileOwners &o, uint32_t tile) {
+    return o.by_rows ? (tile / o.ntx) % o.world : (uint32_t)o.owner[tile % o.period];
+}
 __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t x0, uint32_t y0) {
     if (fb.soa) {
         const float o[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
@@ -576,7 +580,7 @@ __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t 
 __global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *vis, const SrFbView fb, const SrTileOwners own, uint32_t rank,
                                                            uint32_t all, uint32_t fill) {
     const uint32_t tile = blockIdx.x;
-    const bool mine = own.owner[tile % own.period] == rank;
+    const bool mine = sr_tile_owner(own, tile) == rank;
     if (!all && mine) return;
     const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
     for (uint32_t i = threadIdx.x * 2; i < SR_TILE_PIXELS; i += 512)
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(256) k_vis_clear_foreign(unsigned long long *v
 // the framebuffer half of the above on its own (rank 0 runs it on a second stream, beside its k_micro)
 __global__ void __launch_bounds__(256) k_fb_fill_foreign(const SrFbView fb, const SrTileOwners own, uint32_t rank) {
     const uint32_t tile = blockIdx.x;
-    if (own.owner[tile % own.period] == rank) return;
+    if (sr_tile_owner(own, tile) == rank) return;
     const uint32_t x0 = (tile % fb.ntx) * SR_TILE_W, y0 = (tile / fb.ntx) * SR_TILE_H;
     if (x0 < fb.width) sr_fill_tile_clear(fb, x0, y0);
 }
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(256) k_fb_fill_foreign(const SrFbView fb, cons
 __global__ void __launch_bounds__(256) k_vis_rows_touched(const unsigned long long *vis, uint32_t ntx, const SrTileOwners own, uint32_t rank,
                                                           uint32_t *touched) {
     const uint32_t tile = blockIdx.x;
-    if (own.owner[tile % own.period] == rank) return;
+    if (sr_tile_owner(own, tile) == rank) return;
     __shared__ uint32_t bits;
     if (threadIdx.x == 0) bits = 0;
     __syncthreads();
@@ -630,10 +634,11 @@ struct SrMergeParams {
     uint32_t ntris;
     uint32_t *mark;           // or null
     uint32_t skip_lo, skip_hi;  // vertices in [skip_lo, skip_hi) are shaded already
+    const uint8_t *shaded_blocks;  // or: vertices of the 256-vertex blocks flagged here are shaded already (chunk-culled front end)
 };
 __global__ void __launch_bounds__(256) k_shard_merge(const __grid_constant__ SrMergeParams p) {
     const uint32_t tile = blockIdx.x;
-    if (p.owners.owner[tile % p.owners.period] != p.rank) return;
+    if (sr_tile_owner(p.owners, tile) != p.rank) return;
     const uint32_t x0 = (tile % p.ntx) * SR_TILE_W, y0 = (tile / p.ntx) * SR_TILE_H;
     __shared__ uint32_t rows[SR_SHARD_MAX_WORLD - 1];
     if (threadIdx.x < p.npeers) rows[threadIdx.x] = __ldcv(p.peer_touched[threadIdx.x] + tile);
@@ -669,6 +674,7 @@ __global__ void __launch_bounds__(256) k_shard_merge(const __grid_constant__ SrM
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t v = __ldg(p.indices + (uint64_t)(id - 1) * 3 + c);
                     if (v >= p.skip_lo && v < p.skip_hi) continue;
+                    if (p.shaded_blocks != nullptr && p.shaded_blocks[v >> 8]) continue;
                     const uint32_t bit = 1u << (v & 31u);
                     if ((p.mark[v >> 5] & bit) == 0) atomicOr(p.mark + (v >> 5), bit);
                 }
@@ -971,6 +977,26 @@ __device__ __forceinline__ void sr_micro_triangle(const SrMicroParams &p, uint32
 template <bool PRECHECK, bool EARLYZ>
 __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro(const __grid_constant__ SrMicroParams p) {
     const uint32_t t = p.tri_begin + blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
+    float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
+    if (t < p.tri_end) {
+        const SrVertexSet *vs;
+        uint32_t vi[3];
+        sr_prim_vertices<3>(p.src, t, vs, vi);
+        A = __ldg(vs->pos + vi[0]); B = __ldg(vs->pos + vi[1]); C = __ldg(vs->pos + vi[2]);
+    }
+    sr_micro_triangle<PRECHECK, EARLYZ>(p, t, t < p.tri_end, A, B, C, threadIdx.x & 31);
+}
+
+// The same over a LIST of 1024-triangle chunks (chunk-culled front end of a sharded frame): eight CTAs per listed
+// chunk; *count chunks are listed, the launch covers the worst case and the CTAs beyond the count return at once.
+#define SR_CHUNK_TRIS 1024
+template <bool PRECHECK, bool EARLYZ>
+__global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro_chunks(const __grid_constant__ SrMicroParams p, const uint32_t *list,
+                                                                                       const uint32_t *count) {
+    constexpr uint32_t PER = SR_CHUNK_TRIS / SR_MICRO_THREADS;
+    const uint32_t ci = blockIdx.x / PER;
+    if (ci >= *count) return;
+    const uint32_t t = list[ci] * SR_CHUNK_TRIS + (blockIdx.x % PER) * SR_MICRO_THREADS + threadIdx.x;
     float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
     if (t < p.tri_end) {
         const SrVertexSet *vs;
@@ -1290,7 +1316,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
     uint64_t *bar = reinterpret_cast<uint64_t *>(far_row + SR_TILE_W);
 
     const uint32_t tile = PHASE == 2 ? blockIdx.x : p.shard_rank + blockIdx.x * p.shard_world;
-    if (PHASE == 2 && p.owners.owner[tile % p.owners.period] != p.shard_rank) return;
+    if (PHASE == 2 && sr_tile_owner(p.owners, tile) != p.shard_rank) return;
     const uint32_t tx = tile % p.fb.ntx, ty = tile / p.fb.ntx;
     const uint32_t x0 = tx * SR_TILE_W, y0 = ty * SR_TILE_H;
     if (p.tile_off[p.ntiles] > p.list_capacity) return;

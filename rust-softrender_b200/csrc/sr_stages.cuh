@@ -126,7 +126,9 @@ struct SrVertexSpan {
     uint64_t begin, end;
     const uint32_t *mask;
     uint64_t skip_lo, skip_hi;
+    const uint8_t *blocks;  // k_vertex: shade only the 256-vertex blocks flagged here; k_vertex_marked: skip them (shaded already)
 };
+#define SR_VERTEX_BLOCK 256
 template <int VS>
 __device__ __forceinline__ void sr_vertex_one(const SrVsConst &c, const SrMeshView &m, float4 *pos, float4 *attr, const uint64_t onp,
                                               const uint64_t v) {
@@ -153,6 +155,8 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ SrVsCons
                                                 float4 *attr, const uint64_t onp, const SrVertexSpan span) {
     // One vertex per thread: a warp reads 128 contiguous bytes of every SoA input plane and writes 512 contiguous
     // bytes of positions plus 32 contiguous attribute records, so every sector that moves is fully used both ways.
+    static_assert(SR_VERTEX_BLOCK == 256, "one CTA per vertex block");
+    if (span.blocks != nullptr && !span.blocks[(span.begin >> 8) + blockIdx.x]) return;  // (span.begin is a multiple of 256 then)
     const uint64_t v = span.begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= span.end) return;
     sr_vertex_one<VS>(c, m, pos, attr, onp, v);
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(256) k_vertex_marked(const __grid_constant__ S
         if (wj == 0u) continue;
         const uint64_t v = base + j * 32 + lane;
         if (((wj >> lane) & 1u) == 0u || v >= span.end || (v >= span.skip_lo && v < span.skip_hi)) continue;
+        if (span.blocks != nullptr && span.blocks[v >> 8]) continue;
         sr_vertex_one<VS>(c, m, pos, attr, onp, v);
     }
 }
@@ -227,6 +232,119 @@ __global__ void __launch_bounds__(256) k_index_minmax(const uint32_t *idx, uint6
         atomicMin(out, lo);
         atomicMax(out + 1, hi);
     }
+}
+
+// ---- chunk-culled front end of a sharded frame ------------------------------------------------------------
+// Static per mesh: the object-space bounding box of every block of 256 consecutive vertices, and the vertex range every chunk of
+// 1024 consecutive triangles references.  Per frame: the conservative range of screen TILE ROWS each block can reach under the draw's
+// transform, and from that which chunks can touch the rows of a rank.
+__global__ void __launch_bounds__(SR_VERTEX_BLOCK) k_block_aabb(const float *planes, uint64_t pstride, uint64_t nverts, float *aabb /* [nblk][6] */) {
+    const uint64_t v = (uint64_t)blockIdx.x * SR_VERTEX_BLOCK + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (v < nverts) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lo[k] = hi[k] = planes[(uint64_t)k * pstride + v];
+    }
+    __shared__ float s[SR_VERTEX_BLOCK / 32][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s[threadIdx.x >> 5][k] = lo[k]; s[threadIdx.x >> 5][3 + k] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float r = s[0][threadIdx.x];
+        for (int wgt = 1; wgt < SR_VERTEX_BLOCK / 32; ++wgt) r = threadIdx.x < 3 ? fminf(r, s[wgt][threadIdx.x]) : fmaxf(r, s[wgt][threadIdx.x]);
+        aabb[(uint64_t)blockIdx.x * 6 + threadIdx.x] = r;  // a NaN coordinate is dropped by fminf/fmaxf: such triangles draw nothing anyway
+    }
+}
+// vertex range of each chunk of `chunk_tris` consecutive triangles: out[c] = {min index, max index + 1}
+__global__ void __launch_bounds__(256) k_chunk_vrange(const uint32_t *idx, uint32_t ntris, uint32_t chunk_tris, uint2 *out) {
+    const uint32_t c = blockIdx.x;
+    const uint64_t i0 = (uint64_t)c * chunk_tris * 3, i1 = min((uint64_t)ntris * 3, i0 + (uint64_t)chunk_tris * 3);
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+        const uint32_t v = idx[i];
+        lo = min(lo, v);
+        hi = max(hi, v + 1u);
+    }
+    __shared__ uint32_t slo[8], shi[8];
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wgt = 1; wgt < 8; ++wgt) { lo = min(lo, slo[wgt]); hi = max(hi, shi[wgt]); }
+        out[c] = make_uint2(lo, hi);
+    }
+}
+// Conservative tile-row range of every vertex block under clip = pvm * (x, y, z, 1), screen y = vp_sy * (clip.y / clip.w) + vp_ty
+// (the viewport matrix of ClipVertex::normalize).  A projective map with w > 0 on all eight corners maps the box into the convex hull
+// of the corners' images, so the corners' screen y bound every vertex's; the float evaluation of the real vertex shader differs from
+// this one by rounding only, which the margin of two pixels (plus 1e-4 relative) covers by orders of magnitude.  A corner with
+// w <= 0 (or a non-finite value) makes the block "every row".  rows[b] = lo | hi << 16.
+__global__ void __launch_bounds__(256) k_block_rows(const float *aabb, uint32_t nblk, const __grid_constant__ SrVsConst c, uint32_t height, uint32_t nty,
+                                                    uint32_t tile_h, uint32_t *rows) {
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= nblk) return;
+    const float *bb = aabb + (uint64_t)b * 6;
+    float ymin = INFINITY, ymax = -INFINITY;
+    bool bounded = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x = bb[(k & 1) ? 3 : 0], y = bb[(k & 2) ? 4 : 1], z = bb[(k & 4) ? 5 : 2];
+        const float cy = c.pvm[0 * 4 + 1] * x + c.pvm[1 * 4 + 1] * y + c.pvm[2 * 4 + 1] * z + c.pvm[3 * 4 + 1];
+        const float cw = c.pvm[0 * 4 + 3] * x + c.pvm[1 * 4 + 3] * y + c.pvm[2 * 4 + 3] * z + c.pvm[3 * 4 + 3];
+        if (!(cw > 1e-6f) || !isfinite(cy)) { bounded = false; continue; }
+        const float sy = c.vpm[1 * 4 + 1] * (cy / cw) + c.vpm[3 * 4 + 1];
+        ymin = fminf(ymin, sy);
+        ymax = fmaxf(ymax, sy);
+    }
+    uint32_t lo = 0, hi = nty - 1;
+    if (bounded && isfinite(ymin) && isfinite(ymax)) {
+        const float m = 2.0f + 1e-4f * fmaxf(fabsf(ymin), fabsf(ymax));
+        const float a = fminf(fmaxf(ymin - m, 0.0f), (float)(height - 1)), z = fminf(fmaxf(ymax + m, 0.0f), (float)(height - 1));
+        lo = (uint32_t)a / tile_h;
+        hi = (uint32_t)z / tile_h;  // (triangle.rs:66-78 clamps a bounding box into the frame the same way: off-screen boxes land on the border rows)
+    }
+    rows[b] = lo | (hi << 16);
+}
+// flag[c] = 1 iff chunk c can reach a tile row of `rank` (row y belongs to rank y % world); the vertex blocks of flagged chunks are
+// flagged in `blocks` (the rank shades exactly those before its k_micro)
+__global__ void __launch_bounds__(256) k_chunk_select(const uint2 *vrange, const uint32_t *rows, uint32_t nchunk, uint32_t rank, uint32_t world,
+                                                      uint32_t *flag, uint8_t *blocks) {
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= nchunk) return;
+    const uint2 vr = vrange[c];
+    uint32_t lo = 0xFFFFu, hi = 0, sel = 0;
+    if (vr.y > vr.x) {
+        const uint32_t b0 = vr.x >> 8, b1 = (vr.y - 1u) >> 8;
+        for (uint32_t b = b0; b <= b1; ++b) {
+            const uint32_t r = rows[b];
+            lo = min(lo, r & 0xFFFFu);
+            hi = max(hi, r >> 16);
+        }
+        if (hi - lo + 1u >= world) sel = 1;
+        else
+            for (uint32_t y = lo; y <= hi; ++y) sel |= (y % world == rank) ? 1u : 0u;
+        if (sel)
+            for (uint32_t b = b0; b <= b1; ++b) blocks[b] = 1;
+    }
+    flag[c] = sel;
+}
+// ordered compaction of the flagged chunks (pos = exclusive scan of flag); the count lands in *count
+__global__ void __launch_bounds__(256) k_chunk_compact(const uint32_t *flag, const uint32_t *pos, uint32_t nchunk, uint32_t *list, uint32_t *count) {
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= nchunk) return;
+    if (flag[c]) list[pos[c]] = c;
+    if (c == nchunk - 1) *count = pos[c] + flag[c];
 }
 
 // AoS -> SoA plane transpose used by mesh upload and vertex injection

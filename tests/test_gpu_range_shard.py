@@ -112,12 +112,14 @@ def test_range_sharded_frame_is_bit_identical(P, ctx, world, lanes):
                 c.close()
 
 
-@pytest.mark.parametrize("world,fused", [(2, False), (3, False), (2, True)])
-def test_range_sharded_mesh_with_lazy_vertex_stage(P, ctx, world, fused, monkeypatch):
-    """A real mesh through run_to_fragment: with a shard group attached the vertex stage is recorded and each rank shades
-    only the vertex range of its own triangles plus the vertices the winners of its tiles reference (marked by the merge
-    kernel).  `fused` = the variant that merges the peers' keys inside the resolve (whole mesh shaded on every rank).
-    Frame bit-identical to the single-context frame; a later consumer of the draw's vertices still sees the whole mesh."""
+@pytest.mark.parametrize("world,fused,chunks", [(2, False, True), (3, False, True), (4, False, True), (2, False, False), (3, False, False), (2, True, False)])
+def test_range_sharded_mesh_with_lazy_vertex_stage(P, ctx, world, fused, chunks, monkeypatch):
+    """A real mesh through run_to_fragment: with a shard group attached the vertex stage is recorded and each rank shades only
+    the vertices it needs.  `chunks` = the chunk-culled front end (a coherent mesh: every rank rasterises the 1024-triangle
+    chunks that can reach ITS tile rows, all depth layers of a row on one rank, and resolves those rows); otherwise triangle
+    ranges (vertex range of the rank's triangles + the vertices the winners of its tiles reference).  `fused` = the variant
+    that merges the peers' keys inside the resolve.  Frame bit-identical to the single-context frame; a later consumer of the
+    draw's vertices still sees the whole mesh."""
     w, h = 640, 360
     mesh = scenes.make_grid(200, 170, 4, seed=0x5EED0003)
     assert mesh.ntris >= 65536
@@ -138,6 +140,10 @@ def test_range_sharded_mesh_with_lazy_vertex_stage(P, ctx, world, fused, monkeyp
         x.destroy()
 
     monkeypatch.setenv("SR_SHARD_SHARES", "1,1,16" if fused else "2,1,0")  # (read by sr_shard_create: tuning knob)
+    if chunks:
+        monkeypatch.setenv("SR_SHARD_CHUNKS", "1")  # opt-in mode (read at every draw)
+    else:
+        monkeypatch.delenv("SR_SHARD_CHUNKS", raising=False)
     ctxs = [P.Context(0) for _ in range(world)]
     groups = []
     for r, c in enumerate(ctxs):
