@@ -166,6 +166,17 @@ int sr_framebuffer_upload_planes(sr_framebuffer *, const void *color, const floa
  * travel as their values 0..255 in floats (set: they must be such values); any pointer may be NULL. */
 int sr_framebuffer_get_pixel(sr_framebuffer *, uint32_t x, uint32_t y, float rgba[4], float *depth, uint32_t *stencil);
 int sr_framebuffer_set_pixel(sr_framebuffer *, uint32_t x, uint32_t y, const float rgba[4], const float *depth, const uint32_t *stencil);
+/* Texture buffers declared with more than one colour plane (declare_texture_buffer! takes one OR MORE named colours,
+ * src/framebuffer/texturebuffer.rs:72-110; format SR_FB_TEXTURE_2xRGBAF32_DF32 has two).  The planes are addressed by index in
+ * declaration order -- the C-ABI form of the named accessors the macro generates (:110-117).
+ * _clear_attachment: Framebuffer::clear takes the tuple of all colours (:181-197); this records the colour of ONE plane and, like
+ *   sr_framebuffer_clear, a clear of the whole framebuffer (the other planes keep the colour last recorded for them, Color::empty()
+ *   initially).  sr_framebuffer_clear(fb, c) is _clear_attachment(fb, 0, c).
+ * _download_attachment: width*height colours (4 x f32) of plane `index`.
+ * A draw into such a framebuffer needs a fragment shader that returns the tuple (SR_FS_SUZANNE_GBUFFER) and vice versa
+ * (a type error in the reference, SR_ERR_INVALID_STATE here); Blend = (), stencil (), triangles. */
+int sr_framebuffer_clear_attachment(sr_framebuffer *, uint32_t index, const float color[4]);
+int sr_framebuffer_download_attachment(sr_framebuffer *, uint32_t index, float *color);
 /* parity introspection: per pixel, 1 + canonical index of the last primitive of the most recent
  * draw that wrote it (0 = untouched by that draw).  Enable before drawing. */
 int sr_framebuffer_enable_winner(sr_framebuffer *, int enable);
@@ -212,6 +223,9 @@ int sr_pipeline_bind_texture(sr_pipeline *, sr_texture *);
  * a recorded clear of `src` is materialised before the sampling draw.  Like an image texture, `src` must stay alive while it
  * is bound (the pipeline borrows it, as `TextureBufferRef<'a>` borrows its parent); unbind with NULL before destroying it. */
 int sr_pipeline_bind_framebuffer_texture(sr_pipeline *, sr_framebuffer *src);
+/* the same for colour plane `index` of a texture buffer (`buffer.normals()` of a buffer declared with `pub normals: ...`,
+ * texturebuffer.rs:110-117); index 0 of a one-plane texture buffer is sr_pipeline_bind_framebuffer_texture */
+int sr_pipeline_bind_framebuffer_attachment(sr_pipeline *, sr_framebuffer *src, uint32_t index);
 /* Filter and Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45) for every sampling shader of the pipeline.
  * border_rgba: 4 floats, read only for SR_EDGE_BORDER (NULL = transparent black).  Default: NEAREST, CLAMP -- `impl Default for Filter` /
  * `for Edge` (src/texture.rs:27-31,43-45); the config-2 scene sets BILINEAR explicitly. */

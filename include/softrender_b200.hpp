@@ -71,6 +71,9 @@ public:
     ~RenderBuffer() { if (h_) sr_framebuffer_destroy(h_); }
     Dimensions dimensions() const { return dim_; }
     void clear(const float (&color)[4]) { check(sr_framebuffer_clear(h_, color)); }
+    /* one colour of Framebuffer::clear's tuple for a texture buffer with several colour planes (texturebuffer.rs:181-197) */
+    void clear_attachment(uint32_t index, const float (&color)[4]) { check(sr_framebuffer_clear_attachment(h_, index, color)); }
+    void download_attachment(uint32_t index, float *color) { check(sr_framebuffer_download_attachment(h_, index, color)); }
     std::vector<PixelCD> pixels() {
         std::vector<PixelCD> out((size_t)dim_.width * dim_.height);
         check(sr_framebuffer_download(h_, out.data(), out.size() * sizeof(PixelCD)));
@@ -164,6 +167,8 @@ public:
     void set_stencil_config(sr_stencil_test t, sr_stencil_op o) { check(sr_pipeline_set_stencil_config(h_, t, o)); }
     /* render-to-texture: the colour of `src` sampled in place (TextureBufferRef, src/framebuffer/texturebuffer.rs:12-58) */
     void bind_framebuffer_texture(RenderBuffer *src) { check(sr_pipeline_bind_framebuffer_texture(h_, src ? src->handle() : nullptr)); }
+    /* colour plane `index` of a texture buffer declared with several (the named accessors of declare_texture_buffer!, :110-117) */
+    void bind_framebuffer_attachment(RenderBuffer &src, uint32_t index) { check(sr_pipeline_bind_framebuffer_attachment(h_, src.handle(), index)); }
     /* Filter / Edge of texture(t, coord, filter, edge), src/texture.rs:14-45 */
     void set_sampler(sr_texture_filter f, sr_texture_edge e, const float *border_rgba = nullptr) { check(sr_pipeline_set_sampler(h_, f, e, border_rgba)); }
     template <class T>

@@ -80,7 +80,10 @@ enum sr_fb_format {
     SR_FB_TEXTURE_RGBAF32_DF32 = 6,    /* RGBAf32TextureBuffer (src/framebuffer/texturebuffer.rs:200-210, declare_texture_buffer! :72-198): the colour
                                         * attachment is its own plane of width*height Vector4<f32> ("re-used as textures without copying", :63-66) and
                                         * the depths another: 16 + 4 B/pixel, structure of arrays */
-    SR_FB_TEXTURE_RGBAF32_DF32_S8 = 7  /* the same with a u8 stencil plane */
+    SR_FB_TEXTURE_RGBAF32_DF32_S8 = 7, /* the same with a u8 stencil plane */
+    SR_FB_TEXTURE_2xRGBAF32_DF32 = 8   /* a texture buffer declared with TWO colour planes (declare_texture_buffer! { pub a: RGBAf32Color, pub b:
+                                        * RGBAf32Color }): PixelBuffer::Color is the tuple (texturebuffer.rs:129-133), written by fragment shaders
+                                        * with two outputs (SR_FS_SUZANNE_GBUFFER); Blend = (), no stencil; 16 + 16 + 4 B/pixel in three planes */
 };
 
 /* ---- Viewport (src/geometry/clipvertex.rs:40-48) ------------------------ */
@@ -110,7 +113,10 @@ enum sr_fragment_shader {
     SR_FS_GREEN = 4,         /* full_example/src/shaders.rs:102 */
     SR_FS_DISCARD_CHECKER = 5, /* test shader: Fragment::Discard on odd (floor(x)+floor(y)), else colour = K[0..4) (fragment.rs:61-66) */
     SR_FS_TEXTURE_UNLIT = 6  /* second-pass shader of a render-to-texture chain: colour = texture(bound texture, uv = K[0..2), filter, edge)
-                              * -- the call of src/texture.rs:14-18 and nothing else */
+                              * -- the call of src/texture.rs:14-18 and nothing else */,
+    SR_FS_SUZANNE_GBUFFER = 7 /* a fragment shader with TWO colour outputs, for a texture buffer with two colour planes (the tuple colour of
+                               * declare_texture_buffer!, src/framebuffer/texturebuffer.rs:129-147): .0 = the suzanne Blinn-Phong colour
+                               * (examples/suzanne.rs:147-183), .1 = the interpolated world-space normal K[4..8) -- a G-buffer pass */
 };
 
 /* texture sampling state (src/texture.rs:21-45); the arithmetic is the sampler the reference ships,

@@ -514,9 +514,14 @@ void texture_sample(const so_texture *t, float u, float v, float *out) {
     for (int ch = 0; ch < 4; ++ch) out[ch] = (image && ch < 3) ? powf(val[ch], 2.2f) : val[ch];
 }
 
+// `out` = the colour the shader returns; a shader returning a tuple of two colours (SR_FS_SUZANNE_GBUFFER, for a texture buffer
+// with two colour planes: texturebuffer.rs:129-147) writes the second one to out[4..8)
 bool fragment_shader(int fs, const float *sv, const sr_uniforms *u, const so_texture *tex, float *out) {
     const float *K = sv + 4;
     switch (fs) {
+        case SR_FS_SUZANNE_GBUFFER:
+            for (int i = 0; i < 4; ++i) out[4 + i] = K[4 + i];  // .1 = the interpolated normal
+            return fragment_shader(SR_FS_SUZANNE, sv, u, tex, out);  // .0 = the suzanne colour
         case SR_FS_FLAT:
             for (int i = 0; i < 4; ++i) out[i] = K[i];
             return true;
@@ -647,7 +652,15 @@ inline void shade_and_write(const RasterArgs &A, so_framebuffer *fb, uint64_t in
         const float d = z;  // Depth::from_scalar
         const float dt = fb->depth[index];
         if (d >= dt) {
-            float c[4];
+            float c[8];
+            if (fb->color1) {  // tuple colour, Blend = (): set_pixel_unchecked stores each colour into its plane (texturebuffer.rs:141-147)
+                if (!fragment_shader(A.fs, sv, A.uniforms, A.tex, c)) return;
+                if (use_alpha) c[3] = c[3] * alpha;
+                for (int i = 0; i < 4; ++i) { fb->color[index * 4 + i] = c[i]; fb->color1[index * 4 + i] = c[4 + i]; }
+                fb->depth[index] = d;
+                if (fb->winner) fb->winner[index] = prim_id + 1;
+                return;
+            }
             if (fb->color_u8) {  // Blend = () on a u8 colour: blend(c.mul_alpha(..), p) = the source colour
                 if (!fragment_shader(A.fs, sv, A.uniforms, A.tex, c)) return;
                 uint8_t q[4] = {as_u8(c[0]), as_u8(c[1]), as_u8(c[2]), as_u8(c[3])};
@@ -1012,7 +1025,10 @@ int so_draw_fragment_run_tiles(so_draw *d, so_framebuffer *fb, const so_raster_s
                                const so_texture *tex, int nthreads, uint64_t tile_first, uint64_t tile_stride) {
     if (!d || !fb || !st || !u || tile_stride == 0) return SR_ERR_INVALID_ARGUMENT;
     if (d->space != 1) return SR_ERR_INVALID_STATE;
-    if (fs < SR_FS_FLAT || fs > SR_FS_TEXTURE_UNLIT) return SR_ERR_INVALID_ARGUMENT;
+    if (fs < SR_FS_FLAT || fs > SR_FS_SUZANNE_GBUFFER) return SR_ERR_INVALID_ARGUMENT;
+    if ((fs == SR_FS_SUZANNE_GBUFFER) != (fb->color1 != nullptr)) return SR_ERR_INVALID_STATE;  // a type error in the reference
+    if (fb->color1 && (st->blend != SR_BLEND_REPLACE || fb->color_u8)) return SR_ERR_INVALID_ARGUMENT;
+    if (fs == SR_FS_SUZANNE_GBUFFER && d->nk < 8) return SR_ERR_INVALID_ARGUMENT;
     if (fs == SR_FS_TEXTURE_UNLIT && d->nk < 2) return SR_ERR_INVALID_ARGUMENT;
     const uint32_t S = 4 + d->nk;
     if ((fs == SR_FS_FLAT || fs == SR_FS_DISCARD_CHECKER) && d->nk < 4) return SR_ERR_INVALID_ARGUMENT;
@@ -1178,6 +1194,13 @@ void so_framebuffer_clear(so_framebuffer *fb, const float color[4]) {
         if (fb->stencil) stencil_store(fb, i, 0);
         if (fb->winner) fb->winner[i] = 0;
     }
+}
+
+void so_framebuffer_clear2(so_framebuffer *fb, const float color[4], const float color1[4]) {
+    // ref: src/framebuffer/texturebuffer.rs:181-197 -- the tuple is destructured by name, each plane overwritten with its colour
+    so_framebuffer_clear(fb, color);
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    if (fb->color1) for (uint64_t i = 0; i < n; ++i) for (int c = 0; c < 4; ++c) fb->color1[i * 4 + c] = color1[c];
 }
 
 }  // extern "C"

@@ -40,6 +40,10 @@ typedef struct so_framebuffer {
     uint32_t stencil_bytes; /* element size of `stencil`: 1 (u8; 0 means 1), 2 (u16) or 4 (u32) -- src/stencil.rs:9-60 */
     uint8_t *color_u8;      /* non-NULL: the colour attachment is RGBAu8Color (src/color/predefined.rs:26), width*height*4 bytes;
                              * `color` is then unused.  Blend = () only. */
+    float *color1;          /* non-NULL: a texture buffer declared with TWO colour planes (declare_texture_buffer!,
+                             * src/framebuffer/texturebuffer.rs:72-147): PixelBuffer::Color is the tuple (color, color1), the fragment
+                             * shader returns both (SR_FS_SUZANNE_GBUFFER) and set_pixel_unchecked stores each into its own plane
+                             * (:141-147).  Blend = () only. */
 } so_framebuffer;
 
 typedef struct so_texture {
@@ -128,6 +132,8 @@ float so_depth_far(void);
 
 /* RenderBuffer::clear (src/framebuffer/renderbuffer/mod.rs:126-133) */
 void so_framebuffer_clear(so_framebuffer *, const float color[4]);
+/* Framebuffer::clear of a texture buffer with two colour planes: the tuple of colours, one per plane (texturebuffer.rs:181-197) */
+void so_framebuffer_clear2(so_framebuffer *, const float color[4], const float color1[4]);
 
 #ifdef __cplusplus
 }

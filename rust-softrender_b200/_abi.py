@@ -64,6 +64,8 @@ SYMBOLS = {
     "sr_framebuffer_upload_planes": (c_int, [c_void_p, c_void_p, f32p, c_void_p]),
     "sr_framebuffer_get_pixel": (c_int, [c_void_p, c_u32, c_u32, f32p, f32p, u32p]),
     "sr_framebuffer_set_pixel": (c_int, [c_void_p, c_u32, c_u32, f32p, f32p, u32p]),
+    "sr_framebuffer_clear_attachment": (c_int, [c_void_p, c_u32, f32p]),
+    "sr_framebuffer_download_attachment": (c_int, [c_void_p, c_u32, f32p]),
     "sr_framebuffer_enable_winner": (c_int, [c_void_p, c_int]),
     "sr_framebuffer_download_winner": (c_int, [c_void_p, u32p]),
     "sr_framebuffer_device_ptr": (c_void_p, [c_void_p]),
@@ -88,6 +90,7 @@ SYMBOLS = {
     "sr_pipeline_set_stencil_config": (c_int, [c_void_p, c_u32, c_u32]),
     "sr_pipeline_bind_texture": (c_int, [c_void_p, c_void_p]),
     "sr_pipeline_bind_framebuffer_texture": (c_int, [c_void_p, c_void_p]),
+    "sr_pipeline_bind_framebuffer_attachment": (c_int, [c_void_p, c_void_p, c_u32]),
     "sr_pipeline_set_sampler": (c_int, [c_void_p, c_u32, c_u32, ctypes.POINTER(ctypes.c_float)]),
     "sr_render_mesh": (c_int, [c_void_p, c_void_p, c_u32, c_int, c_u32, pp]),
     "sr_vertex_run": (c_int, [c_void_p, c_u32]),

@@ -170,8 +170,9 @@ struct sr_framebuffer {
     Buf aos_buf, stencil_buf, winner_buf;
     uint32_t stencil_bytes = 0;  // element size of the stencil attachment: 1, 2 or 4 (0: stencil type `()`)
     bool u8color = false;        // RGBAu8Color target: 8-byte AoS pixels {rgba8, f32 depth}
-    bool soa = false;            // texture-buffer storage: colour plane (float4 per pixel) followed by the depth plane
-    size_t px_bytes() const { return u8color ? 8 : 20; }
+    uint32_t soa = 0;            // texture-buffer storage: number of colour planes (float4 per pixel each), followed by the depth plane
+    float clear1[4] = {0, 0, 0, 0};  // clear colour of the second colour plane (Color::empty() until set)
+    size_t px_bytes() const { return u8color ? 8 : soa == 2 ? 36 : 20; }
     Buf vis_buf;                // visibility buffer of the opaque path (allocated on first use)
     bool vis_clean = false;     // every key of the tiles of shard (vis_rank, vis_world) is "far": the resolve hands it back that way
     uint32_t vis_rank = 0, vis_world = 0;
@@ -186,7 +187,8 @@ struct sr_framebuffer {
         v.stencil = stencil_buf ? stencil_buf->as<uint8_t>() : nullptr;
         v.stencil_bytes = stencil_bytes;
         v.u8color = u8color ? 1u : 0u;
-        v.soa = soa ? 1u : 0u;
+        v.soa = soa;
+        for (int i = 0; i < 4; ++i) v.clear1[i] = clear1[i];
         v.winner = (winner_enabled && winner_buf) ? winner_buf->as<uint32_t>() : nullptr;
         v.width = width; v.height = height; v.ntx = ntx; v.nty = nty;
         v.pending_clear = pending_clear ? 1u : 0u;
@@ -239,6 +241,7 @@ struct sr_pipeline {
     uint32_t stencil_test = SR_STENCIL_ALWAYS, stencil_op = SR_STENCIL_KEEP;
     sr_texture *texture = nullptr;
     sr_framebuffer *fb_texture = nullptr;  // render-to-texture source, sampled in place (texturebuffer.rs:12-58)
+    uint32_t fb_texture_plane = 0;         // which colour plane of a texture buffer
     uint32_t tex_filter = SR_FILTER_NEAREST, tex_edge = SR_EDGE_CLAMP;  // impl Default for Filter / Edge (src/texture.rs:27-31,43-45)
     float tex_border[4] = {0, 0, 0, 0};
 };
@@ -547,6 +550,7 @@ static int launch_opaque_merge_fs(sr_context *c, uint32_t fs, uint32_t ntiles, c
         case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_opaque_merge<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles, p, ctas_per_sm);
         case SR_FS_GREEN: return launch_opaque_merge<SR_FS_GREEN>(c, ntiles, p, ctas_per_sm);
         case SR_FS_TEXTURE_UNLIT: return launch_opaque_merge<SR_FS_TEXTURE_UNLIT>(c, ntiles, p, ctas_per_sm);
+        case SR_FS_SUZANNE_GBUFFER: return launch_opaque_merge<SR_FS_SUZANNE_GBUFFER>(c, ntiles, p, ctas_per_sm);
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
 }
@@ -560,6 +564,9 @@ static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, c
         SR_OPQ_CASE(SR_FS_FULL_EXAMPLE_TEXTURED);
         SR_OPQ_CASE(SR_FS_GREEN);
         SR_OPQ_CASE(SR_FS_TEXTURE_UNLIT);
+        case SR_FS_SUZANNE_GBUFFER:  // (two colour outputs: triangles only, the sharded-resolve and plain instantiations)
+            if (extra) return sr_fail(SR_ERR_UNSUPPORTED, "two-output fragment shaders draw triangles only");
+            return launch_opaque<SR_FS_SUZANNE_GBUFFER, false>(c, ntiles_owned, p);
     }
 #undef SR_OPQ_CASE
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
@@ -1157,6 +1164,7 @@ static int fs_nk(uint32_t fs) {
         case SR_FS_GREEN: return SrFsInfo<SR_FS_GREEN>::NK;
         case SR_FS_DISCARD_CHECKER: return SrFsInfo<SR_FS_DISCARD_CHECKER>::NK;
         case SR_FS_TEXTURE_UNLIT: return SrFsInfo<SR_FS_TEXTURE_UNLIT>::NK;
+        case SR_FS_SUZANNE_GBUFFER: return SrFsInfo<SR_FS_SUZANNE_GBUFFER>::NK;
     }
     return -1;
 }
@@ -1197,6 +1205,7 @@ static void preload_ranged_kernels() {
     preload(k_tile_opaque<SR_FS_FULL_EXAMPLE_TEXTURED, false, 2>);
     preload(k_tile_opaque<SR_FS_GREEN, false, 2>);
     preload(k_tile_opaque<SR_FS_TEXTURE_UNLIT, false, 2>);
+    preload(k_tile_opaque<SR_FS_SUZANNE_GBUFFER, false, 2>);
     preload(k_vertex<SR_VS_SUZANNE>);
     preload(k_vertex<SR_VS_FULL_EXAMPLE>);
     preload(k_vertex_passthrough);
@@ -1247,6 +1256,7 @@ int sr_registry_entry(uint32_t kind, uint32_t index, sr_shader_info *info) {
         {SR_FS_GREEN, 0, SrFsInfo<SR_FS_GREEN>::NK, 0, 0, "green", "full_example/src/shaders.rs:102"},
         {SR_FS_DISCARD_CHECKER, 0, SrFsInfo<SR_FS_DISCARD_CHECKER>::NK, 1, 0, "discard_checker", "test shader: Fragment::Discard (fragment.rs:61-66)"},
         {SR_FS_TEXTURE_UNLIT, 0, SrFsInfo<SR_FS_TEXTURE_UNLIT>::NK, 0, 1, "texture_unlit", "texture(t, uv, filter, edge): src/texture.rs:14-18 + full_example/src/texture.rs:25-84"},
+        {SR_FS_SUZANNE_GBUFFER, 0, SrFsInfo<SR_FS_SUZANNE_GBUFFER>::NK, 0, 0, "suzanne_gbuffer", "two outputs (colour, normal) for a two-plane texture buffer: texturebuffer.rs:129-147"},
     };
     static const Row bl[] = {
         {SR_BLEND_REPLACE, 0, 0, 0, 0, "replace", "Blend for (): src/color/blend.rs:28-31"},
@@ -1439,7 +1449,7 @@ int sr_context_stage_times(sr_context *c, sr_stage_times *out) {
 // ---- framebuffer -----------------------------------------------------------------------------------------
 int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32_t format, sr_framebuffer **out) {
     if (!c || !out) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    if (format > SR_FB_TEXTURE_RGBAF32_DF32_S8) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
+    if (format > SR_FB_TEXTURE_2xRGBAF32_DF32) return sr_fail(SR_ERR_INVALID_ARGUMENT, "unknown format %u", format);
     if (width > 256u * SR_TILE_W || height > 256u * SR_TILE_H || width > 65535u || height > 65535u)
         return sr_fail(SR_ERR_UNSUPPORTED, "framebuffer %ux%u exceeds %ux%u", width, height, 256u * SR_TILE_W, 256u * SR_TILE_H);
     SR_CUDA(cudaSetDevice(c->device));
@@ -1449,7 +1459,7 @@ int sr_framebuffer_create(sr_context *c, uint32_t width, uint32_t height, uint32
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     const uint64_t n = (uint64_t)width * height;
     fb->u8color = format == SR_FB_RGBAU8_DF32 || format == SR_FB_RGBAU8_DF32_S8;
-    fb->soa = format == SR_FB_TEXTURE_RGBAF32_DF32 || format == SR_FB_TEXTURE_RGBAF32_DF32_S8;
+    fb->soa = (format == SR_FB_TEXTURE_RGBAF32_DF32 || format == SR_FB_TEXTURE_RGBAF32_DF32_S8) ? 1u : format == SR_FB_TEXTURE_2xRGBAF32_DF32 ? 2u : 0u;
     SR_TRY(c->alloc(std::max<uint64_t>(n, 1) * fb->px_bytes(), &fb->aos_buf));
     fb->aos = fb->aos_buf->as<float>();
     fb->stencil_bytes = (format == SR_FB_RGBAF32_DF32_S8 || format == SR_FB_RGBAU8_DF32_S8 || format == SR_FB_TEXTURE_RGBAF32_DF32_S8) ? 1u
@@ -1486,10 +1496,11 @@ int sr_framebuffer_dimensions(const sr_framebuffer *fb, uint32_t *w, uint32_t *h
 int sr_framebuffer_download(sr_framebuffer *fb, void *dst, size_t nbytes) {
     SrRange nvtx("softrender: framebuffer download");
     if (!fb || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
-    const size_t need = (size_t)fb->width * fb->height * fb->px_bytes();
+    const size_t need = (size_t)fb->width * fb->height * (fb->soa ? 20 : fb->px_bytes());
     if (nbytes != need) return sr_fail(SR_ERR_INVALID_ARGUMENT, "download size %zu, expected %zu", nbytes, need);
     SR_CUDA(cudaSetDevice(fb->ctx->device));
     SR_TRY(materialize_clear(fb));
+    if (fb->soa == 2) return sr_fail(SR_ERR_UNSUPPORTED, "a texture buffer with two colour planes has no 20-byte pixel view: use sr_framebuffer_download_planes / _download_attachment");
     if (fb->soa) {  // the reference's PixelRead view of a texture buffer: gathered into the same 20-byte records
         Buf tmp;
         SR_TRY(fb->ctx->alloc(need, &tmp));
@@ -1527,7 +1538,7 @@ int sr_framebuffer_download_planes(sr_framebuffer *fb, void *color, float *depth
     const uint64_t n = (uint64_t)fb->width * fb->height;
     if (fb->soa) {  // the planes ARE the storage: straight copies
         if (color) SR_CUDA(cudaMemcpyAsync(color, fb->aos, n * 16, cudaMemcpyDeviceToHost, c->stream));
-        if (depth) SR_CUDA(cudaMemcpyAsync(depth, fb->aos + 4 * n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(depth, fb->aos + 4 * n * fb->soa, n * 4, cudaMemcpyDeviceToHost, c->stream));
         if (stencil) {
             if (!fb->stencil_buf) return sr_fail(SR_ERR_INVALID_ARGUMENT, "framebuffer has no stencil attachment");
             SR_CUDA(cudaMemcpyAsync(stencil, fb->stencil_buf->ptr, n * fb->stencil_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1562,7 +1573,7 @@ int sr_framebuffer_upload_planes(sr_framebuffer *fb, const void *color, const fl
     const uint64_t n = (uint64_t)fb->width * fb->height;
     if (fb->soa) {
         if (color) SR_CUDA(cudaMemcpyAsync(fb->aos, color, n * 16, cudaMemcpyHostToDevice, c->stream));
-        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * n, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * n * fb->soa, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
         if (stencil) SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->ptr, stencil, n * fb->stencil_bytes, cudaMemcpyHostToDevice, c->stream));
         SR_CUDA(cudaStreamSynchronize(c->stream));
         return SR_OK;
@@ -1602,7 +1613,7 @@ int sr_framebuffer_get_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, float r
     const uint64_t npix = (uint64_t)fb->width * fb->height;
     if (fb->soa) {
         SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 4, 16, cudaMemcpyDeviceToHost, c->stream));
-        SR_CUDA(cudaMemcpyAsync(px + 4, fb->aos + 4 * npix + idx, 4, cudaMemcpyDeviceToHost, c->stream));
+        SR_CUDA(cudaMemcpyAsync(px + 4, fb->aos + 4 * npix * fb->soa + idx, 4, cudaMemcpyDeviceToHost, c->stream));
     } else if (fb->u8color) SR_CUDA(cudaMemcpyAsync(px8, reinterpret_cast<unsigned char *>(fb->aos) + idx * 8, 8, cudaMemcpyDeviceToHost, c->stream));
     else SR_CUDA(cudaMemcpyAsync(px, fb->aos + idx * 5, 20, cudaMemcpyDeviceToHost, c->stream));
     uint32_t s = 0;  // (little-endian: the low bytes of `s` receive a u8 / u16 element)
@@ -1632,7 +1643,7 @@ int sr_framebuffer_set_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, const f
     if (fb->soa) {
         const uint64_t npix = (uint64_t)fb->width * fb->height;
         if (rgba) SR_CUDA(cudaMemcpyAsync(fb->aos + idx * 4, rgba, 16, cudaMemcpyHostToDevice, c->stream));
-        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * npix + idx, depth, 4, cudaMemcpyHostToDevice, c->stream));
+        if (depth) SR_CUDA(cudaMemcpyAsync(fb->aos + 4 * npix * fb->soa + idx, depth, 4, cudaMemcpyHostToDevice, c->stream));
     } else if (fb->u8color) {
         unsigned char *px = reinterpret_cast<unsigned char *>(fb->aos) + idx * 8;
         if (rgba) {
@@ -1654,6 +1665,25 @@ int sr_framebuffer_set_pixel(sr_framebuffer *fb, uint32_t x, uint32_t y, const f
         SR_CUDA(cudaMemcpyAsync(fb->stencil_buf->as<uint8_t>() + idx * fb->stencil_bytes, stencil, fb->stencil_bytes, cudaMemcpyHostToDevice, c->stream));
     }
     SR_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffers are copied before the call returns
+    return SR_OK;
+}
+// the colour planes of a texture buffer by index (the named attachments of declare_texture_buffer!, texturebuffer.rs:110-117)
+int sr_framebuffer_clear_attachment(sr_framebuffer *fb, uint32_t index, const float color[4]) {
+    if (!fb || !color) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (index >= std::max(fb->soa, 1u)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "colour attachment %u of %u", index, std::max(fb->soa, 1u));
+    for (int i = 0; i < 4; ++i) (index ? fb->clear1 : fb->clear)[i] = color[i];
+    fb->pending_clear = true;  // Framebuffer::clear takes the tuple of all colours (texturebuffer.rs:181-197): the other planes are cleared to their recorded colours
+    return SR_OK;
+}
+int sr_framebuffer_download_attachment(sr_framebuffer *fb, uint32_t index, float *color) {
+    if (!fb || !color) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (!fb->soa || index >= fb->soa) return sr_fail(SR_ERR_INVALID_ARGUMENT, "colour plane %u of a framebuffer with %u planes", index, fb->soa);
+    sr_context *c = fb->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(materialize_clear(fb));
+    const uint64_t n = (uint64_t)fb->width * fb->height;
+    SR_CUDA(cudaMemcpyAsync(color, fb->aos + 4 * n * index, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
     return SR_OK;
 }
 int sr_framebuffer_enable_winner(sr_framebuffer *fb, int enable) {
@@ -1703,7 +1733,7 @@ int sr_framebuffer_ipc_open(sr_context *c, const void *handle64, uint32_t width,
     fb->ntx = ceil_div(width, SR_TILE_W); fb->nty = ceil_div(height, SR_TILE_H);
     fb->aos = reinterpret_cast<float *>(p);
     fb->u8color = format == SR_FB_RGBAU8_DF32;
-    fb->soa = format == SR_FB_TEXTURE_RGBAF32_DF32;
+    fb->soa = format == SR_FB_TEXTURE_RGBAF32_DF32 ? 1u : 0u;
     fb->is_peer = true;
     fb->pending_clear = false;
     ++c->refs;  // owns no buffer of the context, so it holds the reference itself (released by sr_framebuffer_destroy)
@@ -1992,7 +2022,16 @@ int sr_pipeline_bind_framebuffer_texture(sr_pipeline *p, sr_framebuffer *src) {
     if (!p) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
     if (src && (src->width == 0 || src->height == 0)) return sr_fail(SR_ERR_INVALID_ARGUMENT, "texture source framebuffer is empty");
     p->fb_texture = src;
+    p->fb_texture_plane = 0;
     p->texture = nullptr;
+    return SR_OK;
+}
+// the same for colour plane `index` of a texture buffer (the named TextureBufferRef accessors, texturebuffer.rs:110-117)
+int sr_pipeline_bind_framebuffer_attachment(sr_pipeline *p, sr_framebuffer *src, uint32_t index) {
+    if (!p || !src) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    if (!src->soa || index >= src->soa) return sr_fail(SR_ERR_INVALID_ARGUMENT, "colour plane %u of a framebuffer with %u planes", index, src->soa);
+    SR_TRY(sr_pipeline_bind_framebuffer_texture(p, src));
+    p->fb_texture_plane = index;
     return SR_OK;
 }
 int sr_pipeline_set_sampler(sr_pipeline *p, uint32_t filter, uint32_t edge, const float *border_rgba) {
@@ -2301,6 +2340,17 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         const bool st_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
         if (d->vertex_lazy && !(d->blend == SR_BLEND_REPLACE && !st_active && fs != SR_FS_DISCARD_CHECKER)) SR_TRY(materialize_vertices(d));
     }
+    {   // the colour type of the target and the shader's return type must agree (a type error in the reference)
+        const bool two_out = fs == SR_FS_SUZANNE_GBUFFER;
+        if (two_out != (fb->soa == 2))
+            return sr_fail(SR_ERR_INVALID_STATE, two_out ? "a fragment shader with two colour outputs needs a texture buffer with two colour planes"
+                                                         : "a texture buffer with two colour planes needs a fragment shader with two colour outputs");
+        if (two_out) {
+            const bool st_active = fb->stencil_buf && !(p->stencil_test == SR_STENCIL_ALWAYS && p->stencil_op == SR_STENCIL_KEEP);
+            if (d->blend != SR_BLEND_REPLACE || st_active || d->primitive != SR_TRIANGLE || d->gen[0].n || d->gen[1].n)
+                return sr_fail(SR_ERR_UNSUPPORTED, "two-plane texture buffers: triangles with Blend = () and stencil () only");
+        }
+    }
     if (fb->u8color && d->blend != SR_BLEND_REPLACE)
         return sr_fail(SR_ERR_UNSUPPORTED, "RGBAu8Color targets take Blend = () only: the registered blend functions are defined on f32 colours "
                        "(full_example/src/color.rs:5-17); see INTEGRATION.md for registering a u8 blend");
@@ -2334,7 +2384,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
     tp.fs.tex_filter = p->tex_filter; tp.fs.tex_edge = p->tex_edge;
     for (int i = 0; i < 4; ++i) tp.fs.tex_border[i] = p->tex_border[i];
     if (p->fb_texture && samples) {
-        tp.fs.tex = reinterpret_cast<const uint8_t *>(p->fb_texture->aos);
+        tp.fs.tex = reinterpret_cast<const uint8_t *>(p->fb_texture->aos + 4ull * p->fb_texture->width * p->fb_texture->height * p->fb_texture_plane);
         tp.fs.tex_w = p->fb_texture->width;
         tp.fs.tex_h = p->fb_texture->height;
         tp.fs.tex_kind = SR_TEX_F32;

@@ -159,8 +159,10 @@ __device__ __forceinline__ uint32_t sr_prim_canonical(const SrPrimSource &s, uin
 // ---- framebuffer view ---------------------------------------------------------------------------
 struct SrFbView {
     float *aos;        // width*height*5 floats {r,g,b,a,depth}; may be a peer (NVLink) address
-    uint32_t soa;      // texture-buffer storage (declare_texture_buffer!, src/framebuffer/texturebuffer.rs:72-110): the colour attachment is
-                       // its own plane of width*height float4 at `aos` (re-usable as a texture without copying), the depths follow it
+    uint32_t soa;      // texture-buffer storage (declare_texture_buffer!, src/framebuffer/texturebuffer.rs:72-110): the number of colour planes
+                       // (0: not a texture buffer).  Plane k holds width*height float4 at `aos` + k*4*width*height floats (each re-usable as
+                       // a texture without copying), the depths follow the last plane
+    float clear1[4];   // clear colour of the second colour plane
     uint32_t u8color;  // colour attachment RGBAu8Color (src/color/predefined.rs:26): the AoS pixel is {rgba8, f32 depth} = 8 bytes instead of 20
     uint8_t *stencil;  // or null; elements of stencil_bytes (1, 2 or 4) bytes
     uint32_t stencil_bytes;
@@ -197,7 +199,13 @@ __device__ __forceinline__ void sr_unpack_u8(uint32_t v, float *q) {
     q[0] = (float)(v & 255u); q[1] = (float)((v >> 8) & 255u); q[2] = (float)((v >> 16) & 255u); q[3] = (float)(v >> 24);
 }
 // one pixel of either AoS layout; colours of a u8 target travel as channel values 0..255 in floats
-__device__ __forceinline__ float *sr_fb_depth_plane(const SrFbView &fb) { return fb.aos + 4ull * fb.width * fb.height; }  // (soa)
+__device__ __forceinline__ float *sr_fb_depth_plane(const SrFbView &fb) { return fb.aos + 4ull * fb.soa * fb.width * fb.height; }  // (soa)
+// a pixel of a two-plane texture buffer: o = {colour .0 (4), depth, colour .1 (4)}
+__device__ __forceinline__ void sr_fb_store_pixel2(const SrFbView &fb, uint64_t index, const float *o) {
+    reinterpret_cast<float4 *>(fb.aos)[index] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4 *>(fb.aos + 4ull * fb.width * fb.height)[index] = make_float4(o[5], o[6], o[7], o[8]);
+    sr_fb_depth_plane(fb)[index] = o[4];
+}
 __device__ __forceinline__ void sr_fb_store_pixel(const SrFbView &fb, uint64_t index, const float *o /* r,g,b,a,depth */) {
     if (fb.soa) {
         reinterpret_cast<float4 *>(fb.aos)[index] = make_float4(o[0], o[1], o[2], o[3]);

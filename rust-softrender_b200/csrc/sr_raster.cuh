@@ -539,11 +539,14 @@ __device__ __forceinline__ uint32_t sr_tile_owner(const SrTileOwners &o, uint32_
 }
 __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t x0, uint32_t y0) {
     if (fb.soa) {
-        const float o[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+        const float o[9] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS),
+                            fb.clear1[0], fb.clear1[1], fb.clear1[2], fb.clear1[3]};
         const uint32_t cols = min(x0 + SR_TILE_W, fb.width) - x0;
         for (uint32_t i = threadIdx.x; i < cols * SR_TILE_H; i += 256) {
             const uint32_t py = y0 + i / cols;
-            if (py < fb.height) sr_fb_store_pixel(fb, (uint64_t)py * fb.width + x0 + i % cols, o);
+            if (py >= fb.height) continue;
+            if (fb.soa == 2) sr_fb_store_pixel2(fb, (uint64_t)py * fb.width + x0 + i % cols, o);
+            else sr_fb_store_pixel(fb, (uint64_t)py * fb.width + x0 + i % cols, o);
         }
         return;
     }
@@ -1538,6 +1541,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
     float *stage = stage_all + warp * 2 * SR_OPQ_STAGE_FLOATS;
     const bool u8c = p.fb.u8color != 0;  // RGBAu8Color target: 8-byte pixels, colours quantised when they are produced
     const bool soa = p.fb.soa != 0;      // texture-buffer storage: colour plane + depth plane, two bulk stores per 32-pixel run
+    constexpr int NOUT = SrFsOutputs<FS>::N;  // 2: the shader returns a tuple of colours for a two-plane texture buffer (plain stores)
     const bool row_aligned = (W % (u8c ? 2u : 4u)) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
     uint32_t nbulk = 0;
     // The winner's vertex indices are fetched one chunk ahead, so the two dependent gathers (indices, then vertices) of
@@ -1569,9 +1573,9 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
         const uint32_t px = x0 + i % SR_TILE_W, py = y0 + i / SR_TILE_W;
         const uint32_t cx0 = x0 + (chunk * 32) % SR_TILE_W;  // first pixel of the chunk (warp-uniform)
         if (cx0 >= W || py >= H) continue;
-        const bool bulk = p.fb.pending_clear && row_aligned && cx0 + 32 <= W;
+        const bool bulk = NOUT == 1 && p.fb.pending_clear && row_aligned && cx0 + 32 <= W;
         const bool in_frame = px < W;
-        float o[5];
+        float o[5 + 4 * (NOUT - 1)];
         bool write = false;
         if (in_frame) {
             if (id_cur == 0) {
@@ -1579,6 +1583,7 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
                     o[0] = p.fb.clear[0]; o[1] = p.fb.clear[1]; o[2] = p.fb.clear[2]; o[3] = p.fb.clear[3];
                     if (u8c) sr_quantise_u8(o, false, 0);
                     o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+                    if constexpr (NOUT == 2) { o[5] = p.fb.clear1[0]; o[6] = p.fb.clear1[1]; o[7] = p.fb.clear1[2]; o[8] = p.fb.clear1[3]; }
                     write = true;
                 }
             } else if (EXTRA && id_cur - 1 >= p.ntris) {
@@ -1708,7 +1713,8 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
             }
             ++nbulk;
         } else if (write) {
-            sr_fb_store_pixel(p.fb, (uint64_t)py * W + px, o);
+            if constexpr (NOUT == 2) sr_fb_store_pixel2(p.fb, (uint64_t)py * W + px, o);
+            else sr_fb_store_pixel(p.fb, (uint64_t)py * W + px, o);
         }
     }
     if ((nbulk && lane == 0) || (p.vis != nullptr && p.reset_vis && tid < SR_TILE_H)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1731,6 +1737,13 @@ struct SrOrdSetup {
 };
 static_assert(sizeof(SrOrdSetup) == 112, "seven float4");
 #define SR_ORD_LIST_CAP 2048  // group ids sorted in shared memory; longer lists are sorted in place in HBM
+#ifndef SR_ORD_LANE_BOX
+#define SR_ORD_LANE_BOX 20  // a band's batch takes the lane-per-triangle sweep when 7 of 8 of its (untightened, band-clipped) boxes are at most this
+#endif
+#ifndef SR_ORD_LANE_PIX
+#define SR_ORD_LANE_PIX 32  // largest (tightened, band-clipped) box a single lane sweeps in k_tile_ordered's small-triangle runs
+#endif
+static_assert(SR_ORD_LANE_PIX <= 32, "box positions are kept in a 32-bit mask");
 #define SR_ORD_RING 64  // fragments a warp can hold between coverage and shading (at most 31 carried over + 32 new)
 #define SR_ORD_SMEM_BYTES (SR_TILE_PIXELS * (16 + 4 + 4 + 1) + SR_RASTER_THREADS * sizeof(SrOrdSetup) + SR_ORD_LIST_CAP * 4 + \
                            SR_RASTER_WARPS * SR_ORD_RING * 16)
@@ -2294,8 +2307,127 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     head = (head + n) % SR_ORD_RING;
                     count -= n;
                 };
-                for (uint32_t k = 0; k < nband; ++k) {
+                // Runs of SMALL triangles (box inside the band of at most 32 pixels) are swept one triangle per LANE: a mesh of
+                // pixel-sized triangles would otherwise keep 3-9 of 32 lanes busy for a whole warp step per triangle.  (A) every
+                // lane finds the covered pixels of its own triangle (a bit mask of box positions, triangle.rs:104-120); (B) bidding
+                // rounds keep every pixel's fragments in submission order: each lane bids (round, 255 - lane) with atomicMax for
+                // the pixels of its not-yet-applied fragments, then applies -- depth test, depth update, queue for shading --
+                // exactly those fragments whose pixel it holds.  Lanes hold consecutive list entries, so the lowest lane wins
+                // every contested pixel: a later triangle never overtakes an earlier one, and the earliest unfinished lane always
+                // completes.  A triangle covers a pixel at most once, so the order among its own fragments is free.  Triangles
+                // seldom overlap inside a 32-triangle run (shared edges only), so nearly every run takes one round.
+                // Active stencil configurations touch every pixel of the box before coverage (triangle.rs:91-99) and keep the
+                // cooperative sweep below.
+                const bool lane_ok = !c.has_stencil || (p.stencil_test == SR_STENCIL_ALWAYS && p.stencil_op == SR_STENCIL_KEEP);
+                uint32_t *claim = s_claim[warp];
+                // The mode is chosen per batch and band: one lane per triangle only pays when the runs are long, i.e. when (nearly)
+                // all the triangles of the band are small; a mixed population keeps the cooperative sweep throughout.
+                bool lane_mode = false;
+                if (lane_ok && nband >= 8) {
+                    uint32_t nsmall = 0;
+                    for (uint32_t k = lane; k < nband; k += 32) {
+                        const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s_band[warp][k]].bx);
+                        const uint32_t bw = (box.x >> 16) - (box.x & 0xffffu) + 1;
+                        const uint32_t bh = min(box.y >> 16, ry_hi) - max(box.y & 0xffffu, ry_lo) + 1;
+                        nsmall += bw * bh <= SR_ORD_LANE_BOX ? 1u : 0u;
+                    }
+                    nsmall = __reduce_add_sync(0xffffffffu, nsmall);
+                    lane_mode = nsmall * 8 >= nband * 7;
+                }
+                uint32_t ncoop = lane_mode ? 0u : nband;  // entries from k on that take the cooperative sweep without another look
+                for (uint32_t k = 0; k < nband;) {
+                    uint32_t run = 0;
+                    if (ncoop == 0) {
+                        bool small = false;
+                        uint32_t s = 0, minx = 0, r0 = 0, bw = 0, bh = 0;
+                        if (k + lane < nband) {
+                            s = s_band[warp][k + lane];
+                            const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
+                            minx = box.x & 0xffffu;
+                            r0 = max(box.y & 0xffffu, ry_lo);
+                            uint32_t maxx = box.x >> 16, r1 = min(box.y >> 16, ry_hi);
+                            // candidate tightening (proof above sr_tightening_applies): the pixels outside the tightened range
+                            // fail the reference's own coverage test, and without an active stencil nothing else looks at them
+                            const SrOrdSetup &q = s_setup[s];
+                            const float xmin = fminf(fminf(q.A.x, q.B.x), q.C.x), xmax = fmaxf(fmaxf(q.A.x, q.B.x), q.C.x);
+                            const float ymin = fminf(fminf(q.A.y, q.B.y), q.C.y), ymax = fmaxf(fmaxf(q.A.y, q.B.y), q.C.y);
+                            bool empty = false;
+                            if (sr_tightening_applies(xmin, xmax, ymin, ymax, q.f.z)) {
+                                const int lx = max((int)minx, sr_tight_lo(xmin)), hx = min((int)maxx, sr_tight_hi(xmax));
+                                const int ly = max((int)r0, sr_tight_lo(ymin)), hy = min((int)r1, sr_tight_hi(ymax));
+                                empty = lx > hx || ly > hy;
+                                if (!empty) { minx = (uint32_t)lx; maxx = (uint32_t)hx; r0 = (uint32_t)ly; r1 = (uint32_t)hy; }
+                            }
+                            bw = empty ? 0u : maxx - minx + 1;
+                            bh = empty ? 0u : r1 - r0 + 1;
+                            small = bw * bh <= SR_ORD_LANE_PIX;
+                        }
+                        const uint32_t smallmask = __ballot_sync(0xffffffffu, small);
+                        run = ~smallmask ? (uint32_t)__ffs(~smallmask) - 1u : 32u;  // leading run of small triangles
+                        if (run == 0) ncoop = min(smallmask ? (uint32_t)__ffs(smallmask) - 1u : 32u, nband - k);  // leading run of the others
+                        if (run > 0) {
+                            const bool mine = lane < run;
+                            const SrOrdSetup &q = s_setup[s];
+                            SrTri tr;
+                            tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
+                            tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
+                            tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
+                            tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                            const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
+                            const uint32_t canonical = q.canonical;
+                            uint32_t rem = 0;  // box positions (row-major) whose fragment is still to be applied
+                            if (mine && bw != 0)
+                                sr_raster_box<false>(tr, z1, z2, z3, minx, r0, bw, bh, 0u, [&](uint32_t px, uint32_t py, unsigned long long) {
+                                    rem |= 1u << ((py - r0) * bw + (px - minx));
+                                });
+                            const uint32_t cbase = (r0 - ry_lo) * SR_TILE_W + (minx - x0);  // box origin inside the band
+                            while (__any_sync(0xffffffffu, rem != 0)) {
+                                ++claim_round;
+                                const uint32_t bid = (claim_round << 8) | (255u - lane);
+                                for (uint32_t m = rem; m; m &= m - 1) {
+                                    const uint32_t i = (uint32_t)__ffs(m) - 1u;
+                                    atomicMax(&claim[cbase + (i / bw) * SR_TILE_W + i % bw], bid);
+                                }
+                                __syncwarp();
+                                uint32_t todo = 0;  // the fragments this lane applies in this round
+                                for (uint32_t m = rem; m; m &= m - 1) {
+                                    const uint32_t i = (uint32_t)__ffs(m) - 1u;
+                                    if (claim[cbase + (i / bw) * SR_TILE_W + i % bw] == bid) todo |= 1u << i;
+                                }
+                                rem &= ~todo;
+                                while (__any_sync(0xffffffffu, todo != 0)) {
+                                    bool pass = false;
+                                    uint32_t li = 0;
+                                    float u = 0.0f, v = 0.0f, w;
+                                    if (todo) {
+                                        const uint32_t i = (uint32_t)__ffs(todo) - 1u;
+                                        todo &= todo - 1;
+                                        const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                                        li = (py - y0) * SR_TILE_W + (px - x0);
+                                        sr_tri_bary(tr, px, py, u, v, w);  // (covered: the same arithmetic as pass A)
+                                        const float z = sr_bary(u, z1, v, z2, w, z3);
+                                        if (z >= s_depth[li]) {  // triangle.rs:126 (z < 0 was part of pass A)
+                                            pass = true;
+                                            s_depth[li] = z;
+                                            s_winner[li] = canonical + 1;
+                                        }
+                                    }
+                                    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                                    if (pass)
+                                        s_ring[(head + count + __popc(m & ((1u << lane) - 1u))) % SR_ORD_RING] =
+                                            make_uint4(li | (s << 16), __float_as_uint(u), __float_as_uint(v), 0u);
+                                    count += __popc(m);
+                                    __syncwarp();
+                                    if (count >= 32) shade_and_blend(32);
+                                }
+                            }
+                            k += run;
+                            continue;
+                        }
+                    }
                     const uint32_t s = s_band[warp][k];
+                    ++k;
+                    --ncoop;
                     const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                     const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
                     const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
@@ -2501,9 +2633,11 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t seed, uint64
 __global__ void __launch_bounds__(256) k_fb_fill(SrFbView fb) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint64_t)fb.width * fb.height) return;
-    float o[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    float o[9] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS), fb.clear1[0], fb.clear1[1], fb.clear1[2],
+                  fb.clear1[3]};
     if (fb.u8color) sr_quantise_u8(o, false, 0);
-    sr_fb_store_pixel(fb, i, o);
+    if (fb.soa == 2) sr_fb_store_pixel2(fb, i, o);
+    else sr_fb_store_pixel(fb, i, o);
     if (fb.stencil) sr_stencil_store(fb.stencil, fb.stencil_bytes, i, 0u);
     if (fb.winner) fb.winner[i] = 0;
 }

@@ -75,6 +75,11 @@ template <> struct SrFsInfo<SR_FS_FULL_EXAMPLE_TEXTURED> { static constexpr int 
 template <> struct SrFsInfo<SR_FS_GREEN> { static constexpr int NK = 0; static constexpr bool DISCARDS = false, LIT = false; };
 template <> struct SrFsInfo<SR_FS_DISCARD_CHECKER> { static constexpr int NK = 4; static constexpr bool DISCARDS = true, LIT = false; };
 template <> struct SrFsInfo<SR_FS_TEXTURE_UNLIT> { static constexpr int NK = 2; static constexpr bool DISCARDS = false, LIT = false; };
+// (LIT = false: the second output IS the interpolated normal, so the attributes are interpolated exactly, without FMA contraction)
+template <> struct SrFsInfo<SR_FS_SUZANNE_GBUFFER> { static constexpr int NK = 8; static constexpr bool DISCARDS = false, LIT = false; };
+// colour outputs of a fragment shader: 2 = it returns a tuple of two colours (out[0..4) and out[5..9); out[4] carries the depth)
+template <int FS> struct SrFsOutputs { static constexpr int N = 1; };
+template <> struct SrFsOutputs<SR_FS_SUZANNE_GBUFFER> { static constexpr int N = 2; };
 
 // Fragment-shader arithmetic is NOT on the bit-exact path (colour parity is 1/255 per channel, and the reference's
 // powf is libm's): normalisation uses rsqrtf and powers use exp2(y*log2(x)) on the SFU unless SR_FS_EXACT is set.
@@ -217,8 +222,12 @@ __device__ __forceinline__ bool sr_fragment_shader(const SrFsConst &c, const flo
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[i] = K[i];
         return true;
-    } else if (FS == SR_FS_SUZANNE) {
-        // examples/suzanne.rs:147-183
+    } else if (FS == SR_FS_SUZANNE || FS == SR_FS_SUZANNE_GBUFFER) {
+        // examples/suzanne.rs:147-183 (the G-buffer variant returns the interpolated normal as its second colour)
+        if (FS == SR_FS_SUZANNE_GBUFFER) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[5 + i] = K[4 + i];
+        }
         const float *position = K, *normal = K + 4;
         float d[4], view_dir[4], light_dir[4], h[4], halfway[4];
 #pragma unroll

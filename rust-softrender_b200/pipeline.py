@@ -175,7 +175,11 @@ class RenderBuffer:
         u8_color: colour attachment RGBAu8Color instead of RGBAf32Color (src/color/predefined.rs:17,26).
         texture_buffer: RGBAf32TextureBuffer storage -- colour and depth in planes of their own, the colour plane re-usable
         as a texture without copying (src/framebuffer/texturebuffer.rs:63-66,200-210)."""
-        if texture_buffer:
+        if texture_buffer == 2:  # declare_texture_buffer! with two colour planes (texturebuffer.rs:72-110)
+            if stencil:
+                raise ValueError("two-plane texture buffers have stencil type ()")
+            fmt = FB_TEXTURE_2xRGBAF32_DF32
+        elif texture_buffer:
             fmt = {False: FB_TEXTURE_RGBAF32_DF32, True: FB_TEXTURE_RGBAF32_DF32_S8, 8: FB_TEXTURE_RGBAF32_DF32_S8}[stencil]
         elif u8_color:
             fmt = {False: FB_RGBAU8_DF32, True: FB_RGBAU8_DF32_S8, 8: FB_RGBAU8_DF32_S8}[stencil]
@@ -197,6 +201,17 @@ class RenderBuffer:
     def clear(self, color):
         c = (ctypes.c_float * 4)(*[float(x) for x in color])
         check(lib.sr_framebuffer_clear(self.h, c))
+
+    def clear_attachment(self, index: int, color):
+        """The colour of ONE plane of Framebuffer::clear's tuple (texturebuffer.rs:181-197); records a clear of the whole buffer."""
+        c = (ctypes.c_float * 4)(*[float(x) for x in color])
+        check(lib.sr_framebuffer_clear_attachment(self.h, index, c))
+
+    def download_attachment(self, index: int) -> np.ndarray:
+        """Colour plane `index` of a texture buffer: float32 [height*width, 4]."""
+        out = np.empty((self.width * self.height, 4), np.float32)
+        check(lib.sr_framebuffer_download_attachment(self.h, index, out.ctypes.data_as(_abi.f32p)))
+        return out
 
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """AoS read-back: float32 [height*width, 5] = {r,g,b,a,depth}, index = x + y*width (an RGBAu8Color target: a
@@ -531,6 +546,10 @@ class Pipeline:
         """Render-to-texture: `src`'s colour attachment becomes the texture in place, no copy
         (TextureBufferRef, src/framebuffer/texturebuffer.rs:12-58)."""
         check(lib.sr_pipeline_bind_framebuffer_texture(self.h, src.h if src else None))
+
+    def bind_framebuffer_attachment(self, src: "RenderBuffer", index: int):
+        """Colour plane `index` of a texture buffer as the texture, in place (the named accessor, texturebuffer.rs:110-117)."""
+        check(lib.sr_pipeline_bind_framebuffer_attachment(self.h, src.h, index))
 
     def set_sampler(self, filter: int, edge: int, border=None):
         """Filter / Edge of texture(t, coord, filter, edge) (src/texture.rs:14-45); `border` = Edge::Border's colour."""

@@ -23,7 +23,8 @@ u8p = ctypes.POINTER(ctypes.c_uint8)
 
 class SoFramebuffer(ctypes.Structure):
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("color", f32p), ("depth", f32p),
-                ("stencil", u8p), ("winner", u32p), ("stencil_bytes", ctypes.c_uint32), ("color_u8", u8p)]
+                ("stencil", u8p), ("winner", u32p), ("stencil_bytes", ctypes.c_uint32), ("color_u8", u8p),
+                ("color1", f32p)]
 
 
 class SoTexture(ctypes.Structure):
@@ -113,6 +114,7 @@ def lib():
         L.so_stencil_op_wide.argtypes = [ctypes.c_uint32] * 4
         L.so_depth_far.restype = ctypes.c_float
         L.so_framebuffer_clear.argtypes = [ctypes.POINTER(SoFramebuffer), f32p]
+        L.so_framebuffer_clear2.argtypes = [ctypes.POINTER(SoFramebuffer), f32p, f32p]
         _lib = L
     return _lib
 
@@ -128,6 +130,7 @@ class OracleFramebuffer:
     height: int
     stencil_bits: int = 0
     u8_color: bool = False  # colour attachment RGBAu8Color (src/color/predefined.rs:26) instead of RGBAf32Color
+    two_colors: bool = False  # a texture buffer declared with two colour planes (texturebuffer.rs:72-147): `color` and `color1`
     color: np.ndarray = field(init=False)
     depth: np.ndarray = field(init=False)
     stencil: np.ndarray | None = field(init=False)
@@ -136,6 +139,7 @@ class OracleFramebuffer:
     def __post_init__(self):
         n = self.width * self.height
         self.color = np.zeros((n, 4), np.uint8 if self.u8_color else np.float32)
+        self.color1 = np.zeros((n, 4), np.float32) if self.two_colors else None
         self.depth = np.full(n, lib().so_depth_far(), np.float32)
         self.stencil = np.zeros(n, {16: np.uint16, 32: np.uint32}.get(self.stencil_bits, np.uint8)) if self.stencil_bits else None
         self.winner = np.zeros(n, np.uint32)
@@ -144,12 +148,16 @@ class OracleFramebuffer:
         return SoFramebuffer(self.width, self.height, None if self.u8_color else _fp(self.color), _fp(self.depth),
                              self.stencil.ctypes.data_as(u8p) if self.stencil is not None else None,
                              self.winner.ctypes.data_as(u32p), self.stencil.itemsize if self.stencil is not None else 0,
-                             self.color.ctypes.data_as(u8p) if self.u8_color else None)
+                             self.color.ctypes.data_as(u8p) if self.u8_color else None,
+                             _fp(self.color1) if self.color1 is not None else None)
 
-    def clear(self, color):
+    def clear(self, color, color1=None):
         c = np.asarray(color, np.float32)
         s = self.struct()
-        lib().so_framebuffer_clear(ctypes.byref(s), _fp(c))
+        if color1 is not None:
+            lib().so_framebuffer_clear2(ctypes.byref(s), _fp(c), _fp(np.asarray(color1, np.float32)))
+        else:
+            lib().so_framebuffer_clear(ctypes.byref(s), _fp(c))
 
 
 class OracleDraw:

@@ -107,7 +107,8 @@ def test_shader_registry_enumerates_without_a_device():
     assert {e["name"]: (e["vin_floats"], e["nk"]) for e in vs}["suzanne"] == (6, 8)        # pos3+normal3 -> {position4, normal4}
     assert {e["name"]: (e["vin_floats"], e["nk"]) for e in vs}["full_example"] == (8, 10)  # + uv2
     assert [e["id"] for e in gs] == [sr.GS_CLIP, sr.GS_FACE_NORMALS, sr.GS_VERTEX_NORMALS, sr.GS_CLIP_SH]
-    assert [e["id"] for e in fs] == [sr.FS_FLAT, sr.FS_SUZANNE, sr.FS_FULL_EXAMPLE, sr.FS_FULL_EXAMPLE_TEXTURED, sr.FS_GREEN, sr.FS_DISCARD_CHECKER, sr.FS_TEXTURE_UNLIT]
+    assert [e["id"] for e in fs] == [sr.FS_FLAT, sr.FS_SUZANNE, sr.FS_FULL_EXAMPLE, sr.FS_FULL_EXAMPLE_TEXTURED, sr.FS_GREEN, sr.FS_DISCARD_CHECKER, sr.FS_TEXTURE_UNLIT,
+                                   sr.FS_SUZANNE_GBUFFER]
     assert [e["name"] for e in fs if e["discards"]] == ["discard_checker"] and [e["name"] for e in fs if e["needs_texture"]] == ["full_example_4light_textured", "texture_unlit"]
     assert [e["name"] for e in bl] == ["replace", "alpha_over", "additive"] and pipeline.registry(9) == []
     assert all(e["reference"] for e in vs + gs + fs + bl)

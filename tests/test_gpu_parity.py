@@ -632,6 +632,100 @@ def test_texture_buffer_storage(P, ctx):
         x.destroy()
 
 
+def test_texture_buffer_with_two_colour_planes(P, ctx):
+    """declare_texture_buffer! takes one OR MORE named colours (src/framebuffer/texturebuffer.rs:72-110): the pixel colour is then the
+    tuple of them (:129-133), the fragment shader returns the tuple and set_pixel_unchecked stores each into its own plane
+    (:141-147); clear takes a tuple too (:181-197).  A G-buffer pass -- Suzanne's lit colour in plane 0, the interpolated normal in
+    plane 1 -- through the clip path and the no-clip path, big and small draws, against the oracle; then the NORMAL plane is bound in
+    place as the texture of a second pass (the named TextureBufferRef accessor, :110-117)."""
+    mesh = H.suzanne_mesh()
+    size = 320
+    u = scenes.suzanne_uniforms(size, size)
+    vp = scenes.Viewport.new(size, size, 0.001, 1000.0)
+    clear0, clear1 = H.CLEAR, (0.5, 0.25, -1.0, 0.0)
+    from softrender_b200._abi import SoftrenderError
+    fb = P.RenderBuffer.with_dimensions(ctx, size, size, texture_buffer=2)
+    fb.enable_winner(True)
+    gmesh = P.Mesh(ctx, mesh)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    # freshly created: Color::empty() in both planes, Depth::far()
+    assert not fb.download_attachment(0).any() and not fb.download_attachment(1).any()
+    for clip in (False, True):
+        fb.clear_attachment(0, clear0)
+        fb.clear_attachment(1, clear1)
+        ofb = ob.OracleFramebuffer(size, size, two_colors=True)
+        ofb.clear(clear0, clear1)
+        od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+        if clip:
+            od.vertex_run(sr.VS_SUZANNE, u, mesh.vertices)
+            od.clip_primitives()
+            od.finish(vp)
+            fs = pipe.render_mesh(sr.TRIANGLE, gmesh).run(sr.VS_SUZANNE).clip_primitives().finish(vp)
+        else:
+            od.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices)
+            fs = pipe.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE)
+        od.fragment_run(ofb, sr.FS_SUZANNE_GBUFFER, u)
+        fs.run(sr.FS_SUZANNE_GBUFFER)
+        assert np.array_equal(fb.download_winner(), ofb.winner), "coverage / winning primitive"
+        c0, c1 = fb.download_attachment(0), fb.download_attachment(1)
+        col, dep, _ = fb.download_planes()
+        H.assert_bits_equal(col, c0, "download_planes' colour is plane 0")
+        H.assert_bits_equal(dep, ofb.depth, "depth plane")
+        assert np.abs(c0 - ofb.color).max() <= COLOR_TOL, "plane 0: lit colour"
+        H.assert_bits_equal(c1, ofb.color1, "plane 1: interpolated normals (no shader arithmetic: bit-exact)")
+        drawn = ofb.winner != 0
+        assert drawn.any() and (~drawn).any()
+        assert np.all(c1[~drawn] == np.float32(clear1)) and np.all(c0[~drawn] == np.float32(clear0))
+    # a second draw onto the existing contents (no pending clear): big screen-space triangles, 8 attributes each
+    rng = np.random.default_rng(77)
+    n = 60
+    verts = H.random_screen_triangles(rng, n, size, size, max_size=90.0, nk=8)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 1)
+    od.fragment_run(ofb, sr.FS_SUZANNE_GBUFFER, u)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_SUZANNE_GBUFFER)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    # (arbitrary "normals" make the lit colour a power of garbage: NaN where the oracle has NaN)
+    c0, c1 = fb.download_attachment(0), fb.download_attachment(1)
+    H.assert_bits_equal(c1, ofb.color1, "plane 1 after the second draw")
+    ok = np.isfinite(ofb.color) & np.isfinite(c0)
+    assert np.array_equal(np.isnan(c0), np.isnan(ofb.color)) and np.abs(c0 - ofb.color)[ok].max() <= COLOR_TOL
+    # accessors see plane 0 and the depth
+    px = 5 * size + 3
+    dep = fb.download_planes()[1]
+    got = fb.pixel(3, 5)
+    assert np.array_equal(np.float32(got[0]), c0[px], equal_nan=True) and np.float32(got[1]) == dep[px]
+    # type agreement between shader and target, both ways
+    with pytest.raises(SoftrenderError):
+        pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_SUZANNE)
+    fb1 = make_fb(P, ctx, size, size)
+    p1 = P.Pipeline.from_framebuffer(fb1, u)
+    with pytest.raises(SoftrenderError):
+        p1.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(sr.FS_SUZANNE_GBUFFER)
+    with pytest.raises(SoftrenderError):
+        pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).with_blend(sr.BLEND_ALPHA_OVER).run(sr.FS_SUZANNE_GBUFFER)
+    with pytest.raises(SoftrenderError):
+        fb.download()  # no 20-byte pixel view of a tuple colour
+    with pytest.raises(SoftrenderError):
+        p1.bind_framebuffer_attachment(fb, 2)
+    # second pass: the NORMAL plane sampled in place
+    normals = fb.download_attachment(1).reshape(size, size, 4)
+    p1.bind_framebuffer_attachment(fb, 1)
+    p1.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
+    quad = np.array([[-1, -1, 0, 1, 0, 1], [1, -1, 0, 1, 1, 1], [1, 1, 0, 1, 1, 0], [-1, 1, 0, 1, 0, 0]], np.float32)
+    qi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    qm = P.Mesh(ctx, vertices=quad, indices=qi)
+    p1.render_mesh(sr.TRIANGLE, qm).run_to_fragment(vp, sr.VS_PASSTHROUGH).run(sr.FS_TEXTURE_UNLIT)
+    ofb2 = oracle_fb(size, size)
+    od2 = ob.OracleDraw(sr.TRIANGLE, qi)
+    od2.vertex_run_to_fragment(vp, sr.VS_PASSTHROUGH, u, quad)
+    od2.fragment_run(ofb2, sr.FS_TEXTURE_UNLIT, u, texture=normals, sampler=(sr.FILTER_BILINEAR, sr.EDGE_CLAMP, None))
+    H.compare_framebuffers(fb1.download(), ofb2, exact_color=True, what="second pass over the normal plane")
+    for x in (p1, qm, fb1, pipe, gmesh, fb):
+        x.destroy()
+
+
 def test_user_blend_function_additive(P, ctx):
     """A third registered blend, the stand-in for a user's GenericBlend::new(|a, b| a + b) (src/color/blend.rs:57-76; recipe in
     INTEGRATION.md): strictly ordered path, triangles + antialiased lines + points, colours bit-exact (f32 addition is not
