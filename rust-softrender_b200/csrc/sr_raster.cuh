@@ -1723,7 +1723,8 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
 // =====================================================================================================
 // Ordered tile rasteriser: any blend, stencil, discarding shaders, lines and points.  Strictly in
 // submission order per pixel.  Tile colour, depth, stencil (and winner) live in shared memory; each
-// warp owns a band of tile rows, so all operations on a pixel are issued by one warp in program order.
+// warp owns a fixed set of tile rows, so all operations on a pixel are issued by one warp in program order
+// (triangles: row r belongs to warp r % 8; lines and points, which run after a CTA barrier: bands of 4 consecutive rows).
 // =====================================================================================================
 // Everything the per-pixel loop needs of one triangle, produced once (one thread per triangle, 256 at a time) so that the
 // strictly ordered sweep -- a serial chain by construction -- contains no dependent global loads and no reciprocal.
@@ -1739,6 +1740,9 @@ static_assert(sizeof(SrOrdSetup) == 112, "seven float4");
 #define SR_ORD_LIST_CAP 2048  // group ids sorted in shared memory; longer lists are sorted in place in HBM
 #ifndef SR_ORD_LANE_BOX
 #define SR_ORD_LANE_BOX 20  // a band's batch takes the lane-per-triangle sweep when 7 of 8 of its (untightened, band-clipped) boxes are at most this
+#endif
+#ifndef SR_ORD_IL_ROWS
+#define SR_ORD_IL_ROWS 5  // a batch whose (tile-clipped) boxes average at most this many rows interleaves the row ownership (k_tile_ordered)
 #endif
 #ifndef SR_ORD_LANE_PIX
 #define SR_ORD_LANE_PIX 32  // largest (tightened, band-clipped) box a single lane sweeps in k_tile_ordered's small-triangle runs
@@ -2070,13 +2074,15 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
     uint32_t *s_list = reinterpret_cast<uint32_t *>(s_setup + SR_RASTER_THREADS);
     uint4 *s_ring = reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + (threadIdx.x >> 5) * SR_ORD_RING;
     uint8_t *s_stencil = reinterpret_cast<uint8_t *>(reinterpret_cast<uint4 *>(s_list + SR_ORD_LIST_CAP) + SR_RASTER_WARPS * SR_ORD_RING);
-    __shared__ uint32_t s_wcount[SR_RASTER_WARPS];
+    __shared__ uint32_t s_wcount[SR_RASTER_WARPS], s_wrows[SR_RASTER_WARPS];
     __shared__ uint32_t s_claim[SR_RASTER_WARPS][SR_ORD_BAND * SR_TILE_W];  // per warp: bids for the pixels of its band (sr_ord_lines_chunk)
     __shared__ uint8_t s_wband[SR_RASTER_WARPS][SR_RASTER_WARPS];     // [warp][band]: hits of that warp's group crossing the band
     __shared__ uint8_t s_band[SR_RASTER_WARPS][SR_RASTER_THREADS];  // per band: compacted record indices, in list order
 
     constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     constexpr uint32_t RH = SR_TILE_H / SR_RASTER_WARPS;  // tile rows owned by each warp
+    constexpr uint32_t NW = SR_RASTER_WARPS;
+    static_assert((NW & (NW - 1)) == 0 && RH * SR_TILE_W <= SR_ORD_BAND * SR_TILE_W, "triangles: row r of the tile belongs to warp r % NW");
     static_assert(SR_TILE_H % SR_RASTER_WARPS == 0, "tile height must split evenly over the warps");
 
     const uint32_t tile = p.shard_rank + blockIdx.x * p.shard_world;
@@ -2215,15 +2221,36 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             // Compaction in list order (ballot + warp counts) and, per band of rows, the ordered list of the hits that cross
             // it: a warp then visits only the triangles of its own band instead of scanning every record of the batch.
             const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            uint32_t bandmask = 0;  // bands (= warps) this triangle's rows cross
+            const uint32_t rows_w = __reduce_add_sync(0xffffffffu, hit ? (su.by >> 16) - (su.by & 0xffffu) + 1u : 0u);
+            if (lane == 0) { s_wcount[warp] = __popc(mask); s_wrows[warp] = rows_w; }
+            __syncthreads();
+            uint32_t base = 0, total = 0, rows_total = 0;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) {
+                const uint32_t cnt = s_wcount[w2];
+                if (w2 < warp) base += cnt;
+                total += cnt;
+                rows_total += s_wrows[w2];
+            }
+            // Row ownership of this batch (CTA-uniform; batches are separated by barriers, so it may change from one to the next):
+            // contiguous bands of RH rows, or -- when the batch's triangles are only a few rows high -- row r belongs to warp
+            // r % NW.  The consecutive small triangles of a batch lie in a few neighbouring rows, which contiguous bands would hand
+            // to one or two warps while the others wait at the barrier; tall triangles would be visited by every warp instead.
+            const bool interleave = rows_total <= SR_ORD_IL_ROWS * total;
+            const uint32_t rstep = interleave ? NW : 1u;
+            uint32_t bandmask = 0;  // warps whose rows this triangle's box crosses
             if (hit) {
-                const uint32_t b0 = ((su.by & 0xffffu) - y0) / RH, b1 = ((su.by >> 16) - y0) / RH;
-                bandmask = ((2u << b1) - 1u) & ~((1u << b0) - 1u);
+                const uint32_t lo = (su.by & 0xffffu) - y0, hi = (su.by >> 16) - y0;
+                if (interleave) {
+                    const uint32_t nrow = hi - lo + 1, m = nrow >= NW ? (1u << NW) - 1u : (1u << nrow) - 1u, sh = lo % NW;
+                    bandmask = ((m << sh) | (m >> (NW - sh))) & ((1u << NW) - 1u);
+                } else {
+                    bandmask = ((2u << (hi / RH)) - 1u) & ~((1u << (lo / RH)) - 1u);
+                }
             }
             uint32_t bm[SR_RASTER_WARPS];
 #pragma unroll
             for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b) bm[b] = __ballot_sync(0xffffffffu, (bandmask >> b) & 1u);
-            if (lane == 0) s_wcount[warp] = __popc(mask);
             if (lane < SR_RASTER_WARPS) {
                 uint32_t mine = 0;
 #pragma unroll
@@ -2231,13 +2258,6 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 s_wband[warp][lane] = (uint8_t)__popc(mine);
             }
             __syncthreads();
-            uint32_t base = 0, total = 0;
-#pragma unroll
-            for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) {
-                const uint32_t cnt = s_wcount[w2];
-                if (w2 < warp) base += cnt;
-                total += cnt;
-            }
             const uint32_t at = base + __popc(mask & ((1u << lane) - 1u));
             if (hit) {
                 s_setup[at] = su;
@@ -2253,7 +2273,18 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
 #pragma unroll
             for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) nband += s_wband[w2][warp];
             __syncthreads();
-            const uint32_t ry_lo = y0 + warp * RH, ry_hi = ry_lo + RH - 1;
+            // the rows of [ylo, yhi] (frame coordinates, inside the tile) this warp owns: first, first + rstep, ...; returns their number
+            auto own_rows = [&](uint32_t ylo, uint32_t yhi, uint32_t &first) -> uint32_t {
+                if (interleave) {
+                    first = ylo + ((warp - (ylo - y0)) & (NW - 1u));
+                    return first <= yhi ? (yhi - first) / NW + 1u : 0u;
+                }
+                first = max(ylo, y0 + warp * RH);
+                const uint32_t last = min(yhi, y0 + warp * RH + RH - 1);
+                return first <= last ? last - first + 1u : 0u;
+            };
+            // index of an owned row among the warp's RH rows (the warp's bidding words, sr_ord_lines_chunk's layout)
+            auto own_row_index = [&](uint32_t py) -> uint32_t { return interleave ? (py - y0) / NW : (py - y0) - warp * RH; };
             if (!SrFsInfo<FS>::DISCARDS) {
                 // Deferred shading.  Whether a fragment passes depends only on coverage, z and the depth left by earlier
                 // fragments of its pixel (the shader cannot discard), so the in-order sweep only runs the cheap part --
@@ -2328,7 +2359,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     for (uint32_t k = lane; k < nband; k += 32) {
                         const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s_band[warp][k]].bx);
                         const uint32_t bw = (box.x >> 16) - (box.x & 0xffffu) + 1;
-                        const uint32_t bh = min(box.y >> 16, ry_hi) - max(box.y & 0xffffu, ry_lo) + 1;
+                        uint32_t first;
+                        const uint32_t bh = own_rows(box.y & 0xffffu, box.y >> 16, first);
                         nsmall += bw * bh <= SR_ORD_LANE_BOX ? 1u : 0u;
                     }
                     nsmall = __reduce_add_sync(0xffffffffu, nsmall);
@@ -2344,8 +2376,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                             s = s_band[warp][k + lane];
                             const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                             minx = box.x & 0xffffu;
-                            r0 = max(box.y & 0xffffu, ry_lo);
-                            uint32_t maxx = box.x >> 16, r1 = min(box.y >> 16, ry_hi);
+                            uint32_t maxx = box.x >> 16, ylo = box.y & 0xffffu, yhi = box.y >> 16;
                             // candidate tightening (proof above sr_tightening_applies): the pixels outside the tightened range
                             // fail the reference's own coverage test, and without an active stencil nothing else looks at them
                             const SrOrdSetup &q = s_setup[s];
@@ -2354,12 +2385,12 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                             bool empty = false;
                             if (sr_tightening_applies(xmin, xmax, ymin, ymax, q.f.z)) {
                                 const int lx = max((int)minx, sr_tight_lo(xmin)), hx = min((int)maxx, sr_tight_hi(xmax));
-                                const int ly = max((int)r0, sr_tight_lo(ymin)), hy = min((int)r1, sr_tight_hi(ymax));
+                                const int ly = max((int)ylo, sr_tight_lo(ymin)), hy = min((int)yhi, sr_tight_hi(ymax));
                                 empty = lx > hx || ly > hy;
-                                if (!empty) { minx = (uint32_t)lx; maxx = (uint32_t)hx; r0 = (uint32_t)ly; r1 = (uint32_t)hy; }
+                                if (!empty) { minx = (uint32_t)lx; maxx = (uint32_t)hx; ylo = (uint32_t)ly; yhi = (uint32_t)hy; }
                             }
-                            bw = empty ? 0u : maxx - minx + 1;
-                            bh = empty ? 0u : r1 - r0 + 1;
+                            bh = empty ? 0u : own_rows(ylo, yhi, r0);  // (r0: the first owned row; box row j is frame row r0 + j * rstep)
+                            bw = bh == 0 ? 0u : maxx - minx + 1;
                             small = bw * bh <= SR_ORD_LANE_PIX;
                         }
                         const uint32_t smallmask = __ballot_sync(0xffffffffu, small);
@@ -2376,11 +2407,12 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                             const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
                             const uint32_t canonical = q.canonical;
                             uint32_t rem = 0;  // box positions (row-major) whose fragment is still to be applied
-                            if (mine && bw != 0)
-                                sr_raster_box<false>(tr, z1, z2, z3, minx, r0, bw, bh, 0u, [&](uint32_t px, uint32_t py, unsigned long long) {
-                                    rem |= 1u << ((py - r0) * bw + (px - minx));
-                                });
-                            const uint32_t cbase = (r0 - ry_lo) * SR_TILE_W + (minx - x0);  // box origin inside the band
+                            if (mine)
+                                for (uint32_t j = 0; j < bh; ++j)  // (one row per call: the owned rows may be NW apart)
+                                    sr_raster_box<false>(tr, z1, z2, z3, minx, r0 + j * rstep, bw, 1u, 0u, [&](uint32_t px, uint32_t, unsigned long long) {
+                                        rem |= 1u << (j * bw + (px - minx));
+                                    });
+                            const uint32_t cbase = own_row_index(r0) * SR_TILE_W + (minx - x0);  // box origin among the warp's rows
                             while (__any_sync(0xffffffffu, rem != 0)) {
                                 ++claim_round;
                                 const uint32_t bid = (claim_round << 8) | (255u - lane);
@@ -2402,7 +2434,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                                     if (todo) {
                                         const uint32_t i = (uint32_t)__ffs(todo) - 1u;
                                         todo &= todo - 1;
-                                        const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                                        const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
                                         li = (py - y0) * SR_TILE_W + (px - x0);
                                         sr_tri_bary(tr, px, py, u, v, w);  // (covered: the same arithmetic as pass A)
                                         const float z = sr_bary(u, z1, v, z2, w, z3);
@@ -2430,7 +2462,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     --ncoop;
                     const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                     const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
-                    const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
+                    uint32_t r0;
+                    const uint32_t nrows = own_rows(box.y & 0xffffu, box.y >> 16, r0);
                     const SrOrdSetup &q = s_setup[s];
                     SrTri tr;
                     tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
@@ -2438,14 +2471,14 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
                     tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
                     const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
-                    const uint32_t bw = maxx - minx + 1, npix = bw * (r1 - r0 + 1), canonical = q.canonical;
+                    const uint32_t bw = maxx - minx + 1, npix = bw * nrows, canonical = q.canonical;
                     for (uint32_t base = 0; base < npix; base += 32) {
                         const uint32_t i = base + lane;
                         bool pass = false;
                         uint32_t li = 0;
                         float u = 0.0f, v = 0.0f, w;
                         if (i < npix) {
-                            const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                            const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
                             li = (py - y0) * SR_TILE_W + (px - x0);
                             if (sr_ord_stencil_step(c, li) && sr_tri_bary(tr, px, py, u, v, w)) {
                                 const float z = sr_bary(u, z1, v, z2, w, z3);
@@ -2471,7 +2504,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 const uint32_t s = s_band[warp][k];
                 const uint2 box = *reinterpret_cast<const uint2 *>(&s_setup[s].bx);
                 const uint32_t minx = box.x & 0xffffu, maxx = box.x >> 16;
-                const uint32_t r0 = max(box.y & 0xffffu, ry_lo), r1 = min(box.y >> 16, ry_hi);
+                uint32_t r0;
+                const uint32_t nrows = own_rows(box.y & 0xffffu, box.y >> 16, r0);
                 const SrOrdSetup &q = s_setup[s];
                 SrTri tr;
                 tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
@@ -2479,11 +2513,11 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
                 tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
                 const float4 A = q.A, B = q.B, C = q.C;
-                const uint32_t bw = maxx - minx + 1, npix = bw * (r1 - r0 + 1);
+                const uint32_t bw = maxx - minx + 1, npix = bw * nrows;
                 const SrVertexSet *vs = q.second ? &p.tris.vs1 : &p.tris.vs0;
                 const uint32_t vi0 = q.vi[0], vi1 = q.vi[1], vi2 = q.vi[2], canonical = q.canonical;
                 for (uint32_t i = lane; i < npix; i += 32) {
-                    const uint32_t px = minx + i % bw, py = r0 + i / bw;
+                    const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
                     const uint32_t li = (py - y0) * SR_TILE_W + (px - x0);
                     if (!sr_ord_stencil_step(c, li)) continue;
                     float u, v, w;
