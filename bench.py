@@ -240,7 +240,7 @@ def bind_to_gpu_numa_node(local_rank: int):
         return f"unbound ({type(e).__name__})"
 
 
-def other_configs(ctx):
+def other_configs(ctx, headline=None):
     """Single-stream frame times of the other BASELINE configs on the same box (reported beside the headline, not part of it):
     config 1 (Suzanne 1024x1024, examples/suzanne.rs path) and config 2 as composed in SURVEY.md 8d (three Suzanne instances
     at 1920x1080, textured 4-light shader, alpha_over blend, then the face-normal line pass with the green shader)."""
@@ -297,6 +297,14 @@ def other_configs(ctx):
 
     out["config2_full_example_1080p_us_per_frame"] = per_frame_us(full_example, 32)
     out["config2_composition"] = "3 x 968 triangles, textured 4-light shader, alpha_over; then 3 x 968 face-normal lines, green shader"
+    # the same frame with the twice-subdivided instances BASELINE's config 2 names (3 x 15,488 triangles; tests/test_gpu_sizes_full.py
+    # compares this frame with the oracle)
+    gm_hi = P.Mesh(ctx, scenes.subdivide(mesh, 2))
+    gm_lo, gm = gm, gm_hi
+    out["config2_subdivided_1080p_us_per_frame"] = per_frame_us(full_example, 16)
+    out["config2_subdivided_composition"] = "3 x 15,488 triangles, textured 4-light shader, alpha_over; then 3 x 15,488 face-normal lines"
+    gm = gm_lo
+    gm_hi.destroy()
 
     # render-to-texture: the config-2 frame above sampled in place by a full-screen second pass
     # (2 triangles through the passthrough vertex shader, texture_unlit, Bilinear + Clamp) into a second 1920x1080 target
@@ -338,6 +346,18 @@ def other_configs(ctx):
     out["config5_note"] = "bench.py --config turntable measures the same batch with four frames in flight, with read-back, and across GPUs"
     for x in (pipe, gm, fb):
         x.destroy()
+
+    # the strictly ordered path at scale: the headline frame (config 3: 10 M triangles at 3840x2160) drawn with alpha_over
+    if headline is not None:
+        hfb, hpipe, hmesh, hvp, ntris = headline
+
+        def ordered():
+            hfb.clear(CLEAR)
+            hpipe.render_mesh(sr.TRIANGLE, hmesh).run_to_fragment(hvp, sr.VS_SUZANNE).with_blend(sr.BLEND_ALPHA_OVER).run(sr.FS_SUZANNE)
+
+        us = per_frame_us(ordered, 8)
+        out["config3_alpha_over_ordered_ms_per_frame"] = us / 1e3
+        out["config3_alpha_over_ordered_Mtris_per_s"] = ntris / us
 
     # config 4 on ONE GPU (the yardstick of the tile-sharded runs at N > 1): 100 M sub-pixel triangles at 7680x4320
     try:
@@ -764,7 +784,7 @@ def run_ours(args):
             line["sharded_config4"] = sharded4
         if world == 1 and args.config == "grid10m" and not args.quick:
             try:
-                line["other_configs"] = other_configs(ctx)
+                line["other_configs"] = other_configs(ctx, (fb, pipe, gmesh, vp, mesh.ntris))
             except Exception as e:  # never let the side measurements take the headline line down
                 line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and not args.no_cpu_baseline and not args.quick:

@@ -499,6 +499,26 @@ def test_alpha_over_blend_in_order(P, ctx):
     H.compare_framebuffers(out, ofb, exact_color=True, what="alpha over")
 
 
+@pytest.mark.parametrize("blend", [sr.BLEND_ALPHA_OVER, sr.BLEND_ADDITIVE])
+@pytest.mark.parametrize("max_size,n,integer_depth,stencil", [(1.2, 300_000, False, False), (2.5, 100_000, True, False),
+                                                               (2.5, 100_000, False, True), (5.0, 40_000, False, False)])
+def test_ordered_blend_of_pixel_sized_triangles(P, ctx, blend, max_size, n, integer_depth, stencil):
+    """Blended meshes of pixel-sized triangles take k_tile_ordered's lane-per-triangle sweep (one triangle per lane, bidding
+    rounds for the pixels two triangles of a run share) and, batch by batch, interleaved or contiguous row ownership.  Random
+    positions in random order, several fragments per covered pixel: the triangles of a run overlap all the time, every pixel sees several
+    blended fragments, and f32 blending is not associative -- any fragment applied out of submission order shows.  With
+    integer depths ties are everywhere (`d >= dt`, triangle.rs:126); a stencil attachment with the default config must not
+    change the path's result.  Winner plane, depth and colours bit-exact (power-free shader)."""
+    rng = np.random.default_rng(int(max_size * 10) + n + blend)
+    w, h = 330, 200  # 6 x 7 tiles, partial tiles at the right and bottom edges
+    verts = H.random_screen_triangles(rng, n, w, h, max_size=max_size, integer_depth=integer_depth, margin=0.02)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    out, win, _, ofb = run_both_screen(P, ctx, w, h, verts, idx, blend=blend, stencil=stencil, stencil_value=1 if stencil else None)
+    assert np.array_equal(win, ofb.winner)
+    H.compare_framebuffers(out, ofb, exact_color=True, what="ordered blend of pixel-sized triangles")
+    assert (ofb.winner != 0).mean() > 0.4
+
+
 def test_ordered_list_arena_overflow_is_replayed(P, ctx):
     """The ordered path enqueues its bin fill and tile pass against the current capacity of its group-list arenas
     without a host synchronisation; with 2-entry arenas both skip themselves on the device and are replayed with larger
@@ -1050,6 +1070,31 @@ def test_grid_scene_reduced(P, ctx, reverse):
     od.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices).fragment_run(ofb, sr.FS_SUZANNE, u)
     assert np.array_equal(fb.download_winner(), ofb.winner)
     H.compare_framebuffers(fb.download(), ofb, color_tol=COLOR_TOL, what="grid")
+    for x in (pipe, gmesh, fb):
+        x.destroy()
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("cells", [(125, 100), (250, 200)])
+def test_grid_scene_reduced_blended_in_order(P, ctx, reverse, cells):
+    """The same generator drawn with the additive blend (strictly ordered path): a coherent mesh of pixel-sized triangles is
+    what k_tile_ordered's lane-per-triangle sweep and per-batch interleaved row ownership are for.  The flat shader returns
+    the interpolated world position, so colours are sums of f32 values in submission order: bit-exact, and back to front
+    (`reverse`) every layer passes the depth test and contributes."""
+    w, h = 960, 540
+    mesh = scenes.make_grid(*cells, 4, seed=0x5EED0003, reverse=reverse)
+    u = scenes.grid_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.1, 100.0)
+    fb = make_fb(P, ctx, w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    gmesh = P.Mesh(ctx, mesh)
+    pipe.render_mesh(sr.TRIANGLE, gmesh).run_to_fragment(vp, sr.VS_SUZANNE).with_blend(sr.BLEND_ADDITIVE).run(sr.FS_FLAT)
+    ofb = oracle_fb(w, h)
+    od = ob.OracleDraw(sr.TRIANGLE, mesh.indices)
+    od.blend = sr.BLEND_ADDITIVE
+    od.vertex_run_to_fragment(vp, sr.VS_SUZANNE, u, mesh.vertices).fragment_run(ofb, sr.FS_FLAT, u)
+    assert np.array_equal(fb.download_winner(), ofb.winner)
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="blended grid")
     for x in (pipe, gmesh, fb):
         x.destroy()
 
