@@ -1259,6 +1259,9 @@ __global__ void __launch_bounds__(256) k_large_fill(const uint32_t *large_count,
 #ifndef SR_OPQ_THREADS
 #define SR_OPQ_THREADS 256
 #endif
+#ifndef SR_OPQ_SKIP_EMPTY
+#define SR_OPQ_SKIP_EMPTY 1
+#endif
 #ifndef SR_OPQ_MIN_CTAS
 #define SR_OPQ_MIN_CTAS 4
 #endif
@@ -1342,6 +1345,16 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
         if (tid < SR_TILE_H) sr_bulk_g2s(keys + tid * SR_TILE_W, p.vis + sr_vis_index(x0, y0 + tid, p.fb.ntx), SR_TILE_W * 8, bar);
         if (p.reset_vis && tid < SR_TILE_W) far_row[tid] = SR_VIS_FAR_KEY;
         sr_mbar_wait(bar, 0);
+        if (SR_OPQ_SKIP_EMPTY && PHASE != 1 && L == 0 && (PHASE != 2 || p.npeers == 0)) {
+            // Nothing was drawn on this tile (config 3 covers 44 % of the frame) and its keys are "far" already: no keys to hand
+            // back, no per-pixel pass -- the clear goes out with 16-byte stores, or nothing at all when the contents stay.
+            uint32_t any = 0;
+            for (uint32_t i = tid; i < SR_TILE_PIXELS; i += SR_OPQ_THREADS) any |= keys[i] != SR_VIS_FAR_KEY ? 1u : 0u;
+            if (__syncthreads_or((int)any) == 0) {
+                if (p.fb.pending_clear && !(PHASE == 2 && p.elide_clear)) sr_fill_tile_clear(p.fb, x0, y0);
+                return;
+            }
+        }
         if (p.reset_vis) {
             // the keys are on chip: hand the visibility buffer back all-far, so the next cleared frame needs no init pass
             sr_fence_proxy_async();
