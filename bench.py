@@ -225,12 +225,33 @@ def bind_to_gpu_numa_node(local_rank: int):
         dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
         path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
         node = int(open(path).read().strip())
+
+        def parse_cpulist(text):
+            cpus = set()
+            for part in text.strip().split(","):
+                lo, _, hi = part.strip().partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            return cpus
+
         if node < 0:
-            return "numa node unknown"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+            # sysfs carries no node for the device (virtualised PCI topology): ask the driver -- the "CPU Affinity" column of
+            # `nvidia-smi topo -m` for this GPU's row
+            try:
+                import re
+                text = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+                rows = re.sub(r"\x1b\[[0-9;]*m", "", text).splitlines()  # (the header cells are underlined with escape codes)
+                head = next(r for r in rows if "CPU Affinity" in r)
+                col = [c.strip() for c in head.split("\t")].index("CPU Affinity")
+                row = next(r for r in rows if r.startswith(f"GPU{local_rank}\t") or r.startswith(f"GPU{local_rank} "))
+                cell = [c.strip() for c in row.split("\t")][col]
+                cpus = parse_cpulist(cell) & os.sched_getaffinity(0)
+                if cpus and cpus != os.sched_getaffinity(0):
+                    os.sched_setaffinity(0, cpus)
+                    return f"nvidia-smi topo cpu affinity {cell} ({len(cpus)} cpus)"
+                return f"numa node unknown (sysfs -1; nvidia-smi topo cpu affinity '{cell}' = every allowed cpu: one node)"
+            except Exception as e:
+                return f"numa node unknown (sysfs -1; nvidia-smi topo: {type(e).__name__})"
+        cpus = parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return f"numa node {node}: no allowed cpus"
