@@ -382,6 +382,8 @@ def other_configs(ctx, headline=None):
 
     # config 4 on ONE GPU (the yardstick of the tile-sharded runs at N > 1): 100 M sub-pixel triangles at 7680x4320
     try:
+        if os.environ.get("SR_NO_CONFIG4"):
+            raise RuntimeError("skipped (SR_NO_CONFIG4)")
         w4, h4, mesh4, u4, vp4 = build_scene("grid100m")
         fb = P.RenderBuffer.with_dimensions(ctx, w4, h4)
         pipe = P.Pipeline.from_framebuffer(fb, u4)

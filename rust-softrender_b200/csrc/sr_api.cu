@@ -276,6 +276,10 @@ struct sr_draw {
     VertexStream gen[3];        // generated points, lines, tris
     Buf tri_seq;                // literal sequence number of each generated triangle (null = identity)
     uint32_t tri_literal_total = 0;
+    // clip_primitives without a host synchronisation (small meshes): gen[2] is sized for the clipper's worst case, the unused
+    // tail of its positions is NaN, and the true numbers {kept, literal} of output triangles live here, on the device, until
+    // somebody needs them on the host (resolve_tri_count)
+    Buf tri_count_dev;
     // FragmentShader builder state (fragment.rs:45-56)
     uint32_t cull = SR_CULL_NONE, blend = SR_BLEND_REPLACE, aa_lines = 0;
     uint32_t tile_w = 128, tile_h = 128;  // DEFAULT_TILE_SIZE (fragment.rs:29); accepted, not used
@@ -287,6 +291,9 @@ struct sr_draw {
 };
 
 static uint32_t nplanes_of(uint32_t nk) { return (nk + 3) / 4; }
+// the one host synchronisation clip_primitives skipped, for the callers that need the counts on the host (introspection, a second
+// geometry pass, draws that also carry lines or points -- their canonical numbers follow the literal triangle count)
+static int resolve_tri_count(sr_draw *d);
 
 // ---------------------------------------------------------------------------------------------------------
 // helpers
@@ -421,7 +428,7 @@ static int build_bins(sr_context *c, const sr_framebuffer *fb, const SrPrimSourc
     p.tile_count = b->count->as<uint32_t>();
     b->grid = ceil_div(nprims, 256);
     b->nv = NV;
-    if (!exact && nprims <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
+    if (!exact && nprims <= (src.n1_dev ? SR_BIN_SMALL_MAX_TRIS_DEV : SR_BIN_SMALL_MAX_TRIS) && ntiles <= SR_BIN_SMALL_MAX_TILES) {
         // small draw: rectangles, counts, scan and fill in one single-CTA launch (no memset, no separate scan / fill)
         Buf &arena = c->ord_arena[NV - 1];
         if (!arena) {
@@ -477,6 +484,7 @@ static SrPrimSource prim_source(const sr_draw *d, uint32_t kind /*1 point,2 line
     s.vs1 = g.set();
     s.n1 = (uint32_t)(g.n / kind);
     s.seq1 = (kind == 3 && d->tri_seq) ? d->tri_seq->as<uint32_t>() : nullptr;
+    s.n1_dev = (kind == 3 && d->tri_count_dev) ? d->tri_count_dev->as<uint32_t>() : nullptr;
     return s;
 }
 
@@ -696,7 +704,8 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
     if (ranged_eligible(c, fb, tp, extra)) return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep, d);
     if (d) SR_TRY(materialize_vertices(d));
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
-    if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_BIN_SMALL_MAX_TRIS && ntiles <= SR_BIN_SMALL_MAX_TILES) {
+    if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= (tp.tris.n1_dev ? SR_BIN_SMALL_MAX_TRIS_DEV : SR_BIN_SMALL_MAX_TRIS) &&
+        ntiles <= SR_BIN_SMALL_MAX_TILES) {
         record(c, 7);
         auto q = std::make_unique<PendingOpaque>();
         SR_TRY(c->alloc((size_t)(ntiles + 1) * 4, &q->off));
@@ -866,6 +875,18 @@ static int launch_vertex(sr_context *c, sr_draw *d, uint32_t vs, const SrVsConst
     return SR_OK;
 }
 // a recorded (lazy) vertex stage becomes vertices: the whole mesh, for every consumer but the range-sharded fragment stage
+static int resolve_tri_count(sr_draw *d) {
+    if (!d->tri_count_dev) return SR_OK;
+    sr_context *c = d->pipeline->ctx;
+    SR_CUDA(cudaSetDevice(c->device));
+    uint32_t host[2] = {0, 0};
+    SR_CUDA(cudaMemcpyAsync(host, d->tri_count_dev->ptr, 8, cudaMemcpyDeviceToHost, c->stream));
+    SR_CUDA(cudaStreamSynchronize(c->stream));
+    d->gen[2].n = (uint64_t)host[0] * 3;  // (the streams stay allocated for the worst case; the NaN tail is simply no longer looked at)
+    d->tri_literal_total = host[1];
+    d->tri_count_dev.reset();
+    return SR_OK;
+}
 static int materialize_vertices(sr_draw *d) {
     if (!d->vertex_lazy) return SR_OK;
     d->vertex_lazy = false;
@@ -1135,7 +1156,7 @@ static int opaque_triangles_ranged(sr_context *c, sr_framebuffer *fb, const SrTi
 static int launch_bin_small(sr_context *c, PendingOpaque *q) {
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
-        SR_CUDA(cudaFuncSetAttribute(k_bin_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (SR_BIN_SMALL_MAX_TILES + SR_BIN_SMALL_MAX_TRIS) * 4));
+        SR_CUDA(cudaFuncSetAttribute(k_bin_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (SR_BIN_SMALL_MAX_TILES + SR_BIN_SMALL_MAX_TRIS_DEV) * 4));
         configured[c->device & 15] = true;
     }
     // per-tile counters + one tile rectangle per triangle (whole rounds of SR_BIN_SMALL_THREADS)
@@ -2158,6 +2179,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
     sr_pipeline *p = d->pipeline;
     sr_context *c = p->ctx;
     SR_CUDA(cudaSetDevice(c->device));
+    SR_TRY(resolve_tri_count(d));  // (a second geometry pass over the output of an unsynchronised clip)
     const uint32_t np = nplanes_of(d->nk);
     auto geo_in = [&](uint32_t kind, bool with_gen, bool with_idx) {
         SrGeoIn in;
@@ -2175,7 +2197,7 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
         return in;
     };
     VertexStream npoints, nlines, ntris;
-    Buf nseq;
+    Buf nseq, count_dev;
     uint32_t literal_total = 0;
     if (gs == SR_GS_CLIP || gs == SR_GS_CLIP_SH) {
         SR_TRY(clip_small<1>(c, geo_in(1, true, true), d->nk, &npoints));
@@ -2199,6 +2221,25 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             const uint32_t grid = ceil_div(n, 128);
             SR_LAUNCH(c, k_clip_tri_count, grid, 128, 0, tin, drop, kept->as<uint32_t>(), lit->as<uint32_t>());
             // both scans are enqueued before the one synchronisation that sizes the output stream
+            // Small meshes (a model of a thousand triangles: configs 1, 2 and 5) do not synchronise at all -- the round trip to the
+            // host was 40 of a Suzanne frame's 111 us.  The literal clipper emits at most 34 triangles per input triangle (a polygon of
+            // at most 36 entries, geometry.rs:265-298), so the output stream is sized for that, its positions are pre-filled with NaN
+            // (every consumer skips a NaN primitive) and the true counts stay on the device (sr_draw::tri_count_dev): the kernels that
+            // walk the stream read them there, the host only ever uses the bound.  Draws that also carry points or lines keep the
+            // synchronisation (their canonical numbers follow the literal triangle count).
+            static const bool force_sync = getenv("SR_CLIP_SYNC") != nullptr;  // A/B switch
+            if (!force_sync && n <= 1024u && n * 34u <= SR_BIN_SMALL_MAX_TRIS_DEV && npoints.n == 0 && nlines.n == 0 && c->shard_world == 1) {
+                const uint32_t bound = n * 34u;
+                SR_TRY(c->alloc(8, &count_dev));
+                SR_LAUNCH(c, k_scan_pair_small, 1, SR_SCAN_THREADS, 0, kept->as<uint32_t>(), lit->as<uint32_t>(), n, kept_off->as<uint32_t>(),
+                          lit_off->as<uint32_t>(), count_dev->as<uint32_t>());
+                SR_TRY(alloc_stream(c, (uint64_t)bound * 3, d->nk, &ntris));
+                SR_CUDA(cudaMemsetAsync(ntris.pos->ptr, 0xFF, (size_t)bound * 3 * sizeof(float4), c->stream));  // NaN positions
+                SR_TRY(c->alloc((size_t)bound * 4, &nseq));
+                SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.np};
+                SR_LAUNCH(c, k_clip_tri_emit, grid, 128, 0, tin, drop, kept_off->as<uint32_t>(), lit_off->as<uint32_t>(), o, nseq->as<uint32_t>());
+                goto clipped;
+            }
             if (n <= SR_SCAN_BLOCK) {
                 Buf totals;
                 SR_TRY(c->alloc(8, &totals));
@@ -2255,10 +2296,12 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
         }
         SR_TRY(alloc_stream(c, 0, d->nk, &ntris));
     }
+clipped:
     d->gen[0] = npoints;
     d->gen[1] = nlines;
     d->gen[2] = ntris;
     d->tri_seq = nseq;
+    d->tri_count_dev = count_dev;
     d->tri_literal_total = literal_total;
     d->have_indexed = false;  // indexed_vertices: None (geometry.rs:250-257)
     d->indexed = VertexStream();
@@ -2365,6 +2408,10 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
         SR_TRY(materialize_clear(src));  // a recorded clear becomes pixels before they are sampled
     }
 
+    // an unsynchronised clip left the triangle counts on the device: fine for a draw of triangles on one GPU, everything else
+    // gets them to the host first (canonical numbers of lines / points follow the literal triangle count; tile-sharded contexts)
+    if (d->tri_count_dev && (d->gen[0].n || d->gen[1].n || (d->have_indexed && d->primitive != SR_TRIANGLE) || c->shard_world > 1 || c->shard))
+        SR_TRY(resolve_tri_count(d));
     SrTileParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.tris = prim_source(d, 3);
@@ -2423,7 +2470,7 @@ int sr_fragment_run(sr_draw *d, uint32_t fs) {
 
     if (owned) {
         std::vector<Buf> keep = {d->indices, d->indexed.pos, d->indexed.attr, d->gen[0].pos, d->gen[0].attr, d->gen[1].pos, d->gen[1].attr,
-                                 d->gen[2].pos, d->gen[2].attr, d->tri_seq};
+                                 d->gen[2].pos, d->gen[2].attr, d->tri_seq, d->tri_count_dev};
         if (p->texture) keep.push_back(p->texture->rgba);
         if (p->fb_texture && samples && p->fb_texture->aos_buf) keep.push_back(p->fb_texture->aos_buf);
         SrTileParams ordered = tp;
@@ -2501,17 +2548,19 @@ int sr_draw_set_generated(sr_draw *d, int which, const float *verts, uint64_t nv
     if (nk != d->nk) return sr_fail(SR_ERR_INVALID_ARGUMENT, "nk mismatch");
     if (d->stage == STAGE_VERTEX) return sr_fail(SR_ERR_INVALID_STATE, "run the vertex stage first");
     SR_TRY(upload_records(d->pipeline->ctx, verts, nverts, nk, &d->gen[which - 1]));
-    if (which == 3) { d->tri_seq.reset(); d->tri_literal_total = 0; }
+    if (which == 3) { d->tri_seq.reset(); d->tri_literal_total = 0; d->tri_count_dev.reset(); }
     return SR_OK;
 }
 int sr_draw_count(sr_draw *d, int which, uint64_t *nverts, uint32_t *nk) {
     if (!d || which < 0 || which > 3) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (which == 3) SR_TRY(resolve_tri_count(d));
     if (nverts) *nverts = which == 0 ? (d->have_indexed ? d->indexed.n : 0) : d->gen[which - 1].n;
     if (nk) *nk = d->nk;
     return SR_OK;
 }
 int sr_draw_download(sr_draw *d, int which, float *dst, uint64_t capacity_floats) {
     if (!d || which < 0 || which > 3 || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (which == 3) SR_TRY(resolve_tri_count(d));
     const VertexStream &s = which == 0 ? d->indexed : d->gen[which - 1];
     const uint64_t n = which == 0 ? (d->have_indexed ? s.n : 0) : s.n;
     if (n == 0) return SR_OK;
@@ -2528,6 +2577,7 @@ int sr_draw_download(sr_draw *d, int which, float *dst, uint64_t capacity_floats
 }
 int sr_draw_download_sequence(sr_draw *d, uint32_t *dst, uint64_t capacity) {
     if (!d || !dst) return sr_fail(SR_ERR_INVALID_ARGUMENT, "null");
+    SR_TRY(resolve_tri_count(d));
     const uint64_t n = d->gen[2].n / 3;
     if (capacity < n) return sr_fail(SR_ERR_INVALID_ARGUMENT, "capacity too small");
     if (n == 0) return SR_OK;
@@ -2591,6 +2641,7 @@ int sr_draw_bins(sr_draw *d, uint64_t *offsets, uint32_t *ids, uint64_t ids_capa
     sr_framebuffer *fb = p->fb;
     SR_CUDA(cudaSetDevice(c->device));
     SR_TRY(materialize_vertices(d));
+    SR_TRY(resolve_tri_count(d));
     const SrPrimSource src = prim_source(d, 3);
     const uint32_t ntris = src.n0 + src.n1, ntiles = fb->ntx * fb->nty;
     Bins b;

@@ -133,9 +133,17 @@ struct SrPrimSource {
     SrVertexSet vs1;          // segment 1: n1 primitives, vertices stored consecutively (NV per primitive)
     uint32_t n1;
     const uint32_t *seq1;     // optional: literal sequence number of each generated primitive
+    const uint32_t *n1_dev;   // optional: the number of generated primitives really present, in device memory.  n1 is then an upper
+                              // bound known to the host (clip_primitives without a host synchronisation: the output stream is sized
+                              // for the worst case and its unused tail holds NaN positions, which every consumer skips); kernels
+                              // that loop over the primitives read the true count so that they do not walk the tail
     uint32_t nplanes;
     uint32_t nk;
 };
+// number of primitives to walk (see n1_dev)
+__device__ __forceinline__ uint32_t sr_prim_count(const SrPrimSource &s) {
+    return s.n0 + (s.n1_dev != nullptr ? min(s.n1, __ldg(s.n1_dev)) : s.n1);
+}
 
 template <int NV>
 __device__ __forceinline__ void sr_prim_vertices(const SrPrimSource &s, uint32_t t, const SrVertexSet *&vs, uint32_t *vi) {

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_G_THREADS) k_bin_small_groups(con
     __shared__ uint32_t s_wsum[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ntiles = p.ntx * p.nty;
-    const uint32_t ngroups = (p.nprims + 31u) / 32u;
+    const uint32_t nprims = min(p.nprims, sr_prim_count(p.src));  // (the true count of a clip stage that did not synchronise)
+    const uint32_t ngroups = (nprims + 31u) / 32u;
     for (uint32_t i = tid; i < ntiles; i += SR_BIN_SMALL_G_THREADS) s_cnt[i] = 0;
     __syncthreads();
     __shared__ uint32_t s_bits[SR_BIN_SMALL_G_THREADS / 32][32];  // per warp: which tiles of the group's union rectangle are hit
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_G_THREADS) k_bin_small_groups(con
     constexpr uint32_t GW = SR_BIN_SMALL_G_THREADS / 32;  // groups in flight
     for (uint32_t g = warp; g < ngroups; g += GW) {
         const uint32_t t = g * 32 + lane;
-        const uint32_t rect = t < p.nprims ? sr_prim_rect<NV>(p, t) : SR_RECT_INVALID;
+        const uint32_t rect = t < nprims ? sr_prim_rect<NV>(p, t) : SR_RECT_INVALID;
         p.rects[t] = rect;  // (the array is padded to whole groups)
         place(rect, g, false);
     }
@@ -1017,6 +1018,7 @@ __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro
 // tile lists (the tile kernel's short-list sweep); the visibility buffer is not used.
 #define SR_BIN_SMALL_THREADS 1024
 #define SR_BIN_SMALL_MAX_TRIS 8192
+#define SR_BIN_SMALL_MAX_TRIS_DEV (34 * 1024)  // host-side bound of a draw whose true count (<= 1024 x the clipper's 34) lives on the device
 #define SR_BIN_SMALL_MAX_TILES 8192
 #define SR_BIN_SMALL_HUGE 256      // tiles
 #define SR_BIN_SMALL_MAX_HUGE 64
@@ -1036,7 +1038,8 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     // instruction cache -- unrolled eight times it was 11.6 k SASS instructions and most of its time was instruction fetch
     // (ncu: 24 of 30 stall cycles per issue `no_instruction`).  The rectangles wait for the fill phase in shared memory.
     uint32_t *s_rect = s_cnt + ntiles;  // [rounds * SR_BIN_SMALL_THREADS], each thread reads back only its own entries
-    const uint32_t rounds = (p.ntris + SR_BIN_SMALL_THREADS - 1) / SR_BIN_SMALL_THREADS;
+    const uint32_t ntris = min(p.ntris, sr_prim_count(p.src));  // (the true count of a clip stage that did not synchronise)
+    const uint32_t rounds = (ntris + SR_BIN_SMALL_THREADS - 1) / SR_BIN_SMALL_THREADS;
     // A lane walks its own triangle's tile rectangle when it is small (the usual case: a handful of tiles); a rectangle of
     // more than 16 tiles is spread over the lanes of the warp (a big triangle touches hundreds of tiles).
     const bool sharded = p.shard_world > 1;
@@ -1072,7 +1075,7 @@ __global__ void __launch_bounds__(SR_BIN_SMALL_THREADS) k_bin_small(const __grid
     for (uint32_t k = 0; k < rounds; ++k) {
         const uint32_t t = k * SR_BIN_SMALL_THREADS + tid;
         uint32_t rect = SR_RECT_INVALID;
-        if (t < p.ntris) {
+        if (t < ntris) {
             const SrVertexSet *vs;
             uint32_t vi[3];
             sr_prim_vertices<3>(p.src, t, vs, vi);
