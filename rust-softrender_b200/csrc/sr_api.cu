@@ -2213,6 +2213,24 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             // zero-area outputs of the literal clipper are dropped unless a stencil op could observe them
             const bool stencil_active = p->fb->stencil_buf && p->stencil_op != SR_STENCIL_KEEP;
             const uint32_t drop = stencil_active ? 0u : 1u;
+            // Small meshes (a model of a thousand triangles: configs 1 and 5) neither synchronise with the host nor take more than one
+            // launch -- the round trip was 18 of a Suzanne frame's 110 us, the chain count -> scan -> emit three of its launches.  The
+            // literal clipper emits at most 34 triangles per input triangle (a polygon of at most 36 entries, geometry.rs:265-298), so
+            // the output stream is sized for that, its positions are pre-filled with NaN (every consumer skips a NaN primitive) and the
+            // true counts stay on the device (sr_draw::tri_count_dev): the kernels that walk the stream read them there, the host only
+            // ever uses the bound.  Draws that also carry points or lines keep the synchronisation (their canonical numbers follow the
+            // literal triangle count).
+            static const bool force_sync = getenv("SR_CLIP_SYNC") != nullptr;  // A/B switch
+            if (!force_sync && n <= SR_CLIP_SMALL_MAX && n * 34u <= SR_BIN_SMALL_MAX_TRIS_DEV && npoints.n == 0 && nlines.n == 0 && c->shard_world == 1) {
+                const uint32_t bound = n * 34u;
+                SR_TRY(c->alloc(8, &count_dev));
+                SR_TRY(alloc_stream(c, (uint64_t)bound * 3, d->nk, &ntris));
+                SR_CUDA(cudaMemsetAsync(ntris.pos->ptr, 0xFF, (size_t)bound * 3 * sizeof(float4), c->stream));  // NaN positions
+                SR_TRY(c->alloc((size_t)bound * 4, &nseq));
+                SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.np};
+                SR_LAUNCH(c, k_clip_tri_small, 1, SR_CLIP_SMALL_MAX, 0, tin, drop, o, nseq->as<uint32_t>(), count_dev->as<uint32_t>());
+                goto clipped;
+            }
             Buf kept, lit, kept_off, lit_off;
             SR_TRY(c->alloc((size_t)n * 4, &kept));
             SR_TRY(c->alloc((size_t)n * 4, &lit));
@@ -2221,25 +2239,6 @@ int sr_geometry_run(sr_draw *d, uint32_t gs) {
             const uint32_t grid = ceil_div(n, 128);
             SR_LAUNCH(c, k_clip_tri_count, grid, 128, 0, tin, drop, kept->as<uint32_t>(), lit->as<uint32_t>());
             // both scans are enqueued before the one synchronisation that sizes the output stream
-            // Small meshes (a model of a thousand triangles: configs 1, 2 and 5) do not synchronise at all -- the round trip to the
-            // host was 40 of a Suzanne frame's 111 us.  The literal clipper emits at most 34 triangles per input triangle (a polygon of
-            // at most 36 entries, geometry.rs:265-298), so the output stream is sized for that, its positions are pre-filled with NaN
-            // (every consumer skips a NaN primitive) and the true counts stay on the device (sr_draw::tri_count_dev): the kernels that
-            // walk the stream read them there, the host only ever uses the bound.  Draws that also carry points or lines keep the
-            // synchronisation (their canonical numbers follow the literal triangle count).
-            static const bool force_sync = getenv("SR_CLIP_SYNC") != nullptr;  // A/B switch
-            if (!force_sync && n <= 1024u && n * 34u <= SR_BIN_SMALL_MAX_TRIS_DEV && npoints.n == 0 && nlines.n == 0 && c->shard_world == 1) {
-                const uint32_t bound = n * 34u;
-                SR_TRY(c->alloc(8, &count_dev));
-                SR_LAUNCH(c, k_scan_pair_small, 1, SR_SCAN_THREADS, 0, kept->as<uint32_t>(), lit->as<uint32_t>(), n, kept_off->as<uint32_t>(),
-                          lit_off->as<uint32_t>(), count_dev->as<uint32_t>());
-                SR_TRY(alloc_stream(c, (uint64_t)bound * 3, d->nk, &ntris));
-                SR_CUDA(cudaMemsetAsync(ntris.pos->ptr, 0xFF, (size_t)bound * 3 * sizeof(float4), c->stream));  // NaN positions
-                SR_TRY(c->alloc((size_t)bound * 4, &nseq));
-                SrGeoOut o = {ntris.pos->as<float4>(), ntris.attr->as<float4>(), ntris.np};
-                SR_LAUNCH(c, k_clip_tri_emit, grid, 128, 0, tin, drop, kept_off->as<uint32_t>(), lit_off->as<uint32_t>(), o, nseq->as<uint32_t>());
-                goto clipped;
-            }
             if (n <= SR_SCAN_BLOCK) {
                 Buf totals;
                 SR_TRY(c->alloc(8, &totals));

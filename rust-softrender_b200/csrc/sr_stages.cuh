@@ -546,6 +546,54 @@ __global__ void __launch_bounds__(128) k_clip_tri_emit(const SrGeoIn in, uint32_
     }
 }
 
+// Both passes and the scans between them for at most 1024 input triangles in ONE single-CTA launch (a model of a thousand
+// triangles: the chain of tiny dependent launches, not the work, is what such a frame costs).  totals = {kept, literal}.
+#define SR_CLIP_SMALL_MAX 1024
+__global__ void __launch_bounds__(SR_CLIP_SMALL_MAX) k_clip_tri_small(const SrGeoIn in, uint32_t drop_degenerate, SrGeoOut out, uint32_t *seq,
+                                                                      uint32_t *totals) {
+    __shared__ uint32_t ws[32];
+    const uint32_t t = threadIdx.x;
+    const bool have = t < in.ngen + in.nidx;
+    float rec[3][4 + SR_MAX_NK];
+    uint8_t poly[36];
+    int n = 0, nt = 0, k = 0;
+    if (have) {
+        sr_geo_load<3>(in, t, rec);
+        n = sr_clip_polygon(rec, poly);
+        nt = sr_clip_tri_count(n);
+        for (int i = 0; i < nt; ++i) {
+            uint8_t ids[3];
+            sr_clip_tri_ids(poly, n, i, ids);
+            if (!(drop_degenerate && sr_clip_tri_degenerate(ids))) ++k;
+        }
+    }
+    uint32_t total_kept, total_literal;
+    uint32_t o = sr_block_exclusive_scan((uint32_t)k, &total_kept, ws);
+    const uint32_t lbase = sr_block_exclusive_scan((uint32_t)nt, &total_literal, ws);
+    if (t == 0) { totals[0] = total_kept; totals[1] = total_literal; }
+    if (!have) return;
+    const uint32_t nfloats = 4 + in.nplanes * 4;
+    float tmp[4 + SR_MAX_NK];
+    for (int i = 0; i < nt; ++i) {
+        uint8_t ids[3];
+        sr_clip_tri_ids(poly, n, i, ids);
+        if (drop_degenerate && sr_clip_tri_degenerate(ids)) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int id = ids[c];
+            if (id < 3) {
+                sr_geo_store(out, (uint64_t)o * 3 + c, rec[id], in.nplanes);
+            } else {
+                const int e = (id - 3) / 6, plane = (id - 3) % 6;
+                sr_intersect(plane, rec[e], rec[e == 2 ? 0 : e + 1], nfloats, tmp);
+                sr_geo_store(out, (uint64_t)o * 3 + c, tmp, in.nplanes);
+            }
+        }
+        seq[o] = lbase + (uint32_t)i;
+        ++o;
+    }
+}
+
 // SR_GS_CLIP_SH: Sutherland-Hodgman against the same six planes, one plane after the other; an edge runs from the
 // previous vertex s to the current vertex p and crossings are intersect(plane, s, p) (clip.rs:47-63).  A triangle
 // clipped by six planes has at most nine vertices; the result is fanned around its first vertex.  MODE 0 = count, 1 = emit.
