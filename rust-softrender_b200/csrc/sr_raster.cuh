@@ -879,6 +879,11 @@ __device__ __forceinline__ bool sr_micro_box(const SrTri &tr, float z1, float z2
     return redo;
 }
 
+#ifndef SR_MICRO_PF_DIST
+#define SR_MICRO_PF_DIST 2048  // CTAs ahead whose index lines a k_micro CTA prefetches into L2 (0: off).  Measured on config 3: micro 128.8 ->
+                                // 123.2 us, frame 0.278 -> 0.271 ms; 1024 / 4096 / 8192 ahead: 0.2725 / 0.2725 / 0.276.  Prefetching the POSITIONS of a
+                                // later CTA as well (its indices loaded here) costs more than it hides: 0.288 ms
+#endif
 // 128-thread CTAs, 12 per SM (40 registers): the finer CTA granularity keeps ~4 more warps resident than 6 x 256
 #define SR_MICRO_THREADS 128
 #define SR_MICRO_MIN_BLOCKS 12
@@ -981,6 +986,16 @@ __device__ __forceinline__ void sr_micro_triangle(const SrMicroParams &p, uint32
 template <bool PRECHECK, bool EARLYZ>
 __global__ void __launch_bounds__(SR_MICRO_THREADS, SR_MICRO_MIN_BLOCKS) k_micro(const __grid_constant__ SrMicroParams p) {
     const uint32_t t = p.tri_begin + blockIdx.x * SR_MICRO_THREADS + threadIdx.x;
+#if SR_MICRO_PF_DIST > 0
+    // The kernel is bound by a chain of three dependent round trips per triangle (indices -> positions -> depth keys).  The first
+    // one is the only access that misses L2 by construction (the index buffer is streamed once): every CTA asks L2 for the index
+    // lines of the CTA SR_MICRO_PF_DIST launches behind it (128 triangles x 12 B = twelve 128-byte lines, one per thread).
+    if (threadIdx.x < SR_MICRO_THREADS * 12 / 128) {
+        const uint64_t tp = (uint64_t)p.tri_begin + (uint64_t)(blockIdx.x + SR_MICRO_PF_DIST) * SR_MICRO_THREADS;
+        if (tp + SR_MICRO_THREADS <= p.tri_end && tp + SR_MICRO_THREADS <= p.src.n0)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src.indices + tp * 3 + threadIdx.x * 32));
+    }
+#endif
     float4 A = make_float4(0, 0, 0, 0), B = A, C = A;
     if (t < p.tri_end) {
         const SrVertexSet *vs;
