@@ -562,6 +562,22 @@ static int launch_opaque_merge_fs(sr_context *c, uint32_t fs, uint32_t ntiles, c
     }
     return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
 }
+template <int FS>
+static int launch_few(sr_context *c, uint32_t ntiles, const SrFewParams &p) {
+    SR_LAUNCH(c, k_tile_few<FS>, ntiles, SR_FEW_THREADS, 0, p);
+    return SR_OK;
+}
+static int launch_few_fs(sr_context *c, uint32_t fs, uint32_t ntiles, const SrFewParams &p) {
+    switch (fs) {
+        case SR_FS_FLAT: return launch_few<SR_FS_FLAT>(c, ntiles, p);
+        case SR_FS_SUZANNE: return launch_few<SR_FS_SUZANNE>(c, ntiles, p);
+        case SR_FS_FULL_EXAMPLE: return launch_few<SR_FS_FULL_EXAMPLE>(c, ntiles, p);
+        case SR_FS_FULL_EXAMPLE_TEXTURED: return launch_few<SR_FS_FULL_EXAMPLE_TEXTURED>(c, ntiles, p);
+        case SR_FS_GREEN: return launch_few<SR_FS_GREEN>(c, ntiles, p);
+        case SR_FS_TEXTURE_UNLIT: return launch_few<SR_FS_TEXTURE_UNLIT>(c, ntiles, p);
+    }
+    return sr_fail(SR_ERR_INVALID_ARGUMENT, "fragment shader %u cannot run on the opaque path", fs);
+}
 static int launch_opaque_fs(sr_context *c, uint32_t fs, uint32_t ntiles_owned, const SrOpaqueParams &p) {
     const bool extra = p.nlines + p.npoints > 0;
 #define SR_OPQ_CASE(F) case F: return extra ? launch_opaque<F, true>(c, ntiles_owned, p) : launch_opaque<F, false>(c, ntiles_owned, p)
@@ -703,6 +719,23 @@ static int opaque_triangles(sr_context *c, sr_framebuffer *fb, const SrTileParam
         SR_CUDA(cudaMemsetAsync(fb->stencil_buf->ptr, 0, (size_t)fb->width * fb->height * fb->stencil_bytes, c->stream));
     if (ranged_eligible(c, fb, tp, extra)) return opaque_triangles_ranged(c, fb, tp, cull, fs, owned, keep, d);
     if (d) SR_TRY(materialize_vertices(d));
+    // a handful of triangles (a full-screen pass, UI rectangles) onto a plain RGBAf32 RenderBuffer: one launch, no lists (k_tile_few)
+    static const bool no_few = getenv("SR_NO_FEW") != nullptr;  // A/B switch
+    if (!no_few && !extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= SR_FEW_MAX && !tp.tris.n1_dev && !fb->u8color && !fb->soa &&
+        !(fb->winner_enabled && fb->winner_buf) && c->shard_world == 1 && !fb->is_peer && fs != SR_FS_SUZANNE_GBUFFER) {
+        record(c, 7);
+        record(c, 5);
+        SrFewParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.tris = tp.tris;
+        fp.ntris = tp.ntris;
+        fp.cull = cull;
+        fp.fb = fb->view();
+        fp.fs = tp.fs;
+        SR_TRY(launch_few_fs(c, fs, ntiles, fp));
+        fb->pending_clear = false;
+        return SR_OK;
+    }
     // small draws: one single-CTA launch builds the per-tile lists (k_bin_small); no visibility buffer
     if (!extra && c->micro_auto && tp.ntris > 0 && tp.ntris <= (tp.tris.n1_dev ? SR_BIN_SMALL_MAX_TRIS_DEV : SR_BIN_SMALL_MAX_TRIS) &&
         ntiles <= SR_BIN_SMALL_MAX_TILES) {

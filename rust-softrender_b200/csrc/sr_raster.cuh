@@ -1751,6 +1751,154 @@ __global__ void __launch_bounds__(SR_OPQ_THREADS, PHASE == 2 ? SR_OPQ_RESOLVE_CT
     if ((nbulk && lane == 0) || (p.vis != nullptr && p.reset_vis && tid < SR_TILE_H)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+
+// =====================================================================================================
+// Draws of a HANDFUL of triangles (a full-screen pass of two, a few UI rectangles): no binning, no keys, no lists.
+// The general opaque path is built for meshes -- bin the triangles, reduce keys per pixel, then look every winner up
+// again (indices, vertices, setup) -- and a full-screen quad pays all of it per pixel (433 warp-instructions per 32
+// pixels, profiles/r2b_*).  Here every CTA (one tile) sets the <= SR_FEW_MAX triangles up once into shared-memory
+// records; every pixel walks the records, keeps the fragment with the largest (depth key, primitive + 1) among those
+// with z < 0 and depth >= the stored one (triangle.rs:104-126 -- the same arithmetic, so the same bits, as the general
+// path) together with its barycentrics, and is shaded from the winner's record at once.  RenderBuffer targets with
+// RGBAf32 colour on one GPU; every other case keeps the general path.
+// =====================================================================================================
+#define SR_FEW_MAX 8
+#define SR_FEW_THREADS 256
+struct SrFewParams {
+    SrPrimSource tris;
+    uint32_t ntris;
+    uint32_t cull;
+    SrFbView fb;
+    SrFsConst fs;
+};
+template <int FS>
+__global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_constant__ SrFewParams p) {
+    __shared__ float4 s_rec[SR_FEW_MAX * 8];
+    __shared__ __align__(16) float s_stage[SR_FEW_THREADS / 32][32 * 5];
+    __shared__ uint32_t s_any;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t W = p.fb.width, H = p.fb.height;
+    const uint32_t x0 = (blockIdx.x % p.fb.ntx) * SR_TILE_W, y0 = (blockIdx.x / p.fb.ntx) * SR_TILE_H;
+    const uint32_t xe = min(x0 + SR_TILE_W, W) - 1, ye = min(y0 + SR_TILE_H, H) - 1;
+    const uint32_t L = p.ntris;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < L) {
+        const SrVertexSet *vs;
+        uint32_t vi[3];
+        sr_prim_vertices<3>(p.tris, tid, vs, vi);
+        const float4 A = __ldg(vs->pos + vi[0]), B = __ldg(vs->pos + vi[1]), C = __ldg(vs->pos + vi[2]);
+        bool skip = isnan(A.x) || isnan(A.y) || isnan(B.x) || isnan(B.y) || isnan(C.x) || isnan(C.y);  // (the reference panics)
+        if (p.cull != SR_CULL_NONE) {  // triangle.rs:54-61
+            const float area = A.x * B.y + B.x * C.y + C.x * A.y - B.x * A.y - C.x * B.y - A.x * C.y;
+            skip = skip || (signbit(area) ? SR_CLOCKWISE : SR_COUNTER_CLOCKWISE) == p.cull;
+        }
+        // triangle.rs:74-78 (bounding box clamped to the frame), intersected with this tile
+        uint32_t minx = max(sr_clamp_as_int(fminf(fminf(A.x, B.x), C.x), 0, W - 1), x0);
+        uint32_t miny = max(sr_clamp_as_int(fminf(fminf(A.y, B.y), C.y), 0, H - 1), y0);
+        const uint32_t maxx = min(sr_clamp_as_int(fmaxf(fmaxf(A.x, B.x), C.x), 0, W - 1), xe);
+        uint32_t maxy = min(sr_clamp_as_int(fmaxf(fmaxf(A.y, B.y), C.y), 0, H - 1), ye);
+        if (skip || minx > maxx || miny > maxy) { minx = 1; miny = 1; maxy = 0; }
+        else s_any = 1;
+        const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
+        float4 *r = s_rec + tid * 8;
+        r[0] = make_float4(tr.a, tr.b, tr.c, tr.d);
+        r[1] = make_float4(tr.x3, tr.y3, tr.det, tr.rdet);
+        r[2] = make_float4(A.z, B.z, C.z, __uint_as_float(tid + 1u));
+        r[3] = make_float4(__uint_as_float(minx), __uint_as_float(maxx), __uint_as_float(miny), __uint_as_float(maxy));
+        r[4] = make_float4(A.x, A.y, A.w, B.x);
+        r[5] = make_float4(B.y, B.w, C.x, C.y);
+        r[6] = make_float4(C.w, __uint_as_float(vi[0]), __uint_as_float(vi[1]), __uint_as_float(vi[2]));
+        r[7] = make_float4(__uint_as_float(tr.dsign), __uint_as_float(tr.fast ? 1u : 0u), __uint_as_float(tid < p.tris.n0 ? 0u : 1u), 0.0f);
+    }
+    __syncthreads();
+    if (s_any == 0) {  // no triangle reaches the tile
+        if (p.fb.pending_clear) sr_fill_tile_clear(p.fb, x0, y0);
+        return;
+    }
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    const bool vec_ok = (W & 3u) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
+    float *sb = s_stage[warp];
+    for (uint32_t chunk = warp; chunk < SR_TILE_PIXELS / 32; chunk += SR_FEW_THREADS / 32) {
+        const uint32_t cx0 = x0 + (chunk * 32) % SR_TILE_W, py = y0 + (chunk * 32) / SR_TILE_W, px = cx0 + lane;
+        if (cx0 >= W || py >= H) continue;  // (warp-uniform)
+        const bool in_frame = px < W;
+        const uint64_t index = (uint64_t)py * W + px;
+        float o[5];
+        bool write = false;
+        if (in_frame) {
+            uint32_t best_hi = ~SR_DEPTH_FAR_BITS, best_l = 0xFFFFFFFFu;
+            if (!p.fb.pending_clear) best_hi = sr_depth_key(p.fb.aos[index * 5 + 4]);
+            float u = 0.0f, v = 0.0f, w = 0.0f;
+            const float xf = (float)px + 0.5f, yf = (float)py + 0.5f;
+            for (uint32_t l = 0; l < L; ++l) {
+                const float4 *r = s_rec + l * 8;
+                const uint4 box = *reinterpret_cast<const uint4 *>(r + 3);
+                if (px < box.x || px > box.y || py < box.z || py > box.w) continue;
+                const float4 r0 = r[0], r1 = r[1], r2 = r[2], r7 = r[7];
+                SrTri s;
+                s.a = r0.x; s.b = r0.y; s.c = r0.z; s.d = r0.w;
+                s.x3 = r1.x; s.y3 = r1.y; s.det = r1.z; s.rdet = r1.w;
+                s.dsign = __float_as_uint(r7.x);
+                s.fast = __float_as_uint(r7.y) != 0u;
+                float nu, nv, uu, vv, ww;
+                sr_tri_numerators(s, xf, yf, nu, nv);
+                if (!sr_tri_inside(s, nu, nv, uu, vv, ww)) continue;
+                const float z = (r2.x * uu + r2.y * vv) + r2.z * ww;
+                if (!(z < 0.0f)) continue;  // triangle.rs:120
+                const uint32_t kh = sr_depth_key(z);
+                if (kh >= best_hi) { best_hi = kh; best_l = l; u = uu; v = vv; w = ww; }  // d >= dt, later primitive wins ties (triangle.rs:126)
+            }
+            if (best_l != 0xFFFFFFFFu) {
+                const float4 *r = s_rec + best_l * 8;
+                const float4 r2 = r[2], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7];
+                const float4 A = make_float4(r4.x, r4.y, r2.x, r4.z), B = make_float4(r4.w, r5.x, r2.y, r5.y), C = make_float4(r5.z, r5.w, r2.z, r6.x);
+                const uint32_t vi0 = __float_as_uint(r6.y), vi1 = __float_as_uint(r6.z), vi2 = __float_as_uint(r6.w);
+                const SrVertexSet *vs = __float_as_uint(r7.z) ? &p.tris.vs1 : &p.tris.vs0;
+                float sv[4 + NP * 4 + 1];
+                sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
+                sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
+                sv[2] = sr_bary(u, A.z, v, B.z, w, C.z);
+                sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                    const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
+                    const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
+                    const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
+                    // (same choice as the general resolve: contraction only for values that feed lit shading, never for texture coordinates)
+                    if (SrFsInfo<FS>::LIT && pl < 2) {
+                        sv[4 + pl * 4 + 0] = sr_bary_fast(u, ka.x, v, kb.x, w, kc.x); sv[4 + pl * 4 + 1] = sr_bary_fast(u, ka.y, v, kb.y, w, kc.y);
+                        sv[4 + pl * 4 + 2] = sr_bary_fast(u, ka.z, v, kb.z, w, kc.z); sv[4 + pl * 4 + 3] = sr_bary_fast(u, ka.w, v, kb.w, w, kc.w);
+                    } else {
+                        sv[4 + pl * 4 + 0] = sr_bary(u, ka.x, v, kb.x, w, kc.x); sv[4 + pl * 4 + 1] = sr_bary(u, ka.y, v, kb.y, w, kc.y);
+                        sv[4 + pl * 4 + 2] = sr_bary(u, ka.z, v, kb.z, w, kc.z); sv[4 + pl * 4 + 3] = sr_bary(u, ka.w, v, kb.w, w, kc.w);
+                    }
+                }
+                sr_fragment_shader<FS>(p.fs, sv, o);
+                o[4] = sv[2];
+                write = true;
+            } else if (p.fb.pending_clear) {
+                o[0] = p.fb.clear[0]; o[1] = p.fb.clear[1]; o[2] = p.fb.clear[2]; o[3] = p.fb.clear[3];
+                o[4] = __uint_as_float(SR_DEPTH_FAR_BITS);
+                write = true;
+            }
+        }
+        // a whole 32-pixel run that is written leaves as forty 16-byte stores (640 contiguous bytes), anything else pixel by pixel
+        if (vec_ok && cx0 + 32 <= W && __all_sync(0xffffffffu, write)) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sb[lane * 5 + k] = o[k];
+            __syncwarp();
+            float4 *dst = reinterpret_cast<float4 *>(p.fb.aos + ((uint64_t)py * W + cx0) * 5);
+            dst[lane] = reinterpret_cast<const float4 *>(sb)[lane];
+            if (lane < 8) dst[32 + lane] = reinterpret_cast<const float4 *>(sb)[32 + lane];
+            __syncwarp();
+        } else if (write) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) p.fb.aos[index * 5 + k] = o[k];
+        }
+    }
+}
+
 // =====================================================================================================
 // Ordered tile rasteriser: any blend, stencil, discarding shaders, lines and points.  Strictly in
 // submission order per pixel.  Tile colour, depth, stencil (and winner) live in shared memory; each

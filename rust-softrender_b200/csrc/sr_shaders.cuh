@@ -122,7 +122,7 @@ __device__ __forceinline__ void sr_texture_bilinear_clamp(const SrFsConst &c, fl
     const uchar4 t11 = __ldg((const uchar4 *)c.tex + (size_t)y1 * c.tex_w + x1);
     // texel / 255 (texture.rs:66-69): correctly rounded quotients through the shared-divisor shortcut (sr_div_exact with
     // r = RN(1/255); 0 / 255 comes out as +0) instead of sixteen IEEE division sequences -- same bits
-    const float r255 = __frcp_rn(255.0f);
+    const float r255 = 0x1.010102p-8f;  // RN(1/255)
     auto unorm = [&](const uchar4 &t, float *a) {
         a[0] = sr_div_exact((float)t.x, 255.0f, r255); a[1] = sr_div_exact((float)t.y, 255.0f, r255);
         a[2] = sr_div_exact((float)t.z, 255.0f, r255); a[3] = sr_div_exact((float)t.w, 255.0f, r255);
@@ -153,7 +153,7 @@ __device__ __forceinline__ float4 sr_texture_sample_body(const SrFsConst &c, flo
     }
     const uint32_t lastx = c.tex_w - 1, lasty = c.tex_h - 1;
     const bool f32 = c.tex_kind == SR_TEX_F32;
-    const float r255 = __frcp_rn(255.0f);
+    const float r255 = 0x1.010102p-8f;  // RN(1/255) (what __frcp_rn(255.0f) returns; as a constant it costs nothing on the f32 path)
     const uint32_t texel_bytes = f32 ? c.tex_stride * 4u : 4u;
     auto texel = [&](uint32_t x, uint32_t y, float *a) {
         x = min(x, lastx); y = min(y, lasty);

@@ -1588,3 +1588,73 @@ def test_render_to_texture_full_screen_pass_through_the_builder_chain(P, ctx):
     H.compare_framebuffers(fba.download(), ofa, color_tol=COLOR_TOL, what="pass 1")
     for x in (pa, gm, fba):
         x.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------
+# draws of a handful of triangles onto a plain RenderBuffer WITHOUT the winner plane: k_tile_few (one launch, no lists)
+# ------------------------------------------------------------------------------------------------------
+def _few_fb(P, ctx, w, h):
+    fb = P.RenderBuffer.with_dimensions(ctx, w, h)  # (no enable_winner: the introspection plane selects the general path)
+    fb.clear(H.CLEAR)
+    return fb
+
+
+@pytest.mark.parametrize("w,h", [(300, 180), (256, 128), (67, 45)])
+@pytest.mark.parametrize("cull", [sr.CULL_NONE, sr.CLOCKWISE])
+def test_few_triangles_direct_path(P, ctx, w, h, cull):
+    """Up to eight triangles of any size (k_tile_few): big ones that cover whole tiles, slivers, triangles that stick out of
+    the frame, exact depth ties between them (the later one wins), a vertex at z >= 0, NaN coordinates; drawn twice -- onto a
+    recorded clear and then, with other triangles, onto the existing contents (stored depth = the bar to pass).  Frame sizes
+    with partial tiles and widths that are not a multiple of four (no 16-byte stores).  Bit-exact against the oracle."""
+    rng = np.random.default_rng(w * 7 + h + cull)
+    u = scenes.suzanne_uniforms(w, h)
+    fb = _few_fb(P, ctx, w, h)
+    ofb = oracle_fb(w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    for draw in range(3):
+        n = int(rng.integers(1, 9))
+        verts = H.random_screen_triangles(rng, n, w, h, max_size=0.9 * max(w, h), integer_depth=(draw == 1), margin=0.3)
+        if draw == 2 and n >= 3:
+            verts[0:3, 2] = [0.5, -1.0, -2.0]     # a triangle crossing z = 0: fragments with z >= 0 are dropped (triangle.rs:120)
+            verts[3, 0] = np.nan                  # the reference panics on NaN; defined as "skipped" (DESIGN section 3)
+        idx = np.arange(3 * n, dtype=np.uint32)
+        od = ob.OracleDraw(sr.TRIANGLE, idx)
+        od.set_vertices(verts, 1)
+        od.cull = cull
+        od.fragment_run(ofb, sr.FS_FLAT, u)
+        pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).cull_faces(cull).run(sr.FS_FLAT)
+        H.compare_framebuffers(fb.download(), ofb, exact_color=True, what=f"few triangles, draw {draw}")
+    for x in (pipe, fb):
+        x.destroy()
+
+
+@pytest.mark.parametrize("filt", [sr.FILTER_NEAREST, sr.FILTER_BILINEAR])
+@pytest.mark.parametrize("edge", [sr.EDGE_CLAMP, sr.EDGE_WRAP, sr.EDGE_BORDER])
+def test_full_screen_pass_direct_path(P, ctx, filt, edge):
+    """The render-to-texture second pass as an application issues it (no winner plane): a quad of two triangles with texture
+    coordinates beyond [0, 1], texture_unlit sampling a rendered target in place, every Filter x Edge -- through k_tile_few."""
+    rng = np.random.default_rng(31 + filt * 3 + edge)
+    w, h = 328, 200
+    u = scenes.suzanne_uniforms(w, h)
+    vp = scenes.Viewport.new(w, h, 0.1, 10.0)
+    src_fb = make_fb(P, ctx, w, h)
+    p1 = P.Pipeline.from_framebuffer(src_fb, u)
+    verts = H.random_screen_triangles(rng, 300, w, h, max_size=40.0)
+    p1.draw_from_vertices(sr.TRIANGLE, verts, np.arange(900, dtype=np.uint32), 1).run(sr.FS_FLAT)
+    src = src_fb.download()[:, :4].reshape(h, w, 4).copy()
+    quad = np.array([[-1, -1, 0, 1, -0.3, 1.2], [1, -1, 0, 1, 1.4, 1.2], [1, 1, 0, 1, 1.4, -0.1], [-1, 1, 0, 1, -0.3, -0.1]], np.float32)
+    qi = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    border = (0.25, 0.5, 0.75, 1.0)
+    fb = _few_fb(P, ctx, w, h)
+    p2 = P.Pipeline.from_framebuffer(fb, u)
+    p2.bind_framebuffer_texture(src_fb)
+    p2.set_sampler(filt, edge, border)
+    qm = P.Mesh(ctx, vertices=quad, indices=qi)
+    p2.render_mesh(sr.TRIANGLE, qm).run_to_fragment(vp, sr.VS_PASSTHROUGH).run(sr.FS_TEXTURE_UNLIT)
+    ofb = oracle_fb(w, h)
+    od = ob.OracleDraw(sr.TRIANGLE, qi)
+    od.vertex_run_to_fragment(vp, sr.VS_PASSTHROUGH, u, quad)
+    od.fragment_run(ofb, sr.FS_TEXTURE_UNLIT, u, texture=src, sampler=(filt, edge, border))
+    H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="full-screen pass, direct path")
+    for x in (p2, qm, fb, p1, src_fb):
+        x.destroy()
