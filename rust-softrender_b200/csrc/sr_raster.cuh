@@ -564,6 +564,23 @@ __device__ __forceinline__ void sr_fill_tile_clear(const SrFbView &fb, uint32_t 
     }
     const uint32_t run = (min(x0 + SR_TILE_W, fb.width) - x0) * 5;  // floats per tile row inside the frame
     const float pat[5] = {fb.clear[0], fb.clear[1], fb.clear[2], fb.clear[3], __uint_as_float(SR_DEPTH_FAR_BITS)};
+    if ((fb.width & 3u) == 0 && (reinterpret_cast<uintptr_t>(fb.aos) & 15u) == 0 && x0 + SR_TILE_W <= fb.width && y0 + SR_TILE_H <= fb.height) {
+        // A whole tile (the usual case; config 3's frame is 56 % background and every empty tile comes through here): a tile row is
+        // 80 float4, the 20-byte pixel pattern repeats every five of them.  Thread t < 240 owns column t % 80 of the rows t / 80,
+        // t / 80 + 3, ...: its float4 is the same in every row, so it is formed once and the loop is eleven 16-byte stores.
+        static_assert(SR_TILE_W * 5 / 4 == 80 && SR_TILE_H == 32, "column / row ownership below");
+        const uint32_t t = threadIdx.x;
+        if (t < 240u) {
+            const uint32_t q = t % 80u, f = (q % 5u) * 4u;  // first float of this float4 within the pattern of four pixels
+            auto at = [&](uint32_t i) { const uint32_t m = i % 5u; return m == 0 ? pat[0] : m == 1 ? pat[1] : m == 2 ? pat[2] : m == 3 ? pat[3] : pat[4]; };
+            const float4 v = make_float4(at(f), at(f + 1u), at(f + 2u), at(f + 3u));
+            const uint64_t pitch4 = (uint64_t)fb.width * 5u / 4u;  // float4 per framebuffer row
+            float4 *dst = reinterpret_cast<float4 *>(fb.aos + ((uint64_t)y0 * fb.width + x0) * 5) + (uint64_t)(t / 80u) * pitch4 + q;
+#pragma unroll 1
+            for (uint32_t r = t / 80u; r < SR_TILE_H; r += 3u, dst += 3u * pitch4) *dst = v;
+        }
+        return;
+    }
     if ((fb.width & 3u) == 0 && (run & 3u) == 0 && (reinterpret_cast<uintptr_t>(fb.aos) & 15u) == 0) {
         // 16-byte stores: the 20-byte pixel pattern repeats every five float4 (x0 is a multiple of 64 pixels = 1280 bytes)
         const uint32_t run4 = run / 4, rows = min(SR_TILE_H, fb.height - y0);
