@@ -1790,7 +1790,9 @@ struct SrFewParams {
 };
 template <int FS>
 __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_constant__ SrFewParams p) {
-    __shared__ float4 s_rec[SR_FEW_MAX * 8];
+    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
+    constexpr int RS = 8 + 3 * NP;  // float4 per record: setup, box, positions, flags, then the three vertices' attribute planes
+    __shared__ float4 s_rec[SR_FEW_MAX * RS];
     __shared__ __align__(16) float s_stage[SR_FEW_THREADS / 32][32 * 5];
     __shared__ uint32_t s_any;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1818,11 +1820,17 @@ __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_consta
         if (skip || minx > maxx || miny > maxy) { minx = 1; miny = 1; maxy = 0; }
         else s_any = 1;
         const SrTri tr = sr_tri_setup(A.x, A.y, B.x, B.y, C.x, C.y);
-        float4 *r = s_rec + tid * 8;
+        float4 *r = s_rec + tid * RS;
         r[0] = make_float4(tr.a, tr.b, tr.c, tr.d);
         r[1] = make_float4(tr.x3, tr.y3, tr.det, tr.rdet);
         r[2] = make_float4(A.z, B.z, C.z, __uint_as_float(tid + 1u));
         r[3] = make_float4(__uint_as_float(minx), __uint_as_float(maxx), __uint_as_float(miny), __uint_as_float(maxy));
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {  // the attributes travel with the record: the pixels read shared memory, not three gathers each
+            r[8 + pl * 3 + 0] = __ldg(vs->attr + sr_attr_at(vs->np, vi[0], pl));
+            r[8 + pl * 3 + 1] = __ldg(vs->attr + sr_attr_at(vs->np, vi[1], pl));
+            r[8 + pl * 3 + 2] = __ldg(vs->attr + sr_attr_at(vs->np, vi[2], pl));
+        }
         r[4] = make_float4(A.x, A.y, A.w, B.x);
         r[5] = make_float4(B.y, B.w, C.x, C.y);
         r[6] = make_float4(C.w, __uint_as_float(vi[0]), __uint_as_float(vi[1]), __uint_as_float(vi[2]));
@@ -1833,7 +1841,6 @@ __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_consta
         if (p.fb.pending_clear) sr_fill_tile_clear(p.fb, x0, y0);
         return;
     }
-    constexpr int NK = SrFsInfo<FS>::NK, NP = (NK + 3) / 4;
     const bool vec_ok = (W & 3u) == 0 && (reinterpret_cast<uintptr_t>(p.fb.aos) & 15u) == 0;
     float *sb = s_stage[warp];
     for (uint32_t chunk = warp; chunk < SR_TILE_PIXELS / 32; chunk += SR_FEW_THREADS / 32) {
@@ -1849,7 +1856,7 @@ __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_consta
             float u = 0.0f, v = 0.0f, w = 0.0f;
             const float xf = (float)px + 0.5f, yf = (float)py + 0.5f;
             for (uint32_t l = 0; l < L; ++l) {
-                const float4 *r = s_rec + l * 8;
+                const float4 *r = s_rec + l * RS;
                 const uint4 box = *reinterpret_cast<const uint4 *>(r + 3);
                 if (px < box.x || px > box.y || py < box.z || py > box.w) continue;
                 const float4 r0 = r[0], r1 = r[1], r2 = r[2], r7 = r[7];
@@ -1867,11 +1874,9 @@ __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_consta
                 if (kh >= best_hi) { best_hi = kh; best_l = l; u = uu; v = vv; w = ww; }  // d >= dt, later primitive wins ties (triangle.rs:126)
             }
             if (best_l != 0xFFFFFFFFu) {
-                const float4 *r = s_rec + best_l * 8;
-                const float4 r2 = r[2], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7];
+                const float4 *r = s_rec + best_l * RS;
+                const float4 r2 = r[2], r4 = r[4], r5 = r[5], r6 = r[6];
                 const float4 A = make_float4(r4.x, r4.y, r2.x, r4.z), B = make_float4(r4.w, r5.x, r2.y, r5.y), C = make_float4(r5.z, r5.w, r2.z, r6.x);
-                const uint32_t vi0 = __float_as_uint(r6.y), vi1 = __float_as_uint(r6.z), vi2 = __float_as_uint(r6.w);
-                const SrVertexSet *vs = __float_as_uint(r7.z) ? &p.tris.vs1 : &p.tris.vs0;
                 float sv[4 + NP * 4 + 1];
                 sv[0] = sr_bary(u, A.x, v, B.x, w, C.x);
                 sv[1] = sr_bary(u, A.y, v, B.y, w, C.y);
@@ -1879,9 +1884,7 @@ __global__ void __launch_bounds__(SR_FEW_THREADS) k_tile_few(const __grid_consta
                 sv[3] = sr_bary(u, A.w, v, B.w, w, C.w);
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl) {
-                    const float4 ka = __ldg(vs->attr + sr_attr_at(vs->np, vi0, pl));
-                    const float4 kb = __ldg(vs->attr + sr_attr_at(vs->np, vi1, pl));
-                    const float4 kc = __ldg(vs->attr + sr_attr_at(vs->np, vi2, pl));
+                    const float4 ka = r[8 + pl * 3 + 0], kb = r[8 + pl * 3 + 1], kc = r[8 + pl * 3 + 2];
                     // (same choice as the general resolve: contraction only for values that feed lit shading, never for texture coordinates)
                     if (SrFsInfo<FS>::LIT && pl < 2) {
                         sv[4 + pl * 4 + 0] = sr_bary_fast(u, ka.x, v, kb.x, w, kc.x); sv[4 + pl * 4 + 1] = sr_bary_fast(u, ka.y, v, kb.y, w, kc.y);
