@@ -2458,16 +2458,16 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
             }
             __syncthreads();
             const uint32_t at = base + __popc(mask & ((1u << lane) - 1u));
-            if (hit) {
-                s_setup[at] = su;
+            // entries the earlier warps put on band b's list: summed once per warp (lane b), handed to the lanes by shuffle
+            uint32_t bprefix = 0;
+            if (lane < SR_RASTER_WARPS)
+                for (uint32_t w2 = 0; w2 < warp; ++w2) bprefix += s_wband[w2][lane];
 #pragma unroll
-                for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b)
-                    if ((bandmask >> b) & 1u) {
-                        uint32_t bbase = 0;
-                        for (uint32_t w2 = 0; w2 < warp; ++w2) bbase += s_wband[w2][b];
-                        s_band[b][bbase + __popc(bm[b] & ((1u << lane) - 1u))] = (uint8_t)at;
-                    }
+            for (uint32_t b = 0; b < SR_RASTER_WARPS; ++b) {
+                const uint32_t bbase = __shfl_sync(0xffffffffu, bprefix, b);
+                if (hit && ((bandmask >> b) & 1u)) s_band[b][bbase + __popc(bm[b] & ((1u << lane) - 1u))] = (uint8_t)at;
             }
+            if (hit) s_setup[at] = su;
             uint32_t nband = 0;
 #pragma unroll
             for (uint32_t w2 = 0; w2 < SR_RASTER_WARPS; ++w2) nband += s_wband[w2][warp];
@@ -2612,18 +2612,23 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                                         rem |= 1u << (j * bw + (px - minx));
                                     });
                             const uint32_t cbase = own_row_index(r0) * SR_TILE_W + (minx - x0);  // box origin among the warp's rows
+                            // box position i < 32 -> (row, column) without an integer division: (i * m) >> 16 == i / bw for every i < 32, bw <= 32
+                            const uint32_t bwm = (1u << 16) / max(bw, 1u) + 1u;
+                            auto row_of = [&](uint32_t i) { return (i * bwm) >> 16; };
                             while (__any_sync(0xffffffffu, rem != 0)) {
                                 ++claim_round;
                                 const uint32_t bid = (claim_round << 8) | (255u - lane);
                                 for (uint32_t m = rem; m; m &= m - 1) {
                                     const uint32_t i = (uint32_t)__ffs(m) - 1u;
-                                    atomicMax(&claim[cbase + (i / bw) * SR_TILE_W + i % bw], bid);
+                                    const uint32_t rr = row_of(i);
+                                    atomicMax(&claim[cbase + rr * SR_TILE_W + (i - rr * bw)], bid);
                                 }
                                 __syncwarp();
                                 uint32_t todo = 0;  // the fragments this lane applies in this round
                                 for (uint32_t m = rem; m; m &= m - 1) {
                                     const uint32_t i = (uint32_t)__ffs(m) - 1u;
-                                    if (claim[cbase + (i / bw) * SR_TILE_W + i % bw] == bid) todo |= 1u << i;
+                                    const uint32_t rr = row_of(i);
+                                    if (claim[cbase + rr * SR_TILE_W + (i - rr * bw)] == bid) todo |= 1u << i;
                                 }
                                 rem &= ~todo;
                                 while (__any_sync(0xffffffffu, todo != 0)) {
@@ -2633,7 +2638,8 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                                     if (todo) {
                                         const uint32_t i = (uint32_t)__ffs(todo) - 1u;
                                         todo &= todo - 1;
-                                        const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
+                                        const uint32_t rr = row_of(i);
+                                        const uint32_t px = minx + (i - rr * bw), py = r0 + rr * rstep;
                                         li = (py - y0) * SR_TILE_W + (px - x0);
                                         sr_tri_bary(tr, px, py, u, v, w);  // (covered: the same arithmetic as pass A)
                                         const float z = sr_bary(u, z1, v, z2, w, z3);
@@ -2671,13 +2677,15 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
                     const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
                     const uint32_t bw = maxx - minx + 1, npix = bw * nrows, canonical = q.canonical;
+                    const uint32_t bwm = 0xFFFFFFFFu / bw + 1u;  // __umulhi(i, bwm) == i / bw for i, bw < 2^16 (one division per triangle, none per pixel)
                     for (uint32_t base = 0; base < npix; base += 32) {
                         const uint32_t i = base + lane;
                         bool pass = false;
                         uint32_t li = 0;
                         float u = 0.0f, v = 0.0f, w;
                         if (i < npix) {
-                            const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
+                            const uint32_t rr = bw == 1u ? i : __umulhi(i, bwm);  // (bw == 1: the multiplier 2^32 does not fit)
+                            const uint32_t px = minx + (i - rr * bw), py = r0 + rr * rstep;
                             li = (py - y0) * SR_TILE_W + (px - x0);
                             if (sr_ord_stencil_step(c, li) && sr_tri_bary(tr, px, py, u, v, w)) {
                                 const float z = sr_bary(u, z1, v, z2, w, z3);
@@ -2713,10 +2721,12 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
                 const float4 A = q.A, B = q.B, C = q.C;
                 const uint32_t bw = maxx - minx + 1, npix = bw * nrows;
+                const uint32_t bwm = 0xFFFFFFFFu / bw + 1u;  // __umulhi(i, bwm) == i / bw
                 const SrVertexSet *vs = q.second ? &p.tris.vs1 : &p.tris.vs0;
                 const uint32_t vi0 = q.vi[0], vi1 = q.vi[1], vi2 = q.vi[2], canonical = q.canonical;
                 for (uint32_t i = lane; i < npix; i += 32) {
-                    const uint32_t px = minx + i % bw, py = r0 + (i / bw) * rstep;
+                    const uint32_t rr = bw == 1u ? i : __umulhi(i, bwm);  // (bw == 1: the multiplier 2^32 does not fit)
+                    const uint32_t px = minx + (i - rr * bw), py = r0 + rr * rstep;
                     const uint32_t li = (py - y0) * SR_TILE_W + (px - x0);
                     if (!sr_ord_stencil_step(c, li)) continue;
                     float u, v, w;
