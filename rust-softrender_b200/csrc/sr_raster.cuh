@@ -2413,7 +2413,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                         su.canonical = sr_prim_canonical(p.tris, t, 0);
                         su.second = t < p.tris.n0 ? 0u : 1u;
                         su.vi[0] = vi[0]; su.vi[1] = vi[1]; su.vi[2] = vi[2];
-                        su.pad = 0;
+                        su.pad = tr.fast ? 1u : 0u;  // (validity of the exact-division shortcut: decided once, at setup)
                     }
                 }
             }
@@ -2602,7 +2602,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                             tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
                             tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
                             tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
-                            tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                            tr.fast = q.pad != 0u;
                             const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
                             const uint32_t canonical = q.canonical;
                             uint32_t rem = 0;  // box positions (row-major) whose fragment is still to be applied
@@ -2674,7 +2674,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                     tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
                     tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
                     tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
-                    tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                    tr.fast = q.pad != 0u;
                     const float z1 = q.A.z, z2 = q.B.z, z3 = q.C.z;
                     const uint32_t bw = maxx - minx + 1, npix = bw * nrows, canonical = q.canonical;
                     const uint32_t bwm = 0xFFFFFFFFu / bw + 1u;  // __umulhi(i, bwm) == i / bw for i, bw < 2^16 (one division per triangle, none per pixel)
@@ -2718,7 +2718,7 @@ __global__ void __launch_bounds__(SR_RASTER_THREADS) k_tile_ordered(const __grid
                 tr.a = q.e.x; tr.b = q.e.y; tr.c = q.e.z; tr.d = q.e.w;
                 tr.x3 = q.f.x; tr.y3 = q.f.y; tr.det = q.f.z; tr.rdet = q.f.w;
                 tr.dsign = __float_as_uint(tr.det) & 0x80000000u;
-                tr.fast = ((__float_as_uint(tr.det) & 0x7FFFFFFFu) - 0x2B800000u) < (0x53800000u - 0x2B800000u);
+                tr.fast = q.pad != 0u;
                 const float4 A = q.A, B = q.B, C = q.C;
                 const uint32_t bw = maxx - minx + 1, npix = bw * nrows;
                 const uint32_t bwm = 0xFFFFFFFFu / bw + 1u;  // __umulhi(i, bwm) == i / bw
