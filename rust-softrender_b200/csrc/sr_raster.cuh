@@ -414,7 +414,7 @@ __device__ __forceinline__ bool sr_tri_bary(const SrTri &t, uint32_t px, uint32_
 
 
 // =====================================================================================================
-// sm_100a async-copy plumbing: mbarrier, cp.async.bulk (TMA bulk copy, SASS UBLKCP) and cp.async (LDGSTS)
+// sm_100a async-copy plumbing: mbarrier and cp.async.bulk (TMA bulk copy, SASS UBLKCP)
 // =====================================================================================================
 __device__ __forceinline__ uint32_t sr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sr_mbar_init(uint64_t *bar, uint32_t count) {
