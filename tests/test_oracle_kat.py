@@ -295,3 +295,42 @@ def test_stencil_ops_on_wider_types():
         assert f(sr.STENCIL_INVERT, 0, 0, bits) == m and f(sr.STENCIL_INVERT, 0x5A, 0, bits) == m ^ 0x5A
         assert f(sr.STENCIL_REPLACE, 3, m - 7, bits) == m - 7 and f(sr.STENCIL_ZERO, m, 1, bits) == 0 and f(sr.STENCIL_KEEP, m, 1, bits) == m
     assert f(sr.STENCIL_INCREMENT_WRAP, 255, 0, 16) == 256 and f(sr.STENCIL_INCREMENT_WRAP, 65535, 0, 32) == 65536
+
+
+def test_two_colour_planes_in_the_oracle():
+    """A texture buffer declared with two colour planes (declare_texture_buffer!, src/framebuffer/texturebuffer.rs:72-147): the
+    fragment shader returns the tuple, set_pixel_unchecked stores each colour into its own plane (:141-147), clear takes the
+    tuple (:181-197).  Known answers: one flat-depth triangle whose three vertices carry the same normal -- plane 1 holds that
+    normal on every covered pixel and its clear colour elsewhere; plane 0 is what the one-plane Suzanne shader produces."""
+    import softrender_b200 as sr
+    from softrender_b200 import scenes
+    w, h = 16, 12
+    u = scenes.suzanne_uniforms(w, h)
+    normal = np.float32([0.0, 0.6, 0.8, 0.0])
+    verts = np.zeros((3, 12), np.float32)
+    verts[:, :4] = [[2.0, 2.0, -1.0, 1.0], [13.0, 3.0, -1.0, 1.0], [6.0, 10.0, -1.0, 1.0]]
+    verts[:, 4:8] = [[0.1, 0.2, 0.3, 1.0], [0.4, 0.1, 0.2, 1.0], [0.3, 0.5, 0.1, 1.0]]  # world positions
+    verts[:, 8:12] = normal
+    idx = np.arange(3, dtype=np.uint32)
+    clear0, clear1 = (0.1, 0.2, 0.3, 1.0), (9.0, 8.0, 7.0, 6.0)
+    two = ob.OracleFramebuffer(w, h, two_colors=True)
+    two.clear(clear0, clear1)
+    one = ob.OracleFramebuffer(w, h)
+    one.clear(clear0)
+    for fb, fs in ((two, sr.FS_SUZANNE_GBUFFER), (one, sr.FS_SUZANNE)):
+        od = ob.OracleDraw(sr.TRIANGLE, idx)
+        od.set_vertices(verts, 1)
+        od.fragment_run(fb, fs, u)
+    covered = two.winner != 0
+    assert 20 < covered.sum() < w * h and np.array_equal(covered, one.winner != 0)
+    assert np.array_equal(two.color, one.color) and np.array_equal(two.depth, one.depth)  # plane 0 and depth: the one-plane result
+    # u + v + w is 1 only up to rounding, so the interpolated constant normal is within an ulp or two of the constant
+    assert np.allclose(two.color1[covered], normal, rtol=0, atol=3e-7)
+    assert np.array_equal(two.color1[~covered], np.tile(np.float32(clear1), ((~covered).sum(), 1)))
+    # the shader's return type and the target's colour type must agree (a type error in the reference)
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 1)
+    with pytest.raises(Exception):
+        od.fragment_run(one, sr.FS_SUZANNE_GBUFFER, u)
+    with pytest.raises(Exception):
+        od.fragment_run(two, sr.FS_SUZANNE, u)
