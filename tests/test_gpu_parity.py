@@ -1658,3 +1658,40 @@ def test_full_screen_pass_direct_path(P, ctx, filt, edge):
     H.compare_framebuffers(fb.download(), ofb, exact_color=True, what="full-screen pass, direct path")
     for x in (p2, qm, fb, p1, src_fb):
         x.destroy()
+
+
+@pytest.mark.parametrize("fs,nk", [(sr.FS_SUZANNE, 8), (sr.FS_FULL_EXAMPLE, 8), (sr.FS_FULL_EXAMPLE_TEXTURED, 10), (sr.FS_GREEN, 4)])
+def test_few_triangles_direct_path_lit_shaders(P, ctx, fs, nk):
+    """k_tile_few with the registered lit shaders (attribute planes carried in the per-CTA records: 2 planes, 3 with texture
+    coordinates) and an image texture: depth bit-exact, colour within 1/255 where the oracle's colour is a number (random
+    "normals" can drive a power's base negative -- NaN in both)."""
+    rng = np.random.default_rng(500 + fs)
+    w, h = 200, 136
+    u = scenes.full_example_uniforms(w / h, np.deg2rad(75.0), 2.0, np.deg2rad(45.0), np.deg2rad(65.0), 0.0) if fs in (
+        sr.FS_FULL_EXAMPLE, sr.FS_FULL_EXAMPLE_TEXTURED) else scenes.suzanne_uniforms(w, h)
+    fb = _few_fb(P, ctx, w, h)
+    ofb = oracle_fb(w, h)
+    pipe = P.Pipeline.from_framebuffer(fb, u)
+    tex_img = scenes.checker_texture(64, 8)
+    tex = P.Texture(ctx, tex_img)
+    if fs == sr.FS_FULL_EXAMPLE_TEXTURED:
+        pipe.bind_texture(tex)
+        pipe.set_sampler(sr.FILTER_BILINEAR, sr.EDGE_CLAMP)
+    n = 8
+    verts = H.random_screen_triangles(rng, n, w, h, nk=nk, max_size=1.5 * w, margin=0.1)
+    verts[:, 8:11] = verts[:, 8:11] * 2.0 - 1.0 if nk >= 8 else verts[:, 8:11]  # normals with both signs
+    idx = np.arange(3 * n, dtype=np.uint32)
+    od = ob.OracleDraw(sr.TRIANGLE, idx)
+    od.set_vertices(verts, 1)
+    kw = dict(texture=tex_img, sampler=(sr.FILTER_BILINEAR, sr.EDGE_CLAMP, None)) if fs == sr.FS_FULL_EXAMPLE_TEXTURED else {}
+    od.fragment_run(ofb, fs, u, **kw)
+    pipe.draw_from_vertices(sr.TRIANGLE, verts, idx, 1).run(fs)
+    out = fb.download()
+    H.assert_bits_equal(out[:, 4], ofb.depth, "depth")
+    col = out[:, :4]
+    assert np.array_equal(np.isnan(col), np.isnan(ofb.color))
+    ok = np.isfinite(ofb.color) & np.isfinite(col)
+    assert np.abs(col - ofb.color)[ok].max() <= COLOR_TOL
+    assert (ofb.depth > np.float32(-3e38)).mean() > 0.02
+    for x in (pipe, tex, fb):
+        x.destroy()
