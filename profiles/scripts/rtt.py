@@ -28,7 +28,13 @@ idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
 p2 = P.Pipeline.from_framebuffer(dst, u)
 img = P.Texture(ctx, scenes.checker_texture(1024, 16))
 names = {0: "nearest", 1: "bilinear"}, {0: "clamp", 1: "wrap", 2: "border"}
-for label, bind in (("render target f32 (in place)", lambda: p2.bind_framebuffer_texture(src)), ("image rgba8 1024^2", lambda: p2.bind_texture(img))):
+# the reference's own render-to-texture source: a texture buffer, whose colour plane is re-used as the texture (texturebuffer.rs:63-66)
+tsrc = P.RenderBuffer.with_dimensions(ctx, w, h, texture_buffer=True); tsrc.clear(H.CLEAR)
+pt = P.Pipeline.from_framebuffer(tsrc, u)
+pt.render_mesh(sr.TRIANGLE, gm).run_to_fragment(vp, sr.VS_SUZANNE).run(sr.FS_SUZANNE)
+for label, bind in (("render target f32 (in place)", lambda: p2.bind_framebuffer_texture(src)),
+                    ("texture buffer f32 plane     ", lambda: p2.bind_framebuffer_texture(tsrc)),
+                    ("image rgba8 1024^2", lambda: p2.bind_texture(img))):
     bind()
     modes = [(f, e) for f in (0, 1) for e in (0, 1, 2)]
     if os.environ.get("RTT_REVERSE") == "1": modes.reverse()  # (order check: a mode's time must not depend on its position)

@@ -159,8 +159,13 @@ __device__ __forceinline__ float4 sr_texture_sample_body(const SrFsConst &c, flo
         x = min(x, lastx); y = min(y, lasty);
         const uint8_t *at = c.tex + (size_t)y * (c.tex_w * texel_bytes) + x * texel_bytes;  // (a row is below 4 GB)
         if (f32) {
-            const float *t = reinterpret_cast<const float *>(at);
-            a[0] = __ldg(t); a[1] = __ldg(t + 1); a[2] = __ldg(t + 2); a[3] = __ldg(t + 3);
+            if (c.tex_stride == 4u) {  // the colour plane of a texture buffer (what the reference samples): one 16-byte load per texel
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(at));
+                a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+            } else {
+                const float *t = reinterpret_cast<const float *>(at);
+                a[0] = __ldg(t); a[1] = __ldg(t + 1); a[2] = __ldg(t + 2); a[3] = __ldg(t + 3);
+            }
         } else {
             const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(at));
             a[0] = sr_div_exact((float)t.x, 255.0f, r255); a[1] = sr_div_exact((float)t.y, 255.0f, r255);
